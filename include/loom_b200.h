@@ -1,0 +1,228 @@
+/*
+ * loom_b200.h -- C ABI of the B200-native CrossCat inference core.
+ *
+ * This is the drop-in boundary for loom's row ("cat") / kind / hyper Gibbs hot
+ * path.  The reference (priorknowledge/loom) has no FFI; its boundary is the
+ * C++ class API (src/loom.hpp, src/cat_kernel.hpp, src/kind_kernel.hpp,
+ * src/hyper_kernel.hpp, src/product_mixture.hpp).  Every entry point below
+ * names the reference interface it replaces (file:line into /root/reference).
+ * The C++ shell in loom_b200/host/ re-hosts those classes on top of this ABI;
+ * see INTEGRATION.md for the binding a loom maintainer would add.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return
+ * 0 on success, non-zero on failure; LB_NAME(last_error)() gives the message
+ * (the C++ shell turns non-zero into LOOM_ERROR-style abort, common.hpp:52-59).
+ *
+ * The CPU oracle (oracle/loom_oracle.c, test infrastructure only) exports the
+ * same functions with the prefix lo_ by including this header with
+ * LB_NAME(x) = lo_##x, so parity tests drive both through identical calls.
+ */
+#ifndef LOOM_B200_H_
+#define LOOM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef LB_NAME
+#define LB_NAME(x) lb_##x
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Feature models (src/models.hpp:116-121).  DD16 and DD256 are one type here:
+ * dim <= 256, value stored in one byte. */
+enum {
+    LB_BB = 0,   /* BetaBernoulli        hp = {alpha, beta}                    */
+    LB_DD = 1,   /* DirichletDiscrete    aux[aux_off .. +dim) = alphas         */
+    LB_DPD = 2,  /* DirichletProcessDiscrete, dictionary-encoded to [0,dim):
+                    hp = {gamma, alpha, beta0}; aux[aux_off .. +dim) = betas   */
+    LB_GP = 3,   /* GammaPoisson         hp = {alpha, inv_beta}                */
+    LB_NICH = 4  /* NormalInverseChiSq   hp = {mu, kappa, sigmasq, nu}         */
+};
+
+typedef struct {
+    int32_t type;     /* LB_BB .. LB_NICH */
+    int32_t dim;      /* DD: number of categories (<=256); DPD: dictionary size; else 0 */
+    float hp[4];
+    int32_t aux_off;  /* offset into the aux float array (DD alphas / DPD betas) */
+} lb_feature_spec;
+
+/* Features must be sorted by type rank bb < dd < dpd < gp < nich (and dd by
+ * ascending dim): that IS loom's global feature-id order
+ * (loom/schema.py:32-72, src/product_value.hpp:586-623).
+ *
+ * Row block (columnar, feature-major), for R rows, F8 = #BB + #DD features,
+ * FW = #DPD + #GP + #NICH features:
+ *   cat8 : uint8  [F8][R]   value of BB (0/1) and DD (0..dim-1) cells
+ *   wide : uint32 [FW][R]   DPD dictionary id / GP count / NICH float bits
+ *   mask : uint32 [F][ceil(R/32)]  bit (r & 31) of word r>>5 = cell observed
+ * Row position = position in the shuffled stream (src/stream_interval.hpp),
+ * so FIFO order of loom's Assignments (src/assignments.hpp:56-74) is row order.
+ */
+
+/* Per-kind group storage, identical for upload and download (the order is the
+ * field order of ProductModel.Group, src/schema.proto:113-121, features in
+ * ascending feature id inside the kind):
+ *   counts : uint32 [G]                 clustering counts
+ *   ints   : uint32 [n_int_rows][G]     BB: heads, tails | DD/DPD: counts[dim], count_sum
+ *                                       GP: count, sum   | NICH: count
+ *   flts   : double [n_flt_rows][G]     GP: log_prod     | NICH: mean, count_times_variance
+ */
+typedef struct {
+    int32_t n_features;
+    int32_t n_groups;      /* G, including the empty groups */
+    int32_t n_int_rows;
+    int32_t n_flt_rows;
+    uint64_t sample_size;  /* rows currently assigned in this kind */
+    float py_alpha, py_d;
+} lb_kind_info;
+
+/* Hyper-prior grids (src/schema.proto:34-71; defaults loom/hyperprior.py:31-67).
+ * Each pointer may be NULL with length 0 = "do not infer this coordinate". */
+typedef struct {
+    const float *topology;   int32_t n_topology;    /* [n][2] = (alpha, d) */
+    const float *clustering; int32_t n_clustering;  /* [n][2] */
+    const float *bb_alpha;   int32_t n_bb_alpha;
+    const float *bb_beta;    int32_t n_bb_beta;
+    const float *dd_alpha;   int32_t n_dd_alpha;
+    const float *dpd_gamma;  int32_t n_dpd_gamma;
+    const float *dpd_alpha;  int32_t n_dpd_alpha;
+    const float *gp_alpha;   int32_t n_gp_alpha;
+    const float *gp_inv_beta; int32_t n_gp_inv_beta;
+    const float *nich_mu;    int32_t n_nich_mu;
+    const float *nich_kappa; int32_t n_nich_kappa;
+    const float *nich_sigmasq; int32_t n_nich_sigmasq;
+    const float *nich_nu;    int32_t n_nich_nu;
+} lb_hyper_prior;
+
+#define LB_UNASSIGNED 0xFFFFFFFFu
+/* cat-sweep action encoding: (row_position << 1) | is_remove */
+#define LB_ACTION_ADD(r)    (((uint32_t)(r)) << 1)
+#define LB_ACTION_REMOVE(r) ((((uint32_t)(r)) << 1) | 1u)
+
+typedef void *lb_handle;
+
+/* Random numbers: every draw is Philox4x32-10 keyed by the caller's 64-bit seed
+ * with counter (a_lo, a_hi, b, stream); u = (x0 >> 8) * 2^-24.  Streams:
+ *   0 cat sweep     a = action_offset + action index, b = kind id
+ *   1 block-PY      a = iteration * F + featureid
+ *   2 hyper         a = task id (hyper_kernel.cc:203-207), b = draw index
+ *   3 ephemeral kind partition   a = row, b = kind id
+ * (replaces distributions::rng_t; sampled values are only statistically
+ *  comparable with the reference, see SURVEY.md section 7 "RNG".) */
+
+const char *LB_NAME(last_error)(void);
+
+/* Engine life cycle.  One engine = one CrossCat + Assignments on one device
+ * (Loom::Loom, src/loom.cc:43-86). */
+int LB_NAME(create)(int device, lb_handle *out);
+void LB_NAME(destroy)(lb_handle h);
+
+/* CrossCat::model_load (src/cross_cat.cc:62-120) followed by
+ * CrossCat::mixture_init_unobserved (src/cross_cat.cc:50-60): installs the
+ * schema, hypers, kind structure and `empty_group_count` empty groups per kind.
+ * kind_py is [K][2] = (alpha, d); topology_py is [2].  Kinds may be
+ * featureless (the kind kernel's ephemeral kinds, src/kind_kernel.cc:159-189). */
+int LB_NAME(set_model)(lb_handle h, int32_t n_features, const lb_feature_spec *specs,
+                       const float *aux, int32_t n_aux, int32_t n_kinds,
+                       const uint32_t *featureid_to_kindid, const float *kind_py,
+                       const float *topology_py, int32_t empty_group_count);
+
+/* Replaces the unzip/parse/split stages (src/cat_pipeline.cc:63-87,
+ * ValueSplitter::split src/product_value.hpp:1071-1092): upload one columnar
+ * row block from HOST memory.  Clears all assignments. */
+int LB_NAME(set_rows)(lb_handle h, uint64_t n_rows, const uint8_t *cat8,
+                      const uint32_t *wide, const uint32_t *mask);
+
+/* CatKernel::add_row / remove_row over a list of actions, every kind
+ * (src/cat_kernel.hpp:177-299; scheduling of src/cat_pipeline.cc:103-125):
+ * exact single-site Gibbs, sequential in action order inside each kind, kinds
+ * independent.  ADD = model.add_value -> score_value -> sample -> add_value ->
+ * push global id; REMOVE = pop -> remove_value.  `kind_mask` selects kinds
+ * (NULL = all; used to shard kinds across devices).  Parity-test taps (HOST,
+ * may be NULL): debug_picks [n_actions][n_kinds] receives the packed group id
+ * chosen by each ADD / vacated by each REMOVE; debug_scores
+ * [n_actions][n_kinds][debug_stride] the score vector of every ADD. */
+int LB_NAME(cat_sweep)(lb_handle h, const uint32_t *actions, uint64_t n_actions,
+                       uint64_t seed, uint64_t action_offset, const uint8_t *kind_mask,
+                       uint32_t *debug_picks, float *debug_scores, int32_t debug_stride);
+
+/* Assignments (src/assignments.hpp): packed group id per row position for one
+ * kind, LB_UNASSIGNED where the row is not assigned. */
+int LB_NAME(get_assignments)(lb_handle h, int32_t kind, uint32_t *out_packed);
+int LB_NAME(set_assignments)(lb_handle h, int32_t kind, const uint32_t *packed);
+
+/* ProductMixture load/dump (src/product_mixture.cc:739-856) without the
+ * protobuf framing. set_groups appends the empty groups and rebuilds the
+ * cached scorers (load_step_2/3_of_3). */
+int LB_NAME(kind_info)(lb_handle h, int32_t kind, lb_kind_info *out);
+int LB_NAME(get_groups)(lb_handle h, int32_t kind, uint32_t *counts, uint32_t *ints,
+                        double *flts);
+int LB_NAME(set_groups)(lb_handle h, int32_t kind, int32_t n_nonempty_groups,
+                        const uint32_t *counts, const uint32_t *ints, const double *flts);
+
+/* ProductMixture_<true>::score_value for a batch of rows of one kind with the
+ * tables frozen (src/product_mixture.cc:421-434): out[r - row_begin][g],
+ * g < G, row stride = G.  `out` is HOST memory; pass NULL to leave the result
+ * in the engine's device scratch (bench use). */
+int LB_NAME(score_rows)(lb_handle h, int32_t kind, uint64_t row_begin, uint64_t row_end,
+                        float *out);
+
+/* ProductMixture_::add_value for rows [row_begin,row_end) with their CURRENT
+ * assignments, all kinds (kind < 0) or one kind: rebuilds/extends sufficient
+ * statistics in bulk (src/product_mixture.cc:165-184; bulk form of
+ * CrossCat::mixture_load src/cross_cat.cc:148-196).  sign = +1 add, -1 remove.
+ * Groups must already exist (packed ids < G); cached scorers are refreshed. */
+int LB_NAME(accumulate_rows)(lb_handle h, int32_t kind, uint64_t row_begin,
+                             uint64_t row_end, int32_t sign);
+
+/* CrossCat::score_data (src/cross_cat.cc:238-250). */
+int LB_NAME(score_data)(lb_handle h, double *out);
+
+/* KindProposer score phase (src/kind_proposer.cc:336-349 ->
+ * ProductMixture_::score_feature src/product_mixture.cc:611-620) after the
+ * bulk form of KindKernel::add_to_kind_proposer (src/kind_kernel.hpp:193-217):
+ * accumulates every assigned row into every kind's all-feature proposer tables
+ * and writes out_scores[f][k] = sum_g log marginal, [F][K] row-major (HOST;
+ * NULL = keep on device).  The scores are NOT yet passed through
+ * scores_to_likelihoods. */
+int LB_NAME(kind_proposer_score)(lb_handle h, float *out_scores);
+
+/* KindKernel::try_run (src/kind_kernel.cc:118-157) given proposer tables from
+ * kind_proposer_score: block Pitman-Yor sampler (src/kind_proposer.cc:269-300)
+ * then move_features (src/kind_kernel.cc:83-116).  Writes the new
+ * featureid_to_kindid and returns the number of moved features in *n_changed.
+ * Featureless kinds are kept (call set_model / add_ephemeral_kinds to manage
+ * them, src/kind_kernel.cc:208-227). */
+int LB_NAME(kind_run)(lb_handle h, int32_t iterations, uint64_t seed,
+                      uint32_t *new_featureid_to_kindid, int32_t *n_changed);
+
+/* KindKernel::init_featureless_kinds (src/kind_kernel.cc:208-227): drop
+ * featureless kinds (swap-remove, patching featureid_to_kindid) and append
+ * `count` ephemeral kinds, each with a Pitman-Yor prior partition of all
+ * assigned rows (src/kind_kernel.cc:159-189). */
+int LB_NAME(init_featureless_kinds)(lb_handle h, int32_t count, uint64_t seed);
+int LB_NAME(get_kinds)(lb_handle h, int32_t *n_kinds, uint32_t *featureid_to_kindid);
+
+/* HyperKernel::run (src/hyper_kernel.cc:195-235): grid Gibbs over topology,
+ * per-kind clustering and per-feature hyper-parameters. */
+int LB_NAME(set_hyper_prior)(lb_handle h, const lb_hyper_prior *prior);
+int LB_NAME(hyper_run)(lb_handle h, uint64_t seed);
+int LB_NAME(get_hypers)(lb_handle h, lb_feature_spec *specs, float *aux, float *kind_py,
+                        float *topology_py);
+
+/* Device timing for bench.py (CUDA events on the engine's stream; the oracle
+ * uses a monotonic clock). */
+int LB_NAME(sync)(lb_handle h);
+int LB_NAME(timer_start)(lb_handle h);
+int LB_NAME(timer_stop)(lb_handle h, float *elapsed_ms);
+/* Launch / kernel-time counters since the last reset:
+ * out[0] = kernels launched, out[1..] = per-kernel-family counts. */
+int LB_NAME(launch_count)(lb_handle h, uint64_t *out, int32_t n, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOOM_B200_H_ */

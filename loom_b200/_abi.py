@@ -1,0 +1,118 @@
+"""ctypes binding of the C ABI declared in include/loom_b200.h.
+
+`Abi(path, prefix)` binds one shared library exporting that ABI.  The product
+binds `loom_b200/csrc/libloomb200.so` with prefix ``lb_`` (see `load_cuda`);
+there is no CPU fallback: if the CUDA library is missing, `load_cuda` raises.
+The tests bind the CPU oracle (`oracle/libloom_oracle.so`, prefix ``lo_``)
+through the same class so both sides are driven by identical calls.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+LB_BB, LB_DD, LB_DPD, LB_GP, LB_NICH = range(5)
+TYPE_NAMES = {"bb": LB_BB, "dd": LB_DD, "dpd": LB_DPD, "gp": LB_GP, "nich": LB_NICH}
+UNASSIGNED = 0xFFFFFFFF
+
+
+class FeatureSpec(C.Structure):
+    _fields_ = [("type", C.c_int32), ("dim", C.c_int32), ("hp", C.c_float * 4),
+                ("aux_off", C.c_int32)]
+
+
+class KindInfo(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("n_groups", C.c_int32),
+                ("n_int_rows", C.c_int32), ("n_flt_rows", C.c_int32),
+                ("sample_size", C.c_uint64), ("py_alpha", C.c_float), ("py_d", C.c_float)]
+
+
+_HP_FIELDS = ["topology", "clustering", "bb_alpha", "bb_beta", "dd_alpha", "dpd_gamma",
+              "dpd_alpha", "gp_alpha", "gp_inv_beta", "nich_mu", "nich_kappa",
+              "nich_sigmasq", "nich_nu"]
+
+
+class HyperPrior(C.Structure):
+    _fields_ = sum(([(n, C.POINTER(C.c_float)), ("n_" + n, C.c_int32)] for n in _HP_FIELDS), [])
+
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_h = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol of include/loom_b200.h
+SIGNATURES = {
+    "last_error": (C.c_char_p, []),
+    "create": (C.c_int, [C.c_int, C.POINTER(_h)]),
+    "destroy": (None, [_h]),
+    "set_model": (C.c_int, [_h, C.c_int32, C.POINTER(FeatureSpec), _f32p, C.c_int32, C.c_int32,
+                            _u32p, _f32p, _f32p, C.c_int32]),
+    "set_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
+    "cat_sweep": (C.c_int, [_h, _u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u32p, _f32p,
+                            C.c_int32]),
+    "get_assignments": (C.c_int, [_h, C.c_int32, _u32p]),
+    "set_assignments": (C.c_int, [_h, C.c_int32, _u32p]),
+    "kind_info": (C.c_int, [_h, C.c_int32, C.POINTER(KindInfo)]),
+    "get_groups": (C.c_int, [_h, C.c_int32, _u32p, _u32p, _f64p]),
+    "set_groups": (C.c_int, [_h, C.c_int32, C.c_int32, _u32p, _u32p, _f64p]),
+    "score_rows": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, _f32p]),
+    "accumulate_rows": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32]),
+    "score_data": (C.c_int, [_h, _f64p]),
+    "kind_proposer_score": (C.c_int, [_h, _f32p]),
+    "kind_run": (C.c_int, [_h, C.c_int32, C.c_uint64, _u32p, C.POINTER(C.c_int32)]),
+    "init_featureless_kinds": (C.c_int, [_h, C.c_int32, C.c_uint64]),
+    "get_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),
+    "set_hyper_prior": (C.c_int, [_h, C.POINTER(HyperPrior)]),
+    "hyper_run": (C.c_int, [_h, C.c_uint64]),
+    "get_hypers": (C.c_int, [_h, C.POINTER(FeatureSpec), _f32p, _f32p, _f32p]),
+    "sync": (C.c_int, [_h]),
+    "timer_start": (C.c_int, [_h]),
+    "timer_stop": (C.c_int, [_h, _f32p]),
+    "launch_count": (C.c_int, [_h, _u64p, C.c_int32, C.c_int32]),
+}
+
+
+class LoomError(RuntimeError):
+    """Non-zero status from the C ABI (the reference aborts: src/common.hpp:52-59)."""
+
+
+def ptr(a, ty):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ty)
+
+
+class Abi:
+    def __init__(self, path, prefix):
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL if prefix == "lb_" else C.RTLD_LOCAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.lib, prefix + name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+    def check(self, status):
+        if status != 0:
+            msg = self.last_error()
+            raise LoomError((msg or b"?").decode(errors="replace"))
+
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_LIB = os.path.join(_REPO, "loom_b200", "csrc", "libloomb200.so")
+_cuda = None
+
+
+def load_cuda():
+    """Bind the CUDA library.  Fails loudly if it has not been built."""
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(CUDA_LIB):
+            raise LoomError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)" % CUDA_LIB)
+        _cuda = Abi(CUDA_LIB, "lb_")
+    return _cuda

@@ -1,0 +1,111 @@
+"""Oracle self-checks: the sequential cat kernel keeps its invariants, bulk and
+sequential sufficient statistics agree, and the sampled assignments pass loom's
+posterior-enumeration chi-square test (the only distributional anchor the
+reference offers: loom/test/test_posterior_enum.py)."""
+import numpy as np
+import pytest
+
+import pe_util
+from loom_b200 import Engine, sweep_actions, UNASSIGNED
+from loom_b200 import synth
+
+
+def small_mixed(rows=300, seed=5):
+    return synth.generate(rows, [("bb", 4), ("dd4", 3), ("dd16", 2), ("dpd5", 2), ("gp", 3),
+                                 ("nich", 3)], density=0.6, seed=seed)
+
+
+def test_add_remove_roundtrip(oracle_abi):
+    model, rows, _ = small_mixed()
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    e.cat_sweep(sweep_actions(rows.n_rows), seed=1)
+    for k in range(model.n_kinds):
+        info = e.kind_info(k)
+        assert info.sample_size == rows.n_rows
+        counts, ints, flts = e.get_groups(k)
+        assert counts.sum() == rows.n_rows
+        assert (counts == 0).sum() == model.empty_group_count  # A5 invariant
+        a = e.get_assignments(k)
+        assert np.array_equal(np.bincount(a, minlength=len(counts)), counts)
+    s1 = e.score_data()
+    assert np.isfinite(s1)
+    # remove everything: back to the empty state
+    e.cat_sweep(sweep_actions(rows.n_rows, add=False), seed=2)
+    for k in range(model.n_kinds):
+        counts, ints, flts = e.get_groups(k)
+        assert len(counts) == model.empty_group_count and counts.sum() == 0
+        assert not ints.any()
+        assert np.allclose(flts, 0, atol=1e-9)
+        assert (e.get_assignments(k) == UNASSIGNED).all()
+
+
+def test_duplicate_row_is_an_error(oracle_abi):
+    model, rows, _ = small_mixed(50)
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    e.cat_sweep(sweep_actions(10), seed=1)
+    with pytest.raises(Exception, match="duplicate row"):  # cat_kernel.hpp:184
+        e.cat_sweep(sweep_actions(1), seed=1)
+
+
+def test_bulk_accumulate_matches_sequential(oracle_abi):
+    model, rows, _ = small_mixed()
+    a = Engine(oracle_abi)
+    a.set_model(model)
+    a.set_rows(rows)
+    a.cat_sweep(sweep_actions(rows.n_rows), seed=3)
+    a.cat_sweep(sweep_actions(rows.n_rows, add=True, remove=True), seed=4)
+    b = Engine(oracle_abi)
+    b.set_model(model)
+    b.set_rows(rows)
+    uniqs = []
+    for k in range(model.n_kinds):
+        uniq, inv = np.unique(a.get_assignments(k), return_inverse=True)
+        uniqs.append(uniq)
+        b.set_groups(k, len(uniq))
+        b.set_assignments(k, inv.astype(np.uint32))
+    b.accumulate_rows()
+    for k in range(model.n_kinds):
+        ca, ia, fa = a.get_groups(k)
+        cb, ib, fb = b.get_groups(k)
+        u, n = uniqs[k], len(uniqs[k])
+        assert np.array_equal(ca[u], cb[:n]) and np.array_equal(ia[:, u], ib[:, :n])  # bit-exact
+        assert np.allclose(fa[:, u], fb[:, :n], rtol=1e-9, atol=1e-9)
+    assert a.score_data() == pytest.approx(b.score_data(), rel=1e-10)
+    sa, sb = a.score_rows(0), b.score_rows(0)
+    assert np.allclose(sa[:, uniqs[0]], sb[:, :len(uniqs[0])], rtol=1e-6, atol=1e-6)
+
+
+def test_score_rows_is_normalizable_predictive(oracle_abi):
+    # For a single fully-observed BB feature the two possible rows must have
+    # total predictive mass 1 once the CRP prior is marginalised.
+    model = pe_util.make_model(1, "bb")
+    table = [[1], [0], [1], [1], [0], [1]]
+    rows = pe_util.RowBlock.from_table(model, table)
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    e.cat_sweep(sweep_actions(4), seed=9)
+    s = e.score_rows(0, 4, 6).astype(np.float64)  # rows 4 (x=0) and 5 (x=1), unassigned
+    total = np.exp(s).sum()
+    assert total == pytest.approx(1.0, rel=1e-6)
+
+
+@pytest.mark.parametrize("feature_type", pe_util.FEATURE_TYPES)
+@pytest.mark.parametrize("density", pe_util.DENSITIES)
+def test_posterior_enum_cats(oracle_abi, feature_type, density):
+    """infer_cats (test_posterior_enum.py:139-160) at nose size 100, on the
+    oracle itself -- validates the restated math + control flow."""
+    rng = np.random.default_rng(123)
+    for (R, C) in pe_util.cat_dimensions(100):
+        model = pe_util.make_model(C, feature_type)
+        rows = pe_util.RowBlock.from_table(
+            model, pe_util.generate_rows(R, C, feature_type, density, rng))
+        e = Engine(oracle_abi)
+        samples = pe_util.run_posterior_enum(e, model, rows, 10 * pe_util.LATENT_SIZES[R][1],
+                                             seed=R * 100 + C)
+        gof, info = pe_util.goodness_of_fit(samples, R, C, infer_kinds=False)
+        assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
