@@ -178,7 +178,10 @@ def goodness_of_fit(samples, object_count, feature_count, infer_kinds, scores_ov
     for latent, score in samples:
         if latent in counts_dict:
             counts_dict[latent] += 1
-            assert abs(score - scores_dict[latent]) < SCORE_TOL, "inconsistent score"
+            # (the reference's own consistency assert is vacuous, :365-369; with
+            # hyper inference the score of a latent legitimately varies)
+            if scores_override is None:
+                assert abs(score - scores_dict[latent]) < SCORE_TOL, "inconsistent score"
         else:
             counts_dict[latent] = 1
             scores_dict[latent] = score
