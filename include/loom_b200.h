@@ -77,7 +77,7 @@ typedef struct {
     int32_t n_flt_rows;
     uint64_t sample_size;  /* rows currently assigned in this kind */
     float py_alpha, py_d;
-} lb_kind_info;
+} lb_kind_info_t;
 
 /* Hyper-prior grids (src/schema.proto:34-71; defaults loom/hyperprior.py:31-67).
  * Each pointer may be NULL with length 0 = "do not infer this coordinate". */
@@ -157,7 +157,7 @@ int LB_NAME(set_assignments)(lb_handle h, int32_t kind, const uint32_t *packed);
 /* ProductMixture load/dump (src/product_mixture.cc:739-856) without the
  * protobuf framing. set_groups appends the empty groups and rebuilds the
  * cached scorers (load_step_2/3_of_3). */
-int LB_NAME(kind_info)(lb_handle h, int32_t kind, lb_kind_info *out);
+int LB_NAME(kind_info)(lb_handle h, int32_t kind, lb_kind_info_t *out);
 int LB_NAME(get_groups)(lb_handle h, int32_t kind, uint32_t *counts, uint32_t *ints,
                         double *flts);
 int LB_NAME(set_groups)(lb_handle h, int32_t kind, int32_t n_nonempty_groups,

@@ -1,0 +1,776 @@
+// lb_cat.cu -- cat-kernel CUDA kernels for sm_100a:
+//   k_cat_sweep      exact sequential single-site Gibbs, one CTA per kind
+//                    (CatKernel::process_add_task / process_remove_task,
+//                     src/cat_kernel.hpp:199-299; one thread per kind in the
+//                     reference, src/cat_pipeline.cc:103-125)
+//   k_score_rows     batch ProductMixture::score_value with frozen tables
+//                    (src/product_mixture.cc:421-434)
+//   k_accumulate     bulk add_value / remove_value for given assignments
+//                    (src/product_mixture.cc:165-239)
+//   + cached-scorer refresh, table restride, id renumbering, row validation,
+//     score_data (src/cross_cat.cc:238-250).
+#include <algorithm>
+#include <cmath>
+
+#include "lb_internal.h"
+
+#define FULL 0xffffffffu
+
+// ===========================================================================
+// K3: sequential Gibbs sweep
+// ===========================================================================
+constexpr int SW_THREADS = 256;
+constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_J = 4;    // groups per lane per chunk (one chunk = 128 groups)
+constexpr int SW_PF = 4;   // row cells prefetched per thread -> nf <= 1024 per kind
+constexpr int SW_MAX_G = 4096;
+
+struct SweepSmem {
+    int G;
+    int stop;
+    int pick;
+    int was_empty;
+    uint32_t removed_global;
+    uint32_t next_global;
+    unsigned long long sample_size;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// Draw from softmax(scores[0..G)) with uniform u, CDF in index order
+// (distributions::sample_from_scores_overwrite; SURVEY.md 8c "Sampling").
+// Executed by one full warp; scores are overwritten with exp(score - max).
+__device__ __forceinline__ int warp_sample(float *scores, int G, float u, int lane) {
+    float m = -INFINITY;
+    for (int g = lane; g < G; g += 32) m = fmaxf(m, scores[g]);
+    m = warp_max(m);
+    const int per = (G + 31) >> 5;
+    const int lo = lane * per, hi = min(G, lo + per);
+    float local = 0.f;
+    for (int g = lo; g < hi; ++g) {
+        const float p = expf(scores[g] - m);
+        scores[g] = p;
+        local += p;
+    }
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const float total = __shfl_sync(FULL, incl, 31);
+    const float t = u * total;
+    const unsigned ballot = __ballot_sync(FULL, incl > t);
+    const unsigned nonzero = __ballot_sync(FULL, local > 0.f);
+    const int src = ballot ? __ffs(ballot) - 1 : 31 - __clz(nonzero);
+    int pick = lo;
+    if (lane == src) {
+        float c = incl - local;
+        int last = lo;
+        pick = -1;
+        for (int g = lo; g < hi; ++g) {
+            const float p = scores[g];
+            if (p > 0.f) last = g;
+            c += p;
+            if (c > t) { pick = g; break; }
+        }
+        if (pick < 0) pick = last;
+    }
+    return __shfl_sync(FULL, pick, src);
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const int32_t *kind_feats,
+            const float *aux, RowsDev rows, const uint32_t *actions, uint64_t n_actions,
+            uint64_t seed, uint64_t offset, int K, int n_empty, uint32_t *dbg_picks,
+            float *dbg_scores, int dbg_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int kid = kind_ids[blockIdx.x];
+    KindDev &kd = kinds[kid];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nf = kd.nf, st = kd.Gcap;
+
+    // carve shared memory
+    SweepSmem *ss = (SweepSmem *)smem_raw;
+    FeatDev *s_feat = (FeatDev *)(smem_raw + 64);
+    int32_t *s_fid = (int32_t *)(s_feat + nf);
+    uint32_t *s_raw = (uint32_t *)(s_fid + nf);          // [2][nf]
+    uint32_t *s_obs = s_raw + 2 * nf;                    // [2][nf]
+    float *s_score = (float *)(s_obs + 2 * nf);          // [st]
+    float *s_part = s_score + st;                        // [SW_WARPS][st]
+
+    uint32_t *const counts = kd.counts;
+    float *const shifted = kd.shifted;
+    uint32_t *const ints = kd.ints;
+    double *const flts = kd.flts;
+    float *const cache = kd.cache;
+    uint32_t *const assign = kd.assign;
+    const float alpha = kd.alpha, d = kd.d;
+
+    for (int j = tid; j < nf; j += SW_THREADS) {
+        const int fid = kind_feats[kd.feat_begin + j];
+        s_feat[j] = feats[fid];
+        s_fid[j] = fid;
+    }
+    if (tid == 0) {
+        ss->G = kd.G; ss->stop = 0; ss->pick = 0; ss->was_empty = 0;
+        ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
+    }
+    __syncthreads();
+
+    uint64_t i = kd.progress;
+    // load row cells of action `idx` into registers
+    uint32_t pf_raw[SW_PF], pf_obs[SW_PF];
+    auto prefetch = [&](uint64_t idx) {
+#pragma unroll
+        for (int q = 0; q < SW_PF; ++q) {
+            const int j = tid + q * SW_THREADS;
+            pf_raw[q] = 0; pf_obs[q] = 0;
+            if (j < nf && idx < n_actions) {
+                const uint64_t r = actions[idx] >> 1;
+                if (r < rows.R) {
+                    const FeatDev &f = s_feat[j];
+                    pf_obs[q] = (rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
+                    pf_raw[q] = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                          : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+                }
+            }
+        }
+    };
+    auto commit = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < SW_PF; ++q) {
+            const int j = tid + q * SW_THREADS;
+            if (j < nf) { s_raw[buf * nf + j] = pf_raw[q]; s_obs[buf * nf + j] = pf_obs[q]; }
+        }
+    };
+    prefetch(i);
+    commit(0);
+    __syncthreads();
+
+    int cur = 0;
+    int status = LB_ST_OK;
+    for (; i < n_actions; ++i) {
+        const uint32_t act = actions[i];
+        const uint64_t r = act >> 1;
+        const bool is_remove = act & 1u;
+        const int G = ss->G;
+        const uint32_t *c_raw = s_raw + cur * nf, *c_obs = s_obs + cur * nf;
+        if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
+        prefetch(i + 1);  // latency overlaps this action's work
+
+        if (!is_remove) {
+            // ---- ADD: model.add_value -> score_value -> sample -> add_value ----
+            if (G >= st || ss->next_global >= kd.g2p_cap) { status = LB_ST_NEED_GROW; break; }
+            float u = 0.f;
+            if (warp == 0) u = lb_uniform(seed, 0u, offset + i, (uint32_t)kid);
+            if (tid == 0 && assign[r] != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
+            // partial scores: warp w owns features w, w+8, ...; lanes own groups
+            for (int g0 = 0; g0 < G; g0 += 32 * SW_J) {
+                float acc[SW_J];
+#pragma unroll
+                for (int jj = 0; jj < SW_J; ++jj) acc[jj] = 0.f;
+                for (int j = warp; j < nf; j += SW_WARPS) {
+                    if (!c_obs[j]) continue;
+                    const FeatDev &f = s_feat[j];
+                    const uint32_t raw = c_raw[j];
+                    const float cc = f.type == LB_GP ? lb_log_factorial(raw) : 0.f;
+                    const uint32_t *in = ints + (size_t)f.int_row * st;
+                    const float *c = cache + (size_t)f.cache_row * st;
+#pragma unroll
+                    for (int jj = 0; jj < SW_J; ++jj) {
+                        const int g = g0 + lane + 32 * jj;
+                        if (g < G) acc[jj] += lb_score_cell(f, in + g, c + g, st, raw, cc);
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < SW_J; ++jj) {
+                    const int g = g0 + lane + 32 * jj;
+                    if (g < G) s_part[warp * st + g] = acc[jj];
+                }
+            }
+            __syncthreads();  // (1) partials visible
+            if (ss->stop) { status = ss->stop; break; }
+            if (warp == 0) {
+                // clustering.score_value: CRP prior (SURVEY.md 8c Pitman-Yor)
+                const float base = -logf((float)ss->sample_size + alpha);
+                const float sh_empty = logf((alpha + d * (float)(G - n_empty)) / (float)n_empty);
+                for (int g = lane; g < G; g += 32) {
+                    float s = (counts[g] ? shifted[g] : sh_empty) + base;
+#pragma unroll
+                    for (int w = 0; w < SW_WARPS; ++w) s += s_part[w * st + g];
+                    s_score[g] = s;
+                    if (dbg_scores && g < dbg_stride)
+                        dbg_scores[((uint64_t)i * K + kid) * dbg_stride + g] = s;
+                }
+                __syncwarp();
+                const int pick = warp_sample(s_score, G, u, lane);
+                if (lane == 0) {
+                    ss->pick = pick;
+                    ss->was_empty = counts[pick] == 0;
+                }
+            }
+            __syncthreads();  // (2) pick visible
+            const int g = ss->pick;
+            const bool add_group = ss->was_empty;
+            if (tid == 0) {
+                const uint32_t n = counts[g] + 1;
+                counts[g] = n;
+                shifted[g] = logf((float)n - d);
+                ss->sample_size += 1;
+                assign[r] = kd.p2g[g];
+                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)g;
+            }
+            for (int j = tid; j < nf; j += SW_THREADS) {
+                if (!c_obs[j]) continue;
+                const FeatDev &f = s_feat[j];
+                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g,
+                               flts + (size_t)f.flt_row * st + g,
+                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], +1);
+            }
+            if (add_group) {
+                // add_group (product_mixture.cc:178-183): append a fresh empty group
+                const int ng = G;
+                for (int row = tid; row < kd.n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
+                for (int row = tid; row < kd.n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
+                __syncthreads();
+                for (int row = tid; row < kd.n_cache_rows; row += SW_THREADS) {
+                    const FeatDev &f = s_feat[kd.cache_row_feat[row]];
+                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng,
+                                   flts + (size_t)f.flt_row * st + ng,
+                                   cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
+                }
+                if (tid == 0) {
+                    counts[ng] = 0u; shifted[ng] = 0.f;
+                    const uint32_t gid = ss->next_global;
+                    kd.p2g[ng] = gid;
+                    kd.g2p[gid] = (uint32_t)ng;
+                    ss->next_global = gid + 1;
+                    ss->G = ng + 1;
+                }
+            }
+        } else {
+            // ---- REMOVE: pop global id -> packed; mixture.remove_value ----
+            if (tid == 0) {
+                const uint32_t a = assign[r];
+                if (a == LB_UNASSIGNED) ss->stop = LB_ST_REMOVE_UNASSIGNED;
+                else {
+                    const uint32_t g = kd.g2p[a];
+                    ss->pick = (int)g;
+                    ss->removed_global = a;
+                    ss->was_empty = counts[g] == 1u;
+                }
+            }
+            __syncthreads();  // (1)
+            if (ss->stop) { status = ss->stop; break; }
+            const int g = ss->pick;
+            const bool remove_group = ss->was_empty;
+            if (tid == 0) {
+                const uint32_t n = counts[g] - 1;
+                counts[g] = n;
+                shifted[g] = n ? logf((float)n - d) : 0.f;
+                ss->sample_size -= 1;
+                assign[r] = LB_UNASSIGNED;
+                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)g;
+            }
+            for (int j = tid; j < nf; j += SW_THREADS) {
+                if (!c_obs[j]) continue;
+                const FeatDev &f = s_feat[j];
+                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g,
+                               flts + (size_t)f.flt_row * st + g,
+                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], -1);
+            }
+            if (remove_group) {
+                // remove_group (product_mixture.cc:233-238): swap-with-last
+                __syncthreads();
+                const int last = G - 1;
+                if (g != last) {
+                    for (int row = tid; row < kd.n_int_rows; row += SW_THREADS)
+                        ints[(size_t)row * st + g] = ints[(size_t)row * st + last];
+                    for (int row = tid; row < kd.n_flt_rows; row += SW_THREADS)
+                        flts[(size_t)row * st + g] = flts[(size_t)row * st + last];
+                    for (int row = tid; row < kd.n_cache_rows; row += SW_THREADS)
+                        cache[(size_t)row * st + g] = cache[(size_t)row * st + last];
+                }
+                if (tid == 0) {
+                    kd.g2p[ss->removed_global] = LB_UNASSIGNED;
+                    if (g != last) {
+                        counts[g] = counts[last];
+                        shifted[g] = shifted[last];
+                        const uint32_t gid = kd.p2g[last];
+                        kd.p2g[g] = gid;
+                        kd.g2p[gid] = (uint32_t)g;
+                    }
+                    ss->G = last;
+                }
+            }
+        }
+        commit(cur ^ 1);
+        cur ^= 1;
+        __syncthreads();  // end of action: tables, G and the next row are visible
+    }
+    if (tid == 0) {
+        kd.G = ss->G;
+        kd.sample_size = ss->sample_size;
+        kd.next_global = ss->next_global;
+        kd.status = status;
+        kd.progress = i;
+    }
+}
+
+static size_t sweep_smem_bytes(int nf, int Gcap) {
+    return 64 + (size_t)nf * (sizeof(FeatDev) + 4 + 16) + (size_t)Gcap * 4 * (1 + SW_WARPS) + 64;
+}
+
+int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
+                    uint64_t offset, uint32_t *d_picks, float *d_scores, int stride) {
+    size_t smem = 0;
+    for (int kid : kind_ids) {
+        const KindHost &k = e->kinds[kid];
+        if ((int)k.fids.size() > SW_PF * SW_THREADS)
+            return lb_fail("cat_sweep: kind %d has %zu features (limit %d)", kid, k.fids.size(), SW_PF * SW_THREADS);
+        if (k.Gcap > SW_MAX_G)
+            return lb_fail("cat_sweep: kind %d needs %d group slots (limit %d)", kid, k.Gcap, SW_MAX_G);
+        smem = std::max(smem, sweep_smem_bytes((int)k.fids.size(), k.Gcap));
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int32_t *d_ids = nullptr;
+    LB_CUDA(cudaMallocAsync((void **)&d_ids, 4 * kind_ids.size(), e->stream));
+    LB_CUDA(cudaMemcpyAsync(d_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    k_cat_sweep<<<(unsigned)kind_ids.size(), SW_THREADS, smem, e->stream>>>(
+        e->d_kinds, d_ids, e->d_feats, e->d_kind_feats, e->d_aux, rows, e->d_actions, n_actions, seed,
+        offset, (int)e->kinds.size(), e->empty_group_count, d_picks, d_scores, stride);
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaFreeAsync(d_ids, e->stream));
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_SWEEP]++;
+    return 0;
+}
+
+// ===========================================================================
+// K1: batch score_value with frozen tables.  One warp per row, lanes own
+// groups; out[(r - b) * G + g].
+// ===========================================================================
+constexpr int SC_THREADS = 256;
+constexpr int SC_J = 4;
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
+             RowsDev rows, uint64_t b, uint64_t en, int n_empty, float *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const KindDev &kd = kinds[kid];
+    const int nf = kd.nf, st = kd.Gcap, G = kd.G;
+    FeatDev *s_feat = (FeatDev *)smem_raw;
+    int32_t *s_fid = (int32_t *)(s_feat + nf);
+    for (int j = threadIdx.x; j < nf; j += SC_THREADS) {
+        const int fid = kind_feats[kd.feat_begin + j];
+        s_feat[j] = feats[fid];
+        s_fid[j] = fid;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)SC_THREADS + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * SC_THREADS) >> 5;
+    const float base = -logf((float)kd.sample_size + kd.alpha);
+    const float sh_empty = logf((kd.alpha + kd.d * (float)(G - n_empty)) / (float)n_empty);
+    for (uint64_t r = b + warp; r < en; r += n_warps) {
+        for (int g0 = 0; g0 < G; g0 += 32 * SC_J) {
+            float acc[SC_J];
+#pragma unroll
+            for (int jj = 0; jj < SC_J; ++jj) {
+                const int g = g0 + lane + 32 * jj;
+                acc[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
+            }
+            for (int j = 0; j < nf; ++j) {
+                const uint32_t obs = (rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
+                if (!obs) continue;
+                const FeatDev &f = s_feat[j];
+                const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                               : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+                const float cc = f.type == LB_GP ? lb_log_factorial(raw) : 0.f;
+                const uint32_t *in = kd.ints + (size_t)f.int_row * st;
+                const float *c = kd.cache + (size_t)f.cache_row * st;
+#pragma unroll
+                for (int jj = 0; jj < SC_J; ++jj) {
+                    const int g = g0 + lane + 32 * jj;
+                    if (g < G) acc[jj] += lb_score_cell(f, in + g, c + g, st, raw, cc);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < SC_J; ++jj) {
+                const int g = g0 + lane + 32 * jj;
+                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[jj];
+            }
+        }
+    }
+}
+
+int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
+    const KindHost &k = e->kinds[kid];
+    const size_t smem = k.fids.size() * (sizeof(FeatDev) + 4) + 16;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        LB_CUDA(cudaFuncSetAttribute(k_score_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const uint64_t n = en - b;
+    const uint64_t want = (n * 32 + SC_THREADS - 1) / SC_THREADS;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)e->n_sm * 8));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    k_score_rows<<<grid, SC_THREADS, smem, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats,
+                                                       rows, b, en, e->empty_group_count, d_out);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    return 0;
+}
+
+// ===========================================================================
+// cached scorer refresh for a whole kind: thread per (cache row, group)
+// ===========================================================================
+__global__ void k_refresh(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
+                          const float *aux) {
+    const KindDev &kd = kinds[kid];
+    const int G = kd.G, st = kd.Gcap;
+    const uint64_t total = (uint64_t)kd.n_cache_rows * G;
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total + G;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        if (idx >= total) {
+            const int g = (int)(idx - total);
+            const uint32_t n = kd.counts[g];
+            kd.shifted[g] = n ? logf((float)n - kd.d) : 0.f;
+            continue;
+        }
+        const int row = (int)(idx / G), g = (int)(idx % G);
+        const FeatDev &f = feats[kind_feats[kd.feat_begin + kd.cache_row_feat[row]]];
+        lb_refresh_row(f, aux, kd.ints + (size_t)f.int_row * st + g, kd.flts + (size_t)f.flt_row * st + g,
+                       kd.cache + (size_t)f.cache_row * st + g, st, row - f.cache_row);
+    }
+}
+
+int lb_launch_refresh(Engine *e, int kid) {
+    const KindHost &k = e->kinds[kid];
+    const uint64_t total = (uint64_t)k.n_cache_rows * k.G + k.G;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, (uint64_t)e->n_sm * 8));
+    k_refresh<<<grid, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, e->d_aux);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_REFRESH]++;
+    return 0;
+}
+int lb_refresh_kind(Engine *e, int kid) { return lb_launch_refresh(e, kid); }
+
+// ===========================================================================
+// K2: bulk accumulate with given assignments.
+// grid.y = feature slot inside the kind (slot nf = clustering counts);
+// grid.x = row chunk; thread per row.  Integer statistics are exact atomics;
+// NICH / GP float statistics are accumulated as double sums (sum x, sum x^2,
+// sum log x!) and converted back afterwards.
+// ===========================================================================
+__global__ void k_moments_to_sums(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats) {
+    const KindDev &kd = kinds[kid];
+    const int G = kd.G, st = kd.Gcap;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kd.nf * G; idx += gridDim.x * blockDim.x) {
+        const int j = idx / G, g = idx % G;
+        const FeatDev &f = feats[kind_feats[kd.feat_begin + j]];
+        if (f.type != LB_NICH) continue;
+        const double n = (double)kd.ints[(size_t)f.int_row * st + g];
+        double *fl = kd.flts + (size_t)f.flt_row * st + g;
+        const double mean = fl[0], ctv = fl[st];
+        fl[0] = n * mean;
+        fl[st] = ctv + n * mean * mean;
+    }
+}
+__global__ void k_sums_to_moments(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats) {
+    const KindDev &kd = kinds[kid];
+    const int G = kd.G, st = kd.Gcap;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kd.nf * G; idx += gridDim.x * blockDim.x) {
+        const int j = idx / G, g = idx % G;
+        const FeatDev &f = feats[kind_feats[kd.feat_begin + j]];
+        double *fl = kd.flts + (size_t)f.flt_row * st + g;
+        if (f.type == LB_NICH) {
+            const double n = (double)kd.ints[(size_t)f.int_row * st + g];
+            if (n == 0.0) { fl[0] = 0.0; fl[st] = 0.0; }
+            else {
+                const double mean = fl[0] / n;
+                fl[0] = mean;
+                fl[st] = fmax(fl[st] - n * mean * mean, 0.0);
+            }
+        } else if (f.type == LB_GP) {
+            if (kd.ints[(size_t)f.int_row * st + g] == 0u) fl[0] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_accumulate(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats, RowsDev rows,
+             uint64_t b, uint64_t en, int sign, int32_t *flag) {
+    KindDev &kd = kinds[kid];
+    const int st = kd.Gcap;
+    const int slot = blockIdx.y;
+    const uint64_t r = b + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint32_t a = LB_UNASSIGNED;
+    if (r < en) a = kd.assign[r];
+    const bool live = a != LB_UNASSIGNED;
+    const uint32_t g = live ? kd.g2p[a] : 0u;
+    if (slot == kd.nf) {  // clustering.add_value
+        if (live) {
+            const uint32_t old = atomicAdd(&kd.counts[g], (uint32_t)sign);
+            if (sign < 0 && old == 0u) *flag = 1;
+        }
+        const unsigned m = __ballot_sync(FULL, live);
+        if ((threadIdx.x & 31) == 0 && m)
+            atomicAdd((unsigned long long *)&kd.sample_size, (unsigned long long)((long long)sign * __popc(m)));
+        return;
+    }
+    if (!live) return;
+    const int fid = kind_feats[kd.feat_begin + slot];
+    if (!((rows.mask[(uint64_t)fid * rows.W + (r >> 5)] >> (r & 31)) & 1u)) return;
+    const FeatDev &f = feats[fid];
+    const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                   : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+    uint32_t *in = kd.ints + (size_t)f.int_row * st + g;
+    double *fl = kd.flts + (size_t)f.flt_row * st + g;
+    switch (f.type) {
+    case LB_BB:
+        atomicAdd(&in[raw ? 0 : st], (uint32_t)sign);
+        break;
+    case LB_DD:
+    case LB_DPD:
+        atomicAdd(&in[(size_t)raw * st], (uint32_t)sign);
+        atomicAdd(&in[(size_t)f.dim * st], (uint32_t)sign);
+        break;
+    case LB_GP:
+        atomicAdd(&in[0], (uint32_t)sign);
+        atomicAdd(&in[st], (uint32_t)(sign * (int64_t)raw));
+        atomicAdd(&fl[0], sign * lb_log_factorial_d(raw));
+        break;
+    case LB_NICH: {
+        const double x = (double)__uint_as_float(raw);
+        atomicAdd(&in[0], (uint32_t)sign);
+        atomicAdd(&fl[0], sign * x);
+        atomicAdd(&fl[st], sign * x * x);
+        break;
+    }
+    }
+}
+
+int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) {
+    const KindHost &k = e->kinds[kid];
+    const int nf = (int)k.fids.size();
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    const int items = std::max(1, nf * k.G);
+    const int g1 = std::min((items + 255) / 256, e->n_sm * 4);
+    if (nf) k_moments_to_sums<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
+    if (en > b) {
+        dim3 grid((unsigned)((en - b + 255) / 256), (unsigned)(nf + 1));
+        k_accumulate<<<grid, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, rows, b, en,
+                                                  sign, e->d_flag);
+    }
+    if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += nf ? 3 : 1; e->launches[LB_L_ACCUM] += nf ? 3 : 1;
+    return lb_launch_refresh(e, kid);
+}
+
+// ===========================================================================
+// table restride (capacity growth) and global-id renumbering
+// ===========================================================================
+template <class T>
+__global__ void k_restride(const T *src, int src_st, T *dst, int dst_st, int rows, int G) {
+    const uint64_t total = (uint64_t)rows * G;
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = idx / G, g = idx % G;
+        dst[row * dst_st + g] = src[row * src_st + g];
+    }
+}
+
+int lb_launch_restride(Engine *e, const KindHost &s, KindHost &d) {
+    auto grid = [&](uint64_t n) { return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)e->n_sm * 8)); };
+    const int G = s.G;
+    k_restride<uint32_t><<<grid(G), 256, 0, e->stream>>>(s.counts, s.Gcap, d.counts, d.Gcap, 1, G);
+    k_restride<float><<<grid(G), 256, 0, e->stream>>>(s.shifted, s.Gcap, d.shifted, d.Gcap, 1, G);
+    k_restride<uint32_t><<<grid(G), 256, 0, e->stream>>>(s.p2g, s.Gcap, d.p2g, d.Gcap, 1, G);
+    if (s.n_int_rows)
+        k_restride<uint32_t><<<grid((uint64_t)s.n_int_rows * G), 256, 0, e->stream>>>(s.ints, s.Gcap, d.ints, d.Gcap, s.n_int_rows, G);
+    if (s.n_flt_rows)
+        k_restride<double><<<grid((uint64_t)s.n_flt_rows * G), 256, 0, e->stream>>>(s.flts, s.Gcap, d.flts, d.Gcap, s.n_flt_rows, G);
+    if (s.n_cache_rows)
+        k_restride<float><<<grid((uint64_t)s.n_cache_rows * G), 256, 0, e->stream>>>(s.cache, s.Gcap, d.cache, d.Gcap, s.n_cache_rows, G);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += 6; e->launches[LB_L_MISC] += 6;
+    return 0;
+}
+
+__global__ void k_renumber_assign(uint32_t *assign, const uint32_t *g2p, uint64_t R) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = assign[r];
+        if (a != LB_UNASSIGNED) assign[r] = g2p[a];
+    }
+}
+__global__ void k_iota_ids(uint32_t *p2g, uint32_t *g2p, int G) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+        p2g[g] = (uint32_t)g;
+        g2p[g] = (uint32_t)g;
+    }
+}
+
+// global ids := packed ids (invisible outside: dumps remap ids anyway,
+// src/cross_cat.cc:212-236), so the global->packed map never outgrows its buffer
+int lb_launch_renumber(Engine *e, int kid) {
+    KindHost &k = e->kinds[kid];
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, (uint64_t)e->n_sm * 8));
+    k_renumber_assign<<<grid, 256, 0, e->stream>>>(k.assign, k.g2p, e->R);
+    LB_CUDA(cudaMemsetAsync(k.g2p, 0xFF, 4 * (size_t)k.g2p_cap, e->stream));
+    k_iota_ids<<<(k.G + 255) / 256, 256, 0, e->stream>>>(k.p2g, k.g2p, k.G);
+    LB_CUDA(cudaGetLastError());
+    k.next_global = (uint32_t)k.G;
+    e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_MISC] += 2;
+    return 0;
+}
+
+// ===========================================================================
+// row validation: observed categorical values must index inside their tables
+// ===========================================================================
+__global__ void k_validate_rows(const FeatDev *feats, int F, RowsDev rows, int32_t *flag) {
+    const int fid = blockIdx.y;
+    const FeatDev &f = feats[fid];
+    uint32_t limit;
+    if (f.type == LB_BB) limit = 2u;
+    else if (f.type == LB_DD || f.type == LB_DPD) limit = (uint32_t)f.dim;
+    else return;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows.R; r += (uint64_t)gridDim.x * blockDim.x) {
+        if (!((rows.mask[(uint64_t)fid * rows.W + (r >> 5)] >> (r & 31)) & 1u)) continue;
+        const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                       : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+        if (raw >= limit) *flag = 1;
+    }
+}
+
+int lb_launch_validate_rows(Engine *e, int *bad) {
+    LB_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    if (e->R) {
+        dim3 grid((unsigned)std::min<uint64_t>((e->R + 255) / 256, 1024), (unsigned)e->F);
+        k_validate_rows<<<grid, 256, 0, e->stream>>>(e->d_feats, e->F, rows, e->d_flag);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+    }
+    LB_CUDA(cudaMemcpyAsync(bad, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ===========================================================================
+// score_data: sum over kinds / features / groups of log marginals
+// ===========================================================================
+__device__ double lb_marginal(const FeatDev &f, const float *aux, const uint32_t *in, const double *fl, int st) {
+    switch (f.type) {
+    case LB_BB: {
+        const float h = (float)in[0], t = (float)in[st];
+        return (double)lb_lgamma_diff(f.hp[0], h) + (double)lb_lgamma_diff(f.hp[1], t) -
+               (double)lb_lgamma_diff(f.hp[0] + f.hp[1], h + t);
+    }
+    case LB_DD:
+    case LB_DPD: {
+        double s = 0;
+        for (int v = 0; v < f.dim; ++v) {
+            const uint32_t n = in[(size_t)v * st];
+            if (n) s += (double)lb_lgamma_diff(f.a_scale * aux[f.aux_off + v], (float)n);
+        }
+        return s - (double)lb_lgamma_diff(f.a_total, (float)in[(size_t)f.dim * st]);
+    }
+    case LB_GP: {
+        const double al = f.hp[0], ib = f.hp[1];
+        const double S = (double)in[st], n = (double)in[0];
+        return (double)lb_lgamma_diff(f.hp[0], (float)in[st]) + al * log(ib) - (al + S) * log(ib + n) - fl[0];
+    }
+    case LB_NICH: {
+        const double mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
+        const double n = (double)in[0], mean = fl[0], ctv = fl[st];
+        const double kn = kappa + n, nun = nu + n, dm = mu - mean;
+        const double sn = (nu * sigmasq + ctv + n * kappa * dm * dm / kn) / nun;
+        return (double)lb_lgamma_diff((float)(0.5 * nu), (float)(0.5 * n)) + 0.5 * log(kappa / kn) +
+               0.5 * nu * log(nu * sigmasq) - 0.5 * nun * log(nun * sn) - 0.5 * n * 1.1447298858494002;
+    }
+    }
+    return 0.0;
+}
+
+__device__ double block_sum(double v, double *s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    }
+    __syncthreads();
+    return t;
+}
+
+// one block per kind; out[kid] = clustering score_counts + feature marginals
+__global__ void __launch_bounds__(256)
+k_score_data(const KindDev *kinds, const FeatDev *feats, const int32_t *kind_feats, const float *aux, double *out) {
+    __shared__ double s_red[8];
+    const KindDev &kd = kinds[blockIdx.x];
+    const int G = kd.G, st = kd.Gcap;
+    double acc = 0;
+    if (kd.nf) {
+        for (int idx = threadIdx.x; idx < kd.nf * G; idx += blockDim.x) {
+            const int j = idx / G, g = idx % G;
+            const FeatDev &f = feats[kind_feats[kd.feat_begin + j]];
+            acc += lb_marginal(f, aux, kd.ints + (size_t)f.int_row * st + g, kd.flts + (size_t)f.flt_row * st + g, st);
+        }
+        // Pitman-Yor score_counts
+        const double a = kd.alpha, d = kd.d;
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            const uint32_t n = kd.counts[g];
+            if (n) acc += lgamma((double)n - d) - lgamma(1.0 - d);
+        }
+        if (threadIdx.x == 0) {
+            int m = 0;
+            double total = 0;
+            for (int g = 0; g < G; ++g) if (kd.counts[g]) { acc += log(a + d * m); ++m; total += kd.counts[g]; }
+            acc += lgamma(a) - lgamma(a + total);
+        }
+    }
+    const double t = block_sum(acc, s_red);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
+int lb_launch_score_data(Engine *e, double *out) {
+    const int K = (int)e->kinds.size();
+    LB_TRY(lb_ensure_scratch(e, 8 * (size_t)K));
+    k_score_data<<<K, 256, 0, e->stream>>>(e->d_kinds, e->d_feats, e->d_kind_feats, e->d_aux, (double *)e->d_scratch);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+    std::vector<double> part(K);
+    LB_CUDA(cudaMemcpyAsync(part.data(), e->d_scratch, 8 * (size_t)K, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    double score = 0;
+    // topology.score_counts over the feature counts of kinds that have features
+    const double a = e->topo[0], d = e->topo[1];
+    int m = 0;
+    double total = 0;
+    for (int k = 0; k < K; ++k) {
+        const size_t nf = e->kinds[k].fids.size();
+        if (!nf) continue;
+        score += part[k];
+        score += std::log(a + d * m) + std::lgamma((double)nf - d) - std::lgamma(1.0 - d);
+        ++m; total += (double)nf;
+    }
+    score += std::lgamma(a) - std::lgamma(a + total);
+    *out = score;
+    return 0;
+}

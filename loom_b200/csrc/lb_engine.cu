@@ -1,0 +1,612 @@
+// lb_engine.cu -- extern "C" entry points of include/loom_b200.h: engine life
+// cycle, model / row / group transfer, and the host logic around the kernels.
+// Product code: everything computes on the device; a missing device or a CUDA
+// failure is an error (non-zero status), never a CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "lb_internal.h"
+
+static thread_local char g_err[1024];
+
+int lb_fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+extern "C" const char *lb_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------
+template <class T> static int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    LB_CUDA(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+template <class T> static void dev_free(T *&p) {
+    if (p) cudaFree((void *)p);
+    p = nullptr;
+}
+
+int lb_ensure_scratch(Engine *e, size_t bytes) {
+    if (bytes <= e->scratch_bytes) return 0;
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    e->d_scratch = nullptr;
+    e->scratch_bytes = 0;
+    LB_CUDA(cudaMalloc(&e->d_scratch, bytes));
+    e->scratch_bytes = bytes;
+    return 0;
+}
+
+void lb_kind_release(KindHost &k) {
+    dev_free(k.counts); dev_free(k.p2g); dev_free(k.g2p); dev_free(k.ints);
+    dev_free(k.shifted); dev_free(k.cache); dev_free(k.flts); dev_free(k.cache_row_feat);
+    // assign is released separately (it survives relayouts)
+}
+
+// row offsets of a kind's features + the cache-row -> feature map
+int lb_kind_layout(Engine *e, KindHost &k, const std::vector<int> &fids) {
+    k.fids = fids;
+    k.int_off.assign(fids.size(), 0);
+    k.flt_off.assign(fids.size(), 0);
+    k.cache_off.assign(fids.size(), 0);
+    k.n_int_rows = k.n_flt_rows = k.n_cache_rows = 0;
+    std::vector<int32_t> row_feat;
+    for (size_t j = 0; j < fids.size(); ++j) {
+        const lb_feature_spec &s = e->specs[fids[j]];
+        k.int_off[j] = k.n_int_rows; k.n_int_rows += spec_int_rows(s);
+        k.flt_off[j] = k.n_flt_rows; k.n_flt_rows += spec_flt_rows(s);
+        k.cache_off[j] = k.n_cache_rows; k.n_cache_rows += spec_cache_rows(s);
+        for (int r = 0; r < spec_cache_rows(s); ++r) row_feat.push_back((int32_t)j);
+    }
+    dev_free(k.cache_row_feat);
+    LB_TRY(dev_alloc(&k.cache_row_feat, row_feat.size()));
+    if (!row_feat.empty())
+        LB_CUDA(cudaMemcpyAsync(k.cache_row_feat, row_feat.data(), 4 * row_feat.size(),
+                                cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// allocate zeroed per-group tables (layout must be set); id tracker = identity
+int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap) {
+    dev_free(k.counts); dev_free(k.p2g); dev_free(k.g2p); dev_free(k.ints);
+    dev_free(k.shifted); dev_free(k.cache); dev_free(k.flts);
+    k.G = G; k.Gcap = Gcap;
+    k.sample_size = 0;
+    k.next_global = (uint32_t)G;
+    k.g2p_cap = std::max<uint32_t>(4096u, 4u * (uint32_t)Gcap);
+    LB_TRY(dev_alloc(&k.counts, Gcap));
+    LB_TRY(dev_alloc(&k.shifted, Gcap));
+    LB_TRY(dev_alloc(&k.p2g, Gcap));
+    LB_TRY(dev_alloc(&k.g2p, k.g2p_cap));
+    LB_TRY(dev_alloc(&k.ints, (size_t)k.n_int_rows * Gcap));
+    LB_TRY(dev_alloc(&k.flts, (size_t)k.n_flt_rows * Gcap));
+    LB_TRY(dev_alloc(&k.cache, (size_t)k.n_cache_rows * Gcap));
+    LB_CUDA(cudaMemsetAsync(k.counts, 0, 4 * (size_t)Gcap, e->stream));
+    LB_CUDA(cudaMemsetAsync(k.shifted, 0, 4 * (size_t)Gcap, e->stream));
+    LB_CUDA(cudaMemsetAsync(k.ints, 0, 4 * (size_t)k.n_int_rows * Gcap + 1 - 1, e->stream));
+    LB_CUDA(cudaMemsetAsync(k.flts, 0, 8 * (size_t)k.n_flt_rows * Gcap, e->stream));
+    LB_CUDA(cudaMemsetAsync(k.cache, 0, 4 * (size_t)k.n_cache_rows * Gcap, e->stream));
+    std::vector<uint32_t> ident(std::max<uint32_t>(k.g2p_cap, (uint32_t)Gcap));
+    for (size_t i = 0; i < ident.size(); ++i) ident[i] = (uint32_t)i;
+    LB_CUDA(cudaMemcpyAsync(k.p2g, ident.data(), 4 * (size_t)Gcap, cudaMemcpyHostToDevice, e->stream));
+    for (size_t i = (size_t)G; i < ident.size(); ++i) ident[i] = LB_UNASSIGNED;
+    LB_CUDA(cudaMemcpyAsync(k.g2p, ident.data(), 4 * (size_t)k.g2p_cap, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int initial_cap(int G) {
+    int cap = 64;
+    while (cap < 2 * G) cap *= 2;
+    return cap;
+}
+
+static int alloc_assign(Engine *e, KindHost &k) {
+    dev_free(k.assign);
+    LB_TRY(dev_alloc(&k.assign, e->R));
+    LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)e->R, e->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+int lb_sync_model(Engine *e) {
+    const int K = (int)e->kinds.size();
+    if (e->model_dirty) {
+        std::vector<FeatDev> feats(e->F);
+        std::vector<int32_t> kind_feats;
+        for (int kid = 0; kid < K; ++kid) {
+            const KindHost &k = e->kinds[kid];
+            for (size_t j = 0; j < k.fids.size(); ++j) {
+                const int f = k.fids[j];
+                const lb_feature_spec &s = e->specs[f];
+                FeatDev &fd = feats[f];
+                fd.type = s.type; fd.dim = s.dim;
+                for (int i = 0; i < 4; ++i) fd.hp[i] = s.hp[i];
+                fd.aux_off = s.aux_off;
+                fd.is_wide = f >= e->F8;
+                fd.col = fd.is_wide ? f - e->F8 : f;
+                fd.int_row = k.int_off[j]; fd.flt_row = k.flt_off[j]; fd.cache_row = k.cache_off[j];
+                fd.a_total = 0.f; fd.a_scale = 1.f;
+                if (s.type == LB_DD) {
+                    double t = 0;  // same order of summation as the oracle
+                    for (int v = 0; v < s.dim; ++v) t += e->aux[s.aux_off + v];
+                    fd.a_total = (float)t;
+                } else if (s.type == LB_DPD) {
+                    fd.a_total = s.hp[1]; fd.a_scale = s.hp[1];
+                }
+                kind_feats.push_back(f);
+            }
+        }
+        dev_free(e->d_feats); dev_free(e->d_kind_feats); dev_free(e->d_aux);
+        LB_TRY(dev_alloc(&e->d_feats, e->F));
+        LB_TRY(dev_alloc(&e->d_kind_feats, kind_feats.size()));
+        LB_TRY(dev_alloc(&e->d_aux, e->aux.size()));
+        LB_CUDA(cudaMemcpyAsync(e->d_feats, feats.data(), sizeof(FeatDev) * e->F, cudaMemcpyHostToDevice, e->stream));
+        if (!kind_feats.empty())
+            LB_CUDA(cudaMemcpyAsync(e->d_kind_feats, kind_feats.data(), 4 * kind_feats.size(), cudaMemcpyHostToDevice, e->stream));
+        if (!e->aux.empty())
+            LB_CUDA(cudaMemcpyAsync(e->d_aux, e->aux.data(), 4 * e->aux.size(), cudaMemcpyHostToDevice, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+        e->model_dirty = false;
+    }
+    if (K > e->d_kinds_cap) {
+        dev_free(e->d_kinds);
+        LB_TRY(dev_alloc(&e->d_kinds, K));
+        e->d_kinds_cap = K;
+    }
+    e->h_kinds.resize(K);
+    int begin = 0;
+    for (int kid = 0; kid < K; ++kid) {
+        const KindHost &k = e->kinds[kid];
+        KindDev &d = e->h_kinds[kid];
+        d.nf = (int)k.fids.size(); d.feat_begin = begin; begin += d.nf;
+        d.alpha = k.alpha; d.d = k.d; d.G = k.G; d.Gcap = k.Gcap;
+        d.sample_size = k.sample_size;
+        d.counts = k.counts; d.shifted = k.shifted; d.p2g = k.p2g; d.g2p = k.g2p;
+        d.g2p_cap = k.g2p_cap; d.next_global = k.next_global;
+        d.ints = k.ints; d.flts = k.flts; d.cache = k.cache; d.cache_row_feat = k.cache_row_feat;
+        d.assign = k.assign;
+        d.n_int_rows = k.n_int_rows; d.n_flt_rows = k.n_flt_rows; d.n_cache_rows = k.n_cache_rows;
+        d.status = LB_ST_OK; d.progress = 0;
+    }
+    LB_CUDA(cudaMemcpyAsync(e->d_kinds, e->h_kinds.data(), sizeof(KindDev) * K, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int lb_pull_kinds(Engine *e) {
+    const int K = (int)e->kinds.size();
+    e->h_kinds.resize(K);
+    LB_CUDA(cudaMemcpyAsync(e->h_kinds.data(), e->d_kinds, sizeof(KindDev) * K, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    for (int kid = 0; kid < K; ++kid) {
+        KindHost &k = e->kinds[kid];
+        const KindDev &d = e->h_kinds[kid];
+        k.G = d.G; k.sample_size = d.sample_size; k.next_global = d.next_global;
+    }
+    return 0;
+}
+
+int lb_kind_grow(Engine *e, int kid, int new_cap) {
+    KindHost &k = e->kinds[kid];
+    KindHost nk;
+    nk.fids = k.fids; nk.int_off = k.int_off; nk.flt_off = k.flt_off; nk.cache_off = k.cache_off;
+    nk.n_int_rows = k.n_int_rows; nk.n_flt_rows = k.n_flt_rows; nk.n_cache_rows = k.n_cache_rows;
+    nk.alpha = k.alpha; nk.d = k.d;
+    LB_TRY(lb_kind_alloc(e, nk, k.G, new_cap));
+    nk.sample_size = k.sample_size;
+    // keep the id tracker (global ids stay valid): copy p2g / g2p verbatim
+    if (nk.g2p_cap < k.g2p_cap) {
+        dev_free(nk.g2p);
+        LB_TRY(dev_alloc(&nk.g2p, k.g2p_cap));
+        nk.g2p_cap = k.g2p_cap;
+    }
+    LB_CUDA(cudaMemsetAsync(nk.g2p, 0xFF, 4 * (size_t)nk.g2p_cap, e->stream));
+    LB_CUDA(cudaMemcpyAsync(nk.g2p, k.g2p, 4 * (size_t)k.g2p_cap, cudaMemcpyDeviceToDevice, e->stream));
+    nk.next_global = k.next_global;
+    LB_TRY(lb_launch_restride(e, k, nk));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    nk.assign = k.assign;
+    nk.cache_row_feat = k.cache_row_feat;
+    k.cache_row_feat = nullptr;
+    lb_kind_release(k);
+    k = nk;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int lb_create(int device, lb_handle *out) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n <= 0)
+        return lb_fail("lb_create: no CUDA device (%s); libloomb200 has no CPU fallback",
+                       cudaGetErrorString(err));
+    if (device < 0 || device >= n) return lb_fail("lb_create: bad device %d of %d", device, n);
+    LB_CUDA(cudaSetDevice(device));
+    Engine *e = new Engine();
+    e->device = device;
+    LB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    LB_CUDA(cudaEventCreate(&e->ev0));
+    LB_CUDA(cudaEventCreate(&e->ev1));
+    cudaDeviceProp prop;
+    LB_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->n_sm = prop.multiProcessorCount;
+    LB_TRY(dev_alloc(&e->d_flag, 4));
+    *out = e;
+    return 0;
+}
+
+static void clear_model(Engine *e) {
+    lb_free_proposer(e);
+    for (auto &k : e->kinds) { lb_kind_release(k); dev_free(k.assign); }
+    e->kinds.clear();
+    dev_free(e->d_feats); dev_free(e->d_kind_feats); dev_free(e->d_aux);
+    e->model_dirty = true;
+}
+
+extern "C" void lb_destroy(lb_handle h) {
+    Engine *e = (Engine *)h;
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    clear_model(e);
+    dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
+    dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_prop_scores);
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int lb_set_model(lb_handle h, int32_t F, const lb_feature_spec *specs, const float *aux,
+                            int32_t n_aux, int32_t K, const uint32_t *f2k, const float *kind_py,
+                            const float *topology_py, int32_t empty_group_count) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (F <= 0 || K <= 0) return lb_fail("set_model: need features and kinds");
+    if (empty_group_count < 1) return lb_fail("empty_group_count must be >= 1");  // cat_kernel.hpp:55
+    int F8 = 0;
+    for (int f = 0; f < F; ++f) {
+        if (f && specs[f].type < specs[f - 1].type)
+            return lb_fail("features must be sorted by type (bb<dd<dpd<gp<nich)");
+        if (specs[f].type == LB_DD && (specs[f].dim < 1 || specs[f].dim > 256))
+            return lb_fail("DD dim must be in [1,256] (product_model.cc:58-68)");
+        if (specs[f].type == LB_BB || specs[f].type == LB_DD) ++F8;
+        if (f2k[f] >= (uint32_t)K) return lb_fail("featureid_to_kindid out of range");
+    }
+    clear_model(e);
+    e->F = F; e->F8 = F8; e->FW = F - F8;
+    e->specs.assign(specs, specs + F);
+    e->aux.assign(aux, aux + n_aux);
+    e->f2k.assign(f2k, f2k + F);
+    e->topo[0] = topology_py[0]; e->topo[1] = topology_py[1];
+    e->empty_group_count = empty_group_count;
+    e->kinds.resize(K);
+    for (int kid = 0; kid < K; ++kid) {
+        KindHost &k = e->kinds[kid];
+        std::vector<int> fids;
+        for (int f = 0; f < F; ++f) if (f2k[f] == (uint32_t)kid) fids.push_back(f);
+        k.alpha = kind_py[2 * kid]; k.d = kind_py[2 * kid + 1];
+        LB_TRY(lb_kind_layout(e, k, fids));
+        LB_TRY(lb_kind_alloc(e, k, empty_group_count, initial_cap(empty_group_count)));
+        if (e->R) LB_TRY(alloc_assign(e, k));
+    }
+    e->model_dirty = true;
+    LB_TRY(lb_sync_model(e));
+    for (int kid = 0; kid < K; ++kid) LB_TRY(lb_launch_refresh(e, kid));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wide,
+                           const uint32_t *mask) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("set_rows before set_model");
+    if (R >= (1ull << 31)) return lb_fail("set_rows: at most 2^31-1 rows per block");
+    if (R != e->R || !e->d_mask) {
+        dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
+        e->R = R; e->W = (R + 31) / 32;
+        LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
+        LB_TRY(dev_alloc(&e->d_wide, (size_t)e->FW * R));
+        LB_TRY(dev_alloc(&e->d_mask, (size_t)e->F * e->W));
+        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, R)); }
+    }
+    if (e->F8) LB_CUDA(cudaMemcpyAsync(e->d_cat8, cat8, (size_t)e->F8 * R, cudaMemcpyHostToDevice, e->stream));
+    if (e->FW) LB_CUDA(cudaMemcpyAsync(e->d_wide, wide, (size_t)e->FW * R * 4, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(e->d_mask, mask, (size_t)e->F * e->W * 4, cudaMemcpyHostToDevice, e->stream));
+    for (auto &k : e->kinds) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)R, e->stream));
+    LB_TRY(lb_sync_model(e));
+    int bad = 0;
+    LB_TRY(lb_launch_validate_rows(e, &bad));
+    if (bad) return lb_fail("set_rows: an observed categorical value is out of range for its feature");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, uint64_t seed,
+                            uint64_t offset, const uint8_t *kind_mask, uint32_t *debug_picks,
+                            float *debug_scores, int32_t stride) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->R) return lb_fail("cat_sweep before set_rows");
+    const int K = (int)e->kinds.size();
+    if (n == 0) return 0;
+    if (n > e->actions_cap) {
+        dev_free(e->d_actions);
+        LB_TRY(dev_alloc(&e->d_actions, n));
+        e->actions_cap = n;
+    }
+    LB_CUDA(cudaMemcpyAsync(e->d_actions, actions, 4 * n, cudaMemcpyHostToDevice, e->stream));
+    uint32_t *d_picks = nullptr;
+    float *d_scores = nullptr;
+    if (debug_picks || debug_scores) {
+        const size_t pb = 4 * n * K, sb = debug_scores ? 4 * n * K * (size_t)stride : 0;
+        LB_TRY(lb_ensure_scratch(e, pb + sb + 256));
+        d_picks = (uint32_t *)e->d_scratch;
+        LB_CUDA(cudaMemsetAsync(d_picks, 0xFF, pb, e->stream));
+        if (debug_scores) {
+            d_scores = (float *)((char *)e->d_scratch + ((pb + 255) / 256) * 256);
+            LB_CUDA(cudaMemsetAsync(d_scores, 0xFF, sb, e->stream));  // NaN pattern
+        }
+    }
+    std::vector<int> active;
+    for (int kid = 0; kid < K; ++kid)
+        if (!kind_mask || kind_mask[kid]) active.push_back(kid);
+    LB_TRY(lb_sync_model(e));
+    std::vector<uint64_t> progress(K, 0);
+    for (int round = 0; !active.empty(); ++round) {
+        if (round > 64) return lb_fail("cat_sweep: no progress after repeated table growth");
+        // resume each kind where it stopped
+        for (int kid : active) e->h_kinds[kid].progress = progress[kid];
+        LB_CUDA(cudaMemcpyAsync(e->d_kinds, e->h_kinds.data(), sizeof(KindDev) * K, cudaMemcpyHostToDevice, e->stream));
+        LB_TRY(lb_launch_sweep(e, active, n, seed, offset, d_picks, d_scores, stride));
+        LB_TRY(lb_pull_kinds(e));
+        std::vector<int> again;
+        for (int kid : active) {
+            const KindDev &d = e->h_kinds[kid];
+            progress[kid] = d.progress;
+            switch (d.status) {
+            case LB_ST_OK: break;
+            case LB_ST_NEED_GROW: again.push_back(kid); break;
+            case LB_ST_DUPLICATE_ROW:
+                return lb_fail("duplicate row: %u (kind %d)", actions[d.progress] >> 1, kid);
+            case LB_ST_REMOVE_UNASSIGNED:
+                return lb_fail("remove of unassigned row %u (kind %d)", actions[d.progress] >> 1, kid);
+            default:
+                return lb_fail("action %llu: row out of range", (unsigned long long)d.progress);
+            }
+        }
+        for (int kid : again) {
+            KindHost &k = e->kinds[kid];
+            if (k.G + 1 > k.Gcap) LB_TRY(lb_kind_grow(e, kid, 2 * k.Gcap));
+            if (k.next_global + 1 > k.g2p_cap) LB_TRY(lb_launch_renumber(e, kid));
+        }
+        if (!again.empty()) LB_TRY(lb_sync_model(e));
+        active.swap(again);
+    }
+    if (debug_picks)
+        LB_CUDA(cudaMemcpyAsync(debug_picks, d_picks, 4 * n * K, cudaMemcpyDeviceToHost, e->stream));
+    if (debug_scores)
+        LB_CUDA(cudaMemcpyAsync(debug_scores, d_scores, 4 * n * K * (size_t)stride, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void k_assign_to_packed(const uint32_t *assign, const uint32_t *g2p, uint32_t *out, uint64_t R) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = assign[r];
+        out[r] = a == LB_UNASSIGNED ? LB_UNASSIGNED : g2p[a];
+    }
+}
+__global__ void k_packed_to_assign(const uint32_t *packed, const uint32_t *p2g, uint32_t *assign, uint64_t R,
+                                   uint32_t G, int32_t *flag) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = packed[r];
+        if (p != LB_UNASSIGNED && p >= G) { *flag = 1; assign[r] = LB_UNASSIGNED; }
+        else assign[r] = p == LB_UNASSIGNED ? LB_UNASSIGNED : p2g[p];
+    }
+}
+
+static int grid_for(uint64_t n, int threads, int n_sm) {
+    uint64_t b = (n + threads - 1) / threads;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(b, (uint64_t)n_sm * 8));
+}
+
+extern "C" int lb_get_assignments(lb_handle h, int32_t kind, uint32_t *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (!e->R) return 0;
+    KindHost &k = e->kinds[kind];
+    LB_TRY(lb_ensure_scratch(e, 4 * e->R));
+    k_assign_to_packed<<<grid_for(e->R, 256, e->n_sm), 256, 0, e->stream>>>(k.assign, k.g2p, (uint32_t *)e->d_scratch, e->R);
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+    LB_CUDA(cudaMemcpyAsync(out, e->d_scratch, 4 * e->R, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int lb_set_assignments(lb_handle h, int32_t kind, const uint32_t *packed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (!e->R) return 0;
+    KindHost &k = e->kinds[kind];
+    LB_TRY(lb_ensure_scratch(e, 4 * e->R));
+    LB_CUDA(cudaMemcpyAsync(e->d_scratch, packed, 4 * e->R, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    k_packed_to_assign<<<grid_for(e->R, 256, e->n_sm), 256, 0, e->stream>>>((uint32_t *)e->d_scratch, k.p2g, k.assign, e->R, (uint32_t)k.G, e->d_flag);
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+    int flag = 0;
+    LB_CUDA(cudaMemcpyAsync(&flag, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (flag) return lb_fail("set_assignments: group id >= G=%d", k.G);
+    return 0;
+}
+
+extern "C" int lb_kind_info(lb_handle h, int32_t kind, lb_kind_info_t *out) {
+    Engine *e = (Engine *)h;
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    const KindHost &k = e->kinds[kind];
+    out->n_features = (int)k.fids.size(); out->n_groups = k.G;
+    out->n_int_rows = k.n_int_rows; out->n_flt_rows = k.n_flt_rows;
+    out->sample_size = k.sample_size; out->py_alpha = k.alpha; out->py_d = k.d;
+    return 0;
+}
+
+extern "C" int lb_get_groups(lb_handle h, int32_t kind, uint32_t *counts, uint32_t *ints, double *flts) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    const KindHost &k = e->kinds[kind];
+    const size_t G = k.G, cap = k.Gcap;
+    if (counts) LB_CUDA(cudaMemcpyAsync(counts, k.counts, 4 * G, cudaMemcpyDeviceToHost, e->stream));
+    if (ints && k.n_int_rows)
+        LB_CUDA(cudaMemcpy2DAsync(ints, 4 * G, k.ints, 4 * cap, 4 * G, k.n_int_rows, cudaMemcpyDeviceToHost, e->stream));
+    if (flts && k.n_flt_rows)
+        LB_CUDA(cudaMemcpy2DAsync(flts, 8 * G, k.flts, 8 * cap, 8 * G, k.n_flt_rows, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int lb_set_groups(lb_handle h, int32_t kind, int32_t n, const uint32_t *counts,
+                             const uint32_t *ints, const double *flts) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (n < 0) return lb_fail("set_groups: negative group count");
+    KindHost &k = e->kinds[kind];
+    const int G = n + e->empty_group_count;
+    LB_TRY(lb_kind_alloc(e, k, G, initial_cap(G)));
+    const size_t cap = k.Gcap;
+    uint64_t total = 0;
+    if (counts && n) {
+        for (int g = 0; g < n; ++g) total += counts[g];
+        LB_CUDA(cudaMemcpyAsync(k.counts, counts, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    }
+    k.sample_size = total;
+    if (ints && n && k.n_int_rows) {
+        // count_sum rows are derived: recompute them on the host copy
+        std::vector<uint32_t> tmp(ints, ints + (size_t)k.n_int_rows * n);
+        for (size_t j = 0; j < k.fids.size(); ++j) {
+            const lb_feature_spec &s = e->specs[k.fids[j]];
+            if (s.type != LB_DD && s.type != LB_DPD) continue;
+            for (int g = 0; g < n; ++g) {
+                uint32_t t = 0;
+                for (int v = 0; v < s.dim; ++v) t += tmp[(size_t)(k.int_off[j] + v) * n + g];
+                tmp[(size_t)(k.int_off[j] + s.dim) * n + g] = t;
+            }
+        }
+        LB_CUDA(cudaMemcpy2DAsync(k.ints, 4 * cap, tmp.data(), 4 * (size_t)n, 4 * (size_t)n, k.n_int_rows, cudaMemcpyHostToDevice, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if (flts && n && k.n_flt_rows)
+        LB_CUDA(cudaMemcpy2DAsync(k.flts, 8 * cap, flts, 8 * (size_t)n, 8 * (size_t)n, k.n_flt_rows, cudaMemcpyHostToDevice, e->stream));
+    if (e->R) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)e->R, e->stream));
+    LB_TRY(lb_sync_model(e));
+    LB_TRY(lb_launch_refresh(e, kind));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int lb_score_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (b > en || en > e->R) return lb_fail("bad row range");
+    if (b == en) return 0;
+    const KindHost &k = e->kinds[kind];
+    const size_t bytes = (size_t)(en - b) * k.G * 4;
+    LB_TRY(lb_ensure_scratch(e, bytes));
+    LB_TRY(lb_sync_model(e));
+    LB_TRY(lb_launch_score_rows(e, kind, b, en, (float *)e->d_scratch));
+    if (out) {
+        LB_CUDA(cudaMemcpyAsync(out, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+extern "C" int lb_accumulate_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, int32_t sign) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (b > en || en > e->R) return lb_fail("bad row range");
+    if (sign != 1 && sign != -1) return lb_fail("sign must be +1 or -1");
+    LB_TRY(lb_sync_model(e));
+    LB_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    for (int kid = 0; kid < (int)e->kinds.size(); ++kid) {
+        if (kind >= 0 && kid != kind) continue;
+        LB_TRY(lb_launch_accumulate(e, kid, b, en, sign));
+    }
+    int flag = 0;
+    LB_CUDA(cudaMemcpyAsync(&flag, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+    LB_TRY(lb_pull_kinds(e));
+    if (flag) return lb_fail("accumulate_rows: removal from an empty group");
+    return 0;
+}
+
+extern "C" int lb_score_data(lb_handle h, double *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    LB_TRY(lb_sync_model(e));
+    return lb_launch_score_data(e, out);
+}
+
+extern "C" int lb_get_kinds(lb_handle h, int32_t *n_kinds, uint32_t *f2k) {
+    Engine *e = (Engine *)h;
+    if (n_kinds) *n_kinds = (int)e->kinds.size();
+    if (f2k) memcpy(f2k, e->f2k.data(), 4 * (size_t)e->F);
+    return 0;
+}
+
+extern "C" int lb_get_hypers(lb_handle h, lb_feature_spec *specs, float *aux, float *kind_py,
+                             float *topology_py) {
+    Engine *e = (Engine *)h;
+    if (specs) memcpy(specs, e->specs.data(), sizeof(lb_feature_spec) * e->F);
+    if (aux && !e->aux.empty()) memcpy(aux, e->aux.data(), 4 * e->aux.size());
+    if (kind_py)
+        for (size_t k = 0; k < e->kinds.size(); ++k) {
+            kind_py[2 * k] = e->kinds[k].alpha;
+            kind_py[2 * k + 1] = e->kinds[k].d;
+        }
+    if (topology_py) { topology_py[0] = e->topo[0]; topology_py[1] = e->topo[1]; }
+    return 0;
+}
+
+// ---- timing / counters ------------------------------------------------------
+extern "C" int lb_sync(lb_handle h) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+extern "C" int lb_timer_start(lb_handle h) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    LB_CUDA(cudaEventRecord(e->ev0, e->stream));
+    return 0;
+}
+extern "C" int lb_timer_stop(lb_handle h, float *ms) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    LB_CUDA(cudaEventRecord(e->ev1, e->stream));
+    LB_CUDA(cudaEventSynchronize(e->ev1));
+    LB_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return 0;
+}
+extern "C" int lb_launch_count(lb_handle h, uint64_t *out, int32_t n, int32_t reset) {
+    Engine *e = (Engine *)h;
+    for (int i = 0; i < n; ++i) out[i] = i < 8 ? e->launches[i] : 0;
+    if (reset) for (int i = 0; i < 8; ++i) e->launches[i] = 0;
+    return 0;
+}

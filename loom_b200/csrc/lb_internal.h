@@ -1,0 +1,134 @@
+// lb_internal.h -- host-side engine state of libloomb200.so.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "lb_common.cuh"
+
+struct KindHost {
+    std::vector<int> fids;  // global feature ids, ascending
+    float alpha = 2.f, d = 0.1f;
+    int G = 0, Gcap = 0;
+    uint64_t sample_size = 0;
+    uint32_t next_global = 0, g2p_cap = 0;
+    int n_int_rows = 0, n_flt_rows = 0, n_cache_rows = 0;
+    std::vector<int> int_off, flt_off, cache_off;  // per kind-local feature
+    uint32_t *counts = nullptr, *p2g = nullptr, *g2p = nullptr, *ints = nullptr, *assign = nullptr;
+    float *shifted = nullptr, *cache = nullptr;
+    double *flts = nullptr;
+    int32_t *cache_row_feat = nullptr;
+};
+
+struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind)
+    int G = 0;
+    uint32_t *ints = nullptr;  // [prop_int_rows][G]
+    double *flts = nullptr;    // [prop_flt_rows][G]
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n_sm = 148;
+
+    int F = 0, F8 = 0, FW = 0;
+    std::vector<lb_feature_spec> specs;
+    std::vector<float> aux;
+    std::vector<uint32_t> f2k;
+    float topo[2] = {2.f, 0.1f};
+    int empty_group_count = 1;
+    std::vector<KindHost> kinds;
+
+    // device mirrors of the model
+    FeatDev *d_feats = nullptr;    // [F] global feature order
+    int32_t *d_kind_feats = nullptr;  // kind-major list of global feature ids
+    float *d_aux = nullptr;
+    KindDev *d_kinds = nullptr;
+    int d_kinds_cap = 0;
+    std::vector<KindDev> h_kinds;
+    bool model_dirty = true;
+
+    // rows
+    uint64_t R = 0, W = 0;
+    uint8_t *d_cat8 = nullptr;
+    uint32_t *d_wide = nullptr, *d_mask = nullptr;
+
+    // scratch
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    uint32_t *d_actions = nullptr;
+    size_t actions_cap = 0;
+    int32_t *d_flag = nullptr;
+
+    // hyper prior
+    std::vector<float> hp[13];
+
+    // kind proposer
+    std::vector<ProposerKind> prop;
+    std::vector<int> prop_int_off, prop_flt_off;
+    int prop_int_rows = 0, prop_flt_rows = 0;
+    std::vector<float> prop_scores;  // [F][K]
+    float *d_prop_scores = nullptr;
+
+    uint64_t launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+// launch-family indices for launch_count
+enum { LB_L_TOTAL = 0, LB_L_SWEEP = 1, LB_L_SCORE = 2, LB_L_ACCUM = 3, LB_L_REFRESH = 4,
+       LB_L_KIND = 5, LB_L_HYPER = 6, LB_L_MISC = 7 };
+
+int lb_fail(const char *fmt, ...);
+#define LB_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t err__ = (expr);                                                     \
+        if (err__ != cudaSuccess)                                                       \
+            return lb_fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),   \
+                           __FILE__, __LINE__);                                         \
+    } while (0)
+#define LB_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+inline int spec_int_rows(const lb_feature_spec &s) {
+    switch (s.type) {
+    case LB_BB: return 2;
+    case LB_DD: case LB_DPD: return s.dim + 1;
+    case LB_GP: return 2;
+    case LB_NICH: return 1;
+    }
+    return 0;
+}
+inline int spec_flt_rows(const lb_feature_spec &s) {
+    return s.type == LB_GP ? 1 : (s.type == LB_NICH ? 2 : 0);
+}
+inline int spec_cache_rows(const lb_feature_spec &s) {
+    switch (s.type) {
+    case LB_BB: return 2;
+    case LB_DD: case LB_DPD: return s.dim + 1;
+    case LB_GP: return 2;
+    case LB_NICH: return 4;
+    }
+    return 0;
+}
+
+// engine helpers (lb_engine.cu)
+int lb_sync_model(Engine *e);                 // upload FeatDev / KindDev if dirty
+int lb_pull_kinds(Engine *e);                 // KindDev -> KindHost dynamic fields
+int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap);
+void lb_kind_release(KindHost &k);
+int lb_kind_layout(Engine *e, KindHost &k, const std::vector<int> &fids);
+int lb_kind_grow(Engine *e, int kid, int new_cap);
+int lb_refresh_kind(Engine *e, int kid);      // rebuild all cached scorers of a kind
+int lb_ensure_scratch(Engine *e, size_t bytes);
+
+// kernels (lb_cat.cu)
+int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
+                    uint64_t offset, uint32_t *d_picks, float *d_scores, int stride);
+int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
+int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
+int lb_launch_refresh(Engine *e, int kid);
+int lb_launch_restride(Engine *e, const KindHost &src, KindHost &dst);
+int lb_launch_renumber(Engine *e, int kid);
+int lb_launch_validate_rows(Engine *e, int *bad);
+int lb_launch_score_data(Engine *e, double *out);
+
+// structure kernels (lb_struct.cu)
+void lb_free_proposer(Engine *e);

@@ -521,7 +521,7 @@ int lo_set_assignments(lb_handle h, int32_t kind, const uint32_t *packed) {
     return 0;
 }
 
-int lo_kind_info(lb_handle h, int32_t kind, lb_kind_info *out) {
+int lo_kind_info(lb_handle h, int32_t kind, lb_kind_info_t *out) {
     engine_t *e = h;
     if (kind < 0 || kind >= e->K) return lo_fail("bad kind %d", kind);
     const kind_t *k = &e->kinds[kind];
