@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- cat-kernel cells/sec on BASELINE.json configs[1] (C2).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload "C2"): synthetic 100k rows x 100 mixed features
+(25 BB / 25 DD-256 / 25 GP / 25 NICH), density 0.5, fixed structure (7 kinds),
+cat kernel only.  One STEP is one self-contained pass of the cat kernel over the
+whole row block, in loom's action semantics (src/cat_kernel.hpp:177-299):
+    ADD every row (greedy pass, Loom::infer_single_pass)          R adds
+    REMOVE+ADD every row (one extra-pass refresh, loom.cc:502-505) R removes + R adds
+    REMOVE every row (drain; returns the mixtures to empty)        R removes
+so every step starts from the same empty state and does identical work.  A
+"cell" is one observed (row, feature) value consumed by one cat-kernel action
+(SURVEY.md 8d): a step consumes 4 x (#observed cells).
+
+value   = cells/s with the row block already resident in HBM (CUDA events).
+e2e     = the same step through the C ABI from HOST buffers: the row block is
+          re-uploaded from pinned host memory and the assignments of every kind
+          are read back inside the timed region.
+roofline= the dominant kernel (k_cat_sweep): algorithmic bytes per launch
+          (in + 4K read + 4K written per row-action) / its CUDA-event
+          time, against the measured HBM copy bandwidth.  The exact sequential
+          Gibbs chain is latency-bound (one CTA per kind); roofline_aux carries the
+          batch kernels (score_rows K1, accumulate_rows K2) that ARE HBM-bound.
+N > 1  : the sequential chain does not shard (kinds already run concurrently on
+          one GPU), so each rank runs one independent replica -- loom's own
+          per-sample parallelism (loom/tasks.py:192) -- "scaling": "weak".
+--impl reference times the restated reference (oracle/, float64 C, OpenMP one
+thread per kind like src/cat_pipeline.cc:103-125) on the host cores, on a bounded
+row sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "cat_kernel_cells_per_sec"
+UNIT = "cells/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_workload(name, rows):
+    from loom_b200 import synth
+    from loom_b200.engine import Model, RowBlock
+    cfg = dict(synth.CONFIGS[name])
+    if rows:
+        cfg["rows"] = rows
+    cache = os.path.join(tempfile.gettempdir(), "loom_b200_%s_%d_%d.npz" % (name, cfg["rows"], cfg["seed"]))
+    feats = synth.make_features(cfg["types"])
+    if os.path.exists(cache):
+        z = np.load(cache)
+        model = Model(feats, z["f2k"], kind_py=[synth.CLUSTERING] * (int(z["f2k"].max()) + 1),
+                      topology=synth.CLUSTERING)
+        return model, RowBlock(cfg["rows"], z["cat8"], z["wide"], z["mask"])
+    model, rows_, _ = synth.generate(**cfg)
+    try:
+        np.savez(cache, f2k=model.f2k, cat8=rows_.cat8, wide=rows_.wide, mask=rows_.mask)
+    except OSError:
+        pass
+    return model, rows_
+
+
+def step_actions(R):
+    from loom_b200 import sweep_actions
+    first = np.concatenate([sweep_actions(R), sweep_actions(R, add=True, remove=True)])
+    drain = sweep_actions(R, add=False)
+    return first, drain
+
+
+def algorithmic_bytes_per_action(model, rows):
+    """per row-action, input cells (BB 1 B, DD 1 B, DPD/GP/NICH 4 B
+    per observed cell) + 1 bit/feature mask + 8 B row id, + 4 B/kind read and
+    4 B/kind written (assignment ids)."""
+    obs = rows.observed()
+    width = np.array([1 if f["type"] in ("bb", "dd") else 4 for f in model.features])
+    cell_bytes = float((obs * width[:, None]).sum()) / rows.n_rows
+    return cell_bytes + model.n_features / 8.0 + 8.0 + 8.0 * model.n_kinds
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def pin(arr):
+    """cudaHostRegister the numpy buffer so the H2D copies of the e2e leg are from pinned memory."""
+    try:
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaHostRegister.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint]
+        if arr.nbytes:
+            return rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0) == 0
+    except OSError:
+        pass
+    return False
+
+
+def run_reference_arm(args, model, rows, n_cells_full):
+    """Restated reference on host cores: same step, bounded row sample."""
+    from loom_b200 import _abi
+    from loom_b200.engine import Engine, RowBlock
+    import __graft_entry__
+    path = os.path.join(REPO, "oracle", "libloom_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(REPO, "oracle")], stdout=subprocess.DEVNULL)
+    oracle = _abi.Abi(path, "lo_")
+    R = min(rows.n_rows, args.ref_rows)
+    W = (R + 31) // 32
+    sub = RowBlock(R, rows.cat8[:, :R], rows.wide[:, :R], rows.mask[:, :W])
+    if R % 32:
+        sub.mask[:, -1] &= np.uint32((1 << (R % 32)) - 1)
+    cells = 4 * sub.n_cells()
+    e = Engine(oracle)
+    e.set_model(model)
+    e.set_rows(sub)
+    first, drain = step_actions(R)
+    cores = os.cpu_count() or 1
+    threads = min(cores, model.n_kinds)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        e.cat_sweep(first, seed=100 + it)
+        e.cat_sweep(drain, seed=100 + it)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = cells / (ms * 1e-3)
+    return {
+        "value": value, "ms_per_step": ms,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "host_cores": cores,
+                         "sample": "first %d of %d rows of C2, same 4-pass step, float64 C oracle "
+                                   "(restated reference, distributions 2.0.28 math in exact libm), "
+                                   "OpenMP one thread per kind" % (R, rows.n_rows)},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--rows", type=int, default=0, help="override the row count (parity runs only)")
+    ap.add_argument("--ref-rows", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": args.workload, "rows": None, "features": None, "kinds": None,
+              "step": "ADD all + REMOVE/ADD all + REMOVE all (4 cat-kernel actions per row)",
+              "l2_policy": "tables and row block (26 MB) are re-streamed every pass; every step rewrites "
+                           "all per-kind tables; inputs are not larger than L2 -- the kernel is latency-bound, "
+                           "not bandwidth-bound (see DESIGN.md)",
+              "parallelism": "replicas x%d" % world if world > 1 else "single chain, one CTA per kind"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        model, rows = load_workload(args.workload, args.rows)
+        config.update(rows=rows.n_rows, features=model.n_features, kinds=model.n_kinds)
+        res = run_reference_arm(args, model, rows, 4 * rows.n_cells())
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": res["cpu_baseline"],
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    from loom_b200 import _abi
+    from loom_b200.engine import Engine
+    cuda = _abi.load_cuda()  # fails loudly if the CUDA library is missing
+    model, rows = load_workload(args.workload, args.rows)
+    R = rows.n_rows
+    config.update(rows=R, features=model.n_features, kinds=model.n_kinds)
+    n_obs = rows.n_cells()
+    cells_per_step = 4 * n_obs
+    first, drain = step_actions(R)
+
+    e = Engine(cuda, device=local_rank)
+    e.set_model(model)
+    e.set_rows(rows)
+    for a in (rows.cat8, rows.wide, rows.mask):
+        pin(a)
+
+    def barrier():
+        e.sync()
+        if dist:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_step(it):
+        e.cat_sweep(first, seed=1000 * rank + it)
+        e.cat_sweep(drain, seed=1000 * rank + it)
+
+    # ---- device-resident value ----
+    for it in range(args.warmup):
+        device_step(it)
+    barrier()
+    e.launch_count(reset=True)
+    e.kernel_ms(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e.timer_start()
+    for it in range(args.steps):
+        device_step(args.warmup + it)
+    total_ms = e.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = e.launch_count()
+    kms = e.kernel_ms()
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * cells_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers in, assignments out, inside the timed region ----
+    def e2e_step(it):
+        e.set_rows(rows)                      # H2D of the whole row block
+        e.cat_sweep(first, seed=5000 * rank + it)
+        for k in range(model.n_kinds):
+            e.get_assignments(k)              # D2H of every kind's assignment column
+        e.cat_sweep(drain, seed=5000 * rank + it)
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    e.timer_start()
+    for it in range(args.steps):
+        e2e_step(1 + it)
+    e2e_ms = e.timer_stop()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall)) / args.steps
+    e2e_value = world * cells_per_step / (e2e_ms * 1e-3)
+    h2d = int(rows.cat8.nbytes + rows.wide.nbytes + rows.mask.nbytes + 4 * (len(first) + len(drain)))
+    d2h = int(4 * R * model.n_kinds)
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    ppath = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        peaks = json.load(open(ppath))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    n_sweep = int(launches[1])
+    sweep_ms = float(kms[1])
+    bytes_per_action = algorithmic_bytes_per_action(model, rows)
+    actions_per_step = len(first) + len(drain)
+    alg_bytes_per_launch = bytes_per_action * actions_per_step * args.steps / max(n_sweep, 1)
+    avg_launch_ms = sweep_ms / max(n_sweep, 1)
+    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
+                "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
+                "note": "exact sequential Gibbs: latency-bound dependent chain, one CTA per kind"}
+
+    # ---- auxiliary: the HBM-bound batch kernels on the same workload ----
+    aux = {}
+    try:
+        e.set_rows(rows)
+        e.cat_sweep(first[:R], seed=9)       # populate groups (ADD pass)
+        # K1 batch score_value, scores materialised, largest kind
+        big = int(np.argmax([len(model.kind_features(k)) for k in range(model.n_kinds)]))
+        G = e.kind_info(big).n_groups
+        for _ in range(3):
+            e.score_rows(big, fetch=False)
+        e.sync()
+        e.timer_start()
+        reps = 10
+        for _ in range(reps):
+            e.score_rows(big, fetch=False)
+        ms = e.timer_stop() / reps
+        kf = model.kind_features(big)
+        obs = rows.observed()[kf]
+        width = np.array([1 if model.features[f]["type"] in ("bb", "dd") else 4 for f in kf])
+        in_bytes = float((obs * width[:, None]).sum()) + R * len(kf) / 8.0
+        out_bytes = 4.0 * G * R
+        gbs = (in_bytes + out_bytes) / (ms * 1e-3) / 1e9
+        aux["k1_score_rows"] = {"kind": big, "features": len(kf), "groups": G, "ms": ms,
+                                "cells_per_s": float(obs.sum()) / (ms * 1e-3), "achieved": gbs,
+                                "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bound": "hbm"}
+        # K2 bulk accumulate of all kinds with the current assignments (remove then add back)
+        e.sync()
+        e.timer_start()
+        e.accumulate_rows(sign=-1)
+        e.accumulate_rows(sign=+1)
+        ms2 = e.timer_stop() / 2
+        in_all = bytes_per_action * R
+        aux["k2_accumulate_rows"] = {"ms": ms2, "cells_per_s": n_obs / (ms2 * 1e-3),
+                                     "achieved": in_all / (ms2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": in_all / (ms2 * 1e-3) / 1e9 / peak, "bound": "hbm"}
+        e.cat_sweep(drain, seed=9)
+    except Exception as exc:  # the auxiliary numbers never mask the headline
+        aux["error"] = str(exc)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches[0]),
+            "roofline": roofline, "roofline_aux": aux, "clocks": clocks,
+            "rates": {"cells_per_step": cells_per_step, "observed_cells": n_obs,
+                      "row_actions_per_s": world * actions_per_step / (ms_per_step * 1e-3)}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref_args = argparse.Namespace(**vars(args))
+        ref_args.steps, ref_args.warmup = 2, 1
+        try:
+            line["cpu_baseline"] = run_reference_arm(ref_args, model, rows, cells_per_step)["cpu_baseline"]
+        except Exception as exc:
+            line["cpu_baseline"] = {"error": str(exc)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -221,6 +221,9 @@ int LB_NAME(timer_stop)(lb_handle h, float *elapsed_ms);
 /* Launch / kernel-time counters since the last reset:
  * out[0] = kernels launched, out[1..] = per-kernel-family counts. */
 int LB_NAME(launch_count)(lb_handle h, uint64_t *out, int32_t n, int32_t reset);
+/* Device time (ms, CUDA events around each launch) accumulated per kernel
+ * family since the last reset, same indexing as launch_count. */
+int LB_NAME(kernel_ms)(lb_handle h, double *out, int32_t n, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "timer_start": (C.c_int, [_h]),
     "timer_stop": (C.c_int, [_h, _f32p]),
     "launch_count": (C.c_int, [_h, _u64p, C.c_int32, C.c_int32]),
+    "kernel_ms": (C.c_int, [_h, _f64p, C.c_int32, C.c_int32]),
 }
 
 

@@ -17,28 +17,42 @@
 #define FULL 0xffffffffu
 
 // ===========================================================================
-// K3: sequential Gibbs sweep
+// K3: sequential Gibbs sweep.
+//
+// One CTA per kind walks the action list; the dependent chain per action is
+//   ADD    score (all warps) -> bar -> sample (warp 0) -> bar -> update (owner warps)
+//   REMOVE lookup (thread 0) -> bar -> update (owner warps)
+// Features are split into three classes (categorical = BB/DD/DPD gathers,
+// GP, NICH) and every warp owns a fixed, class-pure stripe of features for
+// BOTH scoring and updating, so a warp's own table writes are ordered before
+// its next reads without a third block barrier, and no warp diverges over
+// feature types.  Row cells are prefetched two actions ahead into a 4-slot
+// shared-memory ring; the Philox uniform of the next ADD is drawn by an idle
+// warp while warp 0 samples.
 // ===========================================================================
 constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_J = 4;    // groups per lane per chunk (one chunk = 128 groups)
 constexpr int SW_PF = 4;   // row cells prefetched per thread -> nf <= 1024 per kind
 constexpr int SW_MAX_G = 4096;
+enum { CL_CAT = 0, CL_GP = 1, CL_NICH = 2, N_CLASS = 3 };
 
 struct SweepSmem {
-    int G;
-    int stop;
-    int pick;
-    int was_empty;
-    uint32_t removed_global;
-    uint32_t next_global;
+    int G, stop;
+    int pick[2], flag[2];          // indexed by action parity: no end-of-action barrier
+    uint32_t removed_global[2], next_global;
     unsigned long long sample_size;
+    float u[2];
+    int cls_begin[N_CLASS], cls_end[N_CLASS];
+    int warp_cls[SW_WARPS], warp_rank[SW_WARPS], warp_nw[SW_WARPS];
 };
 
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
-    return v;
+    // order-preserving float -> int map, then one redux.sync
+    int i = __float_as_int(v);
+    i ^= (i >> 31) & 0x7fffffff;
+    i = __reduce_max_sync(FULL, i);
+    i ^= (i >> 31) & 0x7fffffff;
+    return __int_as_float(i);
 }
 
 // Draw from softmax(scores[0..G)) with uniform u, CDF in index order
@@ -83,6 +97,62 @@ __device__ __forceinline__ int warp_sample(float *scores, int G, float u, int la
     return __shfl_sync(FULL, pick, src);
 }
 
+__device__ __forceinline__ int feat_class(int type) {
+    return type == LB_GP ? CL_GP : (type == LB_NICH ? CL_NICH : CL_CAT);
+}
+
+// partial scores of one warp's feature stripe for groups g0 + lane + 32*jj
+template <int NJ>
+__device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep, const FeatDev *s_feat,
+                                             const uint32_t *c_raw, const uint32_t *c_obs,
+                                             const uint32_t *ints, const float *cache, int st,
+                                             int zero_row, int g0, int lane, float *acc) {
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) acc[jj] = 0.f;
+    if (cls == CL_CAT) {
+        // branch-free gathers: unobserved cells read the all-zero cache row
+#pragma unroll 4
+        for (int j = fb; j < fe; j += fstep) {
+            const FeatDev &f = s_feat[j];
+            const uint32_t raw = c_raw[j];
+            const bool obs = c_obs[j] != 0u;
+            const bool bb = f.type == LB_BB;
+            const int vrow = obs ? f.cache_row + (bb ? (raw ? 0 : 1) : (int)raw) : zero_row;
+            const int srow = (obs && !bb) ? f.cache_row + f.dim : zero_row;
+            const float *cv = cache + (size_t)vrow * st + g0 + lane;
+            const float *cs = cache + (size_t)srow * st + g0 + lane;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) acc[jj] += cv[32 * jj] - cs[32 * jj];
+        }
+    } else if (cls == CL_GP) {
+        for (int j = fb; j < fe; j += fstep) {
+            if (!c_obs[j]) continue;
+            const FeatDev &f = s_feat[j];
+            const uint32_t raw = c_raw[j];
+            const float lf = lb_log_factorial(raw), x = (float)raw;
+            const uint32_t *sum = ints + (size_t)(f.int_row + 1) * st + g0 + lane;
+            const float *c0 = cache + (size_t)f.cache_row * st + g0 + lane;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float a = f.hp[0] + (float)sum[32 * jj];
+                acc[jj] += lb_lgamma_diff_int(a, raw) - lf + c0[32 * jj] + x * c0[st + 32 * jj];
+            }
+        }
+    } else {
+        for (int j = fb; j < fe; j += fstep) {
+            if (!c_obs[j]) continue;
+            const FeatDev &f = s_feat[j];
+            const float x = __uint_as_float(c_raw[j]);
+            const float *c = cache + (size_t)f.cache_row * st + g0 + lane;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float dx = (x - c[3 * (size_t)st + 32 * jj]) - c[4 * (size_t)st + 32 * jj];
+                acc[jj] += c[32 * jj] - c[st + 32 * jj] * log1pf(c[2 * (size_t)st + 32 * jj] * dx * dx);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(SW_THREADS, 1)
 k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const int32_t *kind_feats,
             const float *aux, RowsDev rows, const uint32_t *actions, uint64_t n_actions,
@@ -93,14 +163,17 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
     KindDev &kd = kinds[kid];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nf = kd.nf, st = kd.Gcap;
+    const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
+    const int zero_row = n_cache_rows;
+    const uint32_t g2p_cap = kd.g2p_cap;
 
     // carve shared memory
     SweepSmem *ss = (SweepSmem *)smem_raw;
-    FeatDev *s_feat = (FeatDev *)(smem_raw + 64);
+    FeatDev *s_feat = (FeatDev *)(smem_raw + 256);
     int32_t *s_fid = (int32_t *)(s_feat + nf);
-    uint32_t *s_raw = (uint32_t *)(s_fid + nf);          // [2][nf]
-    uint32_t *s_obs = s_raw + 2 * nf;                    // [2][nf]
-    float *s_score = (float *)(s_obs + 2 * nf);          // [st]
+    uint32_t *s_raw = (uint32_t *)(s_fid + nf);          // [4][nf]
+    uint32_t *s_obs = s_raw + 4 * nf;                    // [4][nf]
+    float *s_score = (float *)(s_obs + 4 * nf);          // [st]
     float *s_part = s_score + st;                        // [SW_WARPS][st]
 
     uint32_t *const counts = kd.counts;
@@ -109,6 +182,9 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
     double *const flts = kd.flts;
     float *const cache = kd.cache;
     uint32_t *const assign = kd.assign;
+    uint32_t *const p2g = kd.p2g;
+    uint32_t *const g2p = kd.g2p;
+    const int32_t *const cache_row_feat = kd.cache_row_feat;
     const float alpha = kd.alpha, d = kd.d;
 
     for (int j = tid; j < nf; j += SW_THREADS) {
@@ -116,14 +192,45 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         s_feat[j] = feats[fid];
         s_fid[j] = fid;
     }
+    __syncthreads();
     if (tid == 0) {
-        ss->G = kd.G; ss->stop = 0; ss->pick = 0; ss->was_empty = 0;
+        ss->G = kd.G; ss->stop = 0;
         ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
+        // class ranges (features are sorted by type) and warp ownership
+        int cnt[N_CLASS] = {0, 0, 0};
+        for (int c = 0; c < N_CLASS; ++c) { ss->cls_begin[c] = nf; ss->cls_end[c] = 0; }
+        for (int j = 0; j < nf; ++j) {
+            const int c = feat_class(s_feat[j].type);
+            if (j < ss->cls_begin[c]) ss->cls_begin[c] = j;
+            ss->cls_end[c] = j + 1;
+            cnt[c]++;
+        }
+        const float weight[N_CLASS] = {1.f, 4.f, 3.f};
+        int nw[N_CLASS] = {0, 0, 0}, left = SW_WARPS;
+        for (int c = 0; c < N_CLASS; ++c) if (cnt[c]) { nw[c] = 1; --left; }
+        while (left > 0) {
+            int best = -1; float load = 0.f;
+            for (int c = 0; c < N_CLASS; ++c) {
+                if (!cnt[c] || nw[c] >= cnt[c]) continue;
+                const float l = weight[c] * (float)cnt[c] / (float)nw[c];
+                if (l > load) { load = l; best = c; }
+            }
+            if (best < 0) break;
+            nw[best]++; --left;
+        }
+        int w = SW_WARPS - 1;   // hand out from the top so warp 0 (the sampler) is loaded last
+        for (int c = N_CLASS - 1; c >= 0; --c)
+            for (int r = 0; r < nw[c]; ++r, --w) { ss->warp_cls[w] = c; ss->warp_rank[w] = r; ss->warp_nw[w] = nw[c]; }
+        for (; w >= 0; --w) { ss->warp_cls[w] = -1; ss->warp_rank[w] = 0; ss->warp_nw[w] = 1; }
     }
     __syncthreads();
+    const int my_cls = ss->warp_cls[warp];
+    const int fstep = ss->warp_nw[warp];
+    const int fb = my_cls >= 0 ? ss->cls_begin[my_cls] + ss->warp_rank[warp] : 0;
+    const int fe = my_cls >= 0 ? ss->cls_end[my_cls] : 0;
 
     uint64_t i = kd.progress;
-    // load row cells of action `idx` into registers
+    // row cells of action `idx`: global -> registers, later registers -> ring slot
     uint32_t pf_raw[SW_PF], pf_obs[SW_PF];
     auto prefetch = [&](uint64_t idx) {
 #pragma unroll
@@ -141,59 +248,65 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
             }
         }
     };
-    auto commit = [&](int buf) {
+    auto commit = [&](int slot) {
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
             const int j = tid + q * SW_THREADS;
-            if (j < nf) { s_raw[buf * nf + j] = pf_raw[q]; s_obs[buf * nf + j] = pf_obs[q]; }
+            if (j < nf) { s_raw[slot * nf + j] = pf_raw[q]; s_obs[slot * nf + j] = pf_obs[q]; }
         }
     };
-    prefetch(i);
-    commit(0);
+    auto next_uniform = [&](uint64_t idx) {   // drawn by the last warp, off warp 0's critical path
+        if (warp == SW_WARPS - 1 && lane == 0 && idx < n_actions && !(actions[idx] & 1u))
+            ss->u[idx & 1] = lb_uniform(seed, 0u, offset + idx, (uint32_t)kid);
+    };
+    prefetch(i); commit((int)(i & 3));
+    prefetch(i + 1); commit((int)((i + 1) & 3));
+    next_uniform(i);
     __syncthreads();
 
-    int cur = 0;
+    // owner-warp update of this warp's feature stripe at group g
+    auto update_stripe = [&](const uint32_t *c_raw, const uint32_t *c_obs, int g, int sign) {
+        for (int j = fb + lane * fstep; j < fe; j += 32 * fstep) {
+            if (!c_obs[j]) continue;
+            const FeatDev &f = s_feat[j];
+            lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
+                           cache + (size_t)f.cache_row * st + g, st, c_raw[j], sign);
+        }
+        __syncwarp();
+    };
+
     int status = LB_ST_OK;
     for (; i < n_actions; ++i) {
         const uint32_t act = actions[i];
         const uint64_t r = act >> 1;
         const bool is_remove = act & 1u;
-        const int G = ss->G;
-        const uint32_t *c_raw = s_raw + cur * nf, *c_obs = s_obs + cur * nf;
+        const int slot = (int)(i & 3);
+        const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
         if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
-        prefetch(i + 1);  // latency overlaps this action's work
+        const int G = ss->G;
+        prefetch(i + 2);   // latency overlaps this action's work
 
         if (!is_remove) {
             // ---- ADD: model.add_value -> score_value -> sample -> add_value ----
-            if (G >= st || ss->next_global >= kd.g2p_cap) { status = LB_ST_NEED_GROW; break; }
-            float u = 0.f;
-            if (warp == 0) u = lb_uniform(seed, 0u, offset + i, (uint32_t)kid);
+            if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
             if (tid == 0 && assign[r] != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
-            // partial scores: warp w owns features w, w+8, ...; lanes own groups
-            for (int g0 = 0; g0 < G; g0 += 32 * SW_J) {
-                float acc[SW_J];
+            for (int g0 = 0; g0 < G; g0 += 128) {
+                float acc[4];
+                const int left = G - g0;
+                if (left <= 32) {
+                    score_stripe<1>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+                    s_part[warp * st + g0 + lane] = acc[0];
+                } else if (left <= 64) {
+                    score_stripe<2>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+                    s_part[warp * st + g0 + lane] = acc[0];
+                    s_part[warp * st + g0 + lane + 32] = acc[1];
+                } else {
+                    score_stripe<4>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
 #pragma unroll
-                for (int jj = 0; jj < SW_J; ++jj) acc[jj] = 0.f;
-                for (int j = warp; j < nf; j += SW_WARPS) {
-                    if (!c_obs[j]) continue;
-                    const FeatDev &f = s_feat[j];
-                    const uint32_t raw = c_raw[j];
-                    const float cc = f.type == LB_GP ? lb_log_factorial(raw) : 0.f;
-                    const uint32_t *in = ints + (size_t)f.int_row * st;
-                    const float *c = cache + (size_t)f.cache_row * st;
-#pragma unroll
-                    for (int jj = 0; jj < SW_J; ++jj) {
-                        const int g = g0 + lane + 32 * jj;
-                        if (g < G) acc[jj] += lb_score_cell(f, in + g, c + g, st, raw, cc);
-                    }
-                }
-#pragma unroll
-                for (int jj = 0; jj < SW_J; ++jj) {
-                    const int g = g0 + lane + 32 * jj;
-                    if (g < G) s_part[warp * st + g] = acc[jj];
+                    for (int jj = 0; jj < 4; ++jj) s_part[warp * st + g0 + lane + 32 * jj] = acc[jj];
                 }
             }
-            __syncthreads();  // (1) partials visible
+            __syncthreads();  // (A) partial scores visible
             if (ss->stop) { status = ss->stop; break; }
             if (warp == 0) {
                 // clustering.score_value: CRP prior (SURVEY.md 8c Pitman-Yor)
@@ -208,50 +321,46 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                         dbg_scores[((uint64_t)i * K + kid) * dbg_stride + g] = s;
                 }
                 __syncwarp();
-                const int pick = warp_sample(s_score, G, u, lane);
+                const int pick = warp_sample(s_score, G, ss->u[i & 1], lane);
                 if (lane == 0) {
-                    ss->pick = pick;
-                    ss->was_empty = counts[pick] == 0;
+                    // clustering.add_value + push global id (cat_kernel.hpp:222-223)
+                    const uint32_t n = counts[pick] + 1u;
+                    ss->pick[i & 1] = pick;
+                    ss->flag[i & 1] = n == 1u;
+                    counts[pick] = n;
+                    shifted[pick] = logf((float)n - d);
+                    ss->sample_size += 1;
+                    assign[r] = p2g[pick];
+                    if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)pick;
                 }
+            } else {
+                commit((int)((i + 2) & 3));
+                next_uniform(i + 1);
             }
-            __syncthreads();  // (2) pick visible
-            const int g = ss->pick;
-            const bool add_group = ss->was_empty;
-            if (tid == 0) {
-                const uint32_t n = counts[g] + 1;
-                counts[g] = n;
-                shifted[g] = logf((float)n - d);
-                ss->sample_size += 1;
-                assign[r] = kd.p2g[g];
-                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)g;
-            }
-            for (int j = tid; j < nf; j += SW_THREADS) {
-                if (!c_obs[j]) continue;
-                const FeatDev &f = s_feat[j];
-                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g,
-                               flts + (size_t)f.flt_row * st + g,
-                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], +1);
-            }
-            if (add_group) {
+            __syncthreads();  // (B) pick visible
+            if (warp == 0) commit((int)((i + 2) & 3));
+            const int g = ss->pick[i & 1];
+            update_stripe(c_raw, c_obs, g, +1);
+            if (ss->flag[i & 1]) {
                 // add_group (product_mixture.cc:178-183): append a fresh empty group
                 const int ng = G;
-                for (int row = tid; row < kd.n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
-                for (int row = tid; row < kd.n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
+                for (int row = tid; row < n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
+                for (int row = tid; row < n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
                 __syncthreads();
-                for (int row = tid; row < kd.n_cache_rows; row += SW_THREADS) {
-                    const FeatDev &f = s_feat[kd.cache_row_feat[row]];
-                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng,
-                                   flts + (size_t)f.flt_row * st + ng,
+                for (int row = tid; row < n_cache_rows; row += SW_THREADS) {
+                    const FeatDev &f = s_feat[cache_row_feat[row]];
+                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
                                    cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
                 }
                 if (tid == 0) {
                     counts[ng] = 0u; shifted[ng] = 0.f;
                     const uint32_t gid = ss->next_global;
-                    kd.p2g[ng] = gid;
-                    kd.g2p[gid] = (uint32_t)ng;
+                    p2g[ng] = gid;
+                    g2p[gid] = (uint32_t)ng;
                     ss->next_global = gid + 1;
                     ss->G = ng + 1;
                 }
+                __syncthreads();
             }
         } else {
             // ---- REMOVE: pop global id -> packed; mixture.remove_value ----
@@ -259,60 +368,52 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                 const uint32_t a = assign[r];
                 if (a == LB_UNASSIGNED) ss->stop = LB_ST_REMOVE_UNASSIGNED;
                 else {
-                    const uint32_t g = kd.g2p[a];
-                    ss->pick = (int)g;
-                    ss->removed_global = a;
-                    ss->was_empty = counts[g] == 1u;
+                    const uint32_t g = g2p[a];
+                    const uint32_t n = counts[g] - 1u;
+                    ss->pick[i & 1] = (int)g;
+                    ss->removed_global[i & 1] = a;
+                    ss->flag[i & 1] = n == 0u;
+                    counts[g] = n;
+                    shifted[g] = n ? logf((float)n - d) : 0.f;
+                    ss->sample_size -= 1;
+                    assign[r] = LB_UNASSIGNED;
+                    if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = g;
                 }
             }
-            __syncthreads();  // (1)
+            commit((int)((i + 2) & 3));
+            next_uniform(i + 1);
+            __syncthreads();  // (A)
             if (ss->stop) { status = ss->stop; break; }
-            const int g = ss->pick;
-            const bool remove_group = ss->was_empty;
-            if (tid == 0) {
-                const uint32_t n = counts[g] - 1;
-                counts[g] = n;
-                shifted[g] = n ? logf((float)n - d) : 0.f;
-                ss->sample_size -= 1;
-                assign[r] = LB_UNASSIGNED;
-                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)g;
-            }
-            for (int j = tid; j < nf; j += SW_THREADS) {
-                if (!c_obs[j]) continue;
-                const FeatDev &f = s_feat[j];
-                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g,
-                               flts + (size_t)f.flt_row * st + g,
-                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], -1);
-            }
-            if (remove_group) {
+            const int g = ss->pick[i & 1];
+            update_stripe(c_raw, c_obs, g, -1);
+            if (ss->flag[i & 1]) {
                 // remove_group (product_mixture.cc:233-238): swap-with-last
                 __syncthreads();
                 const int last = G - 1;
                 if (g != last) {
-                    for (int row = tid; row < kd.n_int_rows; row += SW_THREADS)
+                    for (int row = tid; row < n_int_rows; row += SW_THREADS)
                         ints[(size_t)row * st + g] = ints[(size_t)row * st + last];
-                    for (int row = tid; row < kd.n_flt_rows; row += SW_THREADS)
+                    for (int row = tid; row < n_flt_rows; row += SW_THREADS)
                         flts[(size_t)row * st + g] = flts[(size_t)row * st + last];
-                    for (int row = tid; row < kd.n_cache_rows; row += SW_THREADS)
+                    for (int row = tid; row < n_cache_rows; row += SW_THREADS)
                         cache[(size_t)row * st + g] = cache[(size_t)row * st + last];
                 }
                 if (tid == 0) {
-                    kd.g2p[ss->removed_global] = LB_UNASSIGNED;
+                    g2p[ss->removed_global[i & 1]] = LB_UNASSIGNED;
                     if (g != last) {
                         counts[g] = counts[last];
                         shifted[g] = shifted[last];
-                        const uint32_t gid = kd.p2g[last];
-                        kd.p2g[g] = gid;
-                        kd.g2p[gid] = (uint32_t)g;
+                        const uint32_t gid = p2g[last];
+                        p2g[g] = gid;
+                        g2p[gid] = (uint32_t)g;
                     }
                     ss->G = last;
                 }
+                __syncthreads();
             }
         }
-        commit(cur ^ 1);
-        cur ^= 1;
-        __syncthreads();  // end of action: tables, G and the next row are visible
     }
+    __syncthreads();
     if (tid == 0) {
         kd.G = ss->G;
         kd.sample_size = ss->sample_size;
@@ -323,7 +424,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
 }
 
 static size_t sweep_smem_bytes(int nf, int Gcap) {
-    return 64 + (size_t)nf * (sizeof(FeatDev) + 4 + 16) + (size_t)Gcap * 4 * (1 + SW_WARPS) + 64;
+    return 256 + (size_t)nf * (sizeof(FeatDev) + 4 + 32) + (size_t)Gcap * 4 * (1 + SW_WARPS) + 64;
 }
 
 int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
@@ -346,10 +447,13 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
     LB_CUDA(cudaMallocAsync((void **)&d_ids, 4 * kind_ids.size(), e->stream));
     LB_CUDA(cudaMemcpyAsync(d_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    LB_CUDA(cudaEventRecord(e->kev0, e->stream));
     k_cat_sweep<<<(unsigned)kind_ids.size(), SW_THREADS, smem, e->stream>>>(
         e->d_kinds, d_ids, e->d_feats, e->d_kind_feats, e->d_aux, rows, e->d_actions, n_actions, seed,
         offset, (int)e->kinds.size(), e->empty_group_count, d_picks, d_scores, stride);
     LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaEventRecord(e->kev1, e->stream));
+    e->kev_pending = true;
     LB_CUDA(cudaFreeAsync(d_ids, e->stream));
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SWEEP]++;
     return 0;

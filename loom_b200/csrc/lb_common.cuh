@@ -21,7 +21,9 @@
 //   cache float  [n_cache_rows][Gcap] BB: log p(1), log p(0)
 //                                     DD/DPD: log(a_v + n_v) [dim], log(A + N)
 //                                     GP: a'*log(b'/(b'+1)), -log(1+b')
-//                                     NICH: c0, (nu'+1)/2, lambda/nu', mu'
+//                                     NICH: c0, (nu'+1)/2, lambda/nu', mu'_hi, mu'_lo
+//   one extra all-zero cache row (index n_cache_rows) lets scorers read
+//   "unobserved" cells branch-free
 struct FeatDev {
     int32_t type, dim;
     float hp[4];
@@ -119,6 +121,27 @@ __device__ __forceinline__ float lb_lgamma_diff(float a, float x) {
     }
     return lb_lgamma(b) - lgammaf(a);
 }
+// lgamma(a + x) - lgamma(a) for an integer count x: short rising factorials are
+// one or two logs of an exact-ish product; longer ones use the Stirling form.
+__device__ __forceinline__ float lb_lgamma_diff_int(float a, uint32_t x) {
+    if (x == 0u) return 0.f;
+    if (x <= 4u) {
+        float p = a;
+        if (x > 1u) p *= a + 1.f;
+        if (x > 2u) p *= a + 2.f;
+        if (x > 3u) p *= a + 3.f;
+        return logf(p);
+    }
+    if (x <= 8u) {
+        const float p1 = a * (a + 1.f) * (a + 2.f) * (a + 3.f);
+        float p2 = a + 4.f;
+        if (x > 5u) p2 *= a + 5.f;
+        if (x > 6u) p2 *= a + 6.f;
+        if (x > 7u) p2 *= a + 7.f;
+        return logf(p1) + logf(p2);
+    }
+    return lb_lgamma_diff(a, (float)x);
+}
 // log(x!) for an integer count
 __device__ __forceinline__ float lb_log_factorial(uint32_t x) {
     const float xf = (float)x;
@@ -132,14 +155,17 @@ __device__ __forceinline__ float lb_log_factorial(uint32_t x) {
 }
 
 // log(x!) in double for the GP log_prod statistic (exact table for small x)
+__device__ const double LB_LOG_FACTORIAL[32] = {
+    0.0, 0.0, 0.69314718055994531, 1.7917594692280550, 3.1780538303479458, 4.7874917427820458,
+    6.5792512120101012, 8.5251613610654147, 10.604602902745251, 12.801827480081469,
+    15.104412573075516, 17.502307845873887, 19.987214495661885, 22.552163853123425,
+    25.191221182738680, 27.899271383840890, 30.671860106080672, 33.505073450136891,
+    36.395445208033053, 39.339884187199495, 42.335616460753485, 45.380138898476908,
+    48.471181351835227, 51.606675567764377, 54.784729398112319, 58.003605222980518,
+    61.261701761002001, 64.557538627006338, 67.889743137181540, 71.257038967168015,
+    74.658236348830158, 78.092223553315307};
 __device__ __forceinline__ double lb_log_factorial_d(uint32_t x) {
-    if (x < 2u) return 0.0;
-    if (x < 16u) {
-        double p = 2.0;
-        for (uint32_t j = 3u; j <= x; ++j) p *= (double)j;
-        return log(p);
-    }
-    return lgamma((double)x + 1.0);
+    return x < 32u ? LB_LOG_FACTORIAL[x] : lgamma((double)x + 1.0);
 }
 
 // ---- per-feature cached scorer refresh (one group) -------------------------
@@ -158,17 +184,24 @@ __device__ __forceinline__ void lb_refresh_gp(const FeatDev &f, const uint32_t *
 }
 __device__ __forceinline__ void lb_refresh_nich(const FeatDev &f, const uint32_t *in,
                                                 const double *fl, float *c, int st) {
-    const double mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
-    const double n = (double)in[0], mean = fl[0], ctv = fl[st];
-    const double kn = kappa + n, mun = (kappa * mu + n * mean) / kn, nun = nu + n;
-    const double dm = mu - mean;
-    const double sn = (nu * sigmasq + ctv + n * kappa * dm * dm / kn) / nun;
-    const double lambda = kn / ((kn + 1.0) * sn);
-    const float half_nu = (float)(0.5 * nun);
-    c[0] = lb_lgamma_diff(half_nu, 0.5f) + 0.5f * logf((float)(lambda / (3.14159265358979323846 * nun)));
+    // posterior NIX parameters.  mu' is formed in double and
+    // cached as a hi/lo float pair so x - mu' keeps full precision when
+    // |mean| >> sigma; everything else is fp32-safe.
+    const double mean = fl[0];
+    const float mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
+    const float n = (float)in[0], ctv = (float)fl[st];
+    const float kn = kappa + n, inv_kn = 1.f / kn, nun = nu + n;
+    const double mun = ((double)kappa * (double)mu + (double)n * mean) * (double)inv_kn;
+    const float dm = (float)((double)mu - mean);
+    const float s_nun = nu * sigmasq + ctv + n * kappa * dm * dm * inv_kn;  // nu' * sigma'^2
+    const float prec = kn / ((kn + 1.f) * s_nun);                           // lambda / nu'
+    const float half_nu = 0.5f * nun;
+    const float mu_hi = (float)mun;
+    c[0] = lb_lgamma_diff(half_nu, 0.5f) + 0.5f * logf(prec * 0.318309886f);
     c[st] = half_nu + 0.5f;
-    c[2 * (size_t)st] = (float)(lambda / nun);
-    c[3 * (size_t)st] = (float)mun;
+    c[2 * (size_t)st] = prec;
+    c[3 * (size_t)st] = mu_hi;
+    c[4 * (size_t)st] = (float)(mun - (double)mu_hi);
 }
 
 // Recompute one cached-scorer row (`local` = row index inside the feature) of
@@ -255,11 +288,11 @@ __device__ __forceinline__ float lb_score_cell(const FeatDev &f, const uint32_t 
     case LB_DPD:
         return c[(size_t)raw * st] - c[(size_t)f.dim * st];
     case LB_GP: {
-        const float a = f.hp[0] + (float)in[st], x = (float)raw;
-        return lb_lgamma_diff(a, x) - cell_const + c[0] + x * c[st];
+        const float a = f.hp[0] + (float)in[st];
+        return lb_lgamma_diff_int(a, raw) - cell_const + c[0] + (float)raw * c[st];
     }
     case LB_NICH: {
-        const float dx = __uint_as_float(raw) - c[3 * (size_t)st];
+        const float dx = (__uint_as_float(raw) - c[3 * (size_t)st]) - c[4 * (size_t)st];
         return c[0] - c[st] * log1pf(c[2 * (size_t)st] * dx * dx);
     }
     }

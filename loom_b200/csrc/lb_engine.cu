@@ -87,12 +87,12 @@ int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap) {
     LB_TRY(dev_alloc(&k.g2p, k.g2p_cap));
     LB_TRY(dev_alloc(&k.ints, (size_t)k.n_int_rows * Gcap));
     LB_TRY(dev_alloc(&k.flts, (size_t)k.n_flt_rows * Gcap));
-    LB_TRY(dev_alloc(&k.cache, (size_t)k.n_cache_rows * Gcap));
+    LB_TRY(dev_alloc(&k.cache, (size_t)(k.n_cache_rows + 1) * Gcap));  // + the all-zero row
     LB_CUDA(cudaMemsetAsync(k.counts, 0, 4 * (size_t)Gcap, e->stream));
     LB_CUDA(cudaMemsetAsync(k.shifted, 0, 4 * (size_t)Gcap, e->stream));
     LB_CUDA(cudaMemsetAsync(k.ints, 0, 4 * (size_t)k.n_int_rows * Gcap + 1 - 1, e->stream));
     LB_CUDA(cudaMemsetAsync(k.flts, 0, 8 * (size_t)k.n_flt_rows * Gcap, e->stream));
-    LB_CUDA(cudaMemsetAsync(k.cache, 0, 4 * (size_t)k.n_cache_rows * Gcap, e->stream));
+    LB_CUDA(cudaMemsetAsync(k.cache, 0, 4 * (size_t)(k.n_cache_rows + 1) * Gcap, e->stream));
     std::vector<uint32_t> ident(std::max<uint32_t>(k.g2p_cap, (uint32_t)Gcap));
     for (size_t i = 0; i < ident.size(); ++i) ident[i] = (uint32_t)i;
     LB_CUDA(cudaMemcpyAsync(k.p2g, ident.data(), 4 * (size_t)Gcap, cudaMemcpyHostToDevice, e->stream));
@@ -235,6 +235,8 @@ extern "C" int lb_create(int device, lb_handle *out) {
     LB_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     LB_CUDA(cudaEventCreate(&e->ev0));
     LB_CUDA(cudaEventCreate(&e->ev1));
+    LB_CUDA(cudaEventCreate(&e->kev0));
+    LB_CUDA(cudaEventCreate(&e->kev1));
     cudaDeviceProp prop;
     LB_CUDA(cudaGetDeviceProperties(&prop, device));
     e->n_sm = prop.multiProcessorCount;
@@ -261,6 +263,7 @@ extern "C" void lb_destroy(lb_handle h) {
     dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_prop_scores);
     if (e->d_scratch) cudaFree(e->d_scratch);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -369,6 +372,12 @@ extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, ui
         LB_CUDA(cudaMemcpyAsync(e->d_kinds, e->h_kinds.data(), sizeof(KindDev) * K, cudaMemcpyHostToDevice, e->stream));
         LB_TRY(lb_launch_sweep(e, active, n, seed, offset, d_picks, d_scores, stride));
         LB_TRY(lb_pull_kinds(e));
+        if (e->kev_pending) {  // the pull synchronised the stream: the kernel's events are complete
+            float ms = 0.f;
+            LB_CUDA(cudaEventElapsedTime(&ms, e->kev0, e->kev1));
+            e->kernel_ms[LB_L_SWEEP] += ms; e->kernel_ms[LB_L_TOTAL] += ms;
+            e->kev_pending = false;
+        }
         std::vector<int> again;
         for (int kid : active) {
             const KindDev &d = e->h_kinds[kid];
@@ -608,5 +617,11 @@ extern "C" int lb_launch_count(lb_handle h, uint64_t *out, int32_t n, int32_t re
     Engine *e = (Engine *)h;
     for (int i = 0; i < n; ++i) out[i] = i < 8 ? e->launches[i] : 0;
     if (reset) for (int i = 0; i < 8; ++i) e->launches[i] = 0;
+    return 0;
+}
+extern "C" int lb_kernel_ms(lb_handle h, double *out, int32_t n, int32_t reset) {
+    Engine *e = (Engine *)h;
+    for (int i = 0; i < n; ++i) out[i] = i < 8 ? e->kernel_ms[i] : 0.0;
+    if (reset) for (int i = 0; i < 8; ++i) e->kernel_ms[i] = 0.0;
     return 0;
 }

@@ -71,6 +71,9 @@ struct Engine {
     float *d_prop_scores = nullptr;
 
     uint64_t launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+    bool kev_pending = false;
 };
 
 // launch-family indices for launch_count
@@ -104,7 +107,7 @@ inline int spec_cache_rows(const lb_feature_spec &s) {
     case LB_BB: return 2;
     case LB_DD: case LB_DPD: return s.dim + 1;
     case LB_GP: return 2;
-    case LB_NICH: return 4;
+    case LB_NICH: return 5;
     }
     return 0;
 }

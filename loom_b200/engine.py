@@ -335,3 +335,8 @@ class Engine:
         out = np.zeros(n, np.uint64)
         self.abi.check(self.abi.launch_count(self.h, ptr(out, _abi._u64p), n, int(reset)))
         return out
+
+    def kernel_ms(self, reset=False, n=8):
+        out = np.zeros(n, np.float64)
+        self.abi.check(self.abi.kernel_ms(self.h, ptr(out, _f64p), n, int(reset)))
+        return out
