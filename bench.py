@@ -23,9 +23,16 @@ roofline= the dominant kernel (k_cat_sweep): algorithmic bytes per launch
           time, against the measured HBM copy bandwidth.  The exact sequential
           Gibbs chain is latency-bound (one CTA per kind); roofline_aux carries the
           batch kernels (score_rows K1, accumulate_rows K2) that ARE HBM-bound.
-N > 1  : the sequential chain does not shard (kinds already run concurrently on
-          one GPU), so each rank runs one independent replica -- loom's own
-          per-sample parallelism (loom/tasks.py:192) -- "scaling": "weak".
+samples : the exact Gibbs chain of one kind is sequential, so one chain keeps only
+          K (=7) of the 148 SMs busy.  loom itself runs `sample_count` independent
+          chains per dataset in parallel processes (loom/tasks.py:173-194, default 10);
+          the GPU runs floor(148 / K) = 21 of them concurrently, one CTA per
+          (chain, kind), each chain its own engine + stream behind the same C ABI.
+          `value` is the aggregate over those chains ("config.samples"); the
+          single-chain rate is in "rates".  The reference arm gets the same treatment:
+          as many chains in parallel as the host cores allow.
+N > 1  : chains do not communicate, so every rank runs its own set of chains on its
+          GPU -- "replicas only", "scaling": "weak" (DESIGN.md).
 --impl reference times the restated reference (oracle/, float64 C, OpenMP one
 thread per kind like src/cat_pipeline.cc:103-125) on the host cores, on a bounded
 row sample of the same workload.
@@ -44,6 +51,8 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+# one hardware work queue per chain stream (the default of 8 would falsely serialise 21 streams)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "cat_kernel_cells_per_sec"
 UNIT = "cells/s"
@@ -100,6 +109,8 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
+        if os.environ.get("LB_BENCH_CLOCK_MS") == "0":
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -108,7 +119,8 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", os.environ.get("LB_BENCH_CLOCK_MS", "200")], stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -169,29 +181,42 @@ def run_reference_arm(args, model, rows, n_cells_full):
     if R % 32:
         sub.mask[:, -1] &= np.uint32((1 << (R % 32)) - 1)
     cells = 4 * sub.n_cells()
-    e = Engine(oracle)
-    e.set_model(model)
-    e.set_rows(sub)
     first, drain = step_actions(R)
     cores = os.cpu_count() or 1
-    threads = min(cores, model.n_kinds)
+    # the reference's threading model: one thread per kind inside a chain
+    # (src/cat_pipeline.cc:103-125), chains in parallel processes (loom/tasks.py:192)
+    n_par = max(1, cores // model.n_kinds)
+    oracle.lib.lo_set_threads(model.n_kinds)
+    engines = []
+    for c in range(n_par):
+        e = Engine(oracle)
+        e.set_model(model)
+        e.set_rows(sub)
+        engines.append(e)
+
+    def chain(c, it):
+        engines[c].cat_sweep(first, seed=100 * c + it)
+        engines[c].cat_sweep(drain, seed=100 * c + it)
+
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        e.cat_sweep(first, seed=100 + it)
-        e.cat_sweep(drain, seed=100 + it)
+        ths = [threading.Thread(target=chain, args=(c, it)) for c in range(n_par)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    value = cells / (ms * 1e-3)
+    value = n_par * cells / (ms * 1e-3)
+    threads = min(cores, n_par * model.n_kinds)
     return {
         "value": value, "ms_per_step": ms,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "host_cores": cores,
-                         "sample": "first %d of %d rows of C2, same 4-pass step, float64 C oracle "
-                                   "(restated reference, distributions 2.0.28 math in exact libm), "
-                                   "OpenMP one thread per kind" % (R, rows.n_rows)},
+                         "host_cores": cores, "chains_in_parallel": n_par,
+                         "sample": "first %d of %d rows of C2, same 4-pass step, %d chain(s) in parallel x one "
+                                   "OpenMP thread per kind; float64 C oracle (restated reference, "
+                                   "distributions 2.0.28 math in exact libm)" % (R, rows.n_rows, n_par)},
     }
 
 
@@ -204,6 +229,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--rows", type=int, default=0, help="override the row count (parity runs only)")
     ap.add_argument("--ref-rows", type=int, default=20000)
+    ap.add_argument("--samples", type=int, default=0,
+                    help="independent chains run concurrently per GPU (0 = floor(#SM / #kinds))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -252,14 +279,38 @@ def main():
     cells_per_step = 4 * n_obs
     first, drain = step_actions(R)
 
-    e = Engine(cuda, device=local_rank)
-    e.set_model(model)
-    e.set_rows(rows)
+    n_chains = args.samples or max(1, 148 // model.n_kinds)
+    config["samples"] = n_chains
+    config["parallelism"] = "%d independent chains x %d kinds per GPU, one CTA per (chain, kind)%s" % (
+        n_chains, model.n_kinds, "; replicas x%d" % world if world > 1 else "")
+    engines = []
+    for c in range(n_chains):
+        eng = Engine(cuda, device=local_rank)
+        eng.set_model(model)
+        eng.set_rows(rows)
+        engines.append(eng)
+    e = engines[0]
     for a in (rows.cat8, rows.wide, rows.mask):
         pin(a)
 
+    def on_all(fn):
+        """run fn(chain_index, engine) for every chain concurrently (ctypes drops the GIL)"""
+        errs = []
+
+        def wrap(c):
+            try:
+                fn(c, engines[c])
+            except Exception as exc:  # surface failures of worker threads
+                errs.append(exc)
+        ths = [threading.Thread(target=wrap, args=(c,)) for c in range(n_chains)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        if errs:
+            raise errs[0]
+
     def barrier():
-        e.sync()
+        for eng in engines:
+            eng.sync()
         if dist:
             import torch
             dist.barrier()
@@ -273,52 +324,73 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def device_step(it):
-        e.cat_sweep(first, seed=1000 * rank + it)
-        e.cat_sweep(drain, seed=1000 * rank + it)
+    def device_step(c, eng, it):
+        seed = 100000 * rank + 1000 * c + it
+        eng.cat_sweep(first, seed=seed)
+        eng.cat_sweep(drain, seed=seed)
 
-    # ---- device-resident value ----
+    # ---- single chain, device resident (rates.single_chain) ----
+    for it in range(2):
+        device_step(0, e, it)
+    e.sync()
+    e.timer_start()
+    device_step(0, e, 2)
+    single_ms = e.timer_stop()
+
+    # ---- device-resident value: all chains concurrently ----
     for it in range(args.warmup):
-        device_step(it)
+        on_all(lambda c, eng: device_step(c, eng, it))
     barrier()
-    e.launch_count(reset=True)
-    e.kernel_ms(reset=True)
+    for eng in engines:
+        eng.launch_count(reset=True)
+        eng.kernel_ms(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e.timer_start()
-    for it in range(args.steps):
-        device_step(args.warmup + it)
-    total_ms = e.timer_stop()
+    elapsed = [0.0] * n_chains
+
+    def timed(c, eng):
+        eng.timer_start()                      # CUDA events on the chain's own stream
+        for it in range(args.steps):
+            device_step(c, eng, args.warmup + it)
+        elapsed[c] = eng.timer_stop()
+    t0 = time.perf_counter()
+    on_all(timed)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if os.environ.get("LB_BENCH_DEBUG"):
+        log("per-chain elapsed ms:", [round(x) for x in elapsed], "wall", round(wall_ms),
+            "groups", [[eng.kind_info(k).n_groups for k in range(model.n_kinds)] for eng in engines[:3]])
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = e.launch_count()
-    kms = e.kernel_ms()
-    total_ms = max_over_ranks(total_ms)
+    launches = sum(eng.launch_count() for eng in engines)
+    kms = sum(eng.kernel_ms() for eng in engines)
+    total_ms = max_over_ranks(max(max(elapsed), wall_ms))   # slowest chain / host view, max over ranks
     ms_per_step = total_ms / args.steps
-    value = world * cells_per_step / (ms_per_step * 1e-3)
+    value = world * n_chains * cells_per_step / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers in, assignments out, inside the timed region ----
-    def e2e_step(it):
-        e.set_rows(rows)                      # H2D of the whole row block
-        e.cat_sweep(first, seed=5000 * rank + it)
+    def e2e_step(c, eng, it):
+        seed = 500000 * rank + 1000 * c + it
+        eng.set_rows(rows)                    # H2D of the whole row block
+        eng.cat_sweep(first, seed=seed)
         for k in range(model.n_kinds):
-            e.get_assignments(k)              # D2H of every kind's assignment column
-        e.cat_sweep(drain, seed=5000 * rank + it)
+            eng.get_assignments(k)            # D2H of every kind's assignment column
+        eng.cat_sweep(drain, seed=seed)
 
-    e2e_step(0)
+    on_all(lambda c, eng: e2e_step(c, eng, 0))
     barrier()
+
+    def e2e_timed(c, eng):
+        for it in range(args.steps):
+            e2e_step(c, eng, 1 + it)
     t0 = time.perf_counter()
-    e.timer_start()
-    for it in range(args.steps):
-        e2e_step(1 + it)
-    e2e_ms = e.timer_stop()
-    e2e_wall = (time.perf_counter() - t0) * 1e3
+    on_all(e2e_timed)
     barrier()
-    e2e_ms = max_over_ranks(max(e2e_ms, e2e_wall)) / args.steps
-    e2e_value = world * cells_per_step / (e2e_ms * 1e-3)
-    h2d = int(rows.cat8.nbytes + rows.wide.nbytes + rows.mask.nbytes + 4 * (len(first) + len(drain)))
-    d2h = int(4 * R * model.n_kinds)
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(e2e_wall) / args.steps
+    e2e_value = world * n_chains * cells_per_step / (e2e_ms * 1e-3)
+    h2d = n_chains * int(rows.cat8.nbytes + rows.wide.nbytes + rows.mask.nbytes + 4 * (len(first) + len(drain)))
+    d2h = n_chains * int(4 * R * model.n_kinds)
 
     # ---- roofline of the dominant kernel ----
     peaks = {}
@@ -331,14 +403,16 @@ def main():
     sweep_ms = float(kms[1])
     bytes_per_action = algorithmic_bytes_per_action(model, rows)
     actions_per_step = len(first) + len(drain)
-    alg_bytes_per_launch = bytes_per_action * actions_per_step * args.steps / max(n_sweep, 1)
+    alg_bytes_per_launch = bytes_per_action * actions_per_step * args.steps * n_chains / max(n_sweep, 1)
     avg_launch_ms = sweep_ms / max(n_sweep, 1)
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
-                "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
-                "note": "exact sequential Gibbs: latency-bound dependent chain, one CTA per kind"}
+                "kernel_share_of_step": sweep_ms / (total_ms * n_chains) if total_ms else None,
+                "concurrent_launches": n_chains,
+                "note": "exact sequential Gibbs: latency-bound dependent chain, one CTA per (chain, kind); "
+                        "achieved is per launch, %d launches run concurrently" % n_chains}
 
     # ---- auxiliary: the HBM-bound batch kernels on the same workload ----
     aux = {}
@@ -387,8 +461,10 @@ def main():
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches[0]),
             "roofline": roofline, "roofline_aux": aux, "clocks": clocks,
-            "rates": {"cells_per_step": cells_per_step, "observed_cells": n_obs,
-                      "row_actions_per_s": world * actions_per_step / (ms_per_step * 1e-3)}}
+            "rates": {"cells_per_step_per_chain": cells_per_step, "observed_cells": n_obs,
+                      "row_actions_per_s": world * n_chains * actions_per_step / (ms_per_step * 1e-3),
+                      "single_chain_cells_per_s": cells_per_step / (single_ms * 1e-3),
+                      "single_chain_ms_per_step": single_ms}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref_args = argparse.Namespace(**vars(args))

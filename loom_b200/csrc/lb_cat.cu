@@ -78,8 +78,10 @@ __device__ __forceinline__ int warp_sample(float *scores, int G, float u, int la
     }
     const float total = __shfl_sync(FULL, incl, 31);
     const float t = u * total;
-    const unsigned ballot = __ballot_sync(FULL, incl > t);
+    // Only lanes holding probability mass may be chosen: the scan's rounding can give a
+    // lane with an empty group range an inclusive sum one ulp above its predecessor's.
     const unsigned nonzero = __ballot_sync(FULL, local > 0.f);
+    const unsigned ballot = __ballot_sync(FULL, incl > t) & nonzero;
     const int src = ballot ? __ffs(ballot) - 1 : 31 - __clz(nonzero);
     int pick = lo;
     if (lane == src) {
@@ -443,8 +445,13 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
         LB_CUDA(cudaFuncSetAttribute(k_cat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    int32_t *d_ids = nullptr;
-    LB_CUDA(cudaMallocAsync((void **)&d_ids, 4 * kind_ids.size(), e->stream));
+    if ((int)kind_ids.size() > e->d_kind_ids_cap) {
+        if (e->d_kind_ids) cudaFree(e->d_kind_ids);
+        e->d_kind_ids = nullptr;
+        LB_CUDA(cudaMalloc((void **)&e->d_kind_ids, 4 * (kind_ids.size() + 16)));
+        e->d_kind_ids_cap = (int)kind_ids.size() + 16;
+    }
+    int32_t *d_ids = e->d_kind_ids;
     LB_CUDA(cudaMemcpyAsync(d_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
     LB_CUDA(cudaEventRecord(e->kev0, e->stream));
@@ -454,7 +461,6 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
     LB_CUDA(cudaGetLastError());
     LB_CUDA(cudaEventRecord(e->kev1, e->stream));
     e->kev_pending = true;
-    LB_CUDA(cudaFreeAsync(d_ids, e->stream));
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SWEEP]++;
     return 0;
 }

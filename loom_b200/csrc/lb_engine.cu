@@ -4,6 +4,7 @@
 // failure is an error (non-zero status), never a CPU fallback.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,6 +34,19 @@ template <class T> static void dev_free(T *&p) {
     p = nullptr;
 }
 
+// Per-kind tables are (re)allocated while other chains' kernels run on other streams of
+// the same device; cudaMalloc/cudaFree would synchronise the whole device and serialise
+// the chains, so these come from the stream-ordered pool.
+template <class T> static int pool_alloc(Engine *e, T **p, size_t n) {
+    *p = nullptr;
+    LB_CUDA(cudaMallocAsync((void **)p, std::max<size_t>(n, 1) * sizeof(T), e->stream));
+    return 0;
+}
+template <class T> static void pool_free(Engine *e, T *&p) {
+    if (p) cudaFreeAsync((void *)p, e->stream);
+    p = nullptr;
+}
+
 int lb_ensure_scratch(Engine *e, size_t bytes) {
     if (bytes <= e->scratch_bytes) return 0;
     if (e->d_scratch) cudaFree(e->d_scratch);
@@ -43,9 +57,9 @@ int lb_ensure_scratch(Engine *e, size_t bytes) {
     return 0;
 }
 
-void lb_kind_release(KindHost &k) {
-    dev_free(k.counts); dev_free(k.p2g); dev_free(k.g2p); dev_free(k.ints);
-    dev_free(k.shifted); dev_free(k.cache); dev_free(k.flts); dev_free(k.cache_row_feat);
+void lb_kind_release(Engine *e, KindHost &k) {
+    pool_free(e, k.counts); pool_free(e, k.p2g); pool_free(e, k.g2p); pool_free(e, k.ints);
+    pool_free(e, k.shifted); pool_free(e, k.cache); pool_free(e, k.flts); pool_free(e, k.cache_row_feat);
     // assign is released separately (it survives relayouts)
 }
 
@@ -64,8 +78,8 @@ int lb_kind_layout(Engine *e, KindHost &k, const std::vector<int> &fids) {
         k.cache_off[j] = k.n_cache_rows; k.n_cache_rows += spec_cache_rows(s);
         for (int r = 0; r < spec_cache_rows(s); ++r) row_feat.push_back((int32_t)j);
     }
-    dev_free(k.cache_row_feat);
-    LB_TRY(dev_alloc(&k.cache_row_feat, row_feat.size()));
+    pool_free(e, k.cache_row_feat);
+    LB_TRY(pool_alloc(e, &k.cache_row_feat, row_feat.size()));
     if (!row_feat.empty())
         LB_CUDA(cudaMemcpyAsync(k.cache_row_feat, row_feat.data(), 4 * row_feat.size(),
                                 cudaMemcpyHostToDevice, e->stream));
@@ -75,19 +89,19 @@ int lb_kind_layout(Engine *e, KindHost &k, const std::vector<int> &fids) {
 
 // allocate zeroed per-group tables (layout must be set); id tracker = identity
 int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap) {
-    dev_free(k.counts); dev_free(k.p2g); dev_free(k.g2p); dev_free(k.ints);
-    dev_free(k.shifted); dev_free(k.cache); dev_free(k.flts);
+    pool_free(e, k.counts); pool_free(e, k.p2g); pool_free(e, k.g2p); pool_free(e, k.ints);
+    pool_free(e, k.shifted); pool_free(e, k.cache); pool_free(e, k.flts);
     k.G = G; k.Gcap = Gcap;
     k.sample_size = 0;
     k.next_global = (uint32_t)G;
     k.g2p_cap = std::max<uint32_t>(4096u, 4u * (uint32_t)Gcap);
-    LB_TRY(dev_alloc(&k.counts, Gcap));
-    LB_TRY(dev_alloc(&k.shifted, Gcap));
-    LB_TRY(dev_alloc(&k.p2g, Gcap));
-    LB_TRY(dev_alloc(&k.g2p, k.g2p_cap));
-    LB_TRY(dev_alloc(&k.ints, (size_t)k.n_int_rows * Gcap));
-    LB_TRY(dev_alloc(&k.flts, (size_t)k.n_flt_rows * Gcap));
-    LB_TRY(dev_alloc(&k.cache, (size_t)(k.n_cache_rows + 1) * Gcap));  // + the all-zero row
+    LB_TRY(pool_alloc(e, &k.counts, Gcap));
+    LB_TRY(pool_alloc(e, &k.shifted, Gcap));
+    LB_TRY(pool_alloc(e, &k.p2g, Gcap));
+    LB_TRY(pool_alloc(e, &k.g2p, k.g2p_cap));
+    LB_TRY(pool_alloc(e, &k.ints, (size_t)k.n_int_rows * Gcap));
+    LB_TRY(pool_alloc(e, &k.flts, (size_t)k.n_flt_rows * Gcap));
+    LB_TRY(pool_alloc(e, &k.cache, (size_t)(k.n_cache_rows + 1) * Gcap));  // + the all-zero row
     LB_CUDA(cudaMemsetAsync(k.counts, 0, 4 * (size_t)Gcap, e->stream));
     LB_CUDA(cudaMemsetAsync(k.shifted, 0, 4 * (size_t)Gcap, e->stream));
     LB_CUDA(cudaMemsetAsync(k.ints, 0, 4 * (size_t)k.n_int_rows * Gcap + 1 - 1, e->stream));
@@ -102,8 +116,10 @@ int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap) {
     return 0;
 }
 
+// Generous initial column capacity: growth is legal at any time but costs a re-stride.
 static int initial_cap(int G) {
-    int cap = 64;
+    int cap = 256;
+    if (const char *env = getenv("LB_INITIAL_GCAP")) cap = std::max(64, atoi(env));  // tests: force growth
     while (cap < 2 * G) cap *= 2;
     return cap;
 }
@@ -184,8 +200,20 @@ int lb_sync_model(Engine *e) {
 int lb_pull_kinds(Engine *e) {
     const int K = (int)e->kinds.size();
     e->h_kinds.resize(K);
-    LB_CUDA(cudaMemcpyAsync(e->h_kinds.data(), e->d_kinds, sizeof(KindDev) * K, cudaMemcpyDeviceToHost, e->stream));
+    // Wait for the stream FIRST: a device-to-host copy into pageable memory blocks inside the
+    // driver until prior work in the stream is done, which stalls other host threads (other
+    // chains) that try to launch meanwhile.  After the wait the copy is immediate; it goes
+    // through a pinned mirror so it stays asynchronous with respect to the driver lock.
     LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (K > e->pinned_kinds_cap) {
+        if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
+        e->pinned_kinds = nullptr;
+        LB_CUDA(cudaHostAlloc((void **)&e->pinned_kinds, sizeof(KindDev) * (size_t)(K + 8), cudaHostAllocDefault));
+        e->pinned_kinds_cap = K + 8;
+    }
+    LB_CUDA(cudaMemcpyAsync(e->pinned_kinds, e->d_kinds, sizeof(KindDev) * K, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    memcpy(e->h_kinds.data(), e->pinned_kinds, sizeof(KindDev) * K);
     for (int kid = 0; kid < K; ++kid) {
         KindHost &k = e->kinds[kid];
         const KindDev &d = e->h_kinds[kid];
@@ -204,8 +232,8 @@ int lb_kind_grow(Engine *e, int kid, int new_cap) {
     nk.sample_size = k.sample_size;
     // keep the id tracker (global ids stay valid): copy p2g / g2p verbatim
     if (nk.g2p_cap < k.g2p_cap) {
-        dev_free(nk.g2p);
-        LB_TRY(dev_alloc(&nk.g2p, k.g2p_cap));
+        pool_free(e, nk.g2p);
+        LB_TRY(pool_alloc(e, &nk.g2p, k.g2p_cap));
         nk.g2p_cap = k.g2p_cap;
     }
     LB_CUDA(cudaMemsetAsync(nk.g2p, 0xFF, 4 * (size_t)nk.g2p_cap, e->stream));
@@ -216,7 +244,7 @@ int lb_kind_grow(Engine *e, int kid, int new_cap) {
     nk.assign = k.assign;
     nk.cache_row_feat = k.cache_row_feat;
     k.cache_row_feat = nullptr;
-    lb_kind_release(k);
+    lb_kind_release(e, k);
     k = nk;
     return 0;
 }
@@ -241,13 +269,21 @@ extern "C" int lb_create(int device, lb_handle *out) {
     LB_CUDA(cudaGetDeviceProperties(&prop, device));
     e->n_sm = prop.multiProcessorCount;
     LB_TRY(dev_alloc(&e->d_flag, 4));
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     *out = e;
     return 0;
 }
 
 static void clear_model(Engine *e) {
     lb_free_proposer(e);
-    for (auto &k : e->kinds) { lb_kind_release(k); dev_free(k.assign); }
+    for (auto &k : e->kinds) { lb_kind_release(e, k); dev_free(k.assign); }
+    if (e->stream) cudaStreamSynchronize(e->stream);
     e->kinds.clear();
     dev_free(e->d_feats); dev_free(e->d_kind_feats); dev_free(e->d_aux);
     e->model_dirty = true;
@@ -260,7 +296,8 @@ extern "C" void lb_destroy(lb_handle h) {
     cudaStreamSynchronize(e->stream);
     clear_model(e);
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
-    dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_prop_scores);
+    if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
+    dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_prop_scores); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);

@@ -46,6 +46,8 @@ struct Engine {
     KindDev *d_kinds = nullptr;
     int d_kinds_cap = 0;
     std::vector<KindDev> h_kinds;
+    KindDev *pinned_kinds = nullptr;   // pinned staging for the device->host status pull
+    int pinned_kinds_cap = 0;
     bool model_dirty = true;
 
     // rows
@@ -59,6 +61,8 @@ struct Engine {
     uint32_t *d_actions = nullptr;
     size_t actions_cap = 0;
     int32_t *d_flag = nullptr;
+    int32_t *d_kind_ids = nullptr;
+    int d_kind_ids_cap = 0;
 
     // hyper prior
     std::vector<float> hp[13];
@@ -116,7 +120,7 @@ inline int spec_cache_rows(const lb_feature_spec &s) {
 int lb_sync_model(Engine *e);                 // upload FeatDev / KindDev if dirty
 int lb_pull_kinds(Engine *e);                 // KindDev -> KindHost dynamic fields
 int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap);
-void lb_kind_release(KindHost &k);
+void lb_kind_release(Engine *e, KindHost &k);
 int lb_kind_layout(Engine *e, KindHost &k, const std::vector<int> &fids);
 int lb_kind_grow(Engine *e, int kid, int new_cap);
 int lb_refresh_kind(Engine *e, int kid);      // rebuild all cached scorers of a kind

@@ -81,9 +81,10 @@ def test_sweep_matches_oracle_by_replay(oracle_abi, cuda_abi):
     assert g.score_data() == pytest.approx(o.score_data(), rel=1e-6)
 
 
-def test_sweep_grows_tables_and_renumbers_ids(oracle_abi, cuda_abi):
+def test_sweep_grows_tables_and_renumbers_ids(oracle_abi, cuda_abi, monkeypatch):
     # many groups: exercises Gcap growth (64 -> 128 -> ...), the >128-group
     # chunked scorer and the global-id renumbering (> 4096 group births)
+    monkeypatch.setenv("LB_INITIAL_GCAP", "64")
     model, rows, _ = mixed(rows=2500, seed=3, alpha=60.0)
     o, g = both(oracle_abi, cuda_abi, model, rows)
     R = rows.n_rows
