@@ -155,7 +155,7 @@ __device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep,
     }
 }
 
-__global__ void __launch_bounds__(SW_THREADS, 1)
+__global__ void __launch_bounds__(SW_THREADS, 2)
 k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const int32_t *kind_feats,
             const float *aux, RowsDev rows, const uint32_t *actions, uint64_t n_actions,
             uint64_t seed, uint64_t offset, int K, int n_empty, uint32_t *dbg_picks,

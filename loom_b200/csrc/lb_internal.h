@@ -20,9 +20,10 @@ struct KindHost {
 };
 
 struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind)
-    int G = 0;
-    uint32_t *ints = nullptr;  // [prop_int_rows][G]
-    double *flts = nullptr;    // [prop_flt_rows][G]
+    int G = 0, pst = 0;        // groups, column stride
+    uint32_t *ints = nullptr;  // [prop_int_rows][pst]
+    double *flts = nullptr;    // [prop_flt_rows][pst]
+    uint32_t *packed = nullptr;  // [R] packed group id of every row in this kind
 };
 
 struct Engine {
@@ -73,6 +74,7 @@ struct Engine {
     int prop_int_rows = 0, prop_flt_rows = 0;
     std::vector<float> prop_scores;  // [F][K]
     float *d_prop_scores = nullptr;
+    FeatDev *d_prop_feats = nullptr;   // all-feature row layout of the proposer tables
 
     uint64_t launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -1,18 +1,694 @@
-// lb_struct.cu -- kind kernel (proposer accumulate, feature x kind scoring,
-// block Pitman-Yor, feature moves) and hyper kernel.  [under construction]
+// lb_struct.cu -- kind kernel and hyper kernel of libloomb200.so.
+//
+//   kind_proposer_score     bulk KindKernel::add_to_kind_proposer (src/kind_kernel.hpp:193-217):
+//                           every assigned row, with ALL its features, into group g_k(row) of
+//                           every kind's all-feature table  [k_prop_accumulate, K4]
+//                           + KindProposer score phase (src/kind_proposer.cc:336-349):
+//                           L[f][k] = sum_g log marginal     [k_prop_score, K5]
+//   kind_run                block Pitman-Yor sampler (src/kind_proposer.cc:269-300, host, tiny)
+//                           + move_features (src/kind_kernel.cc:83-116): moved features take the
+//                           proposer's statistics (src/product_mixture.cc:886-915)
+//   init_featureless_kinds  src/kind_kernel.cc:159-227
+//   hyper_run               HyperKernel::run (src/hyper_kernel.cc:195-235), grid Gibbs
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "lb_internal.h"
+
+#define FULL 0xffffffffu
+
+template <class T> static int dalloc(T **p, size_t n) {
+    *p = nullptr;
+    LB_CUDA(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
 
 void lb_free_proposer(Engine *e) {
     for (auto &p : e->prop) {
         if (p.ints) cudaFree(p.ints);
         if (p.flts) cudaFree(p.flts);
+        if (p.packed) cudaFree(p.packed);
     }
     e->prop.clear();
     e->prop_scores.clear();
+    if (e->d_prop_feats) { cudaFree(e->d_prop_feats); e->d_prop_feats = nullptr; }
 }
 
-extern "C" int lb_kind_proposer_score(lb_handle, float *) { return lb_fail("kind_proposer_score: not built yet"); }
-extern "C" int lb_kind_run(lb_handle, int32_t, uint64_t, uint32_t *, int32_t *) { return lb_fail("kind_run: not built yet"); }
-extern "C" int lb_init_featureless_kinds(lb_handle, int32_t, uint64_t) { return lb_fail("init_featureless_kinds: not built yet"); }
-extern "C" int lb_set_hyper_prior(lb_handle, const lb_hyper_prior *) { return lb_fail("set_hyper_prior: not built yet"); }
-extern "C" int lb_hyper_run(lb_handle, uint64_t) { return lb_fail("hyper_run: not built yet"); }
+// ---------------------------------------------------------------------------
+// K4: proposer accumulate.  grid = (row chunks, F); thread per row.  The
+// all-feature tables are [rows][pst] like the per-kind ones; integer counts
+// are exact atomics, float moments go through double sums.
+// ---------------------------------------------------------------------------
+__global__ void k_pack_assign(const uint32_t *assign, const uint32_t *g2p, uint32_t *packed, uint64_t R) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = assign[r];
+        packed[r] = a == LB_UNASSIGNED ? LB_UNASSIGNED : g2p[a];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_prop_accumulate(const FeatDev *pfeats, RowsDev rows, const uint32_t *packed, uint32_t *ints, double *flts,
+                  int pst) {
+    const int fid = blockIdx.y;
+    const FeatDev &f = pfeats[fid];
+    const uint32_t *mask = rows.mask + (uint64_t)fid * rows.W;
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows.R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = packed[r];
+        if (g == LB_UNASSIGNED) continue;
+        if (!((mask[r >> 5] >> (r & 31)) & 1u)) continue;
+        const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                       : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+        uint32_t *in = ints + (size_t)f.int_row * pst + g;
+        double *fl = flts + (size_t)f.flt_row * pst + g;
+        switch (f.type) {
+        case LB_BB:
+            atomicAdd(&in[raw ? 0 : pst], 1u);
+            break;
+        case LB_DD:
+        case LB_DPD:
+            atomicAdd(&in[(size_t)raw * pst], 1u);
+            atomicAdd(&in[(size_t)f.dim * pst], 1u);
+            break;
+        case LB_GP:
+            atomicAdd(&in[0], 1u);
+            atomicAdd(&in[pst], raw);
+            atomicAdd(&fl[0], lb_log_factorial_d(raw));
+            break;
+        case LB_NICH: {
+            const double x = (double)__uint_as_float(raw);
+            atomicAdd(&in[0], 1u);
+            atomicAdd(&fl[0], x);
+            atomicAdd(&fl[pst], x * x);
+            break;
+        }
+        }
+    }
+}
+
+__global__ void k_prop_sums_to_moments(const FeatDev *pfeats, int F, uint32_t *ints, double *flts, int pst, int G) {
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < F * G; idx += gridDim.x * blockDim.x) {
+        const int fid = idx / G, g = idx % G;
+        const FeatDev &f = pfeats[fid];
+        if (f.type != LB_NICH) continue;
+        double *fl = flts + (size_t)f.flt_row * pst + g;
+        const double n = (double)ints[(size_t)f.int_row * pst + g];
+        if (n == 0.0) { fl[0] = 0.0; fl[pst] = 0.0; }
+        else {
+            const double mean = fl[0] / n;
+            fl[0] = mean;
+            fl[pst] = fmax(fl[pst] - n * mean * mean, 0.0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: L[f][k] = sum over groups of the log marginal likelihood of feature f's
+// statistics in kind k.  One CTA per (f, k); DD/DPD spread (value, group)
+// pairs over the threads, the others one group per thread.
+// ---------------------------------------------------------------------------
+__device__ double lb_marginal_group(const FeatDev &f, const float *aux, const uint32_t *in, const double *fl, int st);
+
+__global__ void __launch_bounds__(256)
+k_prop_score(const FeatDev *pfeats, const float *aux, const uint32_t *ints, const double *flts, int pst,
+             int G, int kid, int K, float *out) {
+    __shared__ double s_red[8];
+    const int fid = blockIdx.x;
+    const FeatDev &f = pfeats[fid];
+    const uint32_t *in = ints + (size_t)f.int_row * pst;
+    const double *fl = flts + (size_t)f.flt_row * pst;
+    double acc = 0;
+    if (f.type == LB_DD || f.type == LB_DPD) {
+        const int total = (f.dim + 1) * G;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int v = idx / G, g = idx % G;
+            const uint32_t n = in[(size_t)v * pst + g];
+            if (!n) continue;
+            if (v < f.dim) acc += (double)lb_lgamma_diff(f.a_scale * aux[f.aux_off + v], (float)n);
+            else acc -= (double)lb_lgamma_diff(f.a_total, (float)n);
+        }
+    } else {
+        for (int g = threadIdx.x; g < G; g += blockDim.x) acc += lb_marginal_group(f, aux, in + g, fl + g, pst);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+        out[(size_t)fid * K + kid] = (float)t;
+    }
+}
+
+// same closed forms as lb_marginal in lb_cat.cu (kept local: no relocatable device code)
+__device__ double lb_marginal_group(const FeatDev &f, const float *aux, const uint32_t *in, const double *fl, int st) {
+    switch (f.type) {
+    case LB_BB: {
+        const float h = (float)in[0], t = (float)in[st];
+        return (double)lb_lgamma_diff(f.hp[0], h) + (double)lb_lgamma_diff(f.hp[1], t) -
+               (double)lb_lgamma_diff(f.hp[0] + f.hp[1], h + t);
+    }
+    case LB_DD:
+    case LB_DPD: {
+        double s = 0;
+        for (int v = 0; v < f.dim; ++v) {
+            const uint32_t n = in[(size_t)v * st];
+            if (n) s += (double)lb_lgamma_diff(f.a_scale * aux[f.aux_off + v], (float)n);
+        }
+        return s - (double)lb_lgamma_diff(f.a_total, (float)in[(size_t)f.dim * st]);
+    }
+    case LB_GP: {
+        const double al = f.hp[0], ib = f.hp[1];
+        const double S = (double)in[st], n = (double)in[0];
+        return (double)lb_lgamma_diff(f.hp[0], (float)in[st]) + al * log(ib) - (al + S) * log(ib + n) - fl[0];
+    }
+    case LB_NICH: {
+        const double mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
+        const double n = (double)in[0], mean = fl[0], ctv = fl[st];
+        const double kn = kappa + n, nun = nu + n, dm = mu - mean;
+        const double sn = (nu * sigmasq + ctv + n * kappa * dm * dm / kn) / nun;
+        return (double)lb_lgamma_diff((float)(0.5 * nu), (float)(0.5 * n)) + 0.5 * log(kappa / kn) +
+               0.5 * nu * log(nu * sigmasq) - 0.5 * nun * log(nun * sn) - 0.5 * n * 1.1447298858494002;
+    }
+    }
+    return 0.0;
+}
+
+// all-feature FeatDev table: rows are laid out feature by feature over ALL F features
+static int build_prop_feats(Engine *e) {
+    const int F = e->F;
+    e->prop_int_off.assign(F, 0);
+    e->prop_flt_off.assign(F, 0);
+    e->prop_int_rows = e->prop_flt_rows = 0;
+    std::vector<FeatDev> pf(F);
+    for (int f = 0; f < F; ++f) {
+        const lb_feature_spec &s = e->specs[f];
+        e->prop_int_off[f] = e->prop_int_rows; e->prop_int_rows += spec_int_rows(s);
+        e->prop_flt_off[f] = e->prop_flt_rows; e->prop_flt_rows += spec_flt_rows(s);
+        FeatDev &fd = pf[f];
+        memset(&fd, 0, sizeof fd);
+        fd.type = s.type; fd.dim = s.dim;
+        for (int i = 0; i < 4; ++i) fd.hp[i] = s.hp[i];
+        fd.aux_off = s.aux_off;
+        fd.is_wide = f >= e->F8;
+        fd.col = fd.is_wide ? f - e->F8 : f;
+        fd.int_row = e->prop_int_off[f]; fd.flt_row = e->prop_flt_off[f]; fd.cache_row = 0;
+        fd.a_total = 0.f; fd.a_scale = 1.f;
+        if (s.type == LB_DD) {
+            double t = 0;
+            for (int v = 0; v < s.dim; ++v) t += e->aux[s.aux_off + v];
+            fd.a_total = (float)t;
+        } else if (s.type == LB_DPD) {
+            fd.a_total = s.hp[1]; fd.a_scale = s.hp[1];
+        }
+    }
+    if (e->d_prop_feats) cudaFree(e->d_prop_feats);
+    LB_TRY(dalloc(&e->d_prop_feats, F));
+    LB_CUDA(cudaMemcpyAsync(e->d_prop_feats, pf.data(), sizeof(FeatDev) * F, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->R) return lb_fail("kind_proposer_score before set_rows");
+    LB_TRY(lb_sync_model(e));
+    lb_free_proposer(e);
+    LB_TRY(build_prop_feats(e));
+    const int F = e->F, K = (int)e->kinds.size();
+    e->prop.resize(K);
+    if (e->d_prop_scores) cudaFree(e->d_prop_scores);
+    LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    const int rgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, 4096));
+    for (int kid = 0; kid < K; ++kid) {
+        const KindHost &k = e->kinds[kid];
+        ProposerKind &p = e->prop[kid];
+        p.G = k.G;
+        p.pst = (k.G + 31) & ~31;
+        LB_TRY(dalloc(&p.ints, (size_t)e->prop_int_rows * p.pst));
+        LB_TRY(dalloc(&p.flts, (size_t)e->prop_flt_rows * p.pst));
+        LB_TRY(dalloc(&p.packed, e->R));
+        LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * (size_t)e->prop_int_rows * p.pst, e->stream));
+        LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * (size_t)e->prop_flt_rows * p.pst, e->stream));
+        k_pack_assign<<<rgrid, 256, 0, e->stream>>>(k.assign, k.g2p, p.packed, e->R);
+        dim3 grid((unsigned)std::min<uint64_t>((e->R + 255) / 256, 1024), (unsigned)F);
+        k_prop_accumulate<<<grid, 256, 0, e->stream>>>(e->d_prop_feats, rows, p.packed, p.ints, p.flts, p.pst);
+        k_prop_sums_to_moments<<<std::max(1, std::min((F * p.G + 255) / 256, 1024)), 256, 0, e->stream>>>(
+            e->d_prop_feats, F, p.ints, p.flts, p.pst, p.G);
+        k_prop_score<<<F, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, p.ints, p.flts, p.pst, p.G, kid, K,
+                                               e->d_prop_scores);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL] += 4; e->launches[LB_L_KIND] += 4;
+    }
+    e->prop_scores.resize((size_t)F * K);
+    LB_CUDA(cudaMemcpyAsync(e->prop_scores.data(), e->d_prop_scores, 4 * (size_t)F * K, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (out) memcpy(out, e->prop_scores.data(), 4 * (size_t)F * K);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// block Pitman-Yor sampler (src/kind_proposer.cc:131-300); F x K is tiny, host
+// ---------------------------------------------------------------------------
+static double likelihood_empty(double alpha, double d, int K, int n_empty) {
+    return n_empty ? (alpha + d * (K - n_empty)) / n_empty : 0.0;
+}
+static int sample_from_likelihoods(double u, const double *p, int n, double total) {
+    double t = u * total, c = 0;
+    int last = 0;
+    for (int i = 0; i < n; ++i) {
+        if (p[i] > 0) last = i;
+        c += p[i];
+        if (c > t) return i;
+    }
+    return last;
+}
+static void block_py(double alpha, double d, int F, int K, const std::vector<double> &lik,
+                     std::vector<uint32_t> &assign, int iterations, uint64_t seed) {
+    std::vector<uint32_t> counts(K, 0);
+    std::vector<double> prior(K), post(K);
+    int n_empty = 0;
+    for (int f = 0; f < F; ++f) counts[assign[f]]++;
+    for (int k = 0; k < K; ++k) if (!counts[k]) ++n_empty;
+    for (int k = 0; k < K; ++k) prior[k] = counts[k] ? counts[k] - d : likelihood_empty(alpha, d, K, n_empty);
+    for (int it = 0; it < iterations; ++it)
+        for (int f = 0; f < F; ++f) {
+            int k = (int)assign[f];
+            if (--counts[k] == 0) {
+                ++n_empty;
+                const double le = likelihood_empty(alpha, d, K, n_empty);
+                for (int j = 0; j < K; ++j) if (!counts[j]) prior[j] = le;
+            } else prior[k] = counts[k] - d;
+            double total = 0;
+            for (int j = 0; j < K; ++j) total += post[j] = prior[j] * lik[(size_t)f * K + j];
+            const double u = (double)lb_uniform(seed, 1u, (uint64_t)it * F + f, 0u);
+            k = sample_from_likelihoods(u, post.data(), K, total);
+            assign[f] = (uint32_t)k;
+            if (counts[k]++ == 0) {
+                --n_empty;
+                const double le = likelihood_empty(alpha, d, K, n_empty);
+                for (int j = 0; j < K; ++j) if (!counts[j]) prior[j] = le;
+            }
+            prior[k] = counts[k] - d;
+        }
+}
+
+// copy `rows` table rows [.][G] between tables of different strides
+template <class T>
+__global__ void k_copy_rows(const T *src, int src_row, int src_st, T *dst, int dst_row, int dst_st, int rows, int G) {
+    const int total = rows * G;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int r = idx / G, g = idx % G;
+        dst[(size_t)(dst_row + r) * dst_st + g] = src[(size_t)(src_row + r) * src_st + g];
+    }
+}
+
+// move_features: rebuild kind `kid`'s tables for the new feature list
+static int kind_relayout(Engine *e, int kid, const std::vector<int> &fids) {
+    KindHost &k = e->kinds[kid];
+    KindHost nk;
+    nk.alpha = k.alpha; nk.d = k.d;
+    LB_TRY(lb_kind_layout(e, nk, fids));
+    LB_TRY(lb_kind_alloc(e, nk, k.G, k.Gcap));
+    nk.sample_size = k.sample_size;
+    // clustering state and the id tracker carry over unchanged
+    LB_CUDA(cudaMemcpyAsync(nk.counts, k.counts, 4 * (size_t)k.Gcap, cudaMemcpyDeviceToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(nk.shifted, k.shifted, 4 * (size_t)k.Gcap, cudaMemcpyDeviceToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(nk.p2g, k.p2g, 4 * (size_t)k.Gcap, cudaMemcpyDeviceToDevice, e->stream));
+    if (nk.g2p_cap != k.g2p_cap) {
+        cudaFreeAsync(nk.g2p, e->stream);
+        LB_CUDA(cudaMallocAsync((void **)&nk.g2p, 4 * (size_t)k.g2p_cap, e->stream));
+        nk.g2p_cap = k.g2p_cap;
+    }
+    LB_CUDA(cudaMemcpyAsync(nk.g2p, k.g2p, 4 * (size_t)k.g2p_cap, cudaMemcpyDeviceToDevice, e->stream));
+    nk.next_global = k.next_global;
+    const ProposerKind &p = e->prop[kid];
+    const int G = k.G;
+    for (size_t j = 0; j < fids.size(); ++j) {
+        const int f = fids[j];
+        const lb_feature_spec &s = e->specs[f];
+        int oj = -1;
+        for (size_t q = 0; q < k.fids.size(); ++q) if (k.fids[q] == f) oj = (int)q;
+        const int ir = spec_int_rows(s), fr = spec_flt_rows(s);
+        const int grid = std::max(1, std::min((ir * G + 255) / 256, 256));
+        if (oj >= 0) {
+            k_copy_rows<uint32_t><<<grid, 256, 0, e->stream>>>(k.ints, k.int_off[oj], k.Gcap, nk.ints, nk.int_off[j], nk.Gcap, ir, G);
+            if (fr) k_copy_rows<double><<<1, 256, 0, e->stream>>>(k.flts, k.flt_off[oj], k.Gcap, nk.flts, nk.flt_off[j], nk.Gcap, fr, G);
+        } else {
+            k_copy_rows<uint32_t><<<grid, 256, 0, e->stream>>>(p.ints, e->prop_int_off[f], p.pst, nk.ints, nk.int_off[j], nk.Gcap, ir, G);
+            if (fr) k_copy_rows<double><<<1, 256, 0, e->stream>>>(p.flts, e->prop_flt_off[f], p.pst, nk.flts, nk.flt_off[j], nk.Gcap, fr, G);
+        }
+        e->launches[LB_L_TOTAL] += fr ? 2 : 1; e->launches[LB_L_KIND] += fr ? 2 : 1;
+    }
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    nk.assign = k.assign;
+    lb_kind_release(e, k);
+    k = nk;
+    return 0;
+}
+
+extern "C" int lb_kind_run(lb_handle h, int32_t iterations, uint64_t seed, uint32_t *new_f2k, int32_t *n_changed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (iterations <= 0) return lb_fail("kind_run: iterations must be > 0");
+    const int F = e->F, K = (int)e->kinds.size();
+    if (e->prop_scores.size() != (size_t)F * K || (int)e->prop.size() != K)
+        return lb_fail("kind_run: call kind_proposer_score first");
+    for (int k = 0; k < K; ++k)
+        if (e->prop[k].G != e->kinds[k].G) return lb_fail("kind_run: stale proposer tables");
+    std::vector<double> lik((size_t)F * K);
+    for (int f = 0; f < F; ++f) {  // scores_to_likelihoods (kind_proposer.cc:347)
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) m = std::max(m, e->prop_scores[(size_t)f * K + k]);
+        for (int k = 0; k < K; ++k) lik[(size_t)f * K + k] = std::exp((double)e->prop_scores[(size_t)f * K + k] - (double)m);
+    }
+    std::vector<uint32_t> assign(e->f2k);
+    block_py(e->topo[0], e->topo[1], F, K, lik, assign, iterations, seed);
+    int changed = 0;
+    for (int f = 0; f < F; ++f) if (assign[f] != e->f2k[f]) ++changed;
+    for (int k = 0; k < K; ++k) {
+        std::vector<int> fids;
+        for (int f = 0; f < F; ++f) if (assign[f] == (uint32_t)k) fids.push_back(f);
+        if (fids != e->kinds[k].fids) LB_TRY(kind_relayout(e, k, fids));
+    }
+    e->f2k = assign;
+    e->model_dirty = true;
+    LB_TRY(lb_sync_model(e));
+    for (int k = 0; k < K; ++k) LB_TRY(lb_launch_refresh(e, k));   // init_cache (kind_kernel.cc:257-315)
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (new_f2k) memcpy(new_f2k, assign.data(), 4 * (size_t)F);
+    if (n_changed) *n_changed = changed;
+    lb_free_proposer(e);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// init_featureless_kinds (src/kind_kernel.cc:159-227).  The Pitman-Yor prior
+// partition of the assigned rows is a sequential seating process
+// (Clustering::PitmanYor::sample_assignments); it is drawn on the host in the
+// same float64 arithmetic as the oracle and uploaded.
+// ---------------------------------------------------------------------------
+extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t seed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    lb_free_proposer(e);
+    for (int i = (int)e->kinds.size() - 1; i >= 0; --i) {
+        if (!e->kinds[i].fids.empty()) continue;
+        if (e->kinds.size() == 1) return lb_fail("cannot remove the only kind");
+        lb_kind_release(e, e->kinds[i]);
+        if (e->kinds[i].assign) cudaFree(e->kinds[i].assign);
+        const int last = (int)e->kinds.size() - 1;
+        if (i != last) {   // remove_featureless_kind: packed_remove + patch featureid_to_kindid
+            e->kinds[i] = e->kinds[last];
+            for (int f : e->kinds[i].fids) e->f2k[f] = (uint32_t)i;
+        }
+        e->kinds.pop_back();
+    }
+    std::vector<uint32_t> a0;
+    if (count > 0 && e->R) {
+        a0.resize(e->R);
+        LB_CUDA(cudaMemcpyAsync(a0.data(), e->kinds[0].assign, 4 * (size_t)e->R, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    const std::vector<float> &grid = e->hp[1];   // clustering grid [n][2]
+    for (int c = 0; c < count; ++c) {
+        const int kid = (int)e->kinds.size();
+        e->kinds.emplace_back();
+        KindHost &k = e->kinds.back();
+        k.alpha = e->kinds[0].alpha; k.d = e->kinds[0].d;
+        if (!grid.empty()) {   // sample_clustering_prior (infer_grid.hpp:127-139)
+            const int n = (int)grid.size() / 2;
+            const double u = (double)lb_uniform(seed, 3u, 0xFFFFFFFFFFFFFFFFull, (uint32_t)kid);
+            int i = (int)(u * n);
+            if (i >= n) i = n - 1;
+            k.alpha = grid[2 * i]; k.d = grid[2 * i + 1];
+        }
+        const double alpha = k.alpha, d = k.d;
+        std::vector<uint32_t> pick(e->R, LB_UNASSIGNED), counts;
+        std::vector<double> p;
+        int m = 0;
+        for (uint64_t r = 0; r < e->R; ++r) {
+            if (a0[r] == LB_UNASSIGNED) continue;
+            p.resize(m + 1);
+            double total = 0;
+            for (int g = 0; g < m; ++g) total += p[g] = counts[g] - d;
+            total += p[m] = alpha + d * m;
+            const double u = (double)lb_uniform(seed, 3u, r, (uint32_t)kid);
+            const int g = sample_from_likelihoods(u, p.data(), m + 1, total);
+            if (g == m) { counts.push_back(0); ++m; }
+            counts[g]++;
+            pick[r] = (uint32_t)g;
+        }
+        const int G = m + e->empty_group_count;
+        LB_TRY(lb_kind_layout(e, k, std::vector<int>()));
+        int cap = 256;
+        while (cap < 2 * G) cap *= 2;
+        LB_TRY(lb_kind_alloc(e, k, G, cap));
+        uint64_t total = 0;
+        for (int g = 0; g < m; ++g) total += counts[g];
+        k.sample_size = total;
+        if (m) LB_CUDA(cudaMemcpyAsync(k.counts, counts.data(), 4 * (size_t)m, cudaMemcpyHostToDevice, e->stream));
+        LB_TRY(dalloc(&k.assign, e->R));
+        if (e->R) LB_CUDA(cudaMemcpyAsync(k.assign, pick.data(), 4 * (size_t)e->R, cudaMemcpyHostToDevice, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    e->model_dirty = true;
+    LB_TRY(lb_sync_model(e));
+    for (int kid = 0; kid < (int)e->kinds.size(); ++kid)
+        if (e->kinds[kid].fids.empty()) LB_TRY(lb_launch_refresh(e, kid));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// hyper kernel
+// ---------------------------------------------------------------------------
+extern "C" int lb_set_hyper_prior(lb_handle h, const lb_hyper_prior *pr) {
+    Engine *e = (Engine *)h;
+    for (auto &v : e->hp) v.clear();
+    if (!pr) return 0;
+    auto put = [&](int i, const float *p, int n, int mult) { if (n > 0) e->hp[i].assign(p, p + (size_t)n * mult); };
+    put(0, pr->topology, pr->n_topology, 2); put(1, pr->clustering, pr->n_clustering, 2);
+    put(2, pr->bb_alpha, pr->n_bb_alpha, 1); put(3, pr->bb_beta, pr->n_bb_beta, 1);
+    put(4, pr->dd_alpha, pr->n_dd_alpha, 1);
+    put(5, pr->dpd_gamma, pr->n_dpd_gamma, 1); put(6, pr->dpd_alpha, pr->n_dpd_alpha, 1);
+    put(7, pr->gp_alpha, pr->n_gp_alpha, 1); put(8, pr->gp_inv_beta, pr->n_gp_inv_beta, 1);
+    put(9, pr->nich_mu, pr->n_nich_mu, 1); put(10, pr->nich_kappa, pr->n_nich_kappa, 1);
+    put(11, pr->nich_sigmasq, pr->n_nich_sigmasq, 1); put(12, pr->nich_nu, pr->n_nich_nu, 1);
+    return 0;
+}
+
+// Pitman-Yor score_counts in float64, host: the count vectors are tiny
+static double py_score_counts(double alpha, double d, const uint32_t *counts, int n) {
+    double score = 0, total = 0;
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (counts[i]) {
+            score += std::log(alpha + d * m);
+            score += std::lgamma(counts[i] - d) - std::lgamma(1.0 - d);
+            total += counts[i];
+            ++m;
+        }
+    return score + std::lgamma(alpha) - std::lgamma(alpha + total);
+}
+static int sample_from_scores(double u, std::vector<double> &s) {
+    double m = -INFINITY, total = 0;
+    for (double v : s) m = std::max(m, v);
+    for (double &v : s) { v = std::exp(v - m); total += v; }
+    return sample_from_likelihoods(u, s.data(), (int)s.size(), total);
+}
+static void sample_py_posterior(const std::vector<float> &grid, const uint32_t *counts, int nc, uint64_t seed,
+                                uint64_t task, float *alpha, float *d) {
+    const int n = (int)grid.size() / 2;
+    if (n <= 0) return;
+    int i = 0;
+    if (n > 1) {
+        std::vector<double> scores(n);
+        for (int j = 0; j < n; ++j) scores[j] = py_score_counts(grid[2 * j], grid[2 * j + 1], counts, nc);
+        i = sample_from_scores((double)lb_uniform(seed, 2u, task, 0u), scores);
+    }
+    *alpha = grid[2 * i]; *d = grid[2 * i + 1];
+}
+
+// Feature-hyper grid Gibbs, one CTA per feature (task 1 + K + f of HyperKernel::run).
+// For every coordinate in the order of src/hyper_prior.hpp:38-146 the block scores each
+// grid value j by sum_g log marginal(group g | shared with coord := grid[j])
+// (InferShared::done, src/infer_grid.hpp:73-89), draws j and commits it.  DD evaluates only
+// the terms that depend on the coordinate (the rest is constant in j and cancels in the draw).
+struct HyperGrids {
+    const float *g[13];
+    int n[13];
+};
+
+__device__ double hyper_block_sum(double v, double *s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_hyper_features(const KindDev *kinds, FeatDev *feats, const uint32_t *f2k, float *aux, HyperGrids hg,
+                 uint64_t seed, int K) {
+    __shared__ double s_red[8];
+    __shared__ double s_scores[256];
+    __shared__ int s_pick;
+    const int fid = blockIdx.x;
+    FeatDev f = feats[fid];
+    const KindDev &kd = kinds[f2k[fid]];
+    const int G = kd.G, st = kd.Gcap;
+    const uint32_t *in = kd.ints + (size_t)f.int_row * st;
+    const double *fl = kd.flts + (size_t)f.flt_row * st;
+    const uint64_t task = 1ull + (uint64_t)K + (uint64_t)fid;
+    uint32_t draw = 0;
+
+    auto choose = [&](int n) -> int {   // softmax draw over s_scores[0..n), float64 like the oracle
+        if (threadIdx.x == 0) {
+            double m = -INFINITY, total = 0;
+            for (int j = 0; j < n; ++j) m = fmax(m, s_scores[j]);
+            for (int j = 0; j < n; ++j) { s_scores[j] = exp(s_scores[j] - m); total += s_scores[j]; }
+            const double t = (double)lb_uniform(seed, 2u, task, draw) * total;
+            double c = 0;
+            int pick = 0, last = 0;
+            bool found = false;
+            for (int j = 0; j < n && !found; ++j) {
+                if (s_scores[j] > 0) last = j;
+                c += s_scores[j];
+                if (c > t) { pick = j; found = true; }
+            }
+            s_pick = found ? pick : last;
+        }
+        __syncthreads();
+        return s_pick;
+    };
+
+    if (f.type == LB_BB || f.type == LB_GP || f.type == LB_NICH) {
+        const int first = f.type == LB_BB ? 2 : (f.type == LB_GP ? 7 : 9);
+        const int ncoord = f.type == LB_NICH ? 4 : 2;
+        for (int c = 0; c < ncoord; ++c) {
+            const int n = hg.n[first + c];
+            const float *grid = hg.g[first + c];
+            if (n <= 0) continue;
+            if (n == 1) { f.hp[c] = grid[0]; continue; }
+            for (int j0 = 0; j0 < n; j0 += 256) {
+                const int nj = min(256, n - j0);
+                for (int j = 0; j < nj; ++j) {
+                    FeatDev t = f;
+                    t.hp[c] = grid[j0 + j];
+                    double acc = 0;
+                    for (int g = threadIdx.x; g < G; g += blockDim.x) acc += lb_marginal_group(t, aux, in + g, fl + g, st);
+                    const double tot = hyper_block_sum(acc, s_red);
+                    if (threadIdx.x == 0) s_scores[j] = tot;
+                }
+                __syncthreads();
+                if (n > 256) break;   // grids larger than 256 points are not supported (default max is 201)
+            }
+            const int pick = choose(min(n, 256));
+            ++draw;
+            f.hp[c] = grid[pick];
+            __syncthreads();
+        }
+    } else if (f.type == LB_DD) {
+        const int n = hg.n[4];
+        const float *grid = hg.g[4];
+        if (n == 1) {
+            for (int v = threadIdx.x; v < f.dim; v += blockDim.x) aux[f.aux_off + v] = grid[0];
+        } else if (n > 1) {
+            // running total of the alphas in float64, in index order like the oracle's sum
+            for (int v = 0; v < f.dim; ++v) {
+                double a_rest = 0;
+                for (int w = 0; w < f.dim; ++w) if (w != v) a_rest += (double)aux[f.aux_off + w];
+                for (int j = 0; j < n && j < 256; ++j) {
+                    const float a_v = grid[j];
+                    const float a_tot = (float)(a_rest + (double)a_v);
+                    double acc = 0;
+                    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                        const uint32_t nv = in[(size_t)v * st + g], nt = in[(size_t)f.dim * st + g];
+                        if (nv) acc += (double)lb_lgamma_diff(a_v, (float)nv);
+                        if (nt) acc -= (double)lb_lgamma_diff(a_tot, (float)nt);
+                    }
+                    const double tot = hyper_block_sum(acc, s_red);
+                    if (threadIdx.x == 0) s_scores[j] = tot;
+                }
+                __syncthreads();
+                const int pick = choose(min(n, 256));
+                ++draw;
+                if (threadIdx.x == 0) aux[f.aux_off + v] = grid[pick];
+                __syncthreads();
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 4; ++c) feats[fid].hp[c] = f.hp[c];
+    }
+}
+
+extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    LB_TRY(lb_sync_model(e));
+    const int K = (int)e->kinds.size(), F = e->F;
+    // task 0: topology; tasks 1..K: per-kind clustering (host, float64: tiny count vectors)
+    if (!e->hp[0].empty()) {
+        std::vector<uint32_t> fc(K);
+        for (int k = 0; k < K; ++k) fc[k] = (uint32_t)e->kinds[k].fids.size();
+        sample_py_posterior(e->hp[0], fc.data(), K, seed, 0, &e->topo[0], &e->topo[1]);
+    }
+    if (!e->hp[1].empty()) {
+        for (int k = 0; k < K; ++k) {
+            KindHost &kh = e->kinds[k];
+            std::vector<uint32_t> counts(kh.G);
+            LB_CUDA(cudaMemcpyAsync(counts.data(), kh.counts, 4 * (size_t)kh.G, cudaMemcpyDeviceToHost, e->stream));
+            LB_CUDA(cudaStreamSynchronize(e->stream));
+            sample_py_posterior(e->hp[1], counts.data(), kh.G, seed, (uint64_t)(1 + k), &kh.alpha, &kh.d);
+        }
+    }
+    // tasks 1+K..: per-feature grids on the device
+    bool any = false;
+    for (int i = 2; i < 13; ++i) if (!e->hp[i].empty()) any = true;
+    if (any) {
+        HyperGrids hg;
+        size_t total = 0;
+        for (int i = 0; i < 13; ++i) total += e->hp[i].size();
+        std::vector<float> flat(total + 1);
+        float *d_flat = nullptr;
+        LB_TRY(dalloc(&d_flat, total + 1));
+        size_t off = 0;
+        for (int i = 0; i < 13; ++i) {
+            hg.g[i] = d_flat + off;
+            hg.n[i] = (int)e->hp[i].size() / (i < 2 ? 2 : 1);
+            std::copy(e->hp[i].begin(), e->hp[i].end(), flat.begin() + off);
+            off += e->hp[i].size();
+        }
+        LB_CUDA(cudaMemcpyAsync(d_flat, flat.data(), 4 * (total + 1), cudaMemcpyHostToDevice, e->stream));
+        uint32_t *d_f2k = nullptr;
+        LB_TRY(dalloc(&d_f2k, F));
+        LB_CUDA(cudaMemcpyAsync(d_f2k, e->f2k.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, e->stream));
+        k_hyper_features<<<F, 256, 0, e->stream>>>(e->d_kinds, e->d_feats, d_f2k, e->d_aux, hg, seed, K);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_HYPER]++;
+        // pull the chosen hypers back into the host mirror
+        std::vector<FeatDev> feats(F);
+        LB_CUDA(cudaMemcpyAsync(feats.data(), e->d_feats, sizeof(FeatDev) * F, cudaMemcpyDeviceToHost, e->stream));
+        if (!e->aux.empty())
+            LB_CUDA(cudaMemcpyAsync(e->aux.data(), e->d_aux, 4 * e->aux.size(), cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+        for (int f = 0; f < F; ++f)
+            for (int c = 0; c < 4; ++c) e->specs[f].hp[c] = feats[f].hp[c];
+        cudaFree(d_flat);
+        cudaFree(d_f2k);
+    }
+    e->model_dirty = true;   // derived fields (a_total, ...) and cached scorers depend on the hypers
+    LB_TRY(lb_sync_model(e));
+    for (int k = 0; k < K; ++k) LB_TRY(lb_launch_refresh(e, k));   // mixture.init(shared)
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
