@@ -26,8 +26,8 @@ roofline= the dominant kernel (k_cat_sweep): algorithmic bytes per launch
 samples : the exact Gibbs chain of one kind is sequential, so one chain keeps only
           K (=7) of the 148 SMs busy.  loom itself runs `sample_count` independent
           chains per dataset in parallel processes (loom/tasks.py:173-194, default 10);
-          the GPU runs floor(148 / K) = 21 of them concurrently, one CTA per
-          (chain, kind), each chain its own engine + stream behind the same C ABI.
+          the GPU runs 2 * floor(148 / K) = 42 of them concurrently (two CTAs per SM),
+          one CTA per (chain, kind), each chain its own engine + stream behind the same C ABI.
           `value` is the aggregate over those chains ("config.samples"); the
           single-chain rate is in "rates".  The reference arm gets the same treatment:
           as many chains in parallel as the host cores allow.
@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override the row count (parity runs only)")
     ap.add_argument("--ref-rows", type=int, default=20000)
     ap.add_argument("--samples", type=int, default=0,
-                    help="independent chains run concurrently per GPU (0 = floor(#SM / #kinds))")
+                    help="independent chains run concurrently per GPU (0 = 2 * floor(#SM / #kinds))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -279,7 +279,7 @@ def main():
     cells_per_step = 4 * n_obs
     first, drain = step_actions(R)
 
-    n_chains = args.samples or max(1, 148 // model.n_kinds)
+    n_chains = args.samples or max(1, 2 * (148 // model.n_kinds))   # 2 CTAs per SM (124 registers)
     config["samples"] = n_chains
     config["parallelism"] = "%d independent chains x %d kinds per GPU, one CTA per (chain, kind)%s" % (
         n_chains, model.n_kinds, "; replicas x%d" % world if world > 1 else "")

@@ -1,0 +1,164 @@
+// loom_b200.hpp -- C++ shell that re-hosts loom's engine classes on the C ABI of
+// include/loom_b200.h.  Header only; link with -lloomb200.
+//
+// Class and method names follow the reference so a loom maintainer can swap
+// the bodies of src/cat_kernel.hpp, src/kind_kernel.{hpp,cc} and
+// src/hyper_kernel.{hpp,cc} for these calls:
+//   loom::CrossCat        src/cross_cat.hpp:43-75      -> b200::CrossCat (device-resident state)
+//   loom::CatKernel       src/cat_kernel.hpp:41-103    -> b200::CatKernel
+//   loom::KindKernel      src/kind_kernel.hpp:41-124   -> b200::KindKernel
+//   loom::HyperKernel     src/hyper_kernel.hpp:43-111  -> b200::HyperKernel
+// Errors follow loom's convention: message to stderr + abort()
+// (LOOM_ERROR, src/common.hpp:52-59); there are no return codes across this API.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/loom_b200.h"
+
+namespace loom {
+namespace b200 {
+
+#define LOOM_B200_CHECK(expr)                                                              \
+    do {                                                                                   \
+        if ((expr) != 0) {                                                                 \
+            std::fprintf(stderr, "ERROR %s\n\t%s : %d\n\t%s\n", lb_last_error(), __FILE__, \
+                         __LINE__, __func__);                                              \
+            std::abort();                                                                  \
+        }                                                                                  \
+    } while (0)
+
+// One batch of rows, already split into typed columns (the product of loom's unzip /
+// parse / ValueSplitter::split stages, src/cat_pipeline.cc:63-87).
+struct RowBlock {
+    uint64_t row_count = 0;
+    std::vector<uint8_t> cat8;    // [F8][R]
+    std::vector<uint32_t> wide;   // [FW][R]
+    std::vector<uint32_t> mask;   // [F][ceil(R/32)]
+};
+
+class CrossCat {
+public:
+    explicit CrossCat(int device = 0) { LOOM_B200_CHECK(lb_create(device, &handle_)); }
+    ~CrossCat() { lb_destroy(handle_); }
+    CrossCat(const CrossCat &) = delete;
+    CrossCat &operator=(const CrossCat &) = delete;
+
+    // CrossCat::model_load + mixture_init_unobserved (src/cross_cat.cc:50-120)
+    void model_load(const std::vector<lb_feature_spec> &features, const std::vector<float> &aux,
+                    const std::vector<uint32_t> &featureid_to_kindid, const std::vector<float> &kind_py,
+                    const float topology_py[2], int empty_group_count = 1) {
+        feature_count_ = (int)features.size();
+        LOOM_B200_CHECK(lb_set_model(handle_, (int32_t)features.size(), features.data(), aux.data(),
+                                     (int32_t)aux.size(), (int32_t)(kind_py.size() / 2),
+                                     featureid_to_kindid.data(), kind_py.data(), topology_py,
+                                     empty_group_count));
+    }
+    void rows_load(const RowBlock &rows) {
+        row_count_ = rows.row_count;
+        LOOM_B200_CHECK(lb_set_rows(handle_, rows.row_count, rows.cat8.data(), rows.wide.data(), rows.mask.data()));
+    }
+    // CrossCat::score_data (src/cross_cat.cc:238-250)
+    float score_data() const {
+        double s = 0;
+        LOOM_B200_CHECK(lb_score_data(handle_, &s));
+        return (float)s;
+    }
+    size_t kind_count() const {
+        int32_t k = 0;
+        LOOM_B200_CHECK(lb_get_kinds(handle_, &k, nullptr));
+        return (size_t)k;
+    }
+    std::vector<uint32_t> featureid_to_kindid() const {
+        std::vector<uint32_t> f2k(feature_count_);
+        int32_t k = 0;
+        LOOM_B200_CHECK(lb_get_kinds(handle_, &k, f2k.data()));
+        return f2k;
+    }
+    // Assignments::groupids(kind) as packed ids (src/assignments.hpp:108-111)
+    std::vector<uint32_t> groupids(size_t kindid) const {
+        std::vector<uint32_t> out(row_count_);
+        LOOM_B200_CHECK(lb_get_assignments(handle_, (int32_t)kindid, out.data()));
+        return out;
+    }
+    // ProductMixture::score_value for a batch of rows (src/product_mixture.cc:421-434)
+    std::vector<float> score_rows(size_t kindid, uint64_t row_begin, uint64_t row_end) const {
+        lb_kind_info_t info;
+        LOOM_B200_CHECK(lb_kind_info(handle_, (int32_t)kindid, &info));
+        std::vector<float> out((size_t)(row_end - row_begin) * info.n_groups);
+        LOOM_B200_CHECK(lb_score_rows(handle_, (int32_t)kindid, row_begin, row_end, out.data()));
+        return out;
+    }
+    lb_handle handle() const { return handle_; }
+    uint64_t row_count() const { return row_count_; }
+
+private:
+    lb_handle handle_ = nullptr;
+    int feature_count_ = 0;
+    uint64_t row_count_ = 0;
+};
+
+// CatKernel (src/cat_kernel.hpp:41-103).  Rows are addressed by their position in the loaded
+// block; add_row / remove_row queue actions and flush() runs them in order on the device,
+// which is what CatPipeline's ring buffer does with threads (src/cat_pipeline.cc:103-125).
+class CatKernel {
+public:
+    CatKernel(CrossCat &cross_cat, uint64_t seed) : cross_cat_(cross_cat), seed_(seed) {}
+    void add_row(uint64_t row_position) { actions_.push_back(LB_ACTION_ADD(row_position)); }
+    void remove_row(uint64_t row_position) { actions_.push_back(LB_ACTION_REMOVE(row_position)); }
+    // pipeline.wait() (src/loom.cc:425-429)
+    void wait() {
+        if (actions_.empty()) return;
+        LOOM_B200_CHECK(lb_cat_sweep(cross_cat_.handle(), actions_.data(), actions_.size(), seed_, offset_,
+                                     nullptr, nullptr, nullptr, 0));
+        offset_ += actions_.size();
+        actions_.clear();
+    }
+
+private:
+    CrossCat &cross_cat_;
+    uint64_t seed_, offset_ = 0;
+    std::vector<uint32_t> actions_;
+};
+
+// KindKernel (src/kind_kernel.hpp:41-124): the cat sweep runs over real + ephemeral kinds;
+// try_run scores every feature against every kind and re-assigns features.
+class KindKernel {
+public:
+    KindKernel(CrossCat &cross_cat, int empty_kind_count, int iterations, uint64_t seed)
+        : cross_cat_(cross_cat), empty_kind_count_(empty_kind_count), iterations_(iterations), seed_(seed) {
+        LOOM_B200_CHECK(lb_init_featureless_kinds(cross_cat_.handle(), empty_kind_count_, next_seed()));
+    }
+    ~KindKernel() { lb_init_featureless_kinds(cross_cat_.handle(), 0, 0); }  // kind_kernel.cc:75-81
+    // KindKernel::try_run (src/kind_kernel.cc:118-157); returns true when a feature moved
+    bool try_run() {
+        LOOM_B200_CHECK(lb_kind_proposer_score(cross_cat_.handle(), nullptr));
+        int32_t changed = 0;
+        LOOM_B200_CHECK(lb_kind_run(cross_cat_.handle(), iterations_, next_seed(), nullptr, &changed));
+        LOOM_B200_CHECK(lb_init_featureless_kinds(cross_cat_.handle(), empty_kind_count_, next_seed()));
+        return changed > 0;
+    }
+
+private:
+    uint64_t next_seed() { return seed_ * 0x9E3779B97F4A7C15ull + (++calls_); }
+    CrossCat &cross_cat_;
+    int empty_kind_count_, iterations_;
+    uint64_t seed_, calls_ = 0;
+};
+
+// HyperKernel (src/hyper_kernel.hpp:43-111)
+class HyperKernel {
+public:
+    HyperKernel(CrossCat &cross_cat, const lb_hyper_prior &prior) : cross_cat_(cross_cat) {
+        LOOM_B200_CHECK(lb_set_hyper_prior(cross_cat_.handle(), &prior));
+    }
+    void run(uint64_t seed) { LOOM_B200_CHECK(lb_hyper_run(cross_cat_.handle(), seed)); }
+
+private:
+    CrossCat &cross_cat_;
+};
+
+}  // namespace b200
+}  // namespace loom

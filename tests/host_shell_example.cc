@@ -1,0 +1,23 @@
+// Compile-and-link check of the C++ host shell (run only where a GPU exists).
+#include <cstring>
+#include "../loom_b200/host/loom_b200.hpp"
+
+int main(int argc, char **argv) {
+    if (argc < 2 || std::strcmp(argv[1], "run") != 0) return 0;  // link check only
+    using namespace loom::b200;
+    CrossCat cross_cat(0);
+    std::vector<lb_feature_spec> feats(2);
+    for (auto &f : feats) { f.type = LB_BB; f.dim = 0; f.hp[0] = 0.5f; f.hp[1] = 0.5f; f.aux_off = 0; }
+    const float topo[2] = {2.f, 0.1f};
+    cross_cat.model_load(feats, {0.f}, {0, 0}, {2.f, 0.1f}, topo);
+    RowBlock rows;
+    rows.row_count = 64;
+    rows.cat8.assign(2 * 64, 1);
+    rows.mask.assign(2 * 2, 0xFFFFFFFFu);
+    cross_cat.rows_load(rows);
+    CatKernel cat(cross_cat, 1);
+    for (uint64_t r = 0; r < 64; ++r) cat.add_row(r);
+    cat.wait();
+    std::printf("score %f kinds %zu\n", cross_cat.score_data(), cross_cat.kind_count());
+    return 0;
+}

@@ -43,3 +43,15 @@ def test_no_device_is_an_error_not_a_fallback():
     h = ctypes.c_void_p()
     assert abi.create(0, ctypes.byref(h)) != 0
     assert b"no CPU fallback" in abi.last_error()
+
+
+def test_cpp_host_shell_compiles_and_links(tmp_path):
+    """The C++ shell with loom's class names (loom_b200/host/loom_b200.hpp) builds against the library."""
+    import subprocess
+    test_cuda_library_exports_every_symbol()
+    exe = tmp_path / "host_shell_example"
+    csrc = os.path.join(REPO, "loom_b200", "csrc")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", os.path.join(REPO, "tests", "host_shell_example.cc"),
+                           "-o", str(exe), "-L" + csrc, "-lloomb200", "-Wl,-rpath," + csrc,
+                           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    subprocess.check_call([str(exe)])   # without "run": link check only
