@@ -449,6 +449,23 @@ def main():
         aux["k2_accumulate_rows"] = {"ms": ms2, "cells_per_s": n_obs / (ms2 * 1e-3),
                                      "achieved": in_all / (ms2 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": in_all / (ms2 * 1e-3) / 1e9 / peak, "bound": "hbm"}
+        # kind kernel on the same rows: 32 ephemeral kinds (loom/config.py:55-61), bulk proposer
+        # accumulate (K4) + feature x kind marginal-likelihood table (K5); one feature-score =
+        # one (feature, kind) entry of KindProposer's score phase (src/kind_proposer.cc:339-346)
+        e.init_featureless_kinds(32, seed=11)
+        Kk = e.n_kinds()
+        e.kind_proposer_score(fetch=False)      # warm-up (allocations)
+        e.sync()
+        reps = 3
+        e.timer_start()
+        for _ in range(reps):
+            e.kind_proposer_score(fetch=False)
+        msk = e.timer_stop() / reps
+        aux["kind_kernel"] = {"kinds": Kk, "features": model.n_features, "ms": msk,
+                              "feature_scores_per_s": model.n_features * Kk / (msk * 1e-3),
+                              "proposer_cells_per_s": n_obs * Kk / (msk * 1e-3),
+                              "note": "K4 accumulate of every row into every kind + K5 scoring, per proposal round"}
+        e.init_featureless_kinds(0, seed=12)
         e.cat_sweep(drain, seed=9)
     except Exception as exc:  # the auxiliary numbers never mask the headline
         aux["error"] = str(exc)

@@ -12,6 +12,9 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstddef>
+
+#include "lb_accum.cuh"
 #include "lb_internal.h"
 
 #define FULL 0xffffffffu
@@ -466,58 +469,186 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
 }
 
 // ===========================================================================
-// K1: batch score_value with frozen tables.  One warp per row, lanes own
-// groups; out[(r - b) * G + g].
+// K1: batch score_value with frozen tables: out[(r - b) * G + g].
+//
+// A CTA takes tiles of SC_TR consecutive rows.  The tile's cells are staged into
+// shared memory with coalesced column reads (rows are contiguous inside a feature
+// column), then each warp scores SC_TR/8 rows with lanes = groups:
+//   * categorical cells and small GP counts are branch-free gathers of one table
+//     row (value row minus shift row; unobserved cells read the all-zero row); the
+//     GP predictive table for counts < LB_GP_TAB is built by k_gp_table just
+//     before the launch, so no lgamma is evaluated per (cell, group);
+//   * NICH loads its five per-group parameters once per feature and reuses them
+//     for all rows of the warp.
+// The 8 x NJ independent gathers per feature give the memory system the
+// parallelism the one-row-at-a-time version lacked.
 // ===========================================================================
 constexpr int SC_THREADS = 256;
-constexpr int SC_J = 4;
+constexpr int SC_TR = 64;               // rows per tile
+constexpr int SC_RW = SC_TR / 8;        // rows per warp
+constexpr int SC_FC = 128;              // features staged per chunk
+constexpr int LB_GP_TAB = 16;
 
+// Score table of one kind, built right before a batch-score launch: row 0 is all zero
+// ("unobserved"), then for every non-NICH feature one row per value holding the COMPLETE
+// log predictive of that value for every group:
+//   BB  2 rows (value 0, value 1)          DD/DPD  dim rows, already minus log(A + N)
+//   GP  LB_GP_TAB rows (counts 0..15; larger counts are evaluated directly)
+// so scoring a cell is one gather + one add per 32 groups.
+__global__ void k_score_table(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
+                              const int32_t *row_base, const int32_t *row_feat, int n_rows, float *tab) {
+    const KindDev &kd = kinds[kid];
+    const int G = kd.G, st = kd.Gcap;
+    const uint64_t total = (uint64_t)n_rows * G;
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(idx / G), g = (int)(idx % G);
+        float v = 0.f;
+        if (row > 0) {
+            const int j = row_feat[row];
+            const int local = row - row_base[j];
+            const FeatDev &f = feats[kind_feats[kd.feat_begin + j]];
+            const float *c = kd.cache + (size_t)f.cache_row * st + g;
+            if (f.type == LB_BB) v = c[local ? 0 : st];           // cache rows: 0 = log p(1), 1 = log p(0)
+            else if (f.type == LB_GP) {
+                const float a = f.hp[0] + (float)kd.ints[(size_t)(f.int_row + 1) * st + g];
+                v = lb_lgamma_diff_int(a, (uint32_t)local) - lb_log_factorial((uint32_t)local) + c[0] + (float)local * c[st];
+            } else v = c[(size_t)local * st] - c[(size_t)f.dim * st];
+        }
+        tab[(size_t)row * st + g] = v;
+    }
+}
+
+template <int NJ>
 __global__ void __launch_bounds__(SC_THREADS)
 k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
-             RowsDev rows, uint64_t b, uint64_t en, int n_empty, float *out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+             const int32_t *row_base, const float *tab, RowsDev rows, uint64_t b, uint64_t en,
+             int n_empty, int g_base, float *out) {
+    __shared__ FeatDev s_feat[SC_FC];
+    __shared__ int32_t s_fid[SC_FC];
+    __shared__ uint32_t s_row[SC_FC][SC_TR];     // table row of the cell (0 = unobserved), or raw bits for NICH
+    __shared__ uint32_t s_obs[SC_FC][SC_TR / 32];
     const KindDev &kd = kinds[kid];
     const int nf = kd.nf, st = kd.Gcap, G = kd.G;
-    FeatDev *s_feat = (FeatDev *)smem_raw;
-    int32_t *s_fid = (int32_t *)(s_feat + nf);
-    for (int j = threadIdx.x; j < nf; j += SC_THREADS) {
-        const int fid = kind_feats[kd.feat_begin + j];
-        s_feat[j] = feats[fid];
-        s_fid[j] = fid;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)SC_THREADS + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * SC_THREADS) >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cache = kd.cache;
+    const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
     const float base = -logf((float)kd.sample_size + kd.alpha);
     const float sh_empty = logf((kd.alpha + kd.d * (float)(G - n_empty)) / (float)n_empty);
-    for (uint64_t r = b + warp; r < en; r += n_warps) {
-        for (int g0 = 0; g0 < G; g0 += 32 * SC_J) {
-            float acc[SC_J];
+    float prior[NJ];
 #pragma unroll
-            for (int jj = 0; jj < SC_J; ++jj) {
-                const int g = g0 + lane + 32 * jj;
-                acc[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
+    for (int jj = 0; jj < NJ; ++jj) {
+        const int g = g_base + lane + 32 * jj;
+        prior[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
+    }
+    const float *tabg = tab + g_base + lane;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t r0 = b + tile * SC_TR;
+        float acc[SC_RW][NJ];
+#pragma unroll
+        for (int q = 0; q < SC_RW; ++q)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) acc[q][jj] = prior[jj];
+        for (int f0 = 0; f0 < nf; f0 += SC_FC) {
+            const int fc = min(SC_FC, nf - f0);
+            __syncthreads();   // previous chunk fully consumed
+            for (int j = tid; j < fc; j += SC_THREADS) {
+                const int fid = kind_feats[kd.feat_begin + f0 + j];
+                s_feat[j] = feats[fid];
+                s_fid[j] = fid;
             }
-            for (int j = 0; j < nf; ++j) {
-                const uint32_t obs = (rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
-                if (!obs) continue;
+            __syncthreads();
+            for (int idx = tid; idx < fc * (SC_TR / 32); idx += SC_THREADS) {
+                const int j = idx / (SC_TR / 32), w = idx % (SC_TR / 32);
+                const uint64_t r = r0 + 32 * w;
+                uint32_t bits = 0;
+                if ((r & 31) == 0 && r + 32 <= en) {
+                    bits = rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)];
+                } else {
+                    for (int k = 0; k < 32; ++k) {
+                        const uint64_t rk = r + k;
+                        if (rk < en) bits |= ((rows.mask[(uint64_t)s_fid[j] * rows.W + (rk >> 5)] >> (rk & 31)) & 1u) << k;
+                    }
+                }
+                s_obs[j][w] = bits;
+            }
+            __syncthreads();
+            // stage the tile: consecutive threads read consecutive rows of one column and turn
+            // the cell into the index of its score-table row
+            for (int idx = tid; idx < fc * SC_TR; idx += SC_THREADS) {
+                const int j = idx / SC_TR, rr = idx % SC_TR;
+                const uint64_t r = r0 + rr;
                 const FeatDev &f = s_feat[j];
-                const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                               : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-                const float cc = f.type == LB_GP ? lb_log_factorial(raw) : 0.f;
-                const uint32_t *in = kd.ints + (size_t)f.int_row * st;
-                const float *c = kd.cache + (size_t)f.cache_row * st;
+                uint32_t raw = 0;
+                if (r < en) raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                            : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+                const bool obs = (s_obs[j][rr >> 5] >> (rr & 31)) & 1u;
+                uint32_t v = raw;
+                if (f.type != LB_NICH) {
+                    if (!obs) v = 0u;
+                    else if (f.type == LB_GP && raw >= (uint32_t)LB_GP_TAB) v = 0x80000000u | raw;  // direct evaluation
+                    else v = (uint32_t)row_base[f0 + j] + raw;
+                }
+                s_row[j][rr] = v;
+            }
+            __syncthreads();
+            for (int j = 0; j < fc; ++j) {
+                const FeatDev &f = s_feat[j];
+                if (f.type == LB_NICH) {
+                    float c0[NJ], c1[NJ], c2[NJ], c3[NJ], c4[NJ];
 #pragma unroll
-                for (int jj = 0; jj < SC_J; ++jj) {
-                    const int g = g0 + lane + 32 * jj;
-                    if (g < G) acc[jj] += lb_score_cell(f, in + g, c + g, st, raw, cc);
+                    for (int jj = 0; jj < NJ; ++jj) {
+                        const float *c = cache + (size_t)f.cache_row * st + g_base + lane + 32 * jj;
+                        c0[jj] = c[0]; c1[jj] = c[st]; c2[jj] = c[2 * (size_t)st];
+                        c3[jj] = c[3 * (size_t)st]; c4[jj] = c[4 * (size_t)st];
+                    }
+#pragma unroll
+                    for (int q = 0; q < SC_RW; ++q) {
+                        const int rr = warp * SC_RW + q;
+                        if (!((s_obs[j][rr >> 5] >> (rr & 31)) & 1u)) continue;
+                        const float x = __uint_as_float(s_row[j][rr]);
+#pragma unroll
+                        for (int jj = 0; jj < NJ; ++jj) {
+                            const float dx = (x - c3[jj]) - c4[jj];
+                            acc[q][jj] += c0[jj] - c1[jj] * log1pf(c2[jj] * dx * dx);
+                        }
+                    }
+                } else if (f.type == LB_GP) {
+#pragma unroll
+                    for (int q = 0; q < SC_RW; ++q) {
+                        const uint32_t row = s_row[j][warp * SC_RW + q];
+                        if (row & 0x80000000u) {   // rare: large count
+                            const uint32_t raw = row & 0x7fffffffu;
+                            const float lf = lb_log_factorial(raw);
+#pragma unroll
+                            for (int jj = 0; jj < NJ; ++jj) {
+                                const int g = g_base + lane + 32 * jj;
+                                acc[q][jj] += lb_score_cell(f, kd.ints + (size_t)f.int_row * st + g,
+                                                            cache + (size_t)f.cache_row * st + g, st, raw, lf);
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < NJ; ++jj) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < SC_RW; ++q) {
+                        const uint32_t row = s_row[j][warp * SC_RW + q];
+#pragma unroll
+                        for (int jj = 0; jj < NJ; ++jj) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
+                    }
                 }
             }
+        }
 #pragma unroll
-            for (int jj = 0; jj < SC_J; ++jj) {
-                const int g = g0 + lane + 32 * jj;
-                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[jj];
+        for (int q = 0; q < SC_RW; ++q) {
+            const uint64_t r = r0 + warp * SC_RW + q;
+            if (r >= en) continue;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const int g = g_base + lane + 32 * jj;
+                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[q][jj];
             }
         }
     }
@@ -525,20 +656,50 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
 
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
     const KindHost &k = e->kinds[kid];
-    const size_t smem = k.fids.size() * (sizeof(FeatDev) + 4) + 16;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        LB_CUDA(cudaFuncSetAttribute(k_score_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const int nf = (int)k.fids.size();
+    // layout of the score table
+    std::vector<int32_t> row_base(std::max(nf, 1), 0), row_feat(1, -1);
+    for (int j = 0; j < nf; ++j) {
+        const lb_feature_spec &s = e->specs[k.fids[j]];
+        row_base[j] = (int32_t)row_feat.size();
+        const int n = s.type == LB_BB ? 2 : (s.type == LB_GP ? LB_GP_TAB : (s.type == LB_NICH ? 0 : s.dim));
+        row_feat.insert(row_feat.end(), n, (int32_t)j);
     }
-    const uint64_t n = en - b;
-    const uint64_t want = (n * 32 + SC_THREADS - 1) / SC_THREADS;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)e->n_sm * 8));
-    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
-    k_score_rows<<<grid, SC_THREADS, smem, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats,
-                                                       rows, b, en, e->empty_group_count, d_out);
-    LB_CUDA(cudaGetLastError());
+    const int n_rows = (int)row_feat.size();
+    const size_t idx_bytes = ((4 * (row_base.size() + row_feat.size()) + 255) / 256) * 256;
+    const size_t need = idx_bytes + 4 * (size_t)n_rows * k.Gcap + 256;
+    if (need > e->score_aux_bytes) {
+        if (e->d_score_aux) cudaFree(e->d_score_aux);
+        e->d_score_aux = nullptr;
+        LB_CUDA(cudaMalloc(&e->d_score_aux, need));
+        e->score_aux_bytes = need;
+    }
+    int32_t *d_row_base = (int32_t *)e->d_score_aux;
+    int32_t *d_row_feat = d_row_base + row_base.size();
+    float *d_tab = (float *)((char *)e->d_score_aux + idx_bytes);
+    LB_CUDA(cudaMemcpyAsync(d_row_base, row_base.data(), 4 * row_base.size(), cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(d_row_feat, row_feat.data(), 4 * row_feat.size(), cudaMemcpyHostToDevice, e->stream));
+    const uint64_t tot = (uint64_t)n_rows * k.G;
+    k_score_table<<<(int)std::max<uint64_t>(1, std::min<uint64_t>((tot + 255) / 256, (uint64_t)e->n_sm * 8)), 256, 0, e->stream>>>(
+        e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_row_feat, n_rows, d_tab);
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 4));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    for (int g_base = 0; g_base < k.G; g_base += 128) {
+        const int left = k.G - g_base;
+        if (left <= 32)
+            k_score_rows<1><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                               d_tab, rows, b, en, e->empty_group_count, g_base, d_out);
+        else if (left <= 64)
+            k_score_rows<2><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                               d_tab, rows, b, en, e->empty_group_count, g_base, d_out);
+        else
+            k_score_rows<4><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                               d_tab, rows, b, en, e->empty_group_count, g_base, d_out);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    }
     return 0;
 }
 
@@ -577,11 +738,9 @@ int lb_launch_refresh(Engine *e, int kid) {
 int lb_refresh_kind(Engine *e, int kid) { return lb_launch_refresh(e, kid); }
 
 // ===========================================================================
-// K2: bulk accumulate with given assignments.
-// grid.y = feature slot inside the kind (slot nf = clustering counts);
-// grid.x = row chunk; thread per row.  Integer statistics are exact atomics;
+// K2 / K4: bulk accumulate with given assignments (kernels in lb_accum.cuh).
 // NICH / GP float statistics are accumulated as double sums (sum x, sum x^2,
-// sum log x!) and converted back afterwards.
+// sum log x!) and converted back to (mean, count_times_variance) afterwards.
 // ===========================================================================
 __global__ void k_moments_to_sums(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats) {
     const KindDev &kd = kinds[kid];
@@ -618,74 +777,85 @@ __global__ void k_sums_to_moments(KindDev *kinds, int kid, const FeatDev *feats,
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_accumulate(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats, RowsDev rows,
-             uint64_t b, uint64_t en, int sign, int32_t *flag) {
-    KindDev &kd = kinds[kid];
-    const int st = kd.Gcap;
-    const int slot = blockIdx.y;
-    const uint64_t r = b + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint32_t a = LB_UNASSIGNED;
-    if (r < en) a = kd.assign[r];
-    const bool live = a != LB_UNASSIGNED;
-    const uint32_t g = live ? kd.g2p[a] : 0u;
-    if (slot == kd.nf) {  // clustering.add_value
-        if (live) {
-            const uint32_t old = atomicAdd(&kd.counts[g], (uint32_t)sign);
-            if (sign < 0 && old == 0u) *flag = 1;
-        }
-        const unsigned m = __ballot_sync(FULL, live);
-        if ((threadIdx.x & 31) == 0 && m)
-            atomicAdd((unsigned long long *)&kd.sample_size, (unsigned long long)((long long)sign * __popc(m)));
-        return;
+__global__ void k_pack_assign_range(const uint32_t *assign, const uint32_t *g2p, uint32_t *packed, uint64_t b, uint64_t en) {
+    for (uint64_t r = b + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < en; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = assign[r];
+        packed[r] = a == LB_UNASSIGNED ? LB_UNASSIGNED : g2p[a];
     }
-    if (!live) return;
-    const int fid = kind_feats[kd.feat_begin + slot];
-    if (!((rows.mask[(uint64_t)fid * rows.W + (r >> 5)] >> (r & 31)) & 1u)) return;
-    const FeatDev &f = feats[fid];
-    const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                   : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-    uint32_t *in = kd.ints + (size_t)f.int_row * st + g;
-    double *fl = kd.flts + (size_t)f.flt_row * st + g;
-    switch (f.type) {
-    case LB_BB:
-        atomicAdd(&in[raw ? 0 : st], (uint32_t)sign);
-        break;
-    case LB_DD:
-    case LB_DPD:
-        atomicAdd(&in[(size_t)raw * st], (uint32_t)sign);
-        atomicAdd(&in[(size_t)f.dim * st], (uint32_t)sign);
-        break;
-    case LB_GP:
-        atomicAdd(&in[0], (uint32_t)sign);
-        atomicAdd(&in[st], (uint32_t)(sign * (int64_t)raw));
-        atomicAdd(&fl[0], sign * lb_log_factorial_d(raw));
-        break;
-    case LB_NICH: {
-        const double x = (double)__uint_as_float(raw);
-        atomicAdd(&in[0], (uint32_t)sign);
-        atomicAdd(&fl[0], sign * x);
-        atomicAdd(&fl[st], sign * x * x);
-        break;
+}
+
+// Launch k_accum_feature over `fids` (global feature ids), grouped by shared-memory need so
+// that small tables (BB / GP / NICH / low-dimensional DD) keep a high occupancy.
+int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
+                             const uint32_t *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
+                             double *flts, int st, int G, int launch_family) {
+    if (en <= b || fids.empty()) return 0;
+    static bool configured = false;
+    const size_t kBig = 200 * 1024, kSmall = 16 * 1024;
+    if (!configured) {
+        LB_CUDA(cudaFuncSetAttribute(k_accum_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
+        configured = true;
     }
+    std::vector<int32_t> cls[3];
+    size_t big_need = 0;
+    for (int fid : fids) {
+        const lb_feature_spec &s = e->specs[fid];
+        const size_t need = lb_acc_smem_bytes(s.type, s.dim, G);
+        if (need <= kSmall) cls[0].push_back(fid);
+        else if (need <= kBig) { cls[1].push_back(fid); big_need = std::max(big_need, need); }
+        else cls[2].push_back(fid);
     }
+    const size_t total = cls[0].size() + cls[1].size() + cls[2].size();
+    if ((int)total > e->d_fid_list_cap) {
+        if (e->d_fid_list) cudaFree(e->d_fid_list);
+        e->d_fid_list = nullptr;
+        LB_CUDA(cudaMalloc((void **)&e->d_fid_list, 4 * (total + 64)));
+        e->d_fid_list_cap = (int)total + 64;
+    }
+    const uint64_t n = en - b;
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    size_t off = 0;
+    const size_t smem_of[3] = {kSmall, big_need, 0};
+    for (int c = 0; c < 3; ++c) {
+        if (cls[c].empty()) continue;
+        // a CTA must see many more cells than its table has entries, or the flush dominates:
+        // big (DD-256-sized) tables take 64k-row chunks, small ones 8k-row chunks
+        uint64_t rows_per_cta = c == 1 ? std::max<uint64_t>(65536, (n + 7) / 8) : std::max<uint64_t>(8192, (n + 31) / 32);
+        rows_per_cta = (rows_per_cta + ACC_THREADS - 1) / ACC_THREADS * ACC_THREADS;
+        const unsigned chunks = (unsigned)((n + rows_per_cta - 1) / rows_per_cta);
+        int32_t *d_list = e->d_fid_list + off;
+        LB_CUDA(cudaMemcpyAsync(d_list, cls[c].data(), 4 * cls[c].size(), cudaMemcpyHostToDevice, e->stream));
+        dim3 grid(chunks, (unsigned)cls[c].size());
+        k_accum_feature<<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, d_packed, b, en, rows_per_cta,
+                                                                   sign, ints, flts, st, G, (int)smem_of[c]);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[launch_family]++;
+        off += cls[c].size();
+    }
+    return 0;
 }
 
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) {
     const KindHost &k = e->kinds[kid];
     const int nf = (int)k.fids.size();
-    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
     const int items = std::max(1, nf * k.G);
     const int g1 = std::min((items + 255) / 256, e->n_sm * 4);
     if (nf) k_moments_to_sums<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
     if (en > b) {
-        dim3 grid((unsigned)((en - b + 255) / 256), (unsigned)(nf + 1));
-        k_accumulate<<<grid, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, rows, b, en,
-                                                  sign, e->d_flag);
+        LB_TRY(lb_ensure_scratch(e, 4 * (size_t)e->R));
+        uint32_t *d_packed = (uint32_t *)e->d_scratch;
+        const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, (uint64_t)e->n_sm * 8));
+        k_pack_assign_range<<<pg, 256, 0, e->stream>>>(k.assign, k.g2p, d_packed, b, en);
+        // clustering.add_value
+        k_accum_counts<<<std::min(pg, e->n_sm * 2), ACC_THREADS, 4 * (size_t)k.G + 16, e->stream>>>(
+            d_packed, b, en, sign, k.counts, (unsigned long long *)((char *)&e->d_kinds[kid] + offsetof(KindDev, sample_size)),
+            k.G, e->d_flag);
+        e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_ACCUM] += 2;
+        LB_TRY(lb_launch_accum_features(e, e->d_feats, k.fids, d_packed, b, en, sign, k.ints, k.flts, k.Gcap, k.G, LB_L_ACCUM));
     }
     if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
     LB_CUDA(cudaGetLastError());
-    e->launches[LB_L_TOTAL] += nf ? 3 : 1; e->launches[LB_L_ACCUM] += nf ? 3 : 1;
+    e->launches[LB_L_TOTAL] += nf ? 2 : 0; e->launches[LB_L_ACCUM] += nf ? 2 : 0;
     return lb_launch_refresh(e, kid);
 }
 

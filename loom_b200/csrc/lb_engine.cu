@@ -297,8 +297,11 @@ extern "C" void lb_destroy(lb_handle h) {
     clear_model(e);
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
-    dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_prop_scores); dev_free(e->d_kind_ids);
+    lb_release_proposer(e);
+    dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
+    if (e->d_score_aux) cudaFree(e->d_score_aux);
+    if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
     cudaStreamDestroy(e->stream);

@@ -24,6 +24,7 @@ struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind
     uint32_t *ints = nullptr;  // [prop_int_rows][pst]
     double *flts = nullptr;    // [prop_flt_rows][pst]
     uint32_t *packed = nullptr;  // [R] packed group id of every row in this kind
+    size_t cap_ints = 0, cap_flts = 0, cap_rows = 0;   // allocated sizes (buffers are reused)
 };
 
 struct Engine {
@@ -63,6 +64,10 @@ struct Engine {
     size_t actions_cap = 0;
     int32_t *d_flag = nullptr;
     int32_t *d_kind_ids = nullptr;
+    int32_t *d_fid_list = nullptr;     // K2/K4: feature id lists per shared-memory class
+    int d_fid_list_cap = 0;
+    void *d_score_aux = nullptr;       // K1: GP feature index + predictive tables
+    size_t score_aux_bytes = 0;
     int d_kind_ids_cap = 0;
 
     // hyper prior
@@ -74,6 +79,8 @@ struct Engine {
     int prop_int_rows = 0, prop_flt_rows = 0;
     std::vector<float> prop_scores;  // [F][K]
     float *d_prop_scores = nullptr;
+    size_t prop_scores_cap = 0;
+    bool prop_valid = false;
     FeatDev *d_prop_feats = nullptr;   // all-feature row layout of the proposer tables
 
     uint64_t launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -133,6 +140,9 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
                     uint64_t offset, uint32_t *d_picks, float *d_scores, int stride);
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
+int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
+                             const uint32_t *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
+                             double *flts, int st, int G, int launch_family);
 int lb_launch_refresh(Engine *e, int kid);
 int lb_launch_restride(Engine *e, const KindHost &src, KindHost &dst);
 int lb_launch_renumber(Engine *e, int kid);
@@ -140,4 +150,5 @@ int lb_launch_validate_rows(Engine *e, int *bad);
 int lb_launch_score_data(Engine *e, double *out);
 
 // structure kernels (lb_struct.cu)
-void lb_free_proposer(Engine *e);
+void lb_free_proposer(Engine *e);      // invalidate (buffers kept)
+void lb_release_proposer(Engine *e);   // free the buffers

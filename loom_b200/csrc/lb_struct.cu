@@ -24,15 +24,23 @@ template <class T> static int dalloc(T **p, size_t n) {
     return 0;
 }
 
+// Proposer tables are invalidated (prop_valid = false) whenever the kinds change, but the
+// device buffers are kept and reused by the next proposal round.
 void lb_free_proposer(Engine *e) {
+    e->prop_valid = false;
+    e->prop_scores.clear();
+}
+void lb_release_proposer(Engine *e) {
     for (auto &p : e->prop) {
         if (p.ints) cudaFree(p.ints);
         if (p.flts) cudaFree(p.flts);
         if (p.packed) cudaFree(p.packed);
     }
     e->prop.clear();
+    e->prop_valid = false;
     e->prop_scores.clear();
     if (e->d_prop_feats) { cudaFree(e->d_prop_feats); e->d_prop_feats = nullptr; }
+    if (e->d_prop_scores) { cudaFree(e->d_prop_scores); e->d_prop_scores = nullptr; }
 }
 
 // ---------------------------------------------------------------------------
@@ -218,24 +226,29 @@ extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
     lb_free_proposer(e);
     LB_TRY(build_prop_feats(e));
     const int F = e->F, K = (int)e->kinds.size();
-    e->prop.resize(K);
-    if (e->d_prop_scores) cudaFree(e->d_prop_scores);
-    LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
-    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    if ((int)e->prop.size() < K) e->prop.resize(K);
+    if ((size_t)F * K > e->prop_scores_cap) {
+        if (e->d_prop_scores) cudaFree(e->d_prop_scores);
+        LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
+        e->prop_scores_cap = (size_t)F * K;
+    }
     const int rgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, 4096));
+    std::vector<int> all_features(F);
+    for (int f = 0; f < F; ++f) all_features[f] = f;
     for (int kid = 0; kid < K; ++kid) {
         const KindHost &k = e->kinds[kid];
         ProposerKind &p = e->prop[kid];
         p.G = k.G;
         p.pst = (k.G + 31) & ~31;
-        LB_TRY(dalloc(&p.ints, (size_t)e->prop_int_rows * p.pst));
-        LB_TRY(dalloc(&p.flts, (size_t)e->prop_flt_rows * p.pst));
-        LB_TRY(dalloc(&p.packed, e->R));
+        const size_t need_i = (size_t)e->prop_int_rows * p.pst, need_f = (size_t)e->prop_flt_rows * p.pst;
+        if (need_i > p.cap_ints) { if (p.ints) cudaFree(p.ints); LB_TRY(dalloc(&p.ints, need_i + need_i / 4)); p.cap_ints = need_i + need_i / 4; }
+        if (need_f > p.cap_flts) { if (p.flts) cudaFree(p.flts); LB_TRY(dalloc(&p.flts, need_f + need_f / 4)); p.cap_flts = need_f + need_f / 4; }
+        if (e->R > p.cap_rows) { if (p.packed) cudaFree(p.packed); LB_TRY(dalloc(&p.packed, e->R)); p.cap_rows = e->R; }
         LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * (size_t)e->prop_int_rows * p.pst, e->stream));
         LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * (size_t)e->prop_flt_rows * p.pst, e->stream));
         k_pack_assign<<<rgrid, 256, 0, e->stream>>>(k.assign, k.g2p, p.packed, e->R);
-        dim3 grid((unsigned)std::min<uint64_t>((e->R + 255) / 256, 1024), (unsigned)F);
-        k_prop_accumulate<<<grid, 256, 0, e->stream>>>(e->d_prop_feats, rows, p.packed, p.ints, p.flts, p.pst);
+        LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, p.packed, 0, e->R, +1, p.ints, p.flts,
+                                        p.pst, p.G, LB_L_KIND));
         k_prop_sums_to_moments<<<std::max(1, std::min((F * p.G + 255) / 256, 1024)), 256, 0, e->stream>>>(
             e->d_prop_feats, F, p.ints, p.flts, p.pst, p.G);
         k_prop_score<<<F, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, p.ints, p.flts, p.pst, p.G, kid, K,
@@ -247,6 +260,7 @@ extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
     LB_CUDA(cudaMemcpyAsync(e->prop_scores.data(), e->d_prop_scores, 4 * (size_t)F * K, cudaMemcpyDeviceToHost, e->stream));
     LB_CUDA(cudaStreamSynchronize(e->stream));
     if (out) memcpy(out, e->prop_scores.data(), 4 * (size_t)F * K);
+    e->prop_valid = true;
     return 0;
 }
 
@@ -356,7 +370,7 @@ extern "C" int lb_kind_run(lb_handle h, int32_t iterations, uint64_t seed, uint3
     LB_CUDA(cudaSetDevice(e->device));
     if (iterations <= 0) return lb_fail("kind_run: iterations must be > 0");
     const int F = e->F, K = (int)e->kinds.size();
-    if (e->prop_scores.size() != (size_t)F * K || (int)e->prop.size() != K)
+    if (!e->prop_valid || e->prop_scores.size() != (size_t)F * K || (int)e->prop.size() < K)
         return lb_fail("kind_run: call kind_proposer_score first");
     for (int k = 0; k < K; ++k)
         if (e->prop[k].G != e->kinds[k].G) return lb_fail("kind_run: stale proposer tables");
