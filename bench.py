@@ -406,8 +406,12 @@ def main():
     alg_bytes_per_launch = bytes_per_action * actions_per_step * args.steps * n_chains / max(n_sweep, 1)
     avg_launch_ms = sweep_ms / max(n_sweep, 1)
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "r1_k_cat_sweep_traffic.json")
+    if os.path.exists(tpath) and args.workload == "C2" and not args.rows:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full, dominant launch type
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
                 "kernel_share_of_step": sweep_ms / (total_ms * n_chains) if total_ms else None,
                 "concurrent_launches": n_chains,
