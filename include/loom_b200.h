@@ -190,6 +190,17 @@ int LB_NAME(score_data)(lb_handle h, double *out);
  * scores_to_likelihoods. */
 int LB_NAME(kind_proposer_score)(lb_handle h, float *out_scores);
 
+/* Row-sharded form of kind_proposer_score for multi-GPU runs: every
+ * device accumulates ITS rows [row_begin,row_end) into zeroed all-feature tables
+ * (proposer_accumulate), the caller all-reduces (sum) the flat buffers exposed by
+ * proposer_tables -- uint32 counts and float64 sums (sum x, sum x^2, sum log x!), DEVICE
+ * pointers for the CUDA library -- and proposer_finish converts sums to moments and
+ * scores.  kind_proposer_score == accumulate(0, R) + finish on one device. */
+int LB_NAME(proposer_accumulate)(lb_handle h, uint64_t row_begin, uint64_t row_end);
+int LB_NAME(proposer_tables)(lb_handle h, int32_t kind, uint32_t **ints, uint64_t *n_ints,
+                             double **flts, uint64_t *n_flts);
+int LB_NAME(proposer_finish)(lb_handle h, float *out_scores);
+
 /* KindKernel::try_run (src/kind_kernel.cc:118-157) given proposer tables from
  * kind_proposer_score: block Pitman-Yor sampler (src/kind_proposer.cc:269-300)
  * then move_features (src/kind_kernel.cc:83-116).  Writes the new

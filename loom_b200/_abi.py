@@ -62,6 +62,9 @@ SIGNATURES = {
     "accumulate_rows": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32]),
     "score_data": (C.c_int, [_h, _f64p]),
     "kind_proposer_score": (C.c_int, [_h, _f32p]),
+    "proposer_accumulate": (C.c_int, [_h, C.c_uint64, C.c_uint64]),
+    "proposer_tables": (C.c_int, [_h, C.c_int32, C.POINTER(C.c_void_p), _u64p, C.POINTER(C.c_void_p), _u64p]),
+    "proposer_finish": (C.c_int, [_h, _f32p]),
     "kind_run": (C.c_int, [_h, C.c_int32, C.c_uint64, _u32p, C.POINTER(C.c_int32)]),
     "init_featureless_kinds": (C.c_int, [_h, C.c_int32, C.c_uint64]),
     "get_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),

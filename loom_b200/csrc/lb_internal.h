@@ -81,6 +81,7 @@ struct Engine {
     float *d_prop_scores = nullptr;
     size_t prop_scores_cap = 0;
     bool prop_valid = false;
+    bool prop_accumulated = false;     // tables hold (possibly partial) sums, not yet finished
     FeatDev *d_prop_feats = nullptr;   // all-feature row layout of the proposer tables
 
     uint64_t launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};

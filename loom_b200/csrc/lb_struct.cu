@@ -28,6 +28,7 @@ template <class T> static int dalloc(T **p, size_t n) {
 // device buffers are kept and reused by the next proposal round.
 void lb_free_proposer(Engine *e) {
     e->prop_valid = false;
+    e->prop_accumulated = false;
     e->prop_scores.clear();
 }
 void lb_release_proposer(Engine *e) {
@@ -218,20 +219,16 @@ static int build_prop_feats(Engine *e) {
     return 0;
 }
 
-extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
+extern "C" int lb_proposer_accumulate(lb_handle h, uint64_t b, uint64_t en) {
     Engine *e = (Engine *)h;
     LB_CUDA(cudaSetDevice(e->device));
-    if (!e->R) return lb_fail("kind_proposer_score before set_rows");
+    if (!e->R) return lb_fail("proposer_accumulate before set_rows");
+    if (b > en || en > e->R) return lb_fail("bad row range");
     LB_TRY(lb_sync_model(e));
     lb_free_proposer(e);
     LB_TRY(build_prop_feats(e));
     const int F = e->F, K = (int)e->kinds.size();
     if ((int)e->prop.size() < K) e->prop.resize(K);
-    if ((size_t)F * K > e->prop_scores_cap) {
-        if (e->d_prop_scores) cudaFree(e->d_prop_scores);
-        LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
-        e->prop_scores_cap = (size_t)F * K;
-    }
     const int rgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, 4096));
     std::vector<int> all_features(F);
     for (int f = 0; f < F; ++f) all_features[f] = f;
@@ -244,24 +241,62 @@ extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
         if (need_i > p.cap_ints) { if (p.ints) cudaFree(p.ints); LB_TRY(dalloc(&p.ints, need_i + need_i / 4)); p.cap_ints = need_i + need_i / 4; }
         if (need_f > p.cap_flts) { if (p.flts) cudaFree(p.flts); LB_TRY(dalloc(&p.flts, need_f + need_f / 4)); p.cap_flts = need_f + need_f / 4; }
         if (e->R > p.cap_rows) { if (p.packed) cudaFree(p.packed); LB_TRY(dalloc(&p.packed, e->R)); p.cap_rows = e->R; }
-        LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * (size_t)e->prop_int_rows * p.pst, e->stream));
-        LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * (size_t)e->prop_flt_rows * p.pst, e->stream));
+        LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * need_i, e->stream));
+        LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * need_f, e->stream));
         k_pack_assign<<<rgrid, 256, 0, e->stream>>>(k.assign, k.g2p, p.packed, e->R);
-        LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, p.packed, 0, e->R, +1, p.ints, p.flts,
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
+        LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, p.packed, b, en, +1, p.ints, p.flts,
                                         p.pst, p.G, LB_L_KIND));
+    }
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    e->prop_accumulated = true;
+    return 0;
+}
+
+extern "C" int lb_proposer_tables(lb_handle h, int32_t kind, uint32_t **ints, uint64_t *n_ints, double **flts,
+                                  uint64_t *n_flts) {
+    Engine *e = (Engine *)h;
+    if (!e->prop_accumulated || kind < 0 || kind >= (int)e->kinds.size() || kind >= (int)e->prop.size())
+        return lb_fail("proposer_tables: call proposer_accumulate first");
+    const ProposerKind &p = e->prop[kind];
+    *ints = p.ints; *n_ints = (uint64_t)e->prop_int_rows * p.pst;
+    *flts = p.flts; *n_flts = (uint64_t)e->prop_flt_rows * p.pst;
+    return 0;
+}
+
+extern "C" int lb_proposer_finish(lb_handle h, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->prop_accumulated) return lb_fail("proposer_finish: call proposer_accumulate first");
+    const int F = e->F, K = (int)e->kinds.size();
+    if ((size_t)F * K > e->prop_scores_cap) {
+        if (e->d_prop_scores) cudaFree(e->d_prop_scores);
+        LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
+        e->prop_scores_cap = (size_t)F * K;
+    }
+    for (int kid = 0; kid < K; ++kid) {
+        ProposerKind &p = e->prop[kid];
         k_prop_sums_to_moments<<<std::max(1, std::min((F * p.G + 255) / 256, 1024)), 256, 0, e->stream>>>(
             e->d_prop_feats, F, p.ints, p.flts, p.pst, p.G);
         k_prop_score<<<F, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, p.ints, p.flts, p.pst, p.G, kid, K,
                                                e->d_prop_scores);
         LB_CUDA(cudaGetLastError());
-        e->launches[LB_L_TOTAL] += 4; e->launches[LB_L_KIND] += 4;
+        e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_KIND] += 2;
     }
     e->prop_scores.resize((size_t)F * K);
     LB_CUDA(cudaMemcpyAsync(e->prop_scores.data(), e->d_prop_scores, 4 * (size_t)F * K, cudaMemcpyDeviceToHost, e->stream));
     LB_CUDA(cudaStreamSynchronize(e->stream));
     if (out) memcpy(out, e->prop_scores.data(), 4 * (size_t)F * K);
+    e->prop_accumulated = false;
     e->prop_valid = true;
     return 0;
+}
+
+extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {
+    Engine *e = (Engine *)h;
+    LB_TRY(lb_proposer_accumulate(h, 0, e->R));
+    return lb_proposer_finish(h, out);
 }
 
 // ---------------------------------------------------------------------------

@@ -273,6 +273,23 @@ class Engine:
         self.abi.check(self.abi.kind_proposer_score(self.h, ptr(out, _f32p)))
         return out
 
+    def proposer_accumulate(self, row_begin=0, row_end=None):
+        row_end = self.n_rows if row_end is None else row_end
+        self.abi.check(self.abi.proposer_accumulate(self.h, row_begin, row_end))
+
+    def proposer_tables(self, kind):
+        """(ints_ptr, n_ints, flts_ptr, n_flts): flat buffers to all-reduce (device pointers for CUDA)."""
+        pi, pf = C.c_void_p(), C.c_void_p()
+        ni, nf = C.c_uint64(), C.c_uint64()
+        self.abi.check(self.abi.proposer_tables(self.h, kind, C.byref(pi), C.byref(ni), C.byref(pf), C.byref(nf)))
+        return pi.value or 0, ni.value, pf.value or 0, nf.value
+
+    def proposer_finish(self, fetch=True):
+        K = self.n_kinds()
+        out = np.empty((self.model.n_features, K), np.float32) if fetch else None
+        self.abi.check(self.abi.proposer_finish(self.h, ptr(out, _f32p)))
+        return out
+
     def kind_run(self, iterations, seed):
         f2k = np.zeros(self.model.n_features, np.uint32)
         n = C.c_int32()

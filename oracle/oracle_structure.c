@@ -24,10 +24,13 @@ void oracle_free_proposer(engine_t *e) {
     e->prop_int_off = e->prop_flt_off = NULL; e->prop_scores = NULL; e->prop_K = 0;
 }
 
-/* Bulk KindKernel::add_to_kind_proposer + KindProposer score phase. */
-int lo_kind_proposer_score(lb_handle h, float *out) {
+/* Bulk KindKernel::add_to_kind_proposer over rows [b, en): every assigned row goes, with ALL
+ * its features, into group g_k(row) of every kind.  Float statistics are kept as mergeable
+ * sums (sum x, sum x^2, sum log x!) until proposer_finish, so row shards can be all-reduced. */
+int lo_proposer_accumulate(lb_handle h, uint64_t b, uint64_t en) {
     engine_t *e = h;
-    if (!e->R) return lo_fail("kind_proposer_score before set_rows");
+    if (!e->R) return lo_fail("proposer_accumulate before set_rows");
+    if (b > en || en > e->R) return lo_fail("bad row range");
     oracle_free_proposer(e);
     const int F = e->F, K = e->K;
     e->prop_K = K;
@@ -42,7 +45,6 @@ int lo_kind_proposer_score(lb_handle h, float *out) {
     e->prop_flts = calloc(K, sizeof(void *));
     e->prop_G = calloc(K, sizeof(int));
     e->prop_scores = calloc((size_t)F * K, sizeof(float));
-    /* every assigned row goes, with ALL its features, into group g_k(row) of every kind */
 #pragma omp parallel for schedule(dynamic, 1)
     for (int kid = 0; kid < K; ++kid) {
         const kind_t *k = &e->kinds[kid];
@@ -51,17 +53,58 @@ int lo_kind_proposer_score(lb_handle h, float *out) {
         uint32_t *ints = calloc((size_t)e->prop_int_rows * G + 1, 4);
         double *flts = calloc((size_t)e->prop_flt_rows * G + 1, 8);
         e->prop_ints[kid] = ints; e->prop_flts[kid] = flts;
-        for (uint64_t r = 0; r < e->R; ++r) {
+        for (uint64_t r = b; r < en; ++r) {
             if (k->assign[r] == LB_UNASSIGNED) continue;
             const uint32_t g = k->g2p[k->assign[r]];
             for (int f = 0; f < F; ++f) {
                 if (!cell_observed(e, f, r)) continue;
-                om_add_value(&e->specs[f], ints + (size_t)e->prop_int_off[f] * G + g,
-                             flts + (size_t)e->prop_flt_off[f] * G + g, G, cell_raw(e, f, r), +1);
+                const lb_feature_spec *s = &e->specs[f];
+                uint32_t *in = ints + (size_t)e->prop_int_off[f] * G + g;
+                double *fl = flts + (size_t)e->prop_flt_off[f] * G + g;
+                const uint32_t raw = cell_raw(e, f, r);
+                if (s->type == LB_NICH) {
+                    float xf; memcpy(&xf, &raw, 4);
+                    in[0] += 1; fl[0] += (double)xf; fl[G] += (double)xf * (double)xf;
+                } else {
+                    om_add_value(s, in, fl, G, raw, +1);
+                }
             }
         }
     }
-    /* score phase: kind_proposer.cc:339-348 (OMP over features) */
+    return 0;
+}
+
+int lo_proposer_tables(lb_handle h, int32_t kind, uint32_t **ints, uint64_t *n_ints, double **flts,
+                       uint64_t *n_flts) {
+    engine_t *e = h;
+    if (!e->prop_ints || kind < 0 || kind >= e->prop_K) return lo_fail("proposer_tables: call proposer_accumulate first");
+    *ints = e->prop_ints[kind]; *n_ints = (uint64_t)e->prop_int_rows * e->prop_G[kind];
+    *flts = e->prop_flts[kind]; *n_flts = (uint64_t)e->prop_flt_rows * e->prop_G[kind];
+    return 0;
+}
+
+/* sums -> (mean, count_times_variance), then the KindProposer score phase
+ * (src/kind_proposer.cc:339-348, OMP over features). */
+int lo_proposer_finish(lb_handle h, float *out) {
+    engine_t *e = h;
+    if (!e->prop_ints) return lo_fail("proposer_finish: call proposer_accumulate first");
+    const int F = e->F, K = e->prop_K;
+    for (int kid = 0; kid < K; ++kid) {
+        const int G = e->prop_G[kid];
+        for (int f = 0; f < F; ++f) {
+            if (e->specs[f].type != LB_NICH) continue;
+            for (int g = 0; g < G; ++g) {
+                const double n = e->prop_ints[kid][(size_t)e->prop_int_off[f] * G + g];
+                double *fl = e->prop_flts[kid] + (size_t)e->prop_flt_off[f] * G + g;
+                if (n == 0) { fl[0] = 0; fl[G] = 0; }
+                else {
+                    const double mean = fl[0] / n;
+                    fl[0] = mean;
+                    fl[G] = fmax(fl[G] - n * mean * mean, 0.0);
+                }
+            }
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int f = 0; f < F; ++f) {
         for (int kid = 0; kid < K; ++kid) {
@@ -76,6 +119,12 @@ int lo_kind_proposer_score(lb_handle h, float *out) {
     }
     if (out) memcpy(out, e->prop_scores, sizeof(float) * (size_t)F * K);
     return 0;
+}
+
+int lo_kind_proposer_score(lb_handle h, float *out) {
+    engine_t *e = h;
+    int rc = lo_proposer_accumulate(h, 0, e->R);
+    return rc ? rc : lo_proposer_finish(h, out);
 }
 
 /* ---- Block Pitman-Yor sampler (src/kind_proposer.cc:131-300) ------------ */

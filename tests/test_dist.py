@@ -1,0 +1,73 @@
+"""N > 1 path: the row-sharded kind proposer with an all-reduce of the proposer tables.
+CPU: world_size 2 over gloo with the oracle as compute backend (host logic + exchange).
+GPU: world_size 2 over NCCL with libloomb200 (skipped with fewer than 2 devices)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests"))
+import numpy as np
+import torch, torch.distributed as dist
+from loom_b200 import Engine, _abi, synth, sweep_actions
+from loom_b200.dist import sharded_kind_proposer_score
+backend = sys.argv[1]
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+if backend == "nccl":
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    abi = _abi.load_cuda()
+else:
+    dist.init_process_group("gloo")
+    abi = _abi.Abi(os.path.join({repo!r}, "oracle", "libloom_oracle.so"), "lo_")
+model, rows, truth = synth.generate(3000, [("bb", 3), ("dd16", 3), ("dd256", 1), ("gp", 3), ("nich", 3)], density=0.6, seed=13)
+e = Engine(abi, device=rank if backend == "nccl" else 0)
+e.set_model(model); e.set_rows(rows)
+for k in range(model.n_kinds):      # identical state on every rank
+    a = truth["assign"][k].astype(np.uint32)
+    uniq, inv = np.unique(a, return_inverse=True)
+    e.set_groups(k, len(uniq)); e.set_assignments(k, inv.astype(np.uint32))
+e.accumulate_rows()
+e.init_featureless_kinds(4, seed=3)
+full = e.kind_proposer_score()                      # single-rank reference
+sharded = sharded_kind_proposer_score(e, rank, world)
+err = np.abs(sharded.astype(np.float64) - full) / np.maximum(1.0, np.abs(full))
+assert err.max() <= 1e-6, err.max()
+f2k, n = e.kind_run(8, seed=5)                       # same seed -> same structure on every rank
+out = torch.tensor(f2k.astype(np.int64))
+if backend == "nccl": out = out.cuda()
+gathered = [torch.zeros_like(out) for _ in range(world)]
+dist.all_gather(gathered, out)
+assert all(torch.equal(g, gathered[0]) for g in gathered)
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ok.%d" % rank), "w").write("%g %d" % (float(err.max()), int(n)))
+dist.destroy_process_group()
+'''
+
+
+def _run(backend, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(repo=REPO))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), backend],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists(), out.stdout + out.stderr[-2000:]
+
+
+def test_row_sharded_proposer_gloo_cpu(oracle_abi, tmp_path):
+    _run("gloo", tmp_path)
+
+
+@pytest.mark.gpu
+def test_row_sharded_proposer_nccl(cuda_abi, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("nccl", tmp_path)
