@@ -136,6 +136,23 @@ int LB_NAME(set_model)(lb_handle h, int32_t n_features, const lb_feature_spec *s
 int LB_NAME(set_rows)(lb_handle h, uint64_t n_rows, const uint8_t *cat8,
                       const uint32_t *wide, const uint32_t *mask);
 
+/* Tare-compressed rows: ProductValue::Diff{pos, neg, tares} (src/schema.proto:87-91) as
+ * produced by loom's tare + sparsify passes (src/differ.cc:191-298; worked example
+ * doc/adapting.md:323-414) with ONE tare row, which is all the automatic pass emits.
+ * true row = (row_has_tare ? tare : nothing) + pos - neg.  The block is decoded on the device
+ * into the same dense columns set_rows uploads, so score_diff / add_diff / remove_diff
+ * (src/product_mixture.cc:241-306, 436-463) reduce to score_value / add_value / remove_value
+ * of the reconstructed row -- identical sufficient statistics and scores, no tare caches.
+ *   tare_observed [F] (0/1), tare_values [F] raw cell value of the tare row
+ *   row_has_tare  [R] (0/1), NULL = every row references the tare
+ *   pos_ptr [R+1], pos_feature [nnz], pos_value [nnz] : cells set by the row (CSR by row)
+ *   neg_ptr [R+1], neg_feature [nnz]                  : tare cells the row removes */
+int LB_NAME(set_rows_diff)(lb_handle h, uint64_t n_rows, const uint8_t *tare_observed,
+                           const uint32_t *tare_values, const uint8_t *row_has_tare,
+                           const uint64_t *pos_ptr, const uint32_t *pos_feature,
+                           const uint32_t *pos_value, const uint64_t *neg_ptr,
+                           const uint32_t *neg_feature);
+
 /* CatKernel::add_row / remove_row over a list of actions, every kind
  * (src/cat_kernel.hpp:177-299; scheduling of src/cat_pipeline.cc:103-125):
  * exact single-site Gibbs, sequential in action order inside each kind, kinds

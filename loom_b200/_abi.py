@@ -51,6 +51,7 @@ SIGNATURES = {
     "set_model": (C.c_int, [_h, C.c_int32, C.POINTER(FeatureSpec), _f32p, C.c_int32, C.c_int32,
                             _u32p, _f32p, _f32p, C.c_int32]),
     "set_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
+    "set_rows_diff": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u8p, _u64p, _u32p, _u32p, _u64p, _u32p]),
     "cat_sweep": (C.c_int, [_h, _u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u32p, _f32p,
                             C.c_int32]),
     "get_assignments": (C.c_int, [_h, C.c_int32, _u32p]),

@@ -374,6 +374,104 @@ extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const u
 }
 
 // ---------------------------------------------------------------------------
+// Tare-compressed rows: decode Diff{pos,neg,tares} into the dense columns on the device.
+__global__ void k_diff_fill(const FeatDev *feats, int F, const uint8_t *tare_obs, const uint32_t *tare_val,
+                            const uint8_t *row_has_tare, uint64_t R, uint64_t W, uint8_t *cat8, uint32_t *wide,
+                            uint32_t *mask) {
+    const int f = blockIdx.y;
+    const FeatDev &fd = feats[f];
+    const bool obs = tare_obs[f] != 0;
+    const uint32_t v = tare_val[f];
+    // one thread per mask word: 32 consecutive rows of this feature's column
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < W; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t bits = 0;
+        for (int k = 0; k < 32; ++k) {
+            const uint64_t r = 32 * w + k;
+            if (r >= R) break;
+            const bool on = obs && (!row_has_tare || row_has_tare[r]);
+            if (on) bits |= 1u << k;
+            if (fd.is_wide) wide[(uint64_t)fd.col * R + r] = on ? v : 0u;
+            else cat8[(uint64_t)fd.col * R + r] = on ? (uint8_t)v : (uint8_t)0;
+        }
+        mask[(uint64_t)f * W + w] = bits;
+    }
+}
+__global__ void k_diff_apply(const FeatDev *feats, int F, uint64_t R, uint64_t W, const uint64_t *pos_ptr,
+                             const uint32_t *pos_feature, const uint32_t *pos_value, const uint64_t *neg_ptr,
+                             const uint32_t *neg_feature, uint8_t *cat8, uint32_t *wide, uint32_t *mask,
+                             int32_t *flag) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t bit = 1u << (r & 31);
+        for (uint64_t i = neg_ptr[r]; i < neg_ptr[r + 1]; ++i) {
+            const uint32_t f = neg_feature[i];
+            if (f >= (uint32_t)F) { *flag = 1; continue; }
+            const uint32_t old = atomicAnd(&mask[(uint64_t)f * W + (r >> 5)], ~bit);
+            if (!(old & bit)) *flag = 1;       // neg must remove a cell the tare holds
+        }
+        for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1]; ++i) {
+            const uint32_t f = pos_feature[i];
+            if (f >= (uint32_t)F) { *flag = 1; continue; }
+            const FeatDev &fd = feats[f];
+            if (fd.is_wide) wide[(uint64_t)fd.col * R + r] = pos_value[i];
+            else cat8[(uint64_t)fd.col * R + r] = (uint8_t)pos_value[i];
+            const uint32_t old = atomicOr(&mask[(uint64_t)f * W + (r >> 5)], bit);
+            if (old & bit) *flag = 1;          // pos must not overwrite a live cell
+        }
+    }
+}
+
+extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs, const uint32_t *tare_val,
+                                const uint8_t *row_has_tare, const uint64_t *pos_ptr, const uint32_t *pos_feature,
+                                const uint32_t *pos_value, const uint64_t *neg_ptr, const uint32_t *neg_feature) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("set_rows_diff before set_model");
+    if (R >= (1ull << 31)) return lb_fail("set_rows_diff: at most 2^31-1 rows per block");
+    const int F = e->F;
+    if (R != e->R || !e->d_mask) {
+        dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
+        e->R = R; e->W = (R + 31) / 32;
+        LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
+        LB_TRY(dev_alloc(&e->d_wide, (size_t)e->FW * R));
+        LB_TRY(dev_alloc(&e->d_mask, (size_t)F * e->W));
+        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, R)); }
+    }
+    for (auto &k : e->kinds) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)R, e->stream));
+    LB_TRY(lb_sync_model(e));
+    const uint64_t n_pos = pos_ptr[R], n_neg = neg_ptr[R];
+    // one staging buffer for the compressed block
+    const size_t sz[] = {(size_t)F, 4 * (size_t)F, row_has_tare ? (size_t)R : 0, 8 * (size_t)(R + 1), 4 * (size_t)n_pos,
+                         4 * (size_t)n_pos, 8 * (size_t)(R + 1), 4 * (size_t)n_neg};
+    size_t off[9] = {0};
+    for (int i = 0; i < 8; ++i) off[i + 1] = ((off[i] + sz[i] + 255) / 256) * 256;
+    LB_TRY(lb_ensure_scratch(e, off[8] + 256));
+    char *base = (char *)e->d_scratch;
+    const void *src[] = {tare_obs, tare_val, row_has_tare, pos_ptr, pos_feature, pos_value, neg_ptr, neg_feature};
+    for (int i = 0; i < 8; ++i)
+        if (sz[i]) LB_CUDA(cudaMemcpyAsync(base + off[i], src[i], sz[i], cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemsetAsync(e->d_flag, 0, 4, e->stream));
+    dim3 grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((e->W + 127) / 128, 512)), (unsigned)F);
+    k_diff_fill<<<grid, 128, 0, e->stream>>>(e->d_feats, F, (const uint8_t *)(base + off[0]), (const uint32_t *)(base + off[1]),
+                                            row_has_tare ? (const uint8_t *)(base + off[2]) : nullptr, R, e->W,
+                                            e->d_cat8, e->d_wide, e->d_mask);
+    const int ag = (int)std::max<uint64_t>(1, std::min<uint64_t>((R + 255) / 256, (uint64_t)e->n_sm * 8));
+    k_diff_apply<<<ag, 256, 0, e->stream>>>(e->d_feats, F, R, e->W, (const uint64_t *)(base + off[3]),
+                                            (const uint32_t *)(base + off[4]), (const uint32_t *)(base + off[5]),
+                                            (const uint64_t *)(base + off[6]), (const uint32_t *)(base + off[7]),
+                                            e->d_cat8, e->d_wide, e->d_mask, e->d_flag);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_MISC] += 2;
+    int flag = 0;
+    LB_CUDA(cudaMemcpyAsync(&flag, e->d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (flag) return lb_fail("set_rows_diff: neg removes a cell the tare does not hold, or pos overwrites a live cell");
+    int bad = 0;
+    LB_TRY(lb_launch_validate_rows(e, &bad));
+    if (bad) return lb_fail("set_rows_diff: an observed categorical value is out of range for its feature");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, uint64_t seed,
                             uint64_t offset, const uint8_t *kind_mask, uint32_t *debug_picks,
                             float *debug_scores, int32_t stride) {

@@ -190,6 +190,18 @@ class Engine:
                            ptr(rows.mask, _u32p)))
         self.n_rows = rows.n_rows
 
+    def set_rows_diff(self, n_rows, tare_observed, tare_values, row_has_tare, pos_ptr, pos_feature, pos_value,
+                      neg_ptr, neg_feature):
+        """Tare-compressed rows (ProductValue::Diff), see loom_b200/tare.py."""
+        c = lambda x, dt: None if x is None else np.ascontiguousarray(x, dtype=dt)
+        to, tv, rh = c(tare_observed, np.uint8), c(tare_values, np.uint32), c(row_has_tare, np.uint8)
+        pp, pf, pv = c(pos_ptr, np.uint64), c(pos_feature, np.uint32), c(pos_value, np.uint32)
+        npt, nf = c(neg_ptr, np.uint64), c(neg_feature, np.uint32)
+        a = self.abi
+        a.check(a.set_rows_diff(self.h, n_rows, ptr(to, _u8p), ptr(tv, _u32p), ptr(rh, _u8p), ptr(pp, _abi._u64p),
+                                ptr(pf, _u32p), ptr(pv, _u32p), ptr(npt, _abi._u64p), ptr(nf, _u32p)))
+        self.n_rows = int(n_rows)
+
     def n_kinds(self):
         n = C.c_int32()
         self.abi.check(self.abi.get_kinds(self.h, C.byref(n), None))

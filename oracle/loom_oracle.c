@@ -283,6 +283,45 @@ int lo_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wi
     return 0;
 }
 
+/* Tare-compressed rows (src/differ.cc:248-298): reconstruct true row = tare + pos - neg. */
+int lo_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs, const uint32_t *tare_val,
+                     const uint8_t *row_has_tare, const uint64_t *pos_ptr, const uint32_t *pos_feature,
+                     const uint32_t *pos_value, const uint64_t *neg_ptr, const uint32_t *neg_feature) {
+    engine_t *e = h;
+    if (!e->F) return lo_fail("set_rows_diff before set_model");
+    const int F = e->F, F8 = e->F8;
+    const uint64_t W = (R + 31) / 32;
+    uint8_t *cat8 = xcalloc((size_t)F8 * R, 1);
+    uint32_t *wide = xcalloc((size_t)(F - F8) * R, 4);
+    uint32_t *mask = xcalloc((size_t)F * W, 4);
+    int rc = 0;
+    for (uint64_t r = 0; r < R && !rc; ++r) {
+        if (!row_has_tare || row_has_tare[r])
+            for (int f = 0; f < F; ++f)
+                if (tare_obs[f]) {
+                    if (f < F8) cat8[(size_t)f * R + r] = (uint8_t)tare_val[f];
+                    else wide[(size_t)(f - F8) * R + r] = tare_val[f];
+                    mask[(size_t)f * W + (r >> 5)] |= 1u << (r & 31);
+                }
+        for (uint64_t i = neg_ptr[r]; i < neg_ptr[r + 1]; ++i) {
+            const uint32_t f = neg_feature[i];
+            if (f >= (uint32_t)F || !((mask[(size_t)f * W + (r >> 5)] >> (r & 31)) & 1u)) { rc = 1; break; }
+            mask[(size_t)f * W + (r >> 5)] &= ~(1u << (r & 31));
+        }
+        for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1] && !rc; ++i) {
+            const uint32_t f = pos_feature[i];
+            if (f >= (uint32_t)F || ((mask[(size_t)f * W + (r >> 5)] >> (r & 31)) & 1u)) { rc = 1; break; }
+            if (f < (uint32_t)F8) cat8[(size_t)f * R + r] = (uint8_t)pos_value[i];
+            else wide[(size_t)(f - F8) * R + r] = pos_value[i];
+            mask[(size_t)f * W + (r >> 5)] |= 1u << (r & 31);
+        }
+    }
+    if (!rc) rc = lo_set_rows(h, R, cat8, wide, mask);
+    else rc = lo_fail("set_rows_diff: neg removes a cell the tare does not hold, or pos overwrites a live cell");
+    free(cat8); free(wide); free(mask);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------ */
 /* ProductMixture_<true>::score_value (src/product_mixture.cc:421-434):
  * clustering prior, then one cached-scorer pass per observed feature. */
