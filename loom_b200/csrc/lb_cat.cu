@@ -45,6 +45,7 @@ struct SweepSmem {
     uint32_t removed_global[2], next_global;
     unsigned long long sample_size;
     float u[2];
+    uint32_t pf_assign[4];         // prefetched assignment of the row of each ring slot
     int cls_begin[N_CLASS], cls_end[N_CLASS];
     int warp_cls[SW_WARPS], warp_rank[SW_WARPS], warp_nw[SW_WARPS];
 };
@@ -69,7 +70,7 @@ __device__ __forceinline__ int warp_sample(float *scores, int G, float u, int la
     const int lo = lane * per, hi = min(G, lo + per);
     float local = 0.f;
     for (int g = lo; g < hi; ++g) {
-        const float p = expf(scores[g] - m);
+        const float p = __expf(scores[g] - m);
         scores[g] = p;
         local += p;
     }
@@ -180,9 +181,9 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
     uint32_t *s_obs = s_raw + 4 * nf;                    // [4][nf]
     float *s_score = (float *)(s_obs + 4 * nf);          // [st]
     float *s_part = s_score + st;                        // [SW_WARPS][st]
+    uint32_t *s_counts = (uint32_t *)(s_part + SW_WARPS * st);   // [st] clustering counts
+    float *s_prior = (float *)(s_counts + st);           // [st] CRP prior per group, empties included
 
-    uint32_t *const counts = kd.counts;
-    float *const shifted = kd.shifted;
     uint32_t *const ints = kd.ints;
     double *const flts = kd.flts;
     float *const cache = kd.cache;
@@ -196,6 +197,15 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         const int fid = kind_feats[kd.feat_begin + j];
         s_feat[j] = feats[fid];
         s_fid[j] = fid;
+    }
+    {   // clustering state lives in shared memory for the whole launch (written back at the end)
+        const int G0 = kd.G;
+        const float sh_empty0 = logf((alpha + d * (float)(G0 - n_empty)) / (float)n_empty);
+        for (int g = tid; g < st; g += SW_THREADS) {
+            const uint32_t n = g < G0 ? kd.counts[g] : 0u;
+            s_counts[g] = n;
+            s_prior[g] = n ? logf((float)n - d) : sh_empty0;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -236,10 +246,15 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
 
     uint64_t i = kd.progress;
     // row cells of action `idx`: global -> registers, later registers -> ring slot
-    uint32_t pf_raw[SW_PF], pf_obs[SW_PF];
+    uint32_t pf_raw[SW_PF], pf_obs[SW_PF], pf_assign = LB_UNASSIGNED;
     auto prefetch = [&](uint64_t idx) {
+        if (tid == 0 && idx < n_actions) {
+            const uint64_t r = actions[idx] >> 1;
+            if (r < rows.R) pf_assign = assign[r];     // this row's assignment (validated for staleness at use)
+        }
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
+            if (q * SW_THREADS + warp * 32 >= nf) break;   // warp-uniform: this warp owns no cells of the row
             const int j = tid + q * SW_THREADS;
             pf_raw[q] = 0; pf_obs[q] = 0;
             if (j < nf && idx < n_actions) {
@@ -254,8 +269,10 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         }
     };
     auto commit = [&](int slot) {
+        if (tid == 0) ss->pf_assign[slot] = pf_assign;
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
+            if (q * SW_THREADS + warp * 32 >= nf) break;
             const int j = tid + q * SW_THREADS;
             if (j < nf) { s_raw[slot * nf + j] = pf_raw[q]; s_obs[slot * nf + j] = pf_obs[q]; }
         }
@@ -280,6 +297,15 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         __syncwarp();
     };
 
+    const uint64_t i0 = i;
+    // assignment of the row of action idx: the ring value unless one of the two actions that ran
+    // after the prefetch was issued touched the same row (thread 0 only)
+    auto row_assignment = [&](uint64_t idx, uint64_t r) -> uint32_t {
+        bool fresh = true;
+        for (int dd = 1; dd <= 2; ++dd)
+            if (idx >= i0 + dd && (actions[idx - dd] >> 1) == r) fresh = false;
+        return fresh ? ss->pf_assign[idx & 3] : assign[r];
+    };
     int status = LB_ST_OK;
     for (; i < n_actions; ++i) {
         const uint32_t act = actions[i];
@@ -294,7 +320,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         if (!is_remove) {
             // ---- ADD: model.add_value -> score_value -> sample -> add_value ----
             if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
-            if (tid == 0 && assign[r] != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
+            if (tid == 0 && row_assignment(i, r) != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
             for (int g0 = 0; g0 < G; g0 += 128) {
                 float acc[4];
                 const int left = G - g0;
@@ -314,26 +340,25 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
             __syncthreads();  // (A) partial scores visible
             if (ss->stop) { status = ss->stop; break; }
             if (warp == 0) {
-                // clustering.score_value: CRP prior (SURVEY.md 8c Pitman-Yor)
-                const float base = -logf((float)ss->sample_size + alpha);
-                const float sh_empty = logf((alpha + d * (float)(G - n_empty)) / (float)n_empty);
+                // clustering.score_value: CRP prior (SURVEY.md 8c Pitman-Yor).  The common
+                // -log(n + alpha) term does not affect the draw; it is added for the debug tap only.
                 for (int g = lane; g < G; g += 32) {
-                    float s = (counts[g] ? shifted[g] : sh_empty) + base;
+                    float s = s_prior[g];
 #pragma unroll
                     for (int w = 0; w < SW_WARPS; ++w) s += s_part[w * st + g];
                     s_score[g] = s;
                     if (dbg_scores && g < dbg_stride)
-                        dbg_scores[((uint64_t)i * K + kid) * dbg_stride + g] = s;
+                        dbg_scores[((uint64_t)i * K + kid) * dbg_stride + g] = s - logf((float)ss->sample_size + alpha);
                 }
                 __syncwarp();
                 const int pick = warp_sample(s_score, G, ss->u[i & 1], lane);
                 if (lane == 0) {
                     // clustering.add_value + push global id (cat_kernel.hpp:222-223)
-                    const uint32_t n = counts[pick] + 1u;
+                    const uint32_t n = s_counts[pick] + 1u;
                     ss->pick[i & 1] = pick;
                     ss->flag[i & 1] = n == 1u;
-                    counts[pick] = n;
-                    shifted[pick] = logf((float)n - d);
+                    s_counts[pick] = n;
+                    s_prior[pick] = logf((float)n - d);
                     ss->sample_size += 1;
                     assign[r] = p2g[pick];
                     if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)pick;
@@ -358,7 +383,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                                    cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
                 }
                 if (tid == 0) {
-                    counts[ng] = 0u; shifted[ng] = 0.f;
+                    s_counts[ng] = 0u;
                     const uint32_t gid = ss->next_global;
                     p2g[ng] = gid;
                     g2p[gid] = (uint32_t)ng;
@@ -366,20 +391,25 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                     ss->G = ng + 1;
                 }
                 __syncthreads();
+                {   // one more occupied group: refresh the prior of the empty groups
+                    const float she = logf((alpha + d * (float)(ng + 1 - n_empty)) / (float)n_empty);
+                    for (int gg = tid; gg <= ng; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
+                }
+                __syncthreads();
             }
         } else {
             // ---- REMOVE: pop global id -> packed; mixture.remove_value ----
             if (tid == 0) {
-                const uint32_t a = assign[r];
+                const uint32_t a = row_assignment(i, r);
                 if (a == LB_UNASSIGNED) ss->stop = LB_ST_REMOVE_UNASSIGNED;
                 else {
                     const uint32_t g = g2p[a];
-                    const uint32_t n = counts[g] - 1u;
+                    const uint32_t n = s_counts[g] - 1u;
                     ss->pick[i & 1] = (int)g;
                     ss->removed_global[i & 1] = a;
                     ss->flag[i & 1] = n == 0u;
-                    counts[g] = n;
-                    shifted[g] = n ? logf((float)n - d) : 0.f;
+                    s_counts[g] = n;
+                    if (n) s_prior[g] = logf((float)n - d);
                     ss->sample_size -= 1;
                     assign[r] = LB_UNASSIGNED;
                     if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = g;
@@ -406,19 +436,30 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                 if (tid == 0) {
                     g2p[ss->removed_global[i & 1]] = LB_UNASSIGNED;
                     if (g != last) {
-                        counts[g] = counts[last];
-                        shifted[g] = shifted[last];
+                        s_counts[g] = s_counts[last];
+                        s_prior[g] = s_prior[last];
                         const uint32_t gid = p2g[last];
                         p2g[g] = gid;
                         g2p[gid] = (uint32_t)g;
                     }
+                    s_counts[last] = 0u;
                     ss->G = last;
+                }
+                __syncthreads();
+                {   // one occupied group fewer: refresh the prior of the empty groups
+                    const float she = logf((alpha + d * (float)(last - n_empty)) / (float)n_empty);
+                    for (int gg = tid; gg < last; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
                 }
                 __syncthreads();
             }
         }
     }
     __syncthreads();
+    for (int g = tid; g < st; g += SW_THREADS) {
+        const uint32_t n = s_counts[g];
+        kd.counts[g] = n;
+        kd.shifted[g] = n ? s_prior[g] : 0.f;
+    }
     if (tid == 0) {
         kd.G = ss->G;
         kd.sample_size = ss->sample_size;
@@ -429,7 +470,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
 }
 
 static size_t sweep_smem_bytes(int nf, int Gcap) {
-    return 256 + (size_t)nf * (sizeof(FeatDev) + 4 + 32) + (size_t)Gcap * 4 * (1 + SW_WARPS) + 64;
+    return 256 + (size_t)nf * (sizeof(FeatDev) + 4 + 32) + (size_t)Gcap * 4 * (3 + SW_WARPS) + 64;
 }
 
 int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
