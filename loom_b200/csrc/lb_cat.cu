@@ -163,11 +163,15 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
 k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const int32_t *kind_feats,
             const float *aux, RowsDev rows, const uint32_t *actions, uint64_t n_actions,
             uint64_t seed, uint64_t offset, int K, int n_empty, uint32_t *dbg_picks,
-            float *dbg_scores, int dbg_stride) {
+            float *dbg_scores, int dbg_stride, unsigned long long *prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int kid = kind_ids[blockIdx.x];
     KindDev &kd = kinds[kid];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // LB_PROFILE=1: cycles per phase seen by lane 0 of every warp
+    // 0 own phase-1 work | 1 wait at (A) | 2 sample / commit | 3 wait at (B) | 4 update
+    long long pt[6] = {0, 0, 0, 0, 0, 0}, pc = 0;
+#define LB_TICK(k) do { if (prof && lane == 0) { const long long now__ = clock64(); pt[k] += now__ - pc; pc = now__; } } while (0)
     const int nf = kd.nf, st = kd.Gcap;
     const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
     const int zero_row = n_cache_rows;
@@ -315,6 +319,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
         if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
         const int G = ss->G;
+        if (prof && lane == 0) pc = clock64();
         prefetch(i + 2);   // latency overlaps this action's work
 
         if (!is_remove) {
@@ -337,8 +342,10 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                     for (int jj = 0; jj < 4; ++jj) s_part[warp * st + g0 + lane + 32 * jj] = acc[jj];
                 }
             }
+            LB_TICK(0);
             __syncthreads();  // (A) partial scores visible
             if (ss->stop) { status = ss->stop; break; }
+            LB_TICK(1);       // after a barrier-dependent read (BAR.SYNC is deferred-blocking)
             if (warp == 0) {
                 // clustering.score_value: CRP prior (SURVEY.md 8c Pitman-Yor).  The common
                 // -log(n + alpha) term does not affect the draw; it is added for the debug tap only.
@@ -367,10 +374,13 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                 commit((int)((i + 2) & 3));
                 next_uniform(i + 1);
             }
+            LB_TICK(2);
             __syncthreads();  // (B) pick visible
             if (warp == 0) commit((int)((i + 2) & 3));
             const int g = ss->pick[i & 1];
+            if (g >= 0) LB_TICK(3);
             update_stripe(c_raw, c_obs, g, +1);
+            LB_TICK(4);
             if (ss->flag[i & 1]) {
                 // add_group (product_mixture.cc:178-183): append a fresh empty group
                 const int ng = G;
@@ -417,10 +427,13 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
             }
             commit((int)((i + 2) & 3));
             next_uniform(i + 1);
+            LB_TICK(0);
             __syncthreads();  // (A)
             if (ss->stop) { status = ss->stop; break; }
             const int g = ss->pick[i & 1];
+            if (g >= 0) LB_TICK(1);
             update_stripe(c_raw, c_obs, g, -1);
+            LB_TICK(4);
             if (ss->flag[i & 1]) {
                 // remove_group (product_mixture.cc:233-238): swap-with-last
                 __syncthreads();
@@ -467,6 +480,9 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         kd.status = status;
         kd.progress = i;
     }
+    if (prof && lane == 0 && kid < 16)
+        for (int k = 0; k < 6; ++k) prof[(kid * SW_WARPS + warp) * 8 + k] += (unsigned long long)pt[k];
+#undef LB_TICK
 }
 
 static size_t sweep_smem_bytes(int nf, int Gcap) {
@@ -501,7 +517,7 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
     LB_CUDA(cudaEventRecord(e->kev0, e->stream));
     k_cat_sweep<<<(unsigned)kind_ids.size(), SW_THREADS, smem, e->stream>>>(
         e->d_kinds, d_ids, e->d_feats, e->d_kind_feats, e->d_aux, rows, e->d_actions, n_actions, seed,
-        offset, (int)e->kinds.size(), e->empty_group_count, d_picks, d_scores, stride);
+        offset, (int)e->kinds.size(), e->empty_group_count, d_picks, d_scores, stride, e->d_prof);
     LB_CUDA(cudaGetLastError());
     LB_CUDA(cudaEventRecord(e->kev1, e->stream));
     e->kev_pending = true;

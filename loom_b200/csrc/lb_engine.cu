@@ -269,6 +269,10 @@ extern "C" int lb_create(int device, lb_handle *out) {
     LB_CUDA(cudaGetDeviceProperties(&prop, device));
     e->n_sm = prop.multiProcessorCount;
     LB_TRY(dev_alloc(&e->d_flag, 4));
+    if (getenv("LB_PROFILE")) {
+        LB_TRY(dev_alloc(&e->d_prof, 16 * 8 * 8));
+        LB_CUDA(cudaMemset(e->d_prof, 0, 8 * 16 * 8 * 8));
+    }
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -294,6 +298,20 @@ extern "C" void lb_destroy(lb_handle h) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    if (e->d_prof) {
+        std::vector<unsigned long long> p(16 * 8 * 8);
+        cudaMemcpy(p.data(), e->d_prof, 8 * p.size(), cudaMemcpyDeviceToHost);
+        const char *names[6] = {"work1", "waitA", "sample", "waitB", "update", "rare"};
+        for (size_t k = 0; k < e->kinds.size() && k < 16; ++k) {
+            fprintf(stderr, "[LB_PROFILE] kind %zu nf=%zu (Mcycles per warp 0..7)\n", k, e->kinds[k].fids.size());
+            for (int j = 0; j < 5; ++j) {
+                fprintf(stderr, "[LB_PROFILE]   %-6s", names[j]);
+                for (int w = 0; w < 8; ++w) fprintf(stderr, " %7.0f", p[(k * 8 + w) * 8 + j] * 1e-6);
+                fprintf(stderr, "\n");
+            }
+        }
+        cudaFree(e->d_prof);
+    }
     clear_model(e);
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);

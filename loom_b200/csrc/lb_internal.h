@@ -88,6 +88,7 @@ struct Engine {
     double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;
     bool kev_pending = false;
+    unsigned long long *d_prof = nullptr;  // LB_PROFILE=1: per-kind, per-warp phase cycles of the sweep
 };
 
 // launch-family indices for launch_count

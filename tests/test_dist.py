@@ -50,9 +50,46 @@ dist.destroy_process_group()
 '''
 
 
-def _run(backend, tmp_path):
+KIND_SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np
+import torch, torch.distributed as dist
+from loom_b200 import Engine, _abi, synth, sweep_actions
+backend = sys.argv[1]
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+if backend == "nccl":
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    abi = _abi.load_cuda()
+else:
+    dist.init_process_group("gloo")
+    abi = _abi.Abi(os.path.join({repo!r}, "oracle", "libloom_oracle.so"), "lo_")
+model, rows, _ = synth.generate(800, [("bb", 4), ("dd16", 4), ("gp", 4), ("nich", 3)], density=0.6, seed=17)
+K = model.n_kinds
+acts = np.concatenate([sweep_actions(800), sweep_actions(800, add=True, remove=True)])
+# kinds are independent (doc/adapting.md:144-147): rank r sweeps kinds k with k % world == r
+e = Engine(abi, device=rank if backend == "nccl" else 0)
+e.set_model(model); e.set_rows(rows)
+mask = np.array([k % world == rank for k in range(K)], np.uint8)
+e.cat_sweep(acts, seed=21, kind_mask=mask)
+mine = np.stack([e.get_assignments(k) if mask[k] else np.zeros(800, np.uint32) for k in range(K)]).astype(np.int64)
+t = torch.tensor(mine)
+if backend == "nccl": t = t.cuda()
+dist.all_reduce(t)                                   # gather of disjoint kind columns
+ref = Engine(abi, device=rank if backend == "nccl" else 0)
+ref.set_model(model); ref.set_rows(rows)
+ref.cat_sweep(acts, seed=21)                         # all kinds on one device
+full = np.stack([ref.get_assignments(k) for k in range(K)]).astype(np.int64)
+assert np.array_equal(t.cpu().numpy(), full)
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ok.%d" % rank), "w").write("1")
+dist.destroy_process_group()
+'''
+
+
+def _run(backend, tmp_path, worker=None):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(repo=REPO))
+    script.write_text((worker or WORKER).format(repo=REPO))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script), backend],
@@ -71,3 +108,16 @@ def test_row_sharded_proposer_nccl(cuda_abi, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run("nccl", tmp_path)
+
+
+def test_kind_sharded_sweep_gloo_cpu(oracle_abi, tmp_path):
+    """cat sweep with kinds sharded over 2 ranks == the same sweep on one rank (no data-path collective)."""
+    _run("gloo", tmp_path, KIND_SHARD_WORKER)
+
+
+@pytest.mark.gpu
+def test_kind_sharded_sweep_nccl(cuda_abi, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("nccl", tmp_path, KIND_SHARD_WORKER)
