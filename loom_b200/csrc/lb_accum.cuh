@@ -13,6 +13,7 @@
 #include "lb_common.cuh"
 
 constexpr int ACC_THREADS = 256;
+constexpr int ACC_UNROLL = 4;
 
 __host__ __device__ inline int lb_acc_int_rows(int type, int dim) {
     return type == LB_BB ? 2 : ((type == LB_DD || type == LB_DPD) ? dim + 1 : (type == LB_GP ? 2 : 1));
@@ -27,8 +28,12 @@ __host__ __device__ inline size_t lb_acc_smem_bytes(int type, int dim, int G) {
 // feats: FeatDev table whose int_row / flt_row address the TARGET tables; fid_list maps
 // blockIdx.y to a global feature id (nullptr: identity).  packed: packed group id per row.
 // Moment rows of the target hold SUMS while accumulating (sum x, sum x^2 / sum log x!).
+// PT: storage type of the packed group ids (uint8_t when G < 255, uint16_t when G < 65535, else
+// uint32_t; the all-ones value means "unassigned").  Narrow ids matter: the id column is re-read
+// once per (feature, kind) and is the largest stream of the proposer accumulate.
+template <typename PT>
 __global__ void __launch_bounds__(ACC_THREADS)
-k_accum_feature(const FeatDev *feats, const int32_t *fid_list, RowsDev rows, const uint32_t *packed,
+k_accum_feature(const FeatDev *feats, const int32_t *fid_list, RowsDev rows, const PT *packed,
                 uint64_t b, uint64_t en, uint64_t rows_per_cta, int sign, uint32_t *ints, double *flts,
                 int st, int G, int use_smem) {
     extern __shared__ __align__(16) unsigned char acc_smem[];
@@ -49,52 +54,70 @@ k_accum_feature(const FeatDev *feats, const int32_t *fid_list, RowsDev rows, con
         for (int i = threadIdx.x; i < nir * G; i += ACC_THREADS) si[i] = 0u;
         __syncthreads();
     }
-    for (uint64_t r = r_lo + threadIdx.x; r < r_hi; r += ACC_THREADS) {
-        const uint32_t g = packed[r];
-        if (g == LB_UNASSIGNED) continue;
-        if (!((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-        const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                       : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-        if (smem_ok) {
-            switch (f.type) {
-            case LB_BB: atomicAdd(&si[(raw ? 0 : 1) * G + g], 1u); break;
-            case LB_DD:
-            case LB_DPD: atomicAdd(&si[(size_t)raw * G + g], 1u); break;
-            case LB_GP:
-                atomicAdd(&si[g], 1u);
-                atomicAdd(&si[G + g], raw);
-                atomicAdd(&sf[g], lb_log_factorial_d(raw));
-                break;
-            case LB_NICH: {
-                const double x = (double)__uint_as_float(raw);
-                atomicAdd(&si[g], 1u);
-                atomicAdd(&sf[g], x);
-                atomicAdd(&sf[G + g], x * x);
-                break;
-            }
-            }
-        } else {
-            uint32_t *in = gi + g;
-            double *fl = gf + g;
-            switch (f.type) {
-            case LB_BB: atomicAdd(&in[raw ? 0 : st], (uint32_t)sign); break;
-            case LB_DD:
-            case LB_DPD:
-                atomicAdd(&in[(size_t)raw * st], (uint32_t)sign);
-                atomicAdd(&in[(size_t)f.dim * st], (uint32_t)sign);
-                break;
-            case LB_GP:
-                atomicAdd(&in[0], (uint32_t)sign);
-                atomicAdd(&in[st], (uint32_t)(sign * (int64_t)raw));
-                atomicAdd(&fl[0], sign * lb_log_factorial_d(raw));
-                break;
-            case LB_NICH: {
-                const double x = (double)__uint_as_float(raw);
-                atomicAdd(&in[0], (uint32_t)sign);
-                atomicAdd(&fl[0], sign * x);
-                atomicAdd(&fl[st], sign * x * x);
-                break;
-            }
+    // ACC_UNROLL rows per thread per trip, all loads issued before any is used: the id, mask and
+    // value loads of one row are independent (unobserved cells are loaded and ignored), so a trip
+    // keeps 3 * ACC_UNROLL requests in flight instead of three serialised L2 round trips per row.
+    const uint8_t *col8 = f.is_wide ? nullptr : rows.cat8 + (uint64_t)f.col * rows.R;
+    const uint32_t *col32 = f.is_wide ? rows.wide + (uint64_t)f.col * rows.R : nullptr;
+    for (uint64_t base = r_lo; base < r_hi; base += (uint64_t)ACC_UNROLL * ACC_THREADS) {
+        PT pgs[ACC_UNROLL];
+        uint32_t mws[ACC_UNROLL], raws[ACC_UNROLL];
+#pragma unroll
+        for (int j = 0; j < ACC_UNROLL; ++j) {
+            const uint64_t r = base + (uint64_t)j * ACC_THREADS + threadIdx.x;
+            const bool in = r < r_hi;
+            pgs[j] = in ? packed[r] : (PT)~(PT)0;
+            mws[j] = in ? mask[r >> 5] : 0u;
+            raws[j] = in ? (col32 ? col32[r] : (uint32_t)col8[r]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < ACC_UNROLL; ++j) {
+            const uint64_t r = base + (uint64_t)j * ACC_THREADS + threadIdx.x;
+            if (pgs[j] == (PT)~(PT)0) continue;
+            if (!((mws[j] >> (r & 31)) & 1u)) continue;
+            const uint32_t g = (uint32_t)pgs[j];
+            const uint32_t raw = raws[j];
+            if (smem_ok) {
+                switch (f.type) {
+                case LB_BB: atomicAdd(&si[(raw ? 0 : 1) * G + g], 1u); break;
+                case LB_DD:
+                case LB_DPD: atomicAdd(&si[(size_t)raw * G + g], 1u); break;
+                case LB_GP:
+                    atomicAdd(&si[g], 1u);
+                    atomicAdd(&si[G + g], raw);
+                    atomicAdd(&sf[g], lb_log_factorial_d(raw));
+                    break;
+                case LB_NICH: {
+                    const double x = (double)__uint_as_float(raw);
+                    atomicAdd(&si[g], 1u);
+                    atomicAdd(&sf[g], x);
+                    atomicAdd(&sf[G + g], x * x);
+                    break;
+                }
+                }
+            } else {
+                uint32_t *in = gi + g;
+                double *fl = gf + g;
+                switch (f.type) {
+                case LB_BB: atomicAdd(&in[raw ? 0 : st], (uint32_t)sign); break;
+                case LB_DD:
+                case LB_DPD:
+                    atomicAdd(&in[(size_t)raw * st], (uint32_t)sign);
+                    atomicAdd(&in[(size_t)f.dim * st], (uint32_t)sign);
+                    break;
+                case LB_GP:
+                    atomicAdd(&in[0], (uint32_t)sign);
+                    atomicAdd(&in[st], (uint32_t)(sign * (int64_t)raw));
+                    atomicAdd(&fl[0], sign * lb_log_factorial_d(raw));
+                    break;
+                case LB_NICH: {
+                    const double x = (double)__uint_as_float(raw);
+                    atomicAdd(&in[0], (uint32_t)sign);
+                    atomicAdd(&fl[0], sign * x);
+                    atomicAdd(&fl[st], sign * x * x);
+                    break;
+                }
+                }
             }
         }
     }
@@ -119,17 +142,27 @@ k_accum_feature(const FeatDev *feats, const int32_t *fid_list, RowsDev rows, con
     }
 }
 
+// packed ids of one kind: g2p[assign[r]] narrowed to PT
+template <typename PT>
+__global__ void k_pack_assign_t(const uint32_t *assign, const uint32_t *g2p, PT *packed, uint64_t b, uint64_t en) {
+    for (uint64_t r = b + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < en; r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = assign[r];
+        packed[r] = a == LB_UNASSIGNED ? (PT)~(PT)0 : (PT)g2p[a];
+    }
+}
+
 // clustering counts of the rows [b, en): histogram of the packed ids
+template <typename PT>
 __global__ void __launch_bounds__(ACC_THREADS)
-k_accum_counts(const uint32_t *packed, uint64_t b, uint64_t en, int sign, uint32_t *counts,
+k_accum_counts(const PT *packed, uint64_t b, uint64_t en, int sign, uint32_t *counts,
                unsigned long long *sample_size, int G, int32_t *flag) {
     extern __shared__ __align__(16) unsigned char acc_smem[];
     uint32_t *sc = (uint32_t *)acc_smem;
     for (int g = threadIdx.x; g < G; g += ACC_THREADS) sc[g] = 0u;
     __syncthreads();
     for (uint64_t r = b + blockIdx.x * (uint64_t)ACC_THREADS + threadIdx.x; r < en; r += (uint64_t)gridDim.x * ACC_THREADS) {
-        const uint32_t g = packed[r];
-        if (g != LB_UNASSIGNED) atomicAdd(&sc[g], 1u);
+        const PT g = packed[r];
+        if (g != (PT)~(PT)0) atomicAdd(&sc[(uint32_t)g], 1u);
     }
     __syncthreads();
     unsigned long long local = 0;

@@ -834,25 +834,38 @@ __global__ void k_sums_to_moments(KindDev *kinds, int kid, const FeatDev *feats,
     }
 }
 
-__global__ void k_pack_assign_range(const uint32_t *assign, const uint32_t *g2p, uint32_t *packed, uint64_t b, uint64_t en) {
-    for (uint64_t r = b + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < en; r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = assign[r];
-        packed[r] = a == LB_UNASSIGNED ? LB_UNASSIGNED : g2p[a];
+// bytes per packed id for a kind with G groups
+int lb_packed_width(int G) { return G < 255 ? 1 : (G < 65535 ? 2 : 4); }
+
+int lb_launch_pack_assign(Engine *e, const uint32_t *assign, const uint32_t *g2p, void *d_packed, int G, uint64_t b,
+                          uint64_t en, int launch_family) {
+    if (en <= b) return 0;
+    const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, (uint64_t)e->n_sm * 8));
+    switch (lb_packed_width(G)) {
+    case 1: k_pack_assign_t<uint8_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint8_t *)d_packed, b, en); break;
+    case 2: k_pack_assign_t<uint16_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint16_t *)d_packed, b, en); break;
+    default: k_pack_assign_t<uint32_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint32_t *)d_packed, b, en); break;
     }
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[launch_family]++;
+    return 0;
 }
 
 // Launch k_accum_feature over `fids` (global feature ids), grouped by shared-memory need so
 // that small tables (BB / GP / NICH / low-dimensional DD) keep a high occupancy.
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
-                             const uint32_t *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
+                             const void *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
                              double *flts, int st, int G, int launch_family) {
     if (en <= b || fids.empty()) return 0;
     static bool configured = false;
     const size_t kBig = 200 * 1024, kSmall = 16 * 1024;
     if (!configured) {
-        LB_CUDA(cudaFuncSetAttribute(k_accum_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
+        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
+        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
+        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
         configured = true;
     }
+    const int pw = lb_packed_width(G);
     std::vector<int32_t> cls[3];
     size_t big_need = 0;
     for (int fid : fids) {
@@ -883,8 +896,15 @@ int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vecto
         int32_t *d_list = e->d_fid_list + off;
         LB_CUDA(cudaMemcpyAsync(d_list, cls[c].data(), 4 * cls[c].size(), cudaMemcpyHostToDevice, e->stream));
         dim3 grid(chunks, (unsigned)cls[c].size());
-        k_accum_feature<<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, d_packed, b, en, rows_per_cta,
-                                                                   sign, ints, flts, st, G, (int)smem_of[c]);
+        if (pw == 1)
+            k_accum_feature<uint8_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint8_t *)d_packed, b, en,
+                                                                                rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
+        else if (pw == 2)
+            k_accum_feature<uint16_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint16_t *)d_packed, b, en,
+                                                                                 rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
+        else
+            k_accum_feature<uint32_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint32_t *)d_packed, b, en,
+                                                                                 rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
         LB_CUDA(cudaGetLastError());
         e->launches[LB_L_TOTAL]++; e->launches[launch_family]++;
         off += cls[c].size();
@@ -900,14 +920,19 @@ int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) 
     if (nf) k_moments_to_sums<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
     if (en > b) {
         LB_TRY(lb_ensure_scratch(e, 4 * (size_t)e->R));
-        uint32_t *d_packed = (uint32_t *)e->d_scratch;
+        void *d_packed = e->d_scratch;
         const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, (uint64_t)e->n_sm * 8));
-        k_pack_assign_range<<<pg, 256, 0, e->stream>>>(k.assign, k.g2p, d_packed, b, en);
+        LB_TRY(lb_launch_pack_assign(e, k.assign, k.g2p, d_packed, k.G, b, en, LB_L_ACCUM));
         // clustering.add_value
-        k_accum_counts<<<std::min(pg, e->n_sm * 2), ACC_THREADS, 4 * (size_t)k.G + 16, e->stream>>>(
-            d_packed, b, en, sign, k.counts, (unsigned long long *)((char *)&e->d_kinds[kid] + offsetof(KindDev, sample_size)),
-            k.G, e->d_flag);
-        e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_ACCUM] += 2;
+        unsigned long long *d_ss = (unsigned long long *)((char *)&e->d_kinds[kid] + offsetof(KindDev, sample_size));
+        const int cg = std::min(pg, e->n_sm * 2);
+        const size_t csm = 4 * (size_t)k.G + 16;
+        switch (lb_packed_width(k.G)) {
+        case 1: k_accum_counts<uint8_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint8_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
+        case 2: k_accum_counts<uint16_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint16_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
+        default: k_accum_counts<uint32_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint32_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
+        }
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_ACCUM]++;
         LB_TRY(lb_launch_accum_features(e, e->d_feats, k.fids, d_packed, b, en, sign, k.ints, k.flts, k.Gcap, k.G, LB_L_ACCUM));
     }
     if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);

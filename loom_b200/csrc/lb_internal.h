@@ -23,7 +23,7 @@ struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind
     int G = 0, pst = 0;        // groups, column stride
     uint32_t *ints = nullptr;  // [prop_int_rows][pst]
     double *flts = nullptr;    // [prop_flt_rows][pst]
-    uint32_t *packed = nullptr;  // [R] packed group id of every row in this kind
+    void *packed = nullptr;      // [R] packed group id of every row in this kind (1, 2 or 4 bytes each)
     size_t cap_ints = 0, cap_flts = 0, cap_rows = 0;   // allocated sizes (buffers are reused)
 };
 
@@ -143,8 +143,11 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
-                             const uint32_t *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
+                             const void *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
                              double *flts, int st, int G, int launch_family);
+int lb_packed_width(int G);
+int lb_launch_pack_assign(Engine *e, const uint32_t *assign, const uint32_t *g2p, void *d_packed, int G, uint64_t b,
+                          uint64_t en, int launch_family);
 int lb_launch_refresh(Engine *e, int kid);
 int lb_launch_restride(Engine *e, const KindHost &src, KindHost &dst);
 int lb_launch_renumber(Engine *e, int kid);

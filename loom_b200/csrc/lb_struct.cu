@@ -45,71 +45,9 @@ void lb_release_proposer(Engine *e) {
 }
 
 // ---------------------------------------------------------------------------
-// K4: proposer accumulate.  grid = (row chunks, F); thread per row.  The
-// all-feature tables are [rows][pst] like the per-kind ones; integer counts
-// are exact atomics, float moments go through double sums.
+// K4: proposer accumulate = k_accum_feature (lb_accum.cuh) over ALL features into the
+// all-feature tables [rows][pst] of every kind, with that kind's packed assignments.
 // ---------------------------------------------------------------------------
-__global__ void k_pack_assign(const uint32_t *assign, const uint32_t *g2p, uint32_t *packed, uint64_t R) {
-    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = assign[r];
-        packed[r] = a == LB_UNASSIGNED ? LB_UNASSIGNED : g2p[a];
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_prop_accumulate(const FeatDev *pfeats, RowsDev rows, const uint32_t *packed, uint32_t *ints, double *flts,
-                  int pst) {
-    const int fid = blockIdx.y;
-    const FeatDev &f = pfeats[fid];
-    const uint32_t *mask = rows.mask + (uint64_t)fid * rows.W;
-    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows.R; r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t g = packed[r];
-        if (g == LB_UNASSIGNED) continue;
-        if (!((mask[r >> 5] >> (r & 31)) & 1u)) continue;
-        const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                       : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-        uint32_t *in = ints + (size_t)f.int_row * pst + g;
-        double *fl = flts + (size_t)f.flt_row * pst + g;
-        switch (f.type) {
-        case LB_BB:
-            atomicAdd(&in[raw ? 0 : pst], 1u);
-            break;
-        case LB_DD:
-        case LB_DPD:
-            atomicAdd(&in[(size_t)raw * pst], 1u);
-            atomicAdd(&in[(size_t)f.dim * pst], 1u);
-            break;
-        case LB_GP:
-            atomicAdd(&in[0], 1u);
-            atomicAdd(&in[pst], raw);
-            atomicAdd(&fl[0], lb_log_factorial_d(raw));
-            break;
-        case LB_NICH: {
-            const double x = (double)__uint_as_float(raw);
-            atomicAdd(&in[0], 1u);
-            atomicAdd(&fl[0], x);
-            atomicAdd(&fl[pst], x * x);
-            break;
-        }
-        }
-    }
-}
-
-__global__ void k_prop_sums_to_moments(const FeatDev *pfeats, int F, uint32_t *ints, double *flts, int pst, int G) {
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < F * G; idx += gridDim.x * blockDim.x) {
-        const int fid = idx / G, g = idx % G;
-        const FeatDev &f = pfeats[fid];
-        if (f.type != LB_NICH) continue;
-        double *fl = flts + (size_t)f.flt_row * pst + g;
-        const double n = (double)ints[(size_t)f.int_row * pst + g];
-        if (n == 0.0) { fl[0] = 0.0; fl[pst] = 0.0; }
-        else {
-            const double mean = fl[0] / n;
-            fl[0] = mean;
-            fl[pst] = fmax(fl[pst] - n * mean * mean, 0.0);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------
 // K5: L[f][k] = sum over groups of the log marginal likelihood of feature f's
@@ -118,26 +56,48 @@ __global__ void k_prop_sums_to_moments(const FeatDev *pfeats, int F, uint32_t *i
 // ---------------------------------------------------------------------------
 __device__ double lb_marginal_group(const FeatDev &f, const float *aux, const uint32_t *in, const double *fl, int st);
 
+struct PropKindDev {       // device view of one kind's proposer tables
+    uint32_t *ints;
+    double *flts;
+    int pst, G;
+};
+
 __global__ void __launch_bounds__(256)
-k_prop_score(const FeatDev *pfeats, const float *aux, const uint32_t *ints, const double *flts, int pst,
-             int G, int kid, int K, float *out) {
+k_prop_score(const FeatDev *pfeats, const float *aux, const PropKindDev *pk, int K, float *out) {
     __shared__ double s_red[8];
-    const int fid = blockIdx.x;
+    const int fid = blockIdx.x, kid = blockIdx.y;
     const FeatDev &f = pfeats[fid];
-    const uint32_t *in = ints + (size_t)f.int_row * pst;
-    const double *fl = flts + (size_t)f.flt_row * pst;
+    const PropKindDev p = pk[kid];
+    const int G = p.G, pst = p.pst;
+    uint32_t *in = p.ints + (size_t)f.int_row * pst;
+    double *fl = p.flts + (size_t)f.flt_row * pst;
     double acc = 0;
     if (f.type == LB_DD || f.type == LB_DPD) {
-        const int total = (f.dim + 1) * G;
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            const int v = idx / G, g = idx % G;
-            const uint32_t n = in[(size_t)v * pst + g];
-            if (!n) continue;
-            if (v < f.dim) acc += (double)lb_lgamma_diff(f.a_scale * aux[f.aux_off + v], (float)n);
-            else acc -= (double)lb_lgamma_diff(f.a_total, (float)n);
+        // 2-D walk (value rows x groups): no divisions, coalesced along groups; counts are
+        // integers, so short rising factorials take the cheap product form
+        const int gl = threadIdx.x & 31, vl = threadIdx.x >> 5;
+        for (int v = vl; v <= f.dim; v += 8) {
+            const float a = v < f.dim ? f.a_scale * aux[f.aux_off + v] : f.a_total;
+            float part = 0.f;
+            for (int g = gl; g < G; g += 32) {
+                const uint32_t n = in[(size_t)v * pst + g];
+                if (n) part += lb_lgamma_diff_int(a, n);
+            }
+            acc += v < f.dim ? (double)part : -(double)part;
         }
     } else {
-        for (int g = threadIdx.x; g < G; g += blockDim.x) acc += lb_marginal_group(f, aux, in + g, fl + g, pst);
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            if (f.type == LB_NICH) {   // sums -> (mean, count_times_variance), once
+                const double n = (double)in[g];
+                if (n == 0.0) { fl[g] = 0.0; fl[pst + g] = 0.0; }
+                else {
+                    const double mean = fl[g] / n;
+                    fl[pst + g] = fmax(fl[pst + g] - n * mean * mean, 0.0);
+                    fl[g] = mean;
+                }
+            }
+            acc += lb_marginal_group(f, aux, in + g, fl + g, pst);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
@@ -240,11 +200,10 @@ extern "C" int lb_proposer_accumulate(lb_handle h, uint64_t b, uint64_t en) {
         const size_t need_i = (size_t)e->prop_int_rows * p.pst, need_f = (size_t)e->prop_flt_rows * p.pst;
         if (need_i > p.cap_ints) { if (p.ints) cudaFree(p.ints); LB_TRY(dalloc(&p.ints, need_i + need_i / 4)); p.cap_ints = need_i + need_i / 4; }
         if (need_f > p.cap_flts) { if (p.flts) cudaFree(p.flts); LB_TRY(dalloc(&p.flts, need_f + need_f / 4)); p.cap_flts = need_f + need_f / 4; }
-        if (e->R > p.cap_rows) { if (p.packed) cudaFree(p.packed); LB_TRY(dalloc(&p.packed, e->R)); p.cap_rows = e->R; }
+        if (e->R > p.cap_rows) { if (p.packed) cudaFree(p.packed); uint32_t *tmp = nullptr; LB_TRY(dalloc(&tmp, e->R)); p.packed = tmp; p.cap_rows = e->R; }
         LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * need_i, e->stream));
         LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * need_f, e->stream));
-        k_pack_assign<<<rgrid, 256, 0, e->stream>>>(k.assign, k.g2p, p.packed, e->R);
-        e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
+        LB_TRY(lb_launch_pack_assign(e, k.assign, k.g2p, p.packed, k.G, 0, e->R, LB_L_KIND));
         LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, p.packed, b, en, +1, p.ints, p.flts,
                                         p.pst, p.G, LB_L_KIND));
     }
@@ -275,14 +234,15 @@ extern "C" int lb_proposer_finish(lb_handle h, float *out) {
         LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
         e->prop_scores_cap = (size_t)F * K;
     }
-    for (int kid = 0; kid < K; ++kid) {
-        ProposerKind &p = e->prop[kid];
-        k_prop_sums_to_moments<<<std::max(1, std::min((F * p.G + 255) / 256, 1024)), 256, 0, e->stream>>>(
-            e->d_prop_feats, F, p.ints, p.flts, p.pst, p.G);
-        k_prop_score<<<F, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, p.ints, p.flts, p.pst, p.G, kid, K,
-                                               e->d_prop_scores);
+    {   // one launch over every (feature, kind) pair
+        std::vector<PropKindDev> pk(K);
+        for (int kid = 0; kid < K; ++kid) pk[kid] = PropKindDev{e->prop[kid].ints, e->prop[kid].flts, e->prop[kid].pst, e->prop[kid].G};
+        LB_TRY(lb_ensure_scratch(e, sizeof(PropKindDev) * (size_t)K + 256));
+        LB_CUDA(cudaMemcpyAsync(e->d_scratch, pk.data(), sizeof(PropKindDev) * (size_t)K, cudaMemcpyHostToDevice, e->stream));
+        dim3 grid((unsigned)F, (unsigned)K);
+        k_prop_score<<<grid, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, (const PropKindDev *)e->d_scratch, K, e->d_prop_scores);
         LB_CUDA(cudaGetLastError());
-        e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_KIND] += 2;
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
     }
     e->prop_scores.resize((size_t)F * K);
     LB_CUDA(cudaMemcpyAsync(e->prop_scores.data(), e->d_prop_scores, 4 * (size_t)F * K, cudaMemcpyDeviceToHost, e->stream));

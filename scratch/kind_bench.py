@@ -24,12 +24,20 @@ cuda = _abi.load_cuda()
 g = setup(cuda, rows, truth["assign"])
 K = g.n_kinds()
 g.kind_proposer_score(fetch=False); g.sync()
-g.timer_start(); reps = 3
-for _ in range(reps): Lg = g.kind_proposer_score(fetch=False)
-ms = g.timer_stop() / reps
+reps = 3
+t_acc = t_fin = 0.0
+for _ in range(reps):
+    g.timer_start(); g.proposer_accumulate(); t_acc += g.timer_stop()
+    g.timer_start(); g.proposer_finish(fetch=False); t_fin += g.timer_stop()
+t_acc /= reps; t_fin /= reps
 ncell = rows.n_cells()
-print("GPU: R %d F %d K %d: %.1f ms per round  feature-scores/s %.3g  proposer cells/s %.3g" % (
-    R, F, K, ms, F * K / ms * 1e3, ncell * K / ms * 1e3))
+G = [g.kind_info(k).n_groups for k in range(K)]
+stat_bytes = sum(4 * 257 * ((gg + 31) // 32 * 32) for gg in G) * F          # uint32 [dim+1][pst] per feature per kind
+print("GPU: R %d F %d K %d groups %s" % (R, F, K, G[:10]))
+print("  K4 accumulate %.2f ms  -> %.3g proposer cells/s" % (t_acc, ncell * K / t_acc * 1e3))
+print("  K5 score      %.2f ms  -> %.3g feature-scores/s ; table bytes %.1f MB -> %.0f GB/s (%.1f%% of 6533.5)" % (
+    t_fin, F * K / t_fin * 1e3, stat_bytes / 1e6, stat_bytes / t_fin / 1e6, 100 * stat_bytes / t_fin / 1e6 / 6533.5))
+ms = t_acc + t_fin
 if RO:
     oracle = _abi.Abi(os.path.join(REPO, "oracle", "libloom_oracle.so"), "lo_")
     W = (RO + 31) // 32
