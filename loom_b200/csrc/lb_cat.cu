@@ -837,35 +837,53 @@ __global__ void k_sums_to_moments(KindDev *kinds, int kid, const FeatDev *feats,
 // bytes per packed id for a kind with G groups
 int lb_packed_width(int G) { return G < 255 ? 1 : (G < 65535 ? 2 : 4); }
 
-int lb_launch_pack_assign(Engine *e, const uint32_t *assign, const uint32_t *g2p, void *d_packed, int G, uint64_t b,
-                          uint64_t en, int launch_family) {
-    if (en <= b) return 0;
-    const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, (uint64_t)e->n_sm * 8));
-    switch (lb_packed_width(G)) {
-    case 1: k_pack_assign_t<uint8_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint8_t *)d_packed, b, en); break;
-    case 2: k_pack_assign_t<uint16_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint16_t *)d_packed, b, en); break;
-    default: k_pack_assign_t<uint32_t><<<pg, 256, 0, e->stream>>>(assign, g2p, (uint32_t *)d_packed, b, en); break;
+// small device array of launch descriptors (AccTarget / PackSrc), reused
+static int lb_upload_desc(Engine *e, const void *host, size_t bytes, void **dev) {
+    if (bytes > e->d_desc_cap) {
+        if (e->d_desc) cudaFree(e->d_desc);
+        e->d_desc = nullptr;
+        LB_CUDA(cudaMalloc(&e->d_desc, 2 * bytes + 4096));
+        e->d_desc_cap = 2 * bytes + 4096;
     }
+    // pageable source: the runtime stages it before returning, so `host` may die after the call
+    LB_CUDA(cudaMemcpyAsync(e->d_desc, host, bytes, cudaMemcpyHostToDevice, e->stream));
+    *dev = e->d_desc;
+    return 0;
+}
+
+int lb_launch_pack_assign(Engine *e, const std::vector<PackSrc> &src, uint64_t b, uint64_t en, int launch_family) {
+    if (en <= b || src.empty()) return 0;
+    const unsigned n = (unsigned)src.size();
+    const uint64_t want = (uint64_t)e->n_sm * 8 / n + 1;
+    const unsigned pg = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, want));
+    const PackSrc *d_many = nullptr;
+    if (n > 1) {
+        void *d = nullptr;
+        LB_TRY(lb_upload_desc(e, src.data(), sizeof(PackSrc) * n, &d));
+        d_many = (const PackSrc *)d;
+    }
+    k_pack_assign<<<dim3(pg, n), 256, 0, e->stream>>>(src[0], d_many, b, en);
     LB_CUDA(cudaGetLastError());
     e->launches[LB_L_TOTAL]++; e->launches[launch_family]++;
     return 0;
 }
 
-// Launch k_accum_feature over `fids` (global feature ids), grouped by shared-memory need so
-// that small tables (BB / GP / NICH / low-dimensional DD) keep a high occupancy.
+// Launch k_accum_feature over `fids` (global feature ids) x `targets` (one per kind), grouped by
+// shared-memory need so that small tables (BB / GP / NICH / low-dimensional DD) keep a high
+// occupancy.  All targets go into ONE grid (blockIdx.z): a proposal round is a handful of
+// launches, each many waves deep, instead of one under-filled launch per kind.
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
-                             const void *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
-                             double *flts, int st, int G, int launch_family) {
-    if (en <= b || fids.empty()) return 0;
+                             const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,
+                             int launch_family) {
+    if (en <= b || fids.empty() || targets.empty()) return 0;
     static bool configured = false;
     const size_t kBig = 200 * 1024, kSmall = 16 * 1024;
     if (!configured) {
-        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
-        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
-        LB_CUDA(cudaFuncSetAttribute(k_accum_feature<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
+        LB_CUDA(cudaFuncSetAttribute(k_accum_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
         configured = true;
     }
-    const int pw = lb_packed_width(G);
+    int G = 1;
+    for (const AccTarget &t : targets) G = std::max(G, t.G);
     std::vector<int32_t> cls[3];
     size_t big_need = 0;
     for (int fid : fids) {
@@ -882,29 +900,33 @@ int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vecto
         LB_CUDA(cudaMalloc((void **)&e->d_fid_list, 4 * (total + 64)));
         e->d_fid_list_cap = (int)total + 64;
     }
+    const unsigned nt = (unsigned)targets.size();
+    const AccTarget *d_many = nullptr;
+    if (nt > 1) {
+        void *d = nullptr;
+        LB_TRY(lb_upload_desc(e, targets.data(), sizeof(AccTarget) * nt, &d));
+        d_many = (const AccTarget *)d;
+    }
     const uint64_t n = en - b;
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
     size_t off = 0;
     const size_t smem_of[3] = {kSmall, big_need, 0};
     for (int c = 0; c < 3; ++c) {
         if (cls[c].empty()) continue;
-        // a CTA must see many more cells than its table has entries, or the flush dominates:
-        // big (DD-256-sized) tables take 64k-row chunks, small ones 8k-row chunks
-        uint64_t rows_per_cta = c == 1 ? std::max<uint64_t>(65536, (n + 7) / 8) : std::max<uint64_t>(8192, (n + 31) / 32);
+        // A CTA must see many more cells than its table has entries, or the flush dominates: big
+        // (DD-256-sized) tables take >= 64k-row chunks, small ones >= 8k-row chunks.  Beyond that,
+        // cut the rows only as far as needed to fill the machine a few times over.
+        const uint64_t min_rows = c == 1 ? 65536 : 8192;
+        const uint64_t pairs = (uint64_t)cls[c].size() * nt;
+        const uint64_t want_chunks = std::max<uint64_t>(1, ((uint64_t)e->n_sm * 16 + pairs - 1) / pairs);
+        uint64_t rows_per_cta = std::max<uint64_t>(min_rows, (n + want_chunks - 1) / want_chunks);
         rows_per_cta = (rows_per_cta + ACC_THREADS - 1) / ACC_THREADS * ACC_THREADS;
         const unsigned chunks = (unsigned)((n + rows_per_cta - 1) / rows_per_cta);
         int32_t *d_list = e->d_fid_list + off;
         LB_CUDA(cudaMemcpyAsync(d_list, cls[c].data(), 4 * cls[c].size(), cudaMemcpyHostToDevice, e->stream));
-        dim3 grid(chunks, (unsigned)cls[c].size());
-        if (pw == 1)
-            k_accum_feature<uint8_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint8_t *)d_packed, b, en,
-                                                                                rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
-        else if (pw == 2)
-            k_accum_feature<uint16_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint16_t *)d_packed, b, en,
-                                                                                 rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
-        else
-            k_accum_feature<uint32_t><<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, (const uint32_t *)d_packed, b, en,
-                                                                                 rows_per_cta, sign, ints, flts, st, G, (int)smem_of[c]);
+        dim3 grid(chunks, (unsigned)cls[c].size(), nt);
+        k_accum_feature<<<grid, ACC_THREADS, smem_of[c], e->stream>>>(d_feats, d_list, rows, targets[0], d_many, b, en,
+                                                                   rows_per_cta, sign, (int)smem_of[c]);
         LB_CUDA(cudaGetLastError());
         e->launches[LB_L_TOTAL]++; e->launches[launch_family]++;
         off += cls[c].size();
@@ -922,18 +944,15 @@ int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) 
         LB_TRY(lb_ensure_scratch(e, 4 * (size_t)e->R));
         void *d_packed = e->d_scratch;
         const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>((en - b + 255) / 256, (uint64_t)e->n_sm * 8));
-        LB_TRY(lb_launch_pack_assign(e, k.assign, k.g2p, d_packed, k.G, b, en, LB_L_ACCUM));
+        const int width = lb_packed_width(k.G);
+        LB_TRY(lb_launch_pack_assign(e, {PackSrc{k.assign, k.g2p, d_packed, width}}, b, en, LB_L_ACCUM));
         // clustering.add_value
         unsigned long long *d_ss = (unsigned long long *)((char *)&e->d_kinds[kid] + offsetof(KindDev, sample_size));
-        const int cg = std::min(pg, e->n_sm * 2);
-        const size_t csm = 4 * (size_t)k.G + 16;
-        switch (lb_packed_width(k.G)) {
-        case 1: k_accum_counts<uint8_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint8_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
-        case 2: k_accum_counts<uint16_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint16_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
-        default: k_accum_counts<uint32_t><<<cg, ACC_THREADS, csm, e->stream>>>((const uint32_t *)d_packed, b, en, sign, k.counts, d_ss, k.G, e->d_flag); break;
-        }
+        k_accum_counts<<<std::min(pg, e->n_sm * 2), ACC_THREADS, 4 * (size_t)k.G + 16, e->stream>>>(
+            d_packed, width, b, en, sign, k.counts, d_ss, k.G, e->d_flag);
         e->launches[LB_L_TOTAL]++; e->launches[LB_L_ACCUM]++;
-        LB_TRY(lb_launch_accum_features(e, e->d_feats, k.fids, d_packed, b, en, sign, k.ints, k.flts, k.Gcap, k.G, LB_L_ACCUM));
+        LB_TRY(lb_launch_accum_features(e, e->d_feats, k.fids, {AccTarget{d_packed, k.ints, k.flts, k.Gcap, k.G, width}},
+                                        b, en, sign, LB_L_ACCUM));
     }
     if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
     LB_CUDA(cudaGetLastError());

@@ -19,12 +19,24 @@ struct KindHost {
     int32_t *cache_row_feat = nullptr;
 };
 
-struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind)
+struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind): views into the slabs
     int G = 0, pst = 0;        // groups, column stride
     uint32_t *ints = nullptr;  // [prop_int_rows][pst]
     double *flts = nullptr;    // [prop_flt_rows][pst]
-    void *packed = nullptr;      // [R] packed group id of every row in this kind (1, 2 or 4 bytes each)
-    size_t cap_ints = 0, cap_flts = 0, cap_rows = 0;   // allocated sizes (buffers are reused)
+    void *packed = nullptr;    // [R] packed group id of every row in this kind (1, 2 or 4 bytes each)
+};
+
+// launch descriptors of the bulk accumulate kernels (lb_accum.cuh)
+struct AccTarget {             // packed ids of every row + the [rows][st] tables the statistics go to
+    const void *packed;
+    uint32_t *ints;
+    double *flts;
+    int st, G, width;
+};
+struct PackSrc {               // out[r] = g2p[assign[r]] narrowed to `width` bytes
+    const uint32_t *assign, *g2p;
+    void *out;
+    int width;
 };
 
 struct Engine {
@@ -75,6 +87,12 @@ struct Engine {
 
     // kind proposer
     std::vector<ProposerKind> prop;
+    uint32_t *d_prop_ints = nullptr;   // slab holding every kind's integer tables
+    double *d_prop_flts = nullptr;
+    unsigned char *d_prop_packed = nullptr;   // [K][R] packed ids, 4 bytes per row reserved
+    size_t prop_cap_ints = 0, prop_cap_flts = 0, prop_cap_packed = 0;
+    void *d_desc = nullptr;            // launch descriptor staging
+    size_t d_desc_cap = 0;
     std::vector<int> prop_int_off, prop_flt_off;
     int prop_int_rows = 0, prop_flt_rows = 0;
     std::vector<float> prop_scores;  // [F][K]
@@ -143,11 +161,10 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
-                             const void *d_packed, uint64_t b, uint64_t en, int sign, uint32_t *ints,
-                             double *flts, int st, int G, int launch_family);
+                             const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,
+                             int launch_family);
 int lb_packed_width(int G);
-int lb_launch_pack_assign(Engine *e, const uint32_t *assign, const uint32_t *g2p, void *d_packed, int G, uint64_t b,
-                          uint64_t en, int launch_family);
+int lb_launch_pack_assign(Engine *e, const std::vector<PackSrc> &src, uint64_t b, uint64_t en, int launch_family);
 int lb_launch_refresh(Engine *e, int kid);
 int lb_launch_restride(Engine *e, const KindHost &src, KindHost &dst);
 int lb_launch_renumber(Engine *e, int kid);

@@ -32,11 +32,11 @@ void lb_free_proposer(Engine *e) {
     e->prop_scores.clear();
 }
 void lb_release_proposer(Engine *e) {
-    for (auto &p : e->prop) {
-        if (p.ints) cudaFree(p.ints);
-        if (p.flts) cudaFree(p.flts);
-        if (p.packed) cudaFree(p.packed);
-    }
+    if (e->d_prop_ints) { cudaFree(e->d_prop_ints); e->d_prop_ints = nullptr; }
+    if (e->d_prop_flts) { cudaFree(e->d_prop_flts); e->d_prop_flts = nullptr; }
+    if (e->d_prop_packed) { cudaFree(e->d_prop_packed); e->d_prop_packed = nullptr; }
+    if (e->d_desc) { cudaFree(e->d_desc); e->d_desc = nullptr; }
+    e->prop_cap_ints = e->prop_cap_flts = e->prop_cap_packed = e->d_desc_cap = 0;
     e->prop.clear();
     e->prop_valid = false;
     e->prop_scores.clear();
@@ -189,24 +189,56 @@ extern "C" int lb_proposer_accumulate(lb_handle h, uint64_t b, uint64_t en) {
     LB_TRY(build_prop_feats(e));
     const int F = e->F, K = (int)e->kinds.size();
     if ((int)e->prop.size() < K) e->prop.resize(K);
-    const int rgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, 4096));
     std::vector<int> all_features(F);
     for (int f = 0; f < F; ++f) all_features[f] = f;
+    // every kind's tables live in one slab each (ints / flts / packed ids): two memsets, one pack
+    // launch and one accumulate launch per shared-memory class cover the whole proposal round
+    size_t need_i = 0, need_f = 0;
+    for (int kid = 0; kid < K; ++kid) {
+        ProposerKind &p = e->prop[kid];
+        p.G = e->kinds[kid].G;
+        p.pst = (p.G + 31) & ~31;
+        need_i += (size_t)e->prop_int_rows * p.pst;
+        need_f += (size_t)e->prop_flt_rows * p.pst;
+    }
+    const size_t need_p = 4 * (size_t)e->R * K;
+    if (need_i > e->prop_cap_ints) {
+        if (e->d_prop_ints) cudaFree(e->d_prop_ints);
+        e->d_prop_ints = nullptr;
+        LB_TRY(dalloc(&e->d_prop_ints, need_i + need_i / 4));
+        e->prop_cap_ints = need_i + need_i / 4;
+    }
+    if (need_f > e->prop_cap_flts) {
+        if (e->d_prop_flts) cudaFree(e->d_prop_flts);
+        e->d_prop_flts = nullptr;
+        LB_TRY(dalloc(&e->d_prop_flts, need_f + need_f / 4));
+        e->prop_cap_flts = need_f + need_f / 4;
+    }
+    if (need_p > e->prop_cap_packed) {
+        if (e->d_prop_packed) cudaFree(e->d_prop_packed);
+        e->d_prop_packed = nullptr;
+        LB_TRY(dalloc(&e->d_prop_packed, need_p + need_p / 4));
+        e->prop_cap_packed = need_p + need_p / 4;
+    }
+    if (need_i) LB_CUDA(cudaMemsetAsync(e->d_prop_ints, 0, 4 * need_i, e->stream));
+    if (need_f) LB_CUDA(cudaMemsetAsync(e->d_prop_flts, 0, 8 * need_f, e->stream));
+    std::vector<PackSrc> src(K);
+    std::vector<AccTarget> targets(K);
+    size_t off_i = 0, off_f = 0;
     for (int kid = 0; kid < K; ++kid) {
         const KindHost &k = e->kinds[kid];
         ProposerKind &p = e->prop[kid];
-        p.G = k.G;
-        p.pst = (k.G + 31) & ~31;
-        const size_t need_i = (size_t)e->prop_int_rows * p.pst, need_f = (size_t)e->prop_flt_rows * p.pst;
-        if (need_i > p.cap_ints) { if (p.ints) cudaFree(p.ints); LB_TRY(dalloc(&p.ints, need_i + need_i / 4)); p.cap_ints = need_i + need_i / 4; }
-        if (need_f > p.cap_flts) { if (p.flts) cudaFree(p.flts); LB_TRY(dalloc(&p.flts, need_f + need_f / 4)); p.cap_flts = need_f + need_f / 4; }
-        if (e->R > p.cap_rows) { if (p.packed) cudaFree(p.packed); uint32_t *tmp = nullptr; LB_TRY(dalloc(&tmp, e->R)); p.packed = tmp; p.cap_rows = e->R; }
-        LB_CUDA(cudaMemsetAsync(p.ints, 0, 4 * need_i, e->stream));
-        LB_CUDA(cudaMemsetAsync(p.flts, 0, 8 * need_f, e->stream));
-        LB_TRY(lb_launch_pack_assign(e, k.assign, k.g2p, p.packed, k.G, 0, e->R, LB_L_KIND));
-        LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, p.packed, b, en, +1, p.ints, p.flts,
-                                        p.pst, p.G, LB_L_KIND));
+        p.ints = e->d_prop_ints + off_i;
+        p.flts = e->d_prop_flts + off_f;
+        p.packed = e->d_prop_packed + 4 * (size_t)e->R * kid;
+        off_i += (size_t)e->prop_int_rows * p.pst;
+        off_f += (size_t)e->prop_flt_rows * p.pst;
+        const int width = lb_packed_width(k.G);
+        src[kid] = PackSrc{k.assign, k.g2p, p.packed, width};
+        targets[kid] = AccTarget{p.packed, p.ints, p.flts, p.pst, p.G, width};
     }
+    LB_TRY(lb_launch_pack_assign(e, src, b, en, LB_L_KIND));
+    LB_TRY(lb_launch_accum_features(e, e->d_prop_feats, all_features, targets, b, en, +1, LB_L_KIND));
     LB_CUDA(cudaGetLastError());
     LB_CUDA(cudaStreamSynchronize(e->stream));
     e->prop_accumulated = true;

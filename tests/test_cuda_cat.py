@@ -191,8 +191,10 @@ def test_score_rows_large_groups_float_accuracy(oracle_abi, cuda_abi):
     assert rel_err(sg, so).max() <= SCORE_TOL, rel_err(sg, so).max()
 
 
-def test_accumulate_parity(oracle_abi, cuda_abi):
-    model, rows, truth = mixed(rows=4000, seed=8)
+@pytest.mark.parametrize("n_rows,lo,hi", [(4000, 0, 2000), (4003, 3, 1999), (4002, 256, 4002)])
+def test_accumulate_parity(oracle_abi, cuda_abi, n_rows, lo, hi):
+    # (4000, 0, 2000) takes the four-rows-per-load path, the others the unaligned one
+    model, rows, truth = mixed(rows=n_rows, seed=8)
     o, g = both(oracle_abi, cuda_abi, model, rows)
     for k in range(model.n_kinds):
         a = truth["assign"][k].astype(np.uint32)
@@ -206,9 +208,9 @@ def test_accumulate_parity(oracle_abi, cuda_abi):
     for e in (o, g):
         e.accumulate_rows()
     assert_same_state(o, g, model, flt_rtol=1e-9)
-    # removing half of the rows again stays exact on the integer statistics
+    # removing part of the rows again stays exact on the integer statistics
     for e in (o, g):
-        e.accumulate_rows(row_begin=0, row_end=2000, sign=-1)
+        e.accumulate_rows(row_begin=lo, row_end=hi, sign=-1)
     for k in range(model.n_kinds):
         co, io, fo = o.get_groups(k)
         cg, ig, fg = g.get_groups(k)
