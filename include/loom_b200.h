@@ -166,6 +166,16 @@ int LB_NAME(cat_sweep)(lb_handle h, const uint32_t *actions, uint64_t n_actions,
                        uint64_t seed, uint64_t action_offset, const uint8_t *kind_mask,
                        uint32_t *debug_picks, float *debug_scores, int32_t debug_stride);
 
+/* The same action list on `n_handles` independent chains at once -- loom's
+ * per-sample parallelism (loom/tasks.py:173-194 infer_many -> parallel_map over
+ * seeds; each sample is its own CrossCat state and its own rng).  Equivalent to
+ * calling cat_sweep(handles[c], actions, n_actions, seeds[c], action_offset,
+ * NULL, NULL, NULL, 0) for every c; the device library runs all (chain, kind)
+ * pairs in ONE launch, which is how many chains fill a GPU.  All handles must
+ * live on the same device. */
+int LB_NAME(cat_sweep_multi)(const lb_handle *handles, int32_t n_handles, const uint32_t *actions,
+                             uint64_t n_actions, const uint64_t *seeds, uint64_t action_offset);
+
 /* Assignments (src/assignments.hpp): packed group id per row position for one
  * kind, LB_UNASSIGNED where the row is not assigned. */
 int LB_NAME(get_assignments)(lb_handle h, int32_t kind, uint32_t *out_packed);

@@ -33,9 +33,8 @@
 // shared-memory ring; the Philox uniform of the next ADD is drawn by an idle
 // warp while warp 0 samples.
 // ===========================================================================
-constexpr int SW_THREADS = 256;
-constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_PF = 4;   // row cells prefetched per thread -> nf <= 1024 per kind
+constexpr int SW_MAX_WARPS = 8;   // warps per (chain, kind) CTA: 8 for latency, fewer when many chains fill the GPU
+constexpr int SW_PF = 4;          // row cells prefetched per thread -> nf <= 128 * warps per kind
 constexpr int SW_MAX_G = 4096;
 enum { CL_CAT = 0, CL_GP = 1, CL_NICH = 2, N_CLASS = 3 };
 
@@ -46,8 +45,9 @@ struct SweepSmem {
     unsigned long long sample_size;
     float u[2];
     uint32_t pf_assign[4];         // prefetched assignment of the row of each ring slot
-    int cls_begin[N_CLASS], cls_end[N_CLASS];
-    int warp_cls[SW_WARPS], warp_rank[SW_WARPS], warp_nw[SW_WARPS];
+    uint32_t pf_pg[4], pf_epoch[4]; // ... its packed group id, valid while no group was swap-removed since
+    uint32_t epoch;                // number of swap-removes so far
+    int own_off[SW_MAX_WARPS][N_CLASS + 1];   // warp w owns s_own[own_off[w][c] .. own_off[w][c+1]) of class c
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -107,18 +107,17 @@ __device__ __forceinline__ int feat_class(int type) {
     return type == LB_GP ? CL_GP : (type == LB_NICH ? CL_NICH : CL_CAT);
 }
 
-// partial scores of one warp's feature stripe for groups g0 + lane + 32*jj
+// add the scores of one warp's features of class `cls` (own[0..n)) for groups g0 + lane + 32*jj
 template <int NJ>
-__device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep, const FeatDev *s_feat,
-                                             const uint32_t *c_raw, const uint32_t *c_obs,
-                                             const uint32_t *ints, const float *cache, int st,
-                                             int zero_row, int g0, int lane, float *acc) {
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) acc[jj] = 0.f;
+__device__ __forceinline__ void score_list(int cls, const uint16_t *own, int n, const FeatDev *s_feat,
+                                           const uint32_t *c_raw, const uint32_t *c_obs,
+                                           const uint32_t *ints, const float *cache, int st,
+                                           int zero_row, int g0, int lane, float *acc) {
     if (cls == CL_CAT) {
         // branch-free gathers: unobserved cells read the all-zero cache row
 #pragma unroll 4
-        for (int j = fb; j < fe; j += fstep) {
+        for (int k = 0; k < n; ++k) {
+            const int j = own[k];
             const FeatDev &f = s_feat[j];
             const uint32_t raw = c_raw[j];
             const bool obs = c_obs[j] != 0u;
@@ -131,7 +130,8 @@ __device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep,
             for (int jj = 0; jj < NJ; ++jj) acc[jj] += cv[32 * jj] - cs[32 * jj];
         }
     } else if (cls == CL_GP) {
-        for (int j = fb; j < fe; j += fstep) {
+        for (int k = 0; k < n; ++k) {
+            const int j = own[k];
             if (!c_obs[j]) continue;
             const FeatDev &f = s_feat[j];
             const uint32_t raw = c_raw[j];
@@ -145,7 +145,8 @@ __device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep,
             }
         }
     } else {
-        for (int j = fb; j < fe; j += fstep) {
+        for (int k = 0; k < n; ++k) {
+            const int j = own[k];
             if (!c_obs[j]) continue;
             const FeatDev &f = s_feat[j];
             const float x = __uint_as_float(c_raw[j]);
@@ -158,19 +159,46 @@ __device__ __forceinline__ void score_stripe(int cls, int fb, int fe, int fstep,
         }
     }
 }
+// all of one warp's features (off[c] .. off[c+1] per class)
+template <int NJ>
+__device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own, const FeatDev *s_feat,
+                                           const uint32_t *c_raw, const uint32_t *c_obs,
+                                           const uint32_t *ints, const float *cache, int st,
+                                           int zero_row, int g0, int lane, float *acc) {
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) acc[jj] = 0.f;
+#pragma unroll
+    for (int c = 0; c < N_CLASS; ++c)
+        if (off[c + 1] > off[c])
+            score_list<NJ>(c, s_own + off[c], off[c + 1] - off[c], s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+}
 
-__global__ void __launch_bounds__(SW_THREADS, 2)
-k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const int32_t *kind_feats,
-            const float *aux, RowsDev rows, const uint32_t *actions, uint64_t n_actions,
-            uint64_t seed, uint64_t offset, int K, int n_empty, uint32_t *dbg_picks,
-            float *dbg_scores, int dbg_stride, unsigned long long *prof) {
+// W warps per CTA; registers are capped at 128 per thread for every W
+template <int W>
+__global__ void __launch_bounds__(W * 32, 16 / W)
+k_cat_sweep(SweepChain one, const SweepChain *many) {
+    constexpr int SW_THREADS = W * 32, SW_WARPS = W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int kid = kind_ids[blockIdx.x];
+    // blockIdx.y = chain (independent CrossCat states swept with the same action list), blockIdx.x = kind
+    const SweepChain &ch = many ? many[blockIdx.y] : one;
+    if ((int)blockIdx.x >= ch.n_ids) return;
+    KindDev *const kinds = ch.kinds;
+    const FeatDev *const feats = ch.feats;
+    const int32_t *const kind_feats = ch.kind_feats;
+    const float *const aux = ch.aux;
+    const RowsDev rows = ch.rows;
+    const uint32_t *const actions = ch.actions;
+    const uint64_t n_actions = ch.n_actions, seed = ch.seed, offset = ch.offset;
+    const int K = ch.K, n_empty = ch.n_empty, dbg_stride = ch.dbg_stride;
+    uint32_t *const dbg_picks = ch.dbg_picks;
+    float *const dbg_scores = ch.dbg_scores;
+    unsigned long long *const prof = ch.prof;
+    const int kid = ch.kind_ids[blockIdx.x];
     KindDev &kd = kinds[kid];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // LB_PROFILE=1: cycles per phase seen by lane 0 of every warp
-    // 0 own phase-1 work | 1 wait at (A) | 2 sample / commit | 3 wait at (B) | 4 update
-    long long pt[6] = {0, 0, 0, 0, 0, 0}, pc = 0;
+    // ADD: 0 score | 1 wait at (A) | 2 sample / commit | 3 wait at (B) | 4 update;  REMOVE: 5 lookup | 6 wait at (A) | 7 update
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define LB_TICK(k) do { if (prof && lane == 0) { const long long now__ = clock64(); pt[k] += now__ - pc; pc = now__; } } while (0)
     const int nf = kd.nf, st = kd.Gcap;
     const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
@@ -187,6 +215,8 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
     float *s_part = s_score + st;                        // [SW_WARPS][st]
     uint32_t *s_counts = (uint32_t *)(s_part + SW_WARPS * st);   // [st] clustering counts
     float *s_prior = (float *)(s_counts + st);           // [st] CRP prior per group, empties included
+    uint16_t *s_own = (uint16_t *)(s_prior + st);        // [nf] feature indices grouped by (owner warp, class)
+    uint8_t *s_owner = (uint8_t *)(s_own + nf);          // [nf]
 
     uint32_t *const ints = kd.ints;
     double *const flts = kd.flts;
@@ -213,48 +243,52 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
     }
     __syncthreads();
     if (tid == 0) {
-        ss->G = kd.G; ss->stop = 0;
+        ss->G = kd.G; ss->stop = 0; ss->epoch = 0;
         ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
-        // class ranges (features are sorted by type) and warp ownership
-        int cnt[N_CLASS] = {0, 0, 0};
-        for (int c = 0; c < N_CLASS; ++c) { ss->cls_begin[c] = nf; ss->cls_end[c] = 0; }
-        for (int j = 0; j < nf; ++j) {
-            const int c = feat_class(s_feat[j].type);
-            if (j < ss->cls_begin[c]) ss->cls_begin[c] = j;
-            ss->cls_end[c] = j + 1;
-            cnt[c]++;
-        }
+        // Features -> warps by cost, longest first (GP 4, NICH 3, categorical 1); warp 0 also
+        // samples, so it starts with a handicap.  A warp owns its features for BOTH scoring and
+        // update; its list is sorted by class so the scoring loops stay class-pure.
+        float load[SW_WARPS];
+        for (int w = 0; w < SW_WARPS; ++w) load[w] = 0.f;
+        if (SW_WARPS > 1) load[0] = 6.f;
+        const int order[N_CLASS] = {CL_GP, CL_NICH, CL_CAT};
         const float weight[N_CLASS] = {1.f, 4.f, 3.f};
-        int nw[N_CLASS] = {0, 0, 0}, left = SW_WARPS;
-        for (int c = 0; c < N_CLASS; ++c) if (cnt[c]) { nw[c] = 1; --left; }
-        while (left > 0) {
-            int best = -1; float load = 0.f;
-            for (int c = 0; c < N_CLASS; ++c) {
-                if (!cnt[c] || nw[c] >= cnt[c]) continue;
-                const float l = weight[c] * (float)cnt[c] / (float)nw[c];
-                if (l > load) { load = l; best = c; }
+        for (int oc = 0; oc < N_CLASS; ++oc)
+            for (int j = 0; j < nf; ++j) {
+                if (feat_class(s_feat[j].type) != order[oc]) continue;
+                int best = 0;
+                for (int w = 1; w < SW_WARPS; ++w) if (load[w] < load[best]) best = w;
+                s_owner[j] = (uint8_t)best;
+                load[best] += weight[order[oc]];
             }
-            if (best < 0) break;
-            nw[best]++; --left;
+        int k = 0;
+        for (int w = 0; w < SW_WARPS; ++w) {
+            for (int c = 0; c < N_CLASS; ++c) {
+                ss->own_off[w][c] = k;
+                for (int j = 0; j < nf; ++j)
+                    if (s_owner[j] == w && feat_class(s_feat[j].type) == c) s_own[k++] = (uint16_t)j;
+            }
+            ss->own_off[w][N_CLASS] = k;
         }
-        int w = SW_WARPS - 1;   // hand out from the top so warp 0 (the sampler) is loaded last
-        for (int c = N_CLASS - 1; c >= 0; --c)
-            for (int r = 0; r < nw[c]; ++r, --w) { ss->warp_cls[w] = c; ss->warp_rank[w] = r; ss->warp_nw[w] = nw[c]; }
-        for (; w >= 0; --w) { ss->warp_cls[w] = -1; ss->warp_rank[w] = 0; ss->warp_nw[w] = 1; }
     }
     __syncthreads();
-    const int my_cls = ss->warp_cls[warp];
-    const int fstep = ss->warp_nw[warp];
-    const int fb = my_cls >= 0 ? ss->cls_begin[my_cls] + ss->warp_rank[warp] : 0;
-    const int fe = my_cls >= 0 ? ss->cls_end[my_cls] : 0;
+    int off[N_CLASS + 1];
+#pragma unroll
+    for (int c = 0; c <= N_CLASS; ++c) off[c] = ss->own_off[warp][c];
 
     uint64_t i = kd.progress;
     // row cells of action `idx`: global -> registers, later registers -> ring slot
-    uint32_t pf_raw[SW_PF], pf_obs[SW_PF], pf_assign = LB_UNASSIGNED;
+    uint32_t pf_raw[SW_PF], pf_obs[SW_PF], pf_assign = LB_UNASSIGNED, pf_pg = LB_UNASSIGNED, pf_epoch = 0;
     auto prefetch = [&](uint64_t idx) {
         if (tid == 0 && idx < n_actions) {
-            const uint64_t r = actions[idx] >> 1;
-            if (r < rows.R) pf_assign = assign[r];     // this row's assignment (validated for staleness at use)
+            const uint32_t a_ = actions[idx];
+            const uint64_t r = a_ >> 1;
+            if (r < rows.R) {
+                // this row's assignment and, for a REMOVE, its packed group (validated for staleness at use)
+                pf_assign = assign[r];
+                pf_epoch = ss->epoch;
+                pf_pg = ((a_ & 1u) && pf_assign != LB_UNASSIGNED) ? g2p[pf_assign] : LB_UNASSIGNED;
+            }
         }
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
@@ -273,7 +307,7 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         }
     };
     auto commit = [&](int slot) {
-        if (tid == 0) ss->pf_assign[slot] = pf_assign;
+        if (tid == 0) { ss->pf_assign[slot] = pf_assign; ss->pf_pg[slot] = pf_pg; ss->pf_epoch[slot] = pf_epoch; }
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
             if (q * SW_THREADS + warp * 32 >= nf) break;
@@ -292,7 +326,8 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
 
     // owner-warp update of this warp's feature stripe at group g
     auto update_stripe = [&](const uint32_t *c_raw, const uint32_t *c_obs, int g, int sign) {
-        for (int j = fb + lane * fstep; j < fe; j += 32 * fstep) {
+        for (int k = off[0] + lane; k < off[N_CLASS]; k += 32) {
+            const int j = s_own[k];
             if (!c_obs[j]) continue;
             const FeatDev &f = s_feat[j];
             lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
@@ -301,19 +336,78 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         __syncwarp();
     };
 
-    const uint64_t i0 = i;
     // assignment of the row of action idx: the ring value unless one of the two actions that ran
     // after the prefetch was issued touched the same row (thread 0 only)
-    auto row_assignment = [&](uint64_t idx, uint64_t r) -> uint32_t {
-        bool fresh = true;
-        for (int dd = 1; dd <= 2; ++dd)
-            if (idx >= i0 + dd && (actions[idx - dd] >> 1) == r) fresh = false;
+    uint64_t prev_r1 = ~0ull, prev_r2 = ~0ull;   // rows of the two previous actions of this launch
+    auto row_assignment = [&](uint64_t idx, uint64_t r, bool &fresh) -> uint32_t {
+        fresh = r != prev_r1 && r != prev_r2;
         return fresh ? ss->pf_assign[idx & 3] : assign[r];
     };
+    // structure changes (rare): add_group / remove_group of product_mixture.cc:178-183,233-238
+    auto structure_add_group = [&](int G) {
+        // add_group (product_mixture.cc:178-183): append a fresh empty group
+        const int ng = G;
+        for (int row = tid; row < n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
+        for (int row = tid; row < n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
+        __syncthreads();
+        for (int row = tid; row < n_cache_rows; row += SW_THREADS) {
+            const FeatDev &f = s_feat[cache_row_feat[row]];
+            lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
+                           cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
+        }
+        if (tid == 0) {
+            s_counts[ng] = 0u;
+            const uint32_t gid = ss->next_global;
+            p2g[ng] = gid;
+            g2p[gid] = (uint32_t)ng;
+            ss->next_global = gid + 1;
+            ss->G = ng + 1;
+        }
+        __syncthreads();
+        {   // one more occupied group: refresh the prior of the empty groups
+            const float she = logf((alpha + d * (float)(ng + 1 - n_empty)) / (float)n_empty);
+            for (int gg = tid; gg <= ng; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
+        }
+        __syncthreads();
+    };
+    auto structure_remove_group = [&](int G, int g, uint64_t i) {
+        // remove_group (product_mixture.cc:233-238): swap-with-last
+        __syncthreads();
+        const int last = G - 1;
+        if (g != last) {
+            for (int row = tid; row < n_int_rows; row += SW_THREADS)
+                ints[(size_t)row * st + g] = ints[(size_t)row * st + last];
+            for (int row = tid; row < n_flt_rows; row += SW_THREADS)
+                flts[(size_t)row * st + g] = flts[(size_t)row * st + last];
+            for (int row = tid; row < n_cache_rows; row += SW_THREADS)
+                cache[(size_t)row * st + g] = cache[(size_t)row * st + last];
+        }
+        if (tid == 0) {
+            g2p[ss->removed_global[i & 1]] = LB_UNASSIGNED;
+            if (g != last) {
+                s_counts[g] = s_counts[last];
+                s_prior[g] = s_prior[last];
+                const uint32_t gid = p2g[last];
+                p2g[g] = gid;
+                g2p[gid] = (uint32_t)g;
+                ss->epoch += 1;
+            }
+            s_counts[last] = 0u;
+            ss->G = last;
+        }
+        __syncthreads();
+        {   // one occupied group fewer: refresh the prior of the empty groups
+            const float she = logf((alpha + d * (float)(last - n_empty)) / (float)n_empty);
+            for (int gg = tid; gg < last; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
+        }
+        __syncthreads();
+    };
     int status = LB_ST_OK;
+    uint64_t cur_r = ~0ull;
     for (; i < n_actions; ++i) {
         const uint32_t act = actions[i];
         const uint64_t r = act >> 1;
+        prev_r2 = prev_r1; prev_r1 = cur_r; cur_r = r;
         const bool is_remove = act & 1u;
         const int slot = (int)(i & 3);
         const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
@@ -325,22 +419,16 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         if (!is_remove) {
             // ---- ADD: model.add_value -> score_value -> sample -> add_value ----
             if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
-            if (tid == 0 && row_assignment(i, r) != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
-            for (int g0 = 0; g0 < G; g0 += 128) {
-                float acc[4];
-                const int left = G - g0;
-                if (left <= 32) {
-                    score_stripe<1>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
-                    s_part[warp * st + g0 + lane] = acc[0];
-                } else if (left <= 64) {
-                    score_stripe<2>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
-                    s_part[warp * st + g0 + lane] = acc[0];
-                    s_part[warp * st + g0 + lane + 32] = acc[1];
-                } else {
-                    score_stripe<4>(my_cls, fb, fe, fstep, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) s_part[warp * st + g0 + lane + 32 * jj] = acc[jj];
-                }
+            if (tid == 0) { bool fresh; if (row_assignment(i, r, fresh) != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW; }
+            // 64 groups per trip (two per lane).  ONE tile shape on purpose: every extra
+            // instantiation of the scoring loops adds ~10 KB of hot code, and the loop body must
+            // stay inside the 32 KB instruction cache when 16 narrow CTAs share an SM.  Columns
+            // past G are allocated (st >= G rounded up to 64) and simply ignored.
+            for (int g0 = 0; g0 < G; g0 += 64) {
+                float acc[2];
+                score_warp<2>(off, s_own, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+                s_part[warp * st + g0 + lane] = acc[0];
+                s_part[warp * st + g0 + lane + 32] = acc[1];
             }
             LB_TICK(0);
             __syncthreads();  // (A) partial scores visible
@@ -367,8 +455,6 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
                     s_counts[pick] = n;
                     s_prior[pick] = logf((float)n - d);
                     ss->sample_size += 1;
-                    assign[r] = p2g[pick];
-                    if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)pick;
                 }
             } else {
                 commit((int)((i + 2) & 3));
@@ -376,44 +462,23 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
             }
             LB_TICK(2);
             __syncthreads();  // (B) pick visible
-            if (warp == 0) commit((int)((i + 2) & 3));
-            const int g = ss->pick[i & 1];
-            if (g >= 0) LB_TICK(3);
-            update_stripe(c_raw, c_obs, g, +1);
-            LB_TICK(4);
-            if (ss->flag[i & 1]) {
-                // add_group (product_mixture.cc:178-183): append a fresh empty group
-                const int ng = G;
-                for (int row = tid; row < n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
-                for (int row = tid; row < n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
-                __syncthreads();
-                for (int row = tid; row < n_cache_rows; row += SW_THREADS) {
-                    const FeatDev &f = s_feat[cache_row_feat[row]];
-                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
-                                   cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
-                }
-                if (tid == 0) {
-                    s_counts[ng] = 0u;
-                    const uint32_t gid = ss->next_global;
-                    p2g[ng] = gid;
-                    g2p[gid] = (uint32_t)ng;
-                    ss->next_global = gid + 1;
-                    ss->G = ng + 1;
-                }
-                __syncthreads();
-                {   // one more occupied group: refresh the prior of the empty groups
-                    const float she = logf((alpha + d * (float)(ng + 1 - n_empty)) / (float)n_empty);
-                    for (int gg = tid; gg <= ng; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
-                }
-                __syncthreads();
+            if (warp == 0) {
+                commit((int)((i + 2) & 3));
+                if (SW_WARPS == 1) next_uniform(i + 1);   // no idle warp to draw it during sampling
             }
+            if (tid == 0) {   // after (B): the p2g round trip overlaps the update instead of delaying the barrier
+                assign[r] = p2g[ss->pick[i & 1]];
+                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)ss->pick[i & 1];
+            }
+            LB_TICK(3);
         } else {
             // ---- REMOVE: pop global id -> packed; mixture.remove_value ----
             if (tid == 0) {
-                const uint32_t a = row_assignment(i, r);
+                bool fresh;
+                const uint32_t a = row_assignment(i, r, fresh);
                 if (a == LB_UNASSIGNED) ss->stop = LB_ST_REMOVE_UNASSIGNED;
                 else {
-                    const uint32_t g = g2p[a];
+                    const uint32_t g = (fresh && ss->pf_epoch[i & 3] == ss->epoch) ? ss->pf_pg[i & 3] : g2p[a];
                     const uint32_t n = s_counts[g] - 1u;
                     ss->pick[i & 1] = (int)g;
                     ss->removed_global[i & 1] = a;
@@ -427,44 +492,18 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
             }
             commit((int)((i + 2) & 3));
             next_uniform(i + 1);
-            LB_TICK(0);
+            LB_TICK(5);
             __syncthreads();  // (A)
             if (ss->stop) { status = ss->stop; break; }
-            const int g = ss->pick[i & 1];
-            if (g >= 0) LB_TICK(1);
-            update_stripe(c_raw, c_obs, g, -1);
-            LB_TICK(4);
-            if (ss->flag[i & 1]) {
-                // remove_group (product_mixture.cc:233-238): swap-with-last
-                __syncthreads();
-                const int last = G - 1;
-                if (g != last) {
-                    for (int row = tid; row < n_int_rows; row += SW_THREADS)
-                        ints[(size_t)row * st + g] = ints[(size_t)row * st + last];
-                    for (int row = tid; row < n_flt_rows; row += SW_THREADS)
-                        flts[(size_t)row * st + g] = flts[(size_t)row * st + last];
-                    for (int row = tid; row < n_cache_rows; row += SW_THREADS)
-                        cache[(size_t)row * st + g] = cache[(size_t)row * st + last];
-                }
-                if (tid == 0) {
-                    g2p[ss->removed_global[i & 1]] = LB_UNASSIGNED;
-                    if (g != last) {
-                        s_counts[g] = s_counts[last];
-                        s_prior[g] = s_prior[last];
-                        const uint32_t gid = p2g[last];
-                        p2g[g] = gid;
-                        g2p[gid] = (uint32_t)g;
-                    }
-                    s_counts[last] = 0u;
-                    ss->G = last;
-                }
-                __syncthreads();
-                {   // one occupied group fewer: refresh the prior of the empty groups
-                    const float she = logf((alpha + d * (float)(last - n_empty)) / (float)n_empty);
-                    for (int gg = tid; gg < last; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
-                }
-                __syncthreads();
-            }
+            LB_TICK(6);
+        }
+        // ---- both: the owner warps apply the row to group g (one copy of the update code) ----
+        const int g = ss->pick[i & 1];
+        update_stripe(c_raw, c_obs, g, is_remove ? -1 : +1);
+        LB_TICK(is_remove ? 7 : 4);
+        if (ss->flag[i & 1]) {
+            if (!is_remove) structure_add_group(G);
+            else structure_remove_group(G, g, i);
         }
     }
     __syncthreads();
@@ -481,29 +520,42 @@ k_cat_sweep(KindDev *kinds, const int32_t *kind_ids, const FeatDev *feats, const
         kd.progress = i;
     }
     if (prof && lane == 0 && kid < 16)
-        for (int k = 0; k < 6; ++k) prof[(kid * SW_WARPS + warp) * 8 + k] += (unsigned long long)pt[k];
+        for (int k = 0; k < 8; ++k) prof[(kid * SW_WARPS + warp) * 8 + k] += (unsigned long long)pt[k];
 #undef LB_TICK
 }
 
-static size_t sweep_smem_bytes(int nf, int Gcap) {
-    return 256 + (size_t)nf * (sizeof(FeatDev) + 4 + 32) + (size_t)Gcap * 4 * (3 + SW_WARPS) + 64;
+static int lb_upload_desc(Engine *e, const void *host, size_t bytes, void **dev);
+
+static size_t sweep_smem_bytes(int nf, int Gcap, int warps) {
+    return 256 + (size_t)nf * (sizeof(FeatDev) + 4 + 32 + 4) + (size_t)Gcap * 4 * (3 + warps) + 64;
 }
 
-int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
-                    uint64_t offset, uint32_t *d_picks, float *d_scores, int stride) {
-    size_t smem = 0;
+// warps per (chain, kind) CTA: 8 when the launch cannot fill the GPU anyway (lowest latency per
+// action), fewer when many chains are swept at once (a CTA spends most of an action waiting on
+// dependent loads and barriers, so narrow CTAs, 16 / W resident per SM, finish more actions per
+// second in aggregate).  LB_SWEEP_WARPS overrides (tests run every width).
+static int sweep_warps(const Engine *e, size_t n_ctas, int max_nf) {
+    int w = 8;
+    if (n_ctas >= (size_t)e->n_sm * 12) w = 1;
+    else if (n_ctas >= (size_t)e->n_sm * 6) w = 2;
+    else if (n_ctas >= (size_t)e->n_sm * 3) w = 4;
+    if (const char *v = getenv("LB_SWEEP_WARPS")) {
+        const int x = atoi(v);
+        if (x == 1 || x == 2 || x == 4 || x == 8) w = x;
+    }
+    while (w < 8 && max_nf > SW_PF * 32 * w) w *= 2;
+    return w;
+}
+
+// Describe one engine's part of a sweep launch (uploads its active kind ids on ITS stream).
+int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *d_actions, uint64_t n_actions,
+                   uint64_t seed, uint64_t offset, uint32_t *d_picks, float *d_scores, int stride, SweepChain *out) {
     for (int kid : kind_ids) {
         const KindHost &k = e->kinds[kid];
-        if ((int)k.fids.size() > SW_PF * SW_THREADS)
-            return lb_fail("cat_sweep: kind %d has %zu features (limit %d)", kid, k.fids.size(), SW_PF * SW_THREADS);
+        if ((int)k.fids.size() > SW_PF * 32 * SW_MAX_WARPS)
+            return lb_fail("cat_sweep: kind %d has %zu features (limit %d)", kid, k.fids.size(), SW_PF * 32 * SW_MAX_WARPS);
         if (k.Gcap > SW_MAX_G)
             return lb_fail("cat_sweep: kind %d needs %d group slots (limit %d)", kid, k.Gcap, SW_MAX_G);
-        smem = std::max(smem, sweep_smem_bytes((int)k.fids.size(), k.Gcap));
-    }
-    static size_t configured = 0;
-    if (smem > configured) {
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
     }
     if ((int)kind_ids.size() > e->d_kind_ids_cap) {
         if (e->d_kind_ids) cudaFree(e->d_kind_ids);
@@ -511,18 +563,68 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
         LB_CUDA(cudaMalloc((void **)&e->d_kind_ids, 4 * (kind_ids.size() + 16)));
         e->d_kind_ids_cap = (int)kind_ids.size() + 16;
     }
-    int32_t *d_ids = e->d_kind_ids;
-    LB_CUDA(cudaMemcpyAsync(d_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
-    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
-    LB_CUDA(cudaEventRecord(e->kev0, e->stream));
-    k_cat_sweep<<<(unsigned)kind_ids.size(), SW_THREADS, smem, e->stream>>>(
-        e->d_kinds, d_ids, e->d_feats, e->d_kind_feats, e->d_aux, rows, e->d_actions, n_actions, seed,
-        offset, (int)e->kinds.size(), e->empty_group_count, d_picks, d_scores, stride, e->d_prof);
-    LB_CUDA(cudaGetLastError());
-    LB_CUDA(cudaEventRecord(e->kev1, e->stream));
-    e->kev_pending = true;
-    e->launches[LB_L_TOTAL]++; e->launches[LB_L_SWEEP]++;
+    LB_CUDA(cudaMemcpyAsync(e->d_kind_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
+    SweepChain c;
+    c.kinds = e->d_kinds; c.kind_ids = e->d_kind_ids; c.n_ids = (int)kind_ids.size();
+    c.feats = e->d_feats; c.kind_feats = e->d_kind_feats; c.aux = e->d_aux;
+    c.rows = RowsDev{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    c.actions = d_actions; c.n_actions = n_actions; c.seed = seed; c.offset = offset;
+    c.K = (int)e->kinds.size(); c.n_empty = e->empty_group_count;
+    c.dbg_picks = d_picks; c.dbg_scores = d_scores; c.dbg_stride = stride; c.prof = e->d_prof;
+    *out = c;
     return 0;
+}
+
+// One launch for `n` chains on the leader's stream: grid (max active kinds, chains).
+int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
+                           const std::vector<std::vector<int>> &kind_ids) {
+    size_t n_ctas = 0, smem = 0;
+    int max_nf = 0, max_ids = 0;
+    for (int c = 0; c < n; ++c) {
+        n_ctas += kind_ids[c].size();
+        max_ids = std::max(max_ids, (int)kind_ids[c].size());
+        for (int kid : kind_ids[c]) max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
+    }
+    if (!n_ctas) return 0;
+    const int W = sweep_warps(leader, n_ctas, max_nf);
+    for (int c = 0; c < n; ++c)
+        for (int kid : kind_ids[c]) {
+            const KindHost &k = engines[c]->kinds[kid];
+            smem = std::max(smem, sweep_smem_bytes((int)k.fids.size(), k.Gcap, W));
+        }
+    static size_t configured[SW_MAX_WARPS + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (smem > configured[W]) {
+        const void *fn = W == 1 ? (const void *)k_cat_sweep<1> : W == 2 ? (const void *)k_cat_sweep<2>
+                       : W == 4 ? (const void *)k_cat_sweep<4> : (const void *)k_cat_sweep<8>;
+        LB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[W] = smem;
+    }
+    const SweepChain *d_many = nullptr;
+    if (n > 1) {
+        void *d = nullptr;
+        LB_TRY(lb_upload_desc(leader, chains, sizeof(SweepChain) * (size_t)n, &d));
+        d_many = (const SweepChain *)d;
+    }
+    const dim3 grid((unsigned)max_ids, (unsigned)n);
+    LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
+    switch (W) {
+    case 1: k_cat_sweep<1><<<grid, 32, smem, leader->stream>>>(chains[0], d_many); break;
+    case 2: k_cat_sweep<2><<<grid, 64, smem, leader->stream>>>(chains[0], d_many); break;
+    case 4: k_cat_sweep<4><<<grid, 128, smem, leader->stream>>>(chains[0], d_many); break;
+    default: k_cat_sweep<8><<<grid, 256, smem, leader->stream>>>(chains[0], d_many); break;
+    }
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaEventRecord(leader->kev1, leader->stream));
+    leader->kev_pending = true;
+    leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
+    return 0;
+}
+
+int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
+                    uint64_t offset, uint32_t *d_picks, float *d_scores, int stride) {
+    SweepChain c;
+    LB_TRY(lb_sweep_chain(e, kind_ids, e->d_actions, n_actions, seed, offset, d_picks, d_scores, stride, &c));
+    return lb_launch_sweep_chains(e, &c, 1, {e}, {kind_ids});
 }
 
 // ===========================================================================

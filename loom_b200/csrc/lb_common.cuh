@@ -103,8 +103,13 @@ __device__ __forceinline__ float lb_stirling_corr(float z) {
 __device__ __forceinline__ float lb_lgamma_big(float z) {  // z >= 8
     return (z - 0.5f) * logf(z) - z + 0.918938533f + lb_stirling_corr(z);
 }
+// libm's lgamma is several hundred instructions: keep ONE copy out of line.  It only serves
+// small arguments (groups of a few rows); inlined at every call site it pushed the hot loop of
+// the sweep kernel past the 32 KB instruction cache.
+static __device__ __noinline__ float lb_lgammaf_small(float z) { return lgammaf(z); }
+static __device__ __noinline__ double lb_lgamma_d(double z) { return lgamma(z); }
 __device__ __forceinline__ float lb_lgamma(float z) {
-    return z >= 8.f ? lb_lgamma_big(z) : lgammaf(z);
+    return z >= 8.f ? lb_lgamma_big(z) : lb_lgammaf_small(z);
 }
 // lgamma(a + x) - lgamma(a), a > 0, x >= 0
 __device__ __forceinline__ float lb_lgamma_diff(float a, float x) {
@@ -119,7 +124,7 @@ __device__ __forceinline__ float lb_lgamma_diff(float a, float x) {
         for (float j = 1.f; j < x; j += 1.f) p *= a + j;
         return logf(p);
     }
-    return lb_lgamma(b) - lgammaf(a);
+    return lb_lgamma(b) - lb_lgammaf_small(a);
 }
 // lgamma(a + x) - lgamma(a) for an integer count x: short rising factorials are
 // one or two logs of an exact-ish product; longer ones use the Stirling form.
@@ -165,7 +170,7 @@ __device__ const double LB_LOG_FACTORIAL[32] = {
     61.261701761002001, 64.557538627006338, 67.889743137181540, 71.257038967168015,
     74.658236348830158, 78.092223553315307};
 __device__ __forceinline__ double lb_log_factorial_d(uint32_t x) {
-    return x < 32u ? LB_LOG_FACTORIAL[x] : lgamma((double)x + 1.0);
+    return x < 32u ? LB_LOG_FACTORIAL[x] : lb_lgamma_d((double)x + 1.0);
 }
 
 // ---- per-feature cached scorer refresh (one group) -------------------------

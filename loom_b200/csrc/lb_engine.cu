@@ -301,11 +301,11 @@ extern "C" void lb_destroy(lb_handle h) {
     if (e->d_prof) {
         std::vector<unsigned long long> p(16 * 8 * 8);
         cudaMemcpy(p.data(), e->d_prof, 8 * p.size(), cudaMemcpyDeviceToHost);
-        const char *names[6] = {"work1", "waitA", "sample", "waitB", "update", "rare"};
+        const char *names[8] = {"a.score", "a.waitA", "a.sample", "a.waitB", "a.update", "r.lookup", "r.waitA", "r.update"};
         for (size_t k = 0; k < e->kinds.size() && k < 16; ++k) {
             fprintf(stderr, "[LB_PROFILE] kind %zu nf=%zu (Mcycles per warp 0..7)\n", k, e->kinds[k].fids.size());
-            for (int j = 0; j < 5; ++j) {
-                fprintf(stderr, "[LB_PROFILE]   %-6s", names[j]);
+            for (int j = 0; j < 8; ++j) {
+                fprintf(stderr, "[LB_PROFILE]   %-8s", names[j]);
                 for (int w = 0; w < 8; ++w) fprintf(stderr, " %7.0f", p[(k * 8 + w) * 8 + j] * 1e-6);
                 fprintf(stderr, "\n");
             }
@@ -562,6 +562,91 @@ extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, ui
     if (debug_scores)
         LB_CUDA(cudaMemcpyAsync(debug_scores, d_scores, 4 * n * K * (size_t)stride, cudaMemcpyDeviceToHost, e->stream));
     LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// loom/tasks.py:173-194 (samples in parallel): the same actions on many chains, one launch
+extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                                  const uint64_t *seeds, uint64_t offset) {
+    if (n_handles <= 0 || n == 0) return 0;
+    std::vector<Engine *> es(n_handles);
+    for (int c = 0; c < n_handles; ++c) {
+        es[c] = (Engine *)handles[c];
+        if (!es[c]) return lb_fail("cat_sweep_multi: null handle %d", c);
+        if (es[c]->device != es[0]->device) return lb_fail("cat_sweep_multi: handles live on different devices");
+        if (!es[c]->R) return lb_fail("cat_sweep before set_rows");
+        for (int b = 0; b < c; ++b) if (es[b] == es[c]) return lb_fail("cat_sweep_multi: handle %d listed twice", c);
+    }
+    Engine *lead = es[0];
+    LB_CUDA(cudaSetDevice(lead->device));
+    if (n > lead->actions_cap) {
+        dev_free(lead->d_actions);
+        LB_TRY(dev_alloc(&lead->d_actions, n));
+        lead->actions_cap = n;
+    }
+    LB_CUDA(cudaMemcpyAsync(lead->d_actions, actions, 4 * n, cudaMemcpyHostToDevice, lead->stream));
+    std::vector<std::vector<int>> active(n_handles);
+    std::vector<std::vector<uint64_t>> progress(n_handles);
+    for (int c = 0; c < n_handles; ++c) {
+        LB_TRY(lb_sync_model(es[c]));
+        const int K = (int)es[c]->kinds.size();
+        for (int kid = 0; kid < K; ++kid) active[c].push_back(kid);
+        progress[c].assign(K, 0);
+    }
+    for (int round = 0;; ++round) {
+        if (round > 64) return lb_fail("cat_sweep: no progress after repeated table growth");
+        std::vector<SweepChain> chains;
+        std::vector<Engine *> live;
+        std::vector<std::vector<int>> live_ids;
+        std::vector<int> live_idx;
+        for (int c = 0; c < n_handles; ++c) {
+            if (active[c].empty()) continue;
+            Engine *e = es[c];
+            const int K = (int)e->kinds.size();
+            for (int kid : active[c]) e->h_kinds[kid].progress = progress[c][kid];
+            LB_CUDA(cudaMemcpyAsync(e->d_kinds, e->h_kinds.data(), sizeof(KindDev) * K, cudaMemcpyHostToDevice, e->stream));
+            SweepChain ch;
+            LB_TRY(lb_sweep_chain(e, active[c], lead->d_actions, n, seeds[c], offset, nullptr, nullptr, 0, &ch));
+            if (e != lead) LB_CUDA(cudaStreamSynchronize(e->stream));   // its uploads precede the leader's launch
+            chains.push_back(ch); live.push_back(e); live_ids.push_back(active[c]); live_idx.push_back(c);
+        }
+        if (chains.empty()) break;
+        LB_TRY(lb_launch_sweep_chains(lead, chains.data(), (int)chains.size(), live, live_ids));
+        LB_CUDA(cudaStreamSynchronize(lead->stream));
+        if (lead->kev_pending) {
+            float ms = 0.f;
+            LB_CUDA(cudaEventElapsedTime(&ms, lead->kev0, lead->kev1));
+            lead->kernel_ms[LB_L_SWEEP] += ms; lead->kernel_ms[LB_L_TOTAL] += ms;
+            lead->kev_pending = false;
+        }
+        for (size_t l = 0; l < live.size(); ++l) {
+            Engine *e = live[l];
+            const int c = live_idx[l];
+            LB_TRY(lb_pull_kinds(e));
+            std::vector<int> again;
+            for (int kid : active[c]) {
+                const KindDev &d = e->h_kinds[kid];
+                progress[c][kid] = d.progress;
+                switch (d.status) {
+                case LB_ST_OK: break;
+                case LB_ST_NEED_GROW: again.push_back(kid); break;
+                case LB_ST_DUPLICATE_ROW:
+                    return lb_fail("duplicate row: %u (chain %d, kind %d)", actions[d.progress] >> 1, c, kid);
+                case LB_ST_REMOVE_UNASSIGNED:
+                    return lb_fail("remove of unassigned row %u (chain %d, kind %d)", actions[d.progress] >> 1, c, kid);
+                default:
+                    return lb_fail("action %llu: row out of range", (unsigned long long)d.progress);
+                }
+            }
+            for (int kid : again) {
+                KindHost &k = e->kinds[kid];
+                if (k.G + 1 > k.Gcap) LB_TRY(lb_kind_grow(e, kid, 2 * k.Gcap));
+                if (k.next_global + 1 > k.g2p_cap) LB_TRY(lb_launch_renumber(e, kid));
+            }
+            if (!again.empty()) LB_TRY(lb_sync_model(e));
+            active[c].swap(again);
+        }
+    }
     return 0;
 }
 

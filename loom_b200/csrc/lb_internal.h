@@ -33,6 +33,23 @@ struct AccTarget {             // packed ids of every row + the [rows][st] table
     double *flts;
     int st, G, width;
 };
+struct KindDev;
+struct SweepChain {            // one chain's part of a sweep launch (k_cat_sweep, blockIdx.y)
+    KindDev *kinds;
+    const int32_t *kind_ids;
+    int n_ids;
+    const FeatDev *feats;
+    const int32_t *kind_feats;
+    const float *aux;
+    RowsDev rows;
+    const uint32_t *actions;
+    uint64_t n_actions, seed, offset;
+    int K, n_empty;
+    uint32_t *dbg_picks;
+    float *dbg_scores;
+    int dbg_stride;
+    unsigned long long *prof;
+};
 struct PackSrc {               // out[r] = g2p[assign[r]] narrowed to `width` bytes
     const uint32_t *assign, *g2p;
     void *out;
@@ -156,6 +173,10 @@ int lb_refresh_kind(Engine *e, int kid);      // rebuild all cached scorers of a
 int lb_ensure_scratch(Engine *e, size_t bytes);
 
 // kernels (lb_cat.cu)
+int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *d_actions, uint64_t n_actions,
+                   uint64_t seed, uint64_t offset, uint32_t *d_picks, float *d_scores, int stride, SweepChain *out);
+int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
+                           const std::vector<std::vector<int>> &kind_ids);
 int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
                     uint64_t offset, uint32_t *d_picks, float *d_scores, int stride);
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);

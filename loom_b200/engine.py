@@ -155,6 +155,20 @@ def sweep_actions(n_rows, add=True, remove=False, start=0):
     return ((rows << 1) | (0 if add else 1)).astype(np.uint32)
 
 
+def cat_sweep_multi(engines, actions, seeds, action_offset=0):
+    """The same action list on several independent chains (loom's samples, loom/tasks.py:173-194)
+    in one call; chain c draws with seeds[c]."""
+    if not engines:
+        return
+    actions = np.ascontiguousarray(actions, dtype=np.uint32)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    assert len(seeds) == len(engines)
+    hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    a = engines[0].abi
+    a.check(a.cat_sweep_multi(hs, len(engines), ptr(actions, _u32p), len(actions),
+                              seeds.ctypes.data_as(C.POINTER(C.c_uint64)), action_offset))
+
+
 class Engine:
     def __init__(self, abi, device=0):
         self.abi = abi

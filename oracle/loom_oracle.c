@@ -526,6 +526,17 @@ int lo_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, uint64_t seed
                      stride, 0, NULL, NULL, NULL);
 }
 
+/* loom/tasks.py:173-194: samples are independent chains; the restatement runs them one after the
+ * other (bench.py runs reference chains in parallel processes, as loom's parallel_map does) */
+int lo_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                       const uint64_t *seeds, uint64_t offset) {
+    for (int32_t c = 0; c < n_handles; ++c) {
+        int rc = lo_cat_sweep(handles[c], actions, n, seeds[c], offset, NULL, NULL, NULL, 0);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int64_t lo_cat_replay(lb_handle h, const uint32_t *actions, uint64_t n, uint64_t seed,
                       uint64_t offset, const uint32_t *picks, const float *dev_scores,
                       int32_t stride, double tol, double *max_score_err) {

@@ -145,6 +145,7 @@ def test_cuda_reproduces_recorded_results(cuda_abi, small):
     for k in range(model.n_kinds):
         c, i, _f = e.get_groups(k)
         want_c, want_i = z["sweep_counts_%d" % k], z["sweep_ints_%d" % k]
-        assert np.array_equal(c, want_c[used[k]]) and want_c.sum() == c.sum()
-        assert np.array_equal(i, want_i[:, used[k]])
+        n = len(used[k])                     # get_groups also returns the trailing empty group
+        assert np.array_equal(c[:n], want_c[used[k]]) and want_c.sum() == c.sum()
+        assert np.array_equal(i[:, :n], want_i[:, used[k]]) and not i[:, n:].any()
     assert rel_err(e.score_data(), float(z["sweep_score_data"])) <= SCORE_TOL
