@@ -25,9 +25,11 @@ roofline= the dominant kernel (k_cat_sweep): algorithmic bytes per launch
           batch kernels (score_rows K1, accumulate_rows K2) that ARE HBM-bound.
 samples : the exact Gibbs chain of one kind is sequential, so one chain keeps only
           K (=7) of the 148 SMs busy.  loom itself runs `sample_count` independent
-          chains per dataset in parallel processes (loom/tasks.py:173-194, default 10);
-          the GPU runs 2 * floor(148 / K) = 42 of them concurrently (two CTAs per SM),
-          one CTA per (chain, kind), each chain its own engine + stream behind the same C ABI.
+          chains per dataset in parallel processes (loom/tasks.py:173-194, default 10)
+          over ONE rows file; the GPU sweeps many chains in ONE launch per action list
+          (lb_cat_sweep_multi, rows shared with lb_share_rows): one CTA per (chain, kind),
+          one warp wide when there are enough chains to fill every SM 16 times over
+          (default 672 chains = two waves), 8 warps wide for a single chain.
           `value` is the aggregate over those chains ("config.samples"); the
           single-chain rate is in "rates".  The reference arm gets the same treatment:
           as many chains in parallel as the host cores allow.
@@ -223,14 +225,14 @@ def run_reference_arm(args, model, rows, n_cells_full):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--rows", type=int, default=0, help="override the row count (parity runs only)")
     ap.add_argument("--ref-rows", type=int, default=20000)
     ap.add_argument("--samples", type=int, default=0,
-                    help="independent chains run concurrently per GPU (0 = 2 * floor(#SM / #kinds))")
+                    help="independent chains swept per GPU in one launch (0 = two waves of 16 one-warp CTAs per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -279,34 +281,28 @@ def main():
     cells_per_step = 4 * n_obs
     first, drain = step_actions(R)
 
-    n_chains = args.samples or max(1, 2 * (148 // model.n_kinds))   # 2 CTAs per SM (124 registers)
+    from loom_b200.engine import cat_sweep_multi
+    # Two waves of 16 one-warp CTAs per SM: 2 * 16 * 148 / K chains, in whole blocks of 8 chains.
+    n_chains = args.samples or max(1, (2 * 16 * 148 // model.n_kinds) // 8 * 8)
     config["samples"] = n_chains
-    config["parallelism"] = "%d independent chains x %d kinds per GPU, one CTA per (chain, kind)%s" % (
-        n_chains, model.n_kinds, "; replicas x%d" % world if world > 1 else "")
+    config["parallelism"] = ("%d independent chains x %d kinds per GPU in ONE launch per sweep "
+                             "(lb_cat_sweep_multi): one CTA per (chain, kind), 1-8 warps wide by how many "
+                             "chains there are; all chains read one shared row block%s" % (
+                                 n_chains, model.n_kinds, "; replicas x%d" % world if world > 1 else ""))
+    config["l2_policy"] = ("per-chain tables (%d chains x ~17 MB) exceed the 126 MB L2 many times over and every "
+                           "step rewrites all of them; the shared 26 MB row block is re-streamed every pass" % n_chains)
     engines = []
     for c in range(n_chains):
         eng = Engine(cuda, device=local_rank)
         eng.set_model(model)
-        eng.set_rows(rows)
+        if c == 0:
+            eng.set_rows(rows)
+        else:
+            eng.share_rows(engines[0])       # loom's samples read one rows file (loom/tasks.py:173-194)
         engines.append(eng)
     e = engines[0]
     for a in (rows.cat8, rows.wide, rows.mask):
         pin(a)
-
-    def on_all(fn):
-        """run fn(chain_index, engine) for every chain concurrently (ctypes drops the GIL)"""
-        errs = []
-
-        def wrap(c):
-            try:
-                fn(c, engines[c])
-            except Exception as exc:  # surface failures of worker threads
-                errs.append(exc)
-        ths = [threading.Thread(target=wrap, args=(c,)) for c in range(n_chains)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
-        if errs:
-            raise errs[0]
 
     def barrier():
         for eng in engines:
@@ -324,22 +320,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def device_step(c, eng, it):
-        seed = 100000 * rank + 1000 * c + it
-        eng.cat_sweep(first, seed=seed)
-        eng.cat_sweep(drain, seed=seed)
+    def chain_seeds(base, it):
+        return np.arange(n_chains, dtype=np.uint64) * 1000 + np.uint64(base * rank + it)
 
-    # ---- single chain, device resident (rates.single_chain) ----
+    def device_step(it):
+        seeds = chain_seeds(100000, it)
+        cat_sweep_multi(engines, first, seeds)
+        cat_sweep_multi(engines, drain, seeds)
+
+    # ---- single chain, device resident (rates.single_chain): 8-warp CTAs, lowest latency ----
     for it in range(2):
-        device_step(0, e, it)
+        e.cat_sweep(first, seed=it)
+        e.cat_sweep(drain, seed=it)
     e.sync()
     e.timer_start()
-    device_step(0, e, 2)
+    e.cat_sweep(first, seed=2)
+    e.cat_sweep(drain, seed=2)
     single_ms = e.timer_stop()
 
-    # ---- device-resident value: all chains concurrently ----
+    # ---- device-resident value: all chains, one launch per sweep ----
     for it in range(args.warmup):
-        on_all(lambda c, eng: device_step(c, eng, it))
+        device_step(it)
     barrier()
     for eng in engines:
         eng.launch_count(reset=True)
@@ -347,49 +348,42 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    elapsed = [0.0] * n_chains
-
-    def timed(c, eng):
-        eng.timer_start()                      # CUDA events on the chain's own stream
-        for it in range(args.steps):
-            device_step(c, eng, args.warmup + it)
-        elapsed[c] = eng.timer_stop()
     t0 = time.perf_counter()
-    on_all(timed)
+    e.timer_start()                            # CUDA events on the stream the sweeps are launched on
+    for it in range(args.steps):
+        device_step(args.warmup + it)
+    dev_ms = e.timer_stop()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    if os.environ.get("LB_BENCH_DEBUG"):
-        log("per-chain elapsed ms:", [round(x) for x in elapsed], "wall", round(wall_ms),
-            "groups", [[eng.kind_info(k).n_groups for k in range(model.n_kinds)] for eng in engines[:3]])
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = sum(eng.launch_count() for eng in engines)
     kms = sum(eng.kernel_ms() for eng in engines)
-    total_ms = max_over_ranks(max(max(elapsed), wall_ms))   # slowest chain / host view, max over ranks
+    total_ms = max_over_ranks(max(dev_ms, wall_ms))   # device events / host view, max over ranks
     ms_per_step = total_ms / args.steps
     value = world * n_chains * cells_per_step / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers in, assignments out, inside the timed region ----
-    def e2e_step(c, eng, it):
-        seed = 500000 * rank + 1000 * c + it
-        eng.set_rows(rows)                    # H2D of the whole row block
-        eng.cat_sweep(first, seed=seed)
-        for k in range(model.n_kinds):
-            eng.get_assignments(k)            # D2H of every kind's assignment column
-        eng.cat_sweep(drain, seed=seed)
+    def e2e_step(it):
+        seeds = chain_seeds(500000, it)
+        e.set_rows(rows)                      # H2D of the whole row block (pinned), once: chains share it
+        for eng in engines[1:]:
+            eng.share_rows(e)
+        cat_sweep_multi(engines, first, seeds)
+        for eng in engines:
+            for k in range(model.n_kinds):
+                eng.get_assignments(k)        # D2H of every chain's assignment columns
+        cat_sweep_multi(engines, drain, seeds)
 
-    on_all(lambda c, eng: e2e_step(c, eng, 0))
+    e2e_step(0)
     barrier()
-
-    def e2e_timed(c, eng):
-        for it in range(args.steps):
-            e2e_step(c, eng, 1 + it)
     t0 = time.perf_counter()
-    on_all(e2e_timed)
+    for it in range(args.steps):
+        e2e_step(1 + it)
     barrier()
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(e2e_wall) / args.steps
     e2e_value = world * n_chains * cells_per_step / (e2e_ms * 1e-3)
-    h2d = n_chains * int(rows.cat8.nbytes + rows.wide.nbytes + rows.mask.nbytes + 4 * (len(first) + len(drain)))
+    h2d = int(rows.cat8.nbytes + rows.wide.nbytes + rows.mask.nbytes + 4 * (len(first) + len(drain)))
     d2h = n_chains * int(4 * R * model.n_kinds)
 
     # ---- roofline of the dominant kernel ----
@@ -407,16 +401,16 @@ def main():
     avg_launch_ms = sweep_ms / max(n_sweep, 1)
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
     traffic = None
-    tpath = os.path.join(REPO, "profiles", "r1_k_cat_sweep_traffic.json")
-    if os.path.exists(tpath) and args.workload == "C2" and not args.rows:
+    tpath = os.path.join(REPO, "profiles", "r1_k_cat_sweep_multi_traffic.json")
+    if os.path.exists(tpath) and args.workload == "C2" and not args.rows and n_chains == 672:
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full, dominant launch type
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
-                "kernel_share_of_step": sweep_ms / (total_ms * n_chains) if total_ms else None,
-                "concurrent_launches": n_chains,
-                "note": "exact sequential Gibbs: latency-bound dependent chain, one CTA per (chain, kind); "
-                        "achieved is per launch, %d launches run concurrently" % n_chains}
+                "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
+                "chains_per_launch": n_chains,
+                "note": "exact sequential Gibbs: a dependent chain per (chain, kind) CTA, latency- and "
+                        "instruction-fetch-bound, not bandwidth-bound; one launch sweeps all %d chains" % n_chains}
 
     # ---- auxiliary: the HBM-bound batch kernels on the same workload ----
     aux = {}

@@ -153,6 +153,14 @@ int LB_NAME(set_rows_diff)(lb_handle h, uint64_t n_rows, const uint8_t *tare_obs
                            const uint32_t *pos_value, const uint64_t *neg_ptr,
                            const uint32_t *neg_feature);
 
+/* Use `owner`'s row block instead of holding a copy: loom's samples all read the
+ * same shuffled rows file (loom/tasks.py:173-194 passes one `rows` path to every
+ * seed).  `h` must carry the same schema; its assignments are reset as by
+ * set_rows.  The block stays valid until `owner` replaces its rows with a
+ * different row count or is destroyed; after the owner re-uploads rows, call
+ * share_rows again. */
+int LB_NAME(share_rows)(lb_handle h, lb_handle owner);
+
 /* CatKernel::add_row / remove_row over a list of actions, every kind
  * (src/cat_kernel.hpp:177-299; scheduling of src/cat_pipeline.cc:103-125):
  * exact single-site Gibbs, sequential in action order inside each kind, kinds

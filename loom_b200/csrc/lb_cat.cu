@@ -33,6 +33,10 @@
 // shared-memory ring; the Philox uniform of the next ADD is drawn by an idle
 // warp while warp 0 samples.
 // ===========================================================================
+#ifndef LB_W1_CTAS
+#define LB_W1_CTAS 16    // resident one-warp CTAs per SM the register budget is set for
+#endif
+constexpr int SW_CPB = 8;         // chains per block when a chain's CTA is a single warp
 constexpr int SW_MAX_WARPS = 8;   // warps per (chain, kind) CTA: 8 for latency, fewer when many chains fill the GPU
 constexpr int SW_PF = 4;          // row cells prefetched per thread -> nf <= 128 * warps per kind
 constexpr int SW_MAX_G = 4096;
@@ -174,13 +178,26 @@ __device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own
 }
 
 // W warps per CTA; registers are capped at 128 per thread for every W
+template <int W> __device__ __forceinline__ void sweep_sync() {
+    if (W == 1) __syncwarp(); else __syncthreads();
+}
+
+// W == 1: a block is SW_CPB independent one-warp "CTAs" -- SW_CPB chains of the SAME kind.  They
+// never synchronise with each other, but they run the same code over the same action list, so
+// they stay close to lockstep and share instruction-cache lines; 16 unrelated one-warp CTAs per
+// SM were instruction-fetch-bound (ncu: stall_no_instruction on top).
 template <int W>
-__global__ void __launch_bounds__(W * 32, 16 / W)
-k_cat_sweep(SweepChain one, const SweepChain *many) {
+__global__ void __launch_bounds__(W == 1 ? 32 * SW_CPB : W * 32, W == 1 ? 16 / SW_CPB : 16 / W)
+k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_chain) {
     constexpr int SW_THREADS = W * 32, SW_WARPS = W;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // blockIdx.y = chain (independent CrossCat states swept with the same action list), blockIdx.x = kind
-    const SweepChain &ch = many ? many[blockIdx.y] : one;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    // blockIdx.x = kind; chain (independent CrossCat states swept with the same action list) =
+    // blockIdx.y, or blockIdx.y * SW_CPB + warp-in-block when W == 1
+    const int sub = W == 1 ? (int)(threadIdx.x >> 5) : 0;
+    const int chain = W == 1 ? (int)blockIdx.y * SW_CPB + sub : (int)blockIdx.y;
+    if (chain >= n_chains) return;
+    unsigned char *const smem_raw = smem_all + (size_t)sub * smem_per_chain;
+    const SweepChain &ch = many ? many[chain] : one;
     if ((int)blockIdx.x >= ch.n_ids) return;
     KindDev *const kinds = ch.kinds;
     const FeatDev *const feats = ch.feats;
@@ -195,7 +212,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
     unsigned long long *const prof = ch.prof;
     const int kid = ch.kind_ids[blockIdx.x];
     KindDev &kd = kinds[kid];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = W == 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // LB_PROFILE=1: cycles per phase seen by lane 0 of every warp
     // ADD: 0 score | 1 wait at (A) | 2 sample / commit | 3 wait at (B) | 4 update;  REMOVE: 5 lookup | 6 wait at (A) | 7 update
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
@@ -241,7 +258,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             s_prior[g] = n ? logf((float)n - d) : sh_empty0;
         }
     }
-    __syncthreads();
+    sweep_sync<W>();
     if (tid == 0) {
         ss->G = kd.G; ss->stop = 0; ss->epoch = 0;
         ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
@@ -271,7 +288,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             ss->own_off[w][N_CLASS] = k;
         }
     }
-    __syncthreads();
+    sweep_sync<W>();
     int off[N_CLASS + 1];
 #pragma unroll
     for (int c = 0; c <= N_CLASS; ++c) off[c] = ss->own_off[warp][c];
@@ -322,7 +339,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
     prefetch(i); commit((int)(i & 3));
     prefetch(i + 1); commit((int)((i + 1) & 3));
     next_uniform(i);
-    __syncthreads();
+    sweep_sync<W>();
 
     // owner-warp update of this warp's feature stripe at group g
     auto update_stripe = [&](const uint32_t *c_raw, const uint32_t *c_obs, int g, int sign) {
@@ -349,7 +366,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
         const int ng = G;
         for (int row = tid; row < n_int_rows; row += SW_THREADS) ints[(size_t)row * st + ng] = 0u;
         for (int row = tid; row < n_flt_rows; row += SW_THREADS) flts[(size_t)row * st + ng] = 0.0;
-        __syncthreads();
+        sweep_sync<W>();
         for (int row = tid; row < n_cache_rows; row += SW_THREADS) {
             const FeatDev &f = s_feat[cache_row_feat[row]];
             lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
@@ -363,16 +380,16 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             ss->next_global = gid + 1;
             ss->G = ng + 1;
         }
-        __syncthreads();
+        sweep_sync<W>();
         {   // one more occupied group: refresh the prior of the empty groups
             const float she = logf((alpha + d * (float)(ng + 1 - n_empty)) / (float)n_empty);
             for (int gg = tid; gg <= ng; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
         }
-        __syncthreads();
+        sweep_sync<W>();
     };
     auto structure_remove_group = [&](int G, int g, uint64_t i) {
         // remove_group (product_mixture.cc:233-238): swap-with-last
-        __syncthreads();
+        sweep_sync<W>();
         const int last = G - 1;
         if (g != last) {
             for (int row = tid; row < n_int_rows; row += SW_THREADS)
@@ -395,12 +412,12 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             s_counts[last] = 0u;
             ss->G = last;
         }
-        __syncthreads();
+        sweep_sync<W>();
         {   // one occupied group fewer: refresh the prior of the empty groups
             const float she = logf((alpha + d * (float)(last - n_empty)) / (float)n_empty);
             for (int gg = tid; gg < last; gg += SW_THREADS) if (!s_counts[gg]) s_prior[gg] = she;
         }
-        __syncthreads();
+        sweep_sync<W>();
     };
     int status = LB_ST_OK;
     uint64_t cur_r = ~0ull;
@@ -431,7 +448,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
                 s_part[warp * st + g0 + lane + 32] = acc[1];
             }
             LB_TICK(0);
-            __syncthreads();  // (A) partial scores visible
+            sweep_sync<W>();  // (A) partial scores visible
             if (ss->stop) { status = ss->stop; break; }
             LB_TICK(1);       // after a barrier-dependent read (BAR.SYNC is deferred-blocking)
             if (warp == 0) {
@@ -461,7 +478,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
                 next_uniform(i + 1);
             }
             LB_TICK(2);
-            __syncthreads();  // (B) pick visible
+            sweep_sync<W>();  // (B) pick visible
             if (warp == 0) {
                 commit((int)((i + 2) & 3));
                 if (SW_WARPS == 1) next_uniform(i + 1);   // no idle warp to draw it during sampling
@@ -493,7 +510,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             commit((int)((i + 2) & 3));
             next_uniform(i + 1);
             LB_TICK(5);
-            __syncthreads();  // (A)
+            sweep_sync<W>();  // (A)
             if (ss->stop) { status = ss->stop; break; }
             LB_TICK(6);
         }
@@ -506,7 +523,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many) {
             else structure_remove_group(G, g, i);
         }
     }
-    __syncthreads();
+    sweep_sync<W>();
     for (int g = tid; g < st; g += SW_THREADS) {
         const uint32_t n = s_counts[g];
         kd.counts[g] = n;
@@ -586,17 +603,23 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         for (int kid : kind_ids[c]) max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
     }
     if (!n_ctas) return 0;
-    const int W = sweep_warps(leader, n_ctas, max_nf);
-    for (int c = 0; c < n; ++c)
-        for (int kid : kind_ids[c]) {
-            const KindHost &k = engines[c]->kinds[kid];
-            smem = std::max(smem, sweep_smem_bytes((int)k.fids.size(), k.Gcap, W));
-        }
+    int W = sweep_warps(leader, n_ctas, max_nf);
+    for (;;) {
+        smem = 0;
+        for (int c = 0; c < n; ++c)
+            for (int kid : kind_ids[c]) {
+                const KindHost &k = engines[c]->kinds[kid];
+                smem = std::max(smem, sweep_smem_bytes((int)k.fids.size(), k.Gcap, W));
+            }
+        smem = (smem + 15) / 16 * 16;
+        if (W == 1 && smem * SW_CPB > 200 * 1024) { W = 2; continue; }   // SW_CPB chains share a block's shared memory
+        break;
+    }
     static size_t configured[SW_MAX_WARPS + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (smem > configured[W]) {
         const void *fn = W == 1 ? (const void *)k_cat_sweep<1> : W == 2 ? (const void *)k_cat_sweep<2>
                        : W == 4 ? (const void *)k_cat_sweep<4> : (const void *)k_cat_sweep<8>;
-        LB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W == 1 ? smem * SW_CPB : smem)));
         configured[W] = smem;
     }
     const SweepChain *d_many = nullptr;
@@ -605,13 +628,13 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         LB_TRY(lb_upload_desc(leader, chains, sizeof(SweepChain) * (size_t)n, &d));
         d_many = (const SweepChain *)d;
     }
-    const dim3 grid((unsigned)max_ids, (unsigned)n);
+    const dim3 grid((unsigned)max_ids, (unsigned)(W == 1 ? (n + SW_CPB - 1) / SW_CPB : n));
     LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
     switch (W) {
-    case 1: k_cat_sweep<1><<<grid, 32, smem, leader->stream>>>(chains[0], d_many); break;
-    case 2: k_cat_sweep<2><<<grid, 64, smem, leader->stream>>>(chains[0], d_many); break;
-    case 4: k_cat_sweep<4><<<grid, 128, smem, leader->stream>>>(chains[0], d_many); break;
-    default: k_cat_sweep<8><<<grid, 256, smem, leader->stream>>>(chains[0], d_many); break;
+    case 1: k_cat_sweep<1><<<grid, 32 * SW_CPB, smem * SW_CPB, leader->stream>>>(chains[0], d_many, n, (int)smem); break;
+    case 2: k_cat_sweep<2><<<grid, 64, smem, leader->stream>>>(chains[0], d_many, n, (int)smem); break;
+    case 4: k_cat_sweep<4><<<grid, 128, smem, leader->stream>>>(chains[0], d_many, n, (int)smem); break;
+    default: k_cat_sweep<8><<<grid, 256, smem, leader->stream>>>(chains[0], d_many, n, (int)smem); break;
     }
     LB_CUDA(cudaGetLastError());
     LB_CUDA(cudaEventRecord(leader->kev1, leader->stream));

@@ -284,6 +284,13 @@ extern "C" int lb_create(int device, lb_handle *out) {
     return 0;
 }
 
+// forget a borrowed row block (never free it) so the engine can allocate its own
+static void drop_borrowed_rows(Engine *e) {
+    if (!e->rows_borrowed) return;
+    e->d_cat8 = nullptr; e->d_wide = nullptr; e->d_mask = nullptr;
+    e->rows_borrowed = false;
+}
+
 static void clear_model(Engine *e) {
     lb_free_proposer(e);
     for (auto &k : e->kinds) { lb_kind_release(e, k); dev_free(k.assign); }
@@ -313,6 +320,7 @@ extern "C" void lb_destroy(lb_handle h) {
         cudaFree(e->d_prof);
     }
     clear_model(e);
+    drop_borrowed_rows(e);
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
     lb_release_proposer(e);
@@ -366,12 +374,36 @@ extern "C" int lb_set_model(lb_handle h, int32_t F, const lb_feature_spec *specs
     return 0;
 }
 
+extern "C" int lb_share_rows(lb_handle h, lb_handle owner_h) {
+    Engine *e = (Engine *)h, *o = (Engine *)owner_h;
+    if (!e || !o || e == o) return lb_fail("share_rows: need two distinct handles");
+    LB_CUDA(cudaSetDevice(e->device));
+    if (e->device != o->device) return lb_fail("share_rows: handles live on different devices");
+    if (!e->F) return lb_fail("set_rows before set_model");
+    if (!o->R || !o->d_mask) return lb_fail("share_rows: the owner holds no rows");
+    if (o->rows_borrowed) return lb_fail("share_rows: the owner itself borrows its rows");
+    if (e->F != o->F || e->F8 != o->F8 || e->FW != o->FW) return lb_fail("share_rows: schemas differ");
+    for (int f = 0; f < e->F; ++f)
+        if (e->specs[f].type != o->specs[f].type || e->specs[f].dim != o->specs[f].dim)
+            return lb_fail("share_rows: feature %d differs between the two models", f);
+    if (!e->rows_borrowed) { dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask); }
+    if (o->R != e->R)
+        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, o->R)); }
+    e->R = o->R; e->W = o->W;
+    e->d_cat8 = o->d_cat8; e->d_wide = o->d_wide; e->d_mask = o->d_mask;
+    e->rows_borrowed = true;
+    for (auto &k : e->kinds) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)e->R, e->stream));
+    LB_CUDA(cudaStreamSynchronize(o->stream));   // the owner's upload (validated by its set_rows) is complete
+    return lb_sync_model(e);
+}
+
 extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wide,
                            const uint32_t *mask) {
     Engine *e = (Engine *)h;
     LB_CUDA(cudaSetDevice(e->device));
     if (!e->F) return lb_fail("set_rows before set_model");
     if (R >= (1ull << 31)) return lb_fail("set_rows: at most 2^31-1 rows per block");
+    drop_borrowed_rows(e);
     if (R != e->R || !e->d_mask) {
         dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
         e->R = R; e->W = (R + 31) / 32;
@@ -446,6 +478,7 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
     if (!e->F) return lb_fail("set_rows_diff before set_model");
     if (R >= (1ull << 31)) return lb_fail("set_rows_diff: at most 2^31-1 rows per block");
     const int F = e->F;
+    drop_borrowed_rows(e);
     if (R != e->R || !e->d_mask) {
         dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
         e->R = R; e->W = (R + 31) / 32;

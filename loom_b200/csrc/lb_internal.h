@@ -83,6 +83,7 @@ struct Engine {
 
     // rows
     uint64_t R = 0, W = 0;
+    bool rows_borrowed = false;        // row block belongs to another engine (lb_share_rows)
     uint8_t *d_cat8 = nullptr;
     uint32_t *d_wide = nullptr, *d_mask = nullptr;
 

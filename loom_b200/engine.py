@@ -204,6 +204,12 @@ class Engine:
                            ptr(rows.mask, _u32p)))
         self.n_rows = rows.n_rows
 
+    def share_rows(self, owner):
+        """read the owner's row block (loom's samples share one rows file)"""
+        self.abi.check(self.abi.share_rows(self.h, owner.h))
+        self.n_rows = owner.n_rows
+        self._rows_owner = owner       # keep it alive
+
     def set_rows_diff(self, n_rows, tare_observed, tare_values, row_has_tare, pos_ptr, pos_feature, pos_value,
                       neg_ptr, neg_feature):
         """Tare-compressed rows (ProductValue::Diff), see loom_b200/tare.py."""

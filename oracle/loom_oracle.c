@@ -208,7 +208,8 @@ void lo_destroy(lb_handle h) {
     if (!e) return;
     oracle_free_proposer(e);
     engine_clear_model(e);
-    free(e->cat8); free(e->wide); free(e->mask); free(e->hp_store);
+    if (!e->rows_borrowed) { free(e->cat8); free(e->wide); free(e->mask); }
+    free(e->hp_store);
     free(e);
 }
 
@@ -262,7 +263,8 @@ int lo_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wi
                 const uint32_t *mask) {
     engine_t *e = h;
     if (!e->F) return lo_fail("set_rows before set_model");
-    free(e->cat8); free(e->wide); free(e->mask);
+    if (!e->rows_borrowed) { free(e->cat8); free(e->wide); free(e->mask); }
+    e->rows_borrowed = 0;
     e->R = R; e->W = (R + 31) / 32;
     e->cat8 = xcalloc((size_t)e->F8 * R, 1);
     e->wide = xcalloc((size_t)e->FW * R, 4);
@@ -279,6 +281,25 @@ int lo_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wi
                     return lo_fail("row %llu feature %d value %u out of range",
                                    (unsigned long long)r, f, v);
             }
+    for (int k = 0; k < e->K; ++k) alloc_assign(e, &e->kinds[k]);
+    return 0;
+}
+
+/* loom/tasks.py:173-194: every sample reads the same rows file */
+int lo_share_rows(lb_handle h, lb_handle owner) {
+    engine_t *e = h, *o = owner;
+    if (!e || !o || e == o) return lo_fail("share_rows: need two distinct handles");
+    if (!e->F) return lo_fail("set_rows before set_model");
+    if (!o->R || !o->mask) return lo_fail("share_rows: the owner holds no rows");
+    if (o->rows_borrowed) return lo_fail("share_rows: the owner itself borrows its rows");
+    if (e->F != o->F || e->F8 != o->F8) return lo_fail("share_rows: schemas differ");
+    for (int f = 0; f < e->F; ++f)
+        if (e->specs[f].type != o->specs[f].type || e->specs[f].dim != o->specs[f].dim)
+            return lo_fail("share_rows: feature %d differs between the two models", f);
+    if (!e->rows_borrowed) { free(e->cat8); free(e->wide); free(e->mask); }
+    e->R = o->R; e->W = o->W;
+    e->cat8 = o->cat8; e->wide = o->wide; e->mask = o->mask;
+    e->rows_borrowed = 1;
     for (int k = 0; k < e->K; ++k) alloc_assign(e, &e->kinds[k]);
     return 0;
 }

@@ -38,6 +38,7 @@ typedef struct {
     double topo_alpha, topo_d;
     int empty_group_count;
     uint64_t R, W; /* rows, mask words per feature */
+    int rows_borrowed; /* cat8 / wide / mask belong to another engine (lo_share_rows) */
     uint8_t *cat8;
     uint32_t *wide;
     uint32_t *mask;

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import pe_util
-from loom_b200 import Engine, Model, sweep_actions, UNASSIGNED
+from loom_b200 import cat_sweep_multi, Engine, Model, sweep_actions, UNASSIGNED
 from loom_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -79,6 +79,53 @@ def test_sweep_matches_oracle_by_replay(oracle_abi, cuda_abi):
     assert bad == 0
     assert_same_state(o, g, model)
     assert g.score_data() == pytest.approx(o.score_data(), rel=1e-6)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_sweep_every_cta_width_and_multi_chain(oracle_abi, cuda_abi, monkeypatch, warps):
+    """1/2/4/8 warps per (chain, kind): each width replays exactly on the oracle, and the
+    many-chains launch (lb_cat_sweep_multi, rows shared by lb_share_rows) leaves every chain in
+    the state its own single-chain sweep reaches."""
+    monkeypatch.setenv("LB_SWEEP_WARPS", str(warps))
+    model, rows, _ = mixed(rows=900, seed=5)
+    R = rows.n_rows
+    acts = np.concatenate([sweep_actions(R), sweep_actions(R, add=True, remove=True)])
+    seeds = [21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31]     # 11 chains: a full block of 8 and a ragged one
+    singles = []
+    for c, seed in enumerate(seeds):
+        g = Engine(cuda_abi)
+        g.set_model(model)
+        g.set_rows(rows)
+        picks, scores = g.cat_sweep(acts, seed=seed, debug=True, debug_stride=64)
+        if c < 2:
+            o = Engine(oracle_abi)
+            o.set_model(model)
+            o.set_rows(rows)
+            bad, err = replay(oracle_abi, o, acts, seed, picks, scores, 64)
+            assert bad == 0 and err <= SCORE_TOL
+            assert_same_state(o, g, model)
+        singles.append(g)
+    owner = Engine(cuda_abi)
+    owner.set_model(model)
+    owner.set_rows(rows)
+    chains = [owner]
+    for _ in seeds[1:]:
+        g = Engine(cuda_abi)
+        g.set_model(model)
+        g.share_rows(owner)
+        chains.append(g)
+    cat_sweep_multi(chains, acts, seeds)
+    for a, b in zip(singles, chains):
+        for k in range(model.n_kinds):
+            assert np.array_equal(a.get_assignments(k), b.get_assignments(k))
+            assert all(np.array_equal(x, y) for x, y in zip(a.get_groups(k), b.get_groups(k)))
+    # chains differ from each other (independent seeds)
+    assert not np.array_equal(chains[0].get_assignments(0), chains[1].get_assignments(0))
+    # a second call continues from the current state; errors name the chain
+    cat_sweep_multi(chains, sweep_actions(R, add=False), seeds)
+    assert all(c.kind_info(0).sample_size == 0 for c in chains)
+    with pytest.raises(Exception, match="remove of unassigned row"):
+        cat_sweep_multi(chains, sweep_actions(4, add=False), seeds)
 
 
 def test_sweep_grows_tables_and_renumbers_ids(oracle_abi, cuda_abi, monkeypatch):

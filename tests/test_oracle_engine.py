@@ -41,6 +41,44 @@ def test_add_remove_roundtrip(oracle_abi):
         assert (e.get_assignments(k) == UNASSIGNED).all()
 
 
+def test_multi_chain_sweep_and_shared_rows(oracle_abi):
+    """cat_sweep_multi == one cat_sweep per chain with its own seed; share_rows aliases the owner's
+    block (loom's samples read one rows file, loom/tasks.py:173-194)."""
+    from loom_b200 import cat_sweep_multi
+    model, rows, _ = synth.generate(300, [("bb", 3), ("dd4", 2), ("gp", 2), ("nich", 2)], density=0.7, seed=3)
+    acts = np.concatenate([sweep_actions(300), sweep_actions(300, add=True, remove=True)])
+    seeds = [5, 6, 7]
+    singles = []
+    for seed in seeds:
+        e = Engine(oracle_abi)
+        e.set_model(model)
+        e.set_rows(rows)
+        e.cat_sweep(acts, seed=seed)
+        singles.append(e)
+    owner = Engine(oracle_abi)
+    owner.set_model(model)
+    owner.set_rows(rows)
+    chains = [owner]
+    for _ in seeds[1:]:
+        e = Engine(oracle_abi)
+        e.set_model(model)
+        e.share_rows(owner)
+        chains.append(e)
+    cat_sweep_multi(chains, acts, seeds)
+    for a, b in zip(singles, chains):
+        for k in range(model.n_kinds):
+            assert np.array_equal(a.get_assignments(k), b.get_assignments(k))
+            assert all(np.array_equal(x, y) for x, y in zip(a.get_groups(k), b.get_groups(k)))
+    other = Engine(oracle_abi)
+    other.set_model(synth.generate(10, [("bb", 2)], seed=1)[0])
+    with pytest.raises(Exception, match="schemas differ"):
+        other.share_rows(owner)
+    with pytest.raises(Exception, match="borrows"):
+        other2 = Engine(oracle_abi)
+        other2.set_model(model)
+        other2.share_rows(chains[1])
+
+
 def test_duplicate_row_is_an_error(oracle_abi):
     model, rows, _ = small_mixed(50)
     e = Engine(oracle_abi)
