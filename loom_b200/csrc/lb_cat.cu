@@ -36,7 +36,10 @@
 #ifndef LB_W1_CTAS
 #define LB_W1_CTAS 16    // resident one-warp CTAs per SM the register budget is set for
 #endif
-constexpr int SW_CPB = 8;         // chains per block when a chain's CTA is a single warp
+#ifndef LB_CPB
+#define LB_CPB 8
+#endif
+constexpr int SW_CPB = LB_CPB;    // chains per block when a chain's CTA is a single warp
 constexpr int SW_MAX_WARPS = 8;   // warps per (chain, kind) CTA: 8 for latency, fewer when many chains fill the GPU
 constexpr int SW_PF = 4;          // row cells prefetched per thread -> nf <= 128 * warps per kind
 constexpr int SW_MAX_G = 4096;
@@ -178,8 +181,17 @@ __device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own
 }
 
 // W warps per CTA; registers are capped at 128 per thread for every W
-template <int W> __device__ __forceinline__ void sweep_sync() {
+#ifndef LB_LOCKSTEP
+#define LB_LOCKSTEP 1
+#endif
+// W == 1: the warp is the whole "CTA" of its chain, so a warp-level sync is all correctness needs.
+// LB_LOCKSTEP >= 2 makes these points block-wide too: pure re-alignment of the block's chains.
+// (A chain that stops early simply exits; barriers only wait for warps that have not exited.)
+template <int W> __device__ __forceinline__ void sweep_sync() {   // rare paths, start-up
     if (W == 1) __syncwarp(); else __syncthreads();
+}
+template <int W> __device__ __forceinline__ void phase_sync() {   // the (A) / (B) points of every action
+    if (W == 1 && LB_LOCKSTEP < 2) __syncwarp(); else __syncthreads();
 }
 
 // W == 1: a block is SW_CPB independent one-warp "CTAs" -- SW_CPB chains of the SAME kind.  They
@@ -187,7 +199,7 @@ template <int W> __device__ __forceinline__ void sweep_sync() {
 // they stay close to lockstep and share instruction-cache lines; 16 unrelated one-warp CTAs per
 // SM were instruction-fetch-bound (ncu: stall_no_instruction on top).
 template <int W>
-__global__ void __launch_bounds__(W == 1 ? 32 * SW_CPB : W * 32, W == 1 ? 16 / SW_CPB : 16 / W)
+__global__ void __launch_bounds__(W == 1 ? 32 * SW_CPB : W * 32, W == 1 ? LB_W1_CTAS / SW_CPB : 16 / W)
 k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_chain) {
     constexpr int SW_THREADS = W * 32, SW_WARPS = W;
     extern __shared__ __align__(16) unsigned char smem_all[];
@@ -425,6 +437,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
         const uint32_t act = actions[i];
         const uint64_t r = act >> 1;
         prev_r2 = prev_r1; prev_r1 = cur_r; cur_r = r;
+        if (W == 1 && LB_LOCKSTEP >= 1) __syncthreads();   // re-align the block's chains (instruction-cache locality)
         const bool is_remove = act & 1u;
         const int slot = (int)(i & 3);
         const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
@@ -448,7 +461,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
                 s_part[warp * st + g0 + lane + 32] = acc[1];
             }
             LB_TICK(0);
-            sweep_sync<W>();  // (A) partial scores visible
+            phase_sync<W>();  // (A) partial scores visible
             if (ss->stop) { status = ss->stop; break; }
             LB_TICK(1);       // after a barrier-dependent read (BAR.SYNC is deferred-blocking)
             if (warp == 0) {
@@ -478,7 +491,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
                 next_uniform(i + 1);
             }
             LB_TICK(2);
-            sweep_sync<W>();  // (B) pick visible
+            phase_sync<W>();  // (B) pick visible
             if (warp == 0) {
                 commit((int)((i + 2) & 3));
                 if (SW_WARPS == 1) next_uniform(i + 1);   // no idle warp to draw it during sampling
@@ -510,7 +523,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
             commit((int)((i + 2) & 3));
             next_uniform(i + 1);
             LB_TICK(5);
-            sweep_sync<W>();  // (A)
+            phase_sync<W>();  // (A)
             if (ss->stop) { status = ss->stop; break; }
             LB_TICK(6);
         }
