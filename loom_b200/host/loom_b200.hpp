@@ -60,6 +60,11 @@ public:
         row_count_ = rows.row_count;
         LOOM_B200_CHECK(lb_set_rows(handle_, rows.row_count, rows.cat8.data(), rows.wide.data(), rows.mask.data()));
     }
+    // another sample over the same rows file (loom/tasks.py:173-194): read `owner`'s block
+    void rows_share(const CrossCat &owner) {
+        row_count_ = owner.row_count_;
+        LOOM_B200_CHECK(lb_share_rows(handle_, owner.handle_));
+    }
     // CrossCat::score_data (src/cross_cat.cc:238-250)
     float score_data() const {
         double s = 0;
@@ -120,6 +125,32 @@ public:
 private:
     CrossCat &cross_cat_;
     uint64_t seed_, offset_ = 0;
+    std::vector<uint32_t> actions_;
+};
+
+// loom.tasks.infer_many (loom/tasks.py:173-194) runs one process per sample; on the device the
+// samples are swept together: the same queued actions on every chain, ONE launch, chain c with
+// seeds[c].  This is the throughput mode (hundreds of chains fill the GPU); a single CatKernel is
+// the latency mode.
+class MultiCatKernel {
+public:
+    MultiCatKernel(const std::vector<CrossCat *> &chains, const std::vector<uint64_t> &seeds) : seeds_(seeds) {
+        for (CrossCat *c : chains) handles_.push_back(c->handle());
+    }
+    void add_row(uint64_t row_position) { actions_.push_back(LB_ACTION_ADD(row_position)); }
+    void remove_row(uint64_t row_position) { actions_.push_back(LB_ACTION_REMOVE(row_position)); }
+    void wait() {
+        if (actions_.empty()) return;
+        LOOM_B200_CHECK(lb_cat_sweep_multi(handles_.data(), (int32_t)handles_.size(), actions_.data(), actions_.size(),
+                                           seeds_.data(), offset_));
+        offset_ += actions_.size();
+        actions_.clear();
+    }
+
+private:
+    std::vector<lb_handle> handles_;
+    std::vector<uint64_t> seeds_;
+    uint64_t offset_ = 0;
     std::vector<uint32_t> actions_;
 };
 

@@ -19,5 +19,15 @@ int main(int argc, char **argv) {
     for (uint64_t r = 0; r < 64; ++r) cat.add_row(r);
     cat.wait();
     std::printf("score %f kinds %zu\n", cross_cat.score_data(), cross_cat.kind_count());
+    // two more samples over the same rows, swept together (loom/tasks.py:173-194)
+    CrossCat second(0);
+    second.model_load(feats, {0.f}, {0, 0}, {2.f, 0.1f}, topo);
+    second.rows_share(cross_cat);
+    for (uint64_t r = 0; r < 64; ++r) cat.remove_row(r);
+    cat.wait();
+    MultiCatKernel multi({&cross_cat, &second}, {7, 8});
+    for (uint64_t r = 0; r < 64; ++r) multi.add_row(r);
+    multi.wait();
+    std::printf("scores %f %f\n", cross_cat.score_data(), second.score_data());
     return 0;
 }
