@@ -203,14 +203,16 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SW_CPB : W * 32, W == 1 ? LB_W1_
 k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_chain) {
     constexpr int SW_THREADS = W * 32, SW_WARPS = W;
     extern __shared__ __align__(16) unsigned char smem_all[];
-    // blockIdx.x = kind; chain (independent CrossCat states swept with the same action list) =
-    // blockIdx.y, or blockIdx.y * SW_CPB + warp-in-block when W == 1
+    // blockIdx.y = kind slot (kind_ids are sorted most expensive first and y is the slow grid
+    // index, so the long CTAs are dispatched first and the cheap ones fill the tail);
+    // chain (independent CrossCat states swept with the same action list) = blockIdx.x, or
+    // blockIdx.x * SW_CPB + warp-in-block when W == 1
     const int sub = W == 1 ? (int)(threadIdx.x >> 5) : 0;
-    const int chain = W == 1 ? (int)blockIdx.y * SW_CPB + sub : (int)blockIdx.y;
+    const int chain = W == 1 ? (int)blockIdx.x * SW_CPB + sub : (int)blockIdx.x;
     if (chain >= n_chains) return;
     unsigned char *const smem_raw = smem_all + (size_t)sub * smem_per_chain;
     const SweepChain &ch = many ? many[chain] : one;
-    if ((int)blockIdx.x >= ch.n_ids) return;
+    if ((int)blockIdx.y >= ch.n_ids) return;
     KindDev *const kinds = ch.kinds;
     const FeatDev *const feats = ch.feats;
     const int32_t *const kind_feats = ch.kind_feats;
@@ -222,7 +224,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
     uint32_t *const dbg_picks = ch.dbg_picks;
     float *const dbg_scores = ch.dbg_scores;
     unsigned long long *const prof = ch.prof;
-    const int kid = ch.kind_ids[blockIdx.x];
+    const int kid = ch.kind_ids[blockIdx.y];
     KindDev &kd = kinds[kid];
     const int tid = W == 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // LB_PROFILE=1: cycles per phase seen by lane 0 of every warp
@@ -593,7 +595,13 @@ int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *
         LB_CUDA(cudaMalloc((void **)&e->d_kind_ids, 4 * (kind_ids.size() + 16)));
         e->d_kind_ids_cap = (int)kind_ids.size() + 16;
     }
-    LB_CUDA(cudaMemcpyAsync(e->d_kind_ids, kind_ids.data(), 4 * kind_ids.size(), cudaMemcpyHostToDevice, e->stream));
+    // most expensive kinds first (features x groups): see the grid layout in k_cat_sweep
+    std::vector<int> order(kind_ids);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const KindHost &ka = e->kinds[a], &kb = e->kinds[b];
+        return ka.fids.size() * (size_t)(ka.G + 8) > kb.fids.size() * (size_t)(kb.G + 8);
+    });
+    LB_CUDA(cudaMemcpyAsync(e->d_kind_ids, order.data(), 4 * order.size(), cudaMemcpyHostToDevice, e->stream));
     SweepChain c;
     c.kinds = e->d_kinds; c.kind_ids = e->d_kind_ids; c.n_ids = (int)kind_ids.size();
     c.feats = e->d_feats; c.kind_feats = e->d_kind_feats; c.aux = e->d_aux;
@@ -616,6 +624,7 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         for (int kid : kind_ids[c]) max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
     }
     if (!n_ctas) return 0;
+    if (max_ids > 65535) return lb_fail("cat_sweep: %d kinds in one launch (limit 65535)", max_ids);
     int W = sweep_warps(leader, n_ctas, max_nf);
     for (;;) {
         smem = 0;
@@ -641,7 +650,7 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         LB_TRY(lb_upload_desc(leader, chains, sizeof(SweepChain) * (size_t)n, &d));
         d_many = (const SweepChain *)d;
     }
-    const dim3 grid((unsigned)max_ids, (unsigned)(W == 1 ? (n + SW_CPB - 1) / SW_CPB : n));
+    const dim3 grid((unsigned)(W == 1 ? (n + SW_CPB - 1) / SW_CPB : n), (unsigned)max_ids);
     LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
     switch (W) {
     case 1: k_cat_sweep<1><<<grid, 32 * SW_CPB, smem * SW_CPB, leader->stream>>>(chains[0], d_many, n, (int)smem); break;
