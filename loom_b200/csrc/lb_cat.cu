@@ -229,8 +229,13 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
     const int tid = W == 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // LB_PROFILE=1: cycles per phase seen by lane 0 of every warp
     // ADD: 0 score | 1 wait at (A) | 2 sample / commit | 3 wait at (B) | 4 update;  REMOVE: 5 lookup | 6 wait at (A) | 7 update
+    // (profiling build only, make EXTRA=-DLB_SWEEP_PROFILE: the counters cost 18 registers)
+#ifdef LB_SWEEP_PROFILE
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define LB_TICK(k) do { if (prof && lane == 0) { const long long now__ = clock64(); pt[k] += now__ - pc; pc = now__; } } while (0)
+#else
+#define LB_TICK(k) do { } while (0)
+#endif
     const int nf = kd.nf, st = kd.Gcap;
     const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
     const int zero_row = n_cache_rows;
@@ -276,22 +281,50 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
     if (tid == 0) {
         ss->G = kd.G; ss->stop = 0; ss->epoch = 0;
         ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
-        // Features -> warps by cost, longest first (GP 4, NICH 3, categorical 1); warp 0 also
-        // samples, so it starts with a handicap.  A warp owns its features for BOTH scoring and
-        // update; its list is sorted by class so the scoring loops stay class-pure.
-        float load[SW_WARPS];
-        for (int w = 0; w < SW_WARPS; ++w) load[w] = 0.f;
-        if (SW_WARPS > 1) load[0] = 6.f;
-        const int order[N_CLASS] = {CL_GP, CL_NICH, CL_CAT};
+        // Features -> warps by cost (GP 4, NICH 3, categorical 1).  A warp owns its features for
+        // BOTH scoring and update; its list is sorted by class so the scoring loops stay class-pure.
+        // With few warps: longest-processing-time first, warp 0 (the sampler) handicapped.
         const float weight[N_CLASS] = {1.f, 4.f, 3.f};
-        for (int oc = 0; oc < N_CLASS; ++oc)
-            for (int j = 0; j < nf; ++j) {
-                if (feat_class(s_feat[j].type) != order[oc]) continue;
-                int best = 0;
-                for (int w = 1; w < SW_WARPS; ++w) if (load[w] < load[best]) best = w;
-                s_owner[j] = (uint8_t)best;
-                load[best] += weight[order[oc]];
+        int cnt[N_CLASS] = {0, 0, 0}, n_cls = 0;
+        for (int j = 0; j < nf; ++j) cnt[feat_class(s_feat[j].type)]++;
+        for (int c = 0; c < N_CLASS; ++c) n_cls += cnt[c] > 0;
+        if (SW_WARPS >= 2 * n_cls) {
+            // enough warps for class-pure ownership: a warp then runs ONE scoring loop, i.e. one
+            // round trip of dependent loads per action instead of one per class.  Warps per class
+            // follow weight x count; the sampler (warp 0) takes the cheapest class.
+            int nw[N_CLASS] = {0, 0, 0}, left = SW_WARPS;
+            for (int c = 0; c < N_CLASS; ++c) if (cnt[c]) { nw[c] = 1; --left; }
+            while (left > 0) {
+                int best = -1; float worst = 0.f;
+                for (int c = 0; c < N_CLASS; ++c) {
+                    if (!cnt[c] || nw[c] >= cnt[c]) continue;
+                    const float l = weight[c] * (float)cnt[c] / (float)nw[c];
+                    if (l > worst) { worst = l; best = c; }
+                }
+                if (best < 0) break;
+                nw[best]++; --left;
             }
+            int w0 = 0, seen[N_CLASS] = {0, 0, 0};
+            int first_warp[N_CLASS];
+            for (int c = 0; c < N_CLASS; ++c) { first_warp[c] = w0; w0 += nw[c]; }
+            for (int j = 0; j < nf; ++j) {
+                const int c = feat_class(s_feat[j].type);
+                s_owner[j] = (uint8_t)(first_warp[c] + seen[c]++ % nw[c]);
+            }
+        } else {
+            float load[SW_WARPS];
+            for (int w = 0; w < SW_WARPS; ++w) load[w] = 0.f;
+            if (SW_WARPS > 1) load[0] = 6.f;
+            const int order[N_CLASS] = {CL_GP, CL_NICH, CL_CAT};
+            for (int oc = 0; oc < N_CLASS; ++oc)
+                for (int j = 0; j < nf; ++j) {
+                    if (feat_class(s_feat[j].type) != order[oc]) continue;
+                    int best = 0;
+                    for (int w = 1; w < SW_WARPS; ++w) if (load[w] < load[best]) best = w;
+                    s_owner[j] = (uint8_t)best;
+                    load[best] += weight[order[oc]];
+                }
+        }
         int k = 0;
         for (int w = 0; w < SW_WARPS; ++w) {
             for (int c = 0; c < N_CLASS; ++c) {
@@ -445,7 +478,9 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
         const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
         if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
         const int G = ss->G;
+#ifdef LB_SWEEP_PROFILE
         if (prof && lane == 0) pc = clock64();
+#endif
         prefetch(i + 2);   // latency overlaps this action's work
 
         if (!is_remove) {
@@ -551,8 +586,12 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
         kd.status = status;
         kd.progress = i;
     }
+#ifdef LB_SWEEP_PROFILE
     if (prof && lane == 0 && kid < 16)
         for (int k = 0; k < 8; ++k) prof[(kid * SW_WARPS + warp) * 8 + k] += (unsigned long long)pt[k];
+#else
+    (void)prof;
+#endif
 #undef LB_TICK
 }
 
