@@ -184,6 +184,9 @@ __device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own
 #ifndef LB_LOCKSTEP
 #define LB_LOCKSTEP 1
 #endif
+#ifndef LB_LOCKSTEP_EVERY
+#define LB_LOCKSTEP_EVERY 1   // actions between two re-alignments (power of two)
+#endif
 // W == 1: the warp is the whole "CTA" of its chain, so a warp-level sync is all correctness needs.
 // LB_LOCKSTEP >= 2 makes these points block-wide too: pure re-alignment of the block's chains.
 // (A chain that stops early simply exits; barriers only wait for warps that have not exited.)
@@ -472,7 +475,8 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
         const uint32_t act = actions[i];
         const uint64_t r = act >> 1;
         prev_r2 = prev_r1; prev_r1 = cur_r; cur_r = r;
-        if (W == 1 && LB_LOCKSTEP >= 1) __syncthreads();   // re-align the block's chains (instruction-cache locality)
+        if (W == 1 && LB_LOCKSTEP >= 1 && (i & (LB_LOCKSTEP_EVERY - 1)) == 0)
+            __syncthreads();   // re-align the block's chains (instruction-cache locality)
         const bool is_remove = act & 1u;
         const int slot = (int)(i & 3);
         const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
