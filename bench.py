@@ -29,7 +29,7 @@ samples : the exact Gibbs chain of one kind is sequential, so one chain keeps on
           over ONE rows file; the GPU sweeps many chains in ONE launch per action list
           (lb_cat_sweep_multi, rows shared with lb_share_rows): one CTA per (chain, kind),
           one warp wide when there are enough chains to fill every SM 16 times over
-          (default 672 chains = two waves), 8 warps wide for a single chain.
+          (default 1008 chains = three waves), 8 warps wide for a single chain.
           `value` is the aggregate over those chains ("config.samples"); the
           single-chain rate is in "rates".  The reference arm gets the same treatment:
           as many chains in parallel as the host cores allow.
@@ -282,8 +282,9 @@ def main():
     first, drain = step_actions(R)
 
     from loom_b200.engine import cat_sweep_multi
-    # Two waves of 16 one-warp CTAs per SM: 2 * 16 * 148 / K chains, in whole blocks of 8 chains.
-    n_chains = args.samples or max(1, (2 * 16 * 148 // model.n_kinds) // 8 * 8)
+    # Three waves of 16 one-warp CTAs per SM: 3 * 16 * 148 / K chains, in whole blocks of 8 chains
+    # (the expensive kinds are dispatched first and the cheap ones fill the tail).
+    n_chains = args.samples or max(1, (3 * 16 * 148 // model.n_kinds) // 8 * 8)
     config["samples"] = n_chains
     config["parallelism"] = ("%d independent chains x %d kinds per GPU in ONE launch per sweep "
                              "(lb_cat_sweep_multi): one CTA per (chain, kind), 1-8 warps wide by how many "
@@ -402,7 +403,7 @@ def main():
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
     traffic = None
     tpath = os.path.join(REPO, "profiles", "r1_k_cat_sweep_multi_traffic.json")
-    if os.path.exists(tpath) and args.workload == "C2" and not args.rows and n_chains == 672:
+    if os.path.exists(tpath) and args.workload == "C2" and not args.rows:
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full, dominant launch type
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

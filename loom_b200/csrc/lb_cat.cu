@@ -491,6 +491,25 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
             // ---- ADD: model.add_value -> score_value -> sample -> add_value ----
             if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
             if (tid == 0) { bool fresh; if (row_assignment(i, r, fresh) != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW; }
+            if (SW_WARPS <= 2 && off[N_CLASS] > off[CL_GP]) {
+                // With one or two warps per chain the class loops run back to back, each behind
+                // its own round trip to the tables: start the GP / NICH lines moving before the
+                // categorical loop (GP: cache rows 0-1 and the sum row; NICH: cache rows 0-4; two
+                // 128-byte lines per row cover 64 groups).
+                for (int k = off[CL_GP]; k < off[N_CLASS]; ++k) {
+                    const int j = s_own[k];
+                    if (!c_obs[j]) continue;
+                    const FeatDev &f = s_feat[j];
+                    const bool gp = f.type == LB_GP;
+                    if (lane < (gp ? 6 : 10)) {
+                        const int row = lane >> 1, half = lane & 1;
+                        const void *p = (gp && row == 2)
+                            ? (const void *)(ints + (size_t)(f.int_row + 1) * st + 32 * half)
+                            : (const void *)(cache + (size_t)(f.cache_row + row) * st + 32 * half);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+                    }
+                }
+            }
             // 64 groups per trip (two per lane).  ONE tile shape on purpose: every extra
             // instantiation of the scoring loops adds ~10 KB of hot code, and the loop body must
             // stay inside the 32 KB instruction cache when 16 narrow CTAs share an SM.  Columns

@@ -176,25 +176,32 @@ __device__ __forceinline__ double lb_log_factorial_d(uint32_t x) {
 // ---- per-feature cached scorer refresh (one group) -------------------------
 // `ints`, `flts`, `cache` point at the feature's first row, column g already
 // applied; `st` is the column stride (Gcap).
-__device__ __forceinline__ void lb_refresh_bb(const FeatDev &f, const uint32_t *in, float *c, int st) {
-    const float h = (float)in[0], t = (float)in[st];
+// The *_v forms take the statistics by value: the update path already holds them in registers,
+// and re-reading what it just stored costs a second L2 round trip on the critical path.
+__device__ __forceinline__ void lb_refresh_bb_v(const FeatDev &f, uint32_t heads, uint32_t tails, float *c, int st) {
+    const float h = (float)heads, t = (float)tails;
     const float inv = 1.f / (f.hp[0] + f.hp[1] + h + t);
     c[0] = logf((f.hp[0] + h) * inv);
     c[st] = logf((f.hp[1] + t) * inv);
 }
-__device__ __forceinline__ void lb_refresh_gp(const FeatDev &f, const uint32_t *in, float *c, int st) {
-    const float a = f.hp[0] + (float)in[st], b = f.hp[1] + (float)in[0];
+__device__ __forceinline__ void lb_refresh_bb(const FeatDev &f, const uint32_t *in, float *c, int st) {
+    lb_refresh_bb_v(f, in[0], in[st], c, st);
+}
+__device__ __forceinline__ void lb_refresh_gp_v(const FeatDev &f, uint32_t count, uint32_t sum, float *c, int st) {
+    const float a = f.hp[0] + (float)sum, b = f.hp[1] + (float)count;
     c[0] = a * log1pf(-1.f / (b + 1.f));
     c[st] = -log1pf(b);
 }
-__device__ __forceinline__ void lb_refresh_nich(const FeatDev &f, const uint32_t *in,
-                                                const double *fl, float *c, int st) {
+__device__ __forceinline__ void lb_refresh_gp(const FeatDev &f, const uint32_t *in, float *c, int st) {
+    lb_refresh_gp_v(f, in[0], in[st], c, st);
+}
+__device__ __forceinline__ void lb_refresh_nich_v(const FeatDev &f, uint32_t count, double mean, double ctv_d,
+                                                  float *c, int st) {
     // posterior NIX parameters.  mu' is formed in double and
     // cached as a hi/lo float pair so x - mu' keeps full precision when
     // |mean| >> sigma; everything else is fp32-safe.
-    const double mean = fl[0];
     const float mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
-    const float n = (float)in[0], ctv = (float)fl[st];
+    const float n = (float)count, ctv = (float)ctv_d;
     const float kn = kappa + n, inv_kn = 1.f / kn, nun = nu + n;
     const double mun = ((double)kappa * (double)mu + (double)n * mean) * (double)inv_kn;
     const float dm = (float)((double)mu - mean);
@@ -207,6 +214,10 @@ __device__ __forceinline__ void lb_refresh_nich(const FeatDev &f, const uint32_t
     c[2 * (size_t)st] = prec;
     c[3 * (size_t)st] = mu_hi;
     c[4 * (size_t)st] = (float)(mun - (double)mu_hi);
+}
+__device__ __forceinline__ void lb_refresh_nich(const FeatDev &f, const uint32_t *in,
+                                                const double *fl, float *c, int st) {
+    lb_refresh_nich_v(f, in[0], fl[0], fl[st], c, st);
 }
 
 // Recompute one cached-scorer row (`local` = row index inside the feature) of
@@ -240,10 +251,12 @@ __device__ __forceinline__ void lb_refresh_row(const FeatDev &f, const float *au
 __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *aux, uint32_t *in,
                                                double *fl, float *c, int st, uint32_t raw, int sign) {
     switch (f.type) {
-    case LB_BB:
-        in[raw ? 0 : st] += (uint32_t)sign;
-        lb_refresh_bb(f, in, c, st);
+    case LB_BB: {
+        uint32_t h = in[0], t = in[st];        // both loads in flight together
+        if (raw) { h += (uint32_t)sign; in[0] = h; } else { t += (uint32_t)sign; in[st] = t; }
+        lb_refresh_bb_v(f, h, t, c, st);
         break;
+    }
     case LB_DD:
     case LB_DPD: {
         const uint32_t n = in[(size_t)raw * st] + (uint32_t)sign;
@@ -255,11 +268,13 @@ __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *au
         break;
     }
     case LB_GP: {
-        const uint32_t n = in[0] + (uint32_t)sign;
+        const uint32_t n0 = in[0], s0 = in[st];
+        const double lp0 = fl[0];
+        const uint32_t n = n0 + (uint32_t)sign, sum = s0 + (uint32_t)(sign * (int64_t)raw);
         in[0] = n;
-        in[st] += (uint32_t)(sign * (int64_t)raw);
-        fl[0] = n ? fl[0] + sign * (double)lb_log_factorial_d(raw) : 0.0;
-        lb_refresh_gp(f, in, c, st);
+        in[st] = sum;
+        fl[0] = n ? lp0 + sign * (double)lb_log_factorial_d(raw) : 0.0;
+        lb_refresh_gp_v(f, n, sum, c, st);
         break;
     }
     case LB_NICH: {
@@ -277,7 +292,7 @@ __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *au
             else { mean = (total - x) / n; ctv -= delta * (x - mean); }
         }
         in[0] = (uint32_t)n; fl[0] = mean; fl[st] = ctv;
-        lb_refresh_nich(f, in, fl, c, st);
+        lb_refresh_nich_v(f, (uint32_t)n, mean, ctv, c, st);
         break;
     }
     }
