@@ -404,7 +404,8 @@ def main():
     traffic = None
     tpath = os.path.join(REPO, "profiles", "r1_k_cat_sweep_multi_traffic.json")
     if os.path.exists(tpath) and args.workload == "C2" and not args.rows:
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")   # ncu --set full, dominant launch type
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_per_chain")   # ncu dram__bytes_{read,write}.sum
+        traffic = traffic * n_chains if traffic else None
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
