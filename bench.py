@@ -411,8 +411,8 @@ def main():
                 "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
                 "kernel_share_of_step": sweep_ms / total_ms if total_ms else None,
                 "chains_per_launch": n_chains,
-                "note": "exact sequential Gibbs: a dependent chain per (chain, kind) CTA, latency- and "
-                        "instruction-fetch-bound, not bandwidth-bound; one launch sweeps all %d chains" % n_chains}
+                "note": "exact sequential Gibbs: a dependent chain per (chain, kind) CTA, bound by the latency of its "
+                        "table round trips, not by bandwidth; one launch sweeps all %d chains" % n_chains}
 
     # ---- auxiliary: the HBM-bound batch kernels on the same workload ----
     aux = {}
