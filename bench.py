@@ -440,6 +440,8 @@ def main():
                                 "cells_per_s": float(obs.sum()) / (ms * 1e-3), "achieved": gbs,
                                 "peak": peak, "unit": "GB/s", "frac": gbs / peak, "bound": "hbm"}
         # K2 bulk accumulate of all kinds with the current assignments (remove then add back)
+        e.accumulate_rows(sign=-1)            # warm-up (first-use allocations)
+        e.accumulate_rows(sign=+1)
         e.sync()
         e.timer_start()
         e.accumulate_rows(sign=-1)
@@ -466,6 +468,20 @@ def main():
                               "proposer_cells_per_s": n_obs * Kk / (msk * 1e-3),
                               "note": "K4 accumulate of every row into every kind + K5 scoring, per proposal round"}
         e.init_featureless_kinds(0, seed=12)
+        # hyper kernel (HyperKernel::run, src/hyper_kernel.cc:195-235) with loom's default grids
+        # (loom/hyperprior.py:33-71): one grid-Gibbs pass over every feature's hyper-parameters and
+        # every kind's Pitman-Yor parameters
+        from loom_b200 import hyperprior
+        e.set_hyper_prior(hyperprior.defaults())
+        e.hyper_run(seed=13)
+        e.sync()
+        e.timer_start()
+        e.hyper_run(seed=14)
+        msh = e.timer_stop()
+        aux["hyper_kernel"] = {"ms": msh, "features": model.n_features,
+                               "features_per_s": model.n_features / (msh * 1e-3),
+                               "note": "default grids: BB 12x12, DD 12 per coordinate (256 coordinates), GP 100x100, "
+                                       "NICH 201/30/100/30, Pitman-Yor 137 points"}
         e.cat_sweep(drain, seed=9)
     except Exception as exc:  # the auxiliary numbers never mask the headline
         aux["error"] = str(exc)

@@ -1,7 +1,7 @@
 """Generate the committed fixtures under tests/golden/.
 
 The reference ships no numeric golden vectors for this path and cannot be built or
-imported in this image, so nothing here comes from running loom.  What is committed instead:
+imported in this image, so nothing here comes from running loom's engine.  What is committed instead:
 
   closed_forms.json   known answers for every conjugate closed form on the hot path, computed by
                       scipy (an independent implementation): betabinom / nbinom / Student-t
@@ -10,6 +10,8 @@ imported in this image, so nothing here comes from running loom.  What is commit
   structural.json     the reference's own structural fixtures, transcribed with their source lines:
                       LATENT_SIZES / BELL_NUMBERS (loom/test/test_posterior_enum.py:65-79,778-781)
                       and the worked tare example (doc/adapting.md:323-414).
+  reference_grids.json  outputs of the reference's own loom/gridding.py (the one piece of the
+                      reference that runs here): pins loom_b200/hyperprior.py.
   engine_small.npz    a small mixed model + rows with the oracle's results on it (statistics for a
                       fixed assignment, row x group scores, data score, feature x kind marginals,
                       a seeded Gibbs sweep): regression vectors for the oracle (all of it) and for
@@ -184,6 +186,25 @@ def engine_small():
     return out
 
 
+def reference_grids():
+    """Outputs of the reference's own loom/gridding.py (pure numpy, importable by file path even
+    though the loom package is not): pins loom_b200/hyperprior.py.  Only runs where
+    /root/reference exists; the JSON it writes is what travels."""
+    import importlib.util
+    path = "/root/reference/loom/gridding.py"
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("ref_gridding", path)
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    return {"source": "loom/gridding.py executed from /root/reference",
+            "uniform_0_1_7": g.uniform(0, 1, 7).tolist(),
+            "center_heavy_0_1_20": g.center_heavy(0, 1, 20).tolist(),
+            "left_heavy_m1_2_30": g.left_heavy(-1, 2, 30).tolist(),
+            "right_heavy_m1_1_20": g.right_heavy(-1, 1, 20).tolist(),
+            "pitman_yor": g.pitman_yor()}
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(20261019)
     with open(os.path.join(HERE, "closed_forms.json"), "w") as f:
@@ -191,4 +212,8 @@ if __name__ == "__main__":
     with open(os.path.join(HERE, "structural.json"), "w") as f:
         json.dump(structural(), f, indent=1)
     np.savez_compressed(os.path.join(HERE, "engine_small.npz"), **engine_small())
+    grids = reference_grids()
+    if grids is not None:
+        with open(os.path.join(HERE, "reference_grids.json"), "w") as f:
+            json.dump(grids, f, indent=0)
     print("wrote", sorted(os.listdir(HERE)))

@@ -149,3 +149,22 @@ def test_cuda_reproduces_recorded_results(cuda_abi, small):
         assert np.array_equal(c[:n], want_c[used[k]]) and want_c.sum() == c.sum()
         assert np.array_equal(i[:, :n], want_i[:, used[k]]) and not i[:, n:].any()
     assert rel_err(e.score_data(), float(z["sweep_score_data"])) <= SCORE_TOL
+
+
+def test_hyperprior_grids_match_the_reference_gridding():
+    """loom_b200/hyperprior.py against the outputs of the reference's own loom/gridding.py
+    (tests/golden/reference_grids.json) and the grid sizes of loom/hyperprior.py:33-71."""
+    from loom_b200 import hyperprior as hp
+    with open(os.path.join(GOLDEN, "reference_grids.json")) as f:
+        ref = json.load(f)
+    assert np.allclose(hp.uniform(0, 1, 7), ref["uniform_0_1_7"], rtol=1e-12)
+    assert np.allclose(hp.center_heavy(0, 1, 20), ref["center_heavy_0_1_20"], rtol=1e-12)
+    assert np.allclose(hp.left_heavy(-1, 2, 30), ref["left_heavy_m1_2_30"], rtol=1e-12)
+    assert np.allclose(hp.right_heavy(-1, 1, 20), ref["right_heavy_m1_1_20"], rtol=1e-12)
+    mine = hp.pitman_yor()
+    assert len(mine) == len(ref["pitman_yor"])
+    for a, b in zip(mine, ref["pitman_yor"]):
+        assert a["alpha"] == pytest.approx(b["alpha"], rel=1e-12) and a["d"] == pytest.approx(b["d"], rel=1e-12, abs=1e-15)
+    d = hp.defaults()
+    assert len(d["dd"]["alpha"]) == 12 and len(d["gp"]["alpha"]) == 100 and len(d["nich"]["mu"]) == 201
+    assert len(d["nich"]["kappa"]) == 30 and len(d["dpd"]["gamma"]) == 30 and len(d["dpd"]["alpha"]) == 20
