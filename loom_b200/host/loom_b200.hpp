@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <vector>
 
 #include "../../include/loom_b200.h"
@@ -190,6 +191,106 @@ public:
 private:
     CrossCat &cross_cat_;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Schedules (src/schedules.hpp:41-321) and the multi-pass driver (src/loom.cc:167-450).  The
+// schedules depend only on counts, so a whole batch of ADD / REMOVE decisions is made up front and
+// handed to the device as one action list; the batch kernels run at the boundary in loom's order.
+struct ScheduleConfig {           // protobuf::Config::Schedule, defaults of loom/config.py:37-43
+    double extra_passes = 500.0, small_data_size = 4e3, big_data_size = 1e9;
+    uint64_t max_reject_iters = 100;
+};
+
+class AnnealingSchedule {         // REMOVE : ADD = N : (1 + N)
+public:
+    explicit AnnealingSchedule(double extra_passes) { set_extra_passes(extra_passes); state_ = 2 * add_rate_; }
+    void set_extra_passes(double n) { add_rate_ = 1.0 + n; remove_rate_ = n; }
+    bool next_action_is_add() {
+        if (state_ >= 0) { state_ -= remove_rate_; return true; }
+        state_ += add_rate_;
+        return false;
+    }
+
+private:
+    double add_rate_ = 1, remove_rate_ = 0, state_ = 0;
+};
+
+class AcceleratingSchedule {      // piecewise linear in log(rows)-log(passes)
+public:
+    explicit AcceleratingSchedule(const ScheduleConfig &c) : c_(c) {}
+    double extra_passes(uint64_t row_count) const {
+        const double n = (double)row_count;
+        if (n <= c_.small_data_size) return c_.extra_passes;
+        if (n > c_.big_data_size) return 0.0;
+        const double power = std::log(c_.big_data_size / n) / std::log(c_.big_data_size / c_.small_data_size);
+        const double passes = std::pow(1.0 + c_.extra_passes, power);
+        return passes > 2.0 ? passes - 1.0 : 0.0;
+    }
+
+private:
+    ScheduleConfig c_;
+};
+
+class BatchingSchedule {          // a batch ends when every previously assigned row was replaced
+public:
+    void add() { ++fresh_; }
+    void remove() { --stale_; }
+    bool test() {
+        if (stale_ == 0 && fresh_) { stale_ = fresh_; fresh_ = 0; return true; }
+        return false;
+    }
+
+private:
+    uint64_t stale_ = 0, fresh_ = 0;
+};
+
+class KernelDisablingSchedule {
+public:
+    explicit KernelDisablingSchedule(uint64_t max_reject_iters) : max_(max_reject_iters) {}
+    void run(bool accepted) { rejects_ = accepted ? 0 : rejects_ + 1; }
+    bool test() const { return rejects_ <= max_; }
+
+private:
+    uint64_t max_, rejects_ = 0;
+};
+
+// Loom::infer_multi_pass for one chain.  `kind` / `hyper` may be null (kernel off).  Rows are the
+// positions of the loaded block; the assigned rows form a window of the cyclic stream
+// (src/stream_interval.hpp:36-140).  Returns the number of batches.
+inline uint64_t infer_multi_pass(CrossCat &cross_cat, CatKernel &cat, KindKernel *kind, HyperKernel *hyper,
+                                 const ScheduleConfig &config, uint64_t seed) {
+    const uint64_t n_rows = cross_cat.row_count();
+    AcceleratingSchedule accelerating(config);
+    AnnealingSchedule annealing(accelerating.extra_passes(0));
+    BatchingSchedule batching;
+    KernelDisablingSchedule disabling(config.max_reject_iters);
+    uint64_t assigned = 0, front = 0, back = 0, batches = 0;
+    while (assigned != n_rows) {
+        if (annealing.next_action_is_add()) {
+            cat.add_row(front);
+            front = (front + 1) % n_rows;
+            ++assigned;
+            batching.add();
+        } else {
+            cat.remove_row(back);
+            back = (back + 1) % n_rows;
+            --assigned;
+            batching.remove();
+        }
+        if (batching.test()) {
+            cat.wait();
+            ++batches;
+            annealing.set_extra_passes(accelerating.extra_passes(assigned));
+            if (kind) {
+                disabling.run(kind->try_run());
+                if (!disabling.test()) kind = nullptr;   // infer_kind_structure returns false (loom.cc:203-209)
+            }
+            if (hyper) hyper->run(seed * 7919 + batches);
+        }
+    }
+    cat.wait();
+    return batches;
+}
 
 }  // namespace b200
 }  // namespace loom

@@ -29,5 +29,12 @@ int main(int argc, char **argv) {
     for (uint64_t r = 0; r < 64; ++r) multi.add_row(r);
     multi.wait();
     std::printf("scores %f %f\n", cross_cat.score_data(), second.score_data());
+    // a whole annealed run on the first chain (schedules of src/schedules.hpp)
+    for (uint64_t r = 0; r < 64; ++r) cat.remove_row(r);
+    cat.wait();
+    ScheduleConfig sched;
+    sched.extra_passes = 3.0; sched.small_data_size = 16; sched.big_data_size = 1e4;
+    const uint64_t batches = infer_multi_pass(cross_cat, cat, nullptr, nullptr, sched, 5);
+    std::printf("batches %llu score %f\n", (unsigned long long)batches, cross_cat.score_data());
     return 0;
 }

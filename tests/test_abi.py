@@ -55,3 +55,19 @@ def test_cpp_host_shell_compiles_and_links(tmp_path):
                            "-o", str(exe), "-L" + csrc, "-lloomb200", "-Wl,-rpath," + csrc,
                            "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
     subprocess.check_call([str(exe)])   # without "run": link check only
+
+
+@pytest.mark.gpu
+def test_cpp_host_shell_runs_on_the_gpu(tmp_path):
+    """CrossCat / CatKernel / MultiCatKernel / the schedule driver of the C++ shell, executed."""
+    import subprocess
+    exe = tmp_path / "host_shell_example"
+    csrc = os.path.join(REPO, "loom_b200", "csrc")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", os.path.join(REPO, "tests", "host_shell_example.cc"),
+                           "-o", str(exe), "-L" + csrc, "-lloomb200", "-Wl,-rpath," + csrc,
+                           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.check_output([str(exe), "run"], timeout=120).decode()
+    lines = out.strip().splitlines()
+    assert lines[0].startswith("score ") and lines[1].startswith("scores ") and lines[2].startswith("batches ")
+    assert int(lines[2].split()[1]) >= 3
+    assert all(np.isfinite(float(x)) for x in lines[1].split()[1:])
