@@ -4,6 +4,7 @@ oracle exports the same ABI under the lo_ prefix."""
 import os
 import re
 
+import numpy as np
 import pytest
 
 from loom_b200 import _abi
