@@ -205,6 +205,14 @@ int LB_NAME(set_groups)(lb_handle h, int32_t kind, int32_t n_nonempty_groups,
 int LB_NAME(score_rows)(lb_handle h, int32_t kind, uint64_t row_begin, uint64_t row_end,
                         float *out);
 
+/* QueryServer::call(Score) for one latent sample (src/query_server.cc:189-231):
+ * out[r - row_begin] = sum over kinds of log_sum_exp_g score_value(row r)[g], the
+ * log predictive probability of the observed cells of row r under this CrossCat
+ * state (kinds in which the row observes nothing contribute 0).  The caller
+ * averages over samples: log_sum_exp_l(out_l) - log(#samples).  out: HOST float
+ * [row_end - row_begin]. */
+int LB_NAME(query_score)(lb_handle h, uint64_t row_begin, uint64_t row_end, float *out);
+
 /* ProductMixture_::add_value for rows [row_begin,row_end) with their CURRENT
  * assignments, all kinds (kind < 0) or one kind: rebuilds/extends sufficient
  * statistics in bulk (src/product_mixture.cc:165-184; bulk form of

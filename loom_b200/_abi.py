@@ -52,6 +52,7 @@ SIGNATURES = {
                             _u32p, _f32p, _f32p, C.c_int32]),
     "set_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
     "set_rows_diff": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u8p, _u64p, _u32p, _u32p, _u64p, _u32p]),
+    "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
     "share_rows": (C.c_int, [_h, _h]),
     "cat_sweep_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
     "cat_sweep": (C.c_int, [_h, _u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u32p, _f32p,

@@ -920,6 +920,30 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
     }
 }
 
+// acc[r] (+)= log_sum_exp over the G scores of row r; one warp per row
+__global__ void k_row_lse_add(const float *scores, uint64_t n_rows, int G, float *acc, int first) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n_rows; r += n_warps) {
+        const float *s = scores + r * (uint64_t)G;
+        float m = -INFINITY;
+        for (int g = lane; g < G; g += 32) m = fmaxf(m, s[g]);
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        float t = 0.f;
+        for (int g = lane; g < G; g += 32) t += expf(s[g] - m);
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+        if (lane == 0) acc[r] = (first ? 0.f : acc[r]) + m + logf(t);
+    }
+}
+int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int G, float *d_acc, int first) {
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_rows * 32 + 255) / 256, (uint64_t)e->n_sm * 8));
+    k_row_lse_add<<<grid, 256, 0, e->stream>>>(d_scores, n_rows, G, d_acc, first);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    return 0;
+}
+
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
     const KindHost &k = e->kinds[kid];
     const int nf = (int)k.fids.size();

@@ -819,6 +819,32 @@ extern "C" int lb_score_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en,
     return 0;
 }
 
+// QueryServer::call(Score) for one sample: K1 per kind, then a per-row log-sum-exp, summed over kinds
+extern "C" int lb_query_score(lb_handle h, uint64_t b, uint64_t en, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (b > en || en > e->R) return lb_fail("bad row range");
+    if (b == en || !out) return 0;
+    LB_TRY(lb_sync_model(e));
+    int gmax = 1;
+    for (const KindHost &k : e->kinds) gmax = std::max(gmax, k.G);
+    const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>(en - b, (64ull << 20) / (4ull * gmax)));
+    const size_t score_bytes = ((size_t)chunk * gmax * 4 + 255) / 256 * 256;
+    LB_TRY(lb_ensure_scratch(e, score_bytes + 4 * (size_t)chunk + 256));
+    float *d_scores = (float *)e->d_scratch;
+    float *d_acc = (float *)((char *)e->d_scratch + score_bytes);
+    for (uint64_t c0 = b; c0 < en; c0 += chunk) {
+        const uint64_t c1 = std::min(en, c0 + chunk);
+        for (int kid = 0; kid < (int)e->kinds.size(); ++kid) {
+            LB_TRY(lb_launch_score_rows(e, kid, c0, c1, d_scores));
+            LB_TRY(lb_launch_row_lse_add(e, d_scores, c1 - c0, e->kinds[kid].G, d_acc, kid == 0));
+        }
+        LB_CUDA(cudaMemcpyAsync(out + (c0 - b), d_acc, 4 * (size_t)(c1 - c0), cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
 extern "C" int lb_accumulate_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, int32_t sign) {
     Engine *e = (Engine *)h;
     LB_CUDA(cudaSetDevice(e->device));

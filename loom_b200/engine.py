@@ -169,6 +169,14 @@ def cat_sweep_multi(engines, actions, seeds, action_offset=0):
                               seeds.ctypes.data_as(C.POINTER(C.c_uint64)), action_offset))
 
 
+def query_score(engines, row_begin=0, row_end=None):
+    """QueryServer::call(Score) over the latent samples `engines` (src/query_server.cc:189-231):
+    log_sum_exp over samples of the per-sample score, minus log(#samples)."""
+    per = np.stack([e.query_score(row_begin, row_end).astype(np.float64) for e in engines])
+    m = per.max(axis=0)
+    return m + np.log(np.exp(per - m).sum(axis=0)) - np.log(len(engines))
+
+
 class Engine:
     def __init__(self, abi, device=0):
         self.abi = abi
@@ -287,6 +295,13 @@ class Engine:
         G = self.kind_info(kind).n_groups
         out = np.empty((row_end - row_begin, G), np.float32) if fetch else None
         self.abi.check(self.abi.score_rows(self.h, kind, row_begin, row_end, ptr(out, _f32p)))
+        return out
+
+    def query_score(self, row_begin=0, row_end=None):
+        """log predictive probability of every loaded row under this sample (QueryServer Score)"""
+        row_end = self.n_rows if row_end is None else row_end
+        out = np.empty(row_end - row_begin, np.float32)
+        self.abi.check(self.abi.query_score(self.h, row_begin, row_end, ptr(out, _f32p)))
         return out
 
     def accumulate_rows(self, kind=-1, row_begin=0, row_end=None, sign=1):

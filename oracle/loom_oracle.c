@@ -674,6 +674,34 @@ int lo_score_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out
     return 0;
 }
 
+/* QueryServer::call(Score) for one sample (src/query_server.cc:189-231) */
+int lo_query_score(lb_handle h, uint64_t b, uint64_t en, float *out) {
+    engine_t *e = h;
+    if (b > en || en > e->R) return lo_fail("bad row range");
+    if (!out) return 0;
+#pragma omp parallel num_threads(n_threads())
+    {
+        int gmax = 1;
+        for (int k = 0; k < e->K; ++k) if (e->kinds[k].G > gmax) gmax = e->kinds[k].G;
+        double *scores = xcalloc(gmax, 8);
+#pragma omp for schedule(static)
+        for (int64_t r = (int64_t)b; r < (int64_t)en; ++r) {
+            double total = 0;
+            for (int k = 0; k < e->K; ++k) {
+                const kind_t *kd = &e->kinds[k];
+                kind_score_row(e, kd, (uint64_t)r, scores);
+                double m = -INFINITY, sum = 0;
+                for (int g = 0; g < kd->G; ++g) if (scores[g] > m) m = scores[g];
+                for (int g = 0; g < kd->G; ++g) sum += exp(scores[g] - m);
+                total += m + log(sum);
+            }
+            out[r - (int64_t)b] = (float)total;
+        }
+        free(scores);
+    }
+    return 0;
+}
+
 /* bulk add_value / remove_value with given assignments */
 int lo_accumulate_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, int32_t sign) {
     engine_t *e = h;

@@ -238,6 +238,23 @@ def test_score_rows_large_groups_float_accuracy(oracle_abi, cuda_abi):
     assert rel_err(sg, so).max() <= SCORE_TOL, rel_err(sg, so).max()
 
 
+def test_query_score_parity(oracle_abi, cuda_abi):
+    """QueryServer Score for one sample (lb_query_score): sum over kinds of log-sum-exp of
+    score_value, within the score tolerance of the float64 oracle."""
+    model, rows, truth = mixed(rows=3000, seed=21)
+    o, g = both(oracle_abi, cuda_abi, model, rows)
+    for k in range(model.n_kinds):
+        uniq, inv = np.unique(truth["assign"][k], return_inverse=True)
+        for e in (o, g):
+            e.set_groups(k, len(uniq))
+            e.set_assignments(k, inv.astype(np.uint32))
+    for e in (o, g):
+        e.accumulate_rows()
+    so, sg = o.query_score().astype(np.float64), g.query_score()
+    assert rel_err(sg, so).max() <= SCORE_TOL, rel_err(sg, so).max()
+    assert np.array_equal(g.query_score(100, 164), sg[100:164])     # sub-ranges address the same rows
+
+
 @pytest.mark.parametrize("n_rows,lo,hi", [(4000, 0, 2000), (4003, 3, 1999), (4002, 256, 4002)])
 def test_accumulate_parity(oracle_abi, cuda_abi, n_rows, lo, hi):
     # (4000, 0, 2000) takes the four-rows-per-load path, the others the unaligned one

@@ -79,6 +79,42 @@ def test_multi_chain_sweep_and_shared_rows(oracle_abi):
         other2.share_rows(chains[1])
 
 
+def test_query_score_is_a_normalised_predictive(oracle_abi):
+    """QueryServer Score (src/query_server.cc:189-231): per sample, sum over kinds of
+    log_sum_exp(score_value); over samples, log-mean-exp.  Summed over every possible row it is a
+    probability distribution."""
+    from loom_b200 import query_score, RowBlock
+    model, rows, truth = synth.generate(200, [("bb", 2), ("dd4", 1)], density=1.0, seed=6, f2k=[0, 1, 0])
+    chains = []
+    for seed in (1, 2):
+        e = Engine(oracle_abi)
+        e.set_model(model)
+        e.set_rows(rows)
+        e.cat_sweep(sweep_actions(200), seed=seed)
+        chains.append(e)
+    # per sample: equals the sum over kinds of log-sum-exp of score_rows
+    e = chains[0]
+    want = sum(np.log(np.exp(e.score_rows(k).astype(np.float64)).sum(axis=1)) for k in range(model.n_kinds))
+    assert np.allclose(e.query_score(), want, rtol=1e-5, atol=1e-5)
+    # all 2 x 2 x 4 complete rows + normalisation, with the trained groups kept and the query rows loaded
+    table = [[a, b, c] for a in (0, 1) for b in (0, 1) for c in range(4)]
+    q = RowBlock.from_table(model, table)
+    states = [[e.get_groups(k) for k in range(model.n_kinds)] for e in chains]
+    for e, st in zip(chains, states):
+        e.set_rows(q)
+        for k, (c, i, f) in enumerate(st):
+            e.set_groups(k, len(c), c, i, f)
+    total = np.exp(query_score(chains)).sum()
+    assert total == pytest.approx(1.0, rel=1e-5)
+    # partially observed rows marginalise: p(a) = sum_b,c p(a, b, c)
+    part = RowBlock.from_table(model, [[0, None, None], [1, None, None]])
+    for e, st in zip(chains, states):
+        e.set_rows(part)
+        for k, (c, i, f) in enumerate(st):
+            e.set_groups(k, len(c), c, i, f)
+    assert np.exp(query_score(chains)).sum() == pytest.approx(1.0, rel=1e-5)
+
+
 def test_duplicate_row_is_an_error(oracle_abi):
     model, rows, _ = small_mixed(50)
     e = Engine(oracle_abi)
