@@ -143,6 +143,41 @@ def test_sweep_grows_tables_and_renumbers_ids(oracle_abi, cuda_abi, monkeypatch)
     assert_same_state(o, g, model, flt_rtol=1e-6)
 
 
+@pytest.mark.parametrize("warps", [1, 8])
+def test_multi_chain_sweep_grows_tables(cuda_abi, monkeypatch, warps):
+    """Table growth and id renumbering inside the many-chain launch: chains stop at different
+    actions, the host grows their tables and relaunches only the unfinished (chain, kind) pairs;
+    every chain must end where its own single-chain sweep ends."""
+    monkeypatch.setenv("LB_INITIAL_GCAP", "64")
+    monkeypatch.setenv("LB_SWEEP_WARPS", str(warps))
+    model, rows, _ = mixed(rows=1200, seed=4, alpha=60.0)
+    R = rows.n_rows
+    acts = np.concatenate([sweep_actions(R)] + [sweep_actions(R, add=True, remove=True)] * 6)
+    seeds = [3, 4, 5, 6, 7]
+    singles = []
+    for seed in seeds:
+        g = Engine(cuda_abi)
+        g.set_model(model)
+        g.set_rows(rows)
+        g.cat_sweep(acts, seed=seed)
+        singles.append(g)
+    assert max(singles[0].kind_info(k).n_groups for k in range(model.n_kinds)) > 64   # growth happened
+    owner = Engine(cuda_abi)
+    owner.set_model(model)
+    owner.set_rows(rows)
+    chains = [owner]
+    for _ in seeds[1:]:
+        g = Engine(cuda_abi)
+        g.set_model(model)
+        g.share_rows(owner)
+        chains.append(g)
+    cat_sweep_multi(chains, acts, seeds)
+    for a, b in zip(singles, chains):
+        for k in range(model.n_kinds):
+            assert np.array_equal(a.get_assignments(k), b.get_assignments(k))
+            assert all(np.array_equal(x, y) for x, y in zip(a.get_groups(k), b.get_groups(k)))
+
+
 def test_remove_everything_returns_to_empty(cuda_abi):
     model, rows, _ = mixed(rows=400)
     g = Engine(cuda_abi)
