@@ -351,6 +351,11 @@ extern "C" int lb_set_model(lb_handle h, int32_t F, const lb_feature_spec *specs
         if (f2k[f] >= (uint32_t)K) return lb_fail("featureid_to_kindid out of range");
     }
     clear_model(e);
+    if (e->R && (F != e->F || F8 != e->F8)) {   // a different schema: the loaded row block no longer fits
+        drop_borrowed_rows(e);
+        dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
+        e->R = 0; e->W = 0;
+    }
     e->F = F; e->F8 = F8; e->FW = F - F8;
     e->specs.assign(specs, specs + F);
     e->aux.assign(aux, aux + n_aux);
