@@ -25,7 +25,7 @@ namespace b200 {
 #define LOOM_B200_CHECK(expr)                                                              \
     do {                                                                                   \
         if ((expr) != 0) {                                                                 \
-            std::fprintf(stderr, "ERROR %s\n\t%s : %d\n\t%s\n", lb_last_error(), __FILE__, \
+            std::fprintf(stderr, "ERROR %s\n\t%s : %d\n\t%s\n", LB_NAME(last_error)(), __FILE__, \
                          __LINE__, __func__);                                              \
             std::abort();                                                                  \
         }                                                                                  \
@@ -42,8 +42,8 @@ struct RowBlock {
 
 class CrossCat {
 public:
-    explicit CrossCat(int device = 0) { LOOM_B200_CHECK(lb_create(device, &handle_)); }
-    ~CrossCat() { lb_destroy(handle_); }
+    explicit CrossCat(int device = 0) { LOOM_B200_CHECK(LB_NAME(create)(device, &handle_)); }
+    ~CrossCat() { LB_NAME(destroy)(handle_); }
     CrossCat(const CrossCat &) = delete;
     CrossCat &operator=(const CrossCat &) = delete;
 
@@ -52,49 +52,59 @@ public:
                     const std::vector<uint32_t> &featureid_to_kindid, const std::vector<float> &kind_py,
                     const float topology_py[2], int empty_group_count = 1) {
         feature_count_ = (int)features.size();
-        LOOM_B200_CHECK(lb_set_model(handle_, (int32_t)features.size(), features.data(), aux.data(),
+        LOOM_B200_CHECK(LB_NAME(set_model)(handle_, (int32_t)features.size(), features.data(), aux.data(),
                                      (int32_t)aux.size(), (int32_t)(kind_py.size() / 2),
                                      featureid_to_kindid.data(), kind_py.data(), topology_py,
                                      empty_group_count));
     }
+    // the same from the arrays of a model file (lbio_model_view, include/loom_b200_io.h)
+    void model_load(int32_t n_features, const lb_feature_spec *features, const float *aux, int32_t n_aux,
+                    int32_t n_kinds, const uint32_t *featureid_to_kindid, const float *kind_py,
+                    const float *topology_py, int empty_group_count) {
+        feature_count_ = n_features;
+        LOOM_B200_CHECK(LB_NAME(set_model)(handle_, n_features, features, aux, n_aux, n_kinds, featureid_to_kindid,
+                                           kind_py, topology_py, empty_group_count));
+    }
+    // rows uploaded through the C ABI directly (lb_set_rows_diff)
+    void rows_attached(uint64_t row_count) { row_count_ = row_count; }
     void rows_load(const RowBlock &rows) {
         row_count_ = rows.row_count;
-        LOOM_B200_CHECK(lb_set_rows(handle_, rows.row_count, rows.cat8.data(), rows.wide.data(), rows.mask.data()));
+        LOOM_B200_CHECK(LB_NAME(set_rows)(handle_, rows.row_count, rows.cat8.data(), rows.wide.data(), rows.mask.data()));
     }
     // another sample over the same rows file (loom/tasks.py:173-194): read `owner`'s block
     void rows_share(const CrossCat &owner) {
         row_count_ = owner.row_count_;
-        LOOM_B200_CHECK(lb_share_rows(handle_, owner.handle_));
+        LOOM_B200_CHECK(LB_NAME(share_rows)(handle_, owner.handle_));
     }
     // CrossCat::score_data (src/cross_cat.cc:238-250)
     float score_data() const {
         double s = 0;
-        LOOM_B200_CHECK(lb_score_data(handle_, &s));
+        LOOM_B200_CHECK(LB_NAME(score_data)(handle_, &s));
         return (float)s;
     }
     size_t kind_count() const {
         int32_t k = 0;
-        LOOM_B200_CHECK(lb_get_kinds(handle_, &k, nullptr));
+        LOOM_B200_CHECK(LB_NAME(get_kinds)(handle_, &k, nullptr));
         return (size_t)k;
     }
     std::vector<uint32_t> featureid_to_kindid() const {
         std::vector<uint32_t> f2k(feature_count_);
         int32_t k = 0;
-        LOOM_B200_CHECK(lb_get_kinds(handle_, &k, f2k.data()));
+        LOOM_B200_CHECK(LB_NAME(get_kinds)(handle_, &k, f2k.data()));
         return f2k;
     }
     // Assignments::groupids(kind) as packed ids (src/assignments.hpp:108-111)
     std::vector<uint32_t> groupids(size_t kindid) const {
         std::vector<uint32_t> out(row_count_);
-        LOOM_B200_CHECK(lb_get_assignments(handle_, (int32_t)kindid, out.data()));
+        LOOM_B200_CHECK(LB_NAME(get_assignments)(handle_, (int32_t)kindid, out.data()));
         return out;
     }
     // ProductMixture::score_value for a batch of rows (src/product_mixture.cc:421-434)
     std::vector<float> score_rows(size_t kindid, uint64_t row_begin, uint64_t row_end) const {
         lb_kind_info_t info;
-        LOOM_B200_CHECK(lb_kind_info(handle_, (int32_t)kindid, &info));
+        LOOM_B200_CHECK(LB_NAME(kind_info)(handle_, (int32_t)kindid, &info));
         std::vector<float> out((size_t)(row_end - row_begin) * info.n_groups);
-        LOOM_B200_CHECK(lb_score_rows(handle_, (int32_t)kindid, row_begin, row_end, out.data()));
+        LOOM_B200_CHECK(LB_NAME(score_rows)(handle_, (int32_t)kindid, row_begin, row_end, out.data()));
         return out;
     }
     lb_handle handle() const { return handle_; }
@@ -117,7 +127,7 @@ public:
     // pipeline.wait() (src/loom.cc:425-429)
     void wait() {
         if (actions_.empty()) return;
-        LOOM_B200_CHECK(lb_cat_sweep(cross_cat_.handle(), actions_.data(), actions_.size(), seed_, offset_,
+        LOOM_B200_CHECK(LB_NAME(cat_sweep)(cross_cat_.handle(), actions_.data(), actions_.size(), seed_, offset_,
                                      nullptr, nullptr, nullptr, 0));
         offset_ += actions_.size();
         actions_.clear();
@@ -142,7 +152,7 @@ public:
     void remove_row(uint64_t row_position) { actions_.push_back(LB_ACTION_REMOVE(row_position)); }
     void wait() {
         if (actions_.empty()) return;
-        LOOM_B200_CHECK(lb_cat_sweep_multi(handles_.data(), (int32_t)handles_.size(), actions_.data(), actions_.size(),
+        LOOM_B200_CHECK(LB_NAME(cat_sweep_multi)(handles_.data(), (int32_t)handles_.size(), actions_.data(), actions_.size(),
                                            seeds_.data(), offset_));
         offset_ += actions_.size();
         actions_.clear();
@@ -161,15 +171,15 @@ class KindKernel {
 public:
     KindKernel(CrossCat &cross_cat, int empty_kind_count, int iterations, uint64_t seed)
         : cross_cat_(cross_cat), empty_kind_count_(empty_kind_count), iterations_(iterations), seed_(seed) {
-        LOOM_B200_CHECK(lb_init_featureless_kinds(cross_cat_.handle(), empty_kind_count_, next_seed()));
+        LOOM_B200_CHECK(LB_NAME(init_featureless_kinds)(cross_cat_.handle(), empty_kind_count_, next_seed()));
     }
-    ~KindKernel() { lb_init_featureless_kinds(cross_cat_.handle(), 0, 0); }  // kind_kernel.cc:75-81
+    ~KindKernel() { LB_NAME(init_featureless_kinds)(cross_cat_.handle(), 0, 0); }  // kind_kernel.cc:75-81
     // KindKernel::try_run (src/kind_kernel.cc:118-157); returns true when a feature moved
     bool try_run() {
-        LOOM_B200_CHECK(lb_kind_proposer_score(cross_cat_.handle(), nullptr));
+        LOOM_B200_CHECK(LB_NAME(kind_proposer_score)(cross_cat_.handle(), nullptr));
         int32_t changed = 0;
-        LOOM_B200_CHECK(lb_kind_run(cross_cat_.handle(), iterations_, next_seed(), nullptr, &changed));
-        LOOM_B200_CHECK(lb_init_featureless_kinds(cross_cat_.handle(), empty_kind_count_, next_seed()));
+        LOOM_B200_CHECK(LB_NAME(kind_run)(cross_cat_.handle(), iterations_, next_seed(), nullptr, &changed));
+        LOOM_B200_CHECK(LB_NAME(init_featureless_kinds)(cross_cat_.handle(), empty_kind_count_, next_seed()));
         return changed > 0;
     }
 
@@ -184,9 +194,9 @@ private:
 class HyperKernel {
 public:
     HyperKernel(CrossCat &cross_cat, const lb_hyper_prior &prior) : cross_cat_(cross_cat) {
-        LOOM_B200_CHECK(lb_set_hyper_prior(cross_cat_.handle(), &prior));
+        LOOM_B200_CHECK(LB_NAME(set_hyper_prior)(cross_cat_.handle(), &prior));
     }
-    void run(uint64_t seed) { LOOM_B200_CHECK(lb_hyper_run(cross_cat_.handle(), seed)); }
+    void run(uint64_t seed) { LOOM_B200_CHECK(LB_NAME(hyper_run)(cross_cat_.handle(), seed)); }
 
 private:
     CrossCat &cross_cat_;
@@ -210,6 +220,8 @@ public:
         state_ += add_rate_;
         return false;
     }
+    void load(double state) { state_ = state; }     // Checkpoint.Schedule.annealing_state (schedules.hpp:88-96)
+    double state() const { return state_; }
 
 private:
     double add_rate_ = 1, remove_rate_ = 0, state_ = 0;
@@ -239,6 +251,8 @@ public:
         if (stale_ == 0 && fresh_) { stale_ = fresh_; fresh_ = 0; return true; }
         return false;
     }
+    void load(uint64_t row_count) { stale_ = row_count; fresh_ = 0; }   // schedules.hpp:184-193
+    uint64_t row_count() const { return stale_ + fresh_; }
 
 private:
     uint64_t stale_ = 0, fresh_ = 0;
@@ -249,6 +263,8 @@ public:
     explicit KernelDisablingSchedule(uint64_t max_reject_iters) : max_(max_reject_iters) {}
     void run(bool accepted) { rejects_ = accepted ? 0 : rejects_ + 1; }
     bool test() const { return rejects_ <= max_; }
+    void load(uint64_t reject_iters) { rejects_ = reject_iters; }      // schedules.hpp:224-232
+    uint64_t reject_iters() const { return rejects_; }
 
 private:
     uint64_t max_, rejects_ = 0;

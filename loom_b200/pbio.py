@@ -319,6 +319,21 @@ class Rows:
     def n_rows(self):
         return len(self.rowids)
 
+    @staticmethod
+    def from_block(block, rowids=None):
+        """a dense columnar `RowBlock` as untared rows: diff{pos = the row, neg = nothing}"""
+        obs = block.observed()                                   # [F][R]
+        F, R = obs.shape
+        F8 = block.cat8.shape[0]
+        vals = np.zeros((F, R), np.uint32)
+        vals[:F8] = block.cat8
+        vals[F8:] = block.wide
+        ptr = np.zeros(R + 1, np.uint64)
+        ptr[1:] = np.cumsum(obs.sum(axis=0))
+        r_idx, f_idx = np.nonzero(obs.T)
+        return Rows(np.arange(R) if rowids is None else rowids, np.zeros(R, np.uint8), ptr, f_idx,
+                    vals[f_idx, r_idx], np.zeros(R + 1, np.uint64), np.zeros(0, np.uint32))
+
     def _view(self):
         v = RowBlockView()
         v.n_rows = self.n_rows

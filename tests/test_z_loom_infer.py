@@ -1,0 +1,237 @@
+"""`loom_infer` end to end on files: the process boundary loom.runner uses (src/infer.cc:68-81).
+
+The host code under test (loom_b200/host/loom.hpp + loom_infer.cc + the file codec) is the
+product's; on this CPU box it is linked against the oracle's copy of the C ABI
+(-D'LB_NAME(x)=lo_##x'), on the GPU box against libloomb200.so.  Inputs are written with
+google.protobuf (what a loom front end produces), outputs are read back with it and checked
+with the invariants loom's own runner tests use (loom/test/test_runner.py:237-250) plus a
+recomputation of every sufficient statistic from the rows and the dumped assignments."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pb_schema
+from conftest import has_gpu
+from loom_b200 import Engine, _abi, pbio, synth, tare
+from loom_b200.engine import RowBlock
+from test_pbio import GRIDS, M, fill_value, io_lib  # noqa: F401  (io_lib: autouse fixture builds the codec)
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(REPO, "loom_b200", "host")
+TYPES = [("bb", 4), ("dd16", 3), ("dd256", 1), ("gp", 2), ("nich", 3)]
+
+
+@pytest.fixture(scope="module")
+def infer_on_oracle(tmp_path_factory, oracle_abi):
+    """loom_infer.cc built against the oracle's lo_ ABI (tests may link oracle/)"""
+    exe = tmp_path_factory.mktemp("bin") / "loom_infer_oracle"
+    oracle_dir, io_dir = os.path.join(REPO, "oracle"), os.path.join(REPO, "loom_b200", "io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-DLB_NAME(x)=lo_##x",
+                           os.path.join(HOST, "loom_infer.cc"), "-o", str(exe),
+                           "-L" + oracle_dir, "-lloom_oracle", "-L" + io_dir, "-lloomb200_io",
+                           "-Wl,-rpath," + oracle_dir, "-Wl,-rpath," + io_dir])
+    return str(exe)
+
+
+def write_inputs(d, n_rows=300, seed=0, extra_passes=2.0, kind_iterations=0, hyper=False, tared=False,
+                 checkpoint_period_sec=1e9):
+    model, block, _ = synth.generate(n_rows, TYPES, density=0.7, seed=seed)
+    mf = pbio.ModelFile.create(model, GRIDS if hyper else None)
+    mf.write(d / "init.pb.gz")
+    rng = np.random.default_rng(seed)
+    rowids = rng.permutation(10 * n_rows)[:n_rows].astype(np.uint64)      # arbitrary, shuffled ids
+    paths = {"tares": "--none"}
+    if tared:
+        tare_obs, tare_val = tare.make_tare(model, block)
+        diff = tare.sparsify(model, block, tare_obs, tare_val)
+        rows = pbio.Rows(rowids, np.ones(n_rows, np.uint8), diff["pos_ptr"], diff["pos_feature"], diff["pos_value"],
+                         diff["neg_ptr"], diff["neg_feature"])
+        pbio.tares_write(d / "tares.pbs.gz", mf, tare_obs, tare_val)
+        paths["tares"] = str(d / "tares.pbs.gz")
+    else:
+        rows = pbio.Rows.from_block(block, rowids)
+    pbio.rows_write(d / "rows.pbs.gz", mf, rows)
+    c = pbio.config_defaults()
+    c.seed, c.extra_passes, c.kind_iterations, c.kind_empty_kind_count = seed, extra_passes, kind_iterations, 3
+    c.hyper_run, c.checkpoint_period_sec = int(hyper), checkpoint_period_sec
+    c.small_data_size = 50.0
+    pbio.config_write(d / "config.pb.gz", c)
+    paths.update(config=str(d / "config.pb.gz"), rows=str(d / "rows.pbs.gz"), model_in=str(d / "init.pb.gz"))
+    return model, block, rowids, paths
+
+
+def run(exe, paths, d, groups_in="--none", assign_in="--none", checkpoint_in="--none", tag="out", checkpoint_out=False,
+        expect_failure=False):
+    out = {"model": str(d / (tag + ".model.pb.gz")), "groups": str(d / (tag + ".groups")),
+           "assign": str(d / (tag + ".assign.pbs.gz")), "log": str(d / (tag + ".log.pbs.gz")),
+           "checkpoint": str(d / (tag + ".checkpoint.pb.gz")) if checkpoint_out else "--none"}
+    cmd = [exe, paths["config"], paths["rows"], paths["tares"], paths["model_in"], groups_in, assign_in, checkpoint_in,
+           out["model"], out["groups"], out["assign"], out["checkpoint"], out["log"]]
+    proc = subprocess.run(cmd, capture_output=True, timeout=600)
+    if expect_failure:
+        assert proc.returncode != 0
+        return proc.stderr.decode()
+    assert proc.returncode == 0, proc.stderr.decode()
+    return out
+
+
+def check_outputs(oracle_abi, block, rowids, out, n_assigned=None, kinds_fixed_to=None, tare_args=None):
+    """structural invariants + every dumped statistic recomputed from rows and assignments"""
+    R = block.n_rows
+    n_assigned = R if n_assigned is None else n_assigned
+    mf = pbio.ModelFile.read(out["model"])
+    model = mf.model()
+    g = pb_schema.load_message(out["model"], M()["CrossCat"])
+    assert g.IsInitialized() and len(g.kinds) == model.n_kinds
+    assert sorted(f for k in g.kinds for f in k.featureids) == list(range(model.n_features))
+    if kinds_fixed_to is not None:
+        assert np.array_equal(model.f2k, kinds_fixed_to)
+    a_rowids, a_gids = pbio.assign_read(out["assign"])
+    assert len(a_rowids) == n_assigned and a_gids.shape == (n_assigned, model.n_kinds)
+    assert len(set(a_rowids.tolist())) == n_assigned and set(a_rowids.tolist()) <= set(rowids.tolist())
+    position = {int(r): i for i, r in enumerate(rowids)}
+    pos = np.asarray([position[int(r)] for r in a_rowids])
+    if n_assigned:
+        assert np.array_equal(pos, (pos[0] + np.arange(n_assigned)) % R)      # a window of the cyclic stream, FIFO order
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(block)
+    dumped = []
+    for k in range(model.n_kinds):
+        fids = model.kind_features(k)
+        counts, ints, flts = pbio.groups_read(pbio.mixture_path(out["groups"], k), mf, fids)
+        assert (counts > 0).all() and counts.sum() == n_assigned
+        assert (np.diff(counts.astype(np.int64)) <= 0).all()                  # largest group first (cross_cat.cc:212-236)
+        assert a_gids[:, k].max(initial=0) < max(len(counts), 1)
+        assert np.array_equal(np.bincount(a_gids[:, k], minlength=len(counts)), counts)
+        packed = np.full(R, _abi.UNASSIGNED, np.uint32)
+        packed[pos] = a_gids[:, k]
+        e.set_groups(k, len(counts))
+        e.set_assignments(k, packed)
+        dumped.append((counts, ints, flts))
+    e.accumulate_rows()
+    for k, (counts, ints, flts) in enumerate(dumped):
+        c2, i2, f2 = e.get_groups(k)
+        n = len(counts)
+        assert np.array_equal(c2[:n], counts) and np.array_equal(i2[:, :n], ints)       # integers bit-exact
+        assert np.allclose(f2[:, :n], flts, rtol=2e-5, atol=2e-5)                       # float32 on the wire
+    return model, a_rowids, a_gids
+
+
+def test_multi_pass_cat_only(tmp_path, infer_on_oracle, oracle_abi):
+    model, block, rowids, paths = write_inputs(tmp_path)
+    out = run(infer_on_oracle, paths, tmp_path)
+    check_outputs(oracle_abi, block, rowids, out, kinds_fixed_to=model.f2k)
+    logs = pb_schema.load_stream(out["log"], M()["LogMessage"])
+    assert len(logs) >= 3 and all(m.IsInitialized() for m in logs)
+    assert [m.args.iter for m in logs] == list(range(len(logs)))
+    assert logs[-1].args.scores.assigned_object_count == block.n_rows
+    assert list(logs[-1].args.summary.feature_counts) == [len(model.kind_features(k)) for k in range(model.n_kinds)]
+    assert np.isfinite(logs[-1].args.scores.score) and logs[-1].args.scores.score < 0
+    # same seed, same files -> same result; another seed -> another sample
+    again = run(infer_on_oracle, paths, tmp_path, tag="again")
+    assert np.array_equal(pbio.assign_read(out["assign"])[1], pbio.assign_read(again["assign"])[1])
+
+
+def test_single_pass(tmp_path, infer_on_oracle, oracle_abi):
+    model, block, rowids, paths = write_inputs(tmp_path, extra_passes=0.0)
+    out = run(infer_on_oracle, paths, tmp_path)
+    # infer_single_pass streams assignments in row order with the ids given at assignment time
+    a_rowids, a_gids = pbio.assign_read(out["assign"])
+    assert np.array_equal(a_rowids, rowids) and a_gids.shape == (block.n_rows, model.n_kinds)
+    mf = pbio.ModelFile.read(out["model"])
+    for k in range(model.n_kinds):
+        counts, _, _ = pbio.groups_read(pbio.mixture_path(out["groups"], k), mf, model.kind_features(k))
+        assert counts.sum() == block.n_rows
+        assert sorted(np.bincount(a_gids[:, k]).tolist(), reverse=True)[:len(counts)] == counts.tolist()
+
+
+def test_kind_and_hyper_kernels_and_tares(tmp_path, infer_on_oracle, oracle_abi):
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=200, seed=3, kind_iterations=4, hyper=True, tared=True)
+    out = run(infer_on_oracle, paths, tmp_path)
+    new_model, _, _ = check_outputs(oracle_abi, block, rowids, out)
+    g = pb_schema.load_message(out["model"], M()["CrossCat"])
+    assert g.hyper_prior == pb_schema.load_message(paths["model_in"], M()["CrossCat"]).hyper_prior   # grids pass through
+    # hypers moved onto grid points
+    assert all(any(np.isclose(k.product_model.clustering.alpha, a) for a, _ in GRIDS["clustering"]) for k in g.kinds)
+    for f in new_model.features:
+        if f["type"] == "bb":
+            assert any(np.isclose(f["alpha"], a) for a in GRIDS["bb"]["alpha"])
+    logs = pb_schema.load_stream(out["log"], M()["LogMessage"])
+    assert logs[-1].args.kernel_status.kind.total_count >= 1
+
+
+def test_checkpoint_resume_loop(tmp_path, infer_on_oracle, oracle_abi):
+    """checkpoint_period_sec = 0: every call stops at its first batch boundary; feeding the outputs back
+    in (groups, assignments, checkpoint) until `finished` is loom's resume protocol (src/loom.cc:178-214)"""
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=120, seed=5, checkpoint_period_sec=0.0)
+    groups_in = assign_in = checkpoint_in = "--none"
+    model_in = paths["model_in"]
+    seen_iters, assigned = [], []
+    for step in range(200):
+        p = dict(paths, model_in=model_in)
+        out = run(infer_on_oracle, p, tmp_path, groups_in, assign_in, checkpoint_in, tag="step%d" % step,
+                  checkpoint_out=True)
+        ck = pbio.checkpoint_read(out["checkpoint"])
+        g = pb_schema.load_message(out["checkpoint"], M()["Checkpoint"])
+        assert g.IsInitialized() and g.row_count == 120 and g.tardis_iter == ck.tardis_iter
+        seen_iters.append(ck.tardis_iter)
+        n = len(pbio.assign_read(out["assign"])[0])
+        assigned.append(n)
+        assert (ck.unassigned_pos - ck.assigned_pos) % 120 == n % 120
+        if ck.finished:
+            break
+        check_outputs(oracle_abi, block, rowids, out, n_assigned=n, kinds_fixed_to=model.f2k)
+        groups_in, assign_in, checkpoint_in, model_in = out["groups"], out["assign"], out["checkpoint"], out["model"]
+    assert ck.finished and assigned[-1] == 120 and len(seen_iters) > 3
+    assert all(b > a for a, b in zip(seen_iters, seen_iters[1:]))
+    check_outputs(oracle_abi, block, rowids, out, kinds_fixed_to=model.f2k)
+    logs = pb_schema.load_stream(out["log"], M()["LogMessage"])      # each resumed call appends to its own log
+    assert len(logs) >= 1
+
+
+def test_errors_abort_with_looms_message(tmp_path, infer_on_oracle):
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=50)
+    err = run(infer_on_oracle, dict(paths, rows=str(tmp_path / "missing.pbs.gz")), tmp_path, expect_failure=True)
+    assert err.startswith("ERROR failed to open input file") and "loom.hpp" in err      # ERROR msg \n\t file : line \n\t function
+    err = run(infer_on_oracle, dict(paths, model_in=paths["rows"]), tmp_path, expect_failure=True)
+    assert err.startswith("ERROR")
+    # assignments that are not a window of the stream
+    out = run(infer_on_oracle, paths, tmp_path)
+    a_rowids, a_gids = pbio.assign_read(out["assign"])
+    pbio.assign_write(tmp_path / "scrambled.pbs.gz", a_rowids[::-1][:20], a_gids[::-1][:20])
+    err = run(infer_on_oracle, paths, tmp_path, groups_in=out["groups"], assign_in=str(tmp_path / "scrambled.pbs.gz"),
+              expect_failure=True)
+    assert "contiguous window" in err or "sample_size" in err
+    proc = subprocess.run([infer_on_oracle, "too", "few"], capture_output=True)
+    assert proc.returncode == 1 and b"Usage: loom_infer CONFIG_IN ROWS_IN TARES_IN MODEL_IN" in proc.stderr
+
+
+def test_product_binary_links_against_the_cuda_library():
+    """`make -C loom_b200/host` links loom_infer with libloomb200.so (no oracle anywhere near it)"""
+    import __graft_entry__
+    __graft_entry__.build()
+    exe = os.path.join(HOST, "loom_infer")
+    assert os.path.exists(exe)
+    needed = subprocess.check_output(["readelf", "-d", exe]).decode()
+    assert "libloomb200.so" in needed and "libloomb200_io.so" in needed and "oracle" not in needed
+    if not has_gpu():
+        # without a device the engine refuses to start: there is no CPU fallback behind the binary
+        proc = subprocess.run([exe] + ["x"] * 12, capture_output=True)
+        assert proc.returncode != 0
+
+
+@pytest.mark.gpu
+def test_loom_infer_on_the_gpu(tmp_path, oracle_abi):
+    """the product binary on the device: files in, files out, statistics recomputed by the oracle"""
+    import __graft_entry__
+    __graft_entry__.build()
+    exe = os.path.join(HOST, "loom_infer")
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=400, seed=7, kind_iterations=4, hyper=True, tared=True)
+    out = run(exe, paths, tmp_path)
+    check_outputs(oracle_abi, block, rowids, out)
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=300, seed=8)
+    out = run(exe, paths, tmp_path, tag="cat")
+    check_outputs(oracle_abi, block, rowids, out, kinds_fixed_to=model.f2k)
