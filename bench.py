@@ -102,6 +102,51 @@ def algorithmic_bytes_per_action(model, rows):
     return cell_bytes + model.n_features / 8.0 + 8.0 + 8.0 * model.n_kinds
 
 
+def measure_ingest(abi, model, rows, device=0):
+    """Row ingest: the workload's rows as loom's `rows.pbs.gz` (a gzip stream of
+    protobuf Row messages), decoded by the native codec (gunzip + framing serial, message decode on all
+    host threads) and expanded on the device by lb_set_rows_diff.  Replaces the unzip / parse / split
+    stages of src/cat_pipeline.cc:63-87.  Host wall clock; the file is written outside the timed region."""
+    from loom_b200 import pbio
+    from loom_b200.engine import Engine
+    mf = pbio.ModelFile.create(model)
+    fd, path = tempfile.mkstemp(suffix=".rows.pbs.gz")
+    os.close(fd)
+    try:
+        pbio.rows_write(path, mf, pbio.Rows.from_block(rows))
+        file_bytes = os.path.getsize(path)
+        n_msgs, _ = pbio.stream_stats(path)
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            view = pbio.RowBlockView()
+            pbio._check(pbio.lib().lbio_rows_read(os.fsencode(path), mf.h, 0, 0, 0, ctypes.byref(view)))
+            t1 = time.perf_counter()
+            dt = t1 - t0
+            if best is None or dt < best[0]:
+                best = (dt, int(view.pos_ptr[view.n_rows]))
+            pbio.lib().lbio_rows_free(ctypes.byref(view))
+        decode_s, n_cells = best
+        decoded = pbio.rows_read(path, mf)
+        eng = Engine(abi, device=device)
+        eng.set_model(model)
+        decoded.upload(eng)        # warm-up (allocations)
+        eng.sync()
+        t0 = time.perf_counter()
+        decoded.upload(eng)
+        eng.sync()
+        upload_s = time.perf_counter() - t0
+        eng.close()
+        return {"rows": int(n_msgs), "cells": n_cells, "file_bytes": file_bytes, "host_threads": os.cpu_count(),
+                "decode_ms": decode_s * 1e3, "rows_per_s": n_msgs / decode_s, "cells_per_s": n_cells / decode_s,
+                "file_MB_per_s": file_bytes / decode_s / 1e6,
+                "upload_and_expand_ms": upload_s * 1e3, "upload_cells_per_s": n_cells / upload_s,
+                "note": "rows.pbs.gz -> CSR diff on the host (lbio_rows_read), then lb_set_rows_diff expands it "
+                        "into the columnar block on the device"}
+    finally:
+        os.unlink(path)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -499,6 +544,12 @@ def main():
         e.cat_sweep(drain, seed=9)
     except Exception as exc:  # the auxiliary numbers never mask the headline
         aux["error"] = str(exc)
+
+    if rank == 0:
+        try:
+            aux["ingest"] = measure_ingest(cuda, model, rows, device=local_rank)
+        except Exception as exc:  # never masks the headline
+            aux["ingest"] = {"error": str(exc)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

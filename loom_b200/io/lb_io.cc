@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <future>
 #include <string>
 #include <sys/time.h>
 #include <sys/resource.h>
@@ -819,38 +821,49 @@ extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t fi
     T = 1;
 #endif
     T = std::max(1, std::min(T, 64));
-    const size_t BATCH = 1 << 16;
+    // gunzip + framing are serial (one gzip stream); they run one batch ahead of the decoders
+    const size_t BATCH = 1 << 14;
     auto *o = new RowsOwner;
     o->pos_ptr.push_back(0);
     o->neg_ptr.push_back(0);
-    std::vector<uint8_t> pool;
-    std::vector<uint64_t> offsets;
+    struct Batch { std::vector<uint8_t> pool; std::vector<uint64_t> offsets; bool bad = false; };
+    Batch batches[2];
     std::vector<RowChunk> chunks((size_t)T);
     bool at_end = false;
     uint64_t taken = 0;
-    while (!at_end && (max_rows == 0 || taken < max_rows)) {
-        pool.clear();
-        offsets.assign(1, 0);
-        while (offsets.size() <= BATCH && (max_rows == 0 || taken < max_rows)) {
-            if (!file.try_read_stream_into(pool, size, bad)) {
-                if (bad) { delete o; return fail("failed to parse message from %s (truncated stream)", path); }
+    auto read_batch = [&](Batch &b) {
+        b.pool.clear();
+        b.offsets.assign(1, 0);
+        b.bad = false;
+        uint32_t sz = 0;
+        bool broken = false;
+        while (!at_end && b.offsets.size() <= BATCH && (max_rows == 0 || taken < max_rows)) {
+            if (!file.try_read_stream_into(b.pool, sz, broken)) {
+                b.bad = broken;
                 at_end = true;
                 break;
             }
-            offsets.push_back(pool.size());
+            b.offsets.push_back(b.pool.size());
             ++taken;
         }
-        const size_t n = offsets.size() - 1;
+    };
+    read_batch(batches[0]);
+    for (int cur = 0;; cur ^= 1) {
+        Batch &b = batches[cur];
+        if (b.bad) { delete o; return fail("failed to parse message from %s (truncated stream)", path); }
+        const size_t n = b.offsets.size() - 1;
         if (!n) break;
+        std::future<void> ahead = std::async(std::launch::async, read_batch, std::ref(batches[cur ^ 1]));
         const int used = (int)std::min<size_t>((size_t)T, (n + 255) / 256);
 #pragma omp parallel for num_threads(used) schedule(static, 1)
         for (int t = 0; t < used; ++t) {
             chunks[t].clear();
-            decode_rows(*m, pool.data(), offsets.data(), n * t / used, n * (t + 1) / used, chunks[t]);
+            decode_rows(*m, b.pool.data(), b.offsets.data(), n * t / used, n * (t + 1) / used, chunks[t]);
         }
-        for (int t = 0; t < used; ++t) {
+        std::string error;
+        for (int t = 0; t < used && error.empty(); ++t) {
             const RowChunk &c = chunks[t];
-            if (!c.error.empty()) { delete o; return fail("%s: %s", path, c.error.c_str()); }
+            if (!c.error.empty()) { error = c.error; break; }
             o->rowids.insert(o->rowids.end(), c.rowids.begin(), c.rowids.end());
             o->has_tare.insert(o->has_tare.end(), c.has_tare.begin(), c.has_tare.end());
             for (uint32_t k : c.pos_count) o->pos_ptr.push_back(o->pos_ptr.back() + k);
@@ -859,6 +872,8 @@ extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t fi
             o->pos_value.insert(o->pos_value.end(), c.pos_value.begin(), c.pos_value.end());
             o->neg_feature.insert(o->neg_feature.end(), c.neg_feature.begin(), c.neg_feature.end());
         }
+        ahead.get();
+        if (!error.empty()) { delete o; return fail("%s: %s", path, error.c_str()); }
     }
     publish_rows(o, out);
     out->stream_rows = at_end ? file.position() : 0;

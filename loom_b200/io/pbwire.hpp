@@ -175,7 +175,12 @@ public:
         if (n == 0) return false;
         if (n != 4) { bad = true; return false; }
         size = (uint32_t)head[0] | (uint32_t)head[1] << 8 | (uint32_t)head[2] << 16 | (uint32_t)head[3] << 24;
-        if (size && gzseek(f_, size, SEEK_CUR) < 0) { bad = true; return false; }
+        uint8_t discard[1 << 14];       // read and drop: gzseek is very slow on uncompressed files
+        for (uint32_t left = size; left;) {
+            const unsigned take = left < sizeof(discard) ? left : (unsigned)sizeof(discard);
+            if (gzread(f_, discard, take) != (int)take) { bad = true; return false; }
+            left -= take;
+        }
         ++position_;
         return true;
     }
