@@ -184,6 +184,17 @@ int LB_NAME(cat_sweep)(lb_handle h, const uint32_t *actions, uint64_t n_actions,
 int LB_NAME(cat_sweep_multi)(const lb_handle *handles, int32_t n_handles, const uint32_t *actions,
                              uint64_t n_actions, const uint64_t *seeds, uint64_t action_offset);
 
+/* cat_sweep_multi with a row order per chain: chain c runs actions[c * n_actions .. + n_actions).
+ * loom shuffles the rows separately for every sample (loom/tasks.py:228-233 infer_one ->
+ * loom.runner.shuffle(seed = sample seed)), so samples visit the same rows in different orders;
+ * here the chains share ONE row block (share_rows) and each brings its own permutation as row
+ * positions in its action list.  The ADD / REMOVE pattern is normally the same for every chain
+ * (the schedules depend only on counts); only n_actions must be.  Equivalent to
+ * cat_sweep(handles[c], actions + c * n_actions, n_actions, seeds[c], action_offset, ...) for
+ * every c, in one launch. */
+int LB_NAME(cat_sweep_streams)(const lb_handle *handles, int32_t n_handles, const uint32_t *actions,
+                               uint64_t n_actions, const uint64_t *seeds, uint64_t action_offset);
+
 /* Assignments (src/assignments.hpp): packed group id per row position for one
  * kind, LB_UNASSIGNED where the row is not assigned. */
 int LB_NAME(get_assignments)(lb_handle h, int32_t kind, uint32_t *out_packed);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
     "share_rows": (C.c_int, [_h, _h]),
     "cat_sweep_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
+    "cat_sweep_streams": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
     "cat_sweep": (C.c_int, [_h, _u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u32p, _f32p,
                             C.c_int32]),
     "get_assignments": (C.c_int, [_h, C.c_int32, _u32p]),

@@ -604,8 +604,9 @@ extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, ui
 }
 
 // loom/tasks.py:173-194 (samples in parallel): the same actions on many chains, one launch
-extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
-                                  const uint64_t *seeds, uint64_t offset) {
+// `per_chain`: chain c runs actions[c * n .. + n) (its own shuffle of the shared rows)
+static int sweep_chains(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                        const uint64_t *seeds, uint64_t offset, bool per_chain) {
     if (n_handles <= 0 || n == 0) return 0;
     std::vector<Engine *> es(n_handles);
     for (int c = 0; c < n_handles; ++c) {
@@ -617,12 +618,13 @@ extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, c
     }
     Engine *lead = es[0];
     LB_CUDA(cudaSetDevice(lead->device));
-    if (n > lead->actions_cap) {
+    const uint64_t n_up = per_chain ? n * (uint64_t)n_handles : n;
+    if (n_up > lead->actions_cap) {
         dev_free(lead->d_actions);
-        LB_TRY(dev_alloc(&lead->d_actions, n));
-        lead->actions_cap = n;
+        LB_TRY(dev_alloc(&lead->d_actions, n_up));
+        lead->actions_cap = n_up;
     }
-    LB_CUDA(cudaMemcpyAsync(lead->d_actions, actions, 4 * n, cudaMemcpyHostToDevice, lead->stream));
+    LB_CUDA(cudaMemcpyAsync(lead->d_actions, actions, 4 * n_up, cudaMemcpyHostToDevice, lead->stream));
     std::vector<std::vector<int>> active(n_handles);
     std::vector<std::vector<uint64_t>> progress(n_handles);
     for (int c = 0; c < n_handles; ++c) {
@@ -644,7 +646,8 @@ extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, c
             for (int kid : active[c]) e->h_kinds[kid].progress = progress[c][kid];
             LB_CUDA(cudaMemcpyAsync(e->d_kinds, e->h_kinds.data(), sizeof(KindDev) * K, cudaMemcpyHostToDevice, e->stream));
             SweepChain ch;
-            LB_TRY(lb_sweep_chain(e, active[c], lead->d_actions, n, seeds[c], offset, nullptr, nullptr, 0, &ch));
+            const uint32_t *d_chain_actions = lead->d_actions + (per_chain ? n * (uint64_t)c : 0);
+            LB_TRY(lb_sweep_chain(e, active[c], d_chain_actions, n, seeds[c], offset, nullptr, nullptr, 0, &ch));
             if (e != lead) LB_CUDA(cudaStreamSynchronize(e->stream));   // its uploads precede the leader's launch
             chains.push_back(ch); live.push_back(e); live_ids.push_back(active[c]); live_idx.push_back(c);
         }
@@ -669,9 +672,11 @@ extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, c
                 case LB_ST_OK: break;
                 case LB_ST_NEED_GROW: again.push_back(kid); break;
                 case LB_ST_DUPLICATE_ROW:
-                    return lb_fail("duplicate row: %u (chain %d, kind %d)", actions[d.progress] >> 1, c, kid);
+                    return lb_fail("duplicate row: %u (chain %d, kind %d)",
+                                   actions[(per_chain ? n * (uint64_t)c : 0) + d.progress] >> 1, c, kid);
                 case LB_ST_REMOVE_UNASSIGNED:
-                    return lb_fail("remove of unassigned row %u (chain %d, kind %d)", actions[d.progress] >> 1, c, kid);
+                    return lb_fail("remove of unassigned row %u (chain %d, kind %d)",
+                                   actions[(per_chain ? n * (uint64_t)c : 0) + d.progress] >> 1, c, kid);
                 default:
                     return lb_fail("action %llu: row out of range", (unsigned long long)d.progress);
                 }
@@ -686,6 +691,17 @@ extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, c
         }
     }
     return 0;
+}
+
+extern "C" int lb_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                                  const uint64_t *seeds, uint64_t offset) {
+    return sweep_chains(handles, n_handles, actions, n, seeds, offset, false);
+}
+
+// loom/tasks.py:228-233: every sample has its own shuffle of the rows
+extern "C" int lb_cat_sweep_streams(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                                    const uint64_t *seeds, uint64_t offset) {
+    return sweep_chains(handles, n_handles, actions, n, seeds, offset, true);
 }
 
 // ---------------------------------------------------------------------------

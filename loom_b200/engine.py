@@ -169,6 +169,21 @@ def cat_sweep_multi(engines, actions, seeds, action_offset=0):
                               seeds.ctypes.data_as(C.POINTER(C.c_uint64)), action_offset))
 
 
+def cat_sweep_streams(engines, actions, seeds, action_offset=0):
+    """One launch, a row order per chain: actions is [n_chains][n_actions] (loom shuffles the rows
+    separately for every sample, loom/tasks.py:228-233; the chains still share one row block)."""
+    if not engines:
+        return
+    actions = np.ascontiguousarray(actions, dtype=np.uint32)
+    assert actions.ndim == 2 and actions.shape[0] == len(engines)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    assert len(seeds) == len(engines)
+    hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    a = engines[0].abi
+    a.check(a.cat_sweep_streams(hs, len(engines), ptr(actions, _u32p), actions.shape[1],
+                                seeds.ctypes.data_as(C.POINTER(C.c_uint64)), action_offset))
+
+
 def query_score(engines, row_begin=0, row_end=None):
     """QueryServer::call(Score) over the latent samples `engines` (src/query_server.cc:189-231):
     log_sum_exp over samples of the per-sample score, minus log(#samples)."""

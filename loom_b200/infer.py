@@ -16,7 +16,7 @@ import math
 
 import numpy as np
 
-from .engine import cat_sweep_multi
+from .engine import cat_sweep_multi, cat_sweep_streams
 
 DEFAULT_CONFIG = {   # loom/config.py:34-74
     "seed": 0,
@@ -155,13 +155,25 @@ def next_batch(n_rows, assigned_count, annealing, batching, window):
     return np.asarray(actions, np.uint32), assigned_count, False
 
 
-def infer_single_pass(engines, seeds):
+def sweep(engines, actions, seeds, action_offset=0, orders=None):
+    """One batch of stream-position actions on every chain.  `orders` ([n_chains][n_rows], optional)
+    is each chain's own shuffle of the shared row block (loom/tasks.py:228-233: loom.runner.shuffle
+    with the sample's seed): stream position p of chain c is row orders[c][p]."""
+    if orders is None:
+        cat_sweep_multi(engines, actions, seeds, action_offset=action_offset)
+        return
+    orders = np.asarray(orders, np.uint32)
+    per_chain = (orders[:, actions >> 1] << 1) | (actions & 1)[None, :]
+    cat_sweep_streams(engines, per_chain, seeds, action_offset=action_offset)
+
+
+def infer_single_pass(engines, seeds, orders=None):
     """Loom::infer_single_pass (src/loom.cc:100-165): one greedy ADD pass over the rows."""
     n_rows = engines[0].n_rows
-    cat_sweep_multi(engines, (np.arange(n_rows, dtype=np.uint32) << 1), seeds)
+    sweep(engines, (np.arange(n_rows, dtype=np.uint32) << 1), seeds, orders=orders)
 
 
-def infer_multi_pass(engines, seeds, config=None, hyper_prior=None, log=None):
+def infer_multi_pass(engines, seeds, config=None, hyper_prior=None, log=None, orders=None):
     """Loom::infer_multi_pass (src/loom.cc:167-450) on one or many chains with a common schedule.
 
     engines      chains (models and rows already set; every chain sees the same rows)
@@ -169,6 +181,7 @@ def infer_multi_pass(engines, seeds, config=None, hyper_prior=None, log=None):
     config       dict shaped like loom/config.py DEFAULTS (missing entries are filled in)
     hyper_prior  grids for the hyper kernel (loom_b200.hyperprior.defaults()); None = hyper kernel off
     log          optional callable(dict) called at every batch boundary (Logger of src/logger.hpp)
+    orders       optional [n_chains][n_rows]: a row order per chain (each sample's own shuffle)
 
     The kind kernel runs while `kernels.kind.iterations` > 0 and the disabling schedule allows it,
     per chain (a chain whose proposals keep being rejected falls back to the cat-only loop, as
@@ -196,7 +209,7 @@ def infer_multi_pass(engines, seeds, config=None, hyper_prior=None, log=None):
     while assigned != n_rows:
         actions, assigned, boundary = next_batch(n_rows, assigned, annealing, batching, window)
         if len(actions):
-            cat_sweep_multi(engines, actions, seeds, action_offset=offset)
+            sweep(engines, actions, seeds, action_offset=offset, orders=orders)
             offset += len(actions)
         if not boundary:
             break

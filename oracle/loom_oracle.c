@@ -558,6 +558,16 @@ int lo_cat_sweep_multi(const lb_handle *handles, int32_t n_handles, const uint32
     return 0;
 }
 
+/* loom/tasks.py:228-233: every sample shuffles the rows with its own seed -> a row order per chain */
+int lo_cat_sweep_streams(const lb_handle *handles, int32_t n_handles, const uint32_t *actions, uint64_t n,
+                         const uint64_t *seeds, uint64_t offset) {
+    for (int32_t c = 0; c < n_handles; ++c) {
+        int rc = lo_cat_sweep(handles[c], actions + (uint64_t)c * n, n, seeds[c], offset, NULL, NULL, NULL, 0);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int64_t lo_cat_replay(lb_handle h, const uint32_t *actions, uint64_t n, uint64_t seed,
                       uint64_t offset, const uint32_t *picks, const float *dev_scores,
                       int32_t stride, double tol, double *max_score_err) {

@@ -77,7 +77,7 @@ def run(exe, paths, d, groups_in="--none", assign_in="--none", checkpoint_in="--
     return out
 
 
-def check_outputs(oracle_abi, block, rowids, out, n_assigned=None, kinds_fixed_to=None, tare_args=None):
+def check_outputs(oracle_abi, block, rowids, out, n_assigned=None, kinds_fixed_to=None, shuffled=False):
     """structural invariants + every dumped statistic recomputed from rows and assignments"""
     R = block.n_rows
     n_assigned = R if n_assigned is None else n_assigned
@@ -93,7 +93,7 @@ def check_outputs(oracle_abi, block, rowids, out, n_assigned=None, kinds_fixed_t
     assert len(set(a_rowids.tolist())) == n_assigned and set(a_rowids.tolist()) <= set(rowids.tolist())
     position = {int(r): i for i, r in enumerate(rowids)}
     pos = np.asarray([position[int(r)] for r in a_rowids])
-    if n_assigned:
+    if n_assigned and not shuffled:
         assert np.array_equal(pos, (pos[0] + np.arange(n_assigned)) % R)      # a window of the cyclic stream, FIFO order
     e = Engine(oracle_abi)
     e.set_model(model)
@@ -235,3 +235,106 @@ def test_loom_infer_on_the_gpu(tmp_path, oracle_abi):
     model, block, rowids, paths = write_inputs(tmp_path, n_rows=300, seed=8)
     out = run(exe, paths, tmp_path, tag="cat")
     check_outputs(oracle_abi, block, rowids, out, kinds_fixed_to=model.f2k)
+
+
+# ------------------------------------------------------------------------------------------ a row order per chain
+def shuffled_streams(n_rows, n_chains, seed):
+    """[n_chains][3R] actions: ADD every row, then REMOVE/ADD every row, each chain in its own row order
+    (loom.runner.shuffle with the sample's seed, loom/tasks.py:228-233); same ADD/REMOVE pattern for all"""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_chains, 3 * n_rows), np.uint32)
+    for c in range(n_chains):
+        perm = rng.permutation(n_rows).astype(np.uint32)
+        out[c, :n_rows] = perm << 1
+        out[c, n_rows::2] = (perm << 1) | 1
+        out[c, n_rows + 1::2] = perm << 1
+    return out
+
+
+def streams_case(abi, n_chains=11, n_rows=500):
+    from loom_b200 import cat_sweep_streams
+    model, block, _ = synth.generate(n_rows, TYPES, density=0.6, seed=4)
+    actions = shuffled_streams(n_rows, n_chains, seed=9)
+    seeds = np.arange(100, 100 + n_chains)
+    owner = Engine(abi)
+    owner.set_model(model)
+    owner.set_rows(block)
+    chains = [owner]
+    for _ in range(n_chains - 1):
+        e = Engine(abi)
+        e.set_model(model)
+        e.share_rows(owner)
+        chains.append(e)
+    cat_sweep_streams(chains, actions, seeds)
+    return model, block, actions, seeds, chains
+
+
+def test_streams_equal_single_chain_sweeps_oracle(oracle_abi):
+    model, block, actions, seeds, chains = streams_case(oracle_abi, n_chains=3, n_rows=200)
+    for c, chain in enumerate(chains):
+        single = Engine(oracle_abi)
+        single.set_model(model)
+        single.set_rows(block)
+        single.cat_sweep(actions[c], seed=int(seeds[c]))
+        for k in range(model.n_kinds):
+            assert np.array_equal(single.get_assignments(k), chain.get_assignments(k))
+            assert all(np.array_equal(x, y) for x, y in zip(single.get_groups(k), chain.get_groups(k)))
+    assert not np.array_equal(chains[0].get_assignments(0), chains[1].get_assignments(0))
+
+
+@pytest.mark.gpu
+def test_streams_equal_single_chain_sweeps_gpu(oracle_abi, cuda_abi):
+    """lb_cat_sweep_streams: one launch, every chain in its own row order over the shared block; each chain
+    ends bit for bit where its own single-chain sweep ends, and one of them replays on the oracle"""
+    import test_cuda_cat as t
+    model, block, actions, seeds, chains = streams_case(cuda_abi)
+    for c, chain in enumerate(chains):
+        single = Engine(cuda_abi)
+        single.set_model(model)
+        single.set_rows(block)
+        picks, scores = single.cat_sweep(actions[c], seed=int(seeds[c]), debug=True, debug_stride=64)
+        if c == 0:
+            o = Engine(oracle_abi)
+            o.set_model(model)
+            o.set_rows(block)
+            bad, err = t.replay(oracle_abi, o, actions[c], int(seeds[c]), picks, scores, 64)
+            assert bad == 0 and err <= 1e-5
+            t.assert_same_state(o, single, model)
+        for k in range(model.n_kinds):
+            assert np.array_equal(single.get_assignments(k), chain.get_assignments(k))
+            assert all(np.array_equal(x, y) for x, y in zip(single.get_groups(k), chain.get_groups(k)))
+    assert not np.array_equal(chains[0].get_assignments(0), chains[1].get_assignments(0))
+
+
+# ------------------------------------------------------------------------------------------ loom.tasks.infer: many samples
+def tasks_case(abi, tmp_path, oracle_abi, n_samples=3):
+    from loom_b200 import hyperprior, tasks
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=150, seed=6, tared=True)
+    feature_sizes = [{"type": "dd", "dim": len(f["alphas"])} if f["type"] == "dd" else {"type": f["type"]}
+                     for f in model.features]
+    inits = []
+    for s in range(n_samples):                      # a fresh init per sample (loom/tasks.py:222-226)
+        init = tasks.generate_init(feature_sizes, hyperprior.defaults(), seed=s)
+        path = tmp_path / ("init.%d.pb.gz" % s)
+        pbio.ModelFile.create(init, GRIDS).write(path)
+        inits.append(str(path))
+    assert len({tuple(pbio.ModelFile.read(p).model().f2k.tolist()) for p in inits}) > 1
+    outs = [{"model": str(tmp_path / ("s%d.model.pb.gz" % s)), "groups": str(tmp_path / ("s%d.groups" % s)),
+             "assign": str(tmp_path / ("s%d.assign.pbs.gz" % s))} for s in range(n_samples)]
+    config = {"schedule": {"extra_passes": 2.0, "small_data_size": 50.0}, "kernels": {"kind": {"iterations": 3, "empty_kind_count": 2}}}
+    tasks.infer(paths["rows"], inits, outs, config, tares_in=paths["tares"], abi=abi)
+    seen = []
+    for out in outs:
+        m, a_rowids, a_gids = check_outputs(oracle_abi, block, rowids, out, shuffled=True)
+        seen.append((tuple(a_rowids[:10].tolist()), m.n_kinds))
+    assert len({s[0] for s in seen}) == n_samples       # every sample walked the rows in its own order
+    return outs
+
+
+def test_tasks_infer_many_samples_oracle(tmp_path, oracle_abi):
+    tasks_case(oracle_abi, tmp_path, oracle_abi)
+
+
+@pytest.mark.gpu
+def test_tasks_infer_many_samples_gpu(tmp_path, oracle_abi, cuda_abi):
+    tasks_case(cuda_abi, tmp_path, oracle_abi, n_samples=9)
