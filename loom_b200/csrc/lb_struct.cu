@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "lb_internal.h"
+#include "lb_dpd_hyper.h"
 
 #define FULL 0xffffffffu
 
@@ -726,6 +727,27 @@ extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
             for (int c = 0; c < 4; ++c) e->specs[f].hp[c] = feats[f].hp[c];
         cudaFree(d_flat);
         cudaFree(d_f2k);
+    }
+    // DPD features (src/hyper_kernel.cc:90-181): auxiliary-variable sampler on the host over the
+    // feature's count table (lb_dpd_hyper.h); task id 1 + K + f like every other feature
+    if (!e->hp[5].empty() || !e->hp[6].empty()) {
+        for (int f = 0; f < F; ++f) {
+            lb_feature_spec &s = e->specs[f];
+            if (s.type != LB_DPD || s.dim <= 0) continue;
+            KindHost &kh = e->kinds[e->f2k[f]];
+            int j = -1;
+            for (size_t q = 0; q < kh.fids.size(); ++q) if (kh.fids[q] == f) j = (int)q;
+            if (j < 0 || kh.G <= 0) continue;
+            const size_t G = (size_t)kh.G;
+            std::vector<uint32_t> table((size_t)(s.dim + 1) * G);
+            LB_CUDA(cudaMemcpy2DAsync(table.data(), 4 * G, kh.ints + (size_t)kh.int_off[j] * kh.Gcap, 4 * (size_t)kh.Gcap,
+                                      4 * G, (size_t)s.dim + 1, cudaMemcpyDeviceToHost, e->stream));
+            LB_CUDA(cudaStreamSynchronize(e->stream));
+            const uint64_t task = (uint64_t)(1 + K + f);
+            lb_dpd::hyper(table.data(), s.dim, (int)G, G, s.hp, e->aux.data() + s.aux_off, e->hp[5].data(),
+                          (int)e->hp[5].size(), e->hp[6].data(), (int)e->hp[6].size(),
+                          [&](uint32_t i) { return (double)lb_uniform(seed, 2u, task, i); });
+        }
     }
     e->model_dirty = true;   // derived fields (a_total, ...) and cached scorers depend on the hypers
     LB_TRY(lb_sync_model(e));

@@ -374,9 +374,101 @@ static void grid_coordinate(engine_t *e, kind_t *k, int j, float *coord, const f
     free(scores);
 }
 
-/* HyperKernel::run (src/hyper_kernel.cc:195-235).  DPD hypers are left
- * untouched (its auxiliary-variable sampler, hyper_kernel.cc:90-181, needs
- * distributions' Stirling tables; documented as out of scope in DESIGN.md). */
+/* Gamma(shape, 1) by Marsaglia-Tsang from the task's uniform stream. */
+static double gamma_from_uniforms(double shape, uint64_t seed, uint64_t task, uint32_t *draw) {
+    if (shape < 1.0) {
+        const double u = lo_uniform(seed, 2, task, (*draw)++);
+        return gamma_from_uniforms(shape + 1.0, seed, task, draw) * pow(u, 1.0 / shape);
+    }
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        const double u1 = lo_uniform(seed, 2, task, (*draw)++), u2 = lo_uniform(seed, 2, task, (*draw)++);
+        const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586 * u2);
+        double v = 1.0 + c * z;
+        if (v <= 0) continue;
+        v = v * v * v;
+        const double u = lo_uniform(seed, 2, task, (*draw)++);
+        if (log(1.0 - u) < 0.5 * z * z + d - d * v + d * log(v)) return d * v;
+    }
+}
+
+#define DPD_MIN_BETA 1e-6 /* distributions' DirichletProcessDiscrete::MIN_BETA() is not vendored: stand-in */
+
+/* The DPD branch of infer_feature_hypers_fun (src/hyper_kernel.cc:90-181):
+ *  - auxiliary table counts per value (:101-122).  The reference samples each cell's count m from a
+ *    row of log Stirling numbers, P(m) ~ |s(n,m)| (alpha beta_v)^m; the number of tables of a CRP with
+ *    concentration alpha beta_v after n customers has exactly that law and needs no table:
+ *    m = 1 + sum_{i=1}^{n-1} Bernoulli(a / (a + i));
+ *  - only when every dictionary value is observed (:124): gamma by grid Gibbs on
+ *    V log gamma + lgamma(gamma) - lgamma(gamma + sum aux) (:127-141); betas, beta0 ~
+ *    Dirichlet(aux, gamma) floored at MIN_BETA (:143-167); alpha by grid Gibbs on the data score of
+ *    every group (:169-176).  The last two only when the alpha grid is non-empty, as in the reference. */
+static void dpd_hyper(engine_t *e, kind_t *k, int j, lb_feature_spec *s, uint64_t seed, uint64_t task) {
+    const int dim = s->dim, G = k->G;
+    const size_t st = k->Gcap;
+    const uint32_t *tab = k->ints + (size_t)k->int_off[j] * st;
+    float *betas = e->aux + s->aux_off;
+    uint32_t draw = 0;
+    if (dim <= 0) return;
+    uint64_t *aux = calloc(dim, sizeof(uint64_t));
+    for (int g = 0; g < G; ++g)
+        for (int v = 0; v < dim; ++v) {
+            const uint32_t n = tab[(size_t)v * st + g];
+            if (!n) continue;
+            const double a = (double)s->hp[1] * (double)betas[v];
+            uint64_t m = 1;
+            for (uint32_t i = 1; i < n; ++i)
+                if (lo_uniform(seed, 2, task, draw++) * (a + (double)i) < a) ++m;
+            aux[v] += m;
+        }
+    int seen = 0;
+    uint64_t aux_total = 0;
+    for (int v = 0; v < dim; ++v) { seen += aux[v] > 0; aux_total += aux[v]; }
+    if (seen == dim) {
+        if (e->hp.n_dpd_gamma > 0) {
+            const int n = e->hp.n_dpd_gamma;
+            double *scores = calloc(n, sizeof(double));
+            for (int i = 0; i < n; ++i) {
+                const double gm = e->hp.dpd_gamma[i];
+                scores[i] = dim * log(gm) + lgamma(gm) - lgamma(gm + (double)aux_total);
+            }
+            s->hp[0] = e->hp.dpd_gamma[om_sample_from_scores(lo_uniform(seed, 2, task, draw++), scores, n)];
+            free(scores);
+        }
+        if (e->hp.n_dpd_alpha > 0) {
+            double *x = calloc(dim + 1, sizeof(double)), total = 0, floored = 0;
+            for (int i = 0; i <= dim; ++i) {
+                x[i] = gamma_from_uniforms(i < dim ? (double)aux[i] : (double)s->hp[0], seed, task, &draw);
+                total += x[i];
+            }
+            for (int i = 0; i <= dim; ++i) { x[i] = fmax(x[i] / total, DPD_MIN_BETA); floored += x[i]; }
+            for (int v = 0; v < dim; ++v) betas[v] = (float)(x[v] / floored);
+            s->hp[2] = (float)(x[dim] / floored);
+            free(x);
+            const int n = e->hp.n_dpd_alpha;
+            double *scores = calloc(n, sizeof(double));
+            for (int i = 0; i < n; ++i) {
+                const double al = e->hp.dpd_alpha[i];
+                double sc = 0;
+                for (int g = 0; g < G; ++g) {
+                    const uint32_t total_g = tab[(size_t)dim * st + g];
+                    if (!total_g) continue;
+                    for (int v = 0; v < dim; ++v) {
+                        const uint32_t c = tab[(size_t)v * st + g];
+                        if (c) sc += lgamma(al * (double)betas[v] + (double)c) - lgamma(al * (double)betas[v]);
+                    }
+                    sc += lgamma(al) - lgamma(al + (double)total_g);
+                }
+                scores[i] = sc;
+            }
+            s->hp[1] = e->hp.dpd_alpha[om_sample_from_scores(lo_uniform(seed, 2, task, draw++), scores, n)];
+            free(scores);
+        }
+    }
+    free(aux);
+}
+
+/* HyperKernel::run (src/hyper_kernel.cc:195-235). */
 int lo_hyper_run(lb_handle h, uint64_t seed) {
     engine_t *e = h;
     const int K = e->K, F = e->F;
@@ -423,6 +515,9 @@ int lo_hyper_run(lb_handle h, uint64_t seed) {
                 grid_coordinate(e, k, j, &s->hp[1], e->hp.nich_kappa, e->hp.n_nich_kappa, seed, task, &draw);
                 grid_coordinate(e, k, j, &s->hp[2], e->hp.nich_sigmasq, e->hp.n_nich_sigmasq, seed, task, &draw);
                 grid_coordinate(e, k, j, &s->hp[3], e->hp.nich_nu, e->hp.n_nich_nu, seed, task, &draw);
+                break;
+            case LB_DPD:
+                dpd_hyper(e, k, j, s, seed, (uint64_t)task);
                 break;
             default:
                 break;

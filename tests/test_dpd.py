@@ -1,0 +1,164 @@
+"""DirichletProcessDiscrete: the hyper-parameter sampler (src/hyper_kernel.cc:90-181) and the
+dictionary built at ingest.
+
+The product's sampler is host code inside libloomb200.so (loom_b200/csrc/lb_dpd_hyper.h, called by
+lb_hyper_run after it downloads the feature's count table); here it is compiled for the CPU through
+tests/dpd_hyper_shim.cc and compared with the oracle's independent C restatement on the same
+tables and the same Philox draws.  Statistical checks pin both to the model: the auxiliary table
+counts follow the Antoniak law, the resampled betas follow the counts."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from loom_b200 import Engine, _abi, synth, sweep_actions
+from loom_b200.engine import Model
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory, oracle_abi):
+    so = tmp_path_factory.mktemp("shim") / "libdpd_hyper_shim.so"
+    oracle_dir = os.path.join(REPO, "oracle")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall",
+                           os.path.join(REPO, "tests", "dpd_hyper_shim.cc"), "-o", str(so),
+                           "-L" + oracle_dir, "-lloom_oracle", "-Wl,-rpath," + oracle_dir])
+    lib = C.CDLL(str(so))
+    lib.dpd_hyper_shim.restype = C.c_uint32
+    lib.dpd_hyper_shim.argtypes = [_abi._u32p, C.c_int, C.c_int, C.c_uint64, _abi._f32p, _abi._f32p, _abi._f32p, C.c_int,
+                                   _abi._f32p, C.c_int, C.c_uint64, C.c_uint64]
+    return lib
+
+
+GRIDS = {"dpd": {"gamma": [0.25, 1.0, 4.0, 16.0], "alpha": [0.5, 2.0, 8.0, 32.0]}}
+
+
+def dpd_engine(oracle_abi, n_rows=400, dims=(5, 9), seed=0):
+    types = [("bb", 2)] + [("dpd%d" % d, 1) for d in dims] + [("nich", 1)]
+    model, rows, _ = synth.generate(n_rows, types, density=0.9, seed=seed)
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    e.cat_sweep(sweep_actions(n_rows), seed=seed + 1)
+    return model, rows, e
+
+
+def feature_table(e, model, f):
+    k = int(model.f2k[f])
+    counts, ints, _ = e.get_groups(k)
+    off = sum(Model.int_rows(model.features[g]) for g in model.kind_features(k) if g < f)
+    dim = len(model.features[f]["betas"])
+    return np.ascontiguousarray(ints[off:off + dim + 1]), dim
+
+
+def run_shim(shim, table, dim, hp, betas, seed, task, grids=GRIDS):
+    hp = np.asarray(hp, np.float32).copy()
+    betas = np.asarray(betas, np.float32).copy()
+    gg = np.asarray(grids["dpd"].get("gamma", []), np.float32)
+    ag = np.asarray(grids["dpd"].get("alpha", []), np.float32)
+    draws = shim.dpd_hyper_shim(_abi.ptr(table, _abi._u32p), dim, table.shape[1], table.shape[1], _abi.ptr(hp, _abi._f32p),
+                                _abi.ptr(betas, _abi._f32p), _abi.ptr(gg, _abi._f32p) if len(gg) else None, len(gg),
+                                _abi.ptr(ag, _abi._f32p) if len(ag) else None, len(ag), seed, task)
+    return hp, betas, draws
+
+
+def test_product_sampler_equals_oracle_draw_for_draw(oracle_abi, shim):
+    model, rows, e = dpd_engine(oracle_abi)
+    dpd = [f for f, ft in enumerate(model.features) if ft["type"] == "dpd"]
+    e.set_hyper_prior(GRIDS)
+    moved = 0
+    for seed in range(6):
+        K = e.n_kinds()
+        before_specs, before_aux, _, _ = e.get_hypers()
+        before = {f: ([before_specs[f].hp[i] for i in range(3)],
+                      before_aux[before_specs[f].aux_off:before_specs[f].aux_off + before_specs[f].dim].copy()) for f in dpd}
+        tables = {f: feature_table(e, model, f) for f in dpd}
+        e.hyper_run(seed=100 + seed)
+        specs, aux, _, _ = e.get_hypers()
+        for f in dpd:
+            table, dim = tables[f]
+            hp, betas, draws = run_shim(shim, table, dim, before[f][0], before[f][1], 100 + seed, 1 + K + f)
+            got_hp = [specs[f].hp[i] for i in range(3)]
+            assert got_hp[0] == hp[0] and got_hp[1] == hp[1]                  # the same grid points
+            assert np.allclose(aux[specs[f].aux_off:specs[f].aux_off + dim], betas, rtol=1e-6, atol=1e-9)
+            assert abs(got_hp[2] - hp[2]) <= 1e-6
+            assert draws > table[:dim].sum() - np.count_nonzero(table[:dim])   # one Bernoulli per customer after the first
+            assert abs(betas.sum() + hp[2] - 1.0) < 1e-5 and (betas > 0).all()
+            moved += (got_hp[0] != before[f][0][0]) + (got_hp[1] != before[f][0][1])
+    assert moved >= 3           # the sampler does move gamma / alpha over a few sweeps
+
+
+def test_unobserved_value_freezes_the_hypers(oracle_abi, shim):
+    """hyper_kernel.cc:124: only infer when every dictionary value has been observed"""
+    table = np.zeros((4, 3), np.uint32)            # dim 3, 3 groups; value 2 never observed
+    table[0] = [5, 0, 2]
+    table[1] = [1, 7, 0]
+    table[3] = table[:3].sum(axis=0)
+    hp, betas, draws = run_shim(shim, table, 3, [1.0, 2.0, 0.25], [0.25, 0.25, 0.25], 1, 9)
+    assert hp.tolist() == [1.0, 2.0, 0.25] and betas.tolist() == [0.25, 0.25, 0.25]
+    assert draws == (5 - 1) + (2 - 1) + (7 - 1)    # the auxiliary draws still happen, as in the reference
+
+
+def test_auxiliary_counts_follow_the_antoniak_law(shim):
+    """one cell of n customers, concentration a: E[m] = sum_i a / (a + i).  Read m off the gamma score: with a
+    one-point alpha grid and V = 1 the sampler is deterministic given m, so recover the law from many seeds
+    through the betas' expectation instead: E[beta_1] = E[m / (m + gamma)] under Dirichlet(m, gamma)."""
+    n, a_alpha, beta = 40, 2.0, 0.5
+    a = a_alpha * beta
+    table = np.asarray([[n], [n]], np.uint32)
+    grids = {"dpd": {"gamma": [3.0], "alpha": [a_alpha]}}
+    got = []
+    for seed in range(3000):
+        hp, betas, _ = run_shim(shim, table, 1, [3.0, a_alpha, 1 - beta], [beta], seed, 7, grids)
+        got.append(betas[0])
+    # exact expectation: sum_m P(m) m / (m + gamma), P(m) from the CRP recursion
+    p = np.zeros(n + 1)
+    p[1] = 1.0
+    for i in range(1, n):
+        q = a / (a + i)
+        p[1:] = p[1:] * (1 - q) + p[:-1] * q
+    want = sum(p[m] * m / (m + 3.0) for m in range(1, n + 1))
+    assert abs(np.mean(got) - want) < 4 * np.std(got) / np.sqrt(len(got))
+
+
+def test_hyper_kernel_leaves_the_posterior_invariant(oracle_abi):
+    """a long alternation of cat sweeps and hyper runs keeps betas a distribution and the score finite"""
+    model, rows, e = dpd_engine(oracle_abi, n_rows=150, dims=(4,), seed=2)
+    e.set_hyper_prior(dict(GRIDS, clustering=[(1.0, 0.1), (4.0, 0.2)]))
+    acts = sweep_actions(150, add=True, remove=True)
+    for it in range(10):
+        e.cat_sweep(acts, seed=50 + it)
+        e.hyper_run(seed=80 + it)
+        specs, aux, _, _ = e.get_hypers()
+        f = [i for i, ft in enumerate(model.features) if ft["type"] == "dpd"][0]
+        betas = aux[specs[f].aux_off:specs[f].aux_off + specs[f].dim]
+        assert abs(betas.sum() + specs[f].hp[2] - 1) < 1e-5 and (betas > 0).all()
+        assert np.isfinite(e.score_data())
+
+
+@pytest.mark.gpu
+def test_hyper_run_with_dpd_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
+    model, rows, o = dpd_engine(oracle_abi)
+    g = Engine(cuda_abi)
+    g.set_model(model)
+    g.set_rows(rows)
+    for k in range(model.n_kinds):              # the oracle's state, so both start from the same tables
+        counts, ints, flts = o.get_groups(k)
+        n = int(np.count_nonzero(counts))
+        g.set_groups(k, n, counts[:n], ints[:, :n], flts[:, :n])
+        g.set_assignments(k, o.get_assignments(k))
+    grids = dict(GRIDS, bb={"alpha": [0.5, 2.0], "beta": [0.5, 2.0]})
+    o.set_hyper_prior(grids)
+    g.set_hyper_prior(grids)
+    for seed in (1, 2, 3):
+        o.hyper_run(seed=seed)
+        g.hyper_run(seed=seed)
+        so, ao, _, _ = o.get_hypers()
+        sg, ag, _, _ = g.get_hypers()
+        for f in range(model.n_features):
+            assert [so[f].hp[i] for i in range(2)] == [sg[f].hp[i] for i in range(2)], f
+        assert np.allclose(ao, ag, rtol=1e-5, atol=1e-8)
+        assert g.score_data() == pytest.approx(o.score_data(), rel=1e-5)
