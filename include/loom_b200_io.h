@@ -135,6 +135,22 @@ typedef struct {
 int lbio_rows_read(const char *path, const lbio_model *m, uint64_t first_row, uint64_t max_rows,
                    int32_t n_threads, lbio_row_block *out);
 void lbio_rows_free(lbio_row_block *b);
+
+/* The same with OPEN dictionaries: a DirichletProcessDiscrete value that the model's dictionary does
+ * not hold is appended to it in order of first appearance in the stream, and its beta is drawn by
+ * stick breaking, beta_v = beta0 * Beta(1, gamma), beta0 -= beta_v -- what distributions'
+ * DPD Shared.add_value does when inference first meets a value (loom's init models
+ * start with EMPTY dictionaries, loom/generate.py:103-107).  Here every value of the file is
+ * materialised at ingest, so the engine's DPD tables have a fixed shape; the end state (all rows
+ * assigned) has the same law.  A DPD feature no row observes gets the single value 0 so that no
+ * feature has an empty table.  Draws: Philox stream 4, counter a = feature id, b = draw index.
+ * The model object is MODIFIED: fetch lbio_model_get again afterwards.  *n_new = values appended. */
+int lbio_rows_read_open(const char *path, lbio_model *m, uint64_t seed, int32_t n_threads, lbio_row_block *out,
+                        int32_t *n_new);
+/* Give `dst` the dictionary of `src`: values of src that dst lacks are appended in src's order with
+ * dst's own stick-breaking draws (several samples share one decoded row block but have their own
+ * hypers).  Fails unless dst's dictionary is then identical to src's. */
+int lbio_model_adopt_dictionaries(lbio_model *dst, const lbio_model *src, uint64_t seed);
 /* InFile::stream_stats (src/protobuf_stream.hpp:156-184) */
 int lbio_stream_stats(const char *path, uint64_t *message_count, uint32_t *max_message_size);
 /* the inverse, for tests / generators: rows as Row messages, dense rows as diff{pos = row, neg = NONE} */

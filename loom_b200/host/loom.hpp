@@ -56,9 +56,9 @@ public:
         LOOM_B200_IO(lbio_model_read(model_in, &model_file_));
         LOOM_B200_IO(lbio_model_get(model_file_, &view_));
         if (config_.cat_empty_group_count < 1) LOOM_B200_ERROR("expected 0 < empty_group_count");
-        cross_cat_.model_load(view_.n_features, view_.specs, view_.aux, view_.n_aux, view_.n_kinds,
-                              view_.featureid_to_kindid, view_.kind_py, view_.topology_py,
-                              (int)config_.cat_empty_group_count);
+        // A model with DirichletProcessDiscrete features is installed by rows_load, once the rows have
+        // completed its dictionaries (loom's init models start with empty ones, loom/generate.py:103-107).
+        if (!view_.n_dpd) model_install();
         const int F = view_.n_features;
         tare_observed_.assign(F, 0);
         tare_values_.assign(F, 0);
@@ -238,9 +238,22 @@ private:
     // The unzip / parse / split stages (src/cat_pipeline.cc:63-87) as one decode + one upload; then
     // CrossCat::mixture_load (src/cross_cat.cc:148-196) and the StreamInterval cursors
     // (src/stream_interval.hpp:66-80, 98-135).
+    void model_install() {
+        cross_cat_.model_load(view_.n_features, view_.specs, view_.aux, view_.n_aux, view_.n_kinds,
+                              view_.featureid_to_kindid, view_.kind_py, view_.topology_py,
+                              (int)config_.cat_empty_group_count);
+    }
+
     void rows_load(const char *rows_in) {
         lbio_row_block rows;
-        LOOM_B200_IO(lbio_rows_read(rows_in, model_file_, 0, 0, 0, &rows));
+        if (view_.n_dpd) {   // DPD Shared.add_value for every value of the stream, then the model goes to the device
+            int32_t n_new = 0;
+            LOOM_B200_IO(lbio_rows_read_open(rows_in, model_file_, config_.seed, 0, &rows, &n_new));
+            LOOM_B200_IO(lbio_model_get(model_file_, &view_));
+            model_install();
+        } else {
+            LOOM_B200_IO(lbio_rows_read(rows_in, model_file_, 0, 0, 0, &rows));
+        }
         if (!rows.n_rows) LOOM_B200_ERROR("stream is empty");
         rowids_.assign(rows.rowids, rows.rowids + rows.n_rows);
         LOOM_B200_CHECK(LB_NAME(set_rows_diff)(h(), rows.n_rows, tare_observed_.data(), tare_values_.data(),

@@ -6,6 +6,7 @@
 #include "../../include/loom_b200_io.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 #include <string>
 #include <sys/time.h>
 #include <sys/resource.h>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -655,8 +657,10 @@ enum { SP_NONE = 0, SP_SPARSE = 1, SP_DENSE = 2, SP_ALL = 3 };   // ProductValue
 
 // Decodes one ProductValue; appends (feature, raw value) in ascending feature order.
 // `values` may be null (only the observed positions are wanted).  Returns an error text or null.
+// With `misses` set, a DPD value missing from the dictionary is not an error: its RAW value is stored and
+// the index of the cell within `values` is recorded for the caller to resolve (open dictionaries).
 static const char *decode_value(Reader r, const lbio_model &m, ValueScratch &t, std::vector<uint32_t> &features,
-                                std::vector<uint32_t> *values) {
+                                std::vector<uint32_t> *values, std::vector<uint64_t> *misses = nullptr) {
     t.dense.clear(); t.booleans.clear(); t.sparse.clear(); t.counts.clear(); t.reals.clear();
     int sparsity = -1;
     uint32_t f, wt;
@@ -693,8 +697,9 @@ static const char *decode_value(Reader r, const lbio_model &m, ValueScratch &t, 
             } else if (s.type == LB_DPD) {
                 const auto &lk = m.dpd_lookup[m.dpd_ordinal[p]];
                 auto it = std::lower_bound(lk.begin(), lk.end(), std::make_pair(raw, 0u));
-                if (it == lk.end() || it->first != raw) { err = "DirichletProcessDiscrete value is not in the model's dictionary"; return; }
-                raw = it->second;
+                if (it != lk.end() && it->first == raw) raw = it->second;
+                else if (misses && values) misses->push_back(values->size());
+                else { err = "DirichletProcessDiscrete value is not in the model's dictionary"; return; }
             }
         } else {
             if (ir >= t.reals.size()) { err = "fewer reals than observed nich features"; return; }
@@ -742,13 +747,14 @@ struct RowChunk {           // one thread's share of a batch
     std::vector<uint64_t> rowids;
     std::vector<uint8_t> has_tare;
     std::vector<uint32_t> pos_count, neg_count, pos_feature, pos_value, neg_feature;
+    std::vector<uint64_t> misses;     // open dictionaries: cells of pos_value still holding a raw DPD value
     std::string error;
-    void clear() { rowids.clear(); has_tare.clear(); pos_count.clear(); neg_count.clear(); pos_feature.clear(); pos_value.clear(); neg_feature.clear(); error.clear(); }
+    void clear() { rowids.clear(); has_tare.clear(); pos_count.clear(); neg_count.clear(); pos_feature.clear(); pos_value.clear(); neg_feature.clear(); misses.clear(); error.clear(); }
 };
 
 // Row :153-156, ProductValue.Diff :87-91
 static void decode_rows(const lbio_model &m, const uint8_t *pool, const uint64_t *offsets, size_t begin, size_t end,
-                        RowChunk &out) {
+                        RowChunk &out, bool open_dictionaries) {
     ValueScratch scratch;
     std::vector<uint32_t> tares;
     for (size_t i = begin; i < end; ++i) {
@@ -766,7 +772,9 @@ static void decode_rows(const lbio_model &m, const uint8_t *pool, const uint64_t
                 Reader d = r.sub();
                 tares.clear();
                 while (!err && d.next(f, wt)) {
-                    if (f == 1 && wt == pbw::BYTES) err = decode_value(d.sub(), m, scratch, out.pos_feature, &out.pos_value);
+                    if (f == 1 && wt == pbw::BYTES)
+                        err = decode_value(d.sub(), m, scratch, out.pos_feature, &out.pos_value,
+                                           open_dictionaries ? &out.misses : nullptr);
                     else if (f == 2 && wt == pbw::BYTES) err = decode_value(d.sub(), m, scratch, out.neg_feature, nullptr);
                     else if (f == 3) d.rep_varint(wt, tares);
                     else d.skip(wt);
@@ -804,9 +812,12 @@ static void publish_rows(RowsOwner *o, lbio_row_block *out) {
     out->owner = o;
 }
 
-extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t first_row, uint64_t max_rows,
-                              int32_t n_threads, lbio_row_block *out) {
+// `fresh` (open dictionaries): per DPD feature, the values met that the dictionary lacks, in stream order
+static int rows_read_impl(const char *path, const lbio_model *m, uint64_t first_row, uint64_t max_rows,
+                          int32_t n_threads, lbio_row_block *out, std::vector<std::vector<uint32_t>> *fresh) {
     std::memset(out, 0, sizeof(*out));
+    std::vector<std::unordered_map<uint32_t, uint32_t>> fresh_index(fresh ? m->dpd_lookup.size() : 0);
+    if (fresh) fresh->assign(m->dpd_lookup.size(), {});
     pbw::InFile file(path);
     if (!file.is_open()) return fail("failed to open input file %s", path);
     bool bad = false;
@@ -858,7 +869,7 @@ extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t fi
 #pragma omp parallel for num_threads(used) schedule(static, 1)
         for (int t = 0; t < used; ++t) {
             chunks[t].clear();
-            decode_rows(*m, b.pool.data(), b.offsets.data(), n * t / used, n * (t + 1) / used, chunks[t]);
+            decode_rows(*m, b.pool.data(), b.offsets.data(), n * t / used, n * (t + 1) / used, chunks[t], fresh != nullptr);
         }
         std::string error;
         for (int t = 0; t < used && error.empty(); ++t) {
@@ -868,8 +879,20 @@ extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t fi
             o->has_tare.insert(o->has_tare.end(), c.has_tare.begin(), c.has_tare.end());
             for (uint32_t k : c.pos_count) o->pos_ptr.push_back(o->pos_ptr.back() + k);
             for (uint32_t k : c.neg_count) o->neg_ptr.push_back(o->neg_ptr.back() + k);
+            const size_t at = o->pos_value.size();
             o->pos_feature.insert(o->pos_feature.end(), c.pos_feature.begin(), c.pos_feature.end());
             o->pos_value.insert(o->pos_value.end(), c.pos_value.begin(), c.pos_value.end());
+            for (uint64_t idx : c.misses) {      // serial and in row order: first appearance decides the index
+                const int ord = m->dpd_ordinal[c.pos_feature[idx]];
+                const uint32_t raw = c.pos_value[idx];
+                auto found = fresh_index[ord].find(raw);
+                if (found == fresh_index[ord].end()) {
+                    const uint32_t index = (uint32_t)(m->dpd_lookup[ord].size() + (*fresh)[ord].size());
+                    (*fresh)[ord].push_back(raw);
+                    found = fresh_index[ord].emplace(raw, index).first;
+                }
+                o->pos_value[at + idx] = found->second;
+            }
             o->neg_feature.insert(o->neg_feature.end(), c.neg_feature.begin(), c.neg_feature.end());
         }
         ahead.get();
@@ -877,6 +900,101 @@ extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t fi
     }
     publish_rows(o, out);
     out->stream_rows = at_end ? file.position() : 0;
+    return 0;
+}
+
+extern "C" int lbio_rows_read(const char *path, const lbio_model *m, uint64_t first_row, uint64_t max_rows,
+                              int32_t n_threads, lbio_row_block *out) {
+    return rows_read_impl(path, m, first_row, max_rows, n_threads, out, nullptr);
+}
+
+// Philox4x32-10 (Salmon et al. 2011), the generator of include/loom_b200.h; u = (x0 >> 8) * 2^-24
+static double philox_uniform(uint64_t seed, uint32_t stream, uint64_t a, uint32_t b) {
+    uint32_t c0 = (uint32_t)a, c1 = (uint32_t)(a >> 32), c2 = b, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return (double)(c0 >> 8) * (1.0 / 16777216.0);
+}
+
+#define LBIO_DPD_MIN_BETA 1e-6   // distributions' DirichletProcessDiscrete::MIN_BETA() is not vendored: stand-in
+
+// Append values to DPD dictionaries; each new value takes beta_v = beta0 * Beta(1, gamma) off the stick
+// (distributions DPD Shared.add_value).  Beta(1, gamma) by inverse CDF: 1 - (1 - u)^(1 / gamma).
+static int model_extend(lbio_model *m, const std::vector<std::vector<uint32_t>> &fresh, uint64_t seed) {
+    const int F = (int)m->specs.size();
+    std::vector<float> aux;
+    std::vector<uint32_t> values;
+    std::vector<uint64_t> counts;
+    std::vector<int32_t> offsets(1, 0);
+    for (int f = 0; f < F; ++f) {
+        lb_feature_spec &s = m->specs[f];
+        if (s.type != LB_DD && s.type != LB_DPD) continue;
+        const int old_off = s.aux_off;
+        s.aux_off = (int32_t)aux.size();
+        aux.insert(aux.end(), m->aux.begin() + old_off, m->aux.begin() + old_off + s.dim);
+        if (s.type != LB_DPD) continue;
+        const int ord = m->dpd_ordinal[f], at = m->dpd_offsets[ord];
+        values.insert(values.end(), m->dpd_values.begin() + at, m->dpd_values.begin() + at + s.dim);
+        counts.insert(counts.end(), m->dpd_counts.begin() + at, m->dpd_counts.begin() + at + s.dim);
+        double beta0 = s.hp[2];
+        const double gamma = s.hp[0] > 0 ? s.hp[0] : 1.0;
+        uint32_t draw = 0;
+        for (uint32_t v : fresh[ord]) {
+            const double u = philox_uniform(seed, 4u, (uint64_t)f, draw++);
+            const double beta = std::max(beta0 * (1.0 - std::pow(1.0 - u, 1.0 / gamma)), (double)LBIO_DPD_MIN_BETA);
+            beta0 = std::max(beta0 - beta, (double)LBIO_DPD_MIN_BETA);
+            aux.push_back((float)beta);
+            values.push_back(v);
+            counts.push_back(0);
+        }
+        s.dim += (int32_t)fresh[ord].size();
+        s.hp[2] = (float)beta0;
+        offsets.push_back((int32_t)values.size());
+    }
+    m->aux.swap(aux);
+    m->dpd_values.swap(values);
+    m->dpd_counts.swap(counts);
+    m->dpd_offsets.swap(offsets);
+    return model_finish(m);
+}
+
+extern "C" int lbio_rows_read_open(const char *path, lbio_model *m, uint64_t seed, int32_t n_threads, lbio_row_block *out,
+                                   int32_t *n_new) {
+    std::vector<std::vector<uint32_t>> fresh;
+    if (rows_read_impl(path, m, 0, 0, n_threads, out, &fresh)) return 1;
+    int32_t appended = 0;
+    for (size_t f = 0; f < m->specs.size(); ++f) {      // no feature keeps an empty table
+        const int ord = m->dpd_ordinal[f];
+        if (ord >= 0 && m->specs[f].dim == 0 && fresh[ord].empty()) fresh[ord].push_back(0);
+    }
+    for (const auto &list : fresh) appended += (int32_t)list.size();
+    if (appended && model_extend(m, fresh, seed)) { lbio_rows_free(out); return 1; }
+    if (n_new) *n_new = appended;
+    return 0;
+}
+
+extern "C" int lbio_model_adopt_dictionaries(lbio_model *dst, const lbio_model *src, uint64_t seed) {
+    if (dst->specs.size() != src->specs.size() || dst->dpd_lookup.size() != src->dpd_lookup.size())
+        return fail("adopt_dictionaries: the models have different schemas");
+    std::vector<std::vector<uint32_t>> fresh(src->dpd_lookup.size());
+    for (size_t ord = 0; ord < fresh.size(); ++ord) {
+        const int a = src->dpd_offsets[ord], b = src->dpd_offsets[ord + 1];
+        const auto &have = dst->dpd_lookup[ord];
+        for (int i = a; i < b; ++i) {
+            const uint32_t v = src->dpd_values[i];
+            auto it = std::lower_bound(have.begin(), have.end(), std::make_pair(v, 0u));
+            if (it == have.end() || it->first != v) fresh[ord].push_back(v);
+        }
+    }
+    if (model_extend(dst, fresh, seed)) return 1;
+    if (dst->dpd_values != src->dpd_values || dst->dpd_offsets != src->dpd_offsets)
+        return fail("adopt_dictionaries: the dictionaries differ in more than missing values");
     return 0;
 }
 

@@ -114,6 +114,8 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "model_free": (None, [_model]),
     "rows_read": (C.c_int, [_cs, _model, C.c_uint64, C.c_uint64, C.c_int32, _P(RowBlockView)]),
     "rows_free": (None, [_P(RowBlockView)]),
+    "rows_read_open": (C.c_int, [_cs, _model, C.c_uint64, C.c_int32, _P(RowBlockView), _i32p]),
+    "model_adopt_dictionaries": (C.c_int, [_model, _model, C.c_uint64]),
     "stream_stats": (C.c_int, [_cs, _u64p, _u32p]),
     "rows_write": (C.c_int, [_cs, _model, _P(RowBlockView)]),
     "rows_to_columns": (C.c_int, [_model, _P(RowBlockView), _u8p, _u32p, _u8p, _u32p, _u32p]),
@@ -201,9 +203,18 @@ class ModelFile:
 
     def __init__(self, handle):
         self.h = handle
+        self.refresh()
+
+    def refresh(self):
+        """re-fetch the view (after the dictionaries grew)"""
         v = ModelView()
         _check(lib().lbio_model_get(self.h, C.byref(v)))
         self.view = v
+
+    def adopt_dictionaries(self, other, seed):
+        """take `other`'s DPD dictionaries; missing values get this model's own stick-breaking betas"""
+        _check(lib().lbio_model_adopt_dictionaries(self.h, other.h, seed))
+        self.refresh()
 
     def __del__(self):
         try:
@@ -371,9 +382,16 @@ class Rows:
         return cat8, wide, mask
 
 
-def rows_read(path, model_file, first_row=0, max_rows=0, n_threads=0):
+def rows_read(path, model_file, first_row=0, max_rows=0, n_threads=0, open_dictionaries=False, seed=0):
+    """open_dictionaries: DPD values the model's dictionary lacks are appended to it (with stick-breaking
+    betas drawn from `seed`) instead of being an error -- `model_file` is modified; whole file only."""
     v = RowBlockView()
-    _check(lib().lbio_rows_read(_path(path), model_file.h, first_row, max_rows, n_threads, C.byref(v)))
+    if open_dictionaries:
+        n_new = C.c_int32()
+        _check(lib().lbio_rows_read_open(_path(path), model_file.h, seed, n_threads, C.byref(v), C.byref(n_new)))
+        model_file.refresh()
+    else:
+        _check(lib().lbio_rows_read(_path(path), model_file.h, first_row, max_rows, n_threads, C.byref(v)))
     try:
         R = v.n_rows
         pos_ptr = _arr(v.pos_ptr, R + 1, np.uint64)

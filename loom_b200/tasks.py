@@ -112,7 +112,11 @@ def infer(rows_in, model_in, samples_out, config=None, tares_in=None, seeds=None
         config = pbio.config_read(config).as_dict()
     model_paths = [model_in] * n if isinstance(model_in, (str, os.PathLike)) else list(model_in)
     files = [pbio.ModelFile.read(p) for p in model_paths]
-    rows = pbio.rows_read(rows_in, files[0])
+    # DPD dictionaries are completed from the rows (loom's init models start with empty ones); every
+    # sample then adopts the same value order, with betas broken off its own stick
+    rows = pbio.rows_read(rows_in, files[0], open_dictionaries=True, seed=seeds[0])
+    for c in range(1, n):
+        files[c].adopt_dictionaries(files[0], seeds[c])
     tare = (None, None)
     if tares_in:
         tare_observed, tare_values, _ = pbio.tares_read(tares_in, files[0])

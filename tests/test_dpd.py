@@ -162,3 +162,108 @@ def test_hyper_run_with_dpd_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
             assert [so[f].hp[i] for i in range(2)] == [sg[f].hp[i] for i in range(2)], f
         assert np.allclose(ao, ag, rtol=1e-5, atol=1e-8)
         assert g.score_data() == pytest.approx(o.score_data(), rel=1e-5)
+
+
+# ------------------------------------------------------------------------------------------ dictionaries at ingest
+def empty_dpd_model(n_dpd=2, gamma=(0.7, 3.0)):
+    feats = [{"type": "bb", "alpha": 0.5, "beta": 0.5}]
+    feats += [{"type": "dpd", "gamma": gamma[i], "alpha": 2.0, "beta0": 1.0, "betas": []} for i in range(n_dpd)]
+    feats += [{"type": "gp", "alpha": 2.0, "inv_beta": 0.5}]
+    return Model(feats, [0] * len(feats))
+
+
+def write_rows(path, mf, table, rowids=None):
+    """table: rows of raw values / None, written through the native writer after a manual CSR build"""
+    from loom_b200 import pbio
+    ptr, feats, vals = [0], [], []
+    for row in table:
+        for f, v in enumerate(row):
+            if v is not None:
+                feats.append(f)
+                vals.append(int(v))
+        ptr.append(len(feats))
+    R = len(table)
+    rows = pbio.Rows(np.arange(R) if rowids is None else rowids, np.zeros(R, np.uint8), ptr, feats, vals,
+                     np.zeros(R + 1, np.uint64), [])
+    return rows
+
+
+def test_open_dictionaries_follow_the_stream(tmp_path, oracle_abi):
+    """loom's init models carry empty DPD dictionaries (loom/generate.py:103-107); values enter in order of
+    first appearance, each taking beta0 * Beta(1, gamma) off the stick (Philox stream 4)"""
+    import pb_schema
+    from loom_b200 import pbio
+    from test_pbio import M, fill_value
+    model = empty_dpd_model()
+    mf = pbio.ModelFile.create(model, None, [[], []])
+    assert [len(d) for d in mf.dpd_values()] == [0, 0]
+    rng = np.random.default_rng(0)
+    raw1 = np.asarray([900, 17, 4000000000, 5, 33])
+    raw2 = np.asarray([1, 0])
+    msgs, table = [], []
+    for r in range(300):
+        row = [int(rng.integers(2)), int(raw1[rng.integers(5)]), int(raw2[rng.integers(2)]), int(rng.poisson(2.0))]
+        if rng.random() < 0.3:
+            row[1] = None
+        table.append(row)
+        msg = M()["Row"]()
+        msg.id = r
+        fill_value(msg.diff.pos, model, {f: v for f, v in enumerate(row) if v is not None}, "auto")
+        msg.diff.neg.observed.sparsity = 0
+        msgs.append(msg)
+    path = tmp_path / "rows.pbs.gz"
+    pb_schema.dump_stream(path, msgs)
+    with pytest.raises(_abi.LoomError, match="dictionary"):
+        pbio.rows_read(path, mf)                                   # closed dictionaries: loud
+    rows = pbio.rows_read(path, mf, open_dictionaries=True, seed=11, n_threads=4)
+    want = [[], []]
+    for row in table:
+        for j, f in enumerate((1, 2)):
+            if row[f] is not None and row[f] not in want[j]:
+                want[j].append(row[f])
+    got = [d.tolist() for d in mf.dpd_values()]
+    assert got == want
+    # cells hold dictionary indices
+    index = [{v: i for i, v in enumerate(d)} for d in got]
+    flat = [(f, (index[f - 1][v] if f in (1, 2) else v)) for row in table for f, v in enumerate(row) if v is not None]
+    assert rows.pos_feature.tolist() == [f for f, _ in flat] and rows.pos_value.tolist() == [v for _, v in flat]
+    # betas: the stick-breaking recursion on the oracle's Philox
+    lo = oracle_abi.lib.lo_uniform
+    lo.restype, lo.argtypes = C.c_double, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32]
+    m2 = mf.model()
+    for j, f in enumerate((1, 2)):
+        gamma, beta0, betas = model.features[f]["gamma"], 1.0, []
+        for d in range(len(got[j])):
+            u = lo(11, 4, f, d)
+            b = max(beta0 * (1.0 - (1.0 - u) ** (1.0 / gamma)), 1e-6)
+            beta0 = max(beta0 - b, 1e-6)
+            betas.append(b)
+        assert np.allclose(m2.features[f]["betas"], betas, rtol=1e-6)
+        assert abs(m2.features[f]["beta0"] - beta0) < 1e-6 and abs(sum(betas) + beta0 - 1) < 1e-5
+    # a second pass finds nothing new and changes nothing
+    before = mf.model().features
+    again = pbio.rows_read(path, mf, open_dictionaries=True, seed=99)
+    assert [d.tolist() for d in mf.dpd_values()] == want and mf.model().features == before
+    assert np.array_equal(again.pos_value, rows.pos_value)
+    # another sample adopts the value order with its own betas
+    other = pbio.ModelFile.create(empty_dpd_model(gamma=(5.0, 0.2)), None, [[], []])
+    other.adopt_dictionaries(mf, seed=12)
+    assert [d.tolist() for d in other.dpd_values()] == want
+    assert not np.allclose(other.model().features[1]["betas"], m2.features[1]["betas"])
+    # the written model is a valid CrossCat message carrying the dictionary
+    mf.write(tmp_path / "model.pb.gz")
+    g = pb_schema.load_message(tmp_path / "model.pb.gz", M()["CrossCat"])
+    assert list(g.kinds[0].product_model.dpd[0].values) == want[0]
+    assert len(g.kinds[0].product_model.dpd[1].betas) == 2
+
+
+def test_unobserved_dpd_feature_gets_one_value(tmp_path):
+    from loom_b200 import pbio
+    model = empty_dpd_model()
+    mf = pbio.ModelFile.create(model, None, [[], []])
+    table = [[1, 7, None, 3], [0, 8, None, 1]]
+    pbio.rows_write(tmp_path / "rows.pbs", pbio.ModelFile.create(
+        Model([dict(f, betas=[0.1] * 9, beta0=0.1) if f["type"] == "dpd" else f for f in model.features],
+              [0] * 4)), write_rows(None, None, table))
+    pbio.rows_read(tmp_path / "rows.pbs", mf, open_dictionaries=True, seed=1)
+    assert [d.tolist() for d in mf.dpd_values()] == [[7, 8], [0]]

@@ -338,3 +338,65 @@ def test_tasks_infer_many_samples_oracle(tmp_path, oracle_abi):
 @pytest.mark.gpu
 def test_tasks_infer_many_samples_gpu(tmp_path, oracle_abi, cuda_abi):
     tasks_case(cuda_abi, tmp_path, oracle_abi, n_samples=9)
+
+
+# ------------------------------------------------------------------------------------------ DPD: open dictionaries
+DPD_TYPES = [("bb", 3), ("dd16", 1), ("dpd6", 2), ("gp", 1), ("nich", 2)]
+
+
+def raw_of(feature, index):
+    """raw value a front end would have given the index-th category of DPD feature `feature`"""
+    return 1000 * feature + 7 * int(index) + 3
+
+
+def dpd_case(exe, tmp_path, oracle_abi, n_rows=250, seed=9):
+    from loom_b200.engine import Model
+    model, block, _ = synth.generate(n_rows, DPD_TYPES, density=0.8, seed=seed)
+    dpd_feats = [f for f, ft in enumerate(model.features) if ft["type"] == "dpd"]
+    # what loom hands over: an init model whose DPD dictionaries are EMPTY, rows holding raw values
+    init = Model([dict(ft, betas=[], beta0=1.0) if ft["type"] == "dpd" else ft for ft in model.features], model.f2k)
+    grids = dict(GRIDS, dpd={"gamma": [0.5, 2.0], "alpha": [0.5, 2.0, 8.0]})
+    pbio.ModelFile.create(init, grids, [[] for _ in dpd_feats]).write(tmp_path / "init.pb.gz")
+    writer_model = pbio.ModelFile.create(model, None, [[raw_of(f, i) for i in range(6)] for f in dpd_feats])
+    rowids = np.arange(n_rows, dtype=np.uint64) + 50
+    pbio.rows_write(tmp_path / "rows.pbs.gz", writer_model, pbio.Rows.from_block(block, rowids))
+    c = pbio.config_defaults()
+    c.seed, c.extra_passes, c.kind_iterations, c.kind_empty_kind_count, c.small_data_size = seed, 2.0, 2, 2, 50.0
+    pbio.config_write(tmp_path / "config.pb.gz", c)
+    paths = {"config": str(tmp_path / "config.pb.gz"), "rows": str(tmp_path / "rows.pbs.gz"), "tares": "--none",
+             "model_in": str(tmp_path / "init.pb.gz")}
+    out = run(exe, paths, tmp_path)
+    # the output model carries the dictionary in order of first appearance; put the block into that numbering
+    mf = pbio.ModelFile.read(out["model"])
+    dicts = [d.tolist() for d in mf.dpd_values()]
+    F8 = model.n8()
+    remapped = RowBlock(block.n_rows, block.cat8, block.wide.copy(), block.mask)
+    obs = block.observed()
+    for j, f in enumerate(dpd_feats):
+        seen = sorted({int(v) for v in block.wide[f - F8][obs[f]]})
+        assert sorted(dicts[j]) == [raw_of(f, i) for i in seen]          # exactly the observed values
+        first = []
+        for v in block.wide[f - F8][obs[f]]:
+            if raw_of(f, v) not in first:
+                first.append(raw_of(f, v))
+        assert dicts[j] == first                                          # in stream order
+        lut = np.zeros(6, np.uint32)
+        for i in seen:
+            lut[i] = dicts[j].index(raw_of(f, i))
+        remapped.wide[f - F8] = np.where(obs[f], lut[block.wide[f - F8]], 0)
+    new_model, _, _ = check_outputs(oracle_abi, remapped, rowids, out)
+    for f in dpd_feats:
+        ft = new_model.features[f]
+        assert abs(sum(ft["betas"]) + ft["beta0"] - 1.0) < 1e-4 and min(ft["betas"]) > 0
+        assert ft["gamma"] in (0.5, 2.0) and ft["alpha"] in (0.5, 2.0, 8.0)   # the DPD hyper kernel ran
+
+
+def test_dpd_features_with_empty_init_dictionaries(tmp_path, infer_on_oracle, oracle_abi):
+    dpd_case(infer_on_oracle, tmp_path, oracle_abi)
+
+
+@pytest.mark.gpu
+def test_dpd_features_with_empty_init_dictionaries_gpu(tmp_path, oracle_abi):
+    import __graft_entry__
+    __graft_entry__.build()
+    dpd_case(os.path.join(HOST, "loom_infer"), tmp_path, oracle_abi)
