@@ -231,6 +231,19 @@ int lbio_log_open(const char *path, int32_t append, lbio_log **out);
 int lbio_log_write(lbio_log *log, const lbio_log_entry *entry);
 void lbio_log_close(lbio_log *log);
 
+/* ------------------------------------------------------------------------- */
+/* Posterior-enumeration samples: a stream of PosteriorEnum.Sample{kinds{featureids, groups{rowids}},
+ * score} (src/schema.proto:326-338; Loom::dump_posterior_enum src/loom.cc:513-546) -- what
+ * loom/test/test_posterior_enum.py reads back.  One call appends one sample:
+ *   kind_feature_ptr [n_kinds + 1] into featureids; kind_group_ptr [n_kinds + 1] into the group list;
+ *   group_row_ptr [n_groups + 1] into rowids. */
+typedef struct lbio_samples lbio_samples;
+int lbio_samples_open(const char *path, lbio_samples **out);
+int lbio_samples_write(lbio_samples *s, int32_t n_kinds, const int32_t *kind_feature_ptr, const uint32_t *featureids,
+                       const int32_t *kind_group_ptr, const uint64_t *group_row_ptr, const uint32_t *rowids,
+                       float score);
+int lbio_samples_close(lbio_samples *s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,6 +228,46 @@ public:
         }
     }
 
+    // Loom::posterior_enum (src/loom.cc:452-511): greedy ADD of every row, then sample_count times
+    // { sample_skip times { REMOVE + ADD every row; [kind kernel]; hyper kernel }; dump the latent
+    // state and its score }.  The protocol of loom/test/test_posterior_enum.py.
+    void posterior_enum(const char *rows_in, const char *samples_out) {
+        const uint32_t sample_count = config_.posterior_enum_sample_count, sample_skip = config_.posterior_enum_sample_skip;
+        if (sample_count < 1) LOOM_B200_ERROR("expected 1 <= sample_count");
+        if (!(sample_skip > 0 || sample_count == 1)) LOOM_B200_ERROR("zero diversity");
+        rows_load(rows_in);
+        const uint64_t R = row_count();
+        SeedStream rng(config_.seed);
+        CatKernel cat_kernel(cross_cat_, rng());
+        std::unique_ptr<HyperKernel> hyper_kernel;
+        if (config_.hyper_run && view_.has_hyper_prior) hyper_kernel.reset(new HyperKernel(cross_cat_, view_.hyper_prior));
+        if (!assigned_count_) {
+            sweep_range(cat_kernel, R);
+            assigned_count_ = R;
+            assigned_pos_ = unassigned_pos_ = 0;
+        }
+        if (assigned_count_ != R) LOOM_B200_ERROR("posterior_enum needs every row assigned or none");
+        lbio_samples *samples = nullptr;
+        LOOM_B200_IO(lbio_samples_open(samples_out, &samples));
+        std::unique_ptr<KindKernel> kind_kernel;
+        if (config_.kind_iterations > 0)
+            kind_kernel.reset(new KindKernel(cross_cat_, (int)config_.kind_empty_kind_count, (int)config_.kind_iterations, rng()));
+        for (uint32_t i = 0; i < sample_count; ++i) {
+            for (uint32_t t = 0; t < sample_skip; ++t) {
+                for (uint64_t r = 0; r < R; ++r) {
+                    cat_kernel.remove_row(r);
+                    cat_kernel.add_row(r);
+                }
+                if (kind_kernel || hyper_kernel) cat_kernel.wait();   // else the whole skip is one action list
+                if (kind_kernel) kind_kernel->try_run();
+                if (hyper_kernel) hyper_kernel->run(rng());
+            }
+            cat_kernel.wait();
+            dump_posterior_enum(samples);
+        }
+        LOOM_B200_IO(lbio_samples_close(samples));
+    }
+
     CrossCat &cross_cat() { return cross_cat_; }
     uint64_t row_count() const { return rowids_.size(); }
     uint64_t assigned_count() const { return assigned_count_; }
@@ -380,6 +420,35 @@ private:
         kind_kernel.reset();   // ~KindKernel drops the ephemeral kinds (src/kind_kernel.cc:75-81)
         log_metrics(checkpoint.tardis_iter, &counters);
         return true;
+    }
+
+    // Loom::dump_posterior_enum (src/loom.cc:513-546): kinds with features, their row partitions, the score
+    void dump_posterior_enum(lbio_samples *samples) {
+        const int K = (int)cross_cat_.kind_count();
+        const uint64_t R = row_count();
+        const std::vector<uint32_t> f2k = cross_cat_.featureid_to_kindid();
+        std::vector<int32_t> kind_feature_ptr(1, 0), kind_group_ptr(1, 0);
+        std::vector<uint32_t> featureids, rowids;
+        std::vector<uint64_t> group_row_ptr(1, 0);
+        for (int k = 0; k < K; ++k) {
+            const size_t before = featureids.size();
+            for (size_t f = 0; f < f2k.size(); ++f)
+                if ((int)f2k[f] == k) featureids.push_back((uint32_t)f);
+            if (featureids.size() == before) continue;        // featureless kinds are not part of the latent state
+            kind_feature_ptr.push_back((int32_t)featureids.size());
+            const std::vector<uint32_t> packed = cross_cat_.groupids(k);
+            std::unordered_map<uint32_t, std::vector<uint32_t>> groups;
+            for (uint64_t r = 0; r < R; ++r)
+                if (packed[r] != LB_UNASSIGNED) groups[packed[r]].push_back((uint32_t)rowids_[r]);
+            for (const auto &g : groups) {
+                rowids.insert(rowids.end(), g.second.begin(), g.second.end());
+                group_row_ptr.push_back(rowids.size());
+            }
+            kind_group_ptr.push_back((int32_t)group_row_ptr.size() - 1);
+        }
+        LOOM_B200_IO(lbio_samples_write(samples, (int32_t)kind_feature_ptr.size() - 1, kind_feature_ptr.data(),
+                                        featureids.data(), kind_group_ptr.data(), group_row_ptr.data(), rowids.data(),
+                                        cross_cat_.score_data()));
     }
 
     struct KernelCounters { uint64_t cat_usec = 0, hyper_usec = 0, kind_usec = 0, kind_total = 0, kind_change = 0; };

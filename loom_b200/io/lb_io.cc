@@ -1465,3 +1465,42 @@ extern "C" void lbio_log_close(lbio_log *log) {
     delete log->file;
     delete log;
 }
+
+// ---------------------------------------------------------------------------------------------
+// PosteriorEnum.Sample (:326-338)
+struct lbio_samples { pbw::OutFile *file; std::string path; };
+
+extern "C" int lbio_samples_open(const char *path, lbio_samples **out) {
+    auto *f = new pbw::OutFile(path);
+    if (!f->is_open()) { delete f; return fail("failed to open output file %s", path); }
+    *out = new lbio_samples{f, path};
+    return 0;
+}
+
+extern "C" int lbio_samples_write(lbio_samples *s, int32_t n_kinds, const int32_t *kind_feature_ptr,
+                                  const uint32_t *featureids, const int32_t *kind_group_ptr,
+                                  const uint64_t *group_row_ptr, const uint32_t *rowids, float score) {
+    Writer w, kind, group;
+    for (int k = 0; k < n_kinds; ++k) {
+        kind.clear();
+        for (int i = kind_feature_ptr[k]; i < kind_feature_ptr[k + 1]; ++i) kind.u64(1, featureids[i]);
+        for (int g = kind_group_ptr[k]; g < kind_group_ptr[k + 1]; ++g) {
+            group.clear();
+            for (uint64_t i = group_row_ptr[g]; i < group_row_ptr[g + 1]; ++i) group.u64(1, rowids[i]);
+            kind.msg(2, group);
+        }
+        w.msg(1, kind);
+    }
+    w.f32(2, score);
+    if (!s->file->write_stream(w.buf)) return fail("failed to write %s", s->path.c_str());
+    return 0;
+}
+
+extern "C" int lbio_samples_close(lbio_samples *s) {
+    if (!s) return 0;
+    const bool ok = s->file->close();
+    const std::string path = s->path;
+    delete s->file;
+    delete s;
+    return ok ? 0 : fail("failed to write %s", path.c_str());
+}

@@ -130,6 +130,9 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_open": (C.c_int, [_cs, C.c_int32, _P(C.c_void_p)]),
     "log_write": (C.c_int, [C.c_void_p, _P(LogEntry)]),
     "log_close": (None, [C.c_void_p]),
+    "samples_open": (C.c_int, [_cs, _P(C.c_void_p)]),
+    "samples_write": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _u32p, _i32p, _u64p, _u32p, C.c_float]),
+    "samples_close": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -400,3 +400,79 @@ def test_dpd_features_with_empty_init_dictionaries_gpu(tmp_path, oracle_abi):
     import __graft_entry__
     __graft_entry__.build()
     dpd_case(os.path.join(HOST, "loom_infer"), tmp_path, oracle_abi)
+
+
+# ------------------------------------------------------------------------------------------ loom_posterior_enum
+def build_on_oracle(tmp_path_factory, source, name):
+    exe = tmp_path_factory.mktemp("bin") / name
+    oracle_dir, io_dir = os.path.join(REPO, "oracle"), os.path.join(REPO, "loom_b200", "io")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-DLB_NAME(x)=lo_##x",
+                           os.path.join(HOST, source), "-o", str(exe), "-L" + oracle_dir, "-lloom_oracle",
+                           "-L" + io_dir, "-lloomb200_io", "-Wl,-rpath," + oracle_dir, "-Wl,-rpath," + io_dir])
+    return str(exe)
+
+
+@pytest.fixture(scope="module")
+def posterior_enum_on_oracle(tmp_path_factory, oracle_abi):
+    return build_on_oracle(tmp_path_factory, "loom_posterior_enum.cc", "loom_posterior_enum_oracle")
+
+
+def posterior_enum_case(exe, d, R, C, feature_type, density, infer_kinds, seed):
+    """loom/test/test_posterior_enum.py through the process: write the files, run the binary, parse the
+    samples stream (parse_sample, :738-745) and return the goodness of fit of the visited latents"""
+    import pe_util
+    rng = np.random.default_rng(1000 + seed)
+    model = pe_util.make_model(C, feature_type)
+    table = pe_util.generate_rows(R, C, feature_type, density, rng)
+    block = RowBlock.from_table(model, table)
+    mf = pbio.ModelFile.create(model)
+    mf.write(d / "model.pb.gz")
+    pbio.rows_write(d / "rows.pbs.gz", mf, pbio.Rows.from_block(block))
+    size = pe_util.LATENT_SIZES[R][C] if infer_kinds else pe_util.LATENT_SIZES[R][1]
+    c = pbio.config_defaults()
+    c.seed, c.posterior_enum_sample_count, c.posterior_enum_sample_skip = seed, 10 * size, 10
+    c.kind_iterations, c.kind_empty_kind_count, c.hyper_run = (32 if infer_kinds else 0), 32, 0
+    pbio.config_write(d / "config.pb.gz", c)
+    out = d / "samples.pbs.gz"
+    proc = subprocess.run([exe, str(d / "config.pb.gz"), str(d / "rows.pbs.gz"), "--none", str(d / "model.pb.gz"),
+                           "--none", "--none", str(out)], capture_output=True, timeout=900)
+    assert proc.returncode == 0, proc.stderr.decode()
+    samples = []
+    for msg in pb_schema.load_stream(out, M()["PosteriorEnum.Sample"]):
+        latent = frozenset((frozenset(k.featureids), frozenset(frozenset(g.rowids) for g in k.groups)) for k in msg.kinds)
+        samples.append((latent, msg.score))
+    assert len(samples) == 10 * size
+    return pe_util.goodness_of_fit(samples, R, C, infer_kinds)
+
+
+@pytest.mark.parametrize("feature_type", ["bb", "nich"])
+def test_posterior_enum_process_cats(tmp_path, posterior_enum_on_oracle, feature_type):
+    import pe_util
+    for i, (R, C) in enumerate([(3, 2), (4, 1)]):
+        d = tmp_path / ("c%d" % i)
+        d.mkdir()
+        gof, info = posterior_enum_case(posterior_enum_on_oracle, d, R, C, feature_type, 0.5, False, seed=i)
+        assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
+
+
+def test_posterior_enum_process_kinds(tmp_path, posterior_enum_on_oracle):
+    import pe_util
+    for i, (R, C) in enumerate([(2, 2), (3, 2)]):
+        d = tmp_path / ("k%d" % i)
+        d.mkdir()
+        gof, info = posterior_enum_case(posterior_enum_on_oracle, d, R, C, "dd", 1.0, True, seed=10 + i)
+        assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
+
+
+@pytest.mark.gpu
+def test_posterior_enum_process_gpu(tmp_path):
+    """loom's chi-square test through the product binary on the device"""
+    import __graft_entry__
+    import pe_util
+    __graft_entry__.build()
+    exe = os.path.join(HOST, "loom_posterior_enum")
+    for i, (R, C, kinds, ftype) in enumerate([(3, 2, False, "gp"), (3, 2, True, "bb")]):
+        d = tmp_path / ("g%d" % i)
+        d.mkdir()
+        gof, info = posterior_enum_case(exe, d, R, C, ftype, 0.5, kinds, seed=20 + i)
+        assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
