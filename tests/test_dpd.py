@@ -139,31 +139,6 @@ def test_hyper_kernel_leaves_the_posterior_invariant(oracle_abi):
         assert np.isfinite(e.score_data())
 
 
-@pytest.mark.gpu
-def test_hyper_run_with_dpd_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
-    model, rows, o = dpd_engine(oracle_abi)
-    g = Engine(cuda_abi)
-    g.set_model(model)
-    g.set_rows(rows)
-    for k in range(model.n_kinds):              # the oracle's state, so both start from the same tables
-        counts, ints, flts = o.get_groups(k)
-        n = int(np.count_nonzero(counts))
-        g.set_groups(k, n, counts[:n], ints[:, :n], flts[:, :n])
-        g.set_assignments(k, o.get_assignments(k))
-    grids = dict(GRIDS, bb={"alpha": [0.5, 2.0], "beta": [0.5, 2.0]})
-    o.set_hyper_prior(grids)
-    g.set_hyper_prior(grids)
-    for seed in (1, 2, 3):
-        o.hyper_run(seed=seed)
-        g.hyper_run(seed=seed)
-        so, ao, _, _ = o.get_hypers()
-        sg, ag, _, _ = g.get_hypers()
-        for f in range(model.n_features):
-            assert [so[f].hp[i] for i in range(2)] == [sg[f].hp[i] for i in range(2)], f
-        assert np.allclose(ao, ag, rtol=1e-5, atol=1e-8)
-        assert g.score_data() == pytest.approx(o.score_data(), rel=1e-5)
-
-
 # ------------------------------------------------------------------------------------------ dictionaries at ingest
 def empty_dpd_model(n_dpd=2, gamma=(0.7, 3.0)):
     feats = [{"type": "bb", "alpha": 0.5, "beta": 0.5}]

@@ -476,3 +476,30 @@ def test_posterior_enum_process_gpu(tmp_path):
         d.mkdir()
         gof, info = posterior_enum_case(exe, d, R, C, ftype, 0.5, kinds, seed=20 + i)
         assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
+
+
+# ------------------------------------------------------------------------------------------ DPD hyper kernel on the device
+@pytest.mark.gpu
+def test_hyper_run_with_dpd_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
+    from test_dpd import GRIDS, dpd_engine
+    model, rows, o = dpd_engine(oracle_abi)
+    g = Engine(cuda_abi)
+    g.set_model(model)
+    g.set_rows(rows)
+    for k in range(model.n_kinds):              # the oracle's state, so both start from the same tables
+        counts, ints, flts = o.get_groups(k)
+        n = int(np.count_nonzero(counts))
+        g.set_groups(k, n, counts[:n], ints[:, :n], flts[:, :n])
+        g.set_assignments(k, o.get_assignments(k))
+    grids = dict(GRIDS, bb={"alpha": [0.5, 2.0], "beta": [0.5, 2.0]})
+    o.set_hyper_prior(grids)
+    g.set_hyper_prior(grids)
+    for seed in (1, 2, 3):
+        o.hyper_run(seed=seed)
+        g.hyper_run(seed=seed)
+        so, ao, _, _ = o.get_hypers()
+        sg, ag, _, _ = g.get_hypers()
+        for f in range(model.n_features):
+            assert [so[f].hp[i] for i in range(2)] == [sg[f].hp[i] for i in range(2)], f
+        assert np.allclose(ao, ag, rtol=1e-5, atol=1e-8)
+        assert g.score_data() == pytest.approx(o.score_data(), rel=1e-5)
