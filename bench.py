@@ -147,6 +147,55 @@ def measure_ingest(abi, model, rows, device=0):
         os.unlink(path)
 
 
+def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeout=180):
+    """The process boundary: `loom_infer` -- the binary loom.runner starts -- on the workload's
+    files: config.pb.gz, rows.pbs.gz, model.pb.gz in; model, groups, assignments, log out.  One chain, cat
+    kernel only, `extra_passes` extra passes of the annealing schedule.  Host wall clock around the whole
+    process: CUDA context, file decode, upload, every batch's sweep, dump, file encode."""
+    import shutil
+    from loom_b200 import infer as driver
+    from loom_b200 import pbio
+    exe = exe or os.path.join(REPO, "loom_b200", "host", "loom_infer")
+    d = tempfile.mkdtemp(prefix="loom_b200_infer_")
+    try:
+        mf = pbio.ModelFile.create(model)
+        mf.write(os.path.join(d, "model.pb.gz"))
+        pbio.rows_write(os.path.join(d, "rows.pbs.gz"), mf, pbio.Rows.from_block(rows))
+        c = pbio.config_defaults()
+        c.seed, c.extra_passes, c.kind_iterations, c.hyper_run = 1, extra_passes, 0, 0
+        pbio.config_write(os.path.join(d, "config.pb.gz"), c)
+        # the schedule depends only on counts: replay it to know how many actions the run performs
+        R = rows.n_rows
+        accelerating = driver.AcceleratingSchedule(c.extra_passes, c.small_data_size, c.big_data_size)
+        annealing = driver.AnnealingSchedule(accelerating.extra_passes(0))
+        batching, window = driver.BatchingSchedule(0), driver.RowWindow(R)
+        assigned, n_actions, batches = 0, 0, 0
+        while assigned != R:
+            acts, assigned, boundary = driver.next_batch(R, assigned, annealing, batching, window)
+            n_actions += len(acts)
+            if not boundary:
+                break
+            batches += 1
+            annealing.set_extra_passes(accelerating.extra_passes(assigned))
+        out = [os.path.join(d, n) for n in ("out.model.pb.gz", "out.groups", "out.assign.pbs.gz")]
+        cmd = [exe, os.path.join(d, "config.pb.gz"), os.path.join(d, "rows.pbs.gz"), "--none",
+               os.path.join(d, "model.pb.gz"), "--none", "--none", "--none", out[0], out[1], out[2], "--none", "--none"]
+        env = dict(os.environ, LOOM_B200_DEVICE=str(device))
+        t0 = time.perf_counter()
+        proc = subprocess.run(cmd, capture_output=True, timeout=timeout, env=env)
+        wall = time.perf_counter() - t0
+        if proc.returncode != 0:
+            return {"error": proc.stderr.decode(errors="replace")[-300:]}
+        n_assigned = len(pbio.assign_read(out[2])[0])
+        cells = n_actions * rows.n_cells() / float(R)
+        return {"wall_s": wall, "rows": R, "row_actions": n_actions, "batches": batches, "assigned_rows_out": n_assigned,
+                "cells_per_s": cells / wall, "extra_passes": extra_passes,
+                "note": "whole process: context + rows.pbs.gz decode + upload + %d batch sweeps (one chain, one CTA per "
+                        "kind) + dump to model/groups/assign files" % batches}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -550,6 +599,10 @@ def main():
             aux["ingest"] = measure_ingest(cuda, model, rows, device=local_rank)
         except Exception as exc:  # never masks the headline
             aux["ingest"] = {"error": str(exc)}
+        try:
+            aux["loom_infer_process"] = measure_loom_infer(model, rows, device=local_rank)
+        except Exception as exc:
+            aux["loom_infer_process"] = {"error": str(exc)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
