@@ -283,10 +283,13 @@ def test_streams_equal_single_chain_sweeps_oracle(oracle_abi):
 
 
 @pytest.mark.gpu
-def test_streams_equal_single_chain_sweeps_gpu(oracle_abi, cuda_abi):
+@pytest.mark.parametrize("warps", [1, 8])
+def test_streams_equal_single_chain_sweeps_gpu(oracle_abi, cuda_abi, monkeypatch, warps):
     """lb_cat_sweep_streams: one launch, every chain in its own row order over the shared block; each chain
-    ends bit for bit where its own single-chain sweep ends, and one of them replays on the oracle"""
+    ends bit for bit where its own single-chain sweep ends, and one of them replays on the oracle.  With one
+    warp per (chain, kind) eight chains share a block and re-align at every action while reading different rows."""
     import test_cuda_cat as t
+    monkeypatch.setenv("LB_SWEEP_WARPS", str(warps))
     model, block, actions, seeds, chains = streams_case(cuda_abi)
     for c, chain in enumerate(chains):
         single = Engine(cuda_abi)
