@@ -110,6 +110,8 @@ typedef void *lb_handle;
  *   1 block-PY      a = iteration * F + featureid
  *   2 hyper         a = task id (hyper_kernel.cc:203-207), b = draw index
  *   3 ephemeral kind partition   a = row, b = kind id
+ *   4 DPD stick-breaking at ingest (loom_b200_io.h)
+ *   5 / 6 query sampler: group pick / value draw (query_sample below)
  * (replaces distributions::rng_t; sampled values are only statistically
  *  comparable with the reference, see SURVEY.md section 7 "RNG".) */
 
@@ -223,6 +225,23 @@ int LB_NAME(score_rows)(lb_handle h, int32_t kind, uint64_t row_begin, uint64_t 
  * averages over samples: log_sum_exp_l(out_l) - log(#samples).  out: HOST float
  * [row_end - row_begin]. */
 int LB_NAME(query_score)(lb_handle h, uint64_t row_begin, uint64_t row_end, float *out);
+
+/* The per-latent half of QueryServer::call(Sample) (src/query_server.cc:100-176 ->
+ * ProductMixture_::sample_value src/product_mixture.cc:637-649): conditioned on the loaded row
+ * `row`, draw n_samples joint values of the features to_sample[n_to_sample] (feature ids,
+ * ascending).  Per kind holding any of them: probs = scores_to_probs(score_value(row)); per
+ * sample: group ~ probs, then every requested feature of the kind ~ that group's posterior
+ * predictive (Group::sample_value of distributions 2.0.28: BB Bernoulli, DD / DPD categorical
+ * with DPD's unseen mass alpha*beta0 reported as LB_DPD_OTHER, GP Gamma-Poisson, NICH Student-t).
+ *   out_values [n_samples][n_to_sample]  raw cell values as in the row block (NICH: float bits)
+ *   out_groups [n_samples][n_kinds]      parity tap, may be NULL: packed group drawn per kind,
+ *                                        LB_UNASSIGNED for kinds none of to_sample lives in
+ * Random numbers: stream 5 (a = draw_offset + sample, b = kind) picks the group; stream 6
+ * (a = draw_offset + sample, b = featureid << 8 | draw index) draws the value. */
+#define LB_DPD_OTHER 0xFFFFFFFFu
+int LB_NAME(query_sample)(lb_handle h, uint64_t row, const uint32_t *to_sample, int32_t n_to_sample,
+                          uint32_t n_samples, uint64_t seed, uint64_t draw_offset,
+                          uint32_t *out_values, uint32_t *out_groups);
 
 /* ProductMixture_::add_value for rows [row_begin,row_end) with their CURRENT
  * assignments, all kinds (kind < 0) or one kind: rebuilds/extends sufficient

@@ -244,6 +244,54 @@ int lbio_samples_write(lbio_samples *s, int32_t n_kinds, const int32_t *kind_fea
                        float score);
 int lbio_samples_close(lbio_samples *s);
 
+/* ------------------------------------------------------------------------- */
+/* Query protocol: a stream of Query.Request in, one Query.Response out per request
+ * (src/schema.proto:342-418; QueryServer::serve src/query_server.cc:36-66).  A request's rows
+ * (sample.data | score.data | score_derivative.update_data, score_data...) are decoded into ONE
+ * CSR block, in that order; the *_row fields index it (-1 = that sub-request is absent).  A
+ * sub-request whose data does not fit the schema is reported through `invalid` exactly as the
+ * reference's validate() does ("invalid request.score.data", ...) and is then marked absent. */
+typedef struct lbio_query lbio_query;
+
+typedef struct {
+    const char *id;
+    lbio_row_block rows;
+    int32_t sample_row;              /* Query.Sample.Request :346-351 */
+    const uint32_t *to_sample;       /* observed positions of to_sample */
+    int32_t n_to_sample;
+    uint32_t sample_count;
+    int32_t score_row;               /* Query.Score.Request :360-363 */
+    int32_t has_entropy;             /* Query.Entropy.Request :372-378 (decoded by the caller if supported) */
+    int32_t update_row;              /* Query.ScoreDerivative.Request :388-393 */
+    int32_t first_score_data_row, n_score_data;
+    uint32_t row_limit;
+    int32_t n_invalid;
+    const char *const *invalid;      /* error strings produced while decoding */
+} lbio_query_request;
+
+typedef struct {
+    int32_t n_errors;
+    const char *const *errors;
+    int32_t has_sample;              /* Sample.Response :352-355: n_samples values of the to_sample cells */
+    int32_t n_samples;
+    const uint64_t *sample_ptr;      /* [n_samples + 1] */
+    const uint32_t *sample_feature;
+    const uint32_t *sample_value;    /* raw cell values (DPD: dictionary index) */
+    int32_t has_score;               /* Score.Response :364-367 */
+    float score;
+    int32_t has_score_derivative;    /* ScoreDerivative.Response :394-398 */
+    int32_t n_ids;
+    const uint64_t *ids;
+    const float *score_diffs;
+} lbio_query_response;
+
+int lbio_query_open(const char *requests_in, const char *responses_out, lbio_query **out);
+/* *got = 0 at the end of the stream.  The request stays valid until the next call. */
+int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_request *req, int32_t *got);
+/* writes Response{id of the current request, errors, ...} and flushes (the client waits on it) */
+int lbio_query_respond(lbio_query *q, const lbio_model *m, const lbio_query_response *resp);
+void lbio_query_close(lbio_query *q);
+
 #ifdef __cplusplus
 }
 #endif

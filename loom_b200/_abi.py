@@ -14,6 +14,7 @@ import numpy as np
 LB_BB, LB_DD, LB_DPD, LB_GP, LB_NICH = range(5)
 TYPE_NAMES = {"bb": LB_BB, "dd": LB_DD, "dpd": LB_DPD, "gp": LB_GP, "nich": LB_NICH}
 UNASSIGNED = 0xFFFFFFFF
+DPD_OTHER = 0xFFFFFFFF   # LB_DPD_OTHER: query_sample drew a value outside the dictionary
 
 
 class FeatureSpec(C.Structure):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "set_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
     "set_rows_diff": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u8p, _u64p, _u32p, _u32p, _u64p, _u32p]),
     "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
+    "query_sample": (C.c_int, [_h, C.c_uint64, _u32p, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, _u32p, _u32p]),
     "share_rows": (C.c_int, [_h, _h]),
     "cat_sweep_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
     "cat_sweep_streams": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),

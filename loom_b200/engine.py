@@ -319,6 +319,18 @@ class Engine:
         self.abi.check(self.abi.query_score(self.h, row_begin, row_end, ptr(out, _f32p)))
         return out
 
+    def query_sample(self, row, to_sample, n_samples, seed, draw_offset=0, groups=False):
+        """n_samples joint draws of the features `to_sample` given the loaded row `row` under this sample
+        (the per-latent half of QueryServer Sample): uint32 [n_samples][len(to_sample)] raw cell values
+        (NICH: float bits; DPD_OTHER for a value outside a DPD dictionary), and with groups=True also the
+        packed group drawn per kind [n_samples][n_kinds]."""
+        to_sample = np.ascontiguousarray(to_sample, np.uint32)
+        values = np.empty((n_samples, len(to_sample)), np.uint32)
+        picked = np.empty((n_samples, self.n_kinds()), np.uint32) if groups else None
+        self.abi.check(self.abi.query_sample(self.h, row, ptr(to_sample, _u32p), len(to_sample), n_samples, seed,
+                                             draw_offset, ptr(values, _u32p), ptr(picked, _u32p)))
+        return (values, picked) if groups else values
+
     def accumulate_rows(self, kind=-1, row_begin=0, row_end=None, sign=1):
         row_end = self.n_rows if row_end is None else row_end
         self.abi.check(self.abi.accumulate_rows(self.h, kind, row_begin, row_end, sign))

@@ -753,6 +753,43 @@ struct RowChunk {           // one thread's share of a batch
 };
 
 // Row :153-156, ProductValue.Diff :87-91
+// One ProductValue.Diff (:87-91) appended to `out` as a row with the given id.  Returns an error text or null
+// (on error the partial cells are rolled back).
+static const char *decode_diff(Reader d, const lbio_model &m, ValueScratch &scratch, std::vector<uint32_t> &tares,
+                               uint64_t id, RowChunk &out, bool open_dictionaries) {
+    const size_t pos0 = out.pos_feature.size(), neg0 = out.neg_feature.size(), miss0 = out.misses.size();
+    const char *err = nullptr;
+    uint8_t has_tare = 0;
+    uint32_t f, wt;
+    bool has_pos = false, has_neg = false;
+    tares.clear();
+    while (!err && d.next(f, wt)) {
+        if (f == 1 && wt == pbw::BYTES) {
+            has_pos = true;
+            err = decode_value(d.sub(), m, scratch, out.pos_feature, &out.pos_value, open_dictionaries ? &out.misses : nullptr);
+        } else if (f == 2 && wt == pbw::BYTES) {
+            has_neg = true;
+            err = decode_value(d.sub(), m, scratch, out.neg_feature, nullptr);
+        } else if (f == 3) d.rep_varint(wt, tares);
+        else d.skip(wt);
+    }
+    if (!err && (!d.ok || !has_pos || !has_neg)) err = "failed to parse ProductValue.Diff (pos and neg are required)";
+    for (uint32_t t : tares) {
+        if (t != 0 && !err) err = "row references a tare other than tare 0 (one tare row is supported)";
+        has_tare = 1;
+    }
+    if (err) {
+        out.pos_feature.resize(pos0); out.pos_value.resize(pos0); out.neg_feature.resize(neg0); out.misses.resize(miss0);
+        return err;
+    }
+    out.rowids.push_back(id);
+    out.has_tare.push_back(has_tare);
+    out.pos_count.push_back((uint32_t)(out.pos_feature.size() - pos0));
+    out.neg_count.push_back((uint32_t)(out.neg_feature.size() - neg0));
+    return nullptr;
+}
+
+// Row :153-156
 static void decode_rows(const lbio_model &m, const uint8_t *pool, const uint64_t *offsets, size_t begin, size_t end,
                         RowChunk &out, bool open_dictionaries) {
     ValueScratch scratch;
@@ -762,41 +799,21 @@ static void decode_rows(const lbio_model &m, const uint8_t *pool, const uint64_t
         uint64_t id = 0;
         bool has_id = false, has_diff = false;
         uint32_t f, wt;
-        const size_t pos0 = out.pos_feature.size(), neg0 = out.neg_feature.size();
-        uint8_t has_tare = 0;
         const char *err = nullptr;
-        while (!err && r.next(f, wt)) {
+        Reader diff(nullptr, 0);
+        while (r.next(f, wt)) {
             if (f == 1 && wt == pbw::VARINT) { id = r.varint(); has_id = true; }
-            else if (f == 2 && wt == pbw::BYTES) {
-                has_diff = true;
-                Reader d = r.sub();
-                tares.clear();
-                while (!err && d.next(f, wt)) {
-                    if (f == 1 && wt == pbw::BYTES)
-                        err = decode_value(d.sub(), m, scratch, out.pos_feature, &out.pos_value,
-                                           open_dictionaries ? &out.misses : nullptr);
-                    else if (f == 2 && wt == pbw::BYTES) err = decode_value(d.sub(), m, scratch, out.neg_feature, nullptr);
-                    else if (f == 3) d.rep_varint(wt, tares);
-                    else d.skip(wt);
-                }
-                if (!err && !d.ok) err = "failed to parse Row.diff";
-                for (uint32_t t : tares) {
-                    if (t != 0) err = "row references a tare other than tare 0 (one tare row is supported)";
-                    has_tare = 1;
-                }
-            } else r.skip(wt);
+            else if (f == 2 && wt == pbw::BYTES) { diff = r.sub(); has_diff = true; }
+            else r.skip(wt);
         }
-        if (!err && (!r.ok || !has_id || !has_diff)) err = "failed to parse Row (id and diff are required)";
+        if (!r.ok || !has_id || !has_diff) err = "failed to parse Row (id and diff are required)";
+        else err = decode_diff(diff, m, scratch, tares, id, out, open_dictionaries);
         if (err) {
             char buf[256];
             snprintf(buf, sizeof(buf), "row %zu of the batch: %s", i, err);
             out.error = buf;
             return;
         }
-        out.rowids.push_back(id);
-        out.has_tare.push_back(has_tare);
-        out.pos_count.push_back((uint32_t)(out.pos_feature.size() - pos0));
-        out.neg_count.push_back((uint32_t)(out.neg_feature.size() - neg0));
     }
 }
 
@@ -1503,4 +1520,190 @@ extern "C" int lbio_samples_close(lbio_samples *s) {
     delete s->file;
     delete s;
     return ok ? 0 : fail("failed to write %s", path.c_str());
+}
+
+// ---------------------------------------------------------------------------------------------
+// Query.Request / Query.Response (:342-418)
+struct lbio_query {
+    pbw::InFile *in;
+    pbw::OutFile *out;
+    std::string in_path, out_path, id;
+    std::vector<uint8_t> msg;
+    RowChunk chunk;
+    RowsOwner rows;
+    std::vector<uint32_t> to_sample;
+    std::vector<std::string> invalid;
+    std::vector<const char *> invalid_ptrs;
+};
+
+extern "C" int lbio_query_open(const char *requests_in, const char *responses_out, lbio_query **out) {
+    auto *q = new lbio_query;
+    q->in = new pbw::InFile(requests_in);
+    q->out = new pbw::OutFile(responses_out);
+    q->in_path = requests_in;
+    q->out_path = responses_out;
+    if (!q->in->is_open() || !q->out->is_open()) {
+        const bool in_bad = !q->in->is_open();
+        lbio_query_close(q);
+        return in_bad ? fail("failed to open input file %s", requests_in) : fail("failed to open output file %s", responses_out);
+    }
+    *out = q;
+    return 0;
+}
+
+extern "C" void lbio_query_close(lbio_query *q) {
+    if (!q) return;
+    delete q->in;
+    delete q->out;
+    delete q;
+}
+
+extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_request *req, int32_t *got) {
+    std::memset(req, 0, sizeof(*req));
+    *got = 0;
+    bool bad = false;
+    if (!q->in->try_read_stream(q->msg, bad)) {
+        if (bad) return fail("failed to parse message from %s (truncated stream)", q->in_path.c_str());
+        return 0;
+    }
+    *got = 1;
+    q->id.clear();
+    q->chunk.clear();
+    q->to_sample.clear();
+    q->invalid.clear();
+    req->sample_row = req->score_row = req->update_row = req->first_score_data_row = -1;
+    ValueScratch scratch;
+    std::vector<uint32_t> tares, unused;
+    auto add_row = [&](Reader diff, const char *what) -> int {      // row index, or -1 with `invalid` extended
+        const char *err = decode_diff(diff, *m, scratch, tares, q->chunk.rowids.size(), q->chunk, false);
+        if (err) { q->invalid.push_back(std::string("invalid request.") + what); return -1; }
+        return (int)q->chunk.rowids.size() - 1;
+    };
+    Reader r(q->msg);
+    uint32_t f, wt;
+    while (r.next(f, wt)) {
+        if (f == 1 && wt == pbw::BYTES) { Reader b = r.sub(); q->id.assign((const char *)b.p, (size_t)(b.end - b.p)); }
+        else if (f == 2 && wt == pbw::BYTES) {                    // Sample.Request
+            Reader s = r.sub();
+            Reader data(nullptr, 0), to_sample(nullptr, 0);
+            bool has_data = false, has_to_sample = false;
+            while (s.next(f, wt)) {
+                if (f == 1 && wt == pbw::BYTES) { data = s.sub(); has_data = true; }
+                else if (f == 2 && wt == pbw::BYTES) { to_sample = s.sub(); has_to_sample = true; }
+                else if (f == 3 && wt == pbw::VARINT) req->sample_count = (uint32_t)s.varint();
+                else s.skip(wt);
+            }
+            if (!s.ok || !has_data) { q->invalid.push_back("invalid request.sample.data"); continue; }
+            const int row = add_row(data, "sample.data");
+            if (row < 0) continue;
+            // to_sample is a bare Observed: wrap it as the `observed` field of an otherwise empty value
+            bool ok = has_to_sample;
+            if (ok) {
+                int sparsity = -1;
+                std::vector<uint8_t> dense;
+                std::vector<uint32_t> sparse;
+                while (to_sample.next(f, wt)) {
+                    if (f == 1 && wt == pbw::VARINT) sparsity = (int)to_sample.varint();
+                    else if (f == 2) to_sample.rep_varint(wt, dense);
+                    else if (f == 3) to_sample.rep_varint(wt, sparse);
+                    else to_sample.skip(wt);
+                }
+                const size_t F = m->specs.size();
+                ok = to_sample.ok;
+                if (ok && sparsity == SP_ALL) for (size_t p = 0; p < F; ++p) q->to_sample.push_back((uint32_t)p);
+                else if (ok && sparsity == SP_DENSE && dense.size() == F) { for (size_t p = 0; p < F; ++p) if (dense[p]) q->to_sample.push_back((uint32_t)p); }
+                else if (ok && sparsity == SP_SPARSE) { for (uint32_t p : sparse) { if (p >= F) ok = false; q->to_sample.push_back(p); } }
+                else if (!(ok && sparsity == SP_NONE)) ok = false;
+            }
+            if (!ok) { q->invalid.push_back("invalid request.sample.to_sample"); continue; }
+            req->sample_row = row;
+        } else if (f == 3 && wt == pbw::BYTES) {                  // Score.Request
+            Reader s = r.sub();
+            Reader data(nullptr, 0);
+            bool has_data = false;
+            while (s.next(f, wt)) {
+                if (f == 1 && wt == pbw::BYTES) { data = s.sub(); has_data = true; }
+                else s.skip(wt);
+            }
+            if (!s.ok || !has_data) { q->invalid.push_back("invalid request.score.data"); continue; }
+            req->score_row = add_row(data, "score.data");
+        } else if (f == 4 && wt == pbw::BYTES) { r.sub(); req->has_entropy = 1; }
+        else if (f == 5 && wt == pbw::BYTES) {                    // ScoreDerivative.Request
+            Reader s = r.sub();
+            std::vector<Reader> score_data;
+            Reader update(nullptr, 0);
+            bool has_update = false;
+            while (s.next(f, wt)) {
+                if (f == 1 && wt == pbw::BYTES) score_data.push_back(s.sub());
+                else if (f == 2 && wt == pbw::BYTES) { update = s.sub(); has_update = true; }
+                else if (f == 3 && wt == pbw::VARINT) req->row_limit = (uint32_t)s.varint();
+                else s.skip(wt);
+            }
+            if (!s.ok || !has_update) { q->invalid.push_back("invalid request.score_derivative.update_data"); continue; }
+            const int row = add_row(update, "score_derivative.update_data");
+            if (row < 0) continue;
+            bool ok = true;
+            const int first = (int)q->chunk.rowids.size();
+            for (Reader &d : score_data) ok = ok && add_row(d, "score_derivative.score_data") >= 0;
+            if (!ok) continue;
+            req->update_row = row;
+            req->first_score_data_row = first;
+            req->n_score_data = (int32_t)score_data.size();
+        } else r.skip(wt);
+    }
+    if (!r.ok) return fail("failed to parse message from %s", q->in_path.c_str());
+    // publish the rows
+    RowsOwner &o = q->rows;
+    o.rowids = q->chunk.rowids;
+    o.has_tare = q->chunk.has_tare;
+    o.pos_feature = q->chunk.pos_feature;
+    o.pos_value = q->chunk.pos_value;
+    o.neg_feature = q->chunk.neg_feature;
+    o.pos_ptr.assign(1, 0);
+    o.neg_ptr.assign(1, 0);
+    for (uint32_t k : q->chunk.pos_count) o.pos_ptr.push_back(o.pos_ptr.back() + k);
+    for (uint32_t k : q->chunk.neg_count) o.neg_ptr.push_back(o.neg_ptr.back() + k);
+    publish_rows(&o, &req->rows);
+    req->rows.owner = nullptr;          // owned by the query object
+    req->id = q->id.c_str();
+    req->to_sample = q->to_sample.data();
+    req->n_to_sample = (int32_t)q->to_sample.size();
+    q->invalid_ptrs.clear();
+    for (const auto &e : q->invalid) q->invalid_ptrs.push_back(e.c_str());
+    req->n_invalid = (int32_t)q->invalid_ptrs.size();
+    req->invalid = q->invalid_ptrs.data();
+    return 0;
+}
+
+extern "C" int lbio_query_respond(lbio_query *q, const lbio_model *m, const lbio_query_response *resp) {
+    Writer w, sub, diff;
+    w.tag(1, pbw::BYTES);
+    w.varint(q->id.size());
+    w.raw(q->id.data(), q->id.size());
+    for (int i = 0; i < resp->n_errors; ++i) {
+        const size_t n = std::strlen(resp->errors[i]);
+        w.tag(2, pbw::BYTES);
+        w.varint(n);
+        w.raw(resp->errors[i], n);
+    }
+    if (resp->has_sample) {
+        sub.clear();
+        for (int i = 0; i < resp->n_samples; ++i) {
+            diff.clear();
+            const uint64_t a = resp->sample_ptr[i], b = resp->sample_ptr[i + 1];
+            encode_value(diff, 1, *m, resp->sample_feature + a, resp->sample_value + a, (size_t)(b - a));
+            encode_value(diff, 2, *m, nullptr, nullptr, 0);
+            sub.msg(1, diff);
+        }
+        w.msg(3, sub);
+    }
+    if (resp->has_score) { sub.clear(); sub.f32(1, resp->score); w.msg(4, sub); }
+    if (resp->has_score_derivative) {
+        sub.clear();
+        for (int i = 0; i < resp->n_ids; ++i) sub.u64(1, resp->ids[i]);
+        for (int i = 0; i < resp->n_ids; ++i) sub.f32(2, resp->score_diffs[i]);
+        w.msg(6, sub);
+    }
+    if (!q->out->write_stream(w.buf) || !q->out->flush()) return fail("failed to write %s", q->out_path.c_str());
+    return 0;
 }

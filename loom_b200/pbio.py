@@ -130,6 +130,10 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_open": (C.c_int, [_cs, C.c_int32, _P(C.c_void_p)]),
     "log_write": (C.c_int, [C.c_void_p, _P(LogEntry)]),
     "log_close": (None, [C.c_void_p]),
+    "query_open": (C.c_int, [_cs, _cs, _P(C.c_void_p)]),
+    "query_next": (C.c_int, [C.c_void_p, _model, C.c_void_p, _i32p]),
+    "query_respond": (C.c_int, [C.c_void_p, _model, C.c_void_p]),
+    "query_close": (None, [C.c_void_p]),
     "samples_open": (C.c_int, [_cs, _P(C.c_void_p)]),
     "samples_write": (C.c_int, [C.c_void_p, C.c_int32, _i32p, _u32p, _i32p, _u64p, _u32p, C.c_float]),
     "samples_close": (C.c_int, [C.c_void_p]),

@@ -712,6 +712,47 @@ int lo_query_score(lb_handle h, uint64_t b, uint64_t en, float *out) {
     return 0;
 }
 
+/* The per-latent half of QueryServer::call(Sample) (src/query_server.cc:100-176): probs of the
+ * conditioning row per kind, then ProductMixture_::sample_value (src/product_mixture.cc:637-649)
+ * per sample = a group from probs and every requested feature from that group. */
+int lo_query_sample(lb_handle h, uint64_t row, const uint32_t *to_sample, int32_t n_to, uint32_t n_samples,
+                    uint64_t seed, uint64_t draw_offset, uint32_t *out_values, uint32_t *out_groups) {
+    engine_t *e = h;
+    if (row >= e->R) return lo_fail("query_sample: bad row");
+    if (n_to < 0 || (n_to && !to_sample)) return lo_fail("query_sample: bad to_sample");
+    for (int j = 0; j < n_to; ++j) {
+        if (to_sample[j] >= (uint32_t)e->F) return lo_fail("query_sample: bad feature id %u", to_sample[j]);
+        if (j && to_sample[j] <= to_sample[j - 1]) return lo_fail("query_sample: to_sample must be ascending");
+    }
+    if (out_groups)
+        for (uint64_t i = 0; i < (uint64_t)n_samples * e->K; ++i) out_groups[i] = LB_UNASSIGNED;
+    for (int kid = 0; kid < e->K; ++kid) {
+        const kind_t *k = &e->kinds[kid];
+        int wanted = 0;
+        for (int j = 0; j < n_to; ++j) wanted += (int)e->f2k[to_sample[j]] == kid;
+        if (!wanted) continue;                              /* query_server.cc:157-159 */
+        double *scores = xcalloc(k->G, 8), *probs = xcalloc(k->G, 8);
+        kind_score_row(e, k, row, scores);
+        for (uint32_t s = 0; s < n_samples; ++s) {
+            memcpy(probs, scores, 8u * (size_t)k->G);
+            const int g = om_sample_from_scores(lo_uniform(seed, 5, draw_offset + s, (uint32_t)kid), probs, k->G);
+            if (out_groups) out_groups[(uint64_t)s * e->K + kid] = (uint32_t)g;
+            for (int j = 0; j < n_to; ++j) {
+                const int f = (int)to_sample[j];
+                if ((int)e->f2k[f] != kid) continue;
+                int local = 0;
+                while (k->fids[local] != f) ++local;
+                out_values[(uint64_t)s * n_to + j] =
+                    om_sample_value(&e->specs[f], e->aux, k->ints + (size_t)k->int_off[local] * k->Gcap + g,
+                                    k->flts + (size_t)k->flt_off[local] * k->Gcap + g, k->Gcap, seed,
+                                    draw_offset + s, (uint32_t)f);
+            }
+        }
+        free(scores); free(probs);
+    }
+    return 0;
+}
+
 /* bulk add_value / remove_value with given assignments */
 int lo_accumulate_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, int32_t sign) {
     engine_t *e = h;

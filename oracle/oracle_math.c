@@ -217,3 +217,105 @@ double lo_feature_score_data(const lb_feature_spec *spec, const float *aux,
                              const uint32_t *ints, const double *flts) {
     return om_score_data(spec, aux, ints, flts, 1);
 }
+
+/* ---- Group::sample_value (distributions 2.0.28; called through
+ * ProductMixture_::sample_value, src/product_mixture.cc:622-649) ------------
+ * distributions draws the group's parameter from its posterior (Sampler::init) and then
+ * the value from that parameter (Sampler::eval), which is a draw from the posterior
+ * predictive.  Restated here on counter-based uniforms so that a draw is a pure function of
+ * (seed, sample, feature): u(j) = Philox(seed, stream 6, a, featureid << 10 | j).
+ *   BB    Bernoulli((alpha + heads) / (alpha + beta + heads + tails))            [1 uniform]
+ *   DD    categorical over alpha_v + n_v                                          [1]
+ *   DPD   categorical over alpha beta_v + n_v, plus alpha beta0 for an unseen value [1]
+ *   GP    lambda ~ Gamma(alpha + sum, 1 / (inv_beta + count)) (Marsaglia-Tsang 2000),
+ *         x ~ Poisson(lambda) (inversion below 30, Hoermann's PTRS 1993 above)
+ *   NICH  Student-t, nu' degrees of freedom, location mu', scale^2 sigma'^2 (kappa'+1)/kappa'
+ *         by Bailey's polar method (1994): t = sqrt(nu (U^(-2/nu) - 1)) cos(2 pi V)   [2] */
+#define I(row) ((double)ints[(size_t)(row) * stride])
+#define D(row) (flts[(size_t)(row) * stride])
+typedef struct { uint64_t seed, a; uint32_t base, j; } draw_t;
+static double draw_u(draw_t *d) { return lo_uniform(d->seed, 6, d->a, d->base | d->j++); }          /* [0,1) */
+static double draw_uo(draw_t *d) { return draw_u(d) + 0.5 / 16777216.0; }                          /* (0,1) */
+
+static double sample_gamma(draw_t *d, double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) { boost = pow(draw_uo(d), 1.0 / shape); shape += 1.0; }
+    const double dd = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * dd);
+    for (int it = 0; it < 100; ++it) {
+        const double u1 = draw_uo(d), u2 = draw_u(d), u3 = draw_uo(d);
+        const double z = sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
+        double v = 1.0 + c * z;
+        if (v <= 0) continue;
+        v = v * v * v;
+        if (log(u3) < 0.5 * z * z + dd - dd * v + dd * log(v)) return boost * dd * v;
+    }
+    return boost * dd;
+}
+
+static double sample_poisson(draw_t *d, double lam) {
+    if (lam < 30.0) {
+        const double t = draw_u(d);
+        double p = exp(-lam), c = p, x = 0;
+        while (t >= c && x < 1000) { x += 1; p *= lam / x; c += p; }
+        return x;
+    }
+    const double slam = sqrt(lam), loglam = log(lam), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int it = 0; it < 100; ++it) {
+        const double u = draw_u(d) - 0.5, v = draw_uo(d), us = 0.5 - fabs(u);
+        const double k = floor((2.0 * a / us + b) * u + lam + 0.43);
+        if (us >= 0.07 && v <= vr) return k;
+        if (k < 0 || (us < 0.013 && v > us)) continue;
+        if (log(v) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) return k;
+    }
+    return floor(lam);
+}
+
+uint32_t om_sample_value(const lb_feature_spec *s, const float *aux, const uint32_t *ints, const double *flts,
+                         int stride, uint64_t seed, uint64_t a, uint32_t featureid) {
+    draw_t d = {seed, a, featureid << 10, 0};
+    switch (s->type) {
+    case LB_BB: {
+        double al = s->hp[0], be = s->hp[1], h = I(0), t = I(1);
+        return draw_u(&d) < (al + h) / (al + be + h + t);
+    }
+    case LB_DD:
+    case LB_DPD: {
+        const float *w0 = aux + s->aux_off;
+        const double scale = s->type == LB_DPD ? (double)s->hp[1] : 1.0;
+        const int n = s->dim + (s->type == LB_DPD);
+        double total = 0;
+        for (int v = 0; v < n; ++v) total += v < s->dim ? scale * w0[v] + I(v) : scale * s->hp[2];
+        const double t = draw_u(&d) * total;
+        double c = 0;
+        int last = 0;
+        for (int v = 0; v < n; ++v) {
+            const double w = v < s->dim ? scale * w0[v] + I(v) : scale * s->hp[2];
+            if (w > 0) last = v;
+            c += w;
+            if (c > t) { last = v; break; }
+        }
+        return last == s->dim ? LB_DPD_OTHER : (uint32_t)last;
+    }
+    case LB_GP: {
+        const double shape = s->hp[0] + I(1), rate = s->hp[1] + I(0);
+        const double lam = sample_gamma(&d, shape) / rate;
+        const double x = sample_poisson(&d, lam);
+        return x >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)x;
+    }
+    case LB_NICH: {
+        double mu = s->hp[0], kappa = s->hp[1], sigmasq = s->hp[2], nu = s->hp[3];
+        double n = I(0), mean = D(0), ctv = D(1);
+        double kn = kappa + n, mun = (kappa * mu + n * mean) / kn, nun = nu + n, dm = mu - mean;
+        double sn = (nu * sigmasq + ctv + n * kappa * dm * dm / kn) / nun;
+        const double u = draw_uo(&d), v = draw_u(&d);
+        const double t = sqrt(nun * (pow(u, -2.0 / nun) - 1.0)) * cos(2.0 * M_PI * v);
+        const float x = (float)(mun + sqrt(sn * (kn + 1.0) / kn) * t);
+        uint32_t raw; memcpy(&raw, &x, 4);
+        return raw;
+    }
+    }
+    return 0;
+}
+#undef I
+#undef D
