@@ -247,8 +247,9 @@ int lbio_samples_close(lbio_samples *s);
 /* ------------------------------------------------------------------------- */
 /* Query protocol: a stream of Query.Request in, one Query.Response out per request
  * (src/schema.proto:342-418; QueryServer::serve src/query_server.cc:36-66).  A request's rows
- * (sample.data | score.data | score_derivative.update_data, score_data...) are decoded into ONE
- * CSR block, in that order; the *_row fields index it (-1 = that sub-request is absent).  A
+ * are decoded into ONE CSR block (sample.data | score.data | entropy.conditional |
+ * score_derivative.update_data, score_data...) in the order the sub-requests appear in the
+ * message; the *_row fields index it (-1 = that sub-request is absent).  A
  * sub-request whose data does not fit the schema is reported through `invalid` exactly as the
  * reference's validate() does ("invalid request.score.data", ...) and is then marked absent. */
 typedef struct lbio_query lbio_query;
@@ -261,7 +262,11 @@ typedef struct {
     int32_t n_to_sample;
     uint32_t sample_count;
     int32_t score_row;               /* Query.Score.Request :360-363 */
-    int32_t has_entropy;             /* Query.Entropy.Request :372-378 (decoded by the caller if supported) */
+    int32_t entropy_row;             /* Query.Entropy.Request :372-378: the conditional */
+    int32_t n_row_sets, n_col_sets;
+    const int32_t *set_ptr;          /* [n_row_sets + n_col_sets + 1] into set_features, row sets first */
+    const uint32_t *set_features;    /* ascending feature positions of each set */
+    uint32_t entropy_sample_count;
     int32_t update_row;              /* Query.ScoreDerivative.Request :388-393 */
     int32_t first_score_data_row, n_score_data;
     uint32_t row_limit;
@@ -279,6 +284,9 @@ typedef struct {
     const uint32_t *sample_value;    /* raw cell values (DPD: dictionary index) */
     int32_t has_score;               /* Score.Response :364-367 */
     float score;
+    int32_t has_entropy;             /* Entropy.Response :379-382: one estimate per (row set, col set) */
+    int32_t n_entropy;
+    const float *means, *variances;
     int32_t has_score_derivative;    /* ScoreDerivative.Response :394-398 */
     int32_t n_ids;
     const uint64_t *ids;

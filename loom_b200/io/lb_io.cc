@@ -1063,7 +1063,8 @@ static void encode_value(Writer &w, uint32_t field, const lbio_model &m, const u
             if (pass == 0) v.boolean(2, raw != 0);
             else if (pass == 1) {
                 uint32_t x = raw;
-                if (s.type == LB_DPD) x = m.dpd_values[m.dpd_offsets[m.dpd_ordinal[p]] + std::min<uint32_t>(raw, (uint32_t)s.dim - 1)];
+                if (s.type == LB_DPD && raw != LB_DPD_OTHER)     // OTHER() of distributions' DPD is the same all-ones sentinel
+                    x = m.dpd_values[m.dpd_offsets[m.dpd_ordinal[p]] + std::min<uint32_t>(raw, (uint32_t)s.dim - 1)];
                 v.u64(3, x);
             } else { float x; std::memcpy(&x, &raw, 4); v.f32(4, x); }
         }
@@ -1531,7 +1532,8 @@ struct lbio_query {
     std::vector<uint8_t> msg;
     RowChunk chunk;
     RowsOwner rows;
-    std::vector<uint32_t> to_sample;
+    std::vector<uint32_t> to_sample, set_features;
+    std::vector<int32_t> set_ptr;
     std::vector<std::string> invalid;
     std::vector<const char *> invalid_ptrs;
 };
@@ -1558,6 +1560,43 @@ extern "C" void lbio_query_close(lbio_query *q) {
     delete q;
 }
 
+// ProductValue.Observed (:76-85) as ascending positions; false = ValueSchema::is_valid(observed) fails
+// (src/product_value.hpp:277-298)
+static bool observed_positions(Reader o, size_t F, std::vector<uint32_t> &out) {
+    int sparsity = -1;
+    std::vector<uint8_t> dense;
+    std::vector<uint32_t> sparse;
+    uint32_t f, wt;
+    while (o.next(f, wt)) {
+        if (f == 1 && wt == pbw::VARINT) sparsity = (int)o.varint();
+        else if (f == 2) o.rep_varint(wt, dense);
+        else if (f == 3) o.rep_varint(wt, sparse);
+        else o.skip(wt);
+    }
+    if (!o.ok) return false;
+    switch (sparsity) {
+    case SP_ALL:
+        if (!dense.empty() || !sparse.empty()) return false;
+        for (size_t p = 0; p < F; ++p) out.push_back((uint32_t)p);
+        return true;
+    case SP_DENSE:
+        if (dense.size() != F || !sparse.empty()) return false;
+        for (size_t p = 0; p < F; ++p)
+            if (dense[p]) out.push_back((uint32_t)p);
+        return true;
+    case SP_SPARSE:
+        if (!dense.empty()) return false;
+        for (size_t i = 0; i < sparse.size(); ++i) {
+            if (sparse[i] >= F || (i && sparse[i - 1] >= sparse[i])) return false;
+            out.push_back(sparse[i]);
+        }
+        return true;
+    case SP_NONE:
+        return dense.empty() && sparse.empty();
+    }
+    return false;
+}
+
 extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_request *req, int32_t *got) {
     std::memset(req, 0, sizeof(*req));
     *got = 0;
@@ -1570,10 +1609,13 @@ extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_re
     q->id.clear();
     q->chunk.clear();
     q->to_sample.clear();
+    q->set_features.clear();
+    q->set_ptr.assign(1, 0);
     q->invalid.clear();
-    req->sample_row = req->score_row = req->update_row = req->first_score_data_row = -1;
+    req->sample_row = req->score_row = req->entropy_row = req->update_row = req->first_score_data_row = -1;
+    const size_t F = m->specs.size();
     ValueScratch scratch;
-    std::vector<uint32_t> tares, unused;
+    std::vector<uint32_t> tares;
     auto add_row = [&](Reader diff, const char *what) -> int {      // row index, or -1 with `invalid` extended
         const char *err = decode_diff(diff, *m, scratch, tares, q->chunk.rowids.size(), q->chunk, false);
         if (err) { q->invalid.push_back(std::string("invalid request.") + what); return -1; }
@@ -1596,26 +1638,11 @@ extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_re
             if (!s.ok || !has_data) { q->invalid.push_back("invalid request.sample.data"); continue; }
             const int row = add_row(data, "sample.data");
             if (row < 0) continue;
-            // to_sample is a bare Observed: wrap it as the `observed` field of an otherwise empty value
-            bool ok = has_to_sample;
-            if (ok) {
-                int sparsity = -1;
-                std::vector<uint8_t> dense;
-                std::vector<uint32_t> sparse;
-                while (to_sample.next(f, wt)) {
-                    if (f == 1 && wt == pbw::VARINT) sparsity = (int)to_sample.varint();
-                    else if (f == 2) to_sample.rep_varint(wt, dense);
-                    else if (f == 3) to_sample.rep_varint(wt, sparse);
-                    else to_sample.skip(wt);
-                }
-                const size_t F = m->specs.size();
-                ok = to_sample.ok;
-                if (ok && sparsity == SP_ALL) for (size_t p = 0; p < F; ++p) q->to_sample.push_back((uint32_t)p);
-                else if (ok && sparsity == SP_DENSE && dense.size() == F) { for (size_t p = 0; p < F; ++p) if (dense[p]) q->to_sample.push_back((uint32_t)p); }
-                else if (ok && sparsity == SP_SPARSE) { for (uint32_t p : sparse) { if (p >= F) ok = false; q->to_sample.push_back(p); } }
-                else if (!(ok && sparsity == SP_NONE)) ok = false;
+            if (!has_to_sample || !observed_positions(to_sample, F, q->to_sample)) {
+                q->to_sample.clear();
+                q->invalid.push_back("invalid request.sample.to_sample");
+                continue;
             }
-            if (!ok) { q->invalid.push_back("invalid request.sample.to_sample"); continue; }
             req->sample_row = row;
         } else if (f == 3 && wt == pbw::BYTES) {                  // Score.Request
             Reader s = r.sub();
@@ -1627,8 +1654,39 @@ extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_re
             }
             if (!s.ok || !has_data) { q->invalid.push_back("invalid request.score.data"); continue; }
             req->score_row = add_row(data, "score.data");
-        } else if (f == 4 && wt == pbw::BYTES) { r.sub(); req->has_entropy = 1; }
-        else if (f == 5 && wt == pbw::BYTES) {                    // ScoreDerivative.Request
+        } else if (f == 4 && wt == pbw::BYTES) {                  // Entropy.Request
+            Reader s = r.sub();
+            std::vector<Reader> row_sets, col_sets;
+            Reader conditional(nullptr, 0);
+            bool has_conditional = false;
+            uint32_t sample_count = 0;
+            while (s.next(f, wt)) {
+                if (f == 1 && wt == pbw::BYTES) row_sets.push_back(s.sub());
+                else if (f == 2 && wt == pbw::BYTES) col_sets.push_back(s.sub());
+                else if (f == 3 && wt == pbw::BYTES) { conditional = s.sub(); has_conditional = true; }
+                else if (f == 4 && wt == pbw::VARINT) sample_count = (uint32_t)s.varint();
+                else s.skip(wt);
+            }
+            if (!s.ok || !has_conditional) { q->invalid.push_back("invalid request.entropy.conditional"); continue; }
+            const int row = add_row(conditional, "entropy.conditional");
+            if (row < 0) continue;
+            bool ok = true;
+            for (int pass = 0; pass < 2 && ok; ++pass)
+                for (Reader &o : pass ? col_sets : row_sets) {
+                    if (!observed_positions(o, F, q->set_features)) {
+                        q->invalid.push_back(pass ? "invalid request.entropy.col_sets" : "invalid request.entropy.row_sets");
+                        ok = false;
+                        break;
+                    }
+                    q->set_ptr.push_back((int32_t)q->set_features.size());
+                }
+            if (ok && sample_count <= 1) { q->invalid.push_back("invalid request.entropy.sample_count"); ok = false; }
+            if (!ok) { q->set_features.clear(); q->set_ptr.assign(1, 0); continue; }
+            req->entropy_row = row;
+            req->n_row_sets = (int32_t)row_sets.size();
+            req->n_col_sets = (int32_t)col_sets.size();
+            req->entropy_sample_count = sample_count;
+        } else if (f == 5 && wt == pbw::BYTES) {                  // ScoreDerivative.Request
             Reader s = r.sub();
             std::vector<Reader> score_data;
             Reader update(nullptr, 0);
@@ -1668,6 +1726,8 @@ extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_re
     req->id = q->id.c_str();
     req->to_sample = q->to_sample.data();
     req->n_to_sample = (int32_t)q->to_sample.size();
+    req->set_ptr = q->set_ptr.data();
+    req->set_features = q->set_features.data();
     q->invalid_ptrs.clear();
     for (const auto &e : q->invalid) q->invalid_ptrs.push_back(e.c_str());
     req->n_invalid = (int32_t)q->invalid_ptrs.size();
@@ -1698,6 +1758,12 @@ extern "C" int lbio_query_respond(lbio_query *q, const lbio_model *m, const lbio
         w.msg(3, sub);
     }
     if (resp->has_score) { sub.clear(); sub.f32(1, resp->score); w.msg(4, sub); }
+    if (resp->has_entropy) {
+        sub.clear();
+        for (int i = 0; i < resp->n_entropy; ++i) sub.f32(1, resp->means[i]);
+        for (int i = 0; i < resp->n_entropy; ++i) sub.f32(2, resp->variances[i]);
+        w.msg(5, sub);
+    }
     if (resp->has_score_derivative) {
         sub.clear();
         for (int i = 0; i < resp->n_ids; ++i) sub.u64(1, resp->ids[i]);

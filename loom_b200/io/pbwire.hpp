@@ -122,20 +122,27 @@ inline bool ends_with(const std::string &s, const char *suffix) {
 class InFile {
 public:
     explicit InFile(const char *path) : path_(path) {
-        if (path_ == "-" || path_ == "-.gz") f_ = gzdopen(dup(STDIN_FILENO), "rb");
+        // plain stdin is read with read(2), exactly as many bytes as the next frame needs: a client that
+        // pipes one request and waits for its response (loom.query's piped server, loom/runner.py:376-381)
+        // must not be held up by zlib filling a buffer first
+        if (path_ == "-") raw_fd_ = dup(STDIN_FILENO);
+        else if (path_ == "-.gz") f_ = gzdopen(dup(STDIN_FILENO), "rb");
         else f_ = gzopen(path, "rb");
         if (f_) gzbuffer(f_, 1 << 20);
     }
-    ~InFile() { if (f_) gzclose(f_); }
+    ~InFile() {
+        if (f_) gzclose(f_);
+        if (raw_fd_ >= 0) ::close(raw_fd_);
+    }
     InFile(const InFile &) = delete;
-    bool is_open() const { return f_ != nullptr; }
+    bool is_open() const { return f_ != nullptr || raw_fd_ >= 0; }
     uint64_t position() const { return position_; }
     // read(): the whole file is one message
     bool read_all(std::vector<uint8_t> &out) {
         out.clear();
         uint8_t chunk[1 << 16];
         for (;;) {
-            const int n = gzread(f_, chunk, sizeof(chunk));
+            const int n = rd(chunk, sizeof(chunk));
             if (n < 0) return false;
             if (n == 0) return true;
             out.insert(out.end(), chunk, chunk + n);
@@ -144,33 +151,33 @@ public:
     // try_read_stream(): false at a clean end of stream; `bad` reports a truncated frame
     bool try_read_stream(std::vector<uint8_t> &msg, bool &bad) {
         uint8_t head[4];
-        const int n = gzread(f_, head, 4);
+        const int n = rd(head, 4);
         bad = false;
         if (n == 0) return false;
         if (n != 4) { bad = true; return false; }
         const uint32_t size = (uint32_t)head[0] | (uint32_t)head[1] << 8 | (uint32_t)head[2] << 16 | (uint32_t)head[3] << 24;
         msg.resize(size);
-        if (size && gzread(f_, msg.data(), size) != (int)size) { bad = true; return false; }
+        if (size && rd(msg.data(), size) != (int)size) { bad = true; return false; }
         ++position_;
         return true;
     }
     // append the next frame's payload to `pool`; returns its size through `size`
     bool try_read_stream_into(std::vector<uint8_t> &pool, uint32_t &size, bool &bad) {
         uint8_t head[4];
-        const int n = gzread(f_, head, 4);
+        const int n = rd(head, 4);
         bad = false;
         if (n == 0) return false;
         if (n != 4) { bad = true; return false; }
         size = (uint32_t)head[0] | (uint32_t)head[1] << 8 | (uint32_t)head[2] << 16 | (uint32_t)head[3] << 24;
         const size_t at = pool.size();
         pool.resize(at + size);
-        if (size && gzread(f_, pool.data() + at, size) != (int)size) { bad = true; return false; }
+        if (size && rd(pool.data() + at, size) != (int)size) { bad = true; return false; }
         ++position_;
         return true;
     }
     bool skip_stream(uint32_t &size, bool &bad) {
         uint8_t head[4];
-        const int n = gzread(f_, head, 4);
+        const int n = rd(head, 4);
         bad = false;
         if (n == 0) return false;
         if (n != 4) { bad = true; return false; }
@@ -178,7 +185,7 @@ public:
         uint8_t discard[1 << 14];       // read and drop: gzseek is very slow on uncompressed files
         for (uint32_t left = size; left;) {
             const unsigned take = left < sizeof(discard) ? left : (unsigned)sizeof(discard);
-            if (gzread(f_, discard, take) != (int)take) { bad = true; return false; }
+            if (rd(discard, take) != (int)take) { bad = true; return false; }
             left -= take;
         }
         ++position_;
@@ -186,8 +193,20 @@ public:
     }
 
 private:
+    int rd(void *buf, unsigned n) {
+        if (raw_fd_ < 0) return gzread(f_, buf, n);
+        unsigned have = 0;
+        while (have < n) {
+            const ssize_t k = ::read(raw_fd_, (char *)buf + have, n - have);
+            if (k < 0) return -1;
+            if (k == 0) break;
+            have += (unsigned)k;
+        }
+        return (int)have;
+    }
     std::string path_;
     gzFile f_ = nullptr;
+    int raw_fd_ = -1;
     uint64_t position_ = 0;
 };
 

@@ -506,3 +506,4 @@ def test_hyper_run_with_dpd_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
             assert [so[f].hp[i] for i in range(2)] == [sg[f].hp[i] for i in range(2)], f
         assert np.allclose(ao, ag, rtol=1e-5, atol=1e-8)
         assert g.score_data() == pytest.approx(o.score_data(), rel=1e-5)
+

@@ -1,0 +1,66 @@
+"""GPU runs of the query path: lb_query_sample against the oracle draw for draw, and the product
+binary loom_query on the device against scores recomputed by the oracle.  Kept in the LAST test file so that a
+failure here cannot hide the results of the earlier GPU tests under `pytest -x`."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from loom_b200 import _abi
+from test_pbio import io_lib  # noqa: F401  (autouse fixture builds the codec)
+from test_z_loom_infer import HOST, infer_on_oracle  # noqa: F401
+import test_query_server as qs
+
+
+# ------------------------------------------------------------------------------------------ query sampler on the device
+@pytest.mark.gpu
+def test_query_sample_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
+    """lb_query_sample draw for draw against the oracle (same Philox counters, float64 samplers on both
+    sides; the group pick inverts fp32 scores on the device and float64 ones on the oracle, so a draw
+    that lands within rounding of a CDF step may differ), then the device's own draws against the
+    device's own scores."""
+    import test_query as tq
+    model, o = tq.trained(oracle_abi)
+    observe = [f for f in range(model.n_features) if f % 3 == 0]
+    cond = tq.conditioning_row(model, observe)
+    to_sample = [f for f in range(model.n_features) if f % 3 != 0]
+    qo = tq.frozen(oracle_abi, model, o, [cond])
+    qg = tq.frozen(cuda_abi, model, o, [cond])
+    n = tq.N_DRAWS
+    vo, go = qo.query_sample(0, to_sample, n, seed=7, groups=True)
+    vg, gg = qg.query_sample(0, to_sample, n, seed=7, groups=True)
+    assert np.array_equal(go == _abi.UNASSIGNED, gg == _abi.UNASSIGNED)
+    assert (go == gg).mean() > 0.9995
+    for j, f in enumerate(to_sample):
+        same_group = go[:, model.f2k[f]] == gg[:, model.f2k[f]]
+        a, b = vo[same_group, j], vg[same_group, j]
+        if model.features[f]["type"] == "nich":
+            a, b = a.copy().view(np.float32).astype(np.float64), b.copy().view(np.float32).astype(np.float64)
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-5), f
+        else:
+            assert (a == b).mean() > 0.9995, (f, (a == b).mean())
+    assert np.array_equal(qg.query_sample(0, to_sample, 64, seed=7, draw_offset=100), vg[100:164])
+    # self-consistency on the device alone: marginals of one feature per discrete type against lb_query_score
+    for ftype in ("bb", "dd", "dpd", "gp"):
+        j, f = next((j, f) for j, f in enumerate(to_sample) if model.features[f]["type"] == ftype)
+        cand = tq.candidates(model, f)
+        p = tq.predictive(cuda_abi, model, o, cond, [{f: v} for v in cand])
+        counts = np.array([(vg[:, j] == v).sum() for v in cand] + [0.0])
+        counts[-1] = n - counts[:-1].sum()
+        assert tq.chi_square_p(counts, np.append(p, max(1.0 - p.sum(), 1e-12))) > tq.MIN_P, ftype
+
+
+# ------------------------------------------------------------------------------------------ the product binary
+@pytest.mark.gpu
+def test_loom_query_on_the_gpu(tmp_path, infer_on_oracle, oracle_abi):  # noqa: F811
+    """loom_query linked against libloomb200.so: Score against the oracle's latents, Sample against the server's own
+    scores, Entropy of the empty set, ScoreDerivative leaves the latents as they were"""
+    import __graft_entry__
+    __graft_entry__.build()
+    exe = os.path.join(HOST, "loom_query")
+    needed = subprocess.check_output(["readelf", "-d", exe]).decode()
+    assert "libloomb200.so" in needed and "oracle" not in needed
+    root = tmp_path / "store"
+    model, block, rowids = qs.make_store(root, infer_on_oracle)
+    qs.mixed_session_case(exe, root, model, block, oracle_abi, tmp_path)
