@@ -155,6 +155,37 @@ int LB_NAME(set_rows_diff)(lb_handle h, uint64_t n_rows, const uint8_t *tare_obs
                            const uint32_t *pos_value, const uint64_t *neg_ptr,
                            const uint32_t *neg_feature);
 
+/* loom's tare / sparsify passes on the LOADED row block -- loom::Differ
+ * (src/differ.hpp, src/differ.cc), what `loom_tare` and `loom_sparsify` run before inference.
+ *
+ * differ_reset     Differ::Differ(schema): zero the per-column summaries and the row count.
+ * differ_add_rows  Differ::add_rows (src/differ.cc:93-127): add every row of the loaded block to the
+ *                  summaries -- per boolean column the counts of {0,1}, per count column (DD, DPD,
+ *                  GP) the counts of the values in [0,16) (CountSummary::max_count,
+ *                  src/differ.hpp:63-95); reals are not summarised ("do not sparsify reals").  May
+ *                  be called once per window of a long stream.
+ * differ_make_tare Differ::_make_tare (src/differ.cc:129-146, 191-206): a column is tared at its
+ *                  mode (first maximum) when more than half of ALL rows added hold the mode.
+ *                  Output as set_rows_diff takes it: tare_observed [F], tare_values [F].
+ * differ_compress_rows  Differ::compress_rows -> _abs_to_rel (src/differ.cc:148-189, 248-298): the
+ *                  loaded block relative to the tare.  For a tared column a row that agrees stores
+ *                  nothing, one that differs stores pos = its value and neg = the tare cell, one
+ *                  that lacks the cell stores neg; untared columns go to pos when observed.  The
+ *                  diff stays on the device; *n_pos / *n_neg give its sizes.
+ * differ_fetch     copy that diff to HOST arrays in the CSR form of set_rows_diff
+ *                  (pos_ptr [R+1], pos_feature / pos_value [n_pos], neg_ptr [R+1], neg_feature [n_neg]).
+ * The [0,16) window is over RAW count values as in the reference; DPD cells hold dictionary
+ * indices, so the dictionaries are passed the way lbio_model_view holds them (dpd_offsets
+ * [n_dpd + 1] into dpd_values, ascending feature id; NULL = identity). */
+int LB_NAME(differ_reset)(lb_handle h);
+int LB_NAME(differ_add_rows)(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values);
+int LB_NAME(differ_make_tare)(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values,
+                              uint8_t *tare_observed, uint32_t *tare_values);
+int LB_NAME(differ_compress_rows)(lb_handle h, const uint8_t *tare_observed, const uint32_t *tare_values,
+                                  uint64_t *n_pos, uint64_t *n_neg);
+int LB_NAME(differ_fetch)(lb_handle h, uint64_t *pos_ptr, uint32_t *pos_feature, uint32_t *pos_value,
+                          uint64_t *neg_ptr, uint32_t *neg_feature);
+
 /* Use `owner`'s row block instead of holding a copy: loom's samples all read the
  * same shuffled rows file (loom/tasks.py:173-194 passes one `rows` path to every
  * seed).  `h` must carry the same schema; its assignments are reset as by

@@ -56,6 +56,11 @@ SIGNATURES = {
     "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
     "query_sample": (C.c_int, [_h, C.c_uint64, _u32p, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, _u32p, _u32p]),
     "share_rows": (C.c_int, [_h, _h]),
+    "differ_reset": (C.c_int, [_h]),
+    "differ_add_rows": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),
+    "differ_make_tare": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p, _u8p, _u32p]),
+    "differ_compress_rows": (C.c_int, [_h, _u8p, _u32p, _u64p, _u64p]),
+    "differ_fetch": (C.c_int, [_h, _u64p, _u32p, _u32p, _u64p, _u32p]),
     "cat_sweep_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
     "cat_sweep_streams": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, _u32p, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
     "cat_sweep": (C.c_int, [_h, _u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u32p, _f32p,

@@ -1,0 +1,284 @@
+// lb_differ.cu -- loom's tare and sparsify passes (loom::Differ, src/differ.hpp, src/differ.cc) as a
+// columnar pre-pass over the device-resident row block (sm_100a).
+//
+//   add_rows      per column a 16-bin histogram of the observed raw values (BooleanSummary /
+//                 CountSummary, src/differ.hpp:49-95): one CTA per (row tile, column), the bins live in
+//                 shared memory, a warp merges equal values with match_any before it touches a bin --
+//                 the interesting columns are exactly the ones where nearly every row holds the same value
+//   compress_rows _abs_to_rel (src/differ.cc:248-298): thread per row walks the columns (adjacent threads
+//                 read adjacent rows of a column: coalesced), counts its pos / neg entries, an exclusive
+//                 scan turns counts into CSR offsets, a second walk writes the entries
+// Both are HBM streams over the block: 1 B (BB, DD) or 4 B (DPD, GP) per cell + 1 mask bit; reals are
+// only read by compress_rows.
+#include <algorithm>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "lb_internal.h"
+
+#define DIFFER_BINS 16   // CountSummary::max_count (src/differ.hpp:65); booleans use bins 0 and 1
+
+struct DifferState {
+    unsigned long long *d_hist = nullptr;   // [F][16]
+    int F = 0;
+    uint64_t rows_added = 0;
+    // the last compress_rows result
+    unsigned long long *d_pos_ptr = nullptr, *d_neg_ptr = nullptr;   // [R + 1]
+    uint32_t *d_pos_feature = nullptr, *d_pos_value = nullptr, *d_neg_feature = nullptr;
+    uint64_t rows = 0, n_pos = 0, n_neg = 0;
+    bool have_diff = false;
+};
+
+static void free_diff(DifferState *s) {
+    cudaFree(s->d_pos_ptr); cudaFree(s->d_neg_ptr);
+    cudaFree(s->d_pos_feature); cudaFree(s->d_pos_value); cudaFree(s->d_neg_feature);
+    s->d_pos_ptr = s->d_neg_ptr = nullptr;
+    s->d_pos_feature = s->d_pos_value = s->d_neg_feature = nullptr;
+    s->have_diff = false;
+}
+
+void lb_release_differ(Engine *e) {
+    DifferState *s = (DifferState *)e->differ;
+    if (!s) return;
+    cudaFree(s->d_hist);
+    free_diff(s);
+    delete s;
+    e->differ = nullptr;
+}
+
+// dict_off[f] = first entry of feature f's dictionary in dict_values, or -1 when the cell IS the raw value
+__global__ void k_differ_hist(const FeatDev *feats, RowsDev rows, const int32_t *dict_off, const uint32_t *dict_values,
+                              unsigned long long *hist) {
+    const int f = blockIdx.y;
+    const FeatDev fd = feats[f];
+    if (fd.type == LB_NICH) return;                        // "do not sparsify reals" (src/differ.cc:121)
+    __shared__ unsigned int s_hist[DIFFER_BINS];
+    if (threadIdx.x < DIFFER_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t *mask = rows.mask + (uint64_t)f * rows.W;
+    const int32_t off = dict_off[f];
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < rows.R; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = base + threadIdx.x;
+        uint32_t bin = DIFFER_BINS;
+        if (r < rows.R && ((mask[r >> 5] >> (r & 31)) & 1u)) {
+            uint32_t v = fd.is_wide ? rows.wide[(uint64_t)fd.col * rows.R + r] : (uint32_t)rows.cat8[(uint64_t)fd.col * rows.R + r];
+            if (off >= 0) v = dict_values[off + (int32_t)v];
+            if (v < DIFFER_BINS) bin = v;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin < DIFFER_BINS && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < DIFFER_BINS && s_hist[threadIdx.x])
+        atomicAdd(&hist[(size_t)f * DIFFER_BINS + threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+}
+
+// One row against the tare.  FILL = false: count the entries (written to ptr[r + 1]); FILL = true: write them at ptr[r].
+template <bool FILL>
+__global__ void k_differ_rows(const FeatDev *feats, int F, RowsDev rows, const uint8_t *tare_obs, const uint32_t *tare_val,
+                              unsigned long long *pos_ptr, unsigned long long *neg_ptr, uint32_t *pos_feature,
+                              uint32_t *pos_value, uint32_t *neg_feature) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows.R; r += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long np = FILL ? pos_ptr[r] : 0ull, nn = FILL ? neg_ptr[r] : 0ull;
+        for (int f = 0; f < F; ++f) {
+            const bool obs = (rows.mask[(uint64_t)f * rows.W + (r >> 5)] >> (r & 31)) & 1u;
+            uint32_t v = 0;
+            if (obs) {
+                const int col = feats[f].col;
+                v = feats[f].is_wide ? rows.wide[(uint64_t)col * rows.R + r] : (uint32_t)rows.cat8[(uint64_t)col * rows.R + r];
+            }
+            bool to_pos, to_neg;
+            if (tare_obs[f]) {
+                const bool differs = obs && v != tare_val[f];
+                to_pos = differs;
+                to_neg = !obs || differs;
+            } else {
+                to_pos = obs;
+                to_neg = false;
+            }
+            if (to_pos) {
+                if (FILL) { pos_feature[np] = (uint32_t)f; pos_value[np] = v; }
+                ++np;
+            }
+            if (to_neg) {
+                if (FILL) neg_feature[nn] = (uint32_t)f;
+                ++nn;
+            }
+        }
+        if (!FILL) { pos_ptr[r + 1] = np; neg_ptr[r + 1] = nn; }
+    }
+}
+
+static DifferState *state(Engine *e) {
+    if (!e->differ) e->differ = new DifferState;
+    return (DifferState *)e->differ;
+}
+
+extern "C" int lb_differ_reset(lb_handle h) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("differ_reset before set_model");
+    DifferState *s = state(e);
+    if (s->F != e->F) {
+        cudaFree(s->d_hist);
+        s->d_hist = nullptr;
+        LB_CUDA(cudaMalloc(&s->d_hist, 8 * (size_t)e->F * DIFFER_BINS));
+        s->F = e->F;
+    }
+    LB_CUDA(cudaMemsetAsync(s->d_hist, 0, 8 * (size_t)e->F * DIFFER_BINS, e->stream));
+    s->rows_added = 0;
+    return 0;
+}
+
+// per feature: the offset of its dictionary, -1 = identity
+static std::vector<int32_t> dictionary_offsets(const Engine *e, const int32_t *dpd_offsets) {
+    std::vector<int32_t> off(e->F, -1);
+    int ord = 0;
+    for (int f = 0; f < e->F; ++f)
+        if (e->specs[f].type == LB_DPD) {
+            if (dpd_offsets) off[f] = dpd_offsets[ord];
+            ++ord;
+        }
+    return off;
+}
+
+extern "C" int lb_differ_add_rows(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    DifferState *s = (DifferState *)e->differ;
+    if (!s || !s->d_hist || s->F != e->F) return lb_fail("differ_add_rows before differ_reset");
+    if (!e->R) return 0;
+    LB_TRY(lb_sync_model(e));
+    const std::vector<int32_t> off = dictionary_offsets(e, dpd_offsets);
+    int n_dict = 0;
+    if (dpd_offsets)
+        for (int f = 0, ord = 0; f < e->F; ++f)
+            if (e->specs[f].type == LB_DPD) {
+                if (dpd_offsets[ord + 1] - dpd_offsets[ord] < e->specs[f].dim)
+                    return lb_fail("differ_add_rows: dictionary of feature %d is shorter than its dim", f);
+                n_dict = dpd_offsets[++ord];
+            }
+    const size_t off_bytes = (4 * (size_t)e->F + 255) / 256 * 256;
+    LB_TRY(lb_ensure_scratch(e, off_bytes + 4 * (size_t)std::max(n_dict, 1) + 256));
+    int32_t *d_off = (int32_t *)e->d_scratch;
+    uint32_t *d_dict = (uint32_t *)((char *)e->d_scratch + off_bytes);
+    LB_CUDA(cudaMemcpyAsync(d_off, off.data(), 4 * (size_t)e->F, cudaMemcpyHostToDevice, e->stream));
+    if (n_dict) LB_CUDA(cudaMemcpyAsync(d_dict, dpd_values, 4 * (size_t)n_dict, cudaMemcpyHostToDevice, e->stream));
+    RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    // row tiles x columns; enough CTAs per column to fill the SMs whatever F is
+    const unsigned tiles = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((e->R + 255) / 256, (uint64_t)std::max(1, e->n_sm * 8 / e->F + 1)));
+    k_differ_hist<<<dim3(tiles, (unsigned)e->F), 256, 0, e->stream>>>(e->d_feats, rows, d_off, d_dict, s->d_hist);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+    LB_CUDA(cudaStreamSynchronize(e->stream));       // the staging copies above came from pageable memory
+    s->rows_added += e->R;
+    return 0;
+}
+
+extern "C" int lb_differ_make_tare(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values,
+                                   uint8_t *tare_observed, uint32_t *tare_values) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    DifferState *s = (DifferState *)e->differ;
+    if (!s || !s->d_hist || s->F != e->F) return lb_fail("differ_make_tare before differ_reset");
+    std::vector<unsigned long long> hist((size_t)e->F * DIFFER_BINS);
+    LB_CUDA(cudaMemcpyAsync(hist.data(), s->d_hist, 8 * hist.size(), cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    // _make_tare_type (src/differ.cc:191-206): F comparisons, on the host
+    const float count_threshold = (float)(0.5 * (double)s->rows_added);
+    int ord = 0;
+    for (int f = 0; f < e->F; ++f) {
+        const bool is_dpd = e->specs[f].type == LB_DPD;
+        const unsigned long long *counts = hist.data() + (size_t)f * DIFFER_BINS;
+        uint32_t mode = 0;
+        for (uint32_t i = 0; i < DIFFER_BINS; ++i)
+            if (counts[i] > counts[mode]) mode = i;
+        tare_observed[f] = e->specs[f].type != LB_NICH && (float)counts[mode] > count_threshold;
+        tare_values[f] = 0;
+        if (tare_observed[f]) {
+            uint32_t cell = mode;
+            if (is_dpd && dpd_offsets) {                   // back to the dictionary index the row block stores
+                cell = LB_UNASSIGNED;
+                for (int32_t i = dpd_offsets[ord]; i < dpd_offsets[ord + 1]; ++i)
+                    if (dpd_values[i] == mode) cell = (uint32_t)(i - dpd_offsets[ord]);
+                if (cell == LB_UNASSIGNED) return lb_fail("differ_make_tare: mode of feature %d is not in its dictionary", f);
+            }
+            tare_values[f] = cell;
+        }
+        ord += is_dpd;
+    }
+    return 0;
+}
+
+extern "C" int lb_differ_compress_rows(lb_handle h, const uint8_t *tare_observed, const uint32_t *tare_values,
+                                       uint64_t *n_pos, uint64_t *n_neg) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("differ_compress_rows before set_model");
+    DifferState *s = state(e);
+    free_diff(s);
+    LB_TRY(lb_sync_model(e));
+    const uint64_t R = e->R;
+    LB_CUDA(cudaMalloc(&s->d_pos_ptr, 8 * (size_t)(R + 1)));
+    LB_CUDA(cudaMalloc(&s->d_neg_ptr, 8 * (size_t)(R + 1)));
+    LB_CUDA(cudaMemsetAsync(s->d_pos_ptr, 0, 8, e->stream));
+    LB_CUDA(cudaMemsetAsync(s->d_neg_ptr, 0, 8, e->stream));
+    size_t scan_bytes = 0;
+    LB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, s->d_pos_ptr, s->d_pos_ptr, (int)std::max<uint64_t>(R, 1), e->stream));
+    const size_t obs_bytes = ((size_t)e->F + 255) / 256 * 256, val_bytes = (4 * (size_t)e->F + 255) / 256 * 256;
+    LB_TRY(lb_ensure_scratch(e, obs_bytes + val_bytes + scan_bytes + 256));
+    uint8_t *d_obs = (uint8_t *)e->d_scratch;
+    uint32_t *d_val = (uint32_t *)((char *)e->d_scratch + obs_bytes);
+    void *d_scan = (char *)e->d_scratch + obs_bytes + val_bytes;
+    LB_CUDA(cudaMemcpyAsync(d_obs, tare_observed, (size_t)e->F, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(d_val, tare_values, 4 * (size_t)e->F, cudaMemcpyHostToDevice, e->stream));
+    RowsDev rows{R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((R + 127) / 128, (uint64_t)e->n_sm * 16));
+    unsigned long long total[2] = {0, 0};
+    if (R) {
+        k_differ_rows<false><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
+                                                         nullptr, nullptr, nullptr);
+        LB_CUDA(cudaGetLastError());
+        LB_CUDA(cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, s->d_pos_ptr + 1, s->d_pos_ptr + 1, (int)R, e->stream));
+        LB_CUDA(cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, s->d_neg_ptr + 1, s->d_neg_ptr + 1, (int)R, e->stream));
+        LB_CUDA(cudaMemcpyAsync(&total[0], s->d_pos_ptr + R, 8, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaMemcpyAsync(&total[1], s->d_neg_ptr + R, 8, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    LB_CUDA(cudaMalloc(&s->d_pos_feature, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
+    LB_CUDA(cudaMalloc(&s->d_pos_value, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
+    LB_CUDA(cudaMalloc(&s->d_neg_feature, 4 * (size_t)std::max<unsigned long long>(total[1], 1)));
+    if (R) {
+        k_differ_rows<true><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
+                                                        s->d_pos_feature, s->d_pos_value, s->d_neg_feature);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL] += 4; e->launches[LB_L_MISC] += 4;
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    s->rows = R;
+    s->n_pos = total[0];
+    s->n_neg = total[1];
+    s->have_diff = true;
+    *n_pos = s->n_pos;
+    *n_neg = s->n_neg;
+    return 0;
+}
+
+extern "C" int lb_differ_fetch(lb_handle h, uint64_t *pos_ptr, uint32_t *pos_feature, uint32_t *pos_value,
+                               uint64_t *neg_ptr, uint32_t *neg_feature) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    DifferState *s = (DifferState *)e->differ;
+    if (!s || !s->have_diff || s->rows != e->R) return lb_fail("differ_fetch before differ_compress_rows");
+    LB_CUDA(cudaMemcpyAsync(pos_ptr, s->d_pos_ptr, 8 * (size_t)(s->rows + 1), cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaMemcpyAsync(neg_ptr, s->d_neg_ptr, 8 * (size_t)(s->rows + 1), cudaMemcpyDeviceToHost, e->stream));
+    if (s->n_pos) {
+        LB_CUDA(cudaMemcpyAsync(pos_feature, s->d_pos_feature, 4 * (size_t)s->n_pos, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaMemcpyAsync(pos_value, s->d_pos_value, 4 * (size_t)s->n_pos, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (s->n_neg) LB_CUDA(cudaMemcpyAsync(neg_feature, s->d_neg_feature, 4 * (size_t)s->n_neg, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}

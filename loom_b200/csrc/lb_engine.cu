@@ -324,6 +324,7 @@ extern "C" void lb_destroy(lb_handle h) {
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
     lb_release_proposer(e);
+    lb_release_differ(e);
     dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
     if (e->d_score_aux) cudaFree(e->d_score_aux);

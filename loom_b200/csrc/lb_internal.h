@@ -125,6 +125,7 @@ struct Engine {
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;
     bool kev_pending = false;
     unsigned long long *d_prof = nullptr;  // LB_PROFILE=1: per-kind, per-warp phase cycles of the sweep
+    void *differ = nullptr;                // tare / sparsify state (lb_differ.cu)
 };
 
 // launch-family indices for launch_count
@@ -193,6 +194,9 @@ int lb_launch_restride(Engine *e, const KindHost &src, KindHost &dst);
 int lb_launch_renumber(Engine *e, int kid);
 int lb_launch_validate_rows(Engine *e, int *bad);
 int lb_launch_score_data(Engine *e, double *out);
+
+// tare / sparsify (lb_differ.cu)
+void lb_release_differ(Engine *e);
 
 // structure kernels (lb_struct.cu)
 void lb_free_proposer(Engine *e);      // invalidate (buffers kept)

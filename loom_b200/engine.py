@@ -319,6 +319,36 @@ class Engine:
         self.abi.check(self.abi.query_score(self.h, row_begin, row_end, ptr(out, _f32p)))
         return out
 
+    # -- loom::Differ (src/differ.cc): the tare / sparsify passes over the loaded block
+    def make_tare(self, dpd_offsets=None, dpd_values=None, reset=True):
+        """Differ::add_rows + _make_tare on the loaded block -> (tare_observed uint8 [F], tare_values uint32 [F]);
+        reset=False keeps adding to the summaries of earlier blocks (windows of one stream)"""
+        i32p = C.POINTER(C.c_int32)
+        off = None if dpd_offsets is None else np.ascontiguousarray(dpd_offsets, np.int32)
+        val = None if dpd_values is None else np.ascontiguousarray(dpd_values, np.uint32)
+        if reset:
+            self.abi.check(self.abi.differ_reset(self.h))
+        self.abi.check(self.abi.differ_add_rows(self.h, ptr(off, i32p), ptr(val, _u32p)))
+        F = self.model.n_features
+        obs, values = np.zeros(F, np.uint8), np.zeros(F, np.uint32)
+        self.abi.check(self.abi.differ_make_tare(self.h, ptr(off, i32p), ptr(val, _u32p), ptr(obs, _abi._u8p), ptr(values, _u32p)))
+        return obs, values
+
+    def sparsify(self, tare_observed, tare_values):
+        """Differ::compress_rows on the loaded block -> dict of the arrays set_rows_diff takes"""
+        obs = np.ascontiguousarray(tare_observed, np.uint8)
+        val = np.ascontiguousarray(tare_values, np.uint32)
+        n_pos, n_neg = C.c_uint64(), C.c_uint64()
+        self.abi.check(self.abi.differ_compress_rows(self.h, ptr(obs, _abi._u8p), ptr(val, _u32p), C.byref(n_pos), C.byref(n_neg)))
+        R = self.n_rows
+        pos_ptr, neg_ptr = np.zeros(R + 1, np.uint64), np.zeros(R + 1, np.uint64)
+        pos_f, pos_v = np.zeros(n_pos.value, np.uint32), np.zeros(n_pos.value, np.uint32)
+        neg_f = np.zeros(n_neg.value, np.uint32)
+        self.abi.check(self.abi.differ_fetch(self.h, ptr(pos_ptr, _abi._u64p), ptr(pos_f, _u32p), ptr(pos_v, _u32p),
+                                             ptr(neg_ptr, _abi._u64p), ptr(neg_f, _u32p)))
+        return dict(n_rows=R, tare_observed=obs, tare_values=val, row_has_tare=None, pos_ptr=pos_ptr, pos_feature=pos_f,
+                    pos_value=pos_v, neg_ptr=neg_ptr, neg_feature=neg_f)
+
     def query_sample(self, row, to_sample, n_samples, seed, draw_offset=0, groups=False):
         """n_samples joint draws of the features `to_sample` given the loaded row `row` under this sample
         (the per-latent half of QueryServer Sample): uint32 [n_samples][len(to_sample)] raw cell values

@@ -210,6 +210,8 @@ void lo_destroy(lb_handle h) {
     engine_clear_model(e);
     if (!e->rows_borrowed) { free(e->cat8); free(e->wide); free(e->mask); }
     free(e->hp_store);
+    free(e->differ_hist);
+    free(e->diff_pos_ptr); free(e->diff_neg_ptr); free(e->diff_pos_feature); free(e->diff_pos_value); free(e->diff_neg_feature);
     free(e);
 }
 
@@ -845,5 +847,125 @@ int lo_launch_count(lb_handle h, uint64_t *out, int32_t n, int32_t reset) {
 int lo_kernel_ms(lb_handle h, double *out, int32_t n, int32_t reset) {
     (void)h; (void)reset;
     for (int i = 0; i < n; ++i) out[i] = 0;
+    return 0;
+}
+
+/* ---- loom::Differ (src/differ.hpp, src/differ.cc): the tare and sparsify passes --------------- */
+#define DIFFER_BINS 16   /* CountSummary::max_count (src/differ.hpp:65); BooleanSummary uses bins 0 and 1 */
+
+/* raw count value of a cell: DPD cells hold dictionary indices */
+static uint32_t differ_raw(const engine_t *e, int f, uint32_t cell, const int32_t *dpd_offsets,
+                           const uint32_t *dpd_values) {
+    if (e->specs[f].type != LB_DPD || !dpd_offsets) return cell;
+    int ord = 0;
+    for (int g = 0; g < f; ++g) ord += e->specs[g].type == LB_DPD;
+    return dpd_values[dpd_offsets[ord] + (int32_t)cell];
+}
+
+int lo_differ_reset(lb_handle h) {
+    engine_t *e = h;
+    if (!e->F) return lo_fail("differ_reset before set_model");
+    free(e->differ_hist);
+    e->differ_hist = xcalloc((size_t)e->F * DIFFER_BINS, 8);
+    e->differ_rows = 0;
+    return 0;
+}
+
+/* Differ::add_rows (src/differ.cc:93-127) */
+int lo_differ_add_rows(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values) {
+    engine_t *e = h;
+    if (!e->differ_hist) return lo_fail("differ_add_rows before differ_reset");
+    for (int f = 0; f < e->F; ++f) {
+        if (e->specs[f].type == LB_NICH) continue;          /* "do not sparsify reals" */
+        for (uint64_t r = 0; r < e->R; ++r) {
+            if (!cell_observed(e, f, r)) continue;
+            const uint32_t raw = differ_raw(e, f, cell_raw(e, f, r), dpd_offsets, dpd_values);
+            if (raw < DIFFER_BINS) ++e->differ_hist[(size_t)f * DIFFER_BINS + raw];
+        }
+    }
+    e->differ_rows += e->R;
+    return 0;
+}
+
+/* Differ::_make_tare / _make_tare_type (src/differ.cc:129-146, 191-206) */
+int lo_differ_make_tare(lb_handle h, const int32_t *dpd_offsets, const uint32_t *dpd_values,
+                        uint8_t *tare_observed, uint32_t *tare_values) {
+    engine_t *e = h;
+    if (!e->differ_hist) return lo_fail("differ_make_tare before differ_reset");
+    const float count_threshold = (float)(0.5 * (double)e->differ_rows);
+    int ord = 0;
+    for (int f = 0; f < e->F; ++f) {
+        const int is_dpd = e->specs[f].type == LB_DPD;
+        const uint64_t *counts = e->differ_hist + (size_t)f * DIFFER_BINS;
+        uint32_t mode = 0;
+        for (uint32_t i = 0; i < DIFFER_BINS; ++i)
+            if (counts[i] > counts[mode]) mode = i;
+        tare_observed[f] = e->specs[f].type != LB_NICH && (float)counts[mode] > count_threshold;
+        tare_values[f] = 0;
+        if (tare_observed[f]) {
+            uint32_t cell = mode;
+            if (is_dpd && dpd_offsets) {                    /* back to the dictionary index */
+                cell = LB_UNASSIGNED;
+                for (int32_t i = dpd_offsets[ord]; i < dpd_offsets[ord + 1]; ++i)
+                    if (dpd_values[i] == mode) cell = (uint32_t)(i - dpd_offsets[ord]);
+                if (cell == LB_UNASSIGNED) return lo_fail("differ_make_tare: mode of feature %d is not in its dictionary", f);
+            }
+            tare_values[f] = cell;
+        }
+        ord += is_dpd;
+    }
+    return 0;
+}
+
+/* Differ::compress_rows -> _abs_to_rel_type (src/differ.cc:148-189, 248-298) */
+int lo_differ_compress_rows(lb_handle h, const uint8_t *tare_observed, const uint32_t *tare_values,
+                            uint64_t *n_pos, uint64_t *n_neg) {
+    engine_t *e = h;
+    if (!e->F) return lo_fail("differ_compress_rows before set_model");
+    free(e->diff_pos_ptr); free(e->diff_neg_ptr); free(e->diff_pos_feature); free(e->diff_pos_value); free(e->diff_neg_feature);
+    e->diff_pos_ptr = xcalloc(e->R + 1, 8);
+    e->diff_rows = e->R;
+    e->diff_neg_ptr = xcalloc(e->R + 1, 8);
+    for (int pass = 0; pass < 2; ++pass) {
+        uint64_t np = 0, nn = 0;
+        for (uint64_t r = 0; r < e->R; ++r) {
+            for (int f = 0; f < e->F; ++f) {
+                const int obs = cell_observed(e, f, r);
+                const uint32_t v = obs ? cell_raw(e, f, r) : 0;
+                int to_pos, to_neg;
+                if (tare_observed[f]) {
+                    const int differs = obs && v != tare_values[f];
+                    to_pos = differs;
+                    to_neg = !obs || differs;
+                } else {
+                    to_pos = obs;
+                    to_neg = 0;
+                }
+                if (to_pos) { if (pass) { e->diff_pos_feature[np] = (uint32_t)f; e->diff_pos_value[np] = v; } ++np; }
+                if (to_neg) { if (pass) e->diff_neg_feature[nn] = (uint32_t)f; ++nn; }
+            }
+            e->diff_pos_ptr[r + 1] = np;
+            e->diff_neg_ptr[r + 1] = nn;
+        }
+        if (!pass) {
+            e->diff_pos_feature = xcalloc(np + 1, 4);
+            e->diff_pos_value = xcalloc(np + 1, 4);
+            e->diff_neg_feature = xcalloc(nn + 1, 4);
+        }
+        *n_pos = np; *n_neg = nn;
+    }
+    return 0;
+}
+
+int lo_differ_fetch(lb_handle h, uint64_t *pos_ptr, uint32_t *pos_feature, uint32_t *pos_value,
+                    uint64_t *neg_ptr, uint32_t *neg_feature) {
+    engine_t *e = h;
+    if (!e->diff_pos_ptr || e->diff_rows != e->R) return lo_fail("differ_fetch before differ_compress_rows");
+    const uint64_t np = e->diff_pos_ptr[e->R], nn = e->diff_neg_ptr[e->R];
+    memcpy(pos_ptr, e->diff_pos_ptr, 8 * (e->R + 1));
+    memcpy(neg_ptr, e->diff_neg_ptr, 8 * (e->R + 1));
+    memcpy(pos_feature, e->diff_pos_feature, 4 * np);
+    memcpy(pos_value, e->diff_pos_value, 4 * np);
+    memcpy(neg_feature, e->diff_neg_feature, 4 * nn);
     return 0;
 }

@@ -42,6 +42,12 @@ typedef struct {
     uint8_t *cat8;
     uint32_t *wide;
     uint32_t *mask;
+    /* Differ summaries (src/differ.hpp:49-95): [F][16] counts of the observed raw values in [0,16) */
+    uint64_t *differ_hist;
+    uint64_t differ_rows;
+    /* the last compress_rows result */
+    uint64_t *diff_pos_ptr, *diff_neg_ptr, diff_rows;
+    uint32_t *diff_pos_feature, *diff_pos_value, *diff_neg_feature;
     /* hyper prior (owned copies) */
     lb_hyper_prior hp;
     float *hp_store;

@@ -70,3 +70,94 @@ def test_diff_path_equals_dense_path_oracle(oracle_abi):
 @pytest.mark.gpu
 def test_diff_path_equals_dense_path_gpu(cuda_abi):
     _equivalence(cuda_abi)
+
+
+# ------------------------------------------------------------------------------------------ the passes themselves
+# loom::Differ on the engine (lb_differ_*: SURVEY.md 8f n4) against the independent numpy restatement in
+# loom_b200/tare.py, which the tests above tie to the reference's worked example.
+def differ_case(abi):
+    rng = np.random.default_rng(3)
+    model, rows, _ = synth.generate(700, [("bb", 6), ("dd4", 2), ("dd256", 1), ("dpd5", 2), ("gp", 3), ("nich", 2)],
+                                    density=0.85, seed=6)
+    F8 = model.n8()
+    rows.cat8[:4] = rng.random((4, 700)) < 0.04                      # sparse booleans: tare = 0
+    rows.cat8[4] = rng.random(700) < 0.97                            # nearly always true: tare = 1
+    rows.cat8[F8 - 1] = np.where(rng.random(700) < 0.8, 200, 3)      # dd256: the mode 200 is outside [0,16) -> no tare
+    dpd = [f for f in range(model.n_features) if model.features[f]["type"] == "dpd"]
+    gp = [f for f in range(model.n_features) if model.features[f]["type"] == "gp"]
+    rows.wide[dpd[0] - F8] = np.where(rng.random(700) < 0.9, 2, rows.wide[dpd[0] - F8])   # dictionary index 2
+    rows.wide[gp[0] - F8] = np.where(rng.random(700) < 0.7, 5, rows.wide[gp[0] - F8])
+    rows.wide[gp[1] - F8] = np.where(rng.random(700) < 0.7, 16, rows.wide[gp[1] - F8])    # first value the summary ignores
+    rows.mask[...] = engine_mask(rows, rng)
+    e = Engine(abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    want_obs, want_val = tare.make_tare(model, rows)
+    got_obs, got_val = e.make_tare()
+    assert np.array_equal(got_obs, want_obs) and np.array_equal(got_val[want_obs > 0], want_val[want_obs > 0])
+    assert want_obs[:5].all() and want_obs[dpd[0]] and want_obs[gp[0]] and not want_obs[gp[1]] and not want_obs[F8 - 1]
+    assert not want_obs[-2:].any()                                    # reals
+    want = tare.sparsify(model, rows, want_obs, want_val)
+    got = e.sparsify(got_obs, got_val)
+    for key in ("pos_ptr", "pos_feature", "pos_value", "neg_ptr", "neg_feature"):
+        assert np.array_equal(got[key], want[key]), key
+    assert int(got["pos_ptr"][-1]) < 0.6 * rows.n_cells()             # it does compress
+    # the diff decodes back to the block it came from: scores of every row agree
+    back = Engine(abi)
+    back.set_model(model)
+    back.set_rows_diff(**got)
+    assert np.array_equal(back.query_score(), e.query_score())
+    # an empty tare passes rows through
+    none = e.sparsify(np.zeros(model.n_features, np.uint8), np.zeros(model.n_features, np.uint32))
+    assert int(none["pos_ptr"][-1]) == rows.n_cells() and int(none["neg_ptr"][-1]) == 0
+    # raw DPD values: the [0,16) window and the mode are over the dictionary's VALUES, the tare holds the index
+    offsets = np.array([0, 5, 10], np.int32)
+    values = np.array([100, 101, 7, 103, 104, 0, 1, 2, 3, 4], np.uint32)    # feature dpd[0]: index 2 <-> raw 7
+    obs2, val2 = e.make_tare(offsets, values)
+    assert obs2[dpd[0]] and val2[dpd[0]] == 2
+    values[2] = 50                                                           # now the common value is outside the window
+    obs3, _ = e.make_tare(offsets, values)
+    assert not obs3[dpd[0]]
+    # windows of one stream: summaries add up, the threshold is over ALL rows added
+    W = rows.mask.shape[1]
+    half = RowBlock(352, rows.cat8[:, :352], rows.wide[:, :352], rows.mask[:, :11])
+    rest_obs = rows.observed()[:, 352:]
+    from loom_b200 import pack_mask
+    rest = RowBlock(700 - 352, rows.cat8[:, 352:], rows.wide[:, 352:], pack_mask(rest_obs))
+    w = Engine(abi)
+    w.set_model(model)
+    w.set_rows(half)
+    w.make_tare()
+    w.set_rows(rest)
+    obs4, val4 = w.make_tare(reset=False)
+    assert np.array_equal(obs4, want_obs) and np.array_equal(val4[want_obs > 0], want_val[want_obs > 0])
+    assert W == 22
+
+
+def engine_mask(rows, rng):
+    from loom_b200 import pack_mask
+    obs = rows.observed()
+    obs[:5] |= rng.random(obs[:5].shape) < 0.9                         # the tared booleans are mostly observed
+    return pack_mask(obs)
+
+
+def test_differ_oracle(oracle_abi):
+    differ_case(oracle_abi)
+
+
+def test_differ_worked_example_and_edges(oracle_abi):
+    model = bool_model(5)
+    e = Engine(oracle_abi)
+    e.set_model(model)
+    e.set_rows(RowBlock.from_table(model, [[0, 1, None, 0, 0]]))
+    d = e.sparsify(np.uint8([1, 1, 0, 0, 0]), np.zeros(5, np.uint32))          # doc/adapting.md:323-414
+    assert list(d["pos_feature"]) == [1, 3, 4] and list(d["pos_value"]) == [1, 0, 0] and list(d["neg_feature"]) == [1]
+    # ties go to the lower value and exactly half is not "more than half" (src/differ.hpp:59, differ.cc:197-199)
+    e.set_rows(RowBlock.from_table(model, [[1, 1, 1, None, 0], [0, 1, 0, None, None]]))
+    obs, val = e.make_tare()
+    assert list(obs) == [0, 1, 0, 0, 0] and val[1] == 1
+    with pytest.raises(Exception, match="before differ_reset"):
+        f = Engine(oracle_abi)
+        f.set_model(model)
+        f.set_rows(RowBlock.from_table(model, [[0, 0, 0, 0, 0]]))
+        f.make_tare(reset=False)

@@ -1,5 +1,5 @@
-"""GPU runs of the query path: lb_query_sample against the oracle draw for draw, and the product
-binary loom_query on the device against scores recomputed by the oracle.  Kept in the LAST test file so that a
+"""GPU runs of the rows SURVEY.md 8f added last: the query path (n3) -- lb_query_sample against the oracle draw for draw, the
+product binary loom_query on the device against scores recomputed by the oracle -- and the tare / sparsify passes (n4).  Kept in the LAST test file so that a
 failure here cannot hide the results of the earlier GPU tests under `pytest -x`."""
 import os
 import subprocess
@@ -64,3 +64,11 @@ def test_loom_query_on_the_gpu(tmp_path, infer_on_oracle, oracle_abi):  # noqa: 
     root = tmp_path / "store"
     model, block, rowids = qs.make_store(root, infer_on_oracle)
     qs.mixed_session_case(exe, root, model, block, oracle_abi, tmp_path)
+
+
+# ------------------------------------------------------------------------------------------ tare / sparsify on the device
+@pytest.mark.gpu
+def test_differ_on_the_gpu(cuda_abi):
+    """lb_differ_* against the numpy restatement of loom::Differ: histograms, tare, CSR diff bit for bit"""
+    from test_tare import differ_case
+    differ_case(cuda_abi)
