@@ -105,6 +105,10 @@ int lbio_model_create(int32_t n_features, const lb_feature_spec *specs, const fl
                       const float *topology_py, const lb_hyper_prior *hyper_prior /* may be NULL */,
                       const int32_t *dpd_offsets /* may be NULL: identity dictionaries */,
                       const uint32_t *dpd_values, lbio_model **out);
+/* A model from a schema row (ValueSchema::load, src/product_value.hpp:125-130; written by loom/format.py:79-101): the
+ * file only holds the number of boolean, count and real columns, which is all `loom_tare` / `loom_sparsify` need
+ * (src/tare.cc:52-55).  Count columns are typed GammaPoisson (any 32-bit value), one kind. */
+int lbio_model_from_schema_row(const char *path, lbio_model **out);
 int lbio_model_get(const lbio_model *m, lbio_model_view *out);
 int lbio_model_write(const lbio_model *m, const char *path);
 void lbio_model_free(lbio_model *m);
@@ -155,6 +159,13 @@ int lbio_model_adopt_dictionaries(lbio_model *dst, const lbio_model *src, uint64
 int lbio_stream_stats(const char *path, uint64_t *message_count, uint32_t *max_message_size);
 /* the inverse, for tests / generators: rows as Row messages, dense rows as diff{pos = row, neg = NONE} */
 int lbio_rows_write(const char *path, const lbio_model *m, const lbio_row_block *rows);
+/* The same block by block (Differ::compress_rows streams, src/differ.cc:166-181).  tare_values [F] (may be NULL): the
+ * tare row's cell values, written as the values of neg the way _abs_to_rel_type does (src/differ.cc:277-286). */
+typedef struct lbio_rows_writer lbio_rows_writer;
+int lbio_rows_writer_open(const char *path, lbio_rows_writer **out);
+int lbio_rows_writer_write(lbio_rows_writer *w, const lbio_model *m, const lbio_row_block *rows,
+                           const uint32_t *tare_values);
+int lbio_rows_writer_close(lbio_rows_writer *w);
 
 /* Expand a decoded block into the dense columnar layout of lb_set_rows on the HOST
  * (cat8 [F8][R], wide [FW][R], mask [F][ceil(R/32)], caller-allocated, zeroed here).

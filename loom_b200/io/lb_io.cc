@@ -546,6 +546,41 @@ extern "C" int lbio_model_create(int32_t n_features, const lb_feature_spec *spec
     return 0;
 }
 
+// ValueSchema::load(ProductValue) (src/product_value.hpp:125-130): a schema row only carries the SIZES of the three
+// value classes.  The tare / sparsify passes need nothing more, so the model built from it types every count column
+// as GammaPoisson (a 32-bit cell that takes any value) and puts everything in one kind.
+extern "C" int lbio_model_from_schema_row(const char *path, lbio_model **out) {
+    pbw::InFile file(path);
+    if (!file.is_open()) return fail("failed to open input file %s", path);
+    std::vector<uint8_t> msg;
+    if (!file.read_all(msg)) return fail("failed to parse message from %s", path);
+    Reader r(msg);
+    std::vector<uint8_t> booleans;
+    std::vector<uint32_t> counts;
+    std::vector<float> reals;
+    uint32_t f, wt;
+    while (r.next(f, wt)) {
+        if (f == 2) r.rep_varint(wt, booleans);
+        else if (f == 3) r.rep_varint(wt, counts);
+        else if (f == 4) r.rep_f32(wt, reals);
+        else r.skip(wt);
+    }
+    if (!r.ok) return fail("failed to parse message from %s", path);
+    const size_t F = booleans.size() + counts.size() + reals.size();
+    if (!F) return fail("schema row %s has no fields", path);
+    std::vector<lb_feature_spec> specs(F);
+    for (size_t i = 0; i < F; ++i) {
+        lb_feature_spec &s = specs[i];
+        std::memset(&s, 0, sizeof(s));
+        s.type = i < booleans.size() ? LB_BB : i < booleans.size() + counts.size() ? LB_GP : LB_NICH;
+        s.hp[0] = s.type == LB_NICH ? 0.f : 1.f;
+        s.hp[1] = s.hp[2] = s.hp[3] = 1.f;
+    }
+    const std::vector<uint32_t> f2k(F, 0);
+    const float py[2] = {1.f, 0.f};
+    return lbio_model_create((int32_t)F, specs.data(), nullptr, 0, 1, f2k.data(), py, py, nullptr, nullptr, nullptr, out);
+}
+
 extern "C" int lbio_model_get(const lbio_model *m, lbio_model_view *v) {
     std::memset(v, 0, sizeof(*v));
     v->n_features = (int32_t)m->specs.size();
@@ -1071,26 +1106,59 @@ static void encode_value(Writer &w, uint32_t field, const lbio_model &m, const u
     w.msg(field, v);
 }
 
-extern "C" int lbio_rows_write(const char *path, const lbio_model *m, const lbio_row_block *rows) {
-    pbw::OutFile file(path);
-    if (!file.is_open()) return fail("failed to open output file %s", path);
+// A rows stream written block by block (Differ::compress_rows writes as it reads, src/differ.cc:166-181)
+struct lbio_rows_writer {
+    pbw::OutFile file;
+    std::string path;
+    explicit lbio_rows_writer(const char *p) : file(p), path(p) {}
+};
+
+extern "C" int lbio_rows_writer_open(const char *path, lbio_rows_writer **out) {
+    auto *w = new lbio_rows_writer(path);
+    if (!w->file.is_open()) { delete w; return fail("failed to open output file %s", path); }
+    *out = w;
+    return 0;
+}
+
+extern "C" int lbio_rows_writer_write(lbio_rows_writer *w, const lbio_model *m, const lbio_row_block *rows,
+                                      const uint32_t *tare_values) {
     Writer row, diff;
+    std::vector<uint32_t> neg_values;
     for (uint64_t r = 0; r < rows->n_rows; ++r) {
         row.clear();
         diff.clear();
         const uint64_t p0 = rows->pos_ptr[r], p1 = rows->pos_ptr[r + 1];
         encode_value(diff, 1, *m, rows->pos_feature + p0, rows->pos_value + p0, (size_t)(p1 - p0));
         const uint64_t n0 = rows->neg_ptr ? rows->neg_ptr[r] : 0, n1 = rows->neg_ptr ? rows->neg_ptr[r + 1] : 0;
-        // neg carries the tare's values in loom; consumers only use its observed positions
-        // (remove_diff re-reads the tare), so zeros are written
-        encode_value(diff, 2, *m, rows->neg_feature + n0, nullptr, (size_t)(n1 - n0));
+        // neg carries the tare's values in loom (_abs_to_rel_type, src/differ.cc:277-286); consumers only use its
+        // observed positions (remove_diff re-reads the tare), so without a tare at hand zeros are written
+        const uint32_t *nv = nullptr;
+        if (tare_values && n1 > n0) {
+            neg_values.clear();
+            for (uint64_t i = n0; i < n1; ++i) neg_values.push_back(tare_values[rows->neg_feature[i]]);
+            nv = neg_values.data();
+        }
+        encode_value(diff, 2, *m, rows->neg_feature + n0, nv, (size_t)(n1 - n0));
         if (rows->row_has_tare && rows->row_has_tare[r]) diff.u64(3, 0);
         row.u64(1, rows->rowids ? rows->rowids[r] : r);
         row.msg(2, diff);
-        if (!file.write_stream(row.buf)) return fail("failed to write %s", path);
+        if (!w->file.write_stream(row.buf)) return fail("failed to write %s", w->path.c_str());
     }
-    if (!file.close()) return fail("failed to write %s", path);
     return 0;
+}
+
+extern "C" int lbio_rows_writer_close(lbio_rows_writer *w) {
+    const bool ok = w->file.close();
+    const std::string path = w->path;
+    delete w;
+    return ok ? 0 : fail("failed to write %s", path.c_str());
+}
+
+extern "C" int lbio_rows_write(const char *path, const lbio_model *m, const lbio_row_block *rows) {
+    lbio_rows_writer *w = nullptr;
+    if (lbio_rows_writer_open(path, &w)) return 1;
+    if (lbio_rows_writer_write(w, m, rows, nullptr)) { lbio_rows_writer_close(w); return 1; }
+    return lbio_rows_writer_close(w);
 }
 
 extern "C" int lbio_rows_to_columns(const lbio_model *m, const lbio_row_block *rows, const uint8_t *tare_observed,
@@ -1158,6 +1226,10 @@ extern "C" int lbio_tares_write(const char *path, const lbio_model *m, const uin
     std::vector<uint32_t> features, values;
     for (size_t f = 0; f < m->specs.size(); ++f)
         if (tare_observed[f]) { features.push_back((uint32_t)f); values.push_back(tare_values[f]); }
+    if (features.empty()) {      // "if (schema.total_size(tare)) tares.write_stream(tare)" (src/tare.cc:66-69): an empty stream
+        if (!file.close()) return fail("failed to write %s", path);
+        return 0;
+    }
     Writer outer;
     encode_value(outer, 1, *m, features.data(), values.data(), features.size());
     // encode_value wrote a field-1 submessage; the stream holds the bare ProductValue

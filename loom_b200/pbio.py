@@ -130,6 +130,10 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_open": (C.c_int, [_cs, C.c_int32, _P(C.c_void_p)]),
     "log_write": (C.c_int, [C.c_void_p, _P(LogEntry)]),
     "log_close": (None, [C.c_void_p]),
+    "rows_writer_open": (C.c_int, [_cs, _P(C.c_void_p)]),
+    "rows_writer_write": (C.c_int, [C.c_void_p, _model, C.c_void_p, _u32p]),
+    "rows_writer_close": (C.c_int, [C.c_void_p]),
+    "model_from_schema_row": (C.c_int, [_cs, _P(C.c_void_p)]),
     "query_open": (C.c_int, [_cs, _cs, _P(C.c_void_p)]),
     "query_next": (C.c_int, [C.c_void_p, _model, C.c_void_p, _i32p]),
     "query_respond": (C.c_int, [C.c_void_p, _model, C.c_void_p]),
@@ -235,6 +239,13 @@ class ModelFile:
     def read(path):
         h = _model()
         _check(lib().lbio_model_read(_path(path), C.byref(h)))
+        return ModelFile(h)
+
+    @staticmethod
+    def from_schema_row(path):
+        """the stand-in model loom_tare / loom_sparsify decode rows with (only column counts are known)"""
+        h = _model()
+        _check(lib().lbio_model_from_schema_row(_path(path), C.byref(h)))
         return ModelFile(h)
 
     @staticmethod

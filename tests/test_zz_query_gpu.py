@@ -72,3 +72,12 @@ def test_differ_on_the_gpu(cuda_abi):
     """lb_differ_* against the numpy restatement of loom::Differ: histograms, tare, CSR diff bit for bit"""
     from test_tare import differ_case
     differ_case(cuda_abi)
+
+
+@pytest.mark.gpu
+def test_loom_tare_and_loom_sparsify_on_the_gpu(tmp_path):
+    """the product binaries on the device, in windows of 200 rows"""
+    import __graft_entry__
+    __graft_entry__.build()
+    from test_differ_process import passes_case
+    passes_case(os.path.join(HOST, "loom_tare"), os.path.join(HOST, "loom_sparsify"), tmp_path, 200)
