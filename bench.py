@@ -196,6 +196,23 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
         shutil.rmtree(d, ignore_errors=True)
 
 
+def measure_in_subprocess(script, script_args, timeout=150):
+    """Run one of scratch/*_bench.py in its OWN process and return the JSON line it prints: the rows of
+    SURVEY.md 8f added last (query path, tare / sparsify) are measured beside the headline without being
+    able to disturb it (a fault in them cannot take the bench process or its CUDA context down)."""
+    cmd = [sys.executable, os.path.join(REPO, "scratch", script)] + [str(a) for a in script_args]
+    try:
+        proc = subprocess.run(cmd, capture_output=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after %d s" % timeout}
+    if proc.returncode != 0:
+        return {"error": "exit %d: %s" % (proc.returncode, proc.stderr.decode(errors="replace")[-300:])}
+    try:
+        return json.loads(proc.stdout.decode().strip().splitlines()[-1])
+    except Exception as exc:
+        return {"error": "unparsable output: %s" % exc}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -603,6 +620,14 @@ def main():
             aux["loom_infer_process"] = measure_loom_infer(model, rows, device=local_rank)
         except Exception as exc:
             aux["loom_infer_process"] = {"error": str(exc)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # query path (8f n3) and tare / sparsify (8f n4) on the same C2 mix, each in its own process
+        aux["query"] = measure_in_subprocess("query_bench.py", [R, 1000000])
+        d = aux["differ"] = measure_in_subprocess("differ_bench.py", [R])
+        for part in ("tare", "sparsify"):
+            if isinstance(d.get(part), dict) and "achieved_gb_s" in d[part]:
+                d[part].update({"achieved": d[part]["achieved_gb_s"], "peak": peak, "unit": "GB/s",
+                                "frac": d[part]["achieved_gb_s"] / peak, "bound": "hbm"})
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -27,6 +27,7 @@ struct DifferState {
     unsigned long long *d_pos_ptr = nullptr, *d_neg_ptr = nullptr;   // [R + 1]
     uint32_t *d_pos_feature = nullptr, *d_pos_value = nullptr, *d_neg_feature = nullptr;
     uint64_t rows = 0, n_pos = 0, n_neg = 0;
+    uint64_t cap_rows = 0, cap_pos = 0, cap_neg = 0;    // buffers are kept between calls and only grow
     bool have_diff = false;
 };
 
@@ -35,6 +36,7 @@ static void free_diff(DifferState *s) {
     cudaFree(s->d_pos_feature); cudaFree(s->d_pos_value); cudaFree(s->d_neg_feature);
     s->d_pos_ptr = s->d_neg_ptr = nullptr;
     s->d_pos_feature = s->d_pos_value = s->d_neg_feature = nullptr;
+    s->cap_rows = s->cap_pos = s->cap_neg = 0;
     s->have_diff = false;
 }
 
@@ -218,11 +220,17 @@ extern "C" int lb_differ_compress_rows(lb_handle h, const uint8_t *tare_observed
     LB_CUDA(cudaSetDevice(e->device));
     if (!e->F) return lb_fail("differ_compress_rows before set_model");
     DifferState *s = state(e);
-    free_diff(s);
+    s->have_diff = false;
     LB_TRY(lb_sync_model(e));
     const uint64_t R = e->R;
-    LB_CUDA(cudaMalloc(&s->d_pos_ptr, 8 * (size_t)(R + 1)));
-    LB_CUDA(cudaMalloc(&s->d_neg_ptr, 8 * (size_t)(R + 1)));
+    if (R + 1 > s->cap_rows) {
+        cudaFree(s->d_pos_ptr); cudaFree(s->d_neg_ptr);
+        s->d_pos_ptr = s->d_neg_ptr = nullptr;
+        s->cap_rows = 0;
+        LB_CUDA(cudaMalloc(&s->d_pos_ptr, 8 * (size_t)(R + 1)));
+        LB_CUDA(cudaMalloc(&s->d_neg_ptr, 8 * (size_t)(R + 1)));
+        s->cap_rows = R + 1;
+    }
     LB_CUDA(cudaMemsetAsync(s->d_pos_ptr, 0, 8, e->stream));
     LB_CUDA(cudaMemsetAsync(s->d_neg_ptr, 0, 8, e->stream));
     size_t scan_bytes = 0;
@@ -247,9 +255,21 @@ extern "C" int lb_differ_compress_rows(lb_handle h, const uint8_t *tare_observed
         LB_CUDA(cudaMemcpyAsync(&total[1], s->d_neg_ptr + R, 8, cudaMemcpyDeviceToHost, e->stream));
         LB_CUDA(cudaStreamSynchronize(e->stream));
     }
-    LB_CUDA(cudaMalloc(&s->d_pos_feature, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
-    LB_CUDA(cudaMalloc(&s->d_pos_value, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
-    LB_CUDA(cudaMalloc(&s->d_neg_feature, 4 * (size_t)std::max<unsigned long long>(total[1], 1)));
+    if (total[0] > s->cap_pos || !s->d_pos_feature) {
+        cudaFree(s->d_pos_feature); cudaFree(s->d_pos_value);
+        s->d_pos_feature = s->d_pos_value = nullptr;
+        s->cap_pos = 0;
+        LB_CUDA(cudaMalloc(&s->d_pos_feature, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
+        LB_CUDA(cudaMalloc(&s->d_pos_value, 4 * (size_t)std::max<unsigned long long>(total[0], 1)));
+        s->cap_pos = total[0];
+    }
+    if (total[1] > s->cap_neg || !s->d_neg_feature) {
+        cudaFree(s->d_neg_feature);
+        s->d_neg_feature = nullptr;
+        s->cap_neg = 0;
+        LB_CUDA(cudaMalloc(&s->d_neg_feature, 4 * (size_t)std::max<unsigned long long>(total[1], 1)));
+        s->cap_neg = total[1];
+    }
     if (R) {
         k_differ_rows<true><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
                                                         s->d_pos_feature, s->d_pos_value, s->d_neg_feature);
