@@ -18,7 +18,12 @@ imported in this image, so nothing here comes from running loom's engine.  What 
                       the CUDA path (everything that does not depend on a sampled pick bit for
                       bit; the sweep itself is checked by replay in tests/test_cuda_cat.py).
 
-Run from the repo root:  python tests/golden/make_golden.py
+  query_differ_small.npz  on the same model in its fixed-assignment state: the oracle's query scores, a seeded batch
+                      of query draws, the tare row and a diff of the whole block (regression vectors for the
+                      oracle; the CUDA path reproduces the scores to 1e-5, the diff bit for bit and the draws
+                      wherever its group pick agrees).
+
+Run from the repo root:  python tests/golden/make_golden.py   (or `... make_golden.py query_differ_small`)
 """
 import json
 import os
@@ -186,6 +191,40 @@ def engine_small():
     return out
 
 
+def query_differ_small():
+    """The rows SURVEY.md 8f added (query n3, tare / sparsify n4) on the engine_small model in its fixed-assignment
+    state: Score of 64 rows, 256 joint draws given row 0, the tare row and the diff of the whole block."""
+    from loom_b200 import Engine, Model, RowBlock
+    from loom_b200._abi import Abi
+    oracle = Abi(os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "libloom_oracle.so"), "lo_")
+    z = np.load(os.path.join(HERE, "engine_small.npz"))
+    model = Model(json.loads(str(z["features"])), z["f2k"], kind_py=z["kind_py"])
+    rows = RowBlock(int(z["n_rows"]), z["cat8"], z["wide"], z["mask"])
+    e = Engine(oracle)
+    e.set_model(model)
+    e.set_rows(rows)
+    for k in range(model.n_kinds):
+        a = z["fixed_assign_%d" % k]
+        e.set_groups(k, int(a.max()) + 1)
+        e.set_assignments(k, a)
+    e.accumulate_rows()
+    out = {"query_scores": e.query_score(0, 64).astype(np.float64)}
+    to_sample = np.arange(1, model.n_features, 2, dtype=np.uint32)
+    values, groups = e.query_sample(0, to_sample, 256, seed=5, groups=True)
+    out.update(to_sample=to_sample, sample_seed=np.uint64(5), sample_values=values, sample_groups=groups)
+    obs, val = e.make_tare()
+    # engine_small has no dominant values; a hand-made tare exercises every branch of the diff encoding
+    hand_obs = np.zeros(model.n_features, np.uint8)
+    hand_val = np.zeros(model.n_features, np.uint32)
+    for f, feat in enumerate(model.features):
+        if feat["type"] != "nich" and f % 2 == 0:
+            hand_obs[f], hand_val[f] = 1, 1
+    d = e.sparsify(hand_obs, hand_val)
+    out.update(tare_observed=obs, tare_values=val, hand_tare_observed=hand_obs, hand_tare_values=hand_val,
+               **{k: d[k] for k in ("pos_ptr", "pos_feature", "pos_value", "neg_ptr", "neg_feature")})
+    return out
+
+
 def reference_grids():
     """Outputs of the reference's own loom/gridding.py (pure numpy, importable by file path even
     though the loom package is not): pins loom_b200/hyperprior.py.  Only runs where
@@ -206,12 +245,16 @@ def reference_grids():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["query_differ_small"]:      # added later: leaves the other fixtures untouched
+        np.savez_compressed(os.path.join(HERE, "query_differ_small.npz"), **query_differ_small())
+        sys.exit(0)
     rng = np.random.default_rng(20261019)
     with open(os.path.join(HERE, "closed_forms.json"), "w") as f:
         json.dump(closed_forms(rng), f, indent=0)
     with open(os.path.join(HERE, "structural.json"), "w") as f:
         json.dump(structural(), f, indent=1)
     np.savez_compressed(os.path.join(HERE, "engine_small.npz"), **engine_small())
+    np.savez_compressed(os.path.join(HERE, "query_differ_small.npz"), **query_differ_small())
     grids = reference_grids()
     if grids is not None:
         with open(os.path.join(HERE, "reference_grids.json"), "w") as f:

@@ -168,3 +168,43 @@ def test_hyperprior_grids_match_the_reference_gridding():
     d = hp.defaults()
     assert len(d["dd"]["alpha"]) == 12 and len(d["gp"]["alpha"]) == 100 and len(d["nich"]["mu"]) == 201
     assert len(d["nich"]["kappa"]) == 30 and len(d["dpd"]["gamma"]) == 30 and len(d["dpd"]["alpha"]) == 20
+
+
+# ------------------------------------------------------------------------------------------ query / differ fixture
+def query_differ_case(abi, small, exact):
+    """tests/golden/query_differ_small.npz: Score, a seeded batch of draws, the tare row and a diff of the block.
+    exact = the oracle itself (regression, bit for bit); otherwise the CUDA path (scores to 1e-5, the diff bit for
+    bit, draws wherever the group pick agrees)."""
+    z, model, rows = small
+    q = np.load(os.path.join(GOLDEN, "query_differ_small.npz"))
+    e = Engine(abi)
+    e.set_model(model)
+    e.set_rows(rows)
+    for k in range(model.n_kinds):
+        a = z["fixed_assign_%d" % k]
+        e.set_groups(k, int(a.max()) + 1)
+        e.set_assignments(k, a)
+    e.accumulate_rows()
+    assert rel_err(e.query_score(0, 64), q["query_scores"]).max() <= (1e-7 if exact else SCORE_TOL)
+    values, groups = e.query_sample(0, q["to_sample"], 256, seed=int(q["sample_seed"]), groups=True)
+    if exact:
+        assert np.array_equal(values, q["sample_values"]) and np.array_equal(groups, q["sample_groups"])
+    else:
+        assert (groups == q["sample_groups"]).mean() > 0.995
+        for j, f in enumerate(q["to_sample"]):
+            same = groups[:, model.f2k[f]] == q["sample_groups"][:, model.f2k[f]]
+            a, b = values[same, j], q["sample_values"][same, j]
+            if model.features[int(f)]["type"] == "nich":
+                a, b = a.copy().view(np.float32).astype(np.float64), b.copy().view(np.float32).astype(np.float64)
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-5)
+            else:
+                assert (a == b).mean() > 0.99
+    obs, val = e.make_tare()
+    assert np.array_equal(obs, q["tare_observed"]) and np.array_equal(val, q["tare_values"])
+    d = e.sparsify(q["hand_tare_observed"], q["hand_tare_values"])
+    for key in ("pos_ptr", "pos_feature", "pos_value", "neg_ptr", "neg_feature"):
+        assert np.array_equal(d[key], q[key]), key
+
+
+def test_oracle_reproduces_query_and_differ_fixture(oracle_abi, small):
+    query_differ_case(oracle_abi, small, True)

@@ -81,3 +81,16 @@ def test_loom_tare_and_loom_sparsify_on_the_gpu(tmp_path):
     __graft_entry__.build()
     from test_differ_process import passes_case
     passes_case(os.path.join(HOST, "loom_tare"), os.path.join(HOST, "loom_sparsify"), tmp_path, 200)
+
+
+# ------------------------------------------------------------------------------------------ committed fixture
+@pytest.mark.gpu
+def test_cuda_reproduces_query_and_differ_fixture(cuda_abi):
+    """tests/golden/query_differ_small.npz through the C ABI on the device"""
+    import json
+    import test_golden as tg
+    from loom_b200 import Model, RowBlock
+    z = np.load(os.path.join(tg.GOLDEN, "engine_small.npz"))
+    model = Model(json.loads(str(z["features"])), z["f2k"], kind_py=z["kind_py"])
+    rows = RowBlock(int(z["n_rows"]), z["cat8"], z["wide"], z["mask"])
+    tg.query_differ_case(cuda_abi, (z, model, rows), False)
