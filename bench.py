@@ -623,6 +623,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # query path (8f n3) and tare / sparsify (8f n4) on the same C2 mix, each in its own process
         aux["query"] = measure_in_subprocess("query_bench.py", [R, 1000000])
+        aux["score_error"] = measure_in_subprocess("score_error.py", [20000])     # parity check 2, per feature type
         d = aux["differ"] = measure_in_subprocess("differ_bench.py", [R])
         for part in ("tare", "sparsify"):
             if isinstance(d.get(part), dict) and "achieved_gb_s" in d[part]:

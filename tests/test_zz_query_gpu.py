@@ -94,3 +94,20 @@ def test_cuda_reproduces_query_and_differ_fixture(cuda_abi):
     model = Model(json.loads(str(z["features"])), z["f2k"], kind_py=z["kind_py"])
     rows = RowBlock(int(z["n_rows"]), z["cat8"], z["wide"], z["mask"])
     tg.query_differ_case(cuda_abi, (z, model, rows), False)
+
+
+# ------------------------------------------------------------------------------------------ score error per feature type
+@pytest.mark.gpu
+def test_score_error_per_feature_type(oracle_abi, cuda_abi):
+    """SURVEY.md 8c, parity check 2: device scores against the float64 oracle within 1e-5 * max(1, |score|) for EVERY
+    feature type separately (max over all row x group scores), float moments against a float64 recomputation"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HOST), "..", "scratch"))
+    import score_error
+    report = score_error.measure(cuda_abi, oracle_abi, 5000)
+    print(report)
+    for t, entry in report.items():
+        assert entry["max_err"] <= 1e-5, (t, entry)
+        assert entry["p999_err"] <= entry["max_err"]
+        if "moment_max_rel_err" in entry:
+            assert entry["moment_max_rel_err"] <= 1e-9, (t, entry)
