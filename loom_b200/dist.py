@@ -54,3 +54,68 @@ def sharded_kind_proposer_score(engine, rank, world, fetch=True, group=None):
     if world > 1:
         allreduce_proposer_tables(engine, group)
     return engine.proposer_finish(fetch=fetch)
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-sharded bulk accumulate (K2, SURVEY.md 8e row 2): every rank adds ITS rows to zeroed group tables, the tables
+# are combined across ranks, every rank ends with the statistics of all rows.  Integer statistics (clustering counts,
+# BB heads / tails, DD / DPD counts, GP count / sum, NICH count) are sums, so one all-reduce(sum) is exact under any
+# order.  Float moments: GP log_prod is a sum; NICH (mean, count_times_variance) are merged with the pairwise update of
+# Chan et al. over two more all-reduces (sum of n*mean, then sum of ctv + n*(mean - global mean)^2), float64.
+def _feature_rows(model, kind):
+    """[(type, first int row, int rows, first flt row)] of the features of `kind` in its tables (include/loom_b200.h)"""
+    out, i, f = [], 0, 0
+    for fid in model.kind_features(kind):
+        feat = model.features[fid]
+        t = feat["type"]
+        ni = {"bb": 2, "gp": 2, "nich": 1}.get(t)
+        if ni is None:
+            ni = len(feat["alphas"] if t == "dd" else feat["betas"]) + 1
+        nf = {"gp": 1, "nich": 2}.get(t, 0)
+        out.append((t, i, ni, f))
+        i, f = i + ni, f + nf
+    return out
+
+
+def _allreduce_numpy(x, device, group=None):
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def sharded_accumulate_rows(engine, rank, world, group=None):
+    """accumulate_rows of the whole block with rows [rank*R/world, (rank+1)*R/world) added on this rank.
+    Every kind must hold groups 0..n-1 (all used by some row) and the assignments of all rows; on return every rank
+    holds the full statistics, as a single-rank accumulate_rows would leave them."""
+    import torch
+    device = torch.device("cuda", torch.cuda.current_device()) if engine.abi.prefix == "lb_" else None
+    R = engine.n_rows
+    lo, hi = (R * rank) // world, (R * (rank + 1)) // world
+    model = engine.model
+    for k in range(engine.n_kinds()):
+        assign = engine.get_assignments(k)
+        n = int(assign[assign != 0xFFFFFFFF].max()) + 1 if (assign != 0xFFFFFFFF).any() else 0
+        engine.set_groups(k, n)                       # zeroed tables (also clears the assignments)
+        engine.set_assignments(k, assign)
+        engine.accumulate_rows(k, lo, hi, +1)
+        counts, ints, flts = engine.get_groups(k)
+        counts, ints, flts = counts[:n].astype(np.int64), ints[:, :n].astype(np.int64), flts[:, :n].copy()
+        if world > 1:
+            local_ints = ints.copy()
+            counts = _allreduce_numpy(counts, device, group)
+            ints = _allreduce_numpy(ints, device, group)
+            for t, i0, ni, f0 in _feature_rows(model, k):
+                if t == "gp":
+                    flts[f0] = _allreduce_numpy(flts[f0], device, group)
+                elif t == "nich":
+                    n_r, n_all = local_ints[i0].astype(np.float64), ints[i0].astype(np.float64)
+                    mean_r, ctv_r = flts[f0].copy(), flts[f0 + 1].copy()
+                    mean = _allreduce_numpy(n_r * mean_r, device, group) / np.maximum(n_all, 1.0)
+                    flts[f0] = np.where(n_all > 0, mean, 0.0)
+                    flts[f0 + 1] = _allreduce_numpy(ctv_r + n_r * (mean_r - mean) ** 2, device, group)
+        engine.set_groups(k, n, counts.astype(np.uint32), ints.astype(np.uint32), flts)
+        engine.set_assignments(k, assign)

@@ -87,6 +87,44 @@ dist.destroy_process_group()
 '''
 
 
+ACCUMULATE_WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np
+import torch, torch.distributed as dist
+from loom_b200 import Engine, _abi, synth
+from loom_b200.dist import sharded_accumulate_rows
+backend = sys.argv[1]
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+if backend == "nccl":
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    abi = _abi.load_cuda()
+else:
+    dist.init_process_group("gloo")
+    abi = _abi.Abi(os.path.join({repo!r}, "oracle", "libloom_oracle.so"), "lo_")
+model, rows, truth = synth.generate(3001, [("bb", 3), ("dd16", 2), ("dpd5", 2), ("gp", 3), ("nich", 3)], density=0.6, seed=19)
+def engine():
+    e = Engine(abi, device=rank if backend == "nccl" else 0)
+    e.set_model(model); e.set_rows(rows)
+    for k in range(model.n_kinds):
+        uniq, inv = np.unique(truth["assign"][k].astype(np.uint32), return_inverse=True)
+        e.set_groups(k, len(uniq)); e.set_assignments(k, inv.astype(np.uint32))
+    return e
+ref = engine(); ref.accumulate_rows()                 # all rows on one rank
+e = engine(); sharded_accumulate_rows(e, rank, world)
+for k in range(model.n_kinds):
+    (c0, i0, f0), (c1, i1, f1) = ref.get_groups(k), e.get_groups(k)
+    assert np.array_equal(c0, c1) and np.array_equal(i0, i1)                       # integers: bit-exact
+    assert np.allclose(f0, f1, rtol=1e-9, atol=1e-9)                               # float64 moments, merged pairwise
+    assert np.array_equal(ref.get_assignments(k), e.get_assignments(k))
+    assert np.abs(ref.score_rows(k, 0, 64) - e.score_rows(k, 0, 64)).max() <= 1e-5
+assert abs(ref.score_data() - e.score_data()) <= 1e-6 * abs(ref.score_data())
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ok.%d" % rank), "w").write("1")
+dist.destroy_process_group()
+'''
+
+
 def _run(backend, tmp_path, worker=None):
     script = tmp_path / "worker.py"
     script.write_text((worker or WORKER).format(repo=REPO))
@@ -121,3 +159,9 @@ def test_kind_sharded_sweep_nccl(cuda_abi, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run("nccl", tmp_path, KIND_SHARD_WORKER)
+
+
+def test_row_sharded_accumulate_gloo_cpu(oracle_abi, tmp_path):
+    """bulk accumulate (K2) with rows sharded over 2 ranks and the group tables combined == one rank over all rows"""
+    _run("gloo", tmp_path, ACCUMULATE_WORKER)
+

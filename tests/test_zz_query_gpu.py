@@ -111,3 +111,13 @@ def test_score_error_per_feature_type(oracle_abi, cuda_abi):
         assert entry["p999_err"] <= entry["max_err"]
         if "moment_max_rel_err" in entry:
             assert entry["moment_max_rel_err"] <= 1e-9, (t, entry)
+
+
+# ------------------------------------------------------------------------------------------ row-sharded accumulate over NCCL
+@pytest.mark.gpu
+def test_row_sharded_accumulate_nccl(cuda_abi, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import test_dist
+    test_dist._run("nccl", tmp_path, test_dist.ACCUMULATE_WORKER)
