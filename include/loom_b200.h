@@ -327,6 +327,17 @@ int LB_NAME(set_hyper_prior)(lb_handle h, const lb_hyper_prior *prior);
 int LB_NAME(hyper_run)(lb_handle h, uint64_t seed);
 int LB_NAME(get_hypers)(lb_handle h, lb_feature_spec *specs, float *aux, float *kind_py,
                         float *topology_py);
+/* The same with the tasks sharded (they are independent: src/hyper_kernel.cc:205-234 runs them as OpenMP
+ * tasks with rng_t(seed + taskid)).  Task 0 = topology, 1..K = clustering of kind k-1, 1+K+f = feature f;
+ * task_mask [1 + K + F] (0/1) selects the tasks THIS call runs, NULL = all.  Draws are keyed by
+ * (seed, task id), so a masked run chooses exactly what the full run chooses for those tasks: ranks that
+ * each run a share and then exchange the chosen values (set_hypers) end where hyper_run ends. */
+int LB_NAME(hyper_run_tasks)(lb_handle h, uint64_t seed, const uint8_t *task_mask);
+/* Install hyper-parameters chosen elsewhere -- the gather step of the sharded hyper kernel.  Same arrays
+ * as get_hypers (only hp[] of each spec is read; type / dim / aux_off must match the model); cached
+ * scorers are rebuilt as after hyper_run. */
+int LB_NAME(set_hypers)(lb_handle h, const lb_feature_spec *specs, const float *aux, const float *kind_py,
+                        const float *topology_py);
 
 /* Device timing for bench.py (CUDA events on the engine's stream; the oracle
  * uses a monotonic clock). */

@@ -82,6 +82,8 @@ SIGNATURES = {
     "get_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),
     "set_hyper_prior": (C.c_int, [_h, C.POINTER(HyperPrior)]),
     "hyper_run": (C.c_int, [_h, C.c_uint64]),
+    "hyper_run_tasks": (C.c_int, [_h, C.c_uint64, _u8p]),
+    "set_hypers": (C.c_int, [_h, C.POINTER(FeatureSpec), _f32p, _f32p, _f32p]),
     "get_hypers": (C.c_int, [_h, C.POINTER(FeatureSpec), _f32p, _f32p, _f32p]),
     "sync": (C.c_int, [_h]),
     "timer_start": (C.c_int, [_h]),

@@ -579,11 +579,12 @@ __device__ double hyper_block_sum(double v, double *s_red) {
 
 __global__ void __launch_bounds__(256)
 k_hyper_features(const KindDev *kinds, FeatDev *feats, const uint32_t *f2k, float *aux, HyperGrids hg,
-                 uint64_t seed, int K) {
+                 uint64_t seed, int K, const uint8_t *task_mask) {
     __shared__ double s_red[8];
     __shared__ double s_scores[256];
     __shared__ int s_pick;
     const int fid = blockIdx.x;
+    if (task_mask && !task_mask[1 + K + fid]) return;      // another rank runs this feature's task
     FeatDev f = feats[fid];
     const KindDev &kd = kinds[f2k[fid]];
     const int G = kd.G, st = kd.Gcap;
@@ -673,19 +674,22 @@ k_hyper_features(const KindDev *kinds, FeatDev *feats, const uint32_t *f2k, floa
     }
 }
 
-extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
+extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) { return lb_hyper_run_tasks(h, seed, nullptr); }
+
+extern "C" int lb_hyper_run_tasks(lb_handle h, uint64_t seed, const uint8_t *task_mask) {
     Engine *e = (Engine *)h;
     LB_CUDA(cudaSetDevice(e->device));
     LB_TRY(lb_sync_model(e));
     const int K = (int)e->kinds.size(), F = e->F;
     // task 0: topology; tasks 1..K: per-kind clustering (host, float64: tiny count vectors)
-    if (!e->hp[0].empty()) {
+    if (!e->hp[0].empty() && (!task_mask || task_mask[0])) {
         std::vector<uint32_t> fc(K);
         for (int k = 0; k < K; ++k) fc[k] = (uint32_t)e->kinds[k].fids.size();
         sample_py_posterior(e->hp[0], fc.data(), K, seed, 0, &e->topo[0], &e->topo[1]);
     }
     if (!e->hp[1].empty()) {
         for (int k = 0; k < K; ++k) {
+            if (task_mask && !task_mask[1 + k]) continue;
             KindHost &kh = e->kinds[k];
             std::vector<uint32_t> counts(kh.G);
             LB_CUDA(cudaMemcpyAsync(counts.data(), kh.counts, 4 * (size_t)kh.G, cudaMemcpyDeviceToHost, e->stream));
@@ -714,7 +718,12 @@ extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
         uint32_t *d_f2k = nullptr;
         LB_TRY(dalloc(&d_f2k, F));
         LB_CUDA(cudaMemcpyAsync(d_f2k, e->f2k.data(), 4 * (size_t)F, cudaMemcpyHostToDevice, e->stream));
-        k_hyper_features<<<F, 256, 0, e->stream>>>(e->d_kinds, e->d_feats, d_f2k, e->d_aux, hg, seed, K);
+        uint8_t *d_mask = nullptr;
+        if (task_mask) {
+            LB_TRY(dalloc(&d_mask, (size_t)(1 + K + F)));
+            LB_CUDA(cudaMemcpyAsync(d_mask, task_mask, (size_t)(1 + K + F), cudaMemcpyHostToDevice, e->stream));
+        }
+        k_hyper_features<<<F, 256, 0, e->stream>>>(e->d_kinds, e->d_feats, d_f2k, e->d_aux, hg, seed, K, d_mask);
         LB_CUDA(cudaGetLastError());
         e->launches[LB_L_TOTAL]++; e->launches[LB_L_HYPER]++;
         // pull the chosen hypers back into the host mirror
@@ -727,6 +736,7 @@ extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
             for (int c = 0; c < 4; ++c) e->specs[f].hp[c] = feats[f].hp[c];
         cudaFree(d_flat);
         cudaFree(d_f2k);
+        if (d_mask) cudaFree(d_mask);
     }
     // DPD features (src/hyper_kernel.cc:90-181): auxiliary-variable sampler on the host over the
     // feature's count table (lb_dpd_hyper.h); task id 1 + K + f like every other feature
@@ -734,6 +744,7 @@ extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
         for (int f = 0; f < F; ++f) {
             lb_feature_spec &s = e->specs[f];
             if (s.type != LB_DPD || s.dim <= 0) continue;
+            if (task_mask && !task_mask[1 + K + f]) continue;
             KindHost &kh = e->kinds[e->f2k[f]];
             int j = -1;
             for (size_t q = 0; q < kh.fids.size(); ++q) if (kh.fids[q] == f) j = (int)q;
@@ -752,6 +763,33 @@ extern "C" int lb_hyper_run(lb_handle h, uint64_t seed) {
     e->model_dirty = true;   // derived fields (a_total, ...) and cached scorers depend on the hypers
     LB_TRY(lb_sync_model(e));
     for (int k = 0; k < K; ++k) LB_TRY(lb_launch_refresh(e, k));   // mixture.init(shared)
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// the gather step of the sharded hyper kernel: install hypers chosen elsewhere
+extern "C" int lb_set_hypers(lb_handle h, const lb_feature_spec *specs, const float *aux, const float *kind_py,
+                             const float *topology_py) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("set_hypers before set_model");
+    LB_TRY(lb_sync_model(e));
+    if (specs)
+        for (int f = 0; f < e->F; ++f) {
+            if (specs[f].type != e->specs[f].type || specs[f].dim != e->specs[f].dim || specs[f].aux_off != e->specs[f].aux_off)
+                return lb_fail("set_hypers: feature %d does not match the model", f);
+            for (int c = 0; c < 4; ++c) e->specs[f].hp[c] = specs[f].hp[c];
+        }
+    if (aux && !e->aux.empty()) std::copy(aux, aux + e->aux.size(), e->aux.begin());
+    if (kind_py)
+        for (size_t k = 0; k < e->kinds.size(); ++k) {
+            e->kinds[k].alpha = kind_py[2 * k];
+            e->kinds[k].d = kind_py[2 * k + 1];
+        }
+    if (topology_py) { e->topo[0] = topology_py[0]; e->topo[1] = topology_py[1]; }
+    e->model_dirty = true;
+    LB_TRY(lb_sync_model(e));
+    for (int k = 0; k < (int)e->kinds.size(); ++k) LB_TRY(lb_launch_refresh(e, k));
     LB_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }

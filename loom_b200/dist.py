@@ -119,3 +119,38 @@ def sharded_accumulate_rows(engine, rank, world, group=None):
                     flts[f0 + 1] = _allreduce_numpy(ctv_r + n_r * (mean_r - mean) ** 2, device, group)
         engine.set_groups(k, n, counts.astype(np.uint32), ints.astype(np.uint32), flts)
         engine.set_assignments(k, assign)
+
+
+# ---------------------------------------------------------------------------------------------
+# Feature-sharded hyper kernel: the tasks of HyperKernel::run are independent
+# (src/hyper_kernel.cc:205-234), so rank r runs the tasks t with t % world == r on its replica of the state and the
+# chosen values are exchanged: every rank zeroes what it did not choose and one all-reduce(sum) per array puts the
+# owner's value everywhere (x + 0 is exact).  Draws are keyed by (seed, task id): the result equals hyper_run's.
+def sharded_hyper_run(engine, rank, world, seed, group=None):
+    import torch
+    K, F = engine.n_kinds(), engine.model.n_features
+    owner = np.arange(1 + K + F) % world
+    engine.hyper_run(seed, task_mask=(owner == rank).astype(np.uint8))
+    if world == 1:
+        return
+    device = torch.device("cuda", torch.cuda.current_device()) if engine.abi.prefix == "lb_" else None
+    specs, aux, kind_py, topo = engine.get_hypers()
+    hp = np.array([[specs[f].hp[c] for c in range(4)] for f in range(F)], np.float32)
+    aux = np.array(aux, np.float32)
+    mine_f = owner[1 + K:] == rank
+    hp[~mine_f] = 0
+    for f in range(F):
+        if not mine_f[f] and specs[f].dim > 0 and specs[f].type in (1, 2):      # DD alphas / DPD betas of unowned features
+            aux[specs[f].aux_off:specs[f].aux_off + specs[f].dim] = 0
+    kind_py = np.array(kind_py, np.float32)
+    kind_py[owner[1:1 + K] != rank] = 0
+    topo = np.array(topo, np.float32) * (owner[0] == rank)
+    hp = _allreduce_numpy(hp, device, group)
+    if len(aux):
+        aux = _allreduce_numpy(aux, device, group)
+    kind_py = _allreduce_numpy(kind_py, device, group)
+    topo = _allreduce_numpy(topo, device, group)
+    for f in range(F):
+        for c in range(4):
+            specs[f].hp[c] = hp[f, c]
+    engine.set_hypers(specs, aux, kind_py, topo)

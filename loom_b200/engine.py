@@ -426,8 +426,22 @@ class Engine:
         self.abi.check(self.abi.set_hyper_prior(self.h, C.byref(hp)))
         self._keep = keep
 
-    def hyper_run(self, seed):
-        self.abi.check(self.abi.hyper_run(self.h, seed))
+    def hyper_run(self, seed, task_mask=None):
+        """HyperKernel::run; task_mask [1 + K + F] (topology | kind clusterings | features) runs a share of the tasks"""
+        if task_mask is None:
+            self.abi.check(self.abi.hyper_run(self.h, seed))
+        else:
+            m = np.ascontiguousarray(task_mask, np.uint8)
+            assert len(m) == 1 + self.n_kinds() + self.model.n_features
+            self.abi.check(self.abi.hyper_run_tasks(self.h, seed, ptr(m, _u8p)))
+
+    def set_hypers(self, specs, aux, kind_py, topology):
+        """install hypers chosen elsewhere (the arrays get_hypers returns)"""
+        full_aux = np.zeros(max(len(aux), 1), np.float32)
+        full_aux[:len(aux)] = aux
+        kind_py = np.ascontiguousarray(kind_py, np.float32)
+        topology = np.ascontiguousarray(topology, np.float32)
+        self.abi.check(self.abi.set_hypers(self.h, specs, ptr(full_aux, _f32p), ptr(kind_py, _f32p), ptr(topology, _f32p)))
 
     def get_hypers(self):
         F = self.model.n_features

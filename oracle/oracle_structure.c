@@ -469,11 +469,13 @@ static void dpd_hyper(engine_t *e, kind_t *k, int j, lb_feature_spec *s, uint64_
 }
 
 /* HyperKernel::run (src/hyper_kernel.cc:195-235). */
-int lo_hyper_run(lb_handle h, uint64_t seed) {
+int lo_hyper_run(lb_handle h, uint64_t seed) { return lo_hyper_run_tasks(h, seed, NULL); }
+
+int lo_hyper_run_tasks(lb_handle h, uint64_t seed, const uint8_t *task_mask) {
     engine_t *e = h;
     const int K = e->K, F = e->F;
     /* task 0: topology */
-    if (e->hp.n_topology) {
+    if (e->hp.n_topology && (!task_mask || task_mask[0])) {
         uint32_t *fc = calloc(K, 4);
         for (int k = 0; k < K; ++k) fc[k] = (uint32_t)e->kinds[k].nf;
         sample_py_posterior(e->hp.topology, e->hp.n_topology, fc, K, seed, 0, &e->topo_alpha,
@@ -482,6 +484,7 @@ int lo_hyper_run(lb_handle h, uint64_t seed) {
     }
 #pragma omp parallel for schedule(dynamic, 1)
     for (int task = 1; task < 1 + K + F; ++task) {
+        if (task_mask && !task_mask[task]) continue;
         if (task < 1 + K) {
             kind_t *k = &e->kinds[task - 1];
             if (e->hp.n_clustering) {
@@ -525,5 +528,28 @@ int lo_hyper_run(lb_handle h, uint64_t seed) {
         }
     }
     for (int k = 0; k < K; ++k) kind_refresh_all(e, &e->kinds[k]); /* mixture.init(shared) */
+    return 0;
+}
+
+/* the gather step of the sharded hyper kernel: install hypers chosen elsewhere */
+int lo_set_hypers(lb_handle h, const lb_feature_spec *specs, const float *aux, const float *kind_py,
+                  const float *topology_py) {
+    engine_t *e = h;
+    if (!e->F) return lo_fail("set_hypers before set_model");
+    if (specs)
+        for (int f = 0; f < e->F; ++f) {
+            if (specs[f].type != e->specs[f].type || specs[f].dim != e->specs[f].dim || specs[f].aux_off != e->specs[f].aux_off)
+                return lo_fail("set_hypers: feature %d does not match the model", f);
+            memcpy(e->specs[f].hp, specs[f].hp, sizeof(specs[f].hp));
+        }
+    if (aux && e->n_aux) memcpy(e->aux, aux, 4u * (size_t)e->n_aux);
+    if (kind_py)
+        for (int k = 0; k < e->K; ++k) {
+            e->kinds[k].alpha = kind_py[2 * k];
+            e->kinds[k].d = kind_py[2 * k + 1];
+            kind_refresh_clustering(&e->kinds[k]);
+        }
+    if (topology_py) { e->topo_alpha = topology_py[0]; e->topo_d = topology_py[1]; }
+    for (int k = 0; k < e->K; ++k) kind_refresh_all(e, &e->kinds[k]);
     return 0;
 }

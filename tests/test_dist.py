@@ -125,6 +125,50 @@ dist.destroy_process_group()
 '''
 
 
+HYPER_WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests"))
+import numpy as np
+import torch, torch.distributed as dist
+from loom_b200 import Engine, _abi, synth
+from loom_b200.dist import sharded_hyper_run
+from test_dpd import GRIDS
+backend = sys.argv[1]
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+if backend == "nccl":
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    abi = _abi.load_cuda()
+else:
+    dist.init_process_group("gloo")
+    abi = _abi.Abi(os.path.join({repo!r}, "oracle", "libloom_oracle.so"), "lo_")
+model, rows, truth = synth.generate(1500, [("bb", 3), ("dd16", 2), ("dpd5", 2), ("gp", 3), ("nich", 3)], density=0.6, seed=23)
+grids = dict(GRIDS, bb={{"alpha": [0.5, 2.0], "beta": [0.5, 2.0]}})
+def engine():
+    e = Engine(abi, device=rank if backend == "nccl" else 0)
+    e.set_model(model); e.set_rows(rows)
+    for k in range(model.n_kinds):
+        uniq, inv = np.unique(truth["assign"][k].astype(np.uint32), return_inverse=True)
+        e.set_groups(k, len(uniq)); e.set_assignments(k, inv.astype(np.uint32))
+    e.accumulate_rows()
+    e.set_hyper_prior(grids)
+    return e
+ref, e = engine(), engine()
+for seed in (1, 2):                                    # two rounds: the second starts from exchanged hypers
+    ref.hyper_run(seed)
+    sharded_hyper_run(e, rank, world, seed)
+    (s0, a0, k0, t0), (s1, a1, k1, t1) = ref.get_hypers(), e.get_hypers()
+    for f in range(model.n_features):
+        assert [s0[f].hp[c] for c in range(4)] == [s1[f].hp[c] for c in range(4)], f
+    assert np.array_equal(a0, a1) and np.array_equal(k0, k1) and np.array_equal(t0, t1)
+    assert ref.score_data() == e.score_data()
+    for k in range(model.n_kinds):
+        assert np.array_equal(ref.score_rows(k, 0, 32), e.score_rows(k, 0, 32))
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ok.%d" % rank), "w").write("1")
+dist.destroy_process_group()
+'''
+
+
 def _run(backend, tmp_path, worker=None):
     script = tmp_path / "worker.py"
     script.write_text((worker or WORKER).format(repo=REPO))
@@ -165,3 +209,8 @@ def test_row_sharded_accumulate_gloo_cpu(oracle_abi, tmp_path):
     """bulk accumulate (K2) with rows sharded over 2 ranks and the group tables combined == one rank over all rows"""
     _run("gloo", tmp_path, ACCUMULATE_WORKER)
 
+
+
+def test_feature_sharded_hyper_gloo_cpu(oracle_abi, tmp_path):
+    """HyperKernel::run with its tasks split over 2 ranks and the chosen hypers exchanged == hyper_run, bit for bit"""
+    _run("gloo", tmp_path, HYPER_WORKER)

@@ -121,3 +121,58 @@ def test_row_sharded_accumulate_nccl(cuda_abi, tmp_path):
         pytest.skip("needs 2 GPUs")
     import test_dist
     test_dist._run("nccl", tmp_path, test_dist.ACCUMULATE_WORKER)
+
+
+@pytest.mark.gpu
+def test_feature_sharded_hyper_nccl(cuda_abi, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import test_dist
+    test_dist._run("nccl", tmp_path, test_dist.HYPER_WORKER)
+
+
+@pytest.mark.gpu
+def test_masked_hyper_run_on_one_gpu(oracle_abi, cuda_abi):
+    """lb_hyper_run_tasks + lb_set_hypers on one device: two complementary masked runs on two replicas, exchanged by hand,
+    end where hyper_run ends (the same property the 2-rank test checks, without a second GPU)"""
+    from loom_b200 import Engine, synth
+    from test_dpd import GRIDS
+    model, rows, truth = synth.generate(1500, [("bb", 3), ("dd16", 2), ("dpd5", 2), ("gp", 3), ("nich", 3)], density=0.6, seed=23)
+    grids = dict(GRIDS, bb={"alpha": [0.5, 2.0], "beta": [0.5, 2.0]})
+
+    def engine():
+        e = Engine(cuda_abi)
+        e.set_model(model)
+        e.set_rows(rows)
+        for k in range(model.n_kinds):
+            uniq, inv = np.unique(truth["assign"][k].astype(np.uint32), return_inverse=True)
+            e.set_groups(k, len(uniq))
+            e.set_assignments(k, inv.astype(np.uint32))
+        e.accumulate_rows()
+        e.set_hyper_prior(grids)
+        return e
+    ref, a, b = engine(), engine(), engine()
+    K, F = model.n_kinds, model.n_features
+    owner = np.arange(1 + K + F) % 2
+    ref.hyper_run(7)
+    a.hyper_run(7, task_mask=(owner == 0).astype(np.uint8))
+    b.hyper_run(7, task_mask=(owner == 1).astype(np.uint8))
+    sa, aa, ka, ta = a.get_hypers()
+    sb, ab, kb, tb = b.get_hypers()
+    for f in range(F):
+        if owner[1 + K + f] == 1:
+            for c in range(4):
+                sa[f].hp[c] = sb[f].hp[c]
+            if sa[f].dim > 0 and sa[f].type in (1, 2):
+                aa[sa[f].aux_off:sa[f].aux_off + sa[f].dim] = ab[sa[f].aux_off:sa[f].aux_off + sa[f].dim]
+    for k in range(K):
+        if owner[1 + k] == 1:
+            ka[k] = kb[k]
+    a.set_hypers(sa, aa, ka, ta)                    # task 0 (topology) belongs to replica a
+    s0, a0, k0, t0 = ref.get_hypers()
+    s1, a1, k1, t1 = a.get_hypers()
+    for f in range(F):
+        assert [s0[f].hp[c] for c in range(4)] == [s1[f].hp[c] for c in range(4)], f
+    assert np.array_equal(a0, a1) and np.array_equal(k0, k1) and np.array_equal(t0, t1)
+    assert ref.score_data() == a.score_data()
