@@ -179,6 +179,11 @@ int lbio_rows_to_columns(const lbio_model *m, const lbio_row_block *rows, const 
  * tare_observed [F], tare_values [F] as lb_set_rows_diff takes them; *n_tares = 0 or 1. */
 int lbio_tares_read(const char *path, const lbio_model *m, uint8_t *tare_observed,
                     uint32_t *tare_values, int32_t *n_tares);
+/* The same with OPEN dictionaries (see lbio_rows_read_open): a DirichletProcessDiscrete value of the tare row that
+ * the model's dictionary lacks is appended with its stick-breaking beta -- the value a tared column holds in most
+ * rows appears in no row's pos.  Call after lbio_rows_read_open; the model object is MODIFIED. */
+int lbio_tares_read_open(const char *path, lbio_model *m, uint64_t seed, uint8_t *tare_observed,
+                         uint32_t *tare_values, int32_t *n_tares, int32_t *n_new);
 int lbio_tares_write(const char *path, const lbio_model *m, const uint8_t *tare_observed,
                      const uint32_t *tare_values);
 

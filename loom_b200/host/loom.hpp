@@ -62,7 +62,8 @@ public:
         const int F = view_.n_features;
         tare_observed_.assign(F, 0);
         tare_values_.assign(F, 0);
-        if (tares_in) {
+        if (tares_in && view_.n_dpd) tares_in_ = tares_in;   // read by rows_load, once the rows have completed the dictionaries
+        else if (tares_in) {
             int32_t n_tares = 0;
             LOOM_B200_IO(lbio_tares_read(tares_in, model_file_, tare_observed_.data(), tare_values_.data(), &n_tares));
         }
@@ -289,6 +290,11 @@ private:
         if (view_.n_dpd) {   // DPD Shared.add_value for every value of the stream, then the model goes to the device
             int32_t n_new = 0;
             LOOM_B200_IO(lbio_rows_read_open(rows_in, model_file_, config_.seed, 0, &rows, &n_new));
+            if (!tares_in_.empty()) {   // the tare row's own DPD values are in no row's pos: they enter the dictionary here
+                int32_t n_tares = 0;
+                LOOM_B200_IO(lbio_tares_read_open(tares_in_.c_str(), model_file_, config_.seed, tare_observed_.data(),
+                                                  tare_values_.data(), &n_tares, &n_new));
+            }
             LOOM_B200_IO(lbio_model_get(model_file_, &view_));
             model_install();
         } else {
@@ -502,7 +508,7 @@ private:
     lbio_model_view view_;
     std::vector<uint8_t> tare_observed_;
     std::vector<uint32_t> tare_values_;
-    std::string groups_in_;
+    std::string groups_in_, tares_in_;
     std::vector<uint64_t> assign_rowids_;
     std::vector<uint32_t> assign_groupids_;
     std::vector<uint64_t> rowids_;              // Row.id by stream position

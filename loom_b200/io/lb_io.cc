@@ -733,7 +733,8 @@ static const char *decode_value(Reader r, const lbio_model &m, ValueScratch &t, 
                 const auto &lk = m.dpd_lookup[m.dpd_ordinal[p]];
                 auto it = std::lower_bound(lk.begin(), lk.end(), std::make_pair(raw, 0u));
                 if (it != lk.end() && it->first == raw) raw = it->second;
-                else if (misses && values) misses->push_back(values->size());
+                else if (!values) {}                          // neg part of a diff: only the positions are used
+                else if (misses) misses->push_back(values->size());
                 else { err = "DirichletProcessDiscrete value is not in the model's dictionary"; return; }
             }
         } else {
@@ -996,7 +997,7 @@ static int model_extend(lbio_model *m, const std::vector<std::vector<uint32_t>> 
         counts.insert(counts.end(), m->dpd_counts.begin() + at, m->dpd_counts.begin() + at + s.dim);
         double beta0 = s.hp[2];
         const double gamma = s.hp[0] > 0 ? s.hp[0] : 1.0;
-        uint32_t draw = 0;
+        uint32_t draw = (uint32_t)s.dim;        // draw index = position in the dictionary, so a later extension continues the stream
         for (uint32_t v : fresh[ord]) {
             const double u = philox_uniform(seed, 4u, (uint64_t)f, draw++);
             const double beta = std::max(beta0 * (1.0 - std::pow(1.0 - u, 1.0 / gamma)), (double)LBIO_DPD_MIN_BETA);
@@ -1217,6 +1218,35 @@ extern "C" int lbio_tares_read(const char *path, const lbio_model *m, uint8_t *t
     }
     if (bad) return fail("failed to parse message from %s (truncated stream)", path);
     return 0;
+}
+
+// Tares with OPEN dictionaries: a DPD value of the tare row that the dictionary lacks is appended the way
+// lbio_rows_read_open appends the values of the rows (a tared column's own value is in no row's pos).
+extern "C" int lbio_tares_read_open(const char *path, lbio_model *m, uint64_t seed, uint8_t *tare_observed,
+                                    uint32_t *tare_values, int32_t *n_tares, int32_t *n_new) {
+    if (n_new) *n_new = 0;
+    {
+        pbw::InFile file(path);
+        if (!file.is_open()) return fail("failed to open input file %s", path);
+        std::vector<uint8_t> msg;
+        bool bad = false;
+        ValueScratch scratch;
+        std::vector<std::vector<uint32_t>> fresh(m->dpd_lookup.size());
+        int32_t appended = 0;
+        while (file.try_read_stream(msg, bad)) {
+            std::vector<uint32_t> features, values;
+            std::vector<uint64_t> misses;
+            if (const char *err = decode_value(Reader(msg), *m, scratch, features, &values, &misses)) return fail("%s: %s", path, err);
+            for (uint64_t at : misses) {
+                auto &list = fresh[m->dpd_ordinal[features[at]]];
+                if (std::find(list.begin(), list.end(), values[at]) == list.end()) { list.push_back(values[at]); ++appended; }
+            }
+        }
+        if (bad) return fail("failed to parse message from %s (truncated stream)", path);
+        if (appended && model_extend(m, fresh, seed)) return 1;
+        if (n_new) *n_new = appended;
+    }
+    return lbio_tares_read(path, m, tare_observed, tare_values, n_tares);
 }
 
 extern "C" int lbio_tares_write(const char *path, const lbio_model *m, const uint8_t *tare_observed,

@@ -130,6 +130,7 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_open": (C.c_int, [_cs, C.c_int32, _P(C.c_void_p)]),
     "log_write": (C.c_int, [C.c_void_p, _P(LogEntry)]),
     "log_close": (None, [C.c_void_p]),
+    "tares_read_open": (C.c_int, [_cs, _model, C.c_uint64, _u8p, _u32p, _i32p, _i32p]),
     "rows_writer_open": (C.c_int, [_cs, _P(C.c_void_p)]),
     "rows_writer_write": (C.c_int, [C.c_void_p, _model, C.c_void_p, _u32p]),
     "rows_writer_close": (C.c_int, [C.c_void_p]),
@@ -432,10 +433,18 @@ def stream_stats(path):
     return n.value, biggest.value
 
 
-def tares_read(path, model_file):
+def tares_read(path, model_file, open_dictionaries=False, seed=0):
+    """open_dictionaries: a DPD value of the tare row that the dictionary lacks is appended (lbio_tares_read_open;
+    call after the rows were read with open dictionaries -- the model file is modified)"""
     F = model_file.view.n_features
     to, tv, n = np.zeros(F, np.uint8), np.zeros(F, np.uint32), C.c_int32()
-    _check(lib().lbio_tares_read(_path(path), model_file.h, _abi.ptr(to, _u8p), _abi.ptr(tv, _u32p), C.byref(n)))
+    if open_dictionaries:
+        n_new = C.c_int32()
+        _check(lib().lbio_tares_read_open(_path(path), model_file.h, seed, _abi.ptr(to, _u8p), _abi.ptr(tv, _u32p),
+                                          C.byref(n), C.byref(n_new)))
+        model_file.refresh()
+    else:
+        _check(lib().lbio_tares_read(_path(path), model_file.h, _abi.ptr(to, _u8p), _abi.ptr(tv, _u32p), C.byref(n)))
     return to, tv, n.value
 
 

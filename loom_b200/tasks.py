@@ -115,12 +115,12 @@ def infer(rows_in, model_in, samples_out, config=None, tares_in=None, seeds=None
     # DPD dictionaries are completed from the rows (loom's init models start with empty ones); every
     # sample then adopts the same value order, with betas broken off its own stick
     rows = pbio.rows_read(rows_in, files[0], open_dictionaries=True, seed=seeds[0])
+    tare = (None, None)
+    if tares_in:                                   # the tare row's own DPD values are in no row's pos
+        tare_observed, tare_values, _ = pbio.tares_read(tares_in, files[0], open_dictionaries=True, seed=seeds[0])
+        tare = (tare_observed, tare_values)
     for c in range(1, n):
         files[c].adopt_dictionaries(files[0], seeds[c])
-    tare = (None, None)
-    if tares_in:
-        tare_observed, tare_values, _ = pbio.tares_read(tares_in, files[0])
-        tare = (tare_observed, tare_values)
     R = rows.n_rows
     empty = int(((config or {}).get("kernels", {}).get("cat", {}) or {}).get("empty_group_count", 1))
     engines = []

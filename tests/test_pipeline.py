@@ -1,0 +1,124 @@
+"""The processes chained the way loom.tasks chains them (ingest -> infer -> query), all built against the oracle's lo_ ABI:
+loom_tare -> loom_sparsify -> loom_infer (x3 seeds, init models with EMPTY DPD dictionaries, the tares file) -> a store
+-> loom_query.  The data has a DPD column whose dominant raw value ends up in the tare row: that value is in no row's
+pos, so it has to enter the dictionary from the tares file (lbio_tares_read_open)."""
+import shutil
+
+import numpy as np
+import pytest
+
+import pb_schema
+from loom_b200 import RowBlock, pack_mask, pbio, synth
+from loom_b200.engine import Model
+from test_pbio import GRIDS, M, fill_value, io_lib  # noqa: F401
+from test_differ_process import run as run_cmd, sparsify_on_oracle, tare_on_oracle  # noqa: F401
+from test_query_server import (N_SAMPLES, cells_of, fill_diff, new_request, query_on_oracle, serve,  # noqa: F401
+                               some_rows, value_cells)
+from test_z_loom_infer import DPD_TYPES, infer_on_oracle, raw_of, run as run_infer  # noqa: F401
+
+
+def raw_dataset(n_rows=300, seed=5):
+    """a block in RAW values (what a front end writes) with sparse booleans and a dominant DPD value below 16"""
+    rng = np.random.default_rng(seed)
+    model, block, _ = synth.generate(n_rows, DPD_TYPES, density=0.85, seed=seed)
+    F8 = model.n8()
+    dpd = [f for f, ft in enumerate(model.features) if ft["type"] == "dpd"]
+    raws = {dpd[0]: [9, 200, 3, 77, 1000, 14], dpd[1]: [raw_of(dpd[1], i) for i in range(6)]}
+    block.cat8[:3] = rng.random((3, n_rows)) < 0.06
+    block.wide[dpd[0] - F8] = np.where(rng.random(n_rows) < 0.8, 0, block.wide[dpd[0] - F8])     # index 0 <-> raw 9
+    obs = block.observed()
+    obs[:3] = True
+    obs[dpd[0]] |= rng.random(n_rows) < 0.95
+    block = RowBlock(n_rows, block.cat8, block.wide, pack_mask(obs))
+    return model, block, dpd, raws
+
+
+def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_on_oracle, query_on_oracle):  # noqa: F811
+    d = tmp_path
+    model, block, dpd, raws = raw_dataset()
+    writer = pbio.ModelFile.create(model, None, [raws[f] for f in dpd])
+    rowids = np.arange(block.n_rows, dtype=np.uint64) + 7
+    pbio.rows_write(d / "rows.pbs.gz", writer, pbio.Rows.from_block(block, rowids))
+    schema_row = M()["ProductValue"]()
+    schema_row.observed.sparsity = 2
+    for f in model.features:
+        schema_row.observed.dense.append(True)
+        (schema_row.booleans if f["type"] == "bb" else schema_row.reals if f["type"] == "nich" else schema_row.counts).append(0)
+    pb_schema.dump_message(d / "schema.pb.gz", schema_row)
+    # ingest
+    assert run_cmd([tare_on_oracle, d / "schema.pb.gz", d / "rows.pbs.gz", d / "tares.pbs.gz"]) == (0, "")
+    tare = value_cells(model, pb_schema.load_stream(d / "tares.pbs.gz", M()["ProductValue"])[0])
+    assert tare[dpd[0]] == 9 and all(tare[f] == 0 for f in range(3))          # RAW value of the DPD column
+    assert run_cmd([sparsify_on_oracle, d / "schema.pb.gz", d / "tares.pbs.gz", d / "rows.pbs.gz", d / "diffs.pbs.gz"]) == (0, "")
+    # infer three samples from init models with empty dictionaries
+    init = Model([dict(ft, betas=[], beta0=1.0) if ft["type"] == "dpd" else ft for ft in model.features], model.f2k)
+    pbio.ModelFile.create(init, GRIDS, [[] for _ in dpd]).write(d / "init.pb.gz")
+    root = d / "store"
+    (root / "ingest").mkdir(parents=True)
+    shutil.copy(d / "diffs.pbs.gz", root / "ingest" / "diffs.pbs.gz")
+    shutil.copy(d / "tares.pbs.gz", root / "ingest" / "tares.pbs.gz")
+    for s in range(N_SAMPLES):
+        c = pbio.config_defaults()
+        c.seed, c.extra_passes, c.kind_iterations, c.hyper_run, c.small_data_size = 40, 1.5, 0, 1, 50.0
+        pbio.config_write(d / "config.pb.gz", c)
+        paths = {"config": str(d / "config.pb.gz"), "rows": str(d / "diffs.pbs.gz"), "tares": str(d / "tares.pbs.gz"),
+                 "model_in": str(d / "init.pb.gz")}
+        out = run_infer(infer_on_oracle, paths, d, tag="s%d" % s)
+        sd = root / "samples" / ("sample.%d" % s)
+        sd.mkdir(parents=True)
+        shutil.copy(d / "config.pb.gz", sd / "config.pb.gz")
+        shutil.copy(out["model"], sd / "model.pb.gz")
+        shutil.copytree(out["groups"], sd / "groups")
+        a_rowids, a_gids = pbio.assign_read(out["assign"])
+        assert sorted(a_rowids.tolist()) == rowids.tolist()
+        mf = pbio.ModelFile.read(out["model"])
+        dicts = [x.tolist() for x in mf.dpd_values()]
+        assert 9 in dicts[0]                                                   # came in through the tares file
+        obs = block.observed()
+        F8 = model.n8()
+        for j, f in enumerate(dpd):
+            assert sorted(dicts[j]) == sorted({raws[f][int(v)] for v in block.wide[f - F8][obs[f]]})
+        # every sufficient statistic of the dump adds up to the data: counts per DPD value over all groups
+        for k in range(mf.model().n_kinds):
+            fids = mf.model().kind_features(k)
+            counts, ints, flts = pbio.groups_read(pbio.mixture_path(out["groups"], k), mf, fids)
+            assert counts.sum() == block.n_rows
+            row = 0
+            for f in fids:
+                ft = mf.model().features[f]
+                if ft["type"] == "dpd":
+                    j = dpd.index(f)
+                    for i, raw in enumerate(dicts[j]):
+                        want = int(((block.wide[f - F8] == raws[f].index(raw)) & obs[f]).sum())
+                        assert int(ints[row + i].sum()) == want, (f, raw)
+                row += {"bb": 2, "gp": 2, "nich": 1}.get(ft["type"]) or (len(ft["alphas"] if ft["type"] == "dd" else ft["betas"]) + 1)
+    qc = pbio.config_defaults()
+    qc.seed = 3
+    pbio.config_write(root / "query_config.pb.gz", qc)
+    # query: a row given densely (raw values) and given as its diff against the tare score the same
+    diffs = pb_schema.load_stream(d / "diffs.pbs.gz", M()["Row"])
+    dense = pb_schema.load_stream(d / "rows.pbs.gz", M()["Row"])
+    requests = []
+    for i in range(5):
+        r = new_request(2 * i)
+        r.score.data.CopyFrom(dense[i].diff)
+        requests.append(r)
+        r = new_request(2 * i + 1)
+        r.score.data.CopyFrom(diffs[i].diff)
+        requests.append(r)
+    s = new_request(100)                                                       # sample the tared DPD column given nothing
+    s.sample.data.pos.observed.sparsity = 0
+    s.sample.data.neg.observed.sparsity = 0
+    s.sample.to_sample.sparsity = 1
+    s.sample.to_sample.sparse.append(dpd[0])
+    s.sample.sample_count = 400
+    requests.append(s)
+    responses = serve(query_on_oracle, root, requests, d)
+    assert not any(r.error for r in responses)
+    scores = [r.score.score for r in responses[:10]]
+    assert all(np.isfinite(scores))
+    for i in range(5):
+        assert scores[2 * i] == pytest.approx(scores[2 * i + 1], abs=1e-5)
+    drawn = [value_cells(model, x.pos)[dpd[0]] for x in responses[10].sample.samples]
+    assert set(drawn) <= set(raws[dpd[0]]) | {0xFFFFFFFF}                      # raw values (or distributions' OTHER)
+    assert np.mean([v == 9 for v in drawn]) > 0.5                              # the dominant value dominates
