@@ -14,7 +14,8 @@ from test_pbio import GRIDS, M, fill_value, io_lib  # noqa: F401
 from test_differ_process import run as run_cmd, sparsify_on_oracle, tare_on_oracle  # noqa: F401
 from test_query_server import (N_SAMPLES, cells_of, fill_diff, new_request, query_on_oracle, serve,  # noqa: F401
                                some_rows, value_cells)
-from test_z_loom_infer import DPD_TYPES, infer_on_oracle, raw_of, run as run_infer  # noqa: F401
+from test_z_loom_infer import (DPD_TYPES, infer_on_oracle, posterior_enum_case, posterior_enum_on_oracle, raw_of,  # noqa: F401
+                               run as run_infer)
 
 
 def raw_dataset(n_rows=300, seed=5):
@@ -122,3 +123,23 @@ def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_
     drawn = [value_cells(model, x.pos)[dpd[0]] for x in responses[10].sample.samples]
     assert set(drawn) <= set(raws[dpd[0]]) | {0xFFFFFFFF}                      # raw values (or distributions' OTHER)
     assert np.mean([v == 9 for v in drawn]) > 0.5                              # the dominant value dominates
+
+
+@pytest.mark.parametrize("feature_type,density", [("bb", 1.0), ("bb", 0.5), ("dd", 1.0), ("gp", 0.5)])
+def test_posterior_enum_through_tare_and_sparsify(tmp_path, tare_on_oracle, sparsify_on_oracle, posterior_enum_on_oracle,  # noqa: F811
+                                                  feature_type, density):
+    """loom's chi-square test on rows that went through loom_tare + loom_sparsify, as the reference's own test does by
+    default (loom/test/test_posterior_enum.py:675-710): the sampled latents of the diff path follow the posterior"""
+    import pe_util
+    checked = tared = 0
+    for i, (R, C, kinds) in enumerate([(3, 2, False), (4, 1, False), (3, 2, True)]):
+        d = tmp_path / ("p%d" % i)
+        d.mkdir()
+        gof, info = posterior_enum_case(posterior_enum_on_oracle, d, R, C, feature_type, density, kinds, seed=30 + i,
+                                        ingest=(tare_on_oracle, sparsify_on_oracle))
+        tared += len(pb_schema.load_stream(d / "tares.pbs.gz", M()["ProductValue"]))
+        assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (R, C, gof, info)
+        checked += gof is not None
+    assert checked >= 1
+    if feature_type in ("bb", "dd") and density == 1.0:
+        assert tared >= 1          # a tare row was actually in play

@@ -420,7 +420,7 @@ def posterior_enum_on_oracle(tmp_path_factory, oracle_abi):
     return build_on_oracle(tmp_path_factory, "loom_posterior_enum.cc", "loom_posterior_enum_oracle")
 
 
-def posterior_enum_case(exe, d, R, C, feature_type, density, infer_kinds, seed):
+def posterior_enum_case(exe, d, R, C, feature_type, density, infer_kinds, seed, ingest=None):
     """loom/test/test_posterior_enum.py through the process: write the files, run the binary, parse the
     samples stream (parse_sample, :738-745) and return the goodness of fit of the visited latents"""
     import pe_util
@@ -437,7 +437,21 @@ def posterior_enum_case(exe, d, R, C, feature_type, density, infer_kinds, seed):
     c.kind_iterations, c.kind_empty_kind_count, c.hyper_run = (32 if infer_kinds else 0), 32, 0
     pbio.config_write(d / "config.pb.gz", c)
     out = d / "samples.pbs.gz"
-    proc = subprocess.run([exe, str(d / "config.pb.gz"), str(d / "rows.pbs.gz"), "--none", str(d / "model.pb.gz"),
+    rows_in, tares_in = str(d / "rows.pbs.gz"), "--none"
+    if ingest:      # the reference's test runs through tare + sparsify by default (loom/test/test_posterior_enum.py:675-710)
+        tare_exe, sparsify_exe = ingest
+        schema_row = M()["ProductValue"]()
+        schema_row.observed.sparsity = 2
+        for f in model.features:
+            schema_row.observed.dense.append(True)
+            (schema_row.booleans if f["type"] == "bb" else schema_row.reals if f["type"] == "nich" else schema_row.counts).append(0)
+        pb_schema.dump_message(d / "schema.pb.gz", schema_row)
+        for cmd in ([tare_exe, d / "schema.pb.gz", d / "rows.pbs.gz", d / "tares.pbs.gz"],
+                    [sparsify_exe, d / "schema.pb.gz", d / "tares.pbs.gz", d / "rows.pbs.gz", d / "diffs.pbs.gz"]):
+            p = subprocess.run([str(c) for c in cmd], capture_output=True, timeout=300)
+            assert p.returncode == 0, p.stderr.decode()
+        rows_in, tares_in = str(d / "diffs.pbs.gz"), str(d / "tares.pbs.gz")
+    proc = subprocess.run([exe, str(d / "config.pb.gz"), rows_in, tares_in, str(d / "model.pb.gz"),
                            "--none", "--none", str(out)], capture_output=True, timeout=900)
     assert proc.returncode == 0, proc.stderr.decode()
     samples = []
