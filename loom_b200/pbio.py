@@ -57,6 +57,31 @@ class Config(C.Structure):
                 "query": {"parallel": bool(self.query_parallel)}}
 
 
+def config_from_dict(d=None):
+    """the inverse of Config.as_dict over loom's defaults (loom/config.py:76-117 fill_in_defaults + protobuf_dump)"""
+    c = config_defaults()
+    d = d or {}
+    sch, ker = d.get("schedule") or {}, d.get("kernels") or {}
+    cat, hyp, kind = ker.get("cat") or {}, ker.get("hyper") or {}, ker.get("kind") or {}
+    pe, gen, qry = d.get("posterior_enum") or {}, d.get("generate") or {}, d.get("query") or {}
+    for field, src, key in (("seed", d, "seed"), ("target_mem_bytes", d, "target_mem_bytes"),
+                            ("extra_passes", sch, "extra_passes"), ("small_data_size", sch, "small_data_size"),
+                            ("big_data_size", sch, "big_data_size"), ("max_reject_iters", sch, "max_reject_iters"),
+                            ("checkpoint_period_sec", sch, "checkpoint_period_sec"),
+                            ("cat_empty_group_count", cat, "empty_group_count"),
+                            ("cat_row_queue_capacity", cat, "row_queue_capacity"), ("cat_parser_threads", cat, "parser_threads"),
+                            ("hyper_run", hyp, "run"), ("hyper_parallel", hyp, "parallel"),
+                            ("kind_iterations", kind, "iterations"), ("kind_empty_kind_count", kind, "empty_kind_count"),
+                            ("kind_row_queue_capacity", kind, "row_queue_capacity"),
+                            ("kind_parser_threads", kind, "parser_threads"), ("kind_score_parallel", kind, "score_parallel"),
+                            ("posterior_enum_sample_count", pe, "sample_count"), ("posterior_enum_sample_skip", pe, "sample_skip"),
+                            ("generate_row_count", gen, "row_count"), ("generate_density", gen, "density"),
+                            ("generate_sample_skip", gen, "sample_skip"), ("query_parallel", qry, "parallel")):
+        if key in src and src[key] is not None:
+            setattr(c, field, type(getattr(c, field))(src[key]))
+    return c
+
+
 class Checkpoint(C.Structure):
     """protobuf::Checkpoint (src/schema.proto:234-253)"""
     _fields_ = [("finished", C.c_int32), ("seed", C.c_uint64), ("tardis_iter", C.c_uint64),

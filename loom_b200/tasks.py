@@ -101,7 +101,9 @@ def infer(rows_in, model_in, samples_out, config=None, tares_in=None, seeds=None
     rows_in      rows.pbs[.gz] (the ingest's `diffs`); tares_in the matching tares file or None
     model_in     one init model path for every sample, or a list with one per sample
                  (loom.tasks.infer_one writes a fresh generate_init per seed)
-    samples_out  per sample {"model": path, "groups": dir, "assign": path} (any may be missing)
+    samples_out  per sample {"model": path, "groups": dir, "assign": path, "config": path} (any may be missing;
+                 "config" receives the sample's Config with its own seed, what loom.tasks.infer_one leaves in the
+                 store and loom_query reads back, loom/tasks.py:217-227)
     config       nested dict like loom/config.py DEFAULTS, or a config.pb[.gz] path
     seeds        per-sample seeds (default 0, 1, ...): the chain's rng and, with shuffle=True, its row order
     """
@@ -142,6 +144,10 @@ def infer(rows_in, model_in, samples_out, config=None, tares_in=None, seeds=None
     else:
         infer_single_pass(engines, seeds, orders=orders)
     for c, e in enumerate(engines):
+        if samples_out[c].get("config"):
+            sample_config = pbio.config_from_dict(config)
+            sample_config.seed = seeds[c]
+            pbio.config_write(samples_out[c]["config"], sample_config)
         _dump_sample(e, files[c], rows.rowids, (0, R, None if orders is None else orders[c]), samples_out[c],
                      files[c].hyper_prior(), files[c].dpd_values())
     return engines

@@ -143,3 +143,43 @@ def test_posterior_enum_through_tare_and_sparsify(tmp_path, tare_on_oracle, spar
     assert checked >= 1
     if feature_type in ("bb", "dd") and density == 1.0:
         assert tared >= 1          # a tare row was actually in play
+
+
+def test_store_written_by_tasks_infer_is_served_by_loom_query(tmp_path, oracle_abi, query_on_oracle):  # noqa: F811
+    """loom_b200.tasks.infer (all samples as chains on one engine) writing the store layout of src/store.hpp:68-89,
+    config.pb.gz per sample included; loom_query then serves it"""
+    from loom_b200 import hyperprior, tasks
+    from test_z_loom_infer import write_inputs
+    from test_query_server import expected_scores
+    work = tmp_path / "work"
+    work.mkdir()
+    model, block, rowids, paths = write_inputs(work, n_rows=150, seed=6, tared=True)
+    root = tmp_path / "store"
+    (root / "ingest").mkdir(parents=True)
+    shutil.copy(paths["rows"], root / "ingest" / "diffs.pbs.gz")
+    shutil.copy(paths["tares"], root / "ingest" / "tares.pbs.gz")
+    feature_sizes = [{"type": "dd", "dim": len(f["alphas"])} if f["type"] == "dd" else {"type": f["type"]} for f in model.features]
+    inits, outs = [], []
+    for s in range(N_SAMPLES):
+        init = tasks.generate_init(feature_sizes, hyperprior.defaults(), seed=s)
+        pbio.ModelFile.create(init, GRIDS).write(work / ("init.%d.pb.gz" % s))
+        inits.append(str(work / ("init.%d.pb.gz" % s)))
+        sd = root / "samples" / ("sample.%d" % s)
+        sd.mkdir(parents=True)
+        outs.append({"config": str(sd / "config.pb.gz"), "model": str(sd / "model.pb.gz"), "groups": str(sd / "groups"),
+                     "assign": str(sd / "assign.pbs.gz")})
+    config = {"schedule": {"extra_passes": 1.5, "small_data_size": 50.0}, "kernels": {"kind": {"iterations": 2, "empty_kind_count": 2}}}
+    tasks.infer(paths["rows"], inits, outs, config, tares_in=paths["tares"], seeds=[11, 12, 13], abi=oracle_abi)
+    assert [pbio.config_read(o["config"]).seed for o in outs] == [11, 12, 13]
+    assert pbio.config_read(outs[0]["config"]).as_dict()["kernels"]["kind"]["iterations"] == 2
+    qc = pbio.config_defaults()
+    pbio.config_write(root / "query_config.pb.gz", qc)
+    table = some_rows(model, block, range(5))
+    requests = []
+    for i, row in enumerate(table):
+        r = new_request(i)
+        fill_diff(r.score.data, model, cells_of(row))
+        requests.append(r)
+    responses = serve(query_on_oracle, root, requests, tmp_path)
+    got = np.array([r.score.score for r in responses])
+    assert np.allclose(got, expected_scores(oracle_abi, root, model, table), rtol=1e-5, atol=1e-5)
