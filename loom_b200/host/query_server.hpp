@@ -71,6 +71,7 @@ public:
         if (std::ifstream(tares_in)) {
             int32_t n_tares = 0;
             LOOM_B200_IO(lbio_tares_read(tares_in.c_str(), latents_[0]->model, tare_observed_.data(), tare_values_.data(), &n_tares));
+            tare_count_ = n_tares;
         }
     }
 
@@ -90,6 +91,18 @@ public:
             for (int i = 0; i < req.n_invalid; ++i) a.errors.push_back(req.invalid[i]);
             Rows request_rows;
             request_rows.append(req.rows, 0, req.rows.n_rows);
+            // validate(): "for (auto id : data.tares()) if (id >= tares().size())" (src/query_server.cc:77-82, 178-183, 241-246,
+            // 421-441) -- the codec rejects ids above 0; a store without a tare row has no tare 0 either
+            auto tare_missing = [&](int32_t row) { return row >= 0 && !tare_count_ && request_rows.has_tare[(size_t)row]; };
+            if (tare_missing(req.sample_row)) { a.errors.push_back("invalid request.sample.data.tares"); req.sample_row = -1; }
+            if (tare_missing(req.score_row)) { a.errors.push_back("invalid request.score.data.tares"); req.score_row = -1; }
+            if (tare_missing(req.entropy_row)) { a.errors.push_back("invalid request.entropy.conditional.tares"); req.entropy_row = -1; }
+            if (tare_missing(req.update_row)) { a.errors.push_back("invalid request.score_derivative.update_data"); req.update_row = -1; }
+            for (int i = 0; req.update_row >= 0 && i < req.n_score_data; ++i)
+                if (tare_missing(req.first_score_data_row + i)) {
+                    a.errors.push_back("invalid request.score_derivative.score_data");
+                    req.update_row = -1;
+                }
             if (req.sample_row >= 0) call_sample(request_rows, (uint64_t)req.sample_row, req.to_sample, req.n_to_sample, req.sample_count, a);
             if (req.score_row >= 0) {
                 a.has_score = true;
@@ -409,6 +422,7 @@ private:
     std::vector<std::unique_ptr<Latent>> latents_;
     std::vector<uint8_t> tare_observed_;
     std::vector<uint32_t> tare_values_;
+    int32_t tare_count_ = 0;
 };
 
 }  // namespace b200

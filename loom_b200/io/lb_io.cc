@@ -791,6 +791,7 @@ struct RowChunk {           // one thread's share of a batch
 // Row :153-156, ProductValue.Diff :87-91
 // One ProductValue.Diff (:87-91) appended to `out` as a row with the given id.  Returns an error text or null
 // (on error the partial cells are rolled back).
+static const char *const BAD_TARE = "row references a tare other than tare 0 (one tare row is supported)";
 static const char *decode_diff(Reader d, const lbio_model &m, ValueScratch &scratch, std::vector<uint32_t> &tares,
                                uint64_t id, RowChunk &out, bool open_dictionaries) {
     const size_t pos0 = out.pos_feature.size(), neg0 = out.neg_feature.size(), miss0 = out.misses.size();
@@ -811,7 +812,7 @@ static const char *decode_diff(Reader d, const lbio_model &m, ValueScratch &scra
     }
     if (!err && (!d.ok || !has_pos || !has_neg)) err = "failed to parse ProductValue.Diff (pos and neg are required)";
     for (uint32_t t : tares) {
-        if (t != 0 && !err) err = "row references a tare other than tare 0 (one tare row is supported)";
+        if (t != 0 && !err) err = BAD_TARE;
         has_tare = 1;
     }
     if (err) {
@@ -1720,7 +1721,11 @@ extern "C" int lbio_query_next(lbio_query *q, const lbio_model *m, lbio_query_re
     std::vector<uint32_t> tares;
     auto add_row = [&](Reader diff, const char *what) -> int {      // row index, or -1 with `invalid` extended
         const char *err = decode_diff(diff, *m, scratch, tares, q->chunk.rowids.size(), q->chunk, false);
-        if (err) { q->invalid.push_back(std::string("invalid request.") + what); return -1; }
+        if (err) {      // validate(): "...data" for a value that does not fit the schema, "...data.tares" for a tare id out of range
+            const bool tares_suffix = err == BAD_TARE && std::strncmp(what, "score_derivative", 16) != 0;
+            q->invalid.push_back(std::string("invalid request.") + what + (tares_suffix ? ".tares" : ""));
+            return -1;
+        }
         return (int)q->chunk.rowids.size() - 1;
     };
     Reader r(q->msg);

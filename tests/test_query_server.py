@@ -315,6 +315,29 @@ def test_invalid_data_is_reported_and_the_server_carries_on(store, query_on_orac
     assert not responses[1].error and responses[1].HasField("score") and len(responses[1].sample.samples) == 3
 
 
+def test_tare_ids_are_validated(store, query_on_oracle, tmp_path):
+    """src/query_server.cc:77-82, 178-183: a tare id the store does not hold (this store has no tare row at all)"""
+    root, model, block, rowids = store
+    r0 = new_request(0)
+    fill_diff(r0.score.data, model, {0: 1})
+    r0.score.data.tares.append(0)
+    fill_diff(r0.sample.data, model, {})
+    r0.sample.data.tares.append(3)
+    fill_observed(r0.sample.to_sample, model, {1}, "sparse")
+    r0.sample.sample_count = 2
+    fill_diff(r0.score_derivative.update_data, model, {0: 1})
+    r0.score_derivative.update_data.tares.append(0)
+    r0.score_derivative.row_limit = 1
+    r1 = new_request(1)
+    fill_diff(r1.score.data, model, {0: 1})
+    responses = serve(query_on_oracle, root, [r0, r1], tmp_path)
+    assert sorted(responses[0].error) == ["invalid request.sample.data.tares", "invalid request.score.data.tares",
+                                          "invalid request.score_derivative.update_data"]
+    assert not responses[0].HasField("score") and not responses[0].HasField("sample")
+    assert not responses[0].HasField("score_derivative")
+    assert responses[1].HasField("score") and not responses[1].error
+
+
 def test_score_derivative(store, query_on_oracle, tmp_path):
     root, model, block, rowids = store
     table = some_rows(model, block, range(8))
