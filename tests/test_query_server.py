@@ -496,3 +496,31 @@ def test_missing_samples_abort_with_looms_message(tmp_path, query_on_oracle):
     proc = subprocess.run([query_on_oracle, str(tmp_path), "--none", str(tmp_path / "config.pb.gz"), "--none", "--none"],
                           capture_output=True, timeout=60)
     assert proc.returncode != 0 and b"no samples were found at" in proc.stderr     # src/multi_loom.cc:69
+
+
+def test_seed(store, query_on_oracle, tmp_path):
+    """loom/test/test_query.py:207-227: the same config seed gives the same responses, another seed different ones"""
+    root, model, block, rowids = store
+    requests = []
+    for i in range(4):
+        r = new_request(i)
+        fill_diff(r.sample.data, model, cells_of(some_rows(model, block, [i])[0]) if i % 2 else {})
+        to_sample = {f for f in range(model.n_features) if f % 2 == i % 2}
+        if i % 2:
+            to_sample -= set(cells_of(some_rows(model, block, [i])[0]))
+        fill_observed(r.sample.to_sample, model, to_sample, "dense")
+        r.sample.sample_count = 5
+        fill_diff(r.score.data, model, {})
+        requests.append(r)
+    pb_schema.dump_stream(tmp_path / "requests.pbs.gz", requests)
+    outs = []
+    for tag, seed in (("a", 0), ("b", 0), ("c", 10)):
+        c = pbio.config_defaults()
+        c.seed = seed
+        pbio.config_write(tmp_path / (tag + ".config.pb.gz"), c)
+        proc = subprocess.run([query_on_oracle, str(root), str(tmp_path / "requests.pbs.gz"), str(tmp_path / (tag + ".config.pb.gz")),
+                               str(tmp_path / (tag + ".responses.pbs")), "--none"], capture_output=True, timeout=600)
+        assert proc.returncode == 0, proc.stderr.decode()
+        outs.append(open(tmp_path / (tag + ".responses.pbs"), "rb").read())
+    assert outs[0] == outs[1] and outs[0] != outs[2]
+    assert len(pb_schema.load_stream(tmp_path / "a.responses.pbs", M()["Query.Response"])) == 4
