@@ -147,7 +147,7 @@ def measure_ingest(abi, model, rows, device=0):
         os.unlink(path)
 
 
-def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeout=180):
+def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeout=90):
     """The process boundary: `loom_infer` -- the binary loom.runner starts -- on the workload's
     files: config.pb.gz, rows.pbs.gz, model.pb.gz in; model, groups, assignments, log out.  One chain, cat
     kernel only, `extra_passes` extra passes of the annealing schedule.  Host wall clock around the whole
@@ -196,7 +196,7 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
         shutil.rmtree(d, ignore_errors=True)
 
 
-def measure_in_subprocess(script, script_args, timeout=150):
+def measure_in_subprocess(script, script_args, timeout=60):
     """Run one of scratch/*_bench.py in its OWN process and return the JSON line it prints: the rows of
     SURVEY.md 8f added last (query path, tare / sparsify) are measured beside the headline without being
     able to disturb it (a fault in them cannot take the bench process or its CUDA context down)."""
