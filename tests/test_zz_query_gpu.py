@@ -176,3 +176,33 @@ def test_masked_hyper_run_on_one_gpu(oracle_abi, cuda_abi):
         assert [s0[f].hp[c] for c in range(4)] == [s1[f].hp[c] for c in range(4)], f
     assert np.array_equal(a0, a1) and np.array_equal(k0, k1) and np.array_equal(t0, t1)
     assert ref.score_data() == a.score_data()
+
+
+# ------------------------------------------------------------------------------------------ the loom.query front end
+@pytest.mark.gpu
+def test_query_client_on_the_gpu(tmp_path, infer_on_oracle):  # noqa: F811
+    """loom_b200.query (loom/query.py's API) over the product binary: the checks of loom/test/test_query_math.py"""
+    import __graft_entry__
+    __graft_entry__.build()
+    from loom_b200 import query
+    from test_query_client import typed_row
+    root = tmp_path / "store"
+    model, block, rowids = qs.make_store(root, infer_on_oracle)
+    F = model.n_features
+    with query.get_server(root, config={"seed": 2}) as s:          # finds loom_b200/host/loom_query
+        assert abs(s.score([None] * F)) < 1e-3
+        cond = typed_row(model, qs.some_rows(model, block, [1])[0])
+        bb = next(f for f in range(F) if model.features[f]["type"] == "bb")
+        cond[bb] = None
+        n = 2000
+        samples = s.sample([f == bb for f in range(F)], cond, n)
+        base = s.score(cond)
+        p = [np.exp(s.score(cond[:bb] + [v] + cond[bb + 1:]) - base) for v in (False, True)]
+        assert abs(sum(p) - 1) < 1e-4
+        ones = sum(bool(x[bb]) for x in samples)
+        assert qs.chi_square_p([n - ones, ones], p) > qs.MIN_P
+        ent = s.entropy([[bb]], [[]], cond, 500)
+        exact = -sum(q * np.log(q) for q in p)
+        est = ent[frozenset([bb])]
+        assert abs(est.mean - exact) < 4.5 * np.sqrt(est.variance) + 1e-6
+        assert len(s.score_derivative(cond, [cond, typed_row(model, qs.some_rows(model, block, [2])[0])])) == 2
