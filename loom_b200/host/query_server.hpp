@@ -91,9 +91,22 @@ public:
             for (int i = 0; i < req.n_invalid; ++i) a.errors.push_back(req.invalid[i]);
             Rows request_rows;
             request_rows.append(req.rows, 0, req.rows.n_rows);
+            const std::vector<uint8_t> inconsistent = sanitize(request_rows);
             // validate(): "for (auto id : data.tares()) if (id >= tares().size())" (src/query_server.cc:77-82, 178-183, 241-246,
             // 421-441) -- the codec rejects ids above 0; a store without a tare row has no tare 0 either
             auto tare_missing = [&](int32_t row) { return row >= 0 && !tare_count_ && request_rows.has_tare[(size_t)row]; };
+            // a diff whose neg / pos do not fit the tare it references (the reference would add and subtract the
+            // likelihoods it names, which is not a probability; here the data is reported invalid)
+            auto bad = [&](int32_t row) { return row >= 0 && inconsistent[(size_t)row]; };
+            if (bad(req.sample_row)) { a.errors.push_back("invalid request.sample.data"); req.sample_row = -1; }
+            if (bad(req.score_row)) { a.errors.push_back("invalid request.score.data"); req.score_row = -1; }
+            if (bad(req.entropy_row)) { a.errors.push_back("invalid request.entropy.conditional"); req.entropy_row = -1; }
+            if (bad(req.update_row)) { a.errors.push_back("invalid request.score_derivative.update_data"); req.update_row = -1; }
+            for (int i = 0; req.update_row >= 0 && i < req.n_score_data; ++i)
+                if (bad(req.first_score_data_row + i)) {
+                    a.errors.push_back("invalid request.score_derivative.score_data");
+                    req.update_row = -1;
+                }
             if (tare_missing(req.sample_row)) { a.errors.push_back("invalid request.sample.data.tares"); req.sample_row = -1; }
             if (tare_missing(req.score_row)) { a.errors.push_back("invalid request.score.data.tares"); req.score_row = -1; }
             if (tare_missing(req.entropy_row)) { a.errors.push_back("invalid request.entropy.conditional.tares"); req.entropy_row = -1; }
@@ -161,6 +174,45 @@ private:
         std::vector<uint64_t> ids;
         std::vector<float> score_diffs;
     };
+
+    // Rows as lb_set_rows_diff accepts them.  A row that references no tare is scored from its pos alone
+    // (mixture.score_value(model, diff.pos(), ...) when !diff.tares_size(), src/query_server.cc:121-125, 216-222): its neg
+    // is dropped.  A row that references the tare must remove only cells the tare holds and set only cells that are
+    // free; returns 1 for the rows that do not.
+    std::vector<uint8_t> sanitize(Rows &rows) const {
+        const uint64_t R = rows.size();
+        std::vector<uint8_t> inconsistent(R, 0);
+        Rows out;
+        std::vector<uint8_t> removed(tare_observed_.size());
+        for (uint64_t r = 0; r < R; ++r) {
+            const uint64_t n0 = rows.neg_ptr[r], n1 = rows.neg_ptr[r + 1], p0 = rows.pos_ptr[r], p1 = rows.pos_ptr[r + 1];
+            out.has_tare.push_back(rows.has_tare[r]);
+            bool ok = true;
+            if (rows.has_tare[r] && tare_count_) {
+                std::fill(removed.begin(), removed.end(), 0);
+                for (uint64_t i = n0; i < n1 && ok; ++i) {
+                    const uint32_t f = rows.neg_feature[i];
+                    ok = tare_observed_[f] && !removed[f];
+                    removed[f] = 1;
+                }
+                for (uint64_t i = p0; i < p1 && ok; ++i) {
+                    const uint32_t f = rows.pos_feature[i];
+                    ok = !tare_observed_[f] || removed[f];
+                }
+            }
+            inconsistent[r] = !ok;
+            if (ok) {
+                out.pos_feature.insert(out.pos_feature.end(), rows.pos_feature.begin() + p0, rows.pos_feature.begin() + p1);
+                out.pos_value.insert(out.pos_value.end(), rows.pos_value.begin() + p0, rows.pos_value.begin() + p1);
+                if (rows.has_tare[r] && tare_count_)
+                    out.neg_feature.insert(out.neg_feature.end(), rows.neg_feature.begin() + n0, rows.neg_feature.begin() + n1);
+            }
+            out.pos_ptr.push_back(out.pos_feature.size());
+            out.neg_ptr.push_back(out.neg_feature.size());
+        }
+        rows = out;
+        return inconsistent;
+    }
 
     double uniform() { return (double)(rng_() >> 11) * (1.0 / 9007199254740992.0); }
 

@@ -455,7 +455,19 @@ def test_tared_store(tmp_path, infer_on_oracle, query_on_oracle, oracle_abi):  #
     fill_observed(e.entropy.col_sets.add(), model, set(), "none")
     e.entropy.sample_count = 50
     requests.append(e)
+    # a diff that does not fit the tare it references: neg names a cell the tare lacks / pos sets a cell the tare holds
+    free_cell = next(f for f in range(model.n_features) if not tare_obs[f] and model.features[f]["type"] == "bb")
+    held_cell = next(f for f in range(model.n_features) if tare_obs[f])
+    for bad_pos, bad_neg in (({}, {free_cell: 0}), ({held_cell: int(tare_val[held_cell])}, {})):
+        r = new_request(len(requests))
+        fill_value(r.score.data.pos, model, bad_pos, "sparse" if bad_pos else "auto")
+        fill_value(r.score.data.neg, model, bad_neg, "sparse" if bad_neg else "auto")
+        r.score.data.tares.append(0)
+        requests.append(r)
     responses = serve(query_on_oracle, root, requests, tmp_path)
+    assert [list(r.error) for r in responses[-2:]] == [["invalid request.score.data"]] * 2
+    assert not any(r.HasField("score") for r in responses[-2:])
+    responses = responses[:-2]
     got = np.array([r.score.score for r in responses[:len(rows)]])
     want = expected_scores(oracle_abi, root, model, some_rows(model, block, rows))
     assert np.allclose(got, want, rtol=1e-5, atol=1e-5)
@@ -524,3 +536,29 @@ def test_seed(store, query_on_oracle, tmp_path):
         outs.append(open(tmp_path / (tag + ".responses.pbs"), "rb").read())
     assert outs[0] == outs[1] and outs[0] != outs[2]
     assert len(pb_schema.load_stream(tmp_path / "a.responses.pbs", M()["Query.Response"])) == 4
+
+
+def test_hostile_but_well_formed_requests_are_answered(store, query_on_oracle, tmp_path):
+    """values a fuzzer found the server aborting on: a neg part without a tare reference (ignored, as the reference scores
+    such a diff from pos alone, src/query_server.cc:121-125), non-finite reals, zero counts and limits"""
+    root, model, block, rowids = store
+    F = model.n_features
+    nich = next(f for f in range(F) if model.features[f]["type"] == "nich")
+    gp = next(f for f in range(F) if model.features[f]["type"] == "gp")
+    r0 = new_request(0)
+    fill_value(r0.score.data.pos, model, {0: 1}, "sparse")
+    fill_value(r0.score.data.neg, model, {1: 0, 2: 1}, "sparse")          # no tares: neg is ignored
+    r1 = new_request(1)
+    fill_diff(r1.score.data, model, {0: 1})
+    r2 = new_request(2)
+    fill_diff(r2.score.data, model, {nich: float("nan"), gp: 10 ** 6})
+    fill_diff(r2.sample.data, model, {nich: float("inf")})
+    fill_observed(r2.sample.to_sample, model, {0}, "sparse")
+    r2.sample.sample_count = 0
+    fill_diff(r2.score_derivative.update_data, model, {0: 1})
+    r2.score_derivative.row_limit = 0
+    fill_diff(r2.score_derivative.score_data.add(), model, {0: 0})
+    responses = serve(query_on_oracle, root, [r0, r1, r2], tmp_path)
+    assert not any(r.error for r in responses)
+    assert responses[0].score.score == pytest.approx(responses[1].score.score, abs=1e-6)
+    assert len(responses[2].sample.samples) == 0 and len(responses[2].score_derivative.ids) == 0
