@@ -269,6 +269,32 @@ public:
         LOOM_B200_IO(lbio_samples_close(samples));
     }
 
+    // Loom::mix (src/loom.cc:564-586): sample_skip times { REMOVE + ADD every row; kind kernel; hyper kernel } on a
+    // fully assigned state -- what loom.generate runs to decorrelate a synthetic dataset from the model that made it
+    void mix(const char *rows_in) {
+        const uint32_t sample_skip = config_.generate_sample_skip;
+        if (!(sample_skip > 0)) LOOM_B200_ERROR("zero diversity");
+        rows_load(rows_in);
+        const uint64_t R = row_count();
+        if (assigned_count_ != R) LOOM_B200_ERROR("mix needs every row assigned");
+        SeedStream rng(config_.seed);
+        CatKernel cat_kernel(cross_cat_, rng());
+        std::unique_ptr<HyperKernel> hyper_kernel;
+        if (config_.hyper_run && view_.has_hyper_prior) hyper_kernel.reset(new HyperKernel(cross_cat_, view_.hyper_prior));
+        std::unique_ptr<KindKernel> kind_kernel;
+        if (config_.kind_iterations > 0)
+            kind_kernel.reset(new KindKernel(cross_cat_, (int)config_.kind_empty_kind_count, (int)config_.kind_iterations, rng()));
+        for (uint32_t i = 0; i < sample_skip; ++i) {
+            for (uint64_t r = 0; r < R; ++r) {
+                cat_kernel.remove_row((assigned_pos_ + r) % R);
+                cat_kernel.add_row((assigned_pos_ + r) % R);
+            }
+            cat_kernel.wait();
+            if (kind_kernel) kind_kernel->try_run();
+            if (hyper_kernel) hyper_kernel->run(rng());
+        }
+    }
+
     CrossCat &cross_cat() { return cross_cat_; }
     uint64_t row_count() const { return rowids_.size(); }
     uint64_t assigned_count() const { return assigned_count_; }

@@ -183,3 +183,39 @@ def test_store_written_by_tasks_infer_is_served_by_loom_query(tmp_path, oracle_a
     responses = serve(query_on_oracle, root, requests, tmp_path)
     got = np.array([r.score.score for r in responses])
     assert np.allclose(got, expected_scores(oracle_abi, root, model, table), rtol=1e-5, atol=1e-5)
+
+
+def test_loom_mix(tmp_path, infer_on_oracle, oracle_abi):  # noqa: F811
+    """Loom::mix through the process (src/mix.cc): a fully assigned state, sample_skip sweeps with the kind and hyper
+    kernels, dumped again -- every statistic of the dump recomputes from the rows and the dumped assignments, and the
+    state moved"""
+    import subprocess
+    from test_query_server import build_on_oracle
+    from test_z_loom_infer import check_outputs, write_inputs
+
+    class Factory:                                   # build_on_oracle wants a tmp_path_factory
+        @staticmethod
+        def mktemp(name):
+            d = tmp_path / name
+            d.mkdir()
+            return d
+    exe = build_on_oracle(Factory, "loom_mix.cc", "loom_mix_oracle")
+    model, block, rowids, paths = write_inputs(tmp_path, n_rows=200, seed=12, extra_passes=1.0, kind_iterations=2, hyper=True)
+    first = run_infer(infer_on_oracle, paths, tmp_path, tag="first")
+    c = pbio.config_read(paths["config"])
+    c.generate_sample_skip, c.seed = 3, 99
+    pbio.config_write(paths["config"], c)
+    out = {"model": str(tmp_path / "mixed.model.pb.gz"), "groups": str(tmp_path / "mixed.groups"),
+           "assign": str(tmp_path / "mixed.assign.pbs.gz")}
+    proc = subprocess.run([exe, paths["config"], paths["rows"], first["model"], first["groups"], first["assign"],
+                           out["model"], out["groups"], out["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr.decode()
+    check_outputs(oracle_abi, block, rowids, out)
+    a0, a1 = pbio.assign_read(first["assign"]), pbio.assign_read(out["assign"])
+    assert sorted(a0[0].tolist()) == sorted(a1[0].tolist())
+    assert a0[1].shape != a1[1].shape or not np.array_equal(a0[1], a1[1])            # the chain moved
+    c.generate_sample_skip = 0
+    pbio.config_write(paths["config"], c)
+    proc = subprocess.run([exe, paths["config"], paths["rows"], first["model"], first["groups"], first["assign"],
+                           out["model"], out["groups"], out["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode != 0 and b"zero diversity" in proc.stderr                 # src/loom.cc:569
