@@ -196,13 +196,13 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
         shutil.rmtree(d, ignore_errors=True)
 
 
-def measure_in_subprocess(script, script_args, timeout=60):
+def measure_in_subprocess(script, script_args, timeout=60, env=None):
     """Run one of scratch/*_bench.py in its OWN process and return the JSON line it prints: the rows of
     SURVEY.md 8f added last (query path, tare / sparsify) are measured beside the headline without being
     able to disturb it (a fault in them cannot take the bench process or its CUDA context down)."""
     cmd = [sys.executable, os.path.join(REPO, "scratch", script)] + [str(a) for a in script_args]
     try:
-        proc = subprocess.run(cmd, capture_output=True, timeout=timeout)
+        proc = subprocess.run(cmd, capture_output=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     except subprocess.TimeoutExpired:
         return {"error": "timed out after %d s" % timeout}
     if proc.returncode != 0:
@@ -624,6 +624,13 @@ def main():
         # query path (8f n3) and tare / sparsify (8f n4) on the same C2 mix, each in its own process
         aux["query"] = measure_in_subprocess("query_bench.py", [R, 1000000])
         aux["score_error"] = measure_in_subprocess("score_error.py", [20000])     # parity check 2, per feature type
+        # experiment for the next round: the sweep scoring BB / DD / DPD cells from the count rows
+        # instead of the cached scorer rows -- the product library and the variant on the same reduced workload
+        variant = os.path.join(REPO, "loom_b200", "csrc", "libloomb200_counts.so")
+        ab = {"default": measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120)}
+        ab["from_counts"] = (measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120, env={"LOOM_B200_LIB": variant})
+                             if os.path.exists(variant) else {"error": "variant library not built (make -C loom_b200/csrc variants)"})
+        aux["k3_variant_score_from_counts"] = ab
         d = aux["differ"] = measure_in_subprocess("differ_bench.py", [R])
         for part in ("tare", "sparsify"):
             if isinstance(d.get(part), dict) and "achieved_gb_s" in d[part]:

@@ -129,6 +129,12 @@ def load_cuda():
     """Bind the CUDA library.  Fails loudly if it has not been built."""
     global _cuda
     if _cuda is None:
+        override = os.environ.get("LOOM_B200_LIB")      # a build variant of the same library (csrc/Makefile `variants`)
+        if override:
+            if not os.path.exists(override):
+                raise LoomError("LOOM_B200_LIB=%s does not exist" % override)
+            _cuda = Abi(override, "lb_")
+            return _cuda
         if not os.path.exists(CUDA_LIB):
             raise LoomError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(there is no CPU fallback)" % CUDA_LIB)

@@ -115,12 +115,45 @@ __device__ __forceinline__ int feat_class(int type) {
 }
 
 // add the scores of one warp's features of class `cls` (own[0..n)) for groups g0 + lane + 32*jj
+#ifdef LB_SCORE_FROM_COUNTS
+#define LB_AUX_PARAM , const float *aux
+#define LB_AUX_ARG , aux
+#else
+#define LB_AUX_PARAM
+#define LB_AUX_ARG
+#endif
 template <int NJ>
 __device__ __forceinline__ void score_list(int cls, const uint16_t *own, int n, const FeatDev *s_feat,
                                            const uint32_t *c_raw, const uint32_t *c_obs,
                                            const uint32_t *ints, const float *cache, int st,
-                                           int zero_row, int g0, int lane, float *acc) {
+                                           int zero_row, int g0, int lane, float *acc LB_AUX_PARAM) {
     if (cls == CL_CAT) {
+#ifdef LB_SCORE_FROM_COUNTS
+        // Variant: score from the count rows.  BB reads heads and tails, DD / DPD the value's count row and
+        // count_sum; unobserved cells read the feature's first rows (valid addresses) and are masked out.
+#pragma unroll 4
+        for (int k = 0; k < n; ++k) {
+            const int j = own[k];
+            const FeatDev &f = s_feat[j];
+            const uint32_t raw = c_raw[j];
+            const bool obs = c_obs[j] != 0u;
+            const bool bb = f.type == LB_BB;
+            const int r0 = f.int_row + ((obs && !bb) ? (int)raw : 0);
+            const int r1 = f.int_row + (bb ? 1 : f.dim);
+            const float a0 = bb ? f.hp[0] : f.a_scale * aux[f.aux_off + ((obs && !bb) ? (int)raw : 0)];
+            const float a1 = bb ? f.hp[1] : f.a_total;
+            const uint32_t *p0 = ints + (size_t)r0 * st + g0 + lane;
+            const uint32_t *p1 = ints + (size_t)r1 * st + g0 + lane;
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float x0 = (float)p0[32 * jj], x1 = (float)p1[32 * jj];
+                const float num = bb ? (raw ? a0 + x0 : a1 + x1) : a0 + x0;
+                const float den = bb ? (a0 + a1) + (x0 + x1) : a1 + x1;
+                acc[jj] += obs ? logf(num / den) : 0.f;
+            }
+        }
+        return;
+#endif
         // branch-free gathers: unobserved cells read the all-zero cache row
 #pragma unroll 4
         for (int k = 0; k < n; ++k) {
@@ -171,13 +204,13 @@ template <int NJ>
 __device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own, const FeatDev *s_feat,
                                            const uint32_t *c_raw, const uint32_t *c_obs,
                                            const uint32_t *ints, const float *cache, int st,
-                                           int zero_row, int g0, int lane, float *acc) {
+                                           int zero_row, int g0, int lane, float *acc LB_AUX_PARAM) {
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) acc[jj] = 0.f;
 #pragma unroll
     for (int c = 0; c < N_CLASS; ++c)
         if (off[c + 1] > off[c])
-            score_list<NJ>(c, s_own + off[c], off[c + 1] - off[c], s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+            score_list<NJ>(c, s_own + off[c], off[c + 1] - off[c], s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc LB_AUX_ARG);
 }
 
 // W warps per CTA; registers are capped at 128 per thread for every W
@@ -516,7 +549,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
             // past G are allocated (st >= G rounded up to 64) and simply ignored.
             for (int g0 = 0; g0 < G; g0 += 64) {
                 float acc[2];
-                score_warp<2>(off, s_own, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
+                score_warp<2>(off, s_own, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc LB_AUX_ARG);
                 s_part[warp * st + g0 + lane] = acc[0];
                 s_part[warp * st + g0 + lane + 32] = acc[1];
             }

@@ -596,6 +596,10 @@ extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, ui
         if (!again.empty()) LB_TRY(lb_sync_model(e));
         active.swap(again);
     }
+#ifdef LB_SCORE_FROM_COUNTS
+    for (int kid = 0; kid < K; ++kid)      // the sweep left the BB / DD / DPD scorer rows stale
+        if (!kind_mask || kind_mask[kid]) LB_TRY(lb_launch_refresh(e, kid));
+#endif
     if (debug_picks)
         LB_CUDA(cudaMemcpyAsync(debug_picks, d_picks, 4 * n * K, cudaMemcpyDeviceToHost, e->stream));
     if (debug_scores)
@@ -691,6 +695,12 @@ static int sweep_chains(const lb_handle *handles, int32_t n_handles, const uint3
             active[c].swap(again);
         }
     }
+#ifdef LB_SCORE_FROM_COUNTS
+    for (Engine *e : es) {                 // the sweep left the BB / DD / DPD scorer rows stale
+        for (int kid = 0; kid < (int)e->kinds.size(); ++kid) LB_TRY(lb_launch_refresh(e, kid));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+#endif
     return 0;
 }
 

@@ -1,0 +1,31 @@
+"""A/B of a build variant of the library on the headline kernel: N chains over ONE shared C2 row block, one timed
+step (ADD all + REMOVE/ADD all + REMOVE all) after one warm-up step, device time from CUDA events.  The library is the
+product's unless LOOM_B200_LIB points at a variant (loom_b200/csrc/Makefile `variants`).
+usage: sweep_variant_bench.py CHAINS ROWS   -> one JSON line"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, bench
+from loom_b200 import Engine, _abi, cat_sweep_multi
+cuda = _abi.load_cuda()
+n, R = int(sys.argv[1]), int(sys.argv[2])
+model, rows = bench.load_workload("C2", R)
+first, drain = bench.step_actions(R)
+cells = 4 * rows.n_cells()
+engines = []
+for c in range(n):
+    e = Engine(cuda); e.set_model(model)
+    if c == 0: e.set_rows(rows)
+    else: e.share_rows(engines[0])
+    engines.append(e)
+def step(it):
+    seeds = np.arange(n, dtype=np.uint64) * 1000 + it
+    cat_sweep_multi(engines, first, seeds); cat_sweep_multi(engines, drain, seeds)
+step(0)
+for e in engines: e.sync()
+engines[0].timer_start()
+step(1)
+ms = engines[0].timer_stop()
+# the state after the step is the empty one for every chain; a cheap invariant that the variant kept the books
+empty = all(int(e.get_groups(0)[0].sum()) == 0 for e in engines[:4])
+print(json.dumps({"lib": os.path.basename(cuda.path), "chains": n, "rows": R, "ms_per_step": ms,
+                  "cells_per_s": n * cells / (ms * 1e-3), "drained_to_empty": empty}))
