@@ -623,6 +623,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # query path (8f n3) and tare / sparsify (8f n4) on the same C2 mix, each in its own process
         aux["query"] = measure_in_subprocess("query_bench.py", [R, 1000000])
+        # the same with K1 reducing scores to log-sum-exp in registers (scores not materialised)
+        aux["query_fused"] = measure_in_subprocess("query_bench.py", [R, 1000], env={"LB_QUERY_FUSED": "1"})
         aux["score_error"] = measure_in_subprocess("score_error.py", [20000])     # parity check 2, per feature type
         # experiment for the next round: the sweep scoring BB / DD / DPD cells from the count rows
         # instead of the cached scorer rows -- the product library and the variant on the same reduced workload

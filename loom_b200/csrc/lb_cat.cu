@@ -818,11 +818,14 @@ __global__ void k_score_table(const KindDev *kinds, int kid, const FeatDev *feat
     }
 }
 
-template <int NJ>
+// LSE = true (one tile of <= 128 groups covers the kind): the scores are not written out; each warp reduces its rows'
+// score vectors to log_sum_exp_g in registers and out[r - b] receives (lse_first) or accumulates that scalar -- the
+// "scores not materialised" form of K1, what QueryServer Score consumes.
+template <int NJ, bool LSE = false>
 __global__ void __launch_bounds__(SC_THREADS)
 k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
              const int32_t *row_base, const float *tab, RowsDev rows, uint64_t b, uint64_t en,
-             int n_empty, int g_base, float *out) {
+             int n_empty, int g_base, float *out, int lse_first = 0) {
     __shared__ FeatDev s_feat[SC_FC];
     __shared__ int32_t s_fid[SC_FC];
     __shared__ uint32_t s_row[SC_FC][SC_TR];     // table row of the cell (0 = unobserved), or raw bits for NICH
@@ -943,11 +946,25 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
 #pragma unroll
         for (int q = 0; q < SC_RW; ++q) {
             const uint64_t r = r0 + warp * SC_RW + q;
-            if (r >= en) continue;
+            if (r >= en) continue;          // warp-uniform
+            if constexpr (LSE) {
+                float m = -INFINITY;
 #pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) {
-                const int g = g_base + lane + 32 * jj;
-                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[q][jj];
+                for (int jj = 0; jj < NJ; ++jj)
+                    if (g_base + lane + 32 * jj < G) m = fmaxf(m, acc[q][jj]);
+                for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+                float t = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj)
+                    if (g_base + lane + 32 * jj < G) t += expf(acc[q][jj] - m);
+                for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+                if (lane == 0) out[r - b] = (lse_first ? 0.f : out[r - b]) + m + logf(t);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < NJ; ++jj) {
+                    const int g = g_base + lane + 32 * jj;
+                    if (g < G) out[(r - b) * (uint64_t)G + g] = acc[q][jj];
+                }
             }
         }
     }
@@ -977,9 +994,11 @@ int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int
     return 0;
 }
 
-int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
+// lse: 0 = scores out [rows][G]; 1 / 2 = out[row] set to / increased by the row's log_sum_exp (needs G <= 128)
+int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse) {
     const KindHost &k = e->kinds[kid];
     const int nf = (int)k.fids.size();
+    if (lse && k.G > 128) return lb_fail("fused score + log-sum-exp needs at most 128 groups (kind %d has %d)", kid, k.G);
     // layout of the score table
     std::vector<int32_t> row_base(std::max(nf, 1), 0), row_feat(1, -1);
     for (int j = 0; j < nf; ++j) {
@@ -1009,6 +1028,21 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
     const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 4));
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+    if (lse) {
+        const int first = lse == 1;
+        if (k.G <= 32)
+            k_score_rows<1, true><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                                     d_tab, rows, b, en, e->empty_group_count, 0, d_out, first);
+        else if (k.G <= 64)
+            k_score_rows<2, true><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                                     d_tab, rows, b, en, e->empty_group_count, 0, d_out, first);
+        else
+            k_score_rows<4, true><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base,
+                                                                     d_tab, rows, b, en, e->empty_group_count, 0, d_out, first);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+        return 0;
+    }
     for (int g_base = 0; g_base < k.G; g_base += 128) {
         const int left = k.G - g_base;
         if (left <= 32)

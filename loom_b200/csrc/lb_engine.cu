@@ -865,9 +865,17 @@ extern "C" int lb_query_score(lb_handle h, uint64_t b, uint64_t en, float *out) 
     LB_TRY(lb_ensure_scratch(e, score_bytes + 4 * (size_t)chunk + 256));
     float *d_scores = (float *)e->d_scratch;
     float *d_acc = (float *)((char *)e->d_scratch + score_bytes);
+    // LB_QUERY_FUSED=1 (an experiment measured beside the default, scratch/query_bench.py): K1 reduces each row's
+    // scores to their log-sum-exp in registers instead of writing [rows][G] scores for a second kernel to read back
+    const char *fused_env = getenv("LB_QUERY_FUSED");
+    const bool fused = fused_env && fused_env[0] == '1' && gmax <= 128;
     for (uint64_t c0 = b; c0 < en; c0 += chunk) {
         const uint64_t c1 = std::min(en, c0 + chunk);
         for (int kid = 0; kid < (int)e->kinds.size(); ++kid) {
+            if (fused) {
+                LB_TRY(lb_launch_score_rows(e, kid, c0, c1, d_acc, kid == 0 ? 1 : 2));
+                continue;
+            }
             LB_TRY(lb_launch_score_rows(e, kid, c0, c1, d_scores));
             LB_TRY(lb_launch_row_lse_add(e, d_scores, c1 - c0, e->kinds[kid].G, d_acc, kid == 0));
         }

@@ -182,7 +182,7 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
 int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_actions, uint64_t seed,
                     uint64_t offset, uint32_t *d_picks, float *d_scores, int stride);
 int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int G, float *d_acc, int first);
-int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
+int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse = 0);
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
                              const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,

@@ -18,10 +18,12 @@ for k in range(model.n_kinds):            # the generating partition as the late
 e.accumulate_rows()
 to_sample = np.arange(1, model.n_features, 2, dtype=np.uint32)
 e.query_score(0, min(R, 4096)); e.query_sample(0, to_sample, 256, seed=1)      # warm-up
-t0 = time.perf_counter(); s = e.query_score(); t_score = time.perf_counter() - t0
+t_score = 1e9
+for _ in range(5):                                                              # best of 5: the call is ~ms
+    t0 = time.perf_counter(); s = e.query_score(); t_score = min(t_score, time.perf_counter() - t0)
 t0 = time.perf_counter(); v = e.query_sample(0, to_sample, DRAWS, seed=2); t_sample = time.perf_counter() - t0
 assert np.isfinite(s).all()
-print(json.dumps({"impl": "oracle" if use_oracle else "cuda", "cores": os.cpu_count(), "rows": R, "kinds": model.n_kinds,
+print(json.dumps({"impl": "oracle" if use_oracle else "cuda", "fused": os.environ.get("LB_QUERY_FUSED") == "1", "cores": os.cpu_count(), "rows": R, "kinds": model.n_kinds,
                   "groups": [int(e.kind_info(k).n_groups) for k in range(model.n_kinds)],
                   "score_rows_per_s": R / t_score, "score_cells_per_s": rows.n_cells() / t_score, "score_ms": t_score * 1e3,
                   "draws": DRAWS, "features_per_draw": len(to_sample), "sample_values_per_s": DRAWS * len(to_sample) / t_sample,

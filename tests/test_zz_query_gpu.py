@@ -258,3 +258,36 @@ def test_score_from_counts_variant_replays_on_the_oracle(tmp_path):
     script.write_text(VARIANT_WORKER.format(repo=repo, lib="libloomb200_counts.so"))
     proc = subprocess.run([sys.executable, str(script)], capture_output=True, timeout=600, env=dict(os.environ, LOOM_B200_LIB=lib))
     assert proc.returncode == 0 and b"variant ok" in proc.stdout, proc.stdout.decode()[-1000:] + proc.stderr.decode()[-3000:]
+
+
+# ------------------------------------------------------------------------------------------ fused Score (K1 without scores out)
+@pytest.mark.gpu
+def test_fused_query_score_matches_the_two_kernel_path(oracle_abi, cuda_abi, monkeypatch):
+    """LB_QUERY_FUSED=1: K1 reduces each row's scores to their log-sum-exp in registers (an experiment measured beside
+    the default path).  Same numbers as score-then-reduce, same 1e-5 against the oracle; kinds with more than 128
+    groups fall back to the two-kernel path."""
+    from loom_b200 import Engine, synth, sweep_actions
+    for n_rows, types in ((3000, [("bb", 4), ("dd16", 3), ("dd256", 2), ("gp", 3), ("nich", 3)]), (700, [("bb", 3), ("nich", 2)])):
+        model, rows, _ = synth.generate(n_rows, types, density=0.6, seed=8)
+        g, o = Engine(cuda_abi), Engine(oracle_abi)
+        for e in (g, o):
+            e.set_model(model)
+            e.set_rows(rows)
+        g.cat_sweep(sweep_actions(n_rows), seed=2)
+        for k in range(model.n_kinds):
+            counts, ints, flts = g.get_groups(k)
+            keep = counts > 0
+            o.set_groups(k, int(keep.sum()), counts[keep], ints[:, keep], flts[:, keep])
+            g.set_groups(k, int(keep.sum()), counts[keep], ints[:, keep], flts[:, keep])
+        monkeypatch.delenv("LB_QUERY_FUSED", raising=False)
+        plain = g.query_score()
+        monkeypatch.setenv("LB_QUERY_FUSED", "1")
+        fused = g.query_score()
+        monkeypatch.delenv("LB_QUERY_FUSED", raising=False)
+        want = o.query_score().astype(np.float64)
+        assert np.allclose(fused, plain, rtol=2e-6, atol=2e-6)
+        assert (np.abs(fused - want) <= 1e-5 * np.maximum(1.0, np.abs(want))).all()
+        ragged = g.query_score(5, n_rows - 3)                     # unaligned range, default path
+        monkeypatch.setenv("LB_QUERY_FUSED", "1")
+        assert np.allclose(g.query_score(5, n_rows - 3), ragged, rtol=2e-6, atol=2e-6)
+        monkeypatch.delenv("LB_QUERY_FUSED", raising=False)
