@@ -196,15 +196,23 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
         shutil.rmtree(d, ignore_errors=True)
 
 
+_BENCH_START = time.time()
+AUX_BUDGET_S = 330.0        # the auxiliary experiments stop being started once the whole run is this old
+
+
 def measure_in_subprocess(script, script_args, timeout=60, env=None):
     """Run one of scratch/*_bench.py in its OWN process and return the JSON line it prints: the rows of
     SURVEY.md 8f added last (query path, tare / sparsify) are measured beside the headline without being
     able to disturb it (a fault in them cannot take the bench process or its CUDA context down)."""
     cmd = [sys.executable, os.path.join(REPO, "scratch", script)] + [str(a) for a in script_args]
+    left = AUX_BUDGET_S - (time.time() - _BENCH_START)
+    if left < 15:
+        return {"skipped": "time budget of the default run (%.0f s) used up" % AUX_BUDGET_S}
+    timeout = min(timeout, left)
     try:
         proc = subprocess.run(cmd, capture_output=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     except subprocess.TimeoutExpired:
-        return {"error": "timed out after %d s" % timeout}
+        return {"error": "timed out after %.0f s" % timeout}
     if proc.returncode != 0:
         return {"error": "exit %d: %s" % (proc.returncode, proc.stderr.decode(errors="replace")[-300:])}
     try:
