@@ -112,6 +112,7 @@ typedef void *lb_handle;
  *   3 ephemeral kind partition   a = row, b = kind id
  *   4 DPD stick-breaking at ingest (loom_b200_io.h)
  *   5 / 6 query sampler: group pick / value draw (query_sample below)
+ *   7 / 8 generate_rows: seating / observed flag and value
  * (replaces distributions::rng_t; sampled values are only statistically
  *  comparable with the reference, see SURVEY.md section 7 "RNG".) */
 
@@ -273,6 +274,20 @@ int LB_NAME(query_score)(lb_handle h, uint64_t row_begin, uint64_t row_end, floa
 int LB_NAME(query_sample)(lb_handle h, uint64_t row, const uint32_t *to_sample, int32_t n_to_sample,
                           uint32_t n_samples, uint64_t seed, uint64_t draw_offset,
                           uint32_t *out_values, uint32_t *out_groups);
+
+/* Loom::generate -> generate_rows (src/loom.cc:548-562, src/generate.hpp:36-93): synthesise n_rows rows from
+ * the model.  Per kind the row's group comes from the kind's Pitman-Yor process (sequential seating), every
+ * feature is observed with probability `density`, and an observed value is drawn from the group's posterior
+ * predictive given the values the group already holds (ProductMixture::sample_value), then added to the group.
+ * Afterwards the engine holds the rows (as after set_rows), every row assigned, and the groups' statistics.
+ * The seating is sequential per kind (host, float64); the values are independent chains per (group, feature)
+ * -- one device thread each, walking its group's rows in order -- which is exactly the reference's order of
+ * draws inside a group.  A DPD draw outside the dictionary leaves the cell unobserved.
+ * Random numbers: stream 7 (a = row, b = kind) seats the row; stream 8 (a = row, b = featureid << 10 | draw)
+ * decides observed (draw 0) and draws the value (draws 1..). */
+int LB_NAME(generate_rows)(lb_handle h, uint64_t n_rows, float density, uint64_t seed);
+/* The loaded row block as the dense columns set_rows takes (HOST buffers of those sizes). */
+int LB_NAME(get_rows)(lb_handle h, uint8_t *cat8, uint32_t *wide, uint32_t *mask);
 
 /* ProductMixture_::add_value for rows [row_begin,row_end) with their CURRENT
  * assignments, all kinds (kind < 0) or one kind: rebuilds/extends sufficient

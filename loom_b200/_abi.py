@@ -56,6 +56,8 @@ SIGNATURES = {
     "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
     "query_sample": (C.c_int, [_h, C.c_uint64, _u32p, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, _u32p, _u32p]),
     "share_rows": (C.c_int, [_h, _h]),
+    "generate_rows": (C.c_int, [_h, C.c_uint64, C.c_float, C.c_uint64]),
+    "get_rows": (C.c_int, [_h, _u8p, _u32p, _u32p]),
     "differ_reset": (C.c_int, [_h]),
     "differ_add_rows": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),
     "differ_make_tare": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p, _u8p, _u32p]),

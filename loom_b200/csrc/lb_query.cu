@@ -63,7 +63,8 @@ __global__ void k_query_pick(const QSlot *slots, int n_slots, const double *cdf,
 struct Draws {
     uint64_t seed, a;
     uint32_t base, j;
-    __device__ double u() { return (double)(lb_philox_u32(seed, 6, a, base | j++) >> 8) * (1.0 / 16777216.0); }   // [0,1)
+    uint32_t stream = 6u;
+    __device__ double u() { return (double)(lb_philox_u32(seed, stream, a, base | j++) >> 8) * (1.0 / 16777216.0); }   // [0,1)
     __device__ double uo() { return u() + 0.5 / 16777216.0; }                                                     // (0,1)
 };
 
@@ -103,28 +104,13 @@ static __device__ double lb_sample_poisson(Draws &d, double lam) {
     return floor(lam);
 }
 
-// Group::sample_value: one thread per (sample, requested feature)
-__global__ void k_query_values(const KindDev *kinds, const FeatDev *feats, const float *aux, const uint32_t *f2k,
-                               const uint32_t *to_sample, int n_to, uint32_t n_samples, int K, uint64_t seed,
-                               uint64_t draw_offset, const uint32_t *groups, uint32_t *values) {
-    const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)n_samples * n_to) return;
-    const uint32_t smp = (uint32_t)(idx / n_to);
-    const uint32_t fid = to_sample[idx % n_to];
-    const FeatDev f = feats[fid];
-    const uint32_t kid = f2k[fid];
-    const KindDev &kd = kinds[kid];
-    const uint32_t g = groups[(uint64_t)smp * K + kid];
-    const size_t st = (size_t)kd.Gcap;
-    const uint32_t *in = kd.ints + (size_t)f.int_row * st + g;
-    const double *fl = kd.flts + (size_t)f.flt_row * st + g;
-    Draws d{seed, draw_offset + smp, fid << 10, 0u};
-    uint32_t out = 0;
+// Group::sample_value of one feature for the group whose statistics start at in / fl (column stride st)
+static __device__ uint32_t lb_sample_value(const FeatDev &f, const float *aux, const uint32_t *in, const double *fl,
+                                           size_t st, Draws &d) {
     switch (f.type) {
     case LB_BB: {
         const double al = f.hp[0], be = f.hp[1], h = in[0], t = in[st];
-        out = d.u() < (al + h) / (al + be + h + t);
-        break;
+        return d.u() < (al + h) / (al + be + h + t);
     }
     case LB_DD:
     case LB_DPD: {
@@ -142,15 +128,13 @@ __global__ void k_query_values(const KindDev *kinds, const FeatDev *feats, const
             c += w;
             if (c > t) { last = v; break; }
         }
-        out = last == f.dim ? LB_DPD_OTHER : (uint32_t)last;
-        break;
+        return last == f.dim ? LB_DPD_OTHER : (uint32_t)last;
     }
     case LB_GP: {
         const double shape = (double)f.hp[0] + (double)in[st], rate = (double)f.hp[1] + (double)in[0];
         const double lam = lb_sample_gamma(d, shape) / rate;
         const double x = lb_sample_poisson(d, lam);
-        out = x >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)x;
-        break;
+        return x >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)x;
     }
     case LB_NICH: {
         const double mu = f.hp[0], kappa = f.hp[1], sigmasq = f.hp[2], nu = f.hp[3];
@@ -159,11 +143,57 @@ __global__ void k_query_values(const KindDev *kinds, const FeatDev *feats, const
         const double sn = (nu * sigmasq + ctv + n * kappa * dm * dm / kn) / nun;
         const double u = d.uo(), v = d.u();
         const double t = sqrt(nun * (pow(u, -2.0 / nun) - 1.0)) * cospi(2.0 * v);
-        out = __float_as_uint((float)(mun + sqrt(sn * (kn + 1.0) / kn) * t));
-        break;
+        return __float_as_uint((float)(mun + sqrt(sn * (kn + 1.0) / kn) * t));
     }
     }
-    values[idx] = out;
+    return 0u;
+}
+
+// Group::sample_value: one thread per (sample, requested feature)
+__global__ void k_query_values(const KindDev *kinds, const FeatDev *feats, const float *aux, const uint32_t *f2k,
+                               const uint32_t *to_sample, int n_to, uint32_t n_samples, int K, uint64_t seed,
+                               uint64_t draw_offset, const uint32_t *groups, uint32_t *values) {
+    const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)n_samples * n_to) return;
+    const uint32_t smp = (uint32_t)(idx / n_to);
+    const uint32_t fid = to_sample[idx % n_to];
+    const FeatDev f = feats[fid];
+    const uint32_t kid = f2k[fid];
+    const KindDev &kd = kinds[kid];
+    const uint32_t g = groups[(uint64_t)smp * K + kid];
+    const size_t st = (size_t)kd.Gcap;
+    Draws d{seed, draw_offset + smp, fid << 10, 0u};
+    values[idx] = lb_sample_value(f, aux, kd.ints + (size_t)f.int_row * st + g, kd.flts + (size_t)f.flt_row * st + g, st, d);
+}
+
+// generate_rows (src/generate.hpp:36-93): one thread per (feature of the kind, group) walks the group's rows in order --
+// observed with probability `density`, value from the group's posterior predictive, added to the group -- and writes
+// the cells of its column.  Chains of different (group, feature) pairs touch disjoint statistics and disjoint cells;
+// only the mask words are shared between the groups of a column (atomicOr).
+__global__ void k_generate(KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats, const float *aux,
+                           uint64_t R, uint64_t W, uint8_t *cat8, uint32_t *wide, uint32_t *mask,
+                           const uint32_t *group_ptr, const uint32_t *group_rows, int n_groups, float density, uint64_t seed) {
+    KindDev &kd = kinds[kid];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kd.nf * n_groups) return;
+    const int j = idx / n_groups, g = idx % n_groups;
+    const int fid = kind_feats[kd.feat_begin + j];
+    const FeatDev f = feats[fid];
+    const int st = kd.Gcap;
+    uint32_t *in = kd.ints + (size_t)f.int_row * st + g;
+    double *fl = kd.flts + (size_t)f.flt_row * st + g;
+    float *c = kd.cache + (size_t)f.cache_row * st + g;
+    for (uint32_t i = group_ptr[g]; i < group_ptr[g + 1]; ++i) {
+        const uint64_t r = group_rows[i];
+        Draws d{seed, r, (uint32_t)fid << 10, 0u, 8u};
+        if (!(d.u() < (double)density)) continue;
+        const uint32_t raw = lb_sample_value(f, aux, in, fl, (size_t)st, d);
+        if (f.type == LB_DPD && raw == LB_DPD_OTHER) continue;
+        lb_update_cell(f, aux, in, fl, c, st, raw, +1);
+        if (f.is_wide) wide[(uint64_t)f.col * R + r] = raw;
+        else cat8[(uint64_t)f.col * R + r] = (uint8_t)raw;
+        atomicOr(&mask[(uint64_t)fid * W + (r >> 5)], 1u << (r & 31));
+    }
 }
 
 extern "C" int lb_query_sample(lb_handle h, uint64_t row, const uint32_t *to_sample, int32_t n_to, uint32_t n_samples,
@@ -221,6 +251,82 @@ extern "C" int lb_query_sample(lb_handle h, uint64_t row, const uint32_t *to_sam
     LB_CUDA(cudaMemcpyAsync(out_values, d_values, 4 * (size_t)n_samples * n_to, cudaMemcpyDeviceToHost, e->stream));
     if (out_groups)
         LB_CUDA(cudaMemcpyAsync(out_groups, d_groups, 4 * (size_t)n_samples * K, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+
+extern "C" int lb_generate_rows(lb_handle h, uint64_t R, float density, uint64_t seed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F) return lb_fail("generate_rows before set_model");
+    if (!(density >= 0.f && density <= 1.f)) return lb_fail("generate_rows: density must be in [0, 1]");
+    if (R == 0 || R >= (1ull << 31)) return lb_fail("generate_rows: bad row count");
+    const uint64_t W = (R + 31) / 32;
+    {   // an all-unobserved block of R rows
+        std::vector<uint8_t> cat8((size_t)e->F8 * R + 1, 0);
+        std::vector<uint32_t> wide((size_t)e->FW * R + 1, 0), mask((size_t)e->F * W, 0);
+        LB_TRY(lb_set_rows(h, R, cat8.data(), wide.data(), mask.data()));
+    }
+    const int K = (int)e->kinds.size();
+    std::vector<uint32_t> pick(R), counts, group_ptr, group_rows(R), cursor;
+    std::vector<double> p;
+    for (int kid = 0; kid < K; ++kid) {
+        // the kind's Pitman-Yor process (Clustering::PitmanYor seating), float64 on the host like the oracle
+        const double alpha = e->kinds[kid].alpha, d = e->kinds[kid].d;
+        counts.clear();
+        int m = 0;
+        for (uint64_t r = 0; r < R; ++r) {
+            p.resize((size_t)m + 1);
+            double total = 0;
+            for (int g = 0; g < m; ++g) total += p[g] = counts[g] - d;
+            total += p[m] = alpha + d * m;
+            const double t = (double)lb_uniform(seed, 7u, r, (uint32_t)kid) * total;
+            double c = 0;
+            int g = m, last = 0;
+            for (int i = 0; i <= m; ++i) {          // distributions::sample_from_likelihoods
+                if (p[i] > 0) last = i;
+                c += p[i];
+                if (c > t) { last = i; break; }
+            }
+            g = last;
+            if (g == m) { counts.push_back(0); ++m; }
+            counts[g]++;
+            pick[r] = (uint32_t)g;
+        }
+        LB_TRY(lb_set_groups(h, kid, m, counts.data(), nullptr, nullptr));
+        LB_TRY(lb_set_assignments(h, kid, pick.data()));
+        const KindHost &k = e->kinds[kid];
+        if (k.fids.empty()) continue;
+        // rows of every group in order (counting sort of the seating)
+        group_ptr.assign((size_t)m + 1, 0);
+        for (int g = 0; g < m; ++g) group_ptr[g + 1] = group_ptr[g] + counts[g];
+        cursor.assign(group_ptr.begin(), group_ptr.end() - 1);
+        for (uint64_t r = 0; r < R; ++r) group_rows[cursor[pick[r]]++] = (uint32_t)r;
+        const size_t ptr_bytes = (4 * ((size_t)m + 1) + 255) / 256 * 256;
+        LB_TRY(lb_ensure_scratch(e, ptr_bytes + 4 * (size_t)R + 256));
+        uint32_t *d_ptr = (uint32_t *)e->d_scratch, *d_rows = (uint32_t *)((char *)e->d_scratch + ptr_bytes);
+        LB_CUDA(cudaMemcpyAsync(d_ptr, group_ptr.data(), 4 * ((size_t)m + 1), cudaMemcpyHostToDevice, e->stream));
+        LB_CUDA(cudaMemcpyAsync(d_rows, group_rows.data(), 4 * (size_t)R, cudaMemcpyHostToDevice, e->stream));
+        LB_TRY(lb_sync_model(e));
+        const int n_threads = (int)k.fids.size() * m;
+        k_generate<<<(n_threads + 63) / 64, 64, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, e->d_aux, R, W,
+                                                                e->d_cat8, e->d_wide, e->d_mask, d_ptr, d_rows, m, density, seed);
+        LB_CUDA(cudaGetLastError());
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_MISC]++;
+        LB_TRY(lb_launch_refresh(e, kid));
+        LB_CUDA(cudaStreamSynchronize(e->stream));       // the staging vectors are reused by the next kind
+    }
+    return 0;
+}
+
+extern "C" int lb_get_rows(lb_handle h, uint8_t *cat8, uint32_t *wide, uint32_t *mask) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->R) return lb_fail("get_rows: no rows loaded");
+    if (e->F8) LB_CUDA(cudaMemcpyAsync(cat8, e->d_cat8, (size_t)e->F8 * e->R, cudaMemcpyDeviceToHost, e->stream));
+    if (e->FW) LB_CUDA(cudaMemcpyAsync(wide, e->d_wide, 4 * (size_t)e->FW * e->R, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaMemcpyAsync(mask, e->d_mask, 4 * (size_t)e->F * e->W, cudaMemcpyDeviceToHost, e->stream));
     LB_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }

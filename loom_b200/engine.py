@@ -227,6 +227,20 @@ class Engine:
                            ptr(rows.mask, _u32p)))
         self.n_rows = rows.n_rows
 
+    def generate_rows(self, n_rows, density, seed):
+        """Loom::generate's generate_rows: synthesise rows from the model; the engine then holds them, assigned"""
+        self.abi.check(self.abi.generate_rows(self.h, n_rows, density, seed))
+        self.n_rows = int(n_rows)
+
+    def get_rows(self):
+        """the loaded block as a RowBlock"""
+        F, F8, R = self.model.n_features, self.model.n8(), self.n_rows
+        cat8 = np.zeros((max(F8, 1), R), np.uint8)
+        wide = np.zeros((max(F - F8, 1), R), np.uint32)
+        mask = np.zeros((F, (R + 31) // 32), np.uint32)
+        self.abi.check(self.abi.get_rows(self.h, ptr(cat8, _u8p), ptr(wide, _u32p), ptr(mask, _u32p)))
+        return RowBlock(R, cat8[:F8] if F8 else cat8[:0], wide[:F - F8] if F > F8 else wide[:0], mask)
+
     def share_rows(self, owner):
         """read the owner's row block (loom's samples share one rows file)"""
         self.abi.check(self.abi.share_rows(self.h, owner.h))

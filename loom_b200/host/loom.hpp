@@ -269,6 +269,40 @@ public:
         LOOM_B200_IO(lbio_samples_close(samples));
     }
 
+    // Loom::generate (src/loom.cc:548-562) + generate_rows (src/generate.hpp:36-93): hypers from the prior grids,
+    // then config.generate.row_count rows synthesised on the device and written as a rows stream (ids 0, 1, ...)
+    void generate(const char *rows_out) {
+        if (assigned_count_ || !assign_rowids_.empty()) LOOM_B200_ERROR("expected assignments.row_count() == 0");
+        if (view_.n_dpd) model_install();      // generate needs the dictionaries the model file carries
+        SeedStream rng(config_.seed);
+        if (config_.hyper_run && view_.has_hyper_prior) HyperKernel(cross_cat_, view_.hyper_prior).run(rng());
+        const uint64_t R = config_.generate_row_count;
+        LOOM_B200_CHECK(LB_NAME(generate_rows)(h(), R, config_.generate_density, rng()));
+        cross_cat_.rows_attached(R);
+        rowids_.resize(R);
+        std::iota(rowids_.begin(), rowids_.end(), (uint64_t)0);
+        assigned_pos_ = unassigned_pos_ = 0;
+        assigned_count_ = R;
+        // the block as a rows stream: the diff encoder with an empty tare gives exactly the observed cells per row
+        const std::vector<uint8_t> no_tare_obs(view_.n_features, 0);
+        const std::vector<uint32_t> no_tare_val(view_.n_features, 0);
+        uint64_t n_pos = 0, n_neg = 0;
+        LOOM_B200_CHECK(LB_NAME(differ_compress_rows)(h(), no_tare_obs.data(), no_tare_val.data(), &n_pos, &n_neg));
+        std::vector<uint64_t> pos_ptr(R + 1), neg_ptr(R + 1);
+        std::vector<uint32_t> pos_feature(n_pos + 1), pos_value(n_pos + 1), neg_feature(n_neg + 1);
+        LOOM_B200_CHECK(LB_NAME(differ_fetch)(h(), pos_ptr.data(), pos_feature.data(), pos_value.data(), neg_ptr.data(), neg_feature.data()));
+        lbio_row_block out;
+        std::memset(&out, 0, sizeof(out));
+        out.n_rows = R;
+        out.rowids = rowids_.data();
+        out.pos_ptr = pos_ptr.data();
+        out.pos_feature = pos_feature.data();
+        out.pos_value = pos_value.data();
+        out.neg_ptr = neg_ptr.data();
+        out.neg_feature = neg_feature.data();
+        LOOM_B200_IO(lbio_rows_write(rows_out, model_file_, &out));
+    }
+
     // Loom::mix (src/loom.cc:564-586): sample_skip times { REMOVE + ADD every row; kind kernel; hyper kernel } on a
     // fully assigned state -- what loom.generate runs to decorrelate a synthetic dataset from the model that made it
     void mix(const char *rows_in) {

@@ -747,7 +747,7 @@ int lo_query_sample(lb_handle h, uint64_t row, const uint32_t *to_sample, int32_
                 out_values[(uint64_t)s * n_to + j] =
                     om_sample_value(&e->specs[f], e->aux, k->ints + (size_t)k->int_off[local] * k->Gcap + g,
                                     k->flts + (size_t)k->flt_off[local] * k->Gcap + g, k->Gcap, seed,
-                                    draw_offset + s, (uint32_t)f);
+                                    draw_offset + s, (uint32_t)f, 6, 0);
             }
         }
         free(scores); free(probs);
@@ -967,5 +967,68 @@ int lo_differ_fetch(lb_handle h, uint64_t *pos_ptr, uint32_t *pos_feature, uint3
     memcpy(pos_feature, e->diff_pos_feature, 4 * np);
     memcpy(pos_value, e->diff_pos_value, 4 * np);
     memcpy(neg_feature, e->diff_neg_feature, 4 * nn);
+    return 0;
+}
+
+/* ---- Loom::generate -> generate_rows (src/generate.hpp:36-93) ------------------------------------------ */
+int lo_generate_rows(lb_handle h, uint64_t R, float density, uint64_t seed) {
+    engine_t *e = h;
+    if (!e->F) return lo_fail("generate_rows before set_model");
+    if (!(density >= 0.f && density <= 1.f)) return lo_fail("generate_rows: density must be in [0, 1]");
+    if (R == 0 || R >= (1ull << 31)) return lo_fail("generate_rows: bad row count");
+    const uint64_t W = (R + 31) / 32;
+    uint8_t *cat8 = xcalloc((size_t)e->F8 * R + 1, 1);
+    uint32_t *wide = xcalloc((size_t)e->FW * R + 1, 4), *mask = xcalloc((size_t)e->F * W, 4);
+    int rc = lo_set_rows(h, R, cat8, wide, mask);
+    free(cat8); free(wide); free(mask);
+    if (rc) return rc;
+    uint32_t *pick = xcalloc(R, 4), *counts = xcalloc(R + 1, 4);
+    double *p = xcalloc(R + 2, 8);
+    for (int kid = 0; kid < e->K && !rc; ++kid) {
+        /* the kind's Pitman-Yor process: Clustering::PitmanYor seating, row by row */
+        const double alpha = e->kinds[kid].alpha, d = e->kinds[kid].d;
+        int m = 0;
+        for (uint64_t r = 0; r < R; ++r) {
+            double total = 0;
+            for (int g = 0; g < m; ++g) total += p[g] = counts[g] - d;
+            total += p[m] = alpha + d * m;
+            const int g = om_sample_from_likelihoods(lo_uniform(seed, 7, r, (uint32_t)kid), p, m + 1, total);
+            if (g == m) counts[m++] = 0;
+            counts[g]++;
+            pick[r] = (uint32_t)g;
+        }
+        rc = lo_set_groups(h, kid, m, counts, NULL, NULL);
+        if (!rc) rc = lo_set_assignments(h, kid, pick);
+        if (rc) break;
+        kind_t *k = &e->kinds[kid];
+        /* values: inside a group the rows are visited in order, every (group, feature) chain is independent */
+        for (int j = 0; j < k->nf; ++j) {
+            const int f = k->fids[j];
+            const lb_feature_spec *s = &e->specs[f];
+            for (uint64_t r = 0; r < R; ++r) {
+                const uint32_t g = pick[r];
+                if (!(lo_uniform(seed, 8, r, ((uint32_t)f << 10)) < (double)density)) continue;
+                uint32_t *in = k->ints + (size_t)k->int_off[j] * k->Gcap + g;
+                double *fl = k->flts + (size_t)k->flt_off[j] * k->Gcap + g;
+                const uint32_t raw = om_sample_value(s, e->aux, in, fl, k->Gcap, seed, r, (uint32_t)f, 8, 1);
+                if (s->type == LB_DPD && raw == LB_DPD_OTHER) continue;
+                om_add_value(s, in, fl, k->Gcap, raw, +1);
+                if (f < e->F8) e->cat8[(size_t)f * R + r] = (uint8_t)raw;
+                else e->wide[(size_t)(f - e->F8) * R + r] = raw;
+                e->mask[(size_t)f * W + (r >> 5)] |= 1u << (r & 31);
+            }
+        }
+        kind_refresh_all(e, k);
+    }
+    free(pick); free(counts); free(p);
+    return rc;
+}
+
+int lo_get_rows(lb_handle h, uint8_t *cat8, uint32_t *wide, uint32_t *mask) {
+    engine_t *e = h;
+    if (!e->R) return lo_fail("get_rows: no rows loaded");
+    if (e->F8) memcpy(cat8, e->cat8, (size_t)e->F8 * e->R);
+    if (e->FW) memcpy(wide, e->wide, 4 * (size_t)e->FW * e->R);
+    memcpy(mask, e->mask, 4 * (size_t)e->F * e->W);
     return 0;
 }

@@ -106,7 +106,7 @@ double om_py_score_counts(double alpha, double d, const uint32_t *counts, int n)
 int om_sample_from_scores(double u, double *scores, int n);
 int om_sample_from_likelihoods(double u, const double *p, int n, double total);
 uint32_t om_sample_value(const lb_feature_spec *s, const float *aux, const uint32_t *ints, const double *flts,
-                         int stride, uint64_t seed, uint64_t a, uint32_t featureid);
+                         int stride, uint64_t seed, uint64_t a, uint32_t featureid, uint32_t stream, uint32_t first_draw);
 
 /* kind helpers (loom_oracle.c) */
 void kind_free(kind_t *k);

@@ -233,8 +233,8 @@ double lo_feature_score_data(const lb_feature_spec *spec, const float *aux,
  *         by Bailey's polar method (1994): t = sqrt(nu (U^(-2/nu) - 1)) cos(2 pi V)   [2] */
 #define I(row) ((double)ints[(size_t)(row) * stride])
 #define D(row) (flts[(size_t)(row) * stride])
-typedef struct { uint64_t seed, a; uint32_t base, j; } draw_t;
-static double draw_u(draw_t *d) { return lo_uniform(d->seed, 6, d->a, d->base | d->j++); }          /* [0,1) */
+typedef struct { uint64_t seed, a; uint32_t base, j, stream; } draw_t;
+static double draw_u(draw_t *d) { return lo_uniform(d->seed, d->stream, d->a, d->base | d->j++); }          /* [0,1) */
 static double draw_uo(draw_t *d) { return draw_u(d) + 0.5 / 16777216.0; }                          /* (0,1) */
 
 static double sample_gamma(draw_t *d, double shape) {
@@ -272,8 +272,8 @@ static double sample_poisson(draw_t *d, double lam) {
 }
 
 uint32_t om_sample_value(const lb_feature_spec *s, const float *aux, const uint32_t *ints, const double *flts,
-                         int stride, uint64_t seed, uint64_t a, uint32_t featureid) {
-    draw_t d = {seed, a, featureid << 10, 0};
+                         int stride, uint64_t seed, uint64_t a, uint32_t featureid, uint32_t stream, uint32_t first_draw) {
+    draw_t d = {seed, a, featureid << 10, first_draw, stream};
     switch (s->type) {
     case LB_BB: {
         double al = s->hp[0], be = s->hp[1], h = I(0), t = I(1);

@@ -219,3 +219,50 @@ def test_loom_mix(tmp_path, infer_on_oracle, oracle_abi):  # noqa: F811
     proc = subprocess.run([exe, paths["config"], paths["rows"], first["model"], first["groups"], first["assign"],
                            out["model"], out["groups"], out["assign"]], capture_output=True, timeout=600)
     assert proc.returncode != 0 and b"zero diversity" in proc.stderr                 # src/loom.cc:569
+
+
+def test_loom_generate_then_mix(tmp_path, oracle_abi):
+    """loom.generate's two steps through the processes (src/generate.cc, src/mix.cc): a dataset synthesised from a model
+    -- rows, model, groups, assignments on disk -- whose every dumped statistic recomputes from the rows it wrote, then
+    mixed; the config's row count and density are honoured"""
+    import subprocess
+    from test_query_server import build_on_oracle
+    from test_z_loom_infer import TYPES, check_outputs
+
+    class Factory:
+        @staticmethod
+        def mktemp(name):
+            d = tmp_path / name
+            d.mkdir(exist_ok=True)
+            return d
+    gen = build_on_oracle(Factory, "loom_generate.cc", "loom_generate_oracle")
+    mix = build_on_oracle(Factory, "loom_mix.cc", "loom_mix_oracle")
+    model, _, _ = synth.generate(10, TYPES, density=1.0, seed=2)
+    pbio.ModelFile.create(model, GRIDS).write(tmp_path / "init.pb.gz")
+    c = pbio.config_defaults()
+    c.seed, c.generate_row_count, c.generate_density, c.generate_sample_skip = 21, 250, 0.6, 2
+    c.kind_iterations, c.kind_empty_kind_count, c.hyper_run = 2, 2, 1
+    pbio.config_write(tmp_path / "config.pb.gz", c)
+    out = {"model": str(tmp_path / "gen.model.pb.gz"), "groups": str(tmp_path / "gen.groups"),
+           "assign": str(tmp_path / "gen.assign.pbs.gz")}
+    rows_path = tmp_path / "rows.pbs.gz"
+    proc = subprocess.run([gen, str(tmp_path / "config.pb.gz"), str(tmp_path / "init.pb.gz"), str(rows_path),
+                           out["model"], out["groups"], out["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr.decode()
+    mf = pbio.ModelFile.read(out["model"])
+    rows = pbio.rows_read(rows_path, mf)
+    assert rows.n_rows == 250 and rows.rowids.tolist() == list(range(250)) and not rows.row_has_tare.any()
+    cat8, wide, mask = rows.to_columns(mf)
+    block = RowBlock(250, cat8, wide, mask)
+    assert abs(block.observed().mean() - 0.6) < 0.03
+    check_outputs(oracle_abi, block, rows.rowids, out)
+    mixed = {"model": str(tmp_path / "mix.model.pb.gz"), "groups": str(tmp_path / "mix.groups"),
+             "assign": str(tmp_path / "mix.assign.pbs.gz")}
+    proc = subprocess.run([mix, str(tmp_path / "config.pb.gz"), str(rows_path), out["model"], out["groups"], out["assign"],
+                           mixed["model"], mixed["groups"], mixed["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr.decode()
+    check_outputs(oracle_abi, block, rows.rowids, mixed)
+    # --none discards the state, the rows are still written
+    proc = subprocess.run([gen, str(tmp_path / "config.pb.gz"), str(tmp_path / "init.pb.gz"), str(tmp_path / "rows2.pbs.gz"),
+                           "--none", "--none", "--none"], capture_output=True, timeout=600)
+    assert proc.returncode == 0 and pbio.stream_stats(tmp_path / "rows2.pbs.gz")[0] == 250

@@ -291,3 +291,30 @@ def test_fused_query_score_matches_the_two_kernel_path(oracle_abi, cuda_abi, mon
         monkeypatch.setenv("LB_QUERY_FUSED", "1")
         assert np.allclose(g.query_score(5, n_rows - 3), ragged, rtol=2e-6, atol=2e-6)
         monkeypatch.delenv("LB_QUERY_FUSED", raising=False)
+
+
+# ------------------------------------------------------------------------------------------ generate_rows on the device
+@pytest.mark.gpu
+def test_generate_rows_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
+    """lb_generate_rows against the oracle: the seating is float64 host code on both sides (identical), the value
+    chains use the same Philox counters and float64 samplers (a draw within rounding of a threshold may differ, and a
+    (group, feature) chain that differed once stays different), and the device's books balance on their own"""
+    import test_generate as tg
+    model, g = tg.generated(cuda_abi, n_rows=500, density=0.7, seed=3)
+    _, o = tg.generated(oracle_abi, n_rows=500, density=0.7, seed=3)
+    for k in range(model.n_kinds):
+        assert np.array_equal(g.get_assignments(k), o.get_assignments(k))
+        assert np.array_equal(g.get_groups(k)[0], o.get_groups(k)[0])
+    rg, ro = g.get_rows(), o.get_rows()
+    assert (rg.observed() == ro.observed()).mean() > 0.999
+    both = rg.observed() & ro.observed()
+    F8 = model.n8()
+    for f in range(model.n_features):
+        a = (rg.cat8[f] if f < F8 else rg.wide[f - F8])[both[f]]
+        b = (ro.cat8[f] if f < F8 else ro.wide[f - F8])[both[f]]
+        if model.features[f]["type"] == "nich":
+            a, b = a.copy().view(np.float32).astype(np.float64), b.copy().view(np.float32).astype(np.float64)
+            assert np.isclose(a, b, rtol=1e-4, atol=1e-4).mean() > 0.98, f
+        else:
+            assert (a == b).mean() > 0.98, (f, (a == b).mean())
+    tg.books_balance(cuda_abi, model, g)
