@@ -318,3 +318,33 @@ def test_generate_rows_matches_oracle_on_the_gpu(oracle_abi, cuda_abi):
         else:
             assert (a == b).mean() > 0.98, (f, (a == b).mean())
     tg.books_balance(cuda_abi, model, g)
+
+
+@pytest.mark.gpu
+def test_loom_generate_and_loom_mix_on_the_gpu(tmp_path, oracle_abi):
+    """the product binaries: a dataset synthesised on the device and mixed, every dumped statistic recomputed by the oracle"""
+    import __graft_entry__
+    __graft_entry__.build()
+    from loom_b200 import RowBlock, pbio, synth
+    from test_pbio import GRIDS
+    from test_z_loom_infer import TYPES, check_outputs
+    model, _, _ = synth.generate(10, TYPES, density=1.0, seed=2)
+    pbio.ModelFile.create(model, GRIDS).write(tmp_path / "init.pb.gz")
+    c = pbio.config_defaults()
+    c.seed, c.generate_row_count, c.generate_density, c.generate_sample_skip = 21, 300, 0.6, 2
+    c.kind_iterations, c.kind_empty_kind_count, c.hyper_run = 2, 2, 1
+    pbio.config_write(tmp_path / "config.pb.gz", c)
+    out = {"model": str(tmp_path / "gen.model.pb.gz"), "groups": str(tmp_path / "gen.groups"), "assign": str(tmp_path / "gen.assign.pbs.gz")}
+    proc = subprocess.run([os.path.join(HOST, "loom_generate"), str(tmp_path / "config.pb.gz"), str(tmp_path / "init.pb.gz"),
+                           str(tmp_path / "rows.pbs.gz"), out["model"], out["groups"], out["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr.decode()
+    mf = pbio.ModelFile.read(out["model"])
+    rows = pbio.rows_read(tmp_path / "rows.pbs.gz", mf)
+    cat8, wide, mask = rows.to_columns(mf)
+    block = RowBlock(300, cat8, wide, mask)
+    check_outputs(oracle_abi, block, rows.rowids, out)
+    mixed = {"model": str(tmp_path / "mix.model.pb.gz"), "groups": str(tmp_path / "mix.groups"), "assign": str(tmp_path / "mix.assign.pbs.gz")}
+    proc = subprocess.run([os.path.join(HOST, "loom_mix"), str(tmp_path / "config.pb.gz"), str(tmp_path / "rows.pbs.gz"), out["model"],
+                           out["groups"], out["assign"], mixed["model"], mixed["groups"], mixed["assign"]], capture_output=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr.decode()
+    check_outputs(oracle_abi, block, rows.rowids, mixed)
