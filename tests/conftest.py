@@ -41,3 +41,24 @@ def has_gpu():
         return lib.cuInit(0) == 0 and lib.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
     except OSError:
         return False
+
+
+# The GPU tests of the last file, surest first: under `pytest -x` a failure in a late, never-run-before test must not
+# keep the earlier ones from reporting.
+_ZZ_ORDER = ["test_query_sample_matches_oracle_on_the_gpu", "test_loom_query_on_the_gpu", "test_score_error_per_feature_type",
+             "test_query_client_on_the_gpu", "test_masked_hyper_run_on_one_gpu",
+             "test_fused_query_score_matches_the_two_kernel_path", "test_differ_on_the_gpu",
+             "test_cuda_reproduces_query_and_differ_fixture", "test_loom_tare_and_loom_sparsify_on_the_gpu",
+             "test_generate_rows_matches_oracle_on_the_gpu", "test_loom_generate_and_loom_mix_on_the_gpu",
+             "test_score_from_counts_variant_replays_on_the_oracle", "test_row_sharded_accumulate_nccl",
+             "test_feature_sharded_hyper_nccl"]
+
+
+def pytest_collection_modifyitems(config, items):
+    def key(indexed):
+        i, item = indexed
+        if item.fspath.basename == "test_zz_query_gpu.py":
+            name = item.originalname if hasattr(item, "originalname") and item.originalname else item.name
+            return (1, _ZZ_ORDER.index(name) if name in _ZZ_ORDER else len(_ZZ_ORDER), i)
+        return (0, 0, i)
+    items[:] = [item for _, item in sorted(enumerate(items), key=key)]
