@@ -645,6 +645,9 @@ def main():
         ab = {"default": measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120)}
         ab["from_counts"] = (measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120, env={"LOOM_B200_LIB": variant})
                              if os.path.exists(variant) else {"error": "variant library not built (make -C loom_b200/csrc variants)"})
+        # and the product library with compact tables: column capacity starting at 64 instead of 256 (a quarter of the
+        # table footprint and of the per-chain shared memory; kinds that outgrow it re-stride on demand)
+        ab["default_gcap64"] = measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120, env={"LB_INITIAL_GCAP": "64"})
         aux["k3_variant_score_from_counts"] = ab
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
