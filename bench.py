@@ -197,7 +197,7 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
 
 
 _BENCH_START = time.time()
-AUX_BUDGET_S = 240.0        # the auxiliary experiments stop being started once the whole run is this old
+AUX_BUDGET_S = 270.0        # the auxiliary experiments stop being started once the whole run is this old
 
 
 def measure_in_subprocess(script, script_args, timeout=60, env=None):
@@ -208,7 +208,6 @@ def measure_in_subprocess(script, script_args, timeout=60, env=None):
     left = AUX_BUDGET_S - (time.time() - _BENCH_START)
     if left < 15:
         return {"skipped": "time budget of the default run (%.0f s) used up" % AUX_BUDGET_S}
-    timeout = min(timeout, left)
     try:
         proc = subprocess.run(cmd, capture_output=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     except subprocess.TimeoutExpired:
@@ -642,12 +641,12 @@ def main():
         # experiment for the next round: the sweep scoring BB / DD / DPD cells from the count rows
         # instead of the cached scorer rows -- the product library and the variant on the same reduced workload
         variant = os.path.join(REPO, "loom_b200", "csrc", "libloomb200_counts.so")
-        ab = {"default": measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120)}
-        ab["from_counts"] = (measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120, env={"LOOM_B200_LIB": variant})
+        ab = {"default": measure_in_subprocess("sweep_variant_bench.py", [168, 50000], timeout=120)}
+        ab["from_counts"] = (measure_in_subprocess("sweep_variant_bench.py", [168, 50000], timeout=120, env={"LOOM_B200_LIB": variant})
                              if os.path.exists(variant) else {"error": "variant library not built (make -C loom_b200/csrc variants)"})
         # and the product library with compact tables: column capacity starting at 64 instead of 256 (a quarter of the
         # table footprint and of the per-chain shared memory; kinds that outgrow it re-stride on demand)
-        ab["default_gcap64"] = measure_in_subprocess("sweep_variant_bench.py", [336, 50000], timeout=120, env={"LB_INITIAL_GCAP": "64"})
+        ab["default_gcap64"] = measure_in_subprocess("sweep_variant_bench.py", [168, 50000], timeout=120, env={"LB_INITIAL_GCAP": "64"})
         aux["k3_variant_score_from_counts"] = ab
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
