@@ -157,6 +157,9 @@ int lbio_rows_read_open(const char *path, lbio_model *m, uint64_t seed, int32_t 
 int lbio_model_adopt_dictionaries(lbio_model *dst, const lbio_model *src, uint64_t seed);
 /* InFile::stream_stats (src/protobuf_stream.hpp:156-184) */
 int lbio_stream_stats(const char *path, uint64_t *message_count, uint32_t *max_message_size);
+/* shuffle_stream (src/shuffle.hpp:38-86): a seeded permutation of the messages of a stream file, produced in chunks
+ * of at most target_mem_bytes (the result does not depend on the chunk size).  What `loom_shuffle` runs. */
+int lbio_shuffle_stream(const char *messages_in, const char *shuffled_out, uint64_t seed, double target_mem_bytes);
 /* the inverse, for tests / generators: rows as Row messages, dense rows as diff{pos = row, neg = NONE} */
 int lbio_rows_write(const char *path, const lbio_model *m, const lbio_row_block *rows);
 /* The same block by block (Differ::compress_rows streams, src/differ.cc:166-181).  tare_values [F] (may be NULL): the

@@ -1069,6 +1069,53 @@ extern "C" int lbio_stream_stats(const char *path, uint64_t *message_count, uint
     return 0;
 }
 
+// shuffle_stream (src/shuffle.hpp:38-86): message j of the input goes to position index[j] of the output, index a
+// seeded permutation; the output is produced in chunks of at most target_mem_bytes, one pass over the input each,
+// so the result does not depend on the chunk size.  (The permutation comes from SplitMix64 + Fisher-Yates, not from
+// the reference's std::shuffle(rng_t): same law, different draws.)
+extern "C" int lbio_shuffle_stream(const char *messages_in, const char *shuffled_out, uint64_t seed, double target_mem_bytes) {
+    if (std::string(messages_in) == std::string(shuffled_out)) return fail("cannot shuffle file in-place: %s", messages_in);
+    if (std::string(messages_in) == "-" || std::string(messages_in) == "-.gz") return fail("shuffle input is not a file: %s", messages_in);
+    if (!(target_mem_bytes > 0)) return fail("expected 0 < target_mem_bytes");
+    uint64_t message_count = 0;
+    uint32_t max_message_size = 0;
+    if (lbio_stream_stats(messages_in, &message_count, &max_message_size)) return 1;
+    if (message_count > 0xFFFFFFFFull) return fail("too many messages to shuffle: %llu", (unsigned long long)message_count);
+    const double index_bytes = 4.0 * (double)message_count;
+    const double target = std::max(1.0, std::min((double)message_count, (target_mem_bytes - index_bytes) / std::max<uint32_t>(max_message_size, 1)));
+    const size_t chunk_size = (size_t)std::llround(target);
+    std::vector<uint32_t> index(message_count);
+    for (size_t i = 0; i < message_count; ++i) index[i] = (uint32_t)i;
+    uint64_t state = seed;
+    auto next = [&]() {
+        uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (size_t i = message_count; i > 1; --i) std::swap(index[i - 1], index[(size_t)(next() % i)]);
+    pbw::OutFile shuffled(shuffled_out);
+    if (!shuffled.is_open()) return fail("failed to open output file %s", shuffled_out);
+    std::vector<std::vector<uint8_t>> chunk;
+    std::vector<uint8_t> message;
+    for (size_t begin = 0; begin < message_count; begin += chunk_size) {
+        const size_t end = std::min(begin + chunk_size, (size_t)message_count);
+        chunk.assign(end - begin, std::vector<uint8_t>());
+        pbw::InFile messages(messages_in);
+        if (!messages.is_open()) return fail("failed to open input file %s", messages_in);
+        bool bad = false;
+        for (size_t j = 0; j < message_count; ++j) {
+            if (!messages.try_read_stream(message, bad)) return fail("failed to parse message from %s", messages_in);
+            const size_t i = index[j];
+            if (begin <= i && i < end) chunk[i - begin].swap(message);
+        }
+        for (const auto &m : chunk)
+            if (!shuffled.write_stream(m)) return fail("failed to write %s", shuffled_out);
+    }
+    if (!shuffled.close()) return fail("failed to write %s", shuffled_out);
+    return 0;
+}
+
 // One ProductValue from (feature, raw value) cells; sparsity chosen as ValueSchema::normalize_small does
 // (src/product_value.hpp:396-451: none / all / sparse below 10 % / dense).
 static void encode_value(Writer &w, uint32_t field, const lbio_model &m, const uint32_t *features, const uint32_t *values,

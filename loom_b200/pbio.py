@@ -156,6 +156,7 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_write": (C.c_int, [C.c_void_p, _P(LogEntry)]),
     "log_close": (None, [C.c_void_p]),
     "tares_read_open": (C.c_int, [_cs, _model, C.c_uint64, _u8p, _u32p, _i32p, _i32p]),
+    "shuffle_stream": (C.c_int, [_cs, _cs, C.c_uint64, C.c_double]),
     "rows_writer_open": (C.c_int, [_cs, _P(C.c_void_p)]),
     "rows_writer_write": (C.c_int, [C.c_void_p, _model, C.c_void_p, _u32p]),
     "rows_writer_close": (C.c_int, [C.c_void_p]),
@@ -523,3 +524,8 @@ def groups_write(path, model_file, featureids, counts, ints, flts, order=None):
 def mixture_path(groups_dir, kindid):
     """store::get_mixture_path (src/store.hpp:59-66)"""
     return os.path.join(groups_dir, "mixture.%d.pbs.gz" % kindid)
+
+
+def shuffle_stream(messages_in, shuffled_out, seed=0, target_mem_bytes=4e9):
+    """loom.runner.shuffle (loom/runner.py:178-194) without the process"""
+    _check(lib().lbio_shuffle_stream(_path(messages_in), _path(shuffled_out), seed, float(target_mem_bytes)))

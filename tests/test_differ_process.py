@@ -130,3 +130,32 @@ def test_errors(tare_on_oracle, sparsify_on_oracle, tmp_path):
     assert rc != 0 and "failed to open input file" in err
     rc, err = run([tare_on_oracle, "too", "few"])
     assert rc == 1 and "Usage: loom_tare SCHEMA_ROW_IN ROWS_IN TARES_OUT" in err
+
+
+# ------------------------------------------------------------------------------------------ loom_shuffle
+def test_shuffle_is_a_seeded_permutation_and_chunk_size_invariant(tmp_path):
+    """loom/test/test_shuffle.py:41-82 through the product binary (host I/O only, no device): the output is a
+    permutation of the input's messages, the same for any memory target, different for another seed"""
+    import os
+    from test_z_loom_infer import HOST
+    exe = os.path.join(HOST, "loom_shuffle")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", HOST, "loom_shuffle"], stdout=subprocess.DEVNULL)
+    model, rows = dataset(n_rows=300)
+    mf, rowids = write_files(tmp_path, model, rows)
+    outs = {}
+    for tag, seed, mem in (("a", 7, 4e9), ("b", 7, 5000), ("c", 7, 1), ("d", 8, 4e9)):
+        out = tmp_path / (tag + ".pbs.gz")
+        assert run([exe, tmp_path / "rows.pbs.gz", out, seed, mem]) == (0, "")
+        outs[tag] = pbio.rows_read(out, mf).rowids.tolist()
+    assert sorted(outs["a"]) == sorted(rowids.tolist()) and outs["a"] != rowids.tolist()
+    assert outs["a"] == outs["b"] == outs["c"]                    # one message per chunk at the smallest target
+    assert outs["d"] != outs["a"] and sorted(outs["d"]) == sorted(outs["a"])
+    rc, err = run([exe, tmp_path / "rows.pbs.gz", tmp_path / "rows.pbs.gz"])
+    assert rc != 0 and "cannot shuffle file in-place" in err       # src/shuffle.hpp:46-48
+    rc, err = run([exe, "-", tmp_path / "x.pbs"])
+    assert rc != 0 and "shuffle input is not a file" in err
+    out = tmp_path / "default.pbs.gz"                              # SEED and TARGET_MEM_BYTES are optional
+    assert run([exe, tmp_path / "rows.pbs.gz", out]) == (0, "") and pbio.stream_stats(out)[0] == 300
+    pbio.shuffle_stream(tmp_path / "rows.pbs.gz", tmp_path / "py.pbs.gz", seed=7)
+    assert pbio.rows_read(tmp_path / "py.pbs.gz", mf).rowids.tolist() == outs["a"]
