@@ -47,6 +47,7 @@ public:
             LOOM_B200_IO(lbio_config_read((sample_root + "/config.pb.gz").c_str(), &sample_config));
             LOOM_B200_IO(lbio_model_read((sample_root + "/model.pb.gz").c_str(), &l.model));
             LOOM_B200_IO(lbio_model_get(l.model, &l.view));
+            if (latents_.size() > 1) adopt_dictionary_order(l, latents_[0]->view);
             if (sample_config.cat_empty_group_count < 1) LOOM_B200_ERROR("expected 0 < empty_group_count");
             l.cross_cat.model_load(l.view.n_features, l.view.specs, l.view.aux, l.view.n_aux, l.view.n_kinds,
                                    l.view.featureid_to_kindid, l.view.kind_py, l.view.topology_py,
@@ -131,12 +132,55 @@ public:
 private:
     struct Latent {
         explicit Latent(int device) : cross_cat(device) {}
-        ~Latent() { lbio_model_free(model); }
+        ~Latent() {
+            lbio_model_free(model);
+            if (file_model) lbio_model_free(file_model);
+        }
         CrossCat cross_cat;
-        lbio_model *model = nullptr;
+        lbio_model *model = nullptr;          // the model the engine runs on (dictionaries in latent 0's order)
+        lbio_model *file_model = nullptr;     // the model as the sample's files have it, when the order differs
         lbio_model_view view;
+        std::vector<std::vector<int32_t>> dictionary_perm;   // per DPD feature: position in the files of the value at index i
         std::string groups_in;
     };
+
+    // Samples of one dataset see its rows in different (shuffled) orders (loom/tasks.py:228-233), so their
+    // DirichletProcessDiscrete dictionaries list the same values in different orders.  The latents share one decoded
+    // row block, so every latent is put into latent 0's order: betas and the groups' count rows are permuted at load.
+    static void adopt_dictionary_order(Latent &l, const lbio_model_view &v0) {
+        const lbio_model_view v = l.view;
+        if (v.n_dpd != v0.n_dpd || v.n_features != v0.n_features)
+            LOOM_B200_ERROR("samples disagree on the schema or on a DirichletProcessDiscrete dictionary");
+        bool differs = false;
+        std::vector<std::vector<int32_t>> perm((size_t)v.n_dpd);
+        for (int ord = 0; ord < v.n_dpd; ++ord) {
+            const int32_t a = v.dpd_offsets[ord], n = v.dpd_offsets[ord + 1] - a, a0 = v0.dpd_offsets[ord];
+            if (n != v0.dpd_offsets[ord + 1] - a0) LOOM_B200_ERROR("samples disagree on the schema or on a DirichletProcessDiscrete dictionary");
+            perm[ord].assign((size_t)n, -1);
+            for (int32_t i0 = 0; i0 < n; ++i0) {
+                for (int32_t i = 0; i < n; ++i)
+                    if (v.dpd_values[a + i] == v0.dpd_values[a0 + i0]) perm[ord][i0] = i;
+                if (perm[ord][i0] < 0) LOOM_B200_ERROR("samples disagree on the schema or on a DirichletProcessDiscrete dictionary");
+                differs = differs || perm[ord][i0] != i0;
+            }
+        }
+        if (!differs) return;
+        std::vector<float> aux(v.aux, v.aux + v.n_aux);
+        int ord = 0;
+        for (int f = 0; f < v.n_features; ++f) {
+            if (v.specs[f].type != LB_DPD) continue;
+            for (int32_t i0 = 0; i0 < v.specs[f].dim; ++i0) aux[v.specs[f].aux_off + i0] = v.aux[v.specs[f].aux_off + perm[ord][i0]];
+            ++ord;
+        }
+        lbio_model *canonical = nullptr;
+        LOOM_B200_IO(lbio_model_create(v.n_features, v.specs, aux.data(), v.n_aux, v.n_kinds, v.featureid_to_kindid, v.kind_py,
+                                       v.topology_py, v.has_hyper_prior ? &v.hyper_prior : nullptr, v0.dpd_offsets, v0.dpd_values,
+                                       &canonical));
+        l.file_model = l.model;
+        l.model = canonical;
+        l.dictionary_perm = perm;
+        LOOM_B200_IO(lbio_model_get(l.model, &l.view));
+    }
 
     // a block of rows in the CSR form lb_set_rows_diff takes
     struct Rows {
@@ -234,7 +278,25 @@ private:
                 if ((int)l.view.featureid_to_kindid[f] == k) fids.push_back((uint32_t)f);
             const std::string path = l.groups_in + "/mixture." + std::to_string(k) + ".pbs.gz";
             lbio_group_block g;
-            LOOM_B200_IO(lbio_groups_read(path.c_str(), l.model, fids.data(), (int32_t)fids.size(), &g));
+            LOOM_B200_IO(lbio_groups_read(path.c_str(), l.file_model ? l.file_model : l.model, fids.data(), (int32_t)fids.size(), &g));
+            if (l.file_model) {     // count rows of the DPD features into latent 0's dictionary order
+                std::vector<uint32_t> rows;
+                size_t first_row = 0;
+                for (uint32_t f : fids) {
+                    const lb_feature_spec &spec = l.view.specs[f];
+                    const size_t n_rows = spec.type == LB_BB || spec.type == LB_GP ? 2 : spec.type == LB_NICH ? 1 : (size_t)spec.dim + 1;
+                    if (spec.type == LB_DPD) {
+                        int ord = 0;
+                        for (uint32_t q = 0; q < f; ++q) ord += l.view.specs[q].type == LB_DPD;
+                        const size_t G = (size_t)g.n_groups;
+                        rows.assign(g.ints + first_row * G, g.ints + (first_row + (size_t)spec.dim) * G);
+                        for (int32_t i0 = 0; i0 < spec.dim; ++i0)
+                            std::copy(rows.begin() + (size_t)l.dictionary_perm[ord][i0] * G,
+                                      rows.begin() + ((size_t)l.dictionary_perm[ord][i0] + 1) * G, g.ints + (first_row + (size_t)i0) * G);
+                    }
+                    first_row += n_rows;
+                }
+            }
             LOOM_B200_CHECK(LB_NAME(set_groups)(l.cross_cat.handle(), k, g.n_groups, g.counts, g.ints, g.flts));
             lbio_groups_free(&g);
         }

@@ -1,6 +1,6 @@
 """The processes chained the way loom.tasks chains them (ingest -> infer -> query), all built against the oracle's lo_ ABI:
-loom_tare -> loom_sparsify -> loom_infer (x3 seeds, init models with EMPTY DPD dictionaries, the tares file) -> a store
--> loom_query.  The data has a DPD column whose dominant raw value ends up in the tare row: that value is in no row's
+loom_tare -> loom_sparsify -> loom_shuffle -> loom_infer (x3 seeds, init models with EMPTY DPD dictionaries, the tares
+file) -> a store -> loom_query.  The data has a DPD column whose dominant raw value ends up in the tare row: that value is in no row's
 pos, so it has to enter the dictionary from the tares file (lbio_tares_read_open)."""
 import shutil
 
@@ -34,7 +34,7 @@ def raw_dataset(n_rows=300, seed=5):
     return model, block, dpd, raws
 
 
-def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_on_oracle, query_on_oracle):  # noqa: F811
+def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_on_oracle, query_on_oracle, oracle_abi):  # noqa: F811
     d = tmp_path
     model, block, dpd, raws = raw_dataset()
     writer = pbio.ModelFile.create(model, None, [raws[f] for f in dpd])
@@ -62,7 +62,11 @@ def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_
         c = pbio.config_defaults()
         c.seed, c.extra_passes, c.kind_iterations, c.hyper_run, c.small_data_size = 40, 1.5, 0, 1, 50.0
         pbio.config_write(d / "config.pb.gz", c)
-        paths = {"config": str(d / "config.pb.gz"), "rows": str(d / "diffs.pbs.gz"), "tares": str(d / "tares.pbs.gz"),
+        # loom.tasks.infer_one shuffles the diffs with the sample's seed first (loom/tasks.py:228-233)
+        import os
+        shuffle_exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "loom_b200", "host", "loom_shuffle")
+        assert run_cmd([shuffle_exe, d / "diffs.pbs.gz", d / ("shuffled.%d.pbs.gz" % s), s]) == (0, "")
+        paths = {"config": str(d / "config.pb.gz"), "rows": str(d / ("shuffled.%d.pbs.gz" % s)), "tares": str(d / "tares.pbs.gz"),
                  "model_in": str(d / "init.pb.gz")}
         out = run_infer(infer_on_oracle, paths, d, tag="s%d" % s)
         sd = root / "samples" / ("sample.%d" % s)
@@ -120,6 +124,46 @@ def test_ingest_infer_query(tmp_path, tare_on_oracle, sparsify_on_oracle, infer_
     assert all(np.isfinite(scores))
     for i in range(5):
         assert scores[2 * i] == pytest.approx(scores[2 * i + 1], abs=1e-5)
+    # ... and equals the log-mean over the samples computed here, every sample with its OWN dictionary order (the samples
+    # saw the rows in different orders, so the orders differ and the server has to line them up)
+    from loom_b200 import Engine
+    orders, per_sample = set(), []
+    F8 = model.n8()
+    obs = block.observed()
+    for s_ in range(N_SAMPLES):
+        sd = root / "samples" / ("sample.%d" % s_)
+        mf = pbio.ModelFile.read(sd / "model.pb.gz")
+        sample_model = mf.model()
+        dicts = [x.tolist() for x in mf.dpd_values()]
+        orders.add(tuple(map(tuple, dicts)))
+        table = []
+        for r in range(5):
+            row = [None] * model.n_features
+            for f in range(model.n_features):
+                if not obs[f, r]:
+                    continue
+                t = model.features[f]["type"]
+                if f < F8:
+                    row[f] = int(block.cat8[f, r])
+                elif t == "nich":
+                    row[f] = float(block.wide[f - F8, r:r + 1].view(np.float32)[0])
+                elif t == "dpd":
+                    row[f] = dicts[dpd.index(f)].index(raws[f][int(block.wide[f - F8, r])])
+                else:
+                    row[f] = int(block.wide[f - F8, r])
+            table.append(row)
+        e = Engine(oracle_abi)
+        e.set_model(sample_model)
+        e.set_rows(RowBlock.from_table(sample_model, table))
+        for k in range(sample_model.n_kinds):
+            counts, ints, flts = pbio.groups_read(pbio.mixture_path(sd / "groups", k), mf, sample_model.kind_features(k))
+            e.set_groups(k, len(counts), counts, ints, flts)
+        per_sample.append(e.query_score().astype(np.float64))
+    assert len(orders) > 1                                                     # the dictionaries really are ordered differently
+    per_sample = np.stack(per_sample)
+    m = per_sample.max(axis=0)
+    want = m + np.log(np.exp(per_sample - m).sum(axis=0)) - np.log(N_SAMPLES)
+    assert np.allclose([scores[2 * i] for i in range(5)], want, rtol=1e-5, atol=1e-5)
     drawn = [value_cells(model, x.pos)[dpd[0]] for x in responses[10].sample.samples]
     assert set(drawn) <= set(raws[dpd[0]]) | {0xFFFFFFFF}                      # raw values (or distributions' OTHER)
     assert np.mean([v == 9 for v in drawn]) > 0.5                              # the dominant value dominates
