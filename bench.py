@@ -35,6 +35,11 @@ samples : the exact Gibbs chain of one kind is sequential, so one chain keeps on
           as many chains in parallel as the host cores allow.
 N > 1  : chains do not communicate, so every rank runs its own set of chains on its
           GPU -- "replicas only", "scaling": "weak" (DESIGN.md).
+roofline_aux (N = 1, rank 0) also carries, each measured in a process of its own (scratch/*_bench.py) so that it
+          cannot disturb the headline and only started while the run is younger than AUX_BUDGET_S: the query path
+          (`query`, `query_fused`), the tare / sparsify passes (`differ`), the per-feature-type score error against the
+          float64 oracle (`score_error`), and A/Bs of the sweep kernel for the next round
+          (`k3_variant_score_from_counts`: product library, -DLB_SCORE_FROM_COUNTS build, compact tables).
 --impl reference times the restated reference (oracle/, float64 C, OpenMP one
 thread per kind like src/cat_pipeline.cc:103-125) on the host cores, on a bounded
 row sample of the same workload.
