@@ -107,6 +107,26 @@ public:
         LOOM_B200_CHECK(LB_NAME(score_rows)(handle_, (int32_t)kindid, row_begin, row_end, out.data()));
         return out;
     }
+    // QueryServer::call(Score) for this sample (src/query_server.cc:189-231): log predictive of rows [row_begin, row_end)
+    std::vector<float> query_score(uint64_t row_begin, uint64_t row_end) const {
+        std::vector<float> out((size_t)(row_end - row_begin));
+        LOOM_B200_CHECK(LB_NAME(query_score)(handle_, row_begin, row_end, out.data()));
+        return out;
+    }
+    // ProductMixture::sample_value per kind (src/product_mixture.cc:637-649): n_samples joint draws of `to_sample`
+    // (ascending feature ids) given the loaded row `row`; values [n_samples][to_sample.size()] as raw cells
+    std::vector<uint32_t> query_sample(uint64_t row, const std::vector<uint32_t> &to_sample, uint32_t n_samples, uint64_t seed,
+                                       uint64_t draw_offset = 0) const {
+        std::vector<uint32_t> out((size_t)n_samples * to_sample.size());
+        LOOM_B200_CHECK(LB_NAME(query_sample)(handle_, row, to_sample.data(), (int32_t)to_sample.size(), n_samples, seed,
+                                              draw_offset, out.data(), nullptr));
+        return out;
+    }
+    // generate_rows (src/generate.hpp:36-93): the engine then holds the synthesised rows, every row assigned
+    void generate_rows(uint64_t row_count, float density, uint64_t seed) {
+        LOOM_B200_CHECK(LB_NAME(generate_rows)(handle_, row_count, density, seed));
+        row_count_ = row_count;
+    }
     lb_handle handle() const { return handle_; }
     uint64_t row_count() const { return row_count_; }
 

@@ -2,6 +2,13 @@
 #include <cstring>
 #include "../loom_b200/host/loom_b200.hpp"
 
+// compiled, never called: the query / generate entry points of the shell type-check against the ABI
+[[maybe_unused]] static void api_surface(loom::b200::CrossCat &cc) {
+    (void)cc.query_score(0, cc.row_count());
+    (void)cc.query_sample(0, std::vector<uint32_t>{0}, 4, 1);
+    cc.generate_rows(10, 0.5f, 2);
+}
+
 int main(int argc, char **argv) {
     if (argc < 2 || std::strcmp(argv[1], "run") != 0) return 0;  // link check only
     using namespace loom::b200;
