@@ -448,9 +448,19 @@ def rows_read(path, model_file, first_row=0, max_rows=0, n_threads=0, open_dicti
         lib().lbio_rows_free(C.byref(v))
 
 
-def rows_write(path, model_file, rows):
+def rows_write(path, model_file, rows, tare_values=None):
+    """tare_values: the tare row's cell values, written as the values of every neg part (what loom's sparsify writes)"""
     view = rows._view()
-    _check(lib().lbio_rows_write(_path(path), model_file.h, C.byref(view)))
+    if tare_values is None:
+        _check(lib().lbio_rows_write(_path(path), model_file.h, C.byref(view)))
+        return
+    tv = np.ascontiguousarray(tare_values, np.uint32)
+    w = C.c_void_p()
+    _check(lib().lbio_rows_writer_open(_path(path), C.byref(w)))
+    status = lib().lbio_rows_writer_write(w, model_file.h, C.byref(view), _abi.ptr(tv, _u32p))
+    closed = lib().lbio_rows_writer_close(w)
+    _check(status)
+    _check(closed)
 
 
 def stream_stats(path):

@@ -151,3 +151,45 @@ def infer(rows_in, model_in, samples_out, config=None, tares_in=None, seeds=None
         _dump_sample(e, files[c], rows.rowids, (0, R, None if orders is None else orders[c]), samples_out[c],
                      files[c].hyper_prior(), files[c].dpd_values())
     return engines
+
+
+# ---------------------------------------------------------------------------------------------
+# The ingest passes in process (loom.runner.tare / sparsify / shuffle, loom/runner.py:120-194): same arguments as the
+# `loom_tare` / `loom_sparsify` / `loom_shuffle` processes, on the device engine through the C ABI.
+def _schema_engine(schema_row_in, abi, device):
+    mf = pbio.ModelFile.from_schema_row(schema_row_in)
+    e = Engine(abi or _abi.load_cuda(), device=device)
+    e.set_model(mf.model())
+    return mf, e
+
+
+def tare(schema_row_in, rows_in, tares_out, abi=None, device=0):
+    """loom.runner.tare: the tare row of a dataset (the mode of every boolean / count column that more than half of
+    the rows hold), written to `tares_out` -- or an empty file when no column qualifies"""
+    mf, e = _schema_engine(schema_row_in, abi, device)
+    rows = pbio.rows_read(rows_in, mf)
+    if rows.row_has_tare.any():
+        raise _abi.LoomError("row is already sparsified")
+    rows.upload(e)
+    tare_observed, tare_values = e.make_tare()
+    pbio.tares_write(tares_out, mf, tare_observed, tare_values)
+    return tare_observed, tare_values
+
+
+def sparsify(schema_row_in, tares_in, rows_in, rows_out, abi=None, device=0):
+    """loom.runner.sparsify: every row as Diff{pos, neg, tares: [0]} against the tare row of `tares_in`"""
+    if str(rows_in) == str(rows_out):
+        raise _abi.LoomError("in-place sparsify is not supported")
+    mf, e = _schema_engine(schema_row_in, abi, device)
+    tare_observed, tare_values, _ = pbio.tares_read(tares_in, mf)
+    rows = pbio.rows_read(rows_in, mf)
+    rows.upload(e)
+    d = e.sparsify(tare_observed, tare_values)
+    tared = np.full(rows.n_rows, 1 if tare_observed.any() else 0, np.uint8)
+    out = pbio.Rows(rows.rowids, tared, d["pos_ptr"], d["pos_feature"], d["pos_value"], d["neg_ptr"], d["neg_feature"])
+    pbio.rows_write(rows_out, mf, out, tare_values=tare_values)
+
+
+def shuffle(rows_in, rows_out, seed=0, target_mem_bytes=4e9):
+    """loom.runner.shuffle"""
+    pbio.shuffle_stream(rows_in, rows_out, seed, target_mem_bytes)

@@ -159,3 +159,21 @@ def test_shuffle_is_a_seeded_permutation_and_chunk_size_invariant(tmp_path):
     assert run([exe, tmp_path / "rows.pbs.gz", out]) == (0, "") and pbio.stream_stats(out)[0] == 300
     pbio.shuffle_stream(tmp_path / "rows.pbs.gz", tmp_path / "py.pbs.gz", seed=7)
     assert pbio.rows_read(tmp_path / "py.pbs.gz", mf).rowids.tolist() == outs["a"]
+
+
+def test_tasks_mirror_equals_the_processes(tare_on_oracle, sparsify_on_oracle, oracle_abi, tmp_path):
+    """loom_b200.tasks.tare / sparsify / shuffle (loom.runner's functions, in process) write the files the processes write"""
+    from loom_b200 import tasks
+    d = tmp_path
+    model, rows, mf = passes_case(tare_on_oracle, sparsify_on_oracle, d)
+    tasks.tare(d / "schema.pb.gz", d / "rows.pbs.gz", d / "py.tares.pbs.gz", abi=oracle_abi)
+    tasks.sparsify(d / "schema.pb.gz", d / "py.tares.pbs.gz", d / "rows.pbs.gz", d / "py.diffs.pbs.gz", abi=oracle_abi)
+    import gzip
+    for name in ("tares.pbs.gz", "diffs.pbs.gz"):
+        assert gzip.open(d / ("py." + name)).read() == gzip.open(d / name).read(), name     # byte for byte
+    tasks.shuffle(d / "diffs.pbs.gz", d / "py.shuffled.pbs.gz", seed=3)
+    assert sorted(pbio.rows_read(d / "py.shuffled.pbs.gz", mf).rowids.tolist()) == sorted(pbio.rows_read(d / "diffs.pbs.gz", mf).rowids.tolist())
+    with pytest.raises(Exception, match="already sparsified"):
+        tasks.tare(d / "schema.pb.gz", d / "diffs.pbs.gz", d / "x.pbs.gz", abi=oracle_abi)
+    with pytest.raises(Exception, match="in-place"):
+        tasks.sparsify(d / "schema.pb.gz", d / "tares.pbs.gz", d / "rows.pbs.gz", d / "rows.pbs.gz", abi=oracle_abi)
