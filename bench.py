@@ -652,6 +652,8 @@ def main():
         # and the product library with compact tables: column capacity starting at 64 instead of 256 (a quarter of the
         # table footprint and of the per-chain shared memory; kinds that outgrow it re-stride on demand)
         ab["default_gcap64"] = measure_in_subprocess("sweep_variant_bench.py", [168, 50000], timeout=120, env={"LB_INITIAL_GCAP": "64"})
+        # and with a row order per chain (lb_cat_sweep_streams: loom's per-sample shuffles) instead of the shared one
+        ab["default_streams"] = measure_in_subprocess("sweep_variant_bench.py", [168, 50000, "streams"], timeout=120)
         aux["k3_variant_score_from_counts"] = ab
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
