@@ -642,7 +642,7 @@ def main():
                                 "frac": d[part]["achieved_gb_s"] / peak, "bound": "hbm"})
         # the same with K1 reducing scores to log-sum-exp in registers (scores not materialised)
         aux["query_fused"] = measure_in_subprocess("query_bench.py", [R, 1000], env={"LB_QUERY_FUSED": "1"})
-        aux["score_error"] = measure_in_subprocess("score_error.py", [20000])     # parity check 2, per feature type
+        aux["score_error"] = measure_in_subprocess("score_error.py", [8000])     # parity check 2, per feature type
         # experiment for the next round: the sweep scoring BB / DD / DPD cells from the count rows
         # instead of the cached scorer rows -- the product library and the variant on the same reduced workload
         variant = os.path.join(REPO, "loom_b200", "csrc", "libloomb200_counts.so")
