@@ -36,7 +36,17 @@ for e in engines: e.sync()
 engines[0].timer_start()
 step(1)
 ms = engines[0].timer_stop()
+# the phases of a step on their own (ADD-only and REMOVE+ADD-pair rates reported separately)
+phases = {}
+if not streams:
+    seeds = np.arange(n, dtype=np.uint64) * 1000 + 2
+    for name, acts, per_row in (("add_only", first[:R], 1), ("remove_add_pairs", first[R:], 2), ("remove_only", drain, 1)):
+        for e in engines: e.sync()
+        engines[0].timer_start()
+        cat_sweep_multi(engines, acts, seeds)
+        t = engines[0].timer_stop()
+        phases[name] = {"ms": t, "cells_per_s": n * per_row * rows.n_cells() / (t * 1e-3)}
 # the state after the step is the empty one for every chain; a cheap invariant that the variant kept the books
 empty = all(int(e.get_groups(0)[0].sum()) == 0 for e in engines[:4])
 print(json.dumps({"lib": os.path.basename(cuda.path), "row_order": "per chain" if streams else "shared", "chains": n, "rows": R, "ms_per_step": ms,
-                  "cells_per_s": n * cells / (ms * 1e-3), "drained_to_empty": empty}))
+                  "cells_per_s": n * cells / (ms * 1e-3), "phases": phases, "drained_to_empty": empty}))
