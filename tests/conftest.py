@@ -50,7 +50,7 @@ _ZZ_ORDER = ["test_query_sample_matches_oracle_on_the_gpu", "test_loom_query_on_
              "test_fused_query_score_matches_the_two_kernel_path", "test_differ_on_the_gpu",
              "test_cuda_reproduces_query_and_differ_fixture", "test_loom_tare_and_loom_sparsify_on_the_gpu",
              "test_generate_rows_matches_oracle_on_the_gpu", "test_loom_generate_and_loom_mix_on_the_gpu",
-             "test_score_from_counts_variant_replays_on_the_oracle", "test_row_sharded_accumulate_nccl",
+             "test_row_sharded_accumulate_nccl",
              "test_feature_sharded_hyper_nccl"]
 
 

@@ -67,7 +67,10 @@ def assert_same_state(o, g, model, flt_rtol=1e-7):
         assert np.array_equal(o.get_assignments(k), g.get_assignments(k)), k
 
 
-def test_sweep_matches_oracle_by_replay(oracle_abi, cuda_abi):
+@pytest.mark.parametrize("kernel", ["spec", "classic"])
+def test_sweep_matches_oracle_by_replay(oracle_abi, cuda_abi, monkeypatch, kernel):
+    """both sweep kernels: K3s (scores gathered one ADD ahead, touched column recomputed) and the classic form"""
+    monkeypatch.setenv("LB_SWEEP_KERNEL", kernel)
     model, rows, _ = mixed()
     o, g = both(oracle_abi, cuda_abi, model, rows)
     R = rows.n_rows
@@ -143,13 +146,16 @@ def test_sweep_grows_tables_and_renumbers_ids(oracle_abi, cuda_abi, monkeypatch)
     assert_same_state(o, g, model, flt_rtol=1e-6)
 
 
-@pytest.mark.parametrize("warps", [1, 8])
+@pytest.mark.parametrize("warps", ["spec", 1, 8])
 def test_multi_chain_sweep_grows_tables(cuda_abi, monkeypatch, warps):
     """Table growth and id renumbering inside the many-chain launch: chains stop at different
     actions, the host grows their tables and relaunches only the unfinished (chain, kind) pairs;
     every chain must end where its own single-chain sweep ends."""
     monkeypatch.setenv("LB_INITIAL_GCAP", "64")
-    monkeypatch.setenv("LB_SWEEP_WARPS", str(warps))
+    if warps == "spec":
+        monkeypatch.setenv("LB_SWEEP_KERNEL", "spec")          # K3s: wide and narrow CTAs on two streams
+    else:
+        monkeypatch.setenv("LB_SWEEP_WARPS", str(warps))       # the classic kernel at that CTA width
     model, rows, _ = mixed(rows=1200, seed=4, alpha=60.0)
     R = rows.n_rows
     acts = np.concatenate([sweep_actions(R)] + [sweep_actions(R, add=True, remove=True)] * 6)

@@ -208,58 +208,6 @@ def test_query_client_on_the_gpu(tmp_path, infer_on_oracle):  # noqa: F811
         assert len(s.score_derivative(cond, [cond, typed_row(model, qs.some_rows(model, block, [2])[0])])) == 2
 
 
-# ------------------------------------------------------------------------------------------ build variant of the sweep kernel
-VARIANT_WORKER = r'''
-import os, sys
-REPO = {repo!r}
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests"))
-import numpy as np
-from loom_b200 import Engine, _abi, synth, sweep_actions, cat_sweep_multi
-import test_cuda_cat as t
-cuda = _abi.load_cuda()
-assert os.path.basename(cuda.path) == {lib!r}, cuda.path
-oracle = _abi.Abi(os.path.join(REPO, "oracle", "libloom_oracle.so"), "lo_")
-model, rows, _ = synth.generate(600, [("bb", 4), ("dd16", 3), ("dd256", 2), ("dpd5", 2), ("gp", 3), ("nich", 3)],
-                                density=0.6, seed=3)
-o, g = t.both(oracle, cuda, model, rows)
-acts = np.concatenate([sweep_actions(600), sweep_actions(600, add=True, remove=True)])
-picks, scores = g.cat_sweep(acts, seed=1, debug=True, debug_stride=64)
-bad, err = t.replay(oracle, o, acts, 1, picks, scores, 64)
-assert bad == 0 and err <= 1e-5, (bad, err)                 # every pick and every score vector of the sweep
-t.assert_same_state(o, g, model)                             # integer statistics bit for bit
-for k in range(model.n_kinds):                               # the scorer rows were rebuilt after the launch
-    a, b = g.score_rows(k).astype(np.float64), o.score_rows(k).astype(np.float64)
-    assert (np.abs(a - b) <= 1e-5 * np.maximum(1.0, np.abs(b))).all(), k
-assert abs(g.score_data() - o.score_data()) <= 1e-5 * abs(o.score_data())
-chains = []
-for seed in (1, 2, 3):
-    c = Engine(cuda); c.set_model(model); c.share_rows(g); chains.append(c)
-cat_sweep_multi(chains, acts, [1, 2, 3])
-for k in range(model.n_kinds):
-    assert np.array_equal(chains[0].get_assignments(k), g.get_assignments(k))
-    a, b = chains[0].score_rows(k), g.score_rows(k)
-    assert np.array_equal(a, b), k
-print("variant ok")
-'''
-
-
-@pytest.mark.gpu
-def test_score_from_counts_variant_replays_on_the_oracle(tmp_path):
-    """libloomb200_counts.so (-DLB_SCORE_FROM_COUNTS, an experiment measured beside the product: DESIGN.md 9, 1b) in a
-    process of its own: the sweep replays exactly on the oracle, leaves the same statistics, and the scorer rows it
-    does not maintain are rebuilt after the launch"""
-    import sys
-    import __graft_entry__
-    __graft_entry__.build()
-    repo = os.path.dirname(os.path.dirname(HOST))
-    lib = os.path.join(repo, "loom_b200", "csrc", "libloomb200_counts.so")
-    assert os.path.exists(lib)
-    script = tmp_path / "variant_worker.py"
-    script.write_text(VARIANT_WORKER.format(repo=repo, lib="libloomb200_counts.so"))
-    proc = subprocess.run([sys.executable, str(script)], capture_output=True, timeout=600, env=dict(os.environ, LOOM_B200_LIB=lib))
-    assert proc.returncode == 0 and b"variant ok" in proc.stdout, proc.stdout.decode()[-1000:] + proc.stderr.decode()[-3000:]
-
-
 # ------------------------------------------------------------------------------------------ fused Score (K1 without scores out)
 @pytest.mark.gpu
 def test_fused_query_score_matches_the_two_kernel_path(oracle_abi, cuda_abi, monkeypatch):
