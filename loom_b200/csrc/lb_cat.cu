@@ -677,65 +677,76 @@ int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *
     return 0;
 }
 
-// K3s launch: the (chain, kind) pairs of a sweep, most expensive first, split into kinds wide enough for an
-// 8-warp CTA (leader's stream) and narrow / featureless kinds that take one warp each, SP_CPB to a block
-// (second stream, concurrently).  Returns 1 when a pair does not fit this kernel (the caller falls back).
+// K3s launch: the (chain, kind) pairs of a sweep, most expensive first, in three width classes that run side by
+// side on three streams: kinds wide enough for 16 warps, for 8 warps, and narrow / featureless kinds that take one
+// warp each, SP_CPB to a block.  Returns 1 when a pair does not fit this kernel (the caller falls back).
 static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
                                 const std::vector<std::vector<int>> &kind_ids) {
     struct Cost { SweepPair p; size_t cost; };
-    std::vector<Cost> wide, narrow;
-    size_t smem_w = 0, smem_n = 0;
+    std::vector<Cost> cls[3];                      // 0 narrow (1 warp), 1 wide (8 warps), 2 wider (16 warps)
+    size_t smem[3] = {0, 0, 0};
+    const int warps_of[3] = {1, 8, LB_SPEC_WIDER};
+    const char *w16 = getenv("LB_SPEC_WIDE16");
+    const bool use16 = !w16 || atoi(w16) != 0;
     for (int c = 0; c < n; ++c)
         for (int kid : kind_ids[c]) {
             const KindHost &k = engines[c]->kinds[kid];
             const int nf = (int)k.fids.size();
-            const bool w = nf >= SP_WIDE_NF;
-            if (nf > SW_PF * 32 * (w ? 8 : 1)) return 1;
-            const size_t sm = (spec_smem_bytes(nf, k.Gcap, w ? 8 : 1) + 15) / 16 * 16;
-            (w ? smem_w : smem_n) = std::max(w ? smem_w : smem_n, sm);
-            (w ? wide : narrow).push_back(Cost{SweepPair{c, kid}, (size_t)(nf + 1) * (size_t)(k.G + 8)});
+            const int w = nf >= SP_WIDER_NF && use16 ? 2 : (nf >= SP_WIDE_NF ? 1 : 0);
+            if (nf > SW_PF * 32 * warps_of[w]) return 1;
+            smem[w] = std::max(smem[w], (spec_smem_bytes(nf, k.Gcap, warps_of[w]) + 15) / 16 * 16);
+            cls[w].push_back(Cost{SweepPair{c, kid}, (size_t)(nf + 1) * (size_t)(k.G + 8)});
         }
-    if (smem_w > 220 * 1024 || smem_n * SP_CPB > 220 * 1024) return 1;
+    if (smem[1] > 220 * 1024 || smem[2] > 220 * 1024 || smem[0] * SP_CPB > 220 * 1024) return 1;
     auto by_cost = [](const Cost &a, const Cost &b) { return a.cost > b.cost; };
-    std::stable_sort(wide.begin(), wide.end(), by_cost);
-    std::stable_sort(narrow.begin(), narrow.end(), by_cost);
-    // one upload: [chains][wide pairs][narrow pairs]
+    for (auto &v : cls) std::stable_sort(v.begin(), v.end(), by_cost);
+    // one upload: [chains][wider pairs][wide pairs][narrow pairs]
     const size_t cb = (sizeof(SweepChain) * (size_t)n + 15) / 16 * 16;
-    std::vector<unsigned char> host(cb + sizeof(SweepPair) * (wide.size() + narrow.size()) + 16);
+    const size_t n_pairs = cls[0].size() + cls[1].size() + cls[2].size();
+    std::vector<unsigned char> host(cb + sizeof(SweepPair) * n_pairs + 16);
     memcpy(host.data(), chains, sizeof(SweepChain) * (size_t)n);
     SweepPair *hp = (SweepPair *)(host.data() + cb);
-    for (size_t q = 0; q < wide.size(); ++q) hp[q] = wide[q].p;
-    for (size_t q = 0; q < narrow.size(); ++q) hp[wide.size() + q] = narrow[q].p;
+    size_t at = 0, first[3];
+    for (int w = 2; w >= 0; --w) { first[w] = at; for (const Cost &c : cls[w]) hp[at++] = c.p; }
     void *d = nullptr;
     LB_TRY(lb_upload_desc(leader, host.data(), host.size(), &d));
     const SweepChain *d_chains = (const SweepChain *)d;
-    const SweepPair *d_wide = (const SweepPair *)((unsigned char *)d + cb), *d_narrow = d_wide + wide.size();
+    const SweepPair *d_pairs = (const SweepPair *)((unsigned char *)d + cb);
     if (!leader->stream2) {
         LB_CUDA(cudaStreamCreateWithFlags(&leader->stream2, cudaStreamNonBlocking));
+        LB_CUDA(cudaStreamCreateWithFlags(&leader->stream3, cudaStreamNonBlocking));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_fork, cudaEventDisableTiming));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join, cudaEventDisableTiming));
+        LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join3, cudaEventDisableTiming));
     }
     // the opt-in is per device and cheap: set it at every launch (engines live on any device)
-    if (!wide.empty())
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    if (!narrow.empty())
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_n * SP_CPB)));
+    if (!cls[2].empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<LB_SPEC_WIDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[2]));
+    if (!cls[1].empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[1]));
+    if (!cls[0].empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem[0] * SP_CPB)));
     LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
-    if (!narrow.empty()) {
-        LB_CUDA(cudaEventRecord(leader->ev_fork, leader->stream));
-        LB_CUDA(cudaStreamWaitEvent(leader->stream2, leader->ev_fork, 0));
-        const unsigned nb = (unsigned)((narrow.size() + SP_CPB - 1) / SP_CPB);
-        k_cat_sweep_spec<1><<<nb, 32 * SP_CPB, smem_n * SP_CPB, leader->stream2>>>(d_chains, d_narrow, (int)narrow.size(), (int)smem_n);
+    LB_CUDA(cudaEventRecord(leader->ev_fork, leader->stream));
+    // the longest-running class goes first on the leader's stream; the others fork off it and join back
+    const int lead_cls = !cls[2].empty() ? 2 : (!cls[1].empty() ? 1 : 0);
+    cudaStream_t side[2] = {leader->stream2, leader->stream3};
+    cudaEvent_t joined[2] = {leader->ev_join, leader->ev_join3};
+    int n_side = 0;
+    for (int w = 2; w >= 0; --w) {
+        if (cls[w].empty()) continue;
+        cudaStream_t s = leader->stream;
+        if (w != lead_cls) { s = side[n_side]; LB_CUDA(cudaStreamWaitEvent(s, leader->ev_fork, 0)); }
+        const int np = (int)cls[w].size();
+        if (w == 2) k_cat_sweep_spec<LB_SPEC_WIDER><<<(unsigned)np, 32 * LB_SPEC_WIDER, smem[2], s>>>(d_chains, d_pairs + first[2], np, (int)smem[2]);
+        else if (w == 1) k_cat_sweep_spec<8><<<(unsigned)np, 256, smem[1], s>>>(d_chains, d_pairs + first[1], np, (int)smem[1]);
+        else k_cat_sweep_spec<1><<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
+                 d_chains, d_pairs + first[0], np, (int)smem[0]);
         LB_CUDA(cudaGetLastError());
-        LB_CUDA(cudaEventRecord(leader->ev_join, leader->stream2));
+        if (w != lead_cls) { LB_CUDA(cudaEventRecord(joined[n_side], s)); ++n_side; }
         leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
     }
-    if (!wide.empty()) {
-        k_cat_sweep_spec<8><<<(unsigned)wide.size(), 256, smem_w, leader->stream>>>(d_chains, d_wide, (int)wide.size(), (int)smem_w);
-        LB_CUDA(cudaGetLastError());
-        leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
-    }
-    if (!narrow.empty()) LB_CUDA(cudaStreamWaitEvent(leader->stream, leader->ev_join, 0));
+    for (int q = 0; q < n_side; ++q) LB_CUDA(cudaStreamWaitEvent(leader->stream, joined[q], 0));
     LB_CUDA(cudaEventRecord(leader->kev1, leader->stream));
     leader->kev_pending = true;
     return 0;

@@ -327,13 +327,17 @@ extern "C" void lb_destroy(lb_handle h) {
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
     lb_release_proposer(e);
     lb_release_differ(e);
+    lb_release_comm(e);
     dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
     if (e->d_score_aux) cudaFree(e->d_score_aux);
     if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
-    if (e->stream2) { cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
+    if (e->stream2) {
+        cudaStreamDestroy(e->stream2); cudaStreamDestroy(e->stream3);
+        cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_join3);
+    }
     cudaStreamDestroy(e->stream);
     delete e;
 }

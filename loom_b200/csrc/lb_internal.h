@@ -59,8 +59,8 @@ struct PackSrc {               // out[r] = g2p[assign[r]] narrowed to `width` by
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;                 // K3s: the narrow kinds of a sweep run beside the wide ones
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;   // K3s: the width classes of a sweep run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sm = 148;
 
@@ -111,6 +111,7 @@ struct Engine {
     double *d_prop_flts = nullptr;
     unsigned char *d_prop_packed = nullptr;   // [K][R] packed ids, 4 bytes per row reserved
     size_t prop_cap_ints = 0, prop_cap_flts = 0, prop_cap_packed = 0;
+    size_t prop_used_ints = 0, prop_used_flts = 0;   // elements of the slabs the current round uses (all-reduce extent)
     void *d_desc = nullptr;            // launch descriptor staging
     size_t d_desc_cap = 0;
     std::vector<int> prop_int_off, prop_flt_off;
@@ -128,6 +129,7 @@ struct Engine {
     bool kev_pending = false;
     unsigned long long *d_prof = nullptr;  // LB_PROFILE=1: per-kind, per-warp phase cycles of the sweep
     void *differ = nullptr;                // tare / sparsify state (lb_differ.cu)
+    void *comm = nullptr;                  // NCCL communicator + rank (lb_comm.cu)
 };
 
 // launch-family indices for launch_count
@@ -201,5 +203,9 @@ int lb_launch_score_data(Engine *e, double *out);
 void lb_release_differ(Engine *e);
 
 // structure kernels (lb_struct.cu)
+int lb_proposer_score_range(Engine *e, int f_lo, int f_hi, int F_pad);
+int lb_proposer_fetch_scores(Engine *e, float *out);
+// collectives (lb_comm.cu)
+void lb_release_comm(Engine *e);
 void lb_free_proposer(Engine *e);      // invalidate (buffers kept)
 void lb_release_proposer(Engine *e);   // free the buffers

@@ -63,42 +63,90 @@ struct PropKindDev {       // device view of one kind's proposer tables
     int pst, G;
 };
 
+// sums -> moments, once per proposal round and on EVERY rank (move_features reads these tables,
+// src/product_mixture.cc:886-915): NICH (sum x, sum x^2) -> (mean, count_times_variance); thread per (feature, kind, group)
+__global__ void k_prop_moments(const FeatDev *pfeats, const int32_t *nich_fids, int n_nich, const PropKindDev *pk, int K) {
+    const int kid = blockIdx.y;
+    const PropKindDev p = pk[kid];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_nich * p.G; idx += gridDim.x * blockDim.x) {
+        const FeatDev &f = pfeats[nich_fids[idx / p.G]];
+        const int g = idx % p.G;
+        const double n = (double)p.ints[(size_t)f.int_row * p.pst + g];
+        double *fl = p.flts + (size_t)f.flt_row * p.pst + g;
+        if (n == 0.0) { fl[0] = 0.0; fl[p.pst] = 0.0; }
+        else {
+            const double mean = fl[0] / n;
+            fl[p.pst] = fmax(fl[p.pst] - n * mean * mean, 0.0);
+            fl[0] = mean;
+        }
+    }
+}
+
+// lgamma of every Dirichlet concentration, once per proposal round: lga[aux_off + v] = lgamma(a_v); the totals
+// lgamma(A) sit in lgA[f].  K5 then evaluates lgamma(a + n) - lgamma(a) with ONE Stirling / product form per count.
+__global__ void k_prop_lgamma_table(const FeatDev *pfeats, int F, const float *aux, float *lga, float *lgA) {
+    const int fid = blockIdx.x;
+    const FeatDev &f = pfeats[fid];
+    if (f.type != LB_DD && f.type != LB_DPD) return;
+    for (int v = threadIdx.x; v < f.dim; v += blockDim.x)
+        lga[f.aux_off + v] = lgammaf(f.a_scale * aux[f.aux_off + v]);
+    if (threadIdx.x == 0) lgA[fid] = lgammaf(f.a_total);
+}
+
+// lgamma(a + n) - lgamma(a) for an integer count n >= 1 given lga = lgamma(a): short rising factorials as one log of
+// a product, everything else the Stirling series of lgamma(a + n) (a + n >= 8 there, since n > 8)
+__device__ __forceinline__ float lb_lgamma_rise(float a, float lga, uint32_t n) {
+    if (n <= 8u) {
+        float p1 = a, p2 = 1.f;
+        if (n > 1u) p1 *= a + 1.f;
+        if (n > 2u) p1 *= a + 2.f;
+        if (n > 3u) p1 *= a + 3.f;
+        if (n > 4u) p2 = a + 4.f;
+        if (n > 5u) p2 *= a + 5.f;
+        if (n > 6u) p2 *= a + 6.f;
+        if (n > 7u) p2 *= a + 7.f;
+        return logf(p1) + logf(p2);
+    }
+    const float z = a + (float)n;
+    if (a >= 8.f) return lb_lgamma_diff(a, (float)n);     // both large: the cancellation-free form
+    return (z - 0.5f) * logf(z) - z + 0.918938533f + lb_stirling_corr(z) - lga;
+}
+
+// K5: L[f][k] = sum_g log marginal(statistics of feature f in kind k), src/product_mixture.cc:594-620.
+// One CTA per (feature, kind).  DD / DPD read their [dim + 1][pst] count table with 128-bit loads (the padding
+// columns hold zeros and add nothing); the table is read exactly once and nothing is written back, so the kernel
+// is bounded by the table stream (stat bytes x G per feature-score).
 __global__ void __launch_bounds__(256)
-k_prop_score(const FeatDev *pfeats, const float *aux, const PropKindDev *pk, int K, float *out) {
+k_prop_score(const FeatDev *pfeats, const float *aux, const float *lga, const float *lgA, const PropKindDev *pk,
+             int K, int f_begin, float *out) {
     __shared__ double s_red[8];
-    const int fid = blockIdx.x, kid = blockIdx.y;
+    const int fid = f_begin + blockIdx.x, kid = blockIdx.y;
     const FeatDev &f = pfeats[fid];
     const PropKindDev p = pk[kid];
     const int G = p.G, pst = p.pst;
-    uint32_t *in = p.ints + (size_t)f.int_row * pst;
-    double *fl = p.flts + (size_t)f.flt_row * pst;
+    const uint32_t *in = p.ints + (size_t)f.int_row * pst;
+    const double *fl = p.flts + (size_t)f.flt_row * pst;
     double acc = 0;
     if (f.type == LB_DD || f.type == LB_DPD) {
-        // 2-D walk (value rows x groups): no divisions, coalesced along groups; counts are
-        // integers, so short rising factorials take the cheap product form
-        const int gl = threadIdx.x & 31, vl = threadIdx.x >> 5;
-        for (int v = vl; v <= f.dim; v += 8) {
-            const float a = v < f.dim ? f.a_scale * aux[f.aux_off + v] : f.a_total;
-            float part = 0.f;
-            for (int g = gl; g < G; g += 32) {
-                const uint32_t n = in[(size_t)v * pst + g];
-                if (n) part += lb_lgamma_diff_int(a, n);
-            }
-            acc += v < f.dim ? (double)part : -(double)part;
+        const int q4 = pst >> 2;                         // uint4 chunks per row (pst is a multiple of 32)
+        const int total = (f.dim + 1) * q4;
+        float part = 0.f;
+        for (int idx = threadIdx.x; idx < total; idx += 256) {
+            const int v = idx / q4, c = idx - v * q4;
+            const uint4 n = *(const uint4 *)(in + (size_t)v * pst + 4 * c);
+            const bool tot = v == f.dim;
+            const float a = tot ? f.a_total : f.a_scale * aux[f.aux_off + v];
+            const float l = tot ? lgA[fid] : lga[f.aux_off + v];
+            float t = 0.f;
+            if (n.x) t += lb_lgamma_rise(a, l, n.x);
+            if (n.y) t += lb_lgamma_rise(a, l, n.y);
+            if (n.z) t += lb_lgamma_rise(a, l, n.z);
+            if (n.w) t += lb_lgamma_rise(a, l, n.w);
+            part += tot ? -t : t;
         }
+        acc = (double)part;
     } else {
-        for (int g = threadIdx.x; g < G; g += blockDim.x) {
-            if (f.type == LB_NICH) {   // sums -> (mean, count_times_variance), once
-                const double n = (double)in[g];
-                if (n == 0.0) { fl[g] = 0.0; fl[pst + g] = 0.0; }
-                else {
-                    const double mean = fl[g] / n;
-                    fl[pst + g] = fmax(fl[pst + g] - n * mean * mean, 0.0);
-                    fl[g] = mean;
-                }
-            }
-            acc += lb_marginal_group(f, aux, in + g, fl + g, pst);
-        }
+        for (int g = threadIdx.x; g < G; g += blockDim.x) acc += lb_marginal_group(f, aux, in + g, fl + g, pst);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
@@ -221,6 +269,7 @@ extern "C" int lb_proposer_accumulate(lb_handle h, uint64_t b, uint64_t en) {
         LB_TRY(dalloc(&e->d_prop_packed, need_p + need_p / 4));
         e->prop_cap_packed = need_p + need_p / 4;
     }
+    e->prop_used_ints = need_i; e->prop_used_flts = need_f;
     if (need_i) LB_CUDA(cudaMemsetAsync(e->d_prop_ints, 0, 4 * need_i, e->stream));
     if (need_f) LB_CUDA(cudaMemsetAsync(e->d_prop_flts, 0, 8 * need_f, e->stream));
     std::vector<PackSrc> src(K);
@@ -257,33 +306,75 @@ extern "C" int lb_proposer_tables(lb_handle h, int32_t kind, uint32_t **ints, ui
     return 0;
 }
 
-extern "C" int lb_proposer_finish(lb_handle h, float *out) {
-    Engine *e = (Engine *)h;
-    LB_CUDA(cudaSetDevice(e->device));
-    if (!e->prop_accumulated) return lb_fail("proposer_finish: call proposer_accumulate first");
+// Score phase over the features [f_lo, f_hi) of the (complete) proposer tables: sums -> moments for every NICH
+// feature (all features, whatever the range: the tables must be whole on every rank), then K5 for the range.
+// Scores stay on the device in d_prop_scores [F_pad][K]; nothing is synchronised.
+int lb_proposer_score_range(Engine *e, int f_lo, int f_hi, int F_pad) {
     const int F = e->F, K = (int)e->kinds.size();
-    if ((size_t)F * K > e->prop_scores_cap) {
+    if ((size_t)F_pad * K > e->prop_scores_cap) {
         if (e->d_prop_scores) cudaFree(e->d_prop_scores);
-        LB_TRY(dalloc(&e->d_prop_scores, (size_t)F * K));
-        e->prop_scores_cap = (size_t)F * K;
+        LB_TRY(dalloc(&e->d_prop_scores, (size_t)F_pad * K));
+        e->prop_scores_cap = (size_t)F_pad * K;
     }
-    {   // one launch over every (feature, kind) pair
-        std::vector<PropKindDev> pk(K);
-        for (int kid = 0; kid < K; ++kid) pk[kid] = PropKindDev{e->prop[kid].ints, e->prop[kid].flts, e->prop[kid].pst, e->prop[kid].G};
-        LB_TRY(lb_ensure_scratch(e, sizeof(PropKindDev) * (size_t)K + 256));
-        LB_CUDA(cudaMemcpyAsync(e->d_scratch, pk.data(), sizeof(PropKindDev) * (size_t)K, cudaMemcpyHostToDevice, e->stream));
-        dim3 grid((unsigned)F, (unsigned)K);
-        k_prop_score<<<grid, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, (const PropKindDev *)e->d_scratch, K, e->d_prop_scores);
-        LB_CUDA(cudaGetLastError());
+    std::vector<PropKindDev> pk(K);
+    for (int kid = 0; kid < K; ++kid) pk[kid] = PropKindDev{e->prop[kid].ints, e->prop[kid].flts, e->prop[kid].pst, e->prop[kid].G};
+    std::vector<int32_t> nich;
+    for (int f = 0; f < F; ++f) if (e->specs[f].type == LB_NICH) nich.push_back(f);
+    // scratch: [PropKindDev K][nich fids][lga aux.size()][lgA F]
+    const size_t o_nich = (sizeof(PropKindDev) * (size_t)K + 255) / 256 * 256;
+    const size_t o_lga = o_nich + (4 * nich.size() + 255) / 256 * 256;
+    const size_t o_lgA = o_lga + (4 * e->aux.size() + 255) / 256 * 256;
+    LB_TRY(lb_ensure_scratch(e, o_lgA + 4 * (size_t)F + 256));
+    char *sc = (char *)e->d_scratch;
+    LB_CUDA(cudaMemcpyAsync(sc, pk.data(), sizeof(PropKindDev) * (size_t)K, cudaMemcpyHostToDevice, e->stream));
+    if (!nich.empty()) {
+        LB_CUDA(cudaMemcpyAsync(sc + o_nich, nich.data(), 4 * nich.size(), cudaMemcpyHostToDevice, e->stream));
+        int maxG = 1;
+        for (int kid = 0; kid < K; ++kid) maxG = std::max(maxG, e->prop[kid].G);
+        const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((nich.size() * (size_t)maxG + 255) / 256, 64));
+        k_prop_moments<<<dim3(gx, (unsigned)K), 256, 0, e->stream>>>(e->d_prop_feats, (const int32_t *)(sc + o_nich), (int)nich.size(),
+                                                                   (const PropKindDev *)sc, K);
         e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
     }
+    k_prop_lgamma_table<<<F, 128, 0, e->stream>>>(e->d_prop_feats, F, e->d_aux, (float *)(sc + o_lga), (float *)(sc + o_lgA));
+    e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
+    if (f_hi > f_lo) {
+        dim3 grid((unsigned)(f_hi - f_lo), (unsigned)K);
+        LB_CUDA(cudaEventRecord(e->kev0, e->stream));
+        k_prop_score<<<grid, 256, 0, e->stream>>>(e->d_prop_feats, e->d_aux, (const float *)(sc + o_lga), (const float *)(sc + o_lgA),
+                                                 (const PropKindDev *)sc, K, f_lo, e->d_prop_scores);
+        LB_CUDA(cudaEventRecord(e->kev1, e->stream));
+        e->kev_pending = true;
+        e->launches[LB_L_TOTAL]++; e->launches[LB_L_KIND]++;
+    }
+    LB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// scores device -> host mirror; marks the proposer tables finished
+int lb_proposer_fetch_scores(Engine *e, float *out) {
+    const int F = e->F, K = (int)e->kinds.size();
     e->prop_scores.resize((size_t)F * K);
     LB_CUDA(cudaMemcpyAsync(e->prop_scores.data(), e->d_prop_scores, 4 * (size_t)F * K, cudaMemcpyDeviceToHost, e->stream));
     LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->kev_pending) {     // K5's own device time (family LB_L_KIND)
+        float ms = 0.f;
+        LB_CUDA(cudaEventElapsedTime(&ms, e->kev0, e->kev1));
+        e->kernel_ms[LB_L_KIND] += ms; e->kernel_ms[LB_L_TOTAL] += ms;
+        e->kev_pending = false;
+    }
     if (out) memcpy(out, e->prop_scores.data(), 4 * (size_t)F * K);
     e->prop_accumulated = false;
     e->prop_valid = true;
     return 0;
+}
+
+extern "C" int lb_proposer_finish(lb_handle h, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->prop_accumulated) return lb_fail("proposer_finish: call proposer_accumulate first");
+    LB_TRY(lb_proposer_score_range(e, 0, e->F, e->F));
+    return lb_proposer_fetch_scores(e, out);
 }
 
 extern "C" int lb_kind_proposer_score(lb_handle h, float *out) {

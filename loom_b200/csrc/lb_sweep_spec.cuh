@@ -24,13 +24,17 @@
 // recompute sums over lanes); the replay test checks every pick against the float64 oracle CDF.
 #pragma once
 
-constexpr int SP_RING = 8;        // ring slots of prefetched row cells
+constexpr int SP_RING = 8;        // ring slots of compiled rows
 constexpr int SP_AHEAD = 3;       // the cells of action i + 3 are fetched while action i runs
 constexpr int SP_LOOK = 2;        // the next ADD is scored ahead when it is at most this far away
-constexpr int SP_SJ = 4;          // sampler: groups per lane kept in registers (G <= 128); larger G uses warp_sample
 constexpr int SP_CPB = 8;         // (chain, kind) pairs per block when W == 1
-constexpr int SP_WIDE_NF = 8;     // kinds with at least this many features get the 8-warp CTA
+constexpr int SP_WIDE_NF = 8;     // kinds with at least this many features get a multi-warp CTA
+constexpr int SP_WIDER_NF = 64;   // ... and with at least this many, 16 warps
 constexpr int SP_HIST = 3;        // actions whose effect on assign[] may be newer than a ring prefetch (= SP_AHEAD)
+constexpr int SP_MAXW = 16;
+#ifndef LB_SPEC_WIDER
+#define LB_SPEC_WIDER 16          // warps of the widest CTA class (kinds with >= SP_WIDER_NF features)
+#endif
 
 struct SweepPair { int32_t chain, kid; };
 
@@ -38,12 +42,12 @@ struct SpecSmem {
     int G, stop, pick, flag;
     uint32_t removed_global, next_global, epoch, pad0;
     unsigned long long sample_size;
-    float u[32];                                   // uniforms of actions [u_base, u_base + 32)
+    float u[32];                                   // uniforms of actions [base, base + 32), base = i & ~31
     uint32_t pf_assign[SP_RING], pf_pg[SP_RING], pf_epoch[SP_RING];
-    float ovr[8];                                  // per-warp sums of a recomputed column
-    int own_off[8][N_CLASS + 1];
+    float ovr[SP_MAXW];                            // per-warp sums of a recomputed column
+    int own_off[SP_MAXW][N_CLASS + 1];
 };
-static_assert(sizeof(SpecSmem) <= 512, "SpecSmem must fit its 512-byte slot");
+static_assert(sizeof(SpecSmem) <= 768, "SpecSmem must fit its 768-byte slot");
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -51,32 +55,30 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// softmax draw with the group scores in registers: lane owns the contiguous groups
-// [lane * per, lane * per + per), per = ceil(G / 32) <= SP_SJ.  Same CDF order, same tie rules as
-// warp_sample (distributions::sample_from_scores_overwrite).
+// softmax draw with the group scores in registers: lane owns the contiguous groups [lane * PER, lane * PER + PER).
+// Same CDF order and tie rules as warp_sample (distributions::sample_from_scores_overwrite).
+template <int PER>
 __device__ __forceinline__ int warp_sample_regs(const float *feat, const float *prior, int G, float u, int lane,
                                                 float *dbg, float dbg_shift, int dbg_stride) {
-    const int per = (G + 31) >> 5;
-    const int lo = lane * per;
-    float v[SP_SJ];
+    const int lo = lane * PER;
+    float v[PER];
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < SP_SJ; ++j) {
+    for (int j = 0; j < PER; ++j) {
         const int g = lo + j;
-        v[j] = -INFINITY;
-        if (j < per && g < G) {
-            v[j] = feat[g] + prior[g];
-            if (dbg && g < dbg_stride) dbg[g] = v[j] - dbg_shift;
-            m = fmaxf(m, v[j]);
-        }
+        v[j] = g < G ? feat[g] + prior[g] : -INFINITY;
+        m = fmaxf(m, v[j]);
+    }
+    if (dbg) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) if (lo + j < G && lo + j < dbg_stride) dbg[lo + j] = v[j] - dbg_shift;
     }
     m = warp_max(m);
     float local = 0.f;
 #pragma unroll
-    for (int j = 0; j < SP_SJ; ++j) {
-        const float p = (j < per && lo + j < G) ? __expf(v[j] - m) : 0.f;
-        v[j] = p;
-        local += p;
+    for (int j = 0; j < PER; ++j) {
+        v[j] = lo + j < G ? __expf(v[j] - m) : 0.f;
+        local += v[j];
     }
     float incl = local;
 #pragma unroll
@@ -95,11 +97,10 @@ __device__ __forceinline__ int warp_sample_regs(const float *feat, const float *
         int last = lo;
         pick = -1;
 #pragma unroll
-        for (int j = 0; j < SP_SJ; ++j) {
-            if (j < per && lo + j < G && pick < 0) {
-                const float p = v[j];
-                if (p > 0.f) last = lo + j;
-                c += p;
+        for (int j = 0; j < PER; ++j) {
+            if (lo + j < G && pick < 0) {
+                if (v[j] > 0.f) last = lo + j;
+                c += v[j];
                 if (c > t) pick = lo + j;
             }
         }
@@ -109,7 +110,7 @@ __device__ __forceinline__ int warp_sample_regs(const float *feat, const float *
 }
 
 template <int W>
-__global__ void __launch_bounds__(W == 1 ? 32 * SP_CPB : W * 32, W == 1 ? 1 : 2)
+__global__ void __launch_bounds__(W == 1 ? 32 * SP_CPB : W * 32, 1)
 k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, int smem_per_pair) {
     constexpr int T = W * 32;
     constexpr int W0 = W > 1 ? 1 : 0;            // first warp that owns features
@@ -133,13 +134,21 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
     const int tid = W == 1 ? (int)(threadIdx.x & 31) : (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nf = kd.nf, st = kd.Gcap;
     const int n_int_rows = kd.n_int_rows, n_flt_rows = kd.n_flt_rows, n_cache_rows = kd.n_cache_rows;
-    const int zero_row = n_cache_rows;
+    const uint32_t zoff = (uint32_t)n_cache_rows * (uint32_t)st;      // the all-zero cache row
     const uint32_t g2p_cap = kd.g2p_cap;
 
+    // Everything per-feature is indexed by POSITION k: features are reordered so that the positions a warp owns
+    // for one class are contiguous (off[c] .. off[c + 1]); no indirection is left in the action loop.
     SpecSmem *ss = (SpecSmem *)smem_raw;
-    FeatDev *s_feat = (FeatDev *)(smem_raw + 512);
-    int32_t *s_fid = (int32_t *)(s_feat + nf);
-    uint32_t *s_raw = (uint32_t *)(s_fid + nf);          // [SP_RING][nf]
+    FeatDev *s_feat = (FeatDev *)(smem_raw + 768);       // [nf] by position
+    int32_t *s_fid = (int32_t *)(s_feat + nf);           // [nf] global feature id (mask row)
+    uint32_t *s_Noff = (uint32_t *)(s_fid + nf);         // [nf] ints offset of the feature's total row (DD / DPD)
+    float *s_A = (float *)(s_Noff + nf);                 // [nf] a_total
+    uint32_t *s_voff = (uint32_t *)(s_A + nf);           // [SP_RING][nf] cache offset of the value row (zero row: unobserved)
+    uint32_t *s_soff = s_voff + SP_RING * nf;            // [SP_RING][nf] cache offset of the shift row (zero row: none)
+    uint32_t *s_ioff = s_soff + SP_RING * nf;            // [SP_RING][nf] ints offset of the count row the cell bumps
+    float *s_av = (float *)(s_ioff + SP_RING * nf);      // [SP_RING][nf] the value's concentration a_v
+    uint32_t *s_raw = (uint32_t *)(s_av + SP_RING * nf); // [SP_RING][nf]
     uint32_t *s_obs = s_raw + SP_RING * nf;              // [SP_RING][nf]
     float *s_part = (float *)(s_obs + SP_RING * nf);     // [W][st] per-warp partial feature scores of a gather
     float *s_a = s_part + W * st;                        // [st] feature scores of the ADD being sampled / pending
@@ -148,8 +157,9 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
     uint32_t *s_counts = (uint32_t *)(s_score + st);     // [st] clustering counts
     float *s_prior = (float *)(s_counts + st);           // [st] CRP prior per group, empties included
     uint32_t *s_p2g = (uint32_t *)(s_prior + st);        // [st] packed -> global
-    uint16_t *s_own = (uint16_t *)(s_p2g + st);          // [nf] feature indices grouped by (owner warp, class)
-    uint8_t *s_owner = (uint8_t *)(s_own + nf);          // [nf]
+    uint16_t *s_own = (uint16_t *)(s_p2g + st);          // [nf] set-up only: kind-local feature index of position k
+    uint8_t *s_owner = (uint8_t *)(s_own + nf);          // [nf] set-up only
+    uint8_t *s_type = s_owner + nf;                      // [nf] set-up only: type by kind-local index
 
     uint32_t *const ints = kd.ints;
     double *const flts = kd.flts;
@@ -159,11 +169,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
     const int32_t *const cache_row_feat = kd.cache_row_feat;
     const float alpha = kd.alpha, d = kd.d;
 
-    for (int j = tid; j < nf; j += T) {
-        const int fid = kind_feats[kd.feat_begin + j];
-        s_feat[j] = feats[fid];
-        s_fid[j] = fid;
-    }
+    for (int j = tid; j < nf; j += T) s_type[j] = (uint8_t)feats[kind_feats[kd.feat_begin + j]].type;
     {
         const int G0 = kd.G;
         const float sh_empty0 = logf((alpha + d * (float)(G0 - n_empty)) / (float)n_empty);
@@ -183,7 +189,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         const float weight[N_CLASS] = {1.f, 4.f, 3.f};
         constexpr int NW = W - W0;
         int cnt[N_CLASS] = {0, 0, 0}, n_cls = 0;
-        for (int j = 0; j < nf; ++j) cnt[feat_class(s_feat[j].type)]++;
+        for (int j = 0; j < nf; ++j) cnt[feat_class(s_type[j])]++;
         for (int c = 0; c < N_CLASS; ++c) n_cls += cnt[c] > 0;
         if (NW >= 2 * n_cls && n_cls > 0) {
             int nw[N_CLASS] = {0, 0, 0}, left = NW;
@@ -201,7 +207,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
             int w0 = W0, seen[N_CLASS] = {0, 0, 0}, first_warp[N_CLASS];
             for (int c = 0; c < N_CLASS; ++c) { first_warp[c] = w0; w0 += nw[c]; }
             for (int j = 0; j < nf; ++j) {
-                const int c = feat_class(s_feat[j].type);
+                const int c = feat_class(s_type[j]);
                 s_owner[j] = (uint8_t)(first_warp[c] + seen[c]++ % nw[c]);
             }
         } else {
@@ -210,7 +216,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
             const int order[N_CLASS] = {CL_GP, CL_NICH, CL_CAT};
             for (int oc = 0; oc < N_CLASS; ++oc)
                 for (int j = 0; j < nf; ++j) {
-                    if (feat_class(s_feat[j].type) != order[oc]) continue;
+                    if (feat_class(s_type[j]) != order[oc]) continue;
                     int best = W0;
                     for (int w = W0 + 1; w < W; ++w) if (load[w] < load[best]) best = w;
                     s_owner[j] = (uint8_t)best;
@@ -223,76 +229,142 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 ss->own_off[w][c] = k;
                 if (w >= W0)
                     for (int j = 0; j < nf; ++j)
-                        if (s_owner[j] == w && feat_class(s_feat[j].type) == c) s_own[k++] = (uint16_t)j;
+                        if (s_owner[j] == w && feat_class(s_type[j]) == c) s_own[k++] = (uint16_t)j;
             }
             ss->own_off[w][N_CLASS] = k;
         }
     }
     sweep_sync<W>();
+    for (int k = tid; k < nf; k += T) {
+        const int fid = kind_feats[kd.feat_begin + s_own[k]];
+        const FeatDev f = feats[fid];
+        s_feat[k] = f;
+        s_fid[k] = fid;
+        s_Noff[k] = (uint32_t)(f.int_row + f.dim) * (uint32_t)st;
+        s_A[k] = f.a_total;
+    }
     int off[N_CLASS + 1];
 #pragma unroll
     for (int c = 0; c <= N_CLASS; ++c) off[c] = ss->own_off[warp][c];
+    sweep_sync<W>();
 
     uint64_t i = kd.progress;
 
-    // ---- row cells: global -> registers (SP_AHEAD actions early) -> ring slot ----
-    // (thread 0 also fetches the row's assignment; the dependent global -> packed lookup of a REMOVE is issued at
-    // commit time, in phase B, so that it never delays the sampler)
+    // ---- compiled rows: global -> registers (SP_AHEAD actions early) -> ring slot ----
+    // Thread t owns positions t + q T.  A cell is fetched as (raw, observed) and "compiled" at commit time into
+    // the offsets the action loop uses directly: value row / shift row of the cached scorer (the all-zero row
+    // when there is nothing to add), the count row it bumps, its concentration.
+    // (thread 0 also fetches the row's assignment; the dependent global -> packed lookup of a REMOVE is issued
+    // at commit time, in phase B, so that it never delays the sampler)
     uint32_t pf_raw[SW_PF], pf_obs[SW_PF], pf_assign = LB_UNASSIGNED, pf_pg = LB_UNASSIGNED, pf_epoch = 0, pf_is_remove = 0;
-    auto prefetch = [&](uint64_t idx) {
+    auto prefetch = [&](uint64_t idx, uint32_t a_) {      // a_ = actions[idx] (garbage when idx >= n_actions)
+        const uint64_t r = a_ >> 1;
+        const bool ok = idx < n_actions && r < rows.R;
         if (tid == 0) {
             pf_assign = LB_UNASSIGNED; pf_pg = LB_UNASSIGNED; pf_epoch = ss->epoch; pf_is_remove = 0;
-            if (idx < n_actions) {
-                const uint32_t a_ = actions[idx];
-                const uint64_t r = a_ >> 1;
-                if (r < rows.R) { pf_assign = assign[r]; pf_is_remove = a_ & 1u; }
-            }
+            if (ok) { pf_assign = assign[r]; pf_is_remove = a_ & 1u; }
         }
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
             if (q * T + warp * 32 >= nf) break;
-            const int j = tid + q * T;
+            const int k = tid + q * T;
             pf_raw[q] = 0; pf_obs[q] = 0;
-            if (j < nf && idx < n_actions) {
-                const uint64_t r = actions[idx] >> 1;
-                if (r < rows.R) {
-                    const FeatDev &f = s_feat[j];
-                    pf_obs[q] = (rows.mask[(uint64_t)s_fid[j] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
-                    pf_raw[q] = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                          : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-                }
+            if (k < nf && ok) {
+                const FeatDev &f = s_feat[k];
+                pf_obs[q] = (rows.mask[(uint64_t)s_fid[k] * rows.W + (r >> 5)] >> (r & 31)) & 1u;
+                pf_raw[q] = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
+                                      : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
             }
         }
     };
-    auto commit = [&](int slot) {
+    // commit in two halves: `begin` compiles the cell, stores what needs no further load and ISSUES the loads the
+    // rest depends on (the value's concentration, thread 0's global -> packed lookup); `end` stores those, a
+    // phase later, so that no warp ever waits on them
+    float pf_av[SW_PF];
+    auto commit_begin = [&](int slot) {
 #pragma unroll
         for (int q = 0; q < SW_PF; ++q) {
             if (q * T + warp * 32 >= nf) break;
-            const int j = tid + q * T;
-            if (j < nf) { s_raw[slot * nf + j] = pf_raw[q]; s_obs[slot * nf + j] = pf_obs[q]; }
+            const int k = tid + q * T;
+            pf_av[q] = 0.f;
+            if (k < nf) {
+                const FeatDev &f = s_feat[k];
+                const uint32_t raw = pf_raw[q], obs = pf_obs[q];
+                uint32_t vo = zoff, so = zoff, io = 0;
+                if (obs) {
+                    if (f.type == LB_BB) {
+                        vo = (uint32_t)(f.cache_row + (raw ? 0 : 1)) * (uint32_t)st;
+                    } else if (f.type == LB_DD || f.type == LB_DPD) {
+                        vo = (uint32_t)(f.cache_row + (int)raw) * (uint32_t)st;
+                        so = (uint32_t)(f.cache_row + f.dim) * (uint32_t)st;
+                        io = (uint32_t)(f.int_row + (int)raw) * (uint32_t)st;
+                        pf_av[q] = f.a_scale * aux[f.aux_off + (int)raw];
+                    }
+                }
+                const int at = slot * nf + k;
+                s_voff[at] = vo; s_soff[at] = so; s_ioff[at] = io; s_raw[at] = raw; s_obs[at] = obs;
+            }
         }
-        if (tid == 0) {
-            pf_pg = (pf_is_remove && pf_assign != LB_UNASSIGNED) ? g2p[pf_assign] : LB_UNASSIGNED;
-            ss->pf_assign[slot] = pf_assign; ss->pf_pg[slot] = pf_pg; ss->pf_epoch[slot] = pf_epoch;
+        if (tid == 0) pf_pg = (pf_is_remove && pf_assign != LB_UNASSIGNED) ? g2p[pf_assign] : LB_UNASSIGNED;
+    };
+    auto commit_end = [&](int slot) {
+#pragma unroll
+        for (int q = 0; q < SW_PF; ++q) {
+            if (q * T + warp * 32 >= nf) break;
+            const int k = tid + q * T;
+            if (k < nf) s_av[slot * nf + k] = pf_av[q];
         }
+        if (tid == 0) { ss->pf_assign[slot] = pf_assign; ss->pf_pg[slot] = pf_pg; ss->pf_epoch[slot] = pf_epoch; }
     };
     // Philox uniforms, 32 actions at a time across the lanes of warp 0
     auto draw_uniforms = [&](uint64_t base) {
         if (warp == 0) ss->u[lane] = lb_uniform(seed, 0u, offset + base + (uint64_t)lane, (uint32_t)kid);
     };
-    for (int q = 0; q < SP_AHEAD; ++q) { prefetch(i + q); commit((int)((i + q) % SP_RING)); }
+    auto action_at = [&](uint64_t idx) -> uint32_t { return idx < n_actions ? actions[idx] : 1u; };   // past the end: a REMOVE
+    for (int q = 0; q < SP_AHEAD; ++q) {
+        prefetch(i + q, action_at(i + q));
+        commit_begin((int)((i + q) % SP_RING));
+        commit_end((int)((i + q) % SP_RING));
+    }
     draw_uniforms(i & ~31ull);
     sweep_sync<W>();
 
-    // feature part of the scores of a row (ring cells g_raw / g_obs) against the tables as they stand,
-    // per-warp partial sums into s_part
-    auto gather = [&](const uint32_t *g_raw, const uint32_t *g_obs, int G) {
+    // feature part of the scores of a compiled row (ring slot) against the tables as they stand: per-warp
+    // partial sums into s_part, 64 groups a trip (lane = group, two per lane)
+    auto gather = [&](int slot, int G) {
         if (warp < W0) return;
+        const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
         for (int g0 = 0; g0 < G; g0 += 64) {
-            float acc[2];
-            score_warp<2>(off, s_own, s_feat, g_raw, g_obs, ints, cache, st, zero_row, g0, lane, acc);
-            s_part[warp * st + g0 + lane] = acc[0];
-            s_part[warp * st + g0 + lane + 32] = acc[1];
+            float acc0 = 0.f, acc1 = 0.f;
+            const float *cg = cache + g0 + lane;
+#pragma unroll 4
+            for (int k = off[CL_CAT]; k < off[CL_CAT + 1]; ++k) {     // branch-free: unobserved cells read the zero row
+                const float *cv = cg + rv[k], *cs = cg + rs[k];
+                acc0 += cv[0] - cs[0];
+                acc1 += cv[32] - cs[32];
+            }
+            for (int k = off[CL_GP]; k < off[CL_GP + 1]; ++k) {
+                if (!ro[k]) continue;
+                const FeatDev &f = s_feat[k];
+                const uint32_t raw = rr[k];
+                const float lf = lb_log_factorial(raw), x = (float)raw;
+                const uint32_t *sum = ints + (size_t)(f.int_row + 1) * st + g0 + lane;
+                const float *c0 = cg + (size_t)f.cache_row * st;
+                acc0 += lb_lgamma_diff_int(f.hp[0] + (float)sum[0], raw) - lf + c0[0] + x * c0[st];
+                acc1 += lb_lgamma_diff_int(f.hp[0] + (float)sum[32], raw) - lf + c0[32] + x * c0[st + 32];
+            }
+            for (int k = off[CL_NICH]; k < off[CL_NICH + 1]; ++k) {
+                if (!ro[k]) continue;
+                const FeatDev &f = s_feat[k];
+                const float x = __uint_as_float(rr[k]);
+                const float *c = cg + (size_t)f.cache_row * st;
+                const float dx0 = (x - c[3 * (size_t)st]) - c[4 * (size_t)st];
+                const float dx1 = (x - c[3 * (size_t)st + 32]) - c[4 * (size_t)st + 32];
+                acc0 += c[0] - c[st] * log1pf(c[2 * (size_t)st] * dx0 * dx0);
+                acc1 += c[32] - c[st + 32] * log1pf(c[2 * (size_t)st + 32] * dx1 * dx1);
+            }
+            s_part[warp * st + g0 + lane] = acc0;
+            s_part[warp * st + g0 + lane + 32] = acc1;
         }
     };
     auto reduce_parts = [&](float *dst, int G) {
@@ -304,62 +376,71 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
             dst[g] = s;
         }
     };
-    // this warp's share of the feature scores of a row at ONE column, lanes = features -> ss->ovr[warp]
-    auto column_part = [&](const uint32_t *n_raw, const uint32_t *n_obs, int col) {
+    // this warp's share of the feature scores of a compiled row at ONE column, lanes = positions -> ss->ovr[warp]
+    auto column_part = [&](int slot, int col) {
+        const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
         float part = 0.f;
-        for (int k = off[0] + lane; k < off[N_CLASS]; k += 32) {
-            const int j = s_own[k];
-            if (!n_obs[j]) continue;
-            const FeatDev &f = s_feat[j];
-            const uint32_t raw = n_raw[j];
+        for (int k = off[CL_CAT] + lane; k < off[CL_CAT + 1]; k += 32) part += cache[rv[k] + col] - cache[rs[k] + col];
+        for (int k = off[CL_GP] + lane; k < off[N_CLASS]; k += 32) {
+            if (!ro[k]) continue;
+            const FeatDev &f = s_feat[k];
+            const uint32_t raw = rr[k];
             part += lb_score_cell(f, ints + (size_t)f.int_row * st + col, cache + (size_t)f.cache_row * st + col, st, raw,
                                   f.type == LB_GP ? lb_log_factorial(raw) : 0.f);
         }
         part = warp_sum_f(part);
         if (lane == 0) ss->ovr[warp] = part;
     };
-    // warp 0, after a barrier: pending[col] = sum of the per-warp column parts
+    // warp 0, after a barrier: pending[col] = sum of the per-warp column parts (one lane, W - W0 independent loads)
     auto apply_column = [&](float *pending, int col) {
-        if (warp == 0) {
-            float v = (lane >= W0 && lane < W) ? ss->ovr[lane] : 0.f;
-            v = warp_sum_f(v);
-            if (lane == 0) pending[col] = v;
-            __syncwarp();
+        if (tid == 0) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = W0; w < W; ++w) v += ss->ovr[w];
+            pending[col] = v;
         }
+        if (warp == 0) __syncwarp();
     };
 
     float *s_cur = s_a, *s_next = s_b;
     uint64_t next_idx = ~0ull;        // ADD action whose feature scores sit in s_next (complete up to the last update)
-    uint64_t cursor = i;              // scan position of the next ADD
     // thread 0: the last SP_HIST actions' effect on assign[] (newer than any ring prefetch)
-    uint64_t h_row[SP_HIST];
-    uint32_t h_val[SP_HIST], h_pg[SP_HIST], h_epoch[SP_HIST];
+    uint32_t h_row[SP_HIST], h_val[SP_HIST], h_pg[SP_HIST], h_epoch[SP_HIST];
 #pragma unroll
-    for (int q = 0; q < SP_HIST; ++q) { h_row[q] = ~0ull; h_val[q] = LB_UNASSIGNED; h_pg[q] = 0; h_epoch[q] = 0; }
+    for (int q = 0; q < SP_HIST; ++q) { h_row[q] = 0xFFFFFFFFu; h_val[q] = LB_UNASSIGNED; h_pg[q] = 0; h_epoch[q] = 0; }
+    // the action words of i .. i + 3 live in registers; the word of i + 4 is loaded one action early
+    uint32_t act0 = action_at(i), act1 = action_at(i + 1), act2 = action_at(i + 2), act3 = action_at(i + 3);
 
+    // make prof: cycles per phase seen by lane 0 of every warp (clock64), summed over the launch
+    // ADD: 0 gather / sample | 1 wait at (A) | 2 phase-B work | 3 wait at (B) | 4 apply, structure
+    // REMOVE: 5 lookup / gather | 6 wait at (A) + phase-B work | 7 wait at (B) + rest
+#ifdef LB_SWEEP_PROFILE
+    unsigned long long *const prof = ch.prof;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = clock64();
+#define SP_TICK(k) do { if (prof && lane == 0) { const long long now__ = clock64(); pt[k] += now__ - pc; pc = now__; } } while (0)
+#else
+#define SP_TICK(k) do { } while (0)
+#endif
     int status = LB_ST_OK;
     for (; i < n_actions; ++i) {
-        const uint32_t act = actions[i];
-        const uint64_t r = act >> 1;
+        const uint32_t act = act0;
+        const uint32_t r = act >> 1;
         const bool is_remove = act & 1u;
         const int slot = (int)(i % SP_RING);
-        const uint32_t *c_raw = s_raw + slot * nf, *c_obs = s_obs + slot * nf;
         if (r >= rows.R) { status = LB_ST_BAD_ROW; break; }
         const int G = ss->G;
-        prefetch(i + SP_AHEAD);
+        const uint32_t act4 = action_at(i + 4);          // consumed next iteration
+        prefetch(i + SP_AHEAD, act3);
 
         // the next ADD after this action, if it is close enough to have its cells in the ring
-        if (cursor <= i) cursor = i + 1;
-        while (cursor < n_actions && cursor <= i + SP_LOOK && (actions[cursor] & 1u)) ++cursor;
-        const bool have_p = cursor < n_actions && cursor <= i + SP_LOOK;
-        const uint64_t p = cursor;
+        const bool have_p = !(act1 & 1u) ? (i + 1 < n_actions) : (!(act2 & 1u) && i + 2 < n_actions);
+        const uint64_t p = !(act1 & 1u) ? i + 1 : i + 2;
 
         if (!is_remove) {
             if (G >= st || ss->next_global >= g2p_cap) { status = LB_ST_NEED_GROW; break; }
             if (next_idx != i) {
-                // no scores were gathered ahead for this ADD (first action of a launch, or an ADD
-                // that came into view late): gather them now
-                gather(c_raw, c_obs, G);
+                // no scores were gathered ahead for this ADD (first action of a launch): gather them now
+                gather(slot, G);
                 sweep_sync<W>();
                 reduce_parts(s_next, G);
                 sweep_sync<W>();
@@ -368,8 +449,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
             next_idx = ~0ull;
         }
         const bool do_gather = have_p && next_idx != p;
-        const int pslot = (int)(p % SP_RING);
-        if (do_gather) gather(s_raw + pslot * nf, s_obs + pslot * nf, G);
+        if (do_gather) gather((int)(p % SP_RING), G);
 
         if (!is_remove) {
             // ---- ADD: duplicate check, sample (warp 0) ----
@@ -384,9 +464,10 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 float *dbg = dbg_scores ? dbg_scores + ((uint64_t)i * K + kid) * dbg_stride : nullptr;
                 const float dbg_shift = dbg ? logf((float)ss->sample_size + alpha) : 0.f;
                 int pick;
-                if (G <= 32 * SP_SJ) {
-                    pick = warp_sample_regs(s_cur, s_prior, G, u, lane, dbg, dbg_shift, dbg_stride);
-                } else {
+                if (G <= 32) pick = warp_sample_regs<1>(s_cur, s_prior, G, u, lane, dbg, dbg_shift, dbg_stride);
+                else if (G <= 64) pick = warp_sample_regs<2>(s_cur, s_prior, G, u, lane, dbg, dbg_shift, dbg_stride);
+                else if (G <= 128) pick = warp_sample_regs<4>(s_cur, s_prior, G, u, lane, dbg, dbg_shift, dbg_stride);
+                else {
                     for (int g = lane; g < G; g += 32) {
                         const float s = s_cur[g] + s_prior[g];
                         s_score[g] = s;
@@ -422,28 +503,44 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 if (dbg_picks) dbg_picks[(uint64_t)i * K + kid] = g;
             }
         }
+        SP_TICK(is_remove ? 5 : 0);
         sweep_sync<W>();   // (A) pick visible; the gather's partial sums are in s_part
         if (ss->stop) { status = ss->stop; break; }
         const int g = ss->pick;
         const int flag = ss->flag;
+        if (!is_remove) SP_TICK(1);
 
         // ---- phase B: apply the row to column g; bring the pending ADD's scores up to date ----
-        commit((int)((i + SP_AHEAD) % SP_RING));
+        commit_begin((int)((i + SP_AHEAD) % SP_RING));
         if (do_gather) { reduce_parts(s_next, G); next_idx = p; }
         const bool pending = next_idx != ~0ull;
         const int nslot = (int)(next_idx % SP_RING);
         {
             const int sign = is_remove ? -1 : +1;
-            for (int k = off[0] + lane; k < off[N_CLASS]; k += 32) {
-                const int j = s_own[k];
-                if (!c_obs[j]) continue;
-                const FeatDev &f = s_feat[j];
-                lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
-                               cache + (size_t)f.cache_row * st + g, st, c_raw[j], sign);
+            const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *ri = s_ioff + slot * nf;
+            const uint32_t *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
+            const float *ra = s_av + slot * nf;
+            for (int k = off[CL_CAT] + lane; k < off[N_CLASS]; k += 32) {
+                if (!ro[k]) continue;
+                const uint32_t so = rs[k];
+                if (so != zoff) {
+                    // DD / DPD: Group::add_value / remove_value on the two count rows + their cached scorer entries
+                    const uint32_t io = ri[k] + (uint32_t)g, no = s_Noff[k] + (uint32_t)g;
+                    const uint32_t n = ints[io] + (uint32_t)sign, tot = ints[no] + (uint32_t)sign;
+                    ints[io] = n;
+                    ints[no] = tot;
+                    cache[rv[k] + g] = logf(ra[k] + (float)n);
+                    cache[so + g] = logf(s_A[k] + (float)tot);
+                } else {
+                    const FeatDev &f = s_feat[k];
+                    lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
+                                   cache + (size_t)f.cache_row * st + g, st, rr[k], sign);
+                }
             }
             __syncwarp();
-            if (pending && !(flag && is_remove)) column_part(s_raw + nslot * nf, s_obs + nslot * nf, g);
+            if (pending && !(flag && is_remove)) column_part(nslot, g);
         }
+        commit_end((int)((i + SP_AHEAD) % SP_RING));
         if (warp == 0) {
             if ((i & 31) == 31) draw_uniforms(i + 1);
             if (lane == 0) {
@@ -460,7 +557,10 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 h_row[SP_HIST - 1] = r; h_val[SP_HIST - 1] = gid; h_pg[SP_HIST - 1] = (uint32_t)g; h_epoch[SP_HIST - 1] = ss->epoch;
             }
         }
+        act0 = act1; act1 = act2; act2 = act3; act3 = act4;
+        SP_TICK(is_remove ? 6 : 2);
         sweep_sync<W>();   // (B) updates visible to the next gather; column parts in ss->ovr
+        if (!is_remove) SP_TICK(3);
         if (pending && !(flag && is_remove)) apply_column(s_next, g);
 
         if (flag) {
@@ -471,7 +571,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 for (int row = tid; row < n_flt_rows; row += T) flts[(size_t)row * st + ng] = 0.0;
                 sweep_sync<W>();
                 for (int row = tid; row < n_cache_rows; row += T) {
-                    const FeatDev &f = s_feat[cache_row_feat[row]];
+                    const FeatDev f = feats[kind_feats[kd.feat_begin + cache_row_feat[row]]];
                     lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
                                    cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
                 }
@@ -489,7 +589,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                     for (int gg = tid; gg <= ng; gg += T) if (!s_counts[gg]) s_prior[gg] = she;
                 }
                 if (pending) {   // the pending ADD sees one more column
-                    column_part(s_raw + nslot * nf, s_obs + nslot * nf, ng);
+                    column_part(nslot, ng);
                     sweep_sync<W>();
                     apply_column(s_next, ng);
                 }
@@ -527,7 +627,13 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 sweep_sync<W>();
             }
         }
+        SP_TICK(is_remove ? 7 : 4);
     }
+#ifdef LB_SWEEP_PROFILE
+    if (prof && lane == 0 && kid < 16 && W > 1 && warp < 8)
+        for (int k = 0; k < 8; ++k) atomicAdd(&prof[(kid * 8 + warp) * 8 + k], (unsigned long long)pt[k]);
+#endif
+#undef SP_TICK
     sweep_sync<W>();
     for (int g = tid; g < st; g += T) {
         const uint32_t n = s_counts[g];
@@ -545,5 +651,5 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
 }
 
 static size_t spec_smem_bytes(int nf, int Gcap, int warps) {
-    return 512 + (size_t)nf * (sizeof(FeatDev) + 4 + 8 * SP_RING + 3) + (size_t)Gcap * 4 * (warps + 6) + 64;
+    return 768 + (size_t)nf * (sizeof(FeatDev) + 12 + 24 * SP_RING + 4) + (size_t)Gcap * 4 * (warps + 6) + 64;
 }
