@@ -138,6 +138,11 @@ int LB_NAME(set_model)(lb_handle h, int32_t n_features, const lb_feature_spec *s
  * row block from HOST memory.  Clears all assignments. */
 int LB_NAME(set_rows)(lb_handle h, uint64_t n_rows, const uint8_t *cat8,
                       const uint32_t *wide, const uint32_t *mask);
+/* Stream the SAME block's cells in again from host buffers (same n_rows; the engine must own its rows): the
+ * reference re-reads its rows file on every pass over the data (StreamInterval, src/stream_interval.hpp:38-75;
+ * Loom::infer_multi_pass, src/loom.cc:217-243).  Assignments and group statistics are untouched. */
+int LB_NAME(reload_rows)(lb_handle h, uint64_t n_rows, const uint8_t *cat8,
+                         const uint32_t *wide, const uint32_t *mask);
 
 /* Tare-compressed rows: ProductValue::Diff{pos, neg, tares} (src/schema.proto:87-91) as
  * produced by loom's tare + sparsify passes (src/differ.cc:191-298; worked example

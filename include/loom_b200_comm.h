@@ -56,6 +56,13 @@ int lb_comm_kind_proposer_score(lb_handle h, float *out_scores, lb_comm_round_st
  * ends where lb_hyper_run ends, bit for bit. */
 int lb_comm_hyper_run(lb_handle h, uint64_t seed, double *allreduce_ms);
 
+/* Kind-sharded cat sweep (doc/adapting.md:144-147: the kinds of a row are independent tasks -- the reference runs one
+ * thread per kind, src/cat_pipeline.cc:103-125): rank owner[k] has swept kind k with lb_cat_sweep(kind_mask); this
+ * publishes every kind's groups, id maps and assignment column from its owner to all ranks (one all-reduce of the
+ * headers + one NCCL group of broadcasts), after which every rank holds the state an unsharded sweep leaves.
+ * bytes_out / ms_out (optional): payload bytes and device time of the broadcast group. */
+int lb_comm_sync_kinds(lb_handle h, const int32_t *owner, double *bytes_out, double *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

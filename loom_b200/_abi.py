@@ -52,6 +52,7 @@ SIGNATURES = {
     "set_model": (C.c_int, [_h, C.c_int32, C.POINTER(FeatureSpec), _f32p, C.c_int32, C.c_int32,
                             _u32p, _f32p, _f32p, C.c_int32]),
     "set_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
+    "reload_rows": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u32p]),
     "set_rows_diff": (C.c_int, [_h, C.c_uint64, _u8p, _u32p, _u8p, _u64p, _u32p, _u32p, _u64p, _u32p]),
     "query_score": (C.c_int, [_h, C.c_uint64, C.c_uint64, _f32p]),
     "query_sample": (C.c_int, [_h, C.c_uint64, _u32p, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, _u32p, _u32p]),
@@ -95,6 +96,26 @@ SIGNATURES = {
 }
 
 
+class CommRoundStats(C.Structure):
+    """lb_comm_round_stats (include/loom_b200_comm.h)"""
+    _fields_ = [(n, C.c_double) for n in ("accumulate_ms", "allreduce_ms", "allreduce_bytes", "score_ms", "allgather_ms",
+                                          "allgather_bytes", "row_begin", "row_end", "feature_begin", "feature_end")]
+
+
+# include/loom_b200_comm.h: NCCL entry points, CUDA library only (the oracle has no collectives)
+COMM_SIGNATURES = {
+    "comm_unique_id": (C.c_int, [_u8p]),
+    "comm_init": (C.c_int, [_h, _u8p, C.c_int32, C.c_int32]),
+    "comm_destroy": (C.c_int, [_h]),
+    "comm_rank": (C.c_int, [_h, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "comm_barrier": (C.c_int, [_h]),
+    "comm_max_f64": (C.c_int, [_h, _f64p, C.c_int32]),
+    "comm_kind_proposer_score": (C.c_int, [_h, _f32p, C.POINTER(CommRoundStats)]),
+    "comm_hyper_run": (C.c_int, [_h, C.c_uint64, _f64p]),
+    "comm_sync_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _f64p, _f64p]),
+}
+
+
 class LoomError(RuntimeError):
     """Non-zero status from the C ABI (the reference aborts: src/common.hpp:52-59)."""
 
@@ -115,6 +136,12 @@ class Abi:
             fn.restype = res
             fn.argtypes = args
             setattr(self, name, fn)
+        if prefix == "lb_":
+            for name, (res, args) in COMM_SIGNATURES.items():
+                fn = getattr(self.lib, prefix + name)
+                fn.restype = res
+                fn.argtypes = args
+                setattr(self, name, fn)
 
     def check(self, status):
         if status != 0:

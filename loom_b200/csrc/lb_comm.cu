@@ -205,3 +205,74 @@ extern "C" int lb_comm_hyper_run(lb_handle h, uint64_t seed, double *allreduce_m
     float topo[2] = {buf[0], buf[1]};
     return lb_set_hypers(h, specs.data(), A ? new_aux.data() : nullptr, kind_py.data(), topo);
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kind-sharded cat sweep: "tasks in different kinds are independent" (doc/adapting.md:144-147),
+// so rank owner[k] sweeps kind k (lb_cat_sweep with a kind mask) and nobody talks during the sweep.  Before a batch
+// kernel that needs every kind's partition (the row-sharded proposer, the hyper kernel, a dump) the owners publish
+// their kinds: one all-reduce of the kinds' headers (G, capacity, id-tracker extent, sample size), then ONE NCCL group
+// of broadcasts -- per kind: clustering counts, id maps, the three group tables and the assignment column.
+extern "C" int lb_comm_sync_kinds(lb_handle h, const int32_t *owner, double *bytes_out, double *ms_out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    Comm *c = comm_of(e);
+    if (bytes_out) *bytes_out = 0.0;
+    if (ms_out) *ms_out = 0.0;
+    if (!c || c->world == 1) return 0;
+    const int K = (int)e->kinds.size();
+    for (int k = 0; k < K; ++k)
+        if (owner[k] < 0 || owner[k] >= c->world) return lb_fail("comm_sync_kinds: kind %d has owner %d of %d", k, owner[k], c->world);
+    LB_TRY(lb_sync_model(e));
+    LB_TRY(lb_pull_kinds(e));
+    std::vector<unsigned long long> hdr(5 * (size_t)K, 0ull);
+    for (int k = 0; k < K; ++k) {
+        if (owner[k] != c->rank) continue;
+        const KindHost &kh = e->kinds[k];
+        unsigned long long *x = &hdr[5 * (size_t)k];
+        x[0] = (unsigned long long)kh.G; x[1] = (unsigned long long)kh.Gcap; x[2] = kh.g2p_cap;
+        x[3] = kh.next_global; x[4] = kh.sample_size;
+    }
+    LB_TRY(comm_tmp(e, 8 * hdr.size()));
+    LB_CUDA(cudaMemcpyAsync(c->d_tmp, hdr.data(), 8 * hdr.size(), cudaMemcpyHostToDevice, e->stream));
+    LB_NCCL(ncclAllReduce(c->d_tmp, c->d_tmp, hdr.size(), ncclUint64, ncclSum, c->comm, e->stream));
+    LB_CUDA(cudaMemcpyAsync(hdr.data(), c->d_tmp, 8 * hdr.size(), cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < K; ++k) {               // receivers take the owner's table shape
+        KindHost &kh = e->kinds[k];
+        const unsigned long long *x = &hdr[5 * (size_t)k];
+        if (owner[k] != c->rank) {
+            if (kh.Gcap != (int)x[1]) LB_TRY(lb_kind_alloc(e, kh, (int)x[0], (int)x[1]));
+            if (kh.g2p_cap != (uint32_t)x[2]) {
+                if (kh.g2p) LB_CUDA(cudaFreeAsync(kh.g2p, e->stream));
+                kh.g2p = nullptr;
+                LB_CUDA(cudaMallocAsync((void **)&kh.g2p, 4 * (size_t)x[2], e->stream));
+                kh.g2p_cap = (uint32_t)x[2];
+            }
+            kh.G = (int)x[0]; kh.next_global = (uint32_t)x[3]; kh.sample_size = x[4];
+        }
+    }
+    double bytes = 0.0;
+    LB_CUDA(cudaEventRecord(c->ev[0], e->stream));
+    LB_NCCL(ncclGroupStart());
+    for (int k = 0; k < K; ++k) {
+        KindHost &kh = e->kinds[k];
+        const size_t cap = (size_t)kh.Gcap;
+        struct { void *p; size_t n; } bufs[] = {
+            {kh.counts, 4 * cap}, {kh.shifted, 4 * cap}, {kh.p2g, 4 * cap}, {kh.g2p, 4 * (size_t)kh.g2p_cap},
+            {kh.ints, 4 * (size_t)kh.n_int_rows * cap}, {kh.flts, 8 * (size_t)kh.n_flt_rows * cap},
+            {kh.cache, 4 * (size_t)(kh.n_cache_rows + 1) * cap}, {kh.assign, 4 * (size_t)e->R}};
+        for (auto &b : bufs) {
+            if (!b.p || !b.n) continue;
+            LB_NCCL(ncclBroadcast(b.p, b.p, b.n, ncclUint8, owner[k], c->comm, e->stream));
+            bytes += (double)b.n;
+        }
+    }
+    LB_NCCL(ncclGroupEnd());
+    LB_CUDA(cudaEventRecord(c->ev[1], e->stream));
+    LB_TRY(lb_sync_model(e));                   // the KindDev mirrors follow the host fields (synchronises)
+    lb_free_proposer(e);
+    if (bytes_out) *bytes_out = bytes;
+    if (ms_out) { float ms = 0; LB_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); *ms_out = ms; }
+    return 0;
+}

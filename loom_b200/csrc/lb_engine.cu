@@ -436,6 +436,21 @@ extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const u
     return 0;
 }
 
+extern "C" int lb_reload_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wide,
+                              const uint32_t *mask) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (!e->F || !e->d_mask || e->rows_borrowed) return lb_fail("reload_rows: the engine holds no rows of its own");
+    if (R != e->R) return lb_fail("reload_rows: %llu rows given, the block holds %llu", (unsigned long long)R, (unsigned long long)e->R);
+    if (e->F8) LB_CUDA(cudaMemcpyAsync(e->d_cat8, cat8, (size_t)e->F8 * R, cudaMemcpyHostToDevice, e->stream));
+    if (e->FW) LB_CUDA(cudaMemcpyAsync(e->d_wide, wide, (size_t)e->FW * R * 4, cudaMemcpyHostToDevice, e->stream));
+    LB_CUDA(cudaMemcpyAsync(e->d_mask, mask, (size_t)e->F * e->W * 4, cudaMemcpyHostToDevice, e->stream));
+    int bad = 0;
+    LB_TRY(lb_launch_validate_rows(e, &bad));
+    if (bad) return lb_fail("reload_rows: an observed categorical value is out of range for its feature");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // Tare-compressed rows: decode Diff{pos,neg,tares} into the dense columns on the device.
 __global__ void k_diff_fill(const FeatDev *feats, int F, const uint8_t *tare_obs, const uint32_t *tare_val,

@@ -125,11 +125,15 @@ class RowBlock:
         bits = np.unpackbits(self.mask.view(np.uint8).reshape(F, -1), axis=1, bitorder="little")
         return bits[:, :self.n_rows].astype(bool)
 
+    def cells_per_feature(self):
+        """observed cells of every feature: popcount of the mask rows (padding bits are zero)"""
+        return np.bitwise_count(self.mask).sum(axis=1, dtype=np.int64)
+
     def n_cells(self, features=None):
-        obs = self.observed()
+        per = self.cells_per_feature()
         if features is not None:
-            obs = obs[list(features)]
-        return int(obs.sum())
+            per = per[list(features)]
+        return int(per.sum())
 
 
 def pack_mask(obs):
@@ -226,6 +230,12 @@ class Engine:
         a.check(a.set_rows(self.h, rows.n_rows, ptr(rows.cat8, _u8p), ptr(rows.wide, _u32p),
                            ptr(rows.mask, _u32p)))
         self.n_rows = rows.n_rows
+
+    def reload_rows(self, rows):
+        """stream the same block in again from host buffers (the reference re-reads its rows file every pass);
+        assignments and statistics are kept"""
+        a = self.abi
+        a.check(a.reload_rows(self.h, rows.n_rows, ptr(rows.cat8, _u8p), ptr(rows.wide, _u32p), ptr(rows.mask, _u32p)))
 
     def generate_rows(self, n_rows, density, seed):
         """Loom::generate's generate_rows: synthesise rows from the model; the engine then holds them, assigned"""

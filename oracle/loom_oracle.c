@@ -287,6 +287,17 @@ int lo_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wi
     return 0;
 }
 
+/* the same block streamed in again (src/stream_interval.hpp:38-75): cells replaced, assignments kept */
+int lo_reload_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const uint32_t *wide, const uint32_t *mask) {
+    engine_t *e = h;
+    if (!e->F || !e->mask || e->rows_borrowed) return lo_fail("reload_rows: the engine holds no rows of its own");
+    if (R != e->R) return lo_fail("reload_rows: %llu rows given, the block holds %llu", (unsigned long long)R, (unsigned long long)e->R);
+    if (e->F8) memcpy(e->cat8, cat8, (size_t)e->F8 * R);
+    if (e->FW) memcpy(e->wide, wide, (size_t)e->FW * R * 4);
+    memcpy(e->mask, mask, (size_t)e->F * e->W * 4);
+    return 0;
+}
+
 /* loom/tasks.py:173-194: every sample reads the same rows file */
 int lo_share_rows(lb_handle h, lb_handle owner) {
     engine_t *e = h, *o = owner;

@@ -30,6 +30,16 @@ def test_cuda_library_exports_every_symbol():
         assert hasattr(abi.lib, "lb_" + name), name
 
 
+def test_comm_header_and_binding_agree_and_are_exported():
+    """include/loom_b200_comm.h: every NCCL entry point is bound (CUDA library only) and exported"""
+    text = open(os.path.join(REPO, "include", "loom_b200_comm.h")).read()
+    declared = sorted(set(re.findall(r"\bint (lb_comm_\w+)\(", text)))
+    assert declared == sorted("lb_" + n for n in _abi.COMM_SIGNATURES)
+    abi = _abi.load_cuda()
+    for name in declared:
+        assert hasattr(abi.lib, name), name
+
+
 def test_oracle_exports_same_abi(oracle_abi):
     for name in declared_symbols():
         assert hasattr(oracle_abi.lib, "lo_" + name), name

@@ -46,10 +46,10 @@ def test_library_override_is_loud(tmp_path):
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--ref-rows", "3000"], capture_output=True, text=True, timeout=600)
+                          "--rows", "4000", "--ref-rows", "1500"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "cells/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["config"]["workload"] == "C2"
+    assert line["config"]["workload"] == "C3" and line["config"]["ephemeral_kinds"] == 32

@@ -1,6 +1,8 @@
-"""N > 1 path: the row-sharded kind proposer with an all-reduce of the proposer tables.
-CPU: world_size 2 over gloo with the oracle as compute backend (host logic + exchange).
-GPU: world_size 2 over NCCL with libloomb200 (skipped with fewer than 2 devices)."""
+"""N > 1 path.
+CPU: world_size 2 over gloo with the oracle as compute backend -- the sharding logic (which rows / features / tasks a
+     rank takes, what is summed, what must come out) restated over torch.distributed in tests/dist_gloo.py.
+GPU: world_size 2 over NCCL through the library's own entry points (include/loom_b200_comm.h, loom_b200/dist.py):
+     two plain processes, no torch; skipped with fewer than 2 devices."""
 import os
 import subprocess
 import sys
@@ -16,7 +18,7 @@ sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests")
 import numpy as np
 import torch, torch.distributed as dist
 from loom_b200 import Engine, _abi, synth, sweep_actions
-from loom_b200.dist import sharded_kind_proposer_score
+from dist_gloo import sharded_kind_proposer_score
 backend = sys.argv[1]
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 if backend == "nccl":
@@ -89,11 +91,11 @@ dist.destroy_process_group()
 
 ACCUMULATE_WORKER = r'''
 import os, sys
-sys.path.insert(0, {repo!r})
+sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests"))
 import numpy as np
 import torch, torch.distributed as dist
 from loom_b200 import Engine, _abi, synth
-from loom_b200.dist import sharded_accumulate_rows
+from dist_gloo import sharded_accumulate_rows
 backend = sys.argv[1]
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 if backend == "nccl":
@@ -131,7 +133,7 @@ sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests")
 import numpy as np
 import torch, torch.distributed as dist
 from loom_b200 import Engine, _abi, synth
-from loom_b200.dist import sharded_hyper_run
+from dist_gloo import sharded_hyper_run
 from test_dpd import GRIDS
 backend = sys.argv[1]
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -169,6 +171,77 @@ dist.destroy_process_group()
 '''
 
 
+NATIVE_WORKER = r'''
+# two plain processes, NCCL through libloomb200's own entry points (no torch anywhere)
+import os, sys
+sys.path.insert(0, {repo!r}); sys.path.insert(0, os.path.join({repo!r}, "tests"))
+import numpy as np
+from loom_b200 import Engine, _abi, synth, sweep_actions, dist
+from test_dpd import GRIDS
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+abi = _abi.load_cuda()
+model, rows, truth = synth.generate(3000, [("bb", 3), ("dd16", 3), ("dd256", 1), ("dpd5", 2), ("gp", 3), ("nich", 3)], density=0.6, seed=13)
+K = model.n_kinds
+def engine(assigned=True):
+    e = Engine(abi, device=rank)
+    e.set_model(model); e.set_rows(rows)
+    if assigned:
+        for k in range(K):      # identical state on every rank
+            uniq, inv = np.unique(truth["assign"][k].astype(np.uint32), return_inverse=True)
+            e.set_groups(k, len(uniq)); e.set_assignments(k, inv.astype(np.uint32))
+        e.accumulate_rows()
+    return e
+e = engine()
+dist.init(e, rank, world, tag={tag!r})
+# --- row-sharded proposer: K4 on this rank's rows, all-reduce, K5 on this rank's features, all-gather
+e.init_featureless_kinds(4, seed=3)
+full = e.kind_proposer_score()                      # single-rank reference on the same device
+sharded, stats = dist.sharded_kind_proposer_score(e)
+err = np.abs(sharded.astype(np.float64) - full) / np.maximum(1.0, np.abs(full))
+assert err.max() <= 1e-6, err.max()
+assert stats["allreduce_bytes"] > 0 and stats["allgather_bytes"] > 0 and stats["row_end"] - stats["row_begin"] == 1500
+f2k, n = e.kind_run(8, seed=5)                       # same seed, same scores -> same structure on every rank
+chk = dist.max_over_ranks(e, np.concatenate([f2k, -f2k.astype(np.float64)]))
+assert np.array_equal(chk[:len(f2k)], f2k) and np.array_equal(-chk[len(f2k):], f2k)    # max == min == mine
+# --- task-sharded hyper kernel == hyper_run, bit for bit
+grids = dict(GRIDS, bb={{"alpha": [0.5, 2.0], "beta": [0.5, 2.0]}})
+ref, h = engine(), engine()
+dist.init(h, rank, world, tag={tag!r} + "h")
+ref.set_hyper_prior(grids); h.set_hyper_prior(grids)
+for seed in (1, 2):
+    ref.hyper_run(seed)
+    dist.sharded_hyper_run(h, seed)
+    (s0, a0, k0, t0), (s1, a1, k1, t1) = ref.get_hypers(), h.get_hypers()
+    for f in range(model.n_features):
+        assert [s0[f].hp[c] for c in range(4)] == [s1[f].hp[c] for c in range(4)], f
+    assert np.array_equal(a0, a1) and np.array_equal(k0, k1) and np.array_equal(t0, t1)
+    assert ref.score_data() == h.score_data()
+# --- kind-sharded sweep + publication of the kinds == the sweep of all kinds on one device
+acts = np.concatenate([sweep_actions(3000), sweep_actions(3000, add=True, remove=True)])
+one, sh = engine(False), engine(False)
+dist.init(sh, rank, world, tag={tag!r} + "s")
+one.cat_sweep(acts, seed=21)
+owner = np.arange(K) % world
+sh.cat_sweep(acts, seed=21, kind_mask=(owner == rank).astype(np.uint8))
+nbytes, ms = dist.sync_kinds(sh, owner)
+assert nbytes > 0
+for k in range(K):
+    assert np.array_equal(one.get_assignments(k), sh.get_assignments(k)), k
+    for a, b in zip(one.get_groups(k), sh.get_groups(k)):
+        assert np.array_equal(a, b), k
+    assert np.array_equal(one.score_rows(k, 0, 64), sh.score_rows(k, 0, 64))
+assert one.score_data() == sh.score_data()
+more = sweep_actions(3000, add=True, remove=True)    # and the chain goes on from the published state
+one.cat_sweep(more, seed=22, action_offset=len(acts)); sh.cat_sweep(more, seed=22, action_offset=len(acts))
+for k in range(K):
+    assert np.array_equal(one.get_assignments(k), sh.get_assignments(k)), k
+dist.barrier(e)
+print("rank %d ok: proposer err %.2e allreduce %.0f B %.3f ms, allgather %.0f B, sync_kinds %.0f B %.3f ms" % (
+    rank, err.max(), stats["allreduce_bytes"], stats["allreduce_ms"], stats["allgather_bytes"], nbytes, ms), flush=True)
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ok.%d" % rank), "w").write("1")
+'''
+
+
 def _run(backend, tmp_path, worker=None):
     script = tmp_path / "worker.py"
     script.write_text((worker or WORKER).format(repo=REPO))
@@ -184,25 +257,9 @@ def test_row_sharded_proposer_gloo_cpu(oracle_abi, tmp_path):
     _run("gloo", tmp_path)
 
 
-@pytest.mark.gpu
-def test_row_sharded_proposer_nccl(cuda_abi, tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    _run("nccl", tmp_path)
-
-
 def test_kind_sharded_sweep_gloo_cpu(oracle_abi, tmp_path):
     """cat sweep with kinds sharded over 2 ranks == the same sweep on one rank (no data-path collective)."""
     _run("gloo", tmp_path, KIND_SHARD_WORKER)
-
-
-@pytest.mark.gpu
-def test_kind_sharded_sweep_nccl(cuda_abi, tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    _run("nccl", tmp_path, KIND_SHARD_WORKER)
 
 
 def test_row_sharded_accumulate_gloo_cpu(oracle_abi, tmp_path):
@@ -210,7 +267,25 @@ def test_row_sharded_accumulate_gloo_cpu(oracle_abi, tmp_path):
     _run("gloo", tmp_path, ACCUMULATE_WORKER)
 
 
-
 def test_feature_sharded_hyper_gloo_cpu(oracle_abi, tmp_path):
     """HyperKernel::run with its tasks split over 2 ranks and the chosen hypers exchanged == hyper_run, bit for bit"""
     _run("gloo", tmp_path, HYPER_WORKER)
+
+
+@pytest.mark.gpu
+def test_native_nccl_sharding_two_gpus(cuda_abi, tmp_path):
+    """lb_comm_*: row-sharded proposer (all-reduce + all-gather), task-sharded hyper kernel, kind-sharded sweep with
+    the kinds published by broadcast -- each against the single-device result, on 2 GPUs, without torch."""
+    n_dev = int(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.count("GPU "))
+    if n_dev < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(NATIVE_WORKER.format(repo=REPO, tag="t%d" % os.getpid()))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(os.environ, RANK=str(r), WORLD_SIZE="2"),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    log_dir = os.path.join(REPO, "gpurun_out")
+    if os.path.isdir(log_dir):
+        open(os.path.join(log_dir, "native_nccl_test.log"), "w").write("\n".join(outs))
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
+    assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists()
