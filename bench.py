@@ -317,10 +317,16 @@ def inference_step(engines, acts, seeds, it, hyper=False, stats=None):
         stats["cat_s"] = stats.get("cat_s", 0.0) + t1 - t0
     moved = 0
     for c, e in enumerate(engines):
+        ta = time.perf_counter()
         e.kind_proposer_score(fetch=False)                       # K4 + K5
+        tb = time.perf_counter()
         _, n = e.kind_run(KIND_ITERATIONS, seed=int(seeds[c]) + 7)   # block Pitman-Yor + move_features
+        tc = time.perf_counter()
         e.init_featureless_kinds(EPHEMERAL, seed=int(seeds[c]) + 11)
         moved += n
+        if stats is not None:
+            for key, dt in (("kind_score_s", tb - ta), ("kind_run_s", tc - tb), ("kind_ephemeral_s", time.perf_counter() - tc)):
+                stats[key] = stats.get(key, 0.0) + dt
     if stats is not None:
         for e in engines:
             e.sync()
@@ -533,7 +539,7 @@ def main():
         return float(dist.max_over_ranks(e, [x])[0]) if world > 1 else x
 
     def seeds_for(it):
-        return np.array([1000 * (rank * S + c) + 17 * it + 3 for c in range(S)], np.uint64)
+        return np.array([1000 * (rank * S + c) + 17 * (it + 1) + 3 for c in range(S)], np.uint64)
 
     pass_acts = sweep_actions(R, add=True, remove=True)
     # ---- set-up (untimed): the greedy first pass of every chain (Loom::infer_single_pass) ----
@@ -629,7 +635,8 @@ def main():
             "in_step": {"value": world * S * F * K_all / (kind_ms * 1e-3) if kind_ms else None, "ms_per_step": kind_ms,
                         "note": "KindKernel::try_run of every local chain inside the timed step: K4 + K5 + %d block "
                                 "Pitman-Yor iterations (host) + move_features + new ephemeral kinds" % KIND_ITERATIONS}}
-    aux = {"phases_ms_per_step": {"cat_kernel": cat_ms, "kind_kernel": kind_ms, "hyper_kernel": hyper_ms},
+    aux = {"phases_ms_per_step": {"cat_kernel": cat_ms, "kind_kernel": kind_ms, "hyper_kernel": hyper_ms,
+                                  "kind_kernel_parts_rank0": {k_: 1e3 * v_ / args.steps for k_, v_ in phases.items() if k_.startswith("kind_") and k_ != "kind_s"}},
            "features_moved_per_step": moved / float(args.steps)}
     try:
         # ONE chain, identical on every rank (the generating partition), its proposal round sharded over the ranks

@@ -1080,6 +1080,21 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
     k_score_table<<<(int)std::max<uint64_t>(1, std::min<uint64_t>((tot + 255) / 256, (uint64_t)e->n_sm * 8)), 256, 0, e->stream>>>(
         e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_row_feat, n_rows, d_tab);
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    if (!lse) {
+        // K1t: a kind made of categorical / Bernoulli columns only can take the tensor-core contraction
+        // (lb_score_tc.cu).  LB_K1_TC = 1 always when applicable, 0 never, unset: when a feature has at most 32 values
+        // on average (the contraction pays for every VALUE of a column, the gather for every observed CELL).
+        const char *env = getenv("LB_K1_TC");
+        const int K_total = n_rows - 1;
+        const bool want = env ? atoi(env) != 0 : (nf > 0 && K_total <= 32 * nf);
+        if (want) {
+            const char *pl = getenv("LB_K1_TC_PLANES");
+            int used = 0;
+            LB_TRY(lb_launch_score_rows_tc(e, kid, b, en, d_tab, row_base.data(), K_total, d_out,
+                                           pl ? std::max(1, std::min(3, atoi(pl))) : 3, &used));
+            if (used) return 0;
+        }
+    }
     const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 4));
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};

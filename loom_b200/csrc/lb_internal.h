@@ -187,6 +187,8 @@ int lb_launch_sweep(Engine *e, const std::vector<int> &kind_ids, uint64_t n_acti
                     uint64_t offset, uint32_t *d_picks, float *d_scores, int stride);
 int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int G, float *d_acc, int first);
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse = 0);
+int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const float *d_tab, const int32_t *row_base,
+                            int K_total, float *d_out, int planes, int *used);   // lb_score_tc.cu
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
                              const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,

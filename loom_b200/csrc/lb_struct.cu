@@ -12,7 +12,9 @@
 //   hyper_run               HyperKernel::run (src/hyper_kernel.cc:195-235), grid Gibbs
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 #include "lb_internal.h"
 #include "lb_dpd_hyper.h"
@@ -548,34 +550,53 @@ extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t se
         LB_CUDA(cudaStreamSynchronize(e->stream));
     }
     const std::vector<float> &grid = e->hp[1];   // clustering grid [n][2]
-    for (int c = 0; c < count; ++c) {
-        const int kid = (int)e->kinds.size();
-        e->kinds.emplace_back();
-        KindHost &k = e->kinds.back();
-        k.alpha = e->kinds[0].alpha; k.d = e->kinds[0].d;
+    // Pitman-Yor seating of every assigned row, one sequential pass per ephemeral kind (src/kind_kernel.cc:159-189).
+    // The kinds are independent and every draw is keyed by (seed, row, kind), so they are seated side by side on the
+    // host threads; the arithmetic (and therefore every pick) is the single-threaded loop's.
+    const int first_kid = (int)e->kinds.size();
+    std::vector<std::vector<uint32_t>> picks(count), all_counts(count);
+    std::vector<std::pair<float, float>> py(count, {e->kinds[0].alpha, e->kinds[0].d});
+    for (int c = 0; c < count; ++c)
         if (!grid.empty()) {   // sample_clustering_prior (infer_grid.hpp:127-139)
             const int n = (int)grid.size() / 2;
-            const double u = (double)lb_uniform(seed, 3u, 0xFFFFFFFFFFFFFFFFull, (uint32_t)kid);
+            const double u = (double)lb_uniform(seed, 3u, 0xFFFFFFFFFFFFFFFFull, (uint32_t)(first_kid + c));
             int i = (int)(u * n);
             if (i >= n) i = n - 1;
-            k.alpha = grid[2 * i]; k.d = grid[2 * i + 1];
+            py[c] = {grid[2 * i], grid[2 * i + 1]};
         }
-        const double alpha = k.alpha, d = k.d;
-        std::vector<uint32_t> pick(e->R, LB_UNASSIGNED), counts;
-        std::vector<double> p;
+    auto seat = [&](int c) {
+        const int kid = first_kid + c;
+        const double alpha = py[c].first, d = py[c].second;
+        std::vector<uint32_t> &pick = picks[c], &counts = all_counts[c];
+        pick.assign(e->R, LB_UNASSIGNED);
+        std::vector<double> p(1, alpha);      // p[g] = counts[g] - d for g < m, p[m] = alpha + d m
         int m = 0;
         for (uint64_t r = 0; r < e->R; ++r) {
             if (a0[r] == LB_UNASSIGNED) continue;
-            p.resize(m + 1);
             double total = 0;
-            for (int g = 0; g < m; ++g) total += p[g] = counts[g] - d;
-            total += p[m] = alpha + d * m;
+            for (int g = 0; g <= m; ++g) total += p[g];
             const double u = (double)lb_uniform(seed, 3u, r, (uint32_t)kid);
             const int g = sample_from_likelihoods(u, p.data(), m + 1, total);
-            if (g == m) { counts.push_back(0); ++m; }
+            if (g == m) { counts.push_back(0); ++m; p.push_back(alpha + d * m); }
             counts[g]++;
+            p[g] = counts[g] - d;
             pick[r] = (uint32_t)g;
         }
+    };
+    {
+        const int n_thr = std::max(1, std::min<int>(count, (int)std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        std::atomic<int> next(0);
+        for (int t = 0; t < n_thr; ++t)
+            pool.emplace_back([&] { for (int c = next++; c < count; c = next++) seat(c); });
+        for (auto &t : pool) t.join();
+    }
+    for (int c = 0; c < count; ++c) {
+        e->kinds.emplace_back();
+        KindHost &k = e->kinds.back();
+        k.alpha = py[c].first; k.d = py[c].second;
+        const std::vector<uint32_t> &pick = picks[c], &counts = all_counts[c];
+        const int m = (int)counts.size();
         const int G = m + e->empty_group_count;
         LB_TRY(lb_kind_layout(e, k, std::vector<int>()));
         int cap = 256;

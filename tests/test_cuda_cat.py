@@ -250,6 +250,36 @@ def test_score_rows_parity(oracle_abi, cuda_abi, seed):
     assert worst <= SCORE_TOL, worst
 
 
+@pytest.mark.parametrize("types,rows_n,planes", [
+    ([("bb", 40)], 1000, 3),                                  # Bernoulli block: 80 operand columns, 2 K chunks
+    ([("bb", 7), ("dd16", 9), ("dpd5", 3)], 2777, 3),         # ragged tile, DPD ids from the wide columns
+    ([("dd16", 24), ("dd256", 3)], 1500, 3),                  # a DD-256 column spans 4 chunks of its own
+    ([("bb", 12), ("dd16", 12)], 1300, 2),                    # two planes (16 mantissa bits) still inside 1e-5
+])
+def test_score_rows_tensor_core_matches_oracle(oracle_abi, cuda_abi, monkeypatch, types, rows_n, planes):
+    """K1t (lb_score_tc.cu): one-hot x score-table contraction on tcgen05 with split precision == the float64
+    oracle within 1e-5 * max(1, |score|), and == the gather kernel to fp32 summation order"""
+    model, rows, _ = synth.generate(rows_n, types, density=0.6, seed=31, single_kind=len(types) == 1)
+    o, g = both(oracle_abi, cuda_abi, model, rows)
+    o.cat_sweep(sweep_actions(rows_n), seed=5)                # ~dozens of groups per kind
+    keeps = _load_state(o, g, model)
+    monkeypatch.setenv("LB_K1_TC_PLANES", str(planes))
+    for k in range(model.n_kinds):
+        so = o.score_rows(k).astype(np.float64)
+        so = np.concatenate([so[:, keeps[k]], so[:, [c for c in range(so.shape[1]) if c not in set(keeps[k])]]], axis=1)
+        monkeypatch.setenv("LB_K1_TC", "0")
+        gather = g.score_rows(k)
+        n0 = g.launch_count()[2]
+        monkeypatch.setenv("LB_K1_TC", "1")
+        tc = g.score_rows(k)
+        assert g.launch_count()[2] - n0 == 3                  # score table + operand table + ONE contraction launch
+        assert tc.shape == so.shape
+        assert rel_err(tc, so).max() <= SCORE_TOL, (k, rel_err(tc, so).max())
+        assert np.abs(tc.astype(np.float64) - gather).max() <= (2e-5 if planes == 3 else 2e-4) * max(1.0, np.abs(gather).max())
+        part = g.score_rows(k, 130, 391)                      # a row range that starts inside a tile
+        assert np.array_equal(part, tc[130:391])
+
+
 def test_score_rows_large_groups_float_accuracy(oracle_abi, cuda_abi):
     # groups holding ~1e5 rows: fp32 lgamma/log cancellation must not leak in
     model = Model([dict(type="gp", alpha=2.0, inv_beta=0.5), dict(type="nich", mu=0.0, kappa=1.0, sigmasq=1.0, nu=2.0),
