@@ -39,6 +39,7 @@ N > 1   : chains are independent (loom runs one process per sample) -> every ran
 builds) on the host cores: the same step on a bounded row sample (cpu_baseline.sample).
 """
 import argparse
+import concurrent.futures
 import ctypes
 import json
 import os
@@ -315,18 +316,27 @@ def inference_step(engines, acts, seeds, it, hyper=False, stats=None):
             e.sync()
         t1 = time.perf_counter()
         stats["cat_s"] = stats.get("cat_s", 0.0) + t1 - t0
-    moved = 0
-    for c, e in enumerate(engines):
+    # the chains' kind kernels run side by side (one host thread per chain, as loom runs one process per sample): one
+    # chain's block Pitman-Yor sampler / ephemeral-kind seating on the host overlaps another chain's K4 / K5 on the device
+    def kind_kernel(c):
+        e = engines[c]
         ta = time.perf_counter()
         e.kind_proposer_score(fetch=False)                       # K4 + K5
         tb = time.perf_counter()
         _, n = e.kind_run(KIND_ITERATIONS, seed=int(seeds[c]) + 7)   # block Pitman-Yor + move_features
         tc = time.perf_counter()
         e.init_featureless_kinds(EPHEMERAL, seed=int(seeds[c]) + 11)
-        moved += n
-        if stats is not None:
-            for key, dt in (("kind_score_s", tb - ta), ("kind_run_s", tc - tb), ("kind_ephemeral_s", time.perf_counter() - tc)):
-                stats[key] = stats.get(key, 0.0) + dt
+        return n, tb - ta, tc - tb, time.perf_counter() - tc
+
+    if len(engines) > 1:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(engines), 16)) as pool:
+            results = list(pool.map(kind_kernel, range(len(engines))))
+    else:
+        results = [kind_kernel(0)]
+    moved = sum(r[0] for r in results)
+    if stats is not None:
+        for key, i in (("kind_score_s", 1), ("kind_run_s", 2), ("kind_ephemeral_s", 3)):
+            stats[key] = stats.get(key, 0.0) + sum(r[i] for r in results) / len(results)     # mean per chain
     if stats is not None:
         for e in engines:
             e.sync()
@@ -636,7 +646,7 @@ def main():
                         "note": "KindKernel::try_run of every local chain inside the timed step: K4 + K5 + %d block "
                                 "Pitman-Yor iterations (host) + move_features + new ephemeral kinds" % KIND_ITERATIONS}}
     aux = {"phases_ms_per_step": {"cat_kernel": cat_ms, "kind_kernel": kind_ms, "hyper_kernel": hyper_ms,
-                                  "kind_kernel_parts_rank0": {k_: 1e3 * v_ / args.steps for k_, v_ in phases.items() if k_.startswith("kind_") and k_ != "kind_s"}},
+                                  "kind_kernel_parts_mean_per_chain_rank0": {k_: 1e3 * v_ / args.steps for k_, v_ in phases.items() if k_.startswith("kind_") and k_ != "kind_s"}},
            "features_moved_per_step": moved / float(args.steps)}
     try:
         # ONE chain, identical on every rank (the generating partition), its proposal round sharded over the ranks

@@ -685,6 +685,7 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
     struct Cost { SweepPair p; size_t cost; };
     std::vector<Cost> cls[3];                      // 0 narrow (1 warp), 1 wide (8 warps), 2 wider (16 warps)
     size_t smem[3] = {0, 0, 0};
+    bool catonly = true;                           // no GP / NICH column anywhere in the launch: the lean instantiation
     const int warps_of[3] = {1, 8, LB_SPEC_WIDER};
     const char *w16 = getenv("LB_SPEC_WIDE16");
     const bool use16 = !w16 || atoi(w16) != 0;
@@ -692,6 +693,10 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
         for (int kid : kind_ids[c]) {
             const KindHost &k = engines[c]->kinds[kid];
             const int nf = (int)k.fids.size();
+            for (int f : k.fids) {
+                const int t = engines[c]->specs[f].type;
+                catonly = catonly && (t == LB_BB || t == LB_DD || t == LB_DPD);
+            }
             const int w = nf >= SP_WIDER_NF && use16 ? 2 : (nf >= SP_WIDE_NF ? 1 : 0);
             if (nf > SW_PF * 32 * warps_of[w]) return 1;
             smem[w] = std::max(smem[w], (spec_smem_bytes(nf, k.Gcap, warps_of[w]) + 15) / 16 * 16);
@@ -719,13 +724,16 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join, cudaEventDisableTiming));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join3, cudaEventDisableTiming));
     }
+    if (const char *v = getenv("LB_SPEC_CATONLY")) catonly = catonly && atoi(v) != 0;      // A/B switch
+    auto kernel_of = [&](int w) {
+        if (w == 2) return catonly ? k_cat_sweep_spec<LB_SPEC_WIDER, true> : k_cat_sweep_spec<LB_SPEC_WIDER, false>;
+        if (w == 1) return catonly ? k_cat_sweep_spec<8, true> : k_cat_sweep_spec<8, false>;
+        return catonly ? k_cat_sweep_spec<1, true> : k_cat_sweep_spec<1, false>;
+    };
     // the opt-in is per device and cheap: set it at every launch (engines live on any device)
-    if (!cls[2].empty())
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<LB_SPEC_WIDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[2]));
-    if (!cls[1].empty())
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[1]));
-    if (!cls[0].empty())
-        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_spec<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem[0] * SP_CPB)));
+    for (int w = 0; w < 3; ++w)
+        if (!cls[w].empty())
+            LB_CUDA(cudaFuncSetAttribute(kernel_of(w), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(w ? smem[w] : smem[0] * SP_CPB)));
     LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
     LB_CUDA(cudaEventRecord(leader->ev_fork, leader->stream));
     // the longest-running class goes first on the leader's stream; the others fork off it and join back
@@ -738,9 +746,9 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
         cudaStream_t s = leader->stream;
         if (w != lead_cls) { s = side[n_side]; LB_CUDA(cudaStreamWaitEvent(s, leader->ev_fork, 0)); }
         const int np = (int)cls[w].size();
-        if (w == 2) k_cat_sweep_spec<LB_SPEC_WIDER><<<(unsigned)np, 32 * LB_SPEC_WIDER, smem[2], s>>>(d_chains, d_pairs + first[2], np, (int)smem[2]);
-        else if (w == 1) k_cat_sweep_spec<8><<<(unsigned)np, 256, smem[1], s>>>(d_chains, d_pairs + first[1], np, (int)smem[1]);
-        else k_cat_sweep_spec<1><<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
+        if (w == 2) kernel_of(2)<<<(unsigned)np, 32 * LB_SPEC_WIDER, smem[2], s>>>(d_chains, d_pairs + first[2], np, (int)smem[2]);
+        else if (w == 1) kernel_of(1)<<<(unsigned)np, 256, smem[1], s>>>(d_chains, d_pairs + first[1], np, (int)smem[1]);
+        else kernel_of(0)<<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
                  d_chains, d_pairs + first[0], np, (int)smem[0]);
         LB_CUDA(cudaGetLastError());
         if (w != lead_cls) { LB_CUDA(cudaEventRecord(joined[n_side], s)); ++n_side; }

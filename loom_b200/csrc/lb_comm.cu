@@ -1,8 +1,11 @@
 // lb_comm.cu -- NCCL collectives of libloomb200.so (include/loom_b200_comm.h): the row-sharded kind proposer and
 // the task-sharded hyper kernel.  One communicator per engine, every collective on the engine's stream.
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include "../../include/loom_b200_comm.h"
@@ -15,6 +18,60 @@ struct Comm {
     size_t tmp_cap = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// NCCL is bound at run time, privately (dlopen, RTLD_LOCAL), the first time a communicator is asked for: a process
+// that never shards (one GPU, the tests, loom_infer) does not load it at all, and a host program that brings its own
+// NCCL build (PyTorch bundles a newer one than the system's) keeps its symbols -- linking libnccl into this library
+// made `import torch` fail with an undefined ncclDevCommCreate once libloomb200 had been loaded first.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    void *handle = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+}  // namespace
+
+static int nccl_load() {
+    if (g_nccl.ok) return 0;
+    const char *names[] = {getenv("LOOM_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return lb_fail("NCCL not found (libnccl.so.2; LOOM_B200_NCCL overrides the path): %s", dlerror());
+    bool all = true;
+    auto bind = [&](auto &fn, const char *sym) {
+        fn = (std::remove_reference_t<decltype(fn)>)dlsym(g_nccl.handle, sym);
+        all = all && fn != nullptr;
+    };
+    bind(g_nccl.GetUniqueId, "ncclGetUniqueId"); bind(g_nccl.CommInitRank, "ncclCommInitRank");
+    bind(g_nccl.CommDestroy, "ncclCommDestroy"); bind(g_nccl.AllReduce, "ncclAllReduce");
+    bind(g_nccl.AllGather, "ncclAllGather"); bind(g_nccl.Broadcast, "ncclBroadcast");
+    bind(g_nccl.GroupStart, "ncclGroupStart"); bind(g_nccl.GroupEnd, "ncclGroupEnd");
+    bind(g_nccl.GetErrorString, "ncclGetErrorString");
+    if (!all) return lb_fail("the NCCL library lacks an entry point this layer needs");
+    g_nccl.ok = true;
+    return 0;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclBroadcast g_nccl.Broadcast
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
 
 #define LB_NCCL(expr)                                                                   \
     do {                                                                                \
@@ -49,6 +106,7 @@ void lb_release_comm(Engine *e) {
 
 extern "C" int lb_comm_unique_id(uint8_t *id_out) {
     static_assert(sizeof(ncclUniqueId) == LB_COMM_ID_BYTES, "ncclUniqueId size");
+    LB_TRY(nccl_load());
     ncclUniqueId id;
     LB_NCCL(ncclGetUniqueId(&id));
     memcpy(id_out, &id, sizeof id);
@@ -60,6 +118,7 @@ extern "C" int lb_comm_init(lb_handle h, const uint8_t *id_bytes, int32_t rank, 
     if (!e) return lb_fail("comm_init: null handle");
     if (world < 1 || rank < 0 || rank >= world) return lb_fail("comm_init: bad rank %d of %d", rank, world);
     LB_CUDA(cudaSetDevice(e->device));
+    LB_TRY(nccl_load());
     lb_release_comm(e);
     Comm *c = new Comm;
     c->rank = rank; c->world = world;

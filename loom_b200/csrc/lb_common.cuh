@@ -298,6 +298,71 @@ __device__ __forceinline__ void lb_update_cell(const FeatDev &f, const float *au
     }
 }
 
+// The same update, also handing back what it stored: in_new = the feature's first two integer rows at this group
+// after the update, c_new = its cached scorer entries (BB 2, GP 2, NICH 5; DD / DPD: [0] the value's entry, [1] the
+// shift entry).  The speculative sweep (lb_sweep_spec.cuh) scores the pending row's cell against these registers
+// instead of re-reading the column it just wrote (a second dependent L2 round trip).
+__device__ __forceinline__ void lb_update_cell_x(const FeatDev &f, const float *aux, uint32_t *in,
+                                                 double *fl, float *c, int st, uint32_t raw, int sign,
+                                                 uint32_t (&in_new)[2], float (&c_new)[5]) {
+    switch (f.type) {
+    case LB_BB: {
+        uint32_t h = in[0], t = in[st];
+        if (raw) { h += (uint32_t)sign; in[0] = h; } else { t += (uint32_t)sign; in[st] = t; }
+        lb_refresh_bb_v(f, h, t, c_new, 1);
+        c[0] = c_new[0]; c[st] = c_new[1];
+        in_new[0] = h; in_new[1] = t;
+        break;
+    }
+    case LB_DD:
+    case LB_DPD: {
+        const uint32_t n = in[(size_t)raw * st] + (uint32_t)sign;
+        const uint32_t tot = in[(size_t)f.dim * st] + (uint32_t)sign;
+        in[(size_t)raw * st] = n;
+        in[(size_t)f.dim * st] = tot;
+        c_new[0] = logf(f.a_scale * aux[f.aux_off + raw] + (float)n);
+        c_new[1] = logf(f.a_total + (float)tot);
+        c[(size_t)raw * st] = c_new[0];
+        c[(size_t)f.dim * st] = c_new[1];
+        in_new[0] = n; in_new[1] = tot;
+        break;
+    }
+    case LB_GP: {
+        const uint32_t n0 = in[0], s0 = in[st];
+        const double lp0 = fl[0];
+        const uint32_t n = n0 + (uint32_t)sign, sum = s0 + (uint32_t)(sign * (int64_t)raw);
+        in[0] = n;
+        in[st] = sum;
+        fl[0] = n ? lp0 + sign * (double)lb_log_factorial_d(raw) : 0.0;
+        lb_refresh_gp_v(f, n, sum, c_new, 1);
+        c[0] = c_new[0]; c[st] = c_new[1];
+        in_new[0] = n; in_new[1] = sum;
+        break;
+    }
+    case LB_NICH: {
+        const double x = (double)__uint_as_float(raw);
+        double n = (double)in[0], mean = fl[0], ctv = fl[st];
+        if (sign > 0) {
+            n += 1.0;
+            const double delta = x - mean;
+            mean += delta / n;
+            ctv += delta * (x - mean);
+        } else {
+            const double total = mean * n, delta = x - mean;
+            n -= 1.0;
+            if (n == 0.0) { mean = 0.0; ctv = 0.0; }
+            else { mean = (total - x) / n; ctv -= delta * (x - mean); }
+        }
+        in[0] = (uint32_t)n; fl[0] = mean; fl[st] = ctv;
+        lb_refresh_nich_v(f, (uint32_t)n, mean, ctv, c_new, 1);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) c[(size_t)q * st] = c_new[q];
+        in_new[0] = (uint32_t)n; in_new[1] = 0u;
+        break;
+    }
+    }
+}
+
 // log posterior-predictive of one cell for one group from the cached scorer.
 __device__ __forceinline__ float lb_score_cell(const FeatDev &f, const uint32_t *in, const float *c,
                                                int st, uint32_t raw, float cell_const) {

@@ -331,6 +331,7 @@ extern "C" void lb_destroy(lb_handle h) {
     dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
     if (e->d_score_aux) cudaFree(e->d_score_aux);
+    if (e->d_tc_aux) cudaFree(e->d_tc_aux);
     if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);

@@ -100,6 +100,8 @@ struct Engine {
     int d_fid_list_cap = 0;
     void *d_score_aux = nullptr;       // K1: GP feature index + predictive tables
     size_t score_aux_bytes = 0;
+    void *d_tc_aux = nullptr;          // K1t: producer records, chunk lists and the bf16 operand planes
+    size_t tc_aux_bytes = 0;
     int d_kind_ids_cap = 0;
 
     // hyper prior

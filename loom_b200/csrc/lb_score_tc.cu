@@ -9,7 +9,7 @@
 // (8 + 8 + 8 mantissa bits), one-hot entries are exactly 0 / 1, products accumulate in fp32 in TMEM, so the result
 // differs from the fp32 gather only in summation order.
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warps 0-3  thread = row of a 128-row tile.  Stage the row's cells (coalesced column reads), then for every
 //              64-wide K chunk write that chunk of the one-hot operand into a ring stage (canonical K-major
 //              no-swizzle core-matrix layout) and publish it (fence.proxy.async + mbarrier); later the epilogue:
@@ -17,6 +17,9 @@
 //              store coalesced.
 //   warp 4     one thread issues tcgen05.mma (M = 128, N = groups padded to 16, K = 16 per instruction):
 //              planes x 4 per chunk; tcgen05.commit frees the ring stage / publishes the accumulator.
+//   warps 6-9  cell loaders: the NEXT tile's cells (one 32-bit load = 4 rows of a column, TC_LD_UNROLL columns in
+//              flight per lane) become operand column indices in a double-buffered shared array, so the row block
+//              streams from HBM under the current tile's MMAs and epilogue.
 //   warp 5     one thread streams the table chunks (all planes of a chunk are contiguous: k_score_table_tc writes
 //              them in the operand layout) with ONE bulk TMA copy per stage (cp.async.bulk + mbarrier complete_tx);
 //              the warp also owns the TMEM allocation.
@@ -39,7 +42,8 @@ namespace {
 constexpr int TC_ROWS = 128;            // M
 constexpr int TC_KC = 64;               // K chunk per ring stage (4 MMAs of K = 16)
 constexpr int TC_A_BYTES = TC_ROWS * TC_KC * 2;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;         // 4 producer / epilogue warps, MMA, table loader, 4 cell loaders
+constexpr int TC_LD_UNROLL = 8;
 
 struct TcFeat {                         // what the producers need per feature
     int32_t col, is_wide, fid, row_base;
@@ -117,8 +121,9 @@ __global__ void k_score_table_tc(const float *tab, int st, int G, int K_total, i
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16_t *chunk_lo, const uint16_t *chunk_hi,
                 const __nv_bfloat16 *btab, RowsDev rows, uint64_t b, uint64_t en, int n_empty, int K_total, int n_pad,
-                int planes, int n_stages, int tmem_cols, float *out) {
+                int planes, int n_stages, int tmem_cols, int n8, float *out) {
     extern __shared__ __align__(128) unsigned char tc_smem[];
+    const uint32_t acc_stride = (uint32_t)(n_pad + 31) & ~31u;     // TMEM columns of one accumulator stage
     const KindDev &kd = kinds[kid];
     const int nf = kd.nf, G = kd.G;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,12 +135,14 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
     unsigned char *sB = sA + (size_t)n_stages * TC_A_BYTES;
     float *s_tr = (float *)(sB + (size_t)n_stages * b_stage_bytes);
     uint16_t *s_cell = (uint16_t *)(s_tr + 4 * 32 * 32);
-    float *s_prior = (float *)(s_cell + (size_t)((nf + 1) & ~1) * TC_ROWS);
+    const int cell_stride = ((nf + 1) & ~1) * TC_ROWS;          // u16 entries of one cell buffer
+    float *s_prior = (float *)(s_cell + 2 * (size_t)cell_stride);
     TcFeat *s_feat = (TcFeat *)(s_prior + n_pad);
     uint64_t *bars = (uint64_t *)(((uintptr_t)(s_feat + nf) + 15) & ~(uintptr_t)15);
     uint64_t *fullA = bars, *fullB = bars + n_stages, *empty = bars + 2 * n_stages;
     uint64_t *tmem_full = bars + 3 * n_stages, *tmem_empty = tmem_full + 2;
-    uint32_t *s_tmem = (uint32_t *)(tmem_empty + 2);
+    uint64_t *cells_full = tmem_empty + 2, *cells_empty = cells_full + 2;
+    uint32_t *s_tmem = (uint32_t *)(cells_empty + 2);
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -143,7 +150,10 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
             mbar_init(smem_u32(&fullB[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), 4);
+            mbar_init(smem_u32(&cells_full[s]), 4); mbar_init(smem_u32(&cells_empty[s]), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -176,9 +186,9 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
             float *tr = s_tr + warp * 32 * 32;
             for (int cb = 0; cb < n_pad; cb += 32) {
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * (uint32_t)n_pad + (uint32_t)cb, v);
+                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_stride + (uint32_t)cb, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tr[lane * 32 + (i ^ lane)] = __uint_as_float(v[i]) + s_prior[cb + i];
+                for (int i = 0; i < 32; ++i) tr[lane * 32 + (i ^ lane)] = __uint_as_float(v[i]) + (cb + i < n_pad ? s_prior[cb + i] : 0.f);
                 __syncwarp();
                 const int g = cb + lane;
                 if (g < G) {
@@ -196,18 +206,8 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
         uint32_t it = 0;
         uint64_t prev_tile = 0;
         for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint64_t r = b + tile * TC_ROWS + row;
-            // the row's cells as K indices + 1 (0 = unobserved): consecutive threads read consecutive rows of a column
-            for (int j = 0; j < nf; ++j) {
-                const TcFeat f = s_feat[j];
-                uint32_t k = 0;
-                if (r < en && ((rows.mask[(uint64_t)f.fid * rows.W + (r >> 5)] >> (r & 31)) & 1u)) {
-                    const uint32_t raw = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r]
-                                                   : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
-                    k = (uint32_t)f.row_base + raw;           // table row; K index = k - 1
-                }
-                s_cell[j * TC_ROWS + row] = (uint16_t)k;
-            }
+            const uint16_t *cell = s_cell + (size_t)(it & 1u) * cell_stride;     // filled by the loader warps
+            mbar_wait(smem_u32(&cells_full[it & 1u]), (it >> 1) & 1u);
             for (int c = 0; c < n_chunks; ++c, ++q) {
                 const uint32_t s = q % (uint32_t)n_stages, ph = (q / (uint32_t)n_stages) & 1u;
                 mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
@@ -216,7 +216,7 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
                 for (int kc = 0; kc < 8; ++kc) *(uint4 *)(a + kc * 2048) = make_uint4(0u, 0u, 0u, 0u);
                 const int jlo = chunk_lo[c], jhi = chunk_hi[c];
                 for (int j = jlo; j <= jhi; ++j) {
-                    const uint32_t k = s_cell[j * TC_ROWS + row];
+                    const uint32_t k = cell[j * TC_ROWS + row];
                     if (k && (int)((k - 1u) >> 6) == c) {
                         const uint32_t kk = (k - 1u) & 63u;
                         *(uint16_t *)(a + (kk >> 3) * 2048 + (kk & 7u) * 2) = (uint16_t)0x3F80;      // bf16 1.0
@@ -226,6 +226,8 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&fullA[s]));
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&cells_empty[it & 1u]));      // the loaders may overwrite this buffer
             if (it > 0) epilogue(prev_tile, it - 1);
             prev_tile = tile;
         }
@@ -240,7 +242,7 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
                 const uint32_t as = it & 1u;
                 mbar_wait(smem_u32(&tmem_empty[as]), ((it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * (uint32_t)n_pad;
+                const uint32_t d_tmem = tmem_base + as * acc_stride;
                 for (int c = 0; c < n_chunks; ++c, ++q) {
                     const uint32_t s = q % (uint32_t)n_stages, ph = (q / (uint32_t)n_stages) & 1u;
                     mbar_wait(smem_u32(&fullA[s]), ph);
@@ -259,6 +261,72 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
                 }
                 tc_commit(smem_u32(&tmem_full[as]));         // accumulator complete
             }
+        }
+    } else if (warp >= 6) {
+        // ================= cell loaders: rows of the next tile -> operand column indices =================
+        // lane q of loader warp lw takes rows 4q .. 4q+3 of the columns lw, lw + 4, ...: one 32-bit load is 4 rows of
+        // an 8-bit column, one 128-bit load 4 rows of a 32-bit column; TC_LD_UNROLL columns are requested at once.
+        const int lw = warp - 6;
+        const bool aligned = (rows.R & 3ull) == 0;
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u;
+            mbar_wait(smem_u32(&cells_empty[buf]), ((it >> 1) & 1u) ^ 1u);
+            uint16_t *cell = s_cell + (size_t)buf * cell_stride;
+            const uint64_t r4 = b + tile * TC_ROWS + 4 * (uint64_t)lane;          // first of this lane's 4 rows
+            // whole tile inside the block and 4-row groups aligned: branch-free vector loads, TC_LD_UNROLL columns in flight
+            const bool fast = aligned && ((b & 3ull) == 0) && b + (tile + 1) * TC_ROWS <= en;
+            auto store4 = [&](int j, uint32_t bits, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+                const uint32_t base = (uint32_t)s_feat[j].row_base;
+                const uint32_t k0 = bits & 1u ? base + v0 : 0u, k1 = bits & 2u ? base + v1 : 0u;
+                const uint32_t k2 = bits & 4u ? base + v2 : 0u, k3 = bits & 8u ? base + v3 : 0u;
+                *(uint2 *)(cell + j * TC_ROWS + 4 * lane) = make_uint2(k0 | (k1 << 16), k2 | (k3 << 16));
+            };
+            if (fast) {
+                const uint64_t mword = r4 >> 5;
+                const uint32_t mshift = (uint32_t)(r4 & 31);
+                for (int j0 = lw; j0 < n8; j0 += 4 * TC_LD_UNROLL) {          // 8-bit columns: one word = 4 rows
+                    uint32_t w[TC_LD_UNROLL], m[TC_LD_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < TC_LD_UNROLL; ++u) {
+                        const TcFeat f = s_feat[min(j0 + 4 * u, n8 - 1)];
+                        m[u] = rows.mask[(uint64_t)f.fid * rows.W + mword];
+                        w[u] = *(const uint32_t *)(rows.cat8 + (uint64_t)f.col * rows.R + r4);
+                    }
+#pragma unroll
+                    for (int u = 0; u < TC_LD_UNROLL; ++u)
+                        if (j0 + 4 * u < n8)
+                            store4(j0 + 4 * u, (m[u] >> mshift) & 15u, w[u] & 255u, (w[u] >> 8) & 255u, (w[u] >> 16) & 255u, w[u] >> 24);
+                }
+                for (int j0 = n8 + lw; j0 < nf; j0 += 4 * (TC_LD_UNROLL / 2)) {   // 32-bit columns: one uint4 = 4 rows
+                    uint4 w[TC_LD_UNROLL / 2];
+                    uint32_t m[TC_LD_UNROLL / 2];
+#pragma unroll
+                    for (int u = 0; u < TC_LD_UNROLL / 2; ++u) {
+                        const TcFeat f = s_feat[min(j0 + 4 * u, nf - 1)];
+                        m[u] = rows.mask[(uint64_t)f.fid * rows.W + mword];
+                        w[u] = *(const uint4 *)(rows.wide + (uint64_t)f.col * rows.R + r4);
+                    }
+#pragma unroll
+                    for (int u = 0; u < TC_LD_UNROLL / 2; ++u)
+                        if (j0 + 4 * u < nf) store4(j0 + 4 * u, (m[u] >> mshift) & 15u, w[u].x, w[u].y, w[u].z, w[u].w);
+                }
+            } else {
+                for (int j = lw; j < nf; j += 4) {
+                    const TcFeat f = s_feat[j];
+                    uint32_t bits = 0u, v[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t r = r4 + i;
+                        if (r >= en) continue;
+                        bits |= ((rows.mask[(uint64_t)f.fid * rows.W + (r >> 5)] >> (r & 31)) & 1u) << i;
+                        v[i] = f.is_wide ? rows.wide[(uint64_t)f.col * rows.R + r] : (uint32_t)rows.cat8[(uint64_t)f.col * rows.R + r];
+                    }
+                    store4(j, bits, v[0], v[1], v[2], v[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&cells_full[buf]));
         }
     } else {
         // ================= table loader: one bulk TMA copy per ring stage =================
@@ -298,20 +366,22 @@ int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const f
     const int n_pad = std::max(16, (k.G + 15) / 16 * 16);
     const int n_chunks = (K_total + TC_KC - 1) / TC_KC;
     const size_t b_stage = (size_t)planes * n_pad * TC_KC * 2;
-    const size_t fixed = 4 * 32 * 32 * 4 + (size_t)((nf + 1) & ~1) * TC_ROWS * 2 + (size_t)n_pad * 4 + sizeof(TcFeat) * (size_t)nf + 16 +
-                         8 * (3 * 8 + 4) + 16 + 128;
+    const size_t fixed = 4 * 32 * 32 * 4 + 2 * (size_t)((nf + 1) & ~1) * TC_ROWS * 2 + (size_t)n_pad * 4 + sizeof(TcFeat) * (size_t)nf + 16 +
+                         8 * (3 * 8 + 8) + 16 + 128;
     int n_stages = 0;
     for (int s = 6; s >= 2; --s)
         if (fixed + (size_t)s * (TC_A_BYTES + b_stage) <= 220 * 1024) { n_stages = s; break; }
     if (!n_stages) return 0;
     n_stages = std::min(n_stages, std::max(2, n_chunks));
     int tmem_cols = 32;
-    while (tmem_cols < 2 * n_pad) tmem_cols *= 2;
+    while (tmem_cols < 2 * ((n_pad + 31) & ~31)) tmem_cols *= 2;
     if (tmem_cols > 512) return 0;
     const size_t smem = fixed + (size_t)n_stages * (TC_A_BYTES + b_stage);
 
     // per-feature producer records and the features each K chunk overlaps
     std::vector<TcFeat> tf(nf);
+    int n8 = 0;                                  // the kind's 8-bit columns come first (feature ids ascend)
+    for (int f : k.fids) n8 += f < e->F8;
     std::vector<uint16_t> lo(n_chunks, 0xFFFF), hi(n_chunks, 0);
     for (int j = 0; j < nf; ++j) {
         const int f = k.fids[j];
@@ -330,8 +400,14 @@ int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const f
     const size_t o_hi = o_lo + (2 * (size_t)n_chunks + 255) / 256 * 256;
     const size_t o_tab = o_hi + (2 * (size_t)n_chunks + 255) / 256 * 256;
     const size_t need = o_tab + (size_t)n_chunks * b_stage + 256;
-    LB_TRY(lb_ensure_scratch(e, need));
-    char *sc = (char *)e->d_scratch;
+    if (need > e->tc_aux_bytes) {          // (the caller's output lives in d_scratch)
+        if (e->d_tc_aux) cudaFree(e->d_tc_aux);
+        e->d_tc_aux = nullptr;
+        e->tc_aux_bytes = 0;
+        LB_CUDA(cudaMalloc(&e->d_tc_aux, need + need / 4));
+        e->tc_aux_bytes = need + need / 4;
+    }
+    char *sc = (char *)e->d_tc_aux;
     LB_CUDA(cudaMemcpyAsync(sc, tf.data(), sizeof(TcFeat) * (size_t)nf, cudaMemcpyHostToDevice, e->stream));
     LB_CUDA(cudaMemcpyAsync(sc + o_lo, lo.data(), 2 * (size_t)n_chunks, cudaMemcpyHostToDevice, e->stream));
     LB_CUDA(cudaMemcpyAsync(sc + o_hi, hi.data(), 2 * (size_t)n_chunks, cudaMemcpyHostToDevice, e->stream));
@@ -348,7 +424,7 @@ int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const f
     RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
     k_score_rows_tc<<<grid, TC_THREADS, smem, e->stream>>>(e->d_kinds, kid, (const TcFeat *)sc, (const uint16_t *)(sc + o_lo),
                                                          (const uint16_t *)(sc + o_hi), d_btab, rows, b, en, e->empty_group_count,
-                                                         K_total, n_pad, planes, n_stages, tmem_cols, d_out);
+                                                         K_total, n_pad, planes, n_stages, tmem_cols, n8, d_out);
     LB_CUDA(cudaGetLastError());
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
     *used = 1;

@@ -569,17 +569,24 @@ extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t se
         const double alpha = py[c].first, d = py[c].second;
         std::vector<uint32_t> &pick = picks[c], &counts = all_counts[c];
         pick.assign(e->R, LB_UNASSIGNED);
-        std::vector<double> p(1, alpha);      // p[g] = counts[g] - d for g < m, p[m] = alpha + d m
         int m = 0;
+        uint64_t seated = 0;
         for (uint64_t r = 0; r < e->R; ++r) {
             if (a0[r] == LB_UNASSIGNED) continue;
-            double total = 0;
-            for (int g = 0; g <= m; ++g) total += p[g];
+            // weights counts[g] - d for the occupied tables, alpha + d m for a new one: they sum to seated + alpha in
+            // closed form, so the scan stops at the pick (the oracle does the same arithmetic)
+            const double total = (double)seated + alpha;
             const double u = (double)lb_uniform(seed, 3u, r, (uint32_t)kid);
-            const int g = sample_from_likelihoods(u, p.data(), m + 1, total);
-            if (g == m) { counts.push_back(0); ++m; p.push_back(alpha + d * m); }
+            const double t = u * total;
+            double c = 0;
+            int g = m;
+            for (int i = 0; i < m; ++i) {
+                c += (double)counts[i] - d;
+                if (c > t) { g = i; break; }
+            }
+            if (g == m) { counts.push_back(0); ++m; }
             counts[g]++;
-            p[g] = counts[g] - d;
+            ++seated;
             pick[r] = (uint32_t)g;
         }
     };

@@ -36,7 +36,34 @@ constexpr int SP_MAXW = 16;
 #define LB_SPEC_WIDER 16          // warps of the widest CTA class (kinds with >= SP_WIDER_NF features)
 #endif
 
+#ifndef LB_CO_GATHER
+#define LB_CO_GATHER 1
+#endif
+#ifndef LB_CO_COLUMN
+#define LB_CO_COLUMN 1
+#endif
+#ifndef LB_CO_PHASEB
+#define LB_CO_PHASEB 1
+#endif
+#ifndef LB_CO_ADDGROUP
+#define LB_CO_ADDGROUP 1
+#endif
+constexpr int SP_UNROLL = 8;      // cells whose table rows a gathering warp requests before it uses the first
+
 struct SweepPair { int32_t chain, kid; };
+
+template <int PER> __device__ __forceinline__ void sp_ldv(const float *p, float (&o)[PER]);
+template <> __device__ __forceinline__ void sp_ldv<1>(const float *p, float (&o)[1]) { o[0] = *p; }
+template <> __device__ __forceinline__ void sp_ldv<2>(const float *p, float (&o)[2]) {
+    const float2 t = *(const float2 *)p; o[0] = t.x; o[1] = t.y;
+}
+template <> __device__ __forceinline__ void sp_ldv<4>(const float *p, float (&o)[4]) {
+    const float4 t = *(const float4 *)p; o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+template <int PER> __device__ __forceinline__ void sp_stv(float *p, const float (&v)[PER]);
+template <> __device__ __forceinline__ void sp_stv<1>(float *p, const float (&v)[1]) { *p = v[0]; }
+template <> __device__ __forceinline__ void sp_stv<2>(float *p, const float (&v)[2]) { *(float2 *)p = make_float2(v[0], v[1]); }
+template <> __device__ __forceinline__ void sp_stv<4>(float *p, const float (&v)[4]) { *(float4 *)p = make_float4(v[0], v[1], v[2], v[3]); }
 
 struct SpecSmem {
     int G, stop, pick, flag;
@@ -109,7 +136,10 @@ __device__ __forceinline__ int warp_sample_regs(const float *feat, const float *
     return __shfl_sync(FULL, pick, src);
 }
 
-template <int W>
+// CATONLY: every kind of the launch holds Bernoulli / categorical columns only (C3): the gamma-Poisson and
+// normal-inverse-chi-squared paths (lgamma, float64 moments) are compiled out, which takes the hot loop from ~280 KB
+// of SASS to a fraction of that -- it has to stream through the instruction cache once per row action.
+template <int W, bool CATONLY = false>
 __global__ void __launch_bounds__(W == 1 ? 32 * SP_CPB : W * 32, 1)
 k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, int smem_per_pair) {
     constexpr int T = W * 32;
@@ -150,7 +180,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
     float *s_av = (float *)(s_ioff + SP_RING * nf);      // [SP_RING][nf] the value's concentration a_v
     uint32_t *s_raw = (uint32_t *)(s_av + SP_RING * nf); // [SP_RING][nf]
     uint32_t *s_obs = s_raw + SP_RING * nf;              // [SP_RING][nf]
-    float *s_part = (float *)(s_obs + SP_RING * nf);     // [W][st] per-warp partial feature scores of a gather
+    float *s_part = (float *)(((uintptr_t)(s_obs + SP_RING * nf) + 15) & ~(uintptr_t)15);   // [W][st] per-warp partial feature scores of a gather (vector stores)
     float *s_a = s_part + W * st;                        // [st] feature scores of the ADD being sampled / pending
     float *s_b = s_a + st;                               // [st]
     float *s_score = s_b + st;                           // [st] scratch of the large-G sampler
@@ -330,42 +360,68 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
     sweep_sync<W>();
 
     // feature part of the scores of a compiled row (ring slot) against the tables as they stand: per-warp
-    // partial sums into s_part, 64 groups a trip (lane = group, two per lane)
-    auto gather = [&](int slot, int G) {
-        if (warp < W0) return;
+    // partial sums into s_part.  A lane owns PER consecutive groups (the sampler's ownership), so one table row is ONE
+    // vector load per warp for up to 128 groups, and SP_UNROLL cells' value and shift rows are all requested before
+    // the first is used: a gather is one L2 round trip per SP_UNROLL cells of the warp, not one per cell.
+    // (CATONLY: the GP / NICH loops get bounds the compiler can see are empty -- `if constexpr` inside the generic
+    // lambda miscompiled the categorical loop above it with nvcc 12.9)
+    const int gp_end = CATONLY ? off[CL_GP] : off[CL_GP + 1];
+    const int nich_begin = CATONLY ? 0 : off[CL_NICH], nich_end = CATONLY ? 0 : off[CL_NICH + 1];
+    auto gather_per = [&](int slot, int G, auto per_tag) {
+        constexpr int PER = decltype(per_tag)::value;
         const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
-        for (int g0 = 0; g0 < G; g0 += 64) {
-            float acc0 = 0.f, acc1 = 0.f;
-            const float *cg = cache + g0 + lane;
-#pragma unroll 4
-            for (int k = off[CL_CAT]; k < off[CL_CAT + 1]; ++k) {     // branch-free: unobserved cells read the zero row
-                const float *cv = cg + rv[k], *cs = cg + rs[k];
-                acc0 += cv[0] - cs[0];
-                acc1 += cv[32] - cs[32];
+        for (int g0 = 0; g0 < G; g0 += 32 * PER) {
+            const int gl = g0 + PER * lane;
+            if (gl >= st) continue;                        // beyond the tables' columns (G > 128 only)
+            float acc[PER];
+#pragma unroll
+            for (int q = 0; q < PER; ++q) acc[q] = 0.f;
+            const float *cg = cache + gl;
+            const int cend = off[CL_CAT + 1];
+            for (int k0 = off[CL_CAT]; k0 < cend; k0 += SP_UNROLL) {   // branch-free: absent cells read the zero row
+                float v[SP_UNROLL][PER], sh[SP_UNROLL][PER];
+#pragma unroll
+                for (int j = 0; j < SP_UNROLL; ++j) {
+                    const int k = k0 + j;
+                    const uint32_t vo = k < cend ? rv[k] : zoff, so = k < cend ? rs[k] : zoff;
+                    sp_ldv<PER>(cg + vo, v[j]);
+                    sp_ldv<PER>(cg + so, sh[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < SP_UNROLL; ++j)
+#pragma unroll
+                    for (int q = 0; q < PER; ++q) acc[q] += v[j][q] - sh[j][q];
             }
-            for (int k = off[CL_GP]; k < off[CL_GP + 1]; ++k) {
+            for (int k = off[CL_GP]; k < gp_end; ++k) {
                 if (!ro[k]) continue;
                 const FeatDev &f = s_feat[k];
                 const uint32_t raw = rr[k];
                 const float lf = lb_log_factorial(raw), x = (float)raw;
-                const uint32_t *sum = ints + (size_t)(f.int_row + 1) * st + g0 + lane;
+                const uint32_t *sum = ints + (size_t)(f.int_row + 1) * st + gl;
                 const float *c0 = cg + (size_t)f.cache_row * st;
-                acc0 += lb_lgamma_diff_int(f.hp[0] + (float)sum[0], raw) - lf + c0[0] + x * c0[st];
-                acc1 += lb_lgamma_diff_int(f.hp[0] + (float)sum[32], raw) - lf + c0[32] + x * c0[st + 32];
+#pragma unroll
+                for (int q = 0; q < PER; ++q)
+                    acc[q] += lb_lgamma_diff_int(f.hp[0] + (float)sum[q], raw) - lf + c0[q] + x * c0[st + q];
             }
-            for (int k = off[CL_NICH]; k < off[CL_NICH + 1]; ++k) {
+            for (int k = nich_begin; k < nich_end; ++k) {
                 if (!ro[k]) continue;
                 const FeatDev &f = s_feat[k];
                 const float x = __uint_as_float(rr[k]);
                 const float *c = cg + (size_t)f.cache_row * st;
-                const float dx0 = (x - c[3 * (size_t)st]) - c[4 * (size_t)st];
-                const float dx1 = (x - c[3 * (size_t)st + 32]) - c[4 * (size_t)st + 32];
-                acc0 += c[0] - c[st] * log1pf(c[2 * (size_t)st] * dx0 * dx0);
-                acc1 += c[32] - c[st + 32] * log1pf(c[2 * (size_t)st + 32] * dx1 * dx1);
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const float dx = (x - c[3 * (size_t)st + q]) - c[4 * (size_t)st + q];
+                    acc[q] += c[q] - c[st + q] * log1pf(c[2 * (size_t)st + q] * dx * dx);
+                }
             }
-            s_part[warp * st + g0 + lane] = acc0;
-            s_part[warp * st + g0 + lane + 32] = acc1;
+            sp_stv<PER>(s_part + warp * st + gl, acc);
         }
+    };
+    auto gather = [&](int slot, int G) {
+        if (warp < W0) return;
+        if (G <= 32) gather_per(slot, G, std::integral_constant<int, 1>());
+        else if (G <= 64) gather_per(slot, G, std::integral_constant<int, 2>());
+        else gather_per(slot, G, std::integral_constant<int, 4>());
     };
     auto reduce_parts = [&](float *dst, int G) {
         const int G64 = min(st, (G + 63) & ~63);
@@ -381,7 +437,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
         float part = 0.f;
         for (int k = off[CL_CAT] + lane; k < off[CL_CAT + 1]; k += 32) part += cache[rv[k] + col] - cache[rs[k] + col];
-        for (int k = off[CL_GP] + lane; k < off[N_CLASS]; k += 32) {
+        for (int k = off[CL_GP] + lane; k < (CATONLY ? off[CL_GP] : off[N_CLASS]); k += 32) {
             if (!ro[k]) continue;
             const FeatDev &f = s_feat[k];
             const uint32_t raw = rr[k];
@@ -392,12 +448,12 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         if (lane == 0) ss->ovr[warp] = part;
     };
     // warp 0, after a barrier: pending[col] = sum of the per-warp column parts (one lane, W - W0 independent loads)
-    auto apply_column = [&](float *pending, int col) {
+    auto apply_column = [&](float *pending, int col, bool add) {
         if (tid == 0) {
             float v = 0.f;
 #pragma unroll
             for (int w = W0; w < W; ++w) v += ss->ovr[w];
-            pending[col] = v;
+            pending[col] = add ? pending[col] + v : v;
         }
         if (warp == 0) __syncwarp();
     };
@@ -511,34 +567,71 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         if (!is_remove) SP_TICK(1);
 
         // ---- phase B: apply the row to column g; bring the pending ADD's scores up to date ----
+        // The pending row's score at column g changes by what THIS update changes: for every feature both rows
+        // observe, the old entries of column g (requested together with the counts the update needs, one round trip)
+        // against the new ones, which the update holds in registers.  Nothing is re-read after the stores.
         commit_begin((int)((i + SP_AHEAD) % SP_RING));
         if (do_gather) { reduce_parts(s_next, G); next_idx = p; }
         const bool pending = next_idx != ~0ull;
         const int nslot = (int)(next_idx % SP_RING);
+        const bool patch = pending && !(flag && is_remove);
         {
             const int sign = is_remove ? -1 : +1;
             const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *ri = s_ioff + slot * nf;
             const uint32_t *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
             const float *ra = s_av + slot * nf;
+            const uint32_t *pv = s_voff + nslot * nf, *pr = s_raw + nslot * nf, *po = s_obs + nslot * nf;
+            float delta = 0.f;
             for (int k = off[CL_CAT] + lane; k < off[N_CLASS]; k += 32) {
                 if (!ro[k]) continue;
+                const bool both = patch && po[k];
                 const uint32_t so = rs[k];
                 if (so != zoff) {
                     // DD / DPD: Group::add_value / remove_value on the two count rows + their cached scorer entries
                     const uint32_t io = ri[k] + (uint32_t)g, no = s_Noff[k] + (uint32_t)g;
-                    const uint32_t n = ints[io] + (uint32_t)sign, tot = ints[no] + (uint32_t)sign;
+                    const uint32_t n0 = ints[io], t0 = ints[no];
+                    float old_s = 0.f, pend_v = 0.f;
+                    const bool same = both && pv[k] == rv[k];
+                    if (both) old_s = cache[so + g];                    // same round trip as the counts
+                    if (same) pend_v = cache[rv[k] + g];
+                    const uint32_t n = n0 + (uint32_t)sign, tot = t0 + (uint32_t)sign;
+                    const float new_v = logf(ra[k] + (float)n), new_s = logf(s_A[k] + (float)tot);
                     ints[io] = n;
                     ints[no] = tot;
-                    cache[rv[k] + g] = logf(ra[k] + (float)n);
-                    cache[so + g] = logf(s_A[k] + (float)tot);
+                    cache[rv[k] + g] = new_v;
+                    cache[so + g] = new_s;
+                    if (both) delta += (same ? new_v - pend_v : 0.f) - (new_s - old_s);
+                } else if constexpr (CATONLY && LB_CO_PHASEB) {
+                    // Bernoulli: heads / tails and the two cached log-probabilities of this group
+                    const FeatDev &f = s_feat[k];
+                    uint32_t *in = ints + (size_t)f.int_row * st + g;
+                    float *c = cache + (size_t)f.cache_row * st + g;
+                    uint32_t h = in[0], t = in[st];
+                    float old = 0.f;
+                    if (both) old = c[pr[k] ? 0 : st];
+                    if (rr[k]) { h += (uint32_t)sign; in[0] = h; } else { t += (uint32_t)sign; in[st] = t; }
+                    float c_new[2];
+                    lb_refresh_bb_v(f, h, t, c_new, 1);
+                    c[0] = c_new[0]; c[st] = c_new[1];
+                    if (both) delta += c_new[pr[k] ? 0 : 1] - old;
                 } else {
                     const FeatDev &f = s_feat[k];
-                    lb_update_cell(f, aux, ints + (size_t)f.int_row * st + g, flts + (size_t)f.flt_row * st + g,
-                                   cache + (size_t)f.cache_row * st + g, st, rr[k], sign);
+                    const uint32_t praw = pr[k];
+                    const float lf = both && f.type == LB_GP ? lb_log_factorial(praw) : 0.f;
+                    uint32_t *in = ints + (size_t)f.int_row * st + g;
+                    float *c = cache + (size_t)f.cache_row * st + g;
+                    float old = 0.f;
+                    if (both) old = lb_score_cell(f, in, c, st, praw, lf);
+                    uint32_t in_new[2];
+                    float c_new[5];
+                    lb_update_cell_x(f, aux, in, flts + (size_t)f.flt_row * st + g, c, st, rr[k], sign, in_new, c_new);
+                    if (both) delta += lb_score_cell(f, in_new, c_new, 1, praw, lf) - old;
                 }
             }
-            __syncwarp();
-            if (pending && !(flag && is_remove)) column_part(nslot, g);
+            if (patch) {
+                delta = warp_sum_f(delta);
+                if (lane == 0) ss->ovr[warp] = delta;
+            }
         }
         commit_end((int)((i + SP_AHEAD) % SP_RING));
         if (warp == 0) {
@@ -561,7 +654,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         SP_TICK(is_remove ? 6 : 2);
         sweep_sync<W>();   // (B) updates visible to the next gather; column parts in ss->ovr
         if (!is_remove) SP_TICK(3);
-        if (pending && !(flag && is_remove)) apply_column(s_next, g);
+        if (patch) apply_column(s_next, g, true);
 
         if (flag) {
             if (!is_remove) {
@@ -572,8 +665,16 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 sweep_sync<W>();
                 for (int row = tid; row < n_cache_rows; row += T) {
                     const FeatDev f = feats[kind_feats[kd.feat_begin + cache_row_feat[row]]];
-                    lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
-                                   cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
+                    if constexpr (CATONLY && LB_CO_ADDGROUP) {       // a fresh group: every count is zero
+                        const int local = row - f.cache_row;
+                        float v;
+                        if (f.type == LB_BB) v = logf((local ? f.hp[1] : f.hp[0]) / (f.hp[0] + f.hp[1]));
+                        else v = logf(local < f.dim ? f.a_scale * aux[f.aux_off + local] : f.a_total);
+                        cache[(size_t)row * st + ng] = v;
+                    } else {
+                        lb_refresh_row(f, aux, ints + (size_t)f.int_row * st + ng, flts + (size_t)f.flt_row * st + ng,
+                                       cache + (size_t)f.cache_row * st + ng, st, row - f.cache_row);
+                    }
                 }
                 if (tid == 0) {
                     s_counts[ng] = 0u;
@@ -591,7 +692,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 if (pending) {   // the pending ADD sees one more column
                     column_part(nslot, ng);
                     sweep_sync<W>();
-                    apply_column(s_next, ng);
+                    apply_column(s_next, ng, false);
                 }
                 sweep_sync<W>();
             } else {
@@ -651,5 +752,5 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
 }
 
 static size_t spec_smem_bytes(int nf, int Gcap, int warps) {
-    return 768 + (size_t)nf * (sizeof(FeatDev) + 12 + 24 * SP_RING + 4) + (size_t)Gcap * 4 * (warps + 6) + 64;
+    return 768 + (size_t)nf * (sizeof(FeatDev) + 12 + 24 * SP_RING + 4) + (size_t)Gcap * 4 * (warps + 6) + 64 + 16;
 }

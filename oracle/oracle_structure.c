@@ -284,6 +284,7 @@ int lo_init_featureless_kinds(lb_handle h, int32_t count, uint64_t seed) {
         uint32_t *counts = NULL;
         double *p = NULL;
         int m = 0, cap = 0;
+        uint64_t seated = 0;
         const kind_t *k0 = &e->kinds[0];
         for (uint64_t r = 0; r < e->R; ++r) {
             pick[r] = LB_UNASSIGNED;
@@ -293,13 +294,20 @@ int lo_init_featureless_kinds(lb_handle h, int32_t count, uint64_t seed) {
                 counts = realloc(counts, 4u * (size_t)cap);
                 p = realloc(p, 8u * (size_t)cap);
             }
-            double total = 0;
-            for (int g = 0; g < m; ++g) total += p[g] = counts[g] - d;
-            total += p[m] = alpha + d * m;
+            /* weights counts[g] - d for the occupied tables and alpha + d m for a new one; their sum is the number of
+             * seated rows + alpha in closed form, so the scan stops at the pick instead of summing all m weights first */
+            const double total = (double)seated + alpha;
             const double u = lo_uniform(seed, 3, r, (uint32_t)kid);
-            const int g = om_sample_from_likelihoods(u, p, m + 1, total);
+            const double t = u * total;
+            double c = 0;
+            int g = m;                              /* nothing reached: the new table (its weight is always > 0) */
+            for (int i = 0; i < m; ++i) {
+                c += (double)counts[i] - d;
+                if (c > t) { g = i; break; }
+            }
             if (g == m) counts[m++] = 0;
             counts[g]++;
+            ++seated;
             pick[r] = (uint32_t)g;
         }
         const int G = m + e->empty_group_count;

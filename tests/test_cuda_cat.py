@@ -84,6 +84,30 @@ def test_sweep_matches_oracle_by_replay(oracle_abi, cuda_abi, monkeypatch, kerne
     assert g.score_data() == pytest.approx(o.score_data(), rel=1e-6)
 
 
+@pytest.mark.parametrize("types,rows_n", [
+    ([("bb", 1)], 5),                                                   # the smallest posterior-enum case
+    ([("bb", 5), ("dd16", 4), ("dpd7", 2)], 700),                       # narrow kinds: one warp per (chain, kind)
+    ([("bb", 30), ("dd16", 40), ("dd256", 10)], 1200),                  # 8- and 16-warp CTAs
+])
+def test_sweep_categorical_only_instantiation_replays(oracle_abi, cuda_abi, monkeypatch, types, rows_n):
+    """K3s compiled without the GP / NICH paths (launches whose kinds hold Bernoulli / categorical columns only, C3):
+    every pick replays on the oracle, final state bit-exact; and it equals the general instantiation's sweep"""
+    monkeypatch.setenv("LB_SWEEP_KERNEL", "spec")
+    model, rows, _ = synth.generate(rows_n, types, density=0.7, seed=9, single_kind=len(types) == 1)
+    acts = np.concatenate([sweep_actions(rows_n)] + [sweep_actions(rows_n, add=True, remove=True)] * 3)
+    o, g = both(oracle_abi, cuda_abi, model, rows)
+    picks, scores = g.cat_sweep(acts, seed=11, debug=True, debug_stride=64)
+    bad, err = replay(oracle_abi, o, acts, 11, picks, scores, 64)
+    assert bad == 0 and err <= SCORE_TOL, (bad, err)
+    assert_same_state(o, g, model)
+    monkeypatch.setenv("LB_SPEC_CATONLY", "0")
+    g2 = Engine(cuda_abi)
+    g2.set_model(model)
+    g2.set_rows(rows)
+    picks2, _ = g2.cat_sweep(acts, seed=11, debug=True)
+    assert np.array_equal(picks, picks2)
+
+
 @pytest.mark.parametrize("warps", [1, 2, 4, 8])
 def test_sweep_every_cta_width_and_multi_chain(oracle_abi, cuda_abi, monkeypatch, warps):
     """1/2/4/8 warps per (chain, kind): each width replays exactly on the oracle, and the

@@ -113,23 +113,8 @@ def test_score_error_per_feature_type(oracle_abi, cuda_abi):
             assert entry["moment_max_rel_err"] <= 1e-9, (t, entry)
 
 
-# ------------------------------------------------------------------------------------------ row-sharded accumulate over NCCL
-@pytest.mark.gpu
-def test_row_sharded_accumulate_nccl(cuda_abi, tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import test_dist
-    test_dist._run("nccl", tmp_path, test_dist.ACCUMULATE_WORKER)
-
-
-@pytest.mark.gpu
-def test_feature_sharded_hyper_nccl(cuda_abi, tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import test_dist
-    test_dist._run("nccl", tmp_path, test_dist.HYPER_WORKER)
+# (the 2-GPU NCCL cases live in tests/test_dist.py::test_native_nccl_sharding_two_gpus: the library's own lb_comm_* entry
+# points, no torch)
 
 
 @pytest.mark.gpu
