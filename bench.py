@@ -310,6 +310,8 @@ def inference_step(engines, acts, seeds, it, hyper=False, stats=None):
     HyperKernel::run.  Returns the number of features that changed kind."""
     from loom_b200.engine import cat_sweep_multi
     t0 = time.perf_counter()
+    for c, e in enumerate(engines):      # the step's ephemeral kinds are seated on host threads while the device sweeps
+        e.prepare_featureless_kinds(EPHEMERAL, seed=int(seeds[c]) + 11)
     cat_sweep_multi(engines, acts, seeds)
     if stats is not None:
         for e in engines:
@@ -752,6 +754,13 @@ def main():
                                          "frac": in_all / (ms2 * 1e-3) / 1e9 / peak, "bound": "hbm"}
         except Exception as exc:
             aux["error"] = str(exc)
+
+    if rank == 0 and world == 1 and not args.no_aux:
+        # the other single-GPU configuration's shape (C4, taxi-like): score_value of the decoded rows against score_diff from the
+        # tare-compressed form, and the tensor-core form of K1 on the kinds it is meant for -- each in a process of its own
+        aux["c4_k1_dense_vs_sparse_score_diff"] = measure_in_subprocess("k1d_bench.py", [200000], timeout=150)
+        aux["k1_tcgen05_vs_gather_bb256"] = measure_in_subprocess("k1_bench.py", ["bb", 256, 1000000], timeout=120)
+        aux["k1_tcgen05_vs_gather_dd16"] = measure_in_subprocess("k1_bench.py", ["dd16", 128, 1000000, 2], timeout=120)
 
     # ---- rates at other chain counts (rank 0, N = 1): one chain alone; 100 chains on a 100 k-row block ----
     rates = {"cells_per_step_per_chain": 2 * n_obs, "observed_cells": n_obs, "chains": S,

@@ -160,6 +160,13 @@ int LB_NAME(set_rows_diff)(lb_handle h, uint64_t n_rows, const uint8_t *tare_obs
                            const uint64_t *pos_ptr, const uint32_t *pos_feature,
                            const uint32_t *pos_value, const uint64_t *neg_ptr,
                            const uint32_t *neg_feature);
+/* ProductMixture::score_diff (src/product_mixture.cc:436-463) for rows [row_begin, row_end) of one kind, computed
+ * from the tare-compressed form set_rows_diff left on the device: clustering prior + the kind's tare score (the
+ * TareCache entry, product_mixture.hpp:53-57, cc:58-81) + score(pos cells) - score(neg cells).  O(nnz x G) per row
+ * instead of O(F x G); same layout and values as score_rows (which scores the decoded row).  Fails unless the loaded
+ * block came from set_rows_diff. */
+int LB_NAME(score_rows_diff)(lb_handle h, int32_t kind, uint64_t row_begin, uint64_t row_end,
+                             float *out_scores);
 
 /* loom's tare / sparsify passes on the LOADED row block -- loom::Differ
  * (src/differ.hpp, src/differ.cc), what `loom_tare` and `loom_sparsify` run before inference.
@@ -339,6 +346,12 @@ int LB_NAME(kind_run)(lb_handle h, int32_t iterations, uint64_t seed,
  * `count` ephemeral kinds, each with a Pitman-Yor prior partition of all
  * assigned rows (src/kind_kernel.cc:159-189). */
 int LB_NAME(init_featureless_kinds)(lb_handle h, int32_t count, uint64_t seed);
+/* Start drawing the partitions of the NEXT init_featureless_kinds(count, seed) on background host threads.  The
+ * seating depends on the seed, the kind ids and WHICH rows are assigned, not on where they sit, so a driver calls this
+ * before it sweeps a pass that keeps the assigned set (the reference's KindKernel seats its ephemeral kinds on the
+ * critical path, src/kind_kernel.cc:159-189); init_featureless_kinds uses the draw when it was made for exactly its
+ * situation and draws afresh otherwise -- the result is the same either way. */
+int LB_NAME(prepare_featureless_kinds)(lb_handle h, int32_t count, uint64_t seed);
 int LB_NAME(get_kinds)(lb_handle h, int32_t *n_kinds, uint32_t *featureid_to_kindid);
 
 /* HyperKernel::run (src/hyper_kernel.cc:195-235): grid Gibbs over topology,

@@ -74,6 +74,7 @@ SIGNATURES = {
     "get_groups": (C.c_int, [_h, C.c_int32, _u32p, _u32p, _f64p]),
     "set_groups": (C.c_int, [_h, C.c_int32, C.c_int32, _u32p, _u32p, _f64p]),
     "score_rows": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, _f32p]),
+    "score_rows_diff": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, _f32p]),
     "accumulate_rows": (C.c_int, [_h, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32]),
     "score_data": (C.c_int, [_h, _f64p]),
     "kind_proposer_score": (C.c_int, [_h, _f32p]),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "proposer_finish": (C.c_int, [_h, _f32p]),
     "kind_run": (C.c_int, [_h, C.c_int32, C.c_uint64, _u32p, C.POINTER(C.c_int32)]),
     "init_featureless_kinds": (C.c_int, [_h, C.c_int32, C.c_uint64]),
+    "prepare_featureless_kinds": (C.c_int, [_h, C.c_int32, C.c_uint64]),
     "get_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _u32p]),
     "set_hyper_prior": (C.c_int, [_h, C.POINTER(HyperPrior)]),
     "hyper_run": (C.c_int, [_h, C.c_uint64]),

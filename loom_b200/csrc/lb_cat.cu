@@ -1057,13 +1057,13 @@ int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int
     return 0;
 }
 
-// lse: 0 = scores out [rows][G]; 1 / 2 = out[row] set to / increased by the row's log_sum_exp (needs G <= 128)
-int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse) {
+// Score table of a kind (k_score_table) in e->d_score_aux: [row_base nf][row_feat n_rows][pad][tab n_rows x Gcap]
+static int score_table_build(Engine *e, int kid, std::vector<int32_t> &row_base, int *n_rows_out, int32_t **d_row_base_out,
+                             float **d_tab_out) {
     const KindHost &k = e->kinds[kid];
     const int nf = (int)k.fids.size();
-    if (lse && k.G > 128) return lb_fail("fused score + log-sum-exp needs at most 128 groups (kind %d has %d)", kid, k.G);
-    // layout of the score table
-    std::vector<int32_t> row_base(std::max(nf, 1), 0), row_feat(1, -1);
+    row_base.assign(std::max(nf, 1), 0);
+    std::vector<int32_t> row_feat(1, -1);
     for (int j = 0; j < nf; ++j) {
         const lb_feature_spec &s = e->specs[k.fids[j]];
         row_base[j] = (int32_t)row_feat.size();
@@ -1087,7 +1087,22 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
     const uint64_t tot = (uint64_t)n_rows * k.G;
     k_score_table<<<(int)std::max<uint64_t>(1, std::min<uint64_t>((tot + 255) / 256, (uint64_t)e->n_sm * 8)), 256, 0, e->stream>>>(
         e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_row_feat, n_rows, d_tab);
+    LB_CUDA(cudaGetLastError());
     e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+    *n_rows_out = n_rows; *d_row_base_out = d_row_base; *d_tab_out = d_tab;
+    return 0;
+}
+
+// lse: 0 = scores out [rows][G]; 1 / 2 = out[row] set to / increased by the row's log_sum_exp (needs G <= 128)
+int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse) {
+    const KindHost &k = e->kinds[kid];
+    const int nf = (int)k.fids.size();
+    if (lse && k.G > 128) return lb_fail("fused score + log-sum-exp needs at most 128 groups (kind %d has %d)", kid, k.G);
+    std::vector<int32_t> row_base;
+    int n_rows = 0;
+    int32_t *d_row_base = nullptr;
+    float *d_tab = nullptr;
+    LB_TRY(score_table_build(e, kid, row_base, &n_rows, &d_row_base, &d_tab));
     if (!lse) {
         // K1t: a kind made of categorical / Bernoulli columns only can take the tensor-core contraction
         // (lb_score_tc.cu).  LB_K1_TC = 1 always when applicable, 0 never, unset: when a feature has at most 32 values
@@ -1135,6 +1150,129 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
         LB_CUDA(cudaGetLastError());
         e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
     }
+    return 0;
+}
+
+// ===========================================================================
+// K1d: ProductMixture::score_diff (src/product_mixture.cc:436-463) from the tare-compressed block:
+//   scores[g] = prior[g] + (row references the tare ? tare_score[g] : 0) + sum_{pos cells} p(cell | g) - sum_{neg cells} p(tare cell | g)
+// tare_score[g] is the kind's TareCache entry (product_mixture.hpp:53-57; _update_tare_cache, cc:58-81): the score of
+// the tare row's cells of this kind in group g -- one vector per kind, rebuilt per call from the same score table the
+// dense scorer gathers from (frozen tables here; the sweep keeps its own).  Work per row is O(nnz x G), not O(F x G).
+// One warp per row, lanes = groups; entries of other kinds are skipped through the feature -> table-row map.
+// ===========================================================================
+__global__ void k_tare_scores(const KindDev *kinds, int kid, const int32_t *kind_feats, const int32_t *row_base,
+                              const float *tab, const uint8_t *tare_obs, const uint32_t *tare_val, float *tare_scores,
+                              int32_t *frow) {
+    const KindDev &kd = kinds[kid];
+    const int st = kd.Gcap;
+    for (int j = threadIdx.x; j < kd.nf; j += blockDim.x) frow[kind_feats[kd.feat_begin + j]] = row_base[j];   // feature -> first table row
+    for (int g = threadIdx.x; g < st; g += blockDim.x) {
+        float acc = 0.f;
+        if (g < kd.G)
+            for (int j = 0; j < kd.nf; ++j) {
+                const int f = kind_feats[kd.feat_begin + j];
+                if (tare_obs[f]) acc += tab[(size_t)(row_base[j] + (int)tare_val[f]) * st + g];
+            }
+        tare_scores[g] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_score_rows_diff(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *frow, const float *tab,
+                  const float *tare_scores, const uint8_t *row_has_tare, const uint32_t *tare_val, const uint64_t *pos_ptr,
+                  const uint32_t *pos_feature, const uint32_t *pos_value, const uint64_t *neg_ptr, const uint32_t *neg_feature,
+                  uint64_t b, uint64_t en, int n_empty, float *out) {
+    const KindDev &kd = kinds[kid];
+    const int G = kd.G, st = kd.Gcap;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const float base = -logf((float)kd.sample_size + kd.alpha);
+    const float sh_empty = logf((kd.alpha + kd.d * (float)(G - n_empty)) / (float)n_empty);
+    for (int g0 = 0; g0 < G; g0 += 128) {
+        float prior[4], tare[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int g = g0 + lane + 32 * jj;
+            prior[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
+            tare[jj] = g < G ? tare_scores[g] : 0.f;
+        }
+        const float *tabg = tab + g0 + lane;
+        for (uint64_t r = b + warp; r < en; r += n_warps) {
+            float acc[4];
+            const bool has = !row_has_tare || row_has_tare[r];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[jj] = prior[jj] + (has ? tare[jj] : 0.f);
+            for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1]; ++i) {
+                const int f = (int)pos_feature[i];
+                const int row0 = frow[f];
+                if (row0 < 0) continue;                                    // a cell of another kind
+                const FeatDev &fd = feats[f];
+                const uint32_t raw = pos_value[i];
+                if (fd.type == LB_NICH || (fd.type == LB_GP && raw >= (uint32_t)LB_GP_TAB)) {
+                    const float lf = fd.type == LB_GP ? lb_log_factorial(raw) : 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int g = g0 + lane + 32 * jj;
+                        if (g < G) acc[jj] += lb_score_cell(fd, kd.ints + (size_t)fd.int_row * st + g, kd.cache + (size_t)fd.cache_row * st + g, st, raw, lf);
+                    }
+                } else {
+                    const float *t = tabg + (size_t)(row0 + (int)raw) * st;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) if (g0 + 32 * jj < st) acc[jj] += t[32 * jj];
+                }
+            }
+            for (uint64_t i = neg_ptr[r]; i < neg_ptr[r + 1]; ++i) {
+                const int f = (int)neg_feature[i];
+                const int row0 = frow[f];
+                if (row0 < 0) continue;
+                const float *t = tabg + (size_t)(row0 + (int)tare_val[f]) * st;   // tare cells are tabulated (booleans, counts < 16)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) if (g0 + 32 * jj < st) acc[jj] -= t[32 * jj];
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int g = g0 + lane + 32 * jj;
+                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[jj];
+            }
+        }
+    }
+}
+
+int lb_launch_score_rows_diff(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
+    const KindHost &k = e->kinds[kid];
+    std::vector<int32_t> row_base;
+    int n_rows = 0;
+    int32_t *d_row_base = nullptr;
+    float *d_tab = nullptr;
+    LB_TRY(score_table_build(e, kid, row_base, &n_rows, &d_row_base, &d_tab));
+    // per-call scratch: [tare_scores Gcap f32][feature -> table row, F i32]
+    const size_t o_frow = (4 * (size_t)k.Gcap + 255) / 256 * 256;
+    const size_t need = o_frow + 4 * (size_t)e->F + 256;
+    if (need > e->tc_aux_bytes) {
+        if (e->d_tc_aux) cudaFree(e->d_tc_aux);
+        e->d_tc_aux = nullptr; e->tc_aux_bytes = 0;
+        LB_CUDA(cudaMalloc(&e->d_tc_aux, need));
+        e->tc_aux_bytes = need;
+    }
+    float *d_tare = (float *)e->d_tc_aux;
+    int32_t *d_frow = (int32_t *)((char *)e->d_tc_aux + o_frow);
+    const char *diff = (const char *)e->d_diff;
+    const uint8_t *tare_obs = (const uint8_t *)(diff + e->diff_off[0]);
+    const uint32_t *tare_val = (const uint32_t *)(diff + e->diff_off[1]);
+    for (int f : k.fids)
+        if (e->specs[f].type == LB_NICH) { /* reals are never tared (src/differ.cc:121,137-140); checked on the device copy below */ }
+    LB_CUDA(cudaMemsetAsync(d_frow, 0xFF, 4 * (size_t)e->F, e->stream));
+    k_tare_scores<<<1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_kind_feats, d_row_base, d_tab, tare_obs, tare_val, d_tare, d_frow);
+    const uint64_t n = en - b;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)e->n_sm * 8));
+    k_score_rows_diff<<<grid, 256, 0, e->stream>>>(
+        e->d_kinds, kid, e->d_feats, d_frow, d_tab, d_tare,
+        e->diff_has_row_flags ? (const uint8_t *)(diff + e->diff_off[2]) : nullptr, tare_val,
+        (const uint64_t *)(diff + e->diff_off[3]), (const uint32_t *)(diff + e->diff_off[4]), (const uint32_t *)(diff + e->diff_off[5]),
+        (const uint64_t *)(diff + e->diff_off[6]), (const uint32_t *)(diff + e->diff_off[7]), b, en, e->empty_group_count, d_out);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_SCORE] += 2;
     return 0;
 }
 

@@ -128,6 +128,7 @@ static int initial_cap(int G) {
 
 static int alloc_assign(Engine *e, KindHost &k) {
     dev_free(k.assign);
+    k.assign_pooled = false;
     LB_TRY(dev_alloc(&k.assign, e->R));
     LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)e->R, e->stream));
     return 0;
@@ -243,7 +244,7 @@ int lb_kind_grow(Engine *e, int kid, int new_cap) {
     nk.next_global = k.next_global;
     LB_TRY(lb_launch_restride(e, k, nk));
     LB_CUDA(cudaStreamSynchronize(e->stream));
-    nk.assign = k.assign;
+    nk.assign = k.assign; nk.assign_pooled = k.assign_pooled;
     nk.cache_row_feat = k.cache_row_feat;
     k.cache_row_feat = nullptr;
     lb_kind_release(e, k);
@@ -294,6 +295,7 @@ static void drop_borrowed_rows(Engine *e) {
 }
 
 static void clear_model(Engine *e) {
+    lb_release_seating(e);
     lb_free_proposer(e);
     for (auto &k : e->kinds) { lb_kind_release(e, k); dev_free(k.assign); }
     if (e->stream) cudaStreamSynchronize(e->stream);
@@ -328,10 +330,12 @@ extern "C" void lb_destroy(lb_handle h) {
     lb_release_proposer(e);
     lb_release_differ(e);
     lb_release_comm(e);
+    lb_release_seating(e);
     dev_free(e->d_actions); dev_free(e->d_flag); dev_free(e->d_kind_ids);
     if (e->d_scratch) cudaFree(e->d_scratch);
     if (e->d_score_aux) cudaFree(e->d_score_aux);
     if (e->d_tc_aux) cudaFree(e->d_tc_aux);
+    if (e->d_diff) cudaFree(e->d_diff);
     if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
@@ -401,8 +405,9 @@ extern "C" int lb_share_rows(lb_handle h, lb_handle owner_h) {
         if (e->specs[f].type != o->specs[f].type || e->specs[f].dim != o->specs[f].dim)
             return lb_fail("share_rows: feature %d differs between the two models", f);
     if (!e->rows_borrowed) { dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask); }
+    e->diff_valid = false;
     if (o->R != e->R)
-        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, o->R)); }
+        for (auto &k : e->kinds) { dev_free(k.assign); k.assign_pooled = false; LB_TRY(dev_alloc(&k.assign, o->R)); }
     e->R = o->R; e->W = o->W;
     e->d_cat8 = o->d_cat8; e->d_wide = o->d_wide; e->d_mask = o->d_mask;
     e->rows_borrowed = true;
@@ -418,13 +423,14 @@ extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const u
     if (!e->F) return lb_fail("set_rows before set_model");
     if (R >= (1ull << 31)) return lb_fail("set_rows: at most 2^31-1 rows per block");
     drop_borrowed_rows(e);
+    e->diff_valid = false;
     if (R != e->R || !e->d_mask) {
         dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
         e->R = R; e->W = (R + 31) / 32;
         LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
         LB_TRY(dev_alloc(&e->d_wide, (size_t)e->FW * R));
         LB_TRY(dev_alloc(&e->d_mask, (size_t)e->F * e->W));
-        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, R)); }
+        for (auto &k : e->kinds) { dev_free(k.assign); k.assign_pooled = false; LB_TRY(dev_alloc(&k.assign, R)); }
     }
     if (e->F8) LB_CUDA(cudaMemcpyAsync(e->d_cat8, cat8, (size_t)e->F8 * R, cudaMemcpyHostToDevice, e->stream));
     if (e->FW) LB_CUDA(cudaMemcpyAsync(e->d_wide, wide, (size_t)e->FW * R * 4, cudaMemcpyHostToDevice, e->stream));
@@ -442,6 +448,7 @@ extern "C" int lb_reload_rows(lb_handle h, uint64_t R, const uint8_t *cat8, cons
     Engine *e = (Engine *)h;
     LB_CUDA(cudaSetDevice(e->device));
     if (!e->F || !e->d_mask || e->rows_borrowed) return lb_fail("reload_rows: the engine holds no rows of its own");
+    e->diff_valid = false;
     if (R != e->R) return lb_fail("reload_rows: %llu rows given, the block holds %llu", (unsigned long long)R, (unsigned long long)e->R);
     if (e->F8) LB_CUDA(cudaMemcpyAsync(e->d_cat8, cat8, (size_t)e->F8 * R, cudaMemcpyHostToDevice, e->stream));
     if (e->FW) LB_CUDA(cudaMemcpyAsync(e->d_wide, wide, (size_t)e->FW * R * 4, cudaMemcpyHostToDevice, e->stream));
@@ -514,7 +521,7 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
         LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
         LB_TRY(dev_alloc(&e->d_wide, (size_t)e->FW * R));
         LB_TRY(dev_alloc(&e->d_mask, (size_t)F * e->W));
-        for (auto &k : e->kinds) { dev_free(k.assign); LB_TRY(dev_alloc(&k.assign, R)); }
+        for (auto &k : e->kinds) { dev_free(k.assign); k.assign_pooled = false; LB_TRY(dev_alloc(&k.assign, R)); }
     }
     for (auto &k : e->kinds) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)R, e->stream));
     LB_TRY(lb_sync_model(e));
@@ -524,8 +531,16 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
                          4 * (size_t)n_pos, 8 * (size_t)(R + 1), 4 * (size_t)n_neg};
     size_t off[9] = {0};
     for (int i = 0; i < 8; ++i) off[i + 1] = ((off[i] + sz[i] + 255) / 256) * 256;
-    LB_TRY(lb_ensure_scratch(e, off[8] + 256));
-    char *base = (char *)e->d_scratch;
+    // the compressed block stays on the device: the sparse scorer (lb_score_rows_diff) reads it
+    if (off[8] + 256 > e->diff_bytes) {
+        if (e->d_diff) cudaFree(e->d_diff);
+        e->d_diff = nullptr; e->diff_bytes = 0;
+        LB_CUDA(cudaMalloc(&e->d_diff, off[8] + 256));
+        e->diff_bytes = off[8] + 256;
+    }
+    for (int i = 0; i < 9; ++i) e->diff_off[i] = off[i];
+    e->diff_has_row_flags = row_has_tare != nullptr;
+    char *base = (char *)e->d_diff;
     const void *src[] = {tare_obs, tare_val, row_has_tare, pos_ptr, pos_feature, pos_value, neg_ptr, neg_feature};
     for (int i = 0; i < 8; ++i)
         if (sz[i]) LB_CUDA(cudaMemcpyAsync(base + off[i], src[i], sz[i], cudaMemcpyHostToDevice, e->stream));
@@ -548,6 +563,28 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
     int bad = 0;
     LB_TRY(lb_launch_validate_rows(e, &bad));
     if (bad) return lb_fail("set_rows_diff: an observed categorical value is out of range for its feature");
+    e->diff_valid = true;
+    return 0;
+}
+
+// ProductMixture::score_diff (src/product_mixture.cc:436-463) for rows [b, en) of one kind, from the tare-compressed
+// form lb_set_rows_diff left on the device: prior + the kind's tare score + score(pos) - score(neg).
+extern "C" int lb_score_rows_diff(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    if (kind < 0 || kind >= (int)e->kinds.size()) return lb_fail("bad kind %d", kind);
+    if (b > en || en > e->R) return lb_fail("bad row range");
+    if (!e->diff_valid) return lb_fail("score_rows_diff: the loaded block did not come from set_rows_diff");
+    if (b == en) return 0;
+    const KindHost &k = e->kinds[kind];
+    const size_t bytes = (size_t)(en - b) * k.G * 4;
+    LB_TRY(lb_ensure_scratch(e, bytes));
+    LB_TRY(lb_sync_model(e));
+    LB_TRY(lb_launch_score_rows_diff(e, kind, b, en, (float *)e->d_scratch));
+    if (out) {
+        LB_CUDA(cudaMemcpyAsync(out, e->d_scratch, bytes, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+    }
     return 0;
 }
 

@@ -17,6 +17,7 @@ struct KindHost {
     float *shifted = nullptr, *cache = nullptr;
     double *flts = nullptr;
     int32_t *cache_row_feat = nullptr;
+    bool assign_pooled = false;   // assign came from the stream-ordered pool (ephemeral kinds: no device-wide sync to make or drop one)
 };
 
 struct ProposerKind {      // all-feature tables of one kind (KindProposer::Kind): views into the slabs
@@ -100,6 +101,10 @@ struct Engine {
     int d_fid_list_cap = 0;
     void *d_score_aux = nullptr;       // K1: GP feature index + predictive tables
     size_t score_aux_bytes = 0;
+    // the tare-compressed form of the loaded block, kept on the device by lb_set_rows_diff for the sparse scorer (K1d)
+    void *d_diff = nullptr;            // [tare_obs F][tare_val F][row_has_tare R?][pos_ptr R+1][pos_feature][pos_value][neg_ptr R+1][neg_feature]
+    size_t diff_bytes = 0, diff_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool diff_valid = false, diff_has_row_flags = false;
     void *d_tc_aux = nullptr;          // K1t: producer records, chunk lists and the bf16 operand planes
     size_t tc_aux_bytes = 0;
     int d_kind_ids_cap = 0;
@@ -132,6 +137,7 @@ struct Engine {
     unsigned long long *d_prof = nullptr;  // LB_PROFILE=1: per-kind, per-warp phase cycles of the sweep
     void *differ = nullptr;                // tare / sparsify state (lb_differ.cu)
     void *comm = nullptr;                  // NCCL communicator + rank (lb_comm.cu)
+    void *seating = nullptr;               // ephemeral-kind seating drawn ahead of time (lb_struct.cu)
 };
 
 // launch-family indices for launch_count
@@ -191,6 +197,7 @@ int lb_launch_row_lse_add(Engine *e, const float *d_scores, uint64_t n_rows, int
 int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out, int lse = 0);
 int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const float *d_tab, const int32_t *row_base,
                             int K_total, float *d_out, int planes, int *used);   // lb_score_tc.cu
+int lb_launch_score_rows_diff(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
 int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
                              const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,
@@ -211,5 +218,6 @@ int lb_proposer_score_range(Engine *e, int f_lo, int f_hi, int F_pad);
 int lb_proposer_fetch_scores(Engine *e, float *out);
 // collectives (lb_comm.cu)
 void lb_release_comm(Engine *e);
+void lb_release_seating(Engine *e);
 void lb_free_proposer(Engine *e);      // invalidate (buffers kept)
 void lb_release_proposer(Engine *e);   // free the buffers

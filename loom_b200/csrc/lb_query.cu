@@ -258,6 +258,7 @@ extern "C" int lb_query_sample(lb_handle h, uint64_t row, const uint32_t *to_sam
 
 extern "C" int lb_generate_rows(lb_handle h, uint64_t R, float density, uint64_t seed) {
     Engine *e = (Engine *)h;
+    e->diff_valid = false;
     LB_CUDA(cudaSetDevice(e->device));
     if (!e->F) return lb_fail("generate_rows before set_model");
     if (!(density >= 0.f && density <= 1.f)) return lb_fail("generate_rows: density must be in [0, 1]");

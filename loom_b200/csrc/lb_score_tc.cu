@@ -192,10 +192,11 @@ k_score_rows_tc(const KindDev *kinds, int kid, const TcFeat *tfeat, const uint16
                 __syncwarp();
                 const int g = cb + lane;
                 if (g < G) {
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const uint64_t r = r0 + warp * 32 + rr;
-                        if (r < en) out[(r - b) * (uint64_t)G + g] = tr[rr * 32 + (lane ^ rr)];
-                    }
+                    const uint64_t rw = r0 + warp * 32;                       // first row of this warp
+                    const int n_valid = rw >= en ? 0 : (int)min((uint64_t)32, en - rw);
+                    float *op = out + (rw - b) * (uint64_t)G + g;
+#pragma unroll 8
+                    for (int rr = 0; rr < n_valid; ++rr, op += G) *op = tr[rr * 32 + (lane ^ rr)];
                 }
                 __syncwarp();
             }

@@ -480,7 +480,7 @@ static int kind_relayout(Engine *e, int kid, const std::vector<int> &fids) {
     }
     LB_CUDA(cudaGetLastError());
     LB_CUDA(cudaStreamSynchronize(e->stream));
-    nk.assign = k.assign;
+    nk.assign = k.assign; nk.assign_pooled = k.assign_pooled;
     lb_kind_release(e, k);
     k = nk;
     return 0;
@@ -522,6 +522,111 @@ extern "C" int lb_kind_run(lb_handle h, int32_t iterations, uint64_t seed, uint3
 }
 
 // ---------------------------------------------------------------------------
+// Pitman-Yor seating of the ephemeral kinds (src/kind_kernel.cc:159-189): one sequential pass over the assigned rows
+// per kind.  The kinds are independent and every draw is keyed by (seed, row, kind id), so they are seated side by
+// side on host threads; the arithmetic (and therefore every pick) is the single-threaded loop's.
+// ---------------------------------------------------------------------------
+struct Seating {
+    int count = 0, first_kid = 0;
+    uint64_t seed = 0, R = 0;
+    std::vector<uint64_t> assigned;                     // bit per row: assigned in kind 0 when the seating was requested
+    std::vector<std::pair<float, float>> py;            // (alpha, d) of every new kind
+    std::vector<std::vector<uint32_t>> picks, counts;   // results
+    bool same_request(const Seating &o) const {
+        return count == o.count && first_kid == o.first_kid && seed == o.seed && R == o.R && py == o.py && assigned == o.assigned;
+    }
+};
+struct PendingSeating {
+    Seating s;
+    std::vector<uint32_t> a0;
+    std::thread th;
+};
+
+static void seating_describe(Engine *e, Seating &s, int count, uint64_t seed, int first_kid, const std::vector<uint32_t> &a0) {
+    s.count = count; s.seed = seed; s.first_kid = first_kid; s.R = count > 0 ? e->R : 0;
+    s.assigned.assign(count > 0 ? (e->R + 63) / 64 : 0, 0ull);
+    if (count > 0)
+        for (uint64_t r = 0; r < e->R; ++r) if (a0[r] != LB_UNASSIGNED) s.assigned[r >> 6] |= 1ull << (r & 63);
+    const std::vector<float> &grid = e->hp[1];   // clustering grid [n][2]
+    s.py.assign(std::max(count, 0), {e->kinds[0].alpha, e->kinds[0].d});
+    for (int c = 0; c < count; ++c)
+        if (!grid.empty()) {   // sample_clustering_prior (infer_grid.hpp:127-139)
+            const int n = (int)grid.size() / 2;
+            const double u = (double)lb_uniform(seed, 3u, 0xFFFFFFFFFFFFFFFFull, (uint32_t)(first_kid + c));
+            int i = (int)(u * n);
+            if (i >= n) i = n - 1;
+            s.py[c] = {grid[2 * i], grid[2 * i + 1]};
+        }
+}
+
+static void seat_kinds(Seating &s, const std::vector<uint32_t> &a0) {
+    const int count = s.count;
+    s.picks.assign(std::max(count, 0), {});
+    s.counts.assign(std::max(count, 0), {});
+    if (count <= 0) return;
+    auto seat = [&](int c) {
+        const int kid = s.first_kid + c;
+        const double alpha = s.py[c].first, d = s.py[c].second;
+        std::vector<uint32_t> &pick = s.picks[c], &counts = s.counts[c];
+        pick.assign(s.R, LB_UNASSIGNED);
+        int m = 0;
+        uint64_t seated = 0;
+        for (uint64_t r = 0; r < s.R; ++r) {
+            if (a0[r] == LB_UNASSIGNED) continue;
+            // weights counts[g] - d for the occupied tables, alpha + d m for a new one: they sum to seated + alpha in
+            // closed form, so the scan stops at the pick (the oracle does the same arithmetic)
+            const double total = (double)seated + alpha;
+            const double u = (double)lb_uniform(s.seed, 3u, r, (uint32_t)kid);
+            const double t = u * total;
+            double cum = 0;
+            int g = m;
+            for (int i = 0; i < m; ++i) {
+                cum += (double)counts[i] - d;
+                if (cum > t) { g = i; break; }
+            }
+            if (g == m) { counts.push_back(0); ++m; }
+            counts[g]++;
+            ++seated;
+            pick[r] = (uint32_t)g;
+        }
+    };
+    const int n_thr = std::max(1, std::min<int>(count, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    std::atomic<int> next(0);
+    for (int t = 0; t < n_thr; ++t)
+        pool.emplace_back([&] { for (int c = next++; c < count; c = next++) seat(c); });
+    for (auto &t : pool) t.join();
+}
+
+void lb_release_seating(Engine *e) {
+    PendingSeating *p = (PendingSeating *)e->seating;
+    if (!p) return;
+    if (p->th.joinable()) p->th.join();
+    delete p;
+    e->seating = nullptr;
+}
+
+// Draw the NEXT lb_init_featureless_kinds(count, seed) ahead of time on background host threads: the seating depends
+// only on the seed, the kind ids and WHICH rows are assigned -- not on where they sit -- so a driver calls this before
+// it launches a pass that keeps the assigned set (a REMOVE + ADD pass), and the host work runs under the device sweep.
+extern "C" int lb_prepare_featureless_kinds(lb_handle h, int32_t count, uint64_t seed) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    lb_release_seating(e);
+    if (count <= 0 || !e->R || e->kinds.empty() || e->kinds[0].fids.empty()) return 0;
+    PendingSeating *p = new PendingSeating;
+    p->a0.resize(e->R);
+    LB_CUDA(cudaMemcpyAsync(p->a0.data(), e->kinds[0].assign, 4 * (size_t)e->R, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    int first_kid = 0;
+    for (const KindHost &k : e->kinds) first_kid += !k.fids.empty();     // the ids the new kinds get once the featureless ones are gone
+    seating_describe(e, p->s, count, seed, first_kid, p->a0);
+    e->seating = p;
+    p->th = std::thread([p] { seat_kinds(p->s, p->a0); });
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // init_featureless_kinds (src/kind_kernel.cc:159-227).  The Pitman-Yor prior
 // partition of the assigned rows is a sequential seating process
 // (Clustering::PitmanYor::sample_assignments); it is drawn on the host in the
@@ -535,7 +640,10 @@ extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t se
         if (!e->kinds[i].fids.empty()) continue;
         if (e->kinds.size() == 1) return lb_fail("cannot remove the only kind");
         lb_kind_release(e, e->kinds[i]);
-        if (e->kinds[i].assign) cudaFree(e->kinds[i].assign);
+        if (e->kinds[i].assign) {
+            if (e->kinds[i].assign_pooled) cudaFreeAsync(e->kinds[i].assign, e->stream);
+            else cudaFree(e->kinds[i].assign);
+        }
         const int last = (int)e->kinds.size() - 1;
         if (i != last) {   // remove_featureless_kind: packed_remove + patch featureid_to_kindid
             e->kinds[i] = e->kinds[last];
@@ -549,55 +657,20 @@ extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t se
         LB_CUDA(cudaMemcpyAsync(a0.data(), e->kinds[0].assign, 4 * (size_t)e->R, cudaMemcpyDeviceToHost, e->stream));
         LB_CUDA(cudaStreamSynchronize(e->stream));
     }
-    const std::vector<float> &grid = e->hp[1];   // clustering grid [n][2]
-    // Pitman-Yor seating of every assigned row, one sequential pass per ephemeral kind (src/kind_kernel.cc:159-189).
-    // The kinds are independent and every draw is keyed by (seed, row, kind), so they are seated side by side on the
-    // host threads; the arithmetic (and therefore every pick) is the single-threaded loop's.
     const int first_kid = (int)e->kinds.size();
-    std::vector<std::vector<uint32_t>> picks(count), all_counts(count);
-    std::vector<std::pair<float, float>> py(count, {e->kinds[0].alpha, e->kinds[0].d});
-    for (int c = 0; c < count; ++c)
-        if (!grid.empty()) {   // sample_clustering_prior (infer_grid.hpp:127-139)
-            const int n = (int)grid.size() / 2;
-            const double u = (double)lb_uniform(seed, 3u, 0xFFFFFFFFFFFFFFFFull, (uint32_t)(first_kid + c));
-            int i = (int)(u * n);
-            if (i >= n) i = n - 1;
-            py[c] = {grid[2 * i], grid[2 * i + 1]};
-        }
-    auto seat = [&](int c) {
-        const int kid = first_kid + c;
-        const double alpha = py[c].first, d = py[c].second;
-        std::vector<uint32_t> &pick = picks[c], &counts = all_counts[c];
-        pick.assign(e->R, LB_UNASSIGNED);
-        int m = 0;
-        uint64_t seated = 0;
-        for (uint64_t r = 0; r < e->R; ++r) {
-            if (a0[r] == LB_UNASSIGNED) continue;
-            // weights counts[g] - d for the occupied tables, alpha + d m for a new one: they sum to seated + alpha in
-            // closed form, so the scan stops at the pick (the oracle does the same arithmetic)
-            const double total = (double)seated + alpha;
-            const double u = (double)lb_uniform(seed, 3u, r, (uint32_t)kid);
-            const double t = u * total;
-            double c = 0;
-            int g = m;
-            for (int i = 0; i < m; ++i) {
-                c += (double)counts[i] - d;
-                if (c > t) { g = i; break; }
-            }
-            if (g == m) { counts.push_back(0); ++m; }
-            counts[g]++;
-            ++seated;
-            pick[r] = (uint32_t)g;
-        }
-    };
+    // the seating may have been drawn ahead of time, under the sweep (lb_prepare_featureless_kinds); it is used when it
+    // was drawn for exactly this situation (same seed, count, kind ids, clustering, set of assigned rows)
+    Seating local, *seating = &local;
+    PendingSeating *pend = (PendingSeating *)e->seating;
+    if (pend && pend->th.joinable()) pend->th.join();
     {
-        const int n_thr = std::max(1, std::min<int>(count, (int)std::thread::hardware_concurrency()));
-        std::vector<std::thread> pool;
-        std::atomic<int> next(0);
-        for (int t = 0; t < n_thr; ++t)
-            pool.emplace_back([&] { for (int c = next++; c < count; c = next++) seat(c); });
-        for (auto &t : pool) t.join();
+        Seating want;
+        seating_describe(e, want, count, seed, first_kid, a0);
+        if (pend && pend->s.same_request(want)) seating = &pend->s;
+        else { local = std::move(want); seat_kinds(local, a0); }
     }
+    const std::vector<std::vector<uint32_t>> &picks = seating->picks, &all_counts = seating->counts;
+    const std::vector<std::pair<float, float>> &py = seating->py;
     for (int c = 0; c < count; ++c) {
         e->kinds.emplace_back();
         KindHost &k = e->kinds.back();
@@ -613,10 +686,12 @@ extern "C" int lb_init_featureless_kinds(lb_handle h, int32_t count, uint64_t se
         for (int g = 0; g < m; ++g) total += counts[g];
         k.sample_size = total;
         if (m) LB_CUDA(cudaMemcpyAsync(k.counts, counts.data(), 4 * (size_t)m, cudaMemcpyHostToDevice, e->stream));
-        LB_TRY(dalloc(&k.assign, e->R));
+        LB_CUDA(cudaMallocAsync((void **)&k.assign, 4 * std::max<size_t>(e->R, 1), e->stream));
+        k.assign_pooled = true;
         if (e->R) LB_CUDA(cudaMemcpyAsync(k.assign, pick.data(), 4 * (size_t)e->R, cudaMemcpyHostToDevice, e->stream));
         LB_CUDA(cudaStreamSynchronize(e->stream));
     }
+    lb_release_seating(e);                 // the picks are on the device now
     e->model_dirty = true;
     LB_TRY(lb_sync_model(e));
     for (int kid = 0; kid < (int)e->kinds.size(); ++kid)

@@ -336,6 +336,13 @@ class Engine:
         self.abi.check(self.abi.score_rows(self.h, kind, row_begin, row_end, ptr(out, _f32p)))
         return out
 
+    def score_rows_diff(self, kind, row_begin=0, row_end=None, fetch=True):
+        row_end = self.n_rows if row_end is None else row_end
+        G = self.kind_info(kind).n_groups
+        out = np.empty((row_end - row_begin, G), np.float32) if fetch else None
+        self.abi.check(self.abi.score_rows_diff(self.h, kind, row_begin, row_end, ptr(out, _f32p)))
+        return out
+
     def query_score(self, row_begin=0, row_end=None):
         """log predictive probability of every loaded row under this sample (QueryServer Score)"""
         row_end = self.n_rows if row_end is None else row_end
@@ -423,6 +430,10 @@ class Engine:
         n = C.c_int32()
         self.abi.check(self.abi.kind_run(self.h, iterations, seed, ptr(f2k, _u32p), C.byref(n)))
         return f2k, n.value
+
+    def prepare_featureless_kinds(self, count, seed):
+        """start the next init_featureless_kinds(count, seed)'s host-side seating in the background (under a sweep)"""
+        self.abi.check(self.abi.prepare_featureless_kinds(self.h, count, seed))
 
     def init_featureless_kinds(self, count, seed):
         self.abi.check(self.abi.init_featureless_kinds(self.h, count, seed))

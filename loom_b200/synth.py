@@ -31,6 +31,14 @@ CONFIGS = {
                density=0.5, seed=2),
     "C3": dict(rows=1_000_000, types=[("dd256", 256)], density=0.5, seed=3),
     "C3-16": dict(rows=1_000_000, types=[("dd16", 256)], density=0.5, seed=3),
+    # taxi-like (examples/taxi/schema.json proportions): 200 dense columns (10 dictionary-encoded DPD, 100 DD of mixed
+    # cardinality, 90 NICH) observed with probability 0.9 + 300 sparse booleans, always observed, on with probability
+    # ~0.02 -- the columns loom_tare turns into one tare row
+    "C4": dict(rows=10_000_000, types=[("sbb", 300), ("dd4", 30), ("dd16", 40), ("dd256", 30), ("dpd32", 10), ("nich", 90)],
+               density=0.9, seed=4),
+    # C5: 100M x 1000, a quarter each BB / DD-256 / GP / NICH; kinds sharded over 8 GPUs for the sweep, rows for the
+    # kind and hyper kernels (runs at N = 8 only, in windows)
+    "C5": dict(rows=100_000_000, types=[("bb", 250), ("dd256", 250), ("gp", 250), ("nich", 250)], density=0.5, seed=5),
 }
 
 
@@ -40,6 +48,8 @@ def make_features(types):
         for _ in range(count):
             if name == "bb":
                 feats.append(dict(type="bb", **DEFAULT_HYPERS["bb"]))
+            elif name == "sbb":        # a sparse boolean: rarely on, always observed
+                feats.append(dict(type="bb", sparse=True, **DEFAULT_HYPERS["bb"]))
             elif name.startswith("dd"):
                 dim = int(name[2:])
                 feats.append(dict(type="dd", alphas=[DEFAULT_HYPERS["dd_alpha"]] * dim))
@@ -117,7 +127,7 @@ def _sample_feature(f, assign, n_groups, rng):
     R = len(assign)
     t = f["type"]
     if t == "bb":
-        p = rng.beta(f["alpha"], f["beta"], n_groups)
+        p = rng.beta(0.2, 9.8, n_groups) if f.get("sparse") else rng.beta(f["alpha"], f["beta"], n_groups)
         return (rng.random(R) < p[assign]).astype(np.uint32)
     if t in ("dd", "dpd"):
         if t == "dd":
@@ -172,6 +182,9 @@ def generate(rows, types, density=0.5, seed=0, f2k=None, single_kind=False):
             else:
                 wide[f - F8] = v
     obs = rng.random((F, rows)) < density
+    for f in range(F):
+        if feats[f].get("sparse"):
+            obs[f] = True
     return model, RowBlock(rows, cat8, wide, pack_mask(obs)), truth
 
 

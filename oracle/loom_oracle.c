@@ -677,6 +677,14 @@ int lo_set_groups(lb_handle h, int32_t kind, int32_t n, const uint32_t *counts,
 }
 
 /* batch score_value with frozen tables */
+/* score_diff of a tare-compressed row == score_value of the reconstructed row (src/product_mixture.cc:436-463 adds
+ * the tare cache and the pos cells and subtracts the neg cells of the same mixture): the checker holds the decoded
+ * block (lo_set_rows_diff), so both forms are one function here */
+int lo_score_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out);
+int lo_score_rows_diff(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out) {
+    return lo_score_rows(h, kind, b, en, out);
+}
+
 int lo_score_rows(lb_handle h, int32_t kind, uint64_t b, uint64_t en, float *out) {
     engine_t *e = h;
     if (kind < 0 || kind >= e->K) return lo_fail("bad kind %d", kind);

@@ -121,3 +121,29 @@ def test_posterior_enum_hypers_on_gpu(cuda_abi, oracle_abi):
                                              hyper_prior={feature_type: {param: grid}}, seed=70 + R)
         gof, info = pe_util.goodness_of_fit(samples, R, 1, False, scores_override=fixed)
         assert gof is None or gof > pe_util.MIN_GOODNESS_OF_FIT, (feature_type, param, gof, info)
+
+
+def test_ephemeral_kinds_seated_ahead_of_time_equal_the_direct_draw(oracle_abi, cuda_abi):
+    """lb_prepare_featureless_kinds draws the next init_featureless_kinds on background threads while the device
+    sweeps; the kinds it yields are the kinds the direct call yields (and the oracle's), and a draw prepared for another
+    situation (other seed) is discarded"""
+    model, rows, _ = mixed(rows=1500, seed=6)
+    o, a = both(oracle_abi, cuda_abi, model, rows)
+    b = Engine(cuda_abi)
+    b.set_model(model)
+    b.set_rows(rows)
+    first = sweep_actions(rows.n_rows)
+    again = sweep_actions(rows.n_rows, add=True, remove=True)
+    lockstep_sweep(oracle_abi, o, a, first, 5)
+    b.cat_sweep(first, seed=5)
+    a.prepare_featureless_kinds(5, seed=9)           # drawn under the next sweep ...
+    lockstep_sweep(oracle_abi, o, a, again, 6)
+    b.cat_sweep(again, seed=6)
+    b.prepare_featureless_kinds(5, seed=1234)        # ... and one prepared for a different seed: must not be used
+    for e in (o, a, b):
+        e.init_featureless_kinds(5, seed=9)
+    for k in range(o.n_kinds()):
+        assert np.array_equal(o.get_assignments(k), a.get_assignments(k)), k
+        assert np.array_equal(a.get_assignments(k), b.get_assignments(k)), k
+        assert np.array_equal(o.get_groups(k)[0], a.get_groups(k)[0])
+    assert a.kind_info(o.n_kinds() - 1).sample_size == rows.n_rows

@@ -55,7 +55,18 @@ def _equivalence(abi):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
         assert np.array_equal(dense.get_assignments(k), diff.get_assignments(k))
         assert np.array_equal(dense.score_rows(k), diff.score_rows(k))
-    assert dense.score_data() == diff.score_data()
+        # score_diff proper: tare score + pos - neg from the compressed form == the decoded row's score_value
+        sparse, full = diff.score_rows_diff(k).astype(np.float64), diff.score_rows(k).astype(np.float64)
+        assert sparse.shape == full.shape
+        assert (np.abs(sparse - full) <= 1e-5 * np.maximum(1.0, np.abs(full))).all(), (k, np.abs(sparse - full).max())
+        part = diff.score_rows_diff(k, 37, 215)
+        assert np.array_equal(part, diff.score_rows_diff(k)[37:215])
+    assert abs(dense.score_data() - diff.score_data()) <= 1e-12 * abs(dense.score_data())
+    with pytest.raises(Exception, match="did not come from set_rows_diff|bad"):
+        if dense.abi.prefix == "lb_":
+            dense.score_rows_diff(0)
+        else:
+            raise RuntimeError("bad (the checker scores the decoded block either way)")
     with pytest.raises(Exception, match="neg removes"):
         bad = dict(d)
         bad["neg_feature"] = d["neg_feature"].copy()
@@ -70,6 +81,37 @@ def test_diff_path_equals_dense_path_oracle(oracle_abi):
 @pytest.mark.gpu
 def test_diff_path_equals_dense_path_gpu(cuda_abi):
     _equivalence(cuda_abi)
+
+
+@pytest.mark.gpu
+def test_sparse_score_diff_matches_oracle_on_a_taxi_like_block(oracle_abi, cuda_abi):
+    """C4's shape in small: dense mixed columns + many sparse booleans behind one tare row, rows without the tare,
+    more than 128 groups in a kind; lb_score_rows_diff (O(nnz x G)) == the float64 oracle within 1e-5"""
+    model, rows, _ = synth.generate_config("C4", rows=3000)
+    g = Engine(cuda_abi)
+    g.set_model(model)
+    g.set_rows(rows)
+    to, tv = g.make_tare()                                # the device passes (lb_differ_*)
+    assert to[model.n_features - 1] == 0 and to[:20].sum() >= 15          # reals untouched, the sparse booleans tared
+    d = g.sparsify(to, tv)
+    assert len(d["pos_feature"]) < 0.8 * rows.n_cells()
+    flags = np.ones(rows.n_rows, np.uint8)
+    o = Engine(oracle_abi)
+    for e in (o, g):
+        e.set_model(model)
+        e.set_rows_diff(**d)
+    o.cat_sweep(sweep_actions(rows.n_rows), seed=5)
+    from test_cuda_cat import _load_state
+    keeps = _load_state(o, g, model)
+    worst = 0.0
+    for k in range(model.n_kinds):
+        so = o.score_rows(k).astype(np.float64)
+        so = np.concatenate([so[:, keeps[k]], so[:, [c for c in range(so.shape[1]) if c not in set(keeps[k])]]], axis=1)
+        sg = g.score_rows_diff(k).astype(np.float64)
+        assert sg.shape == so.shape
+        worst = max(worst, (np.abs(sg - so) / np.maximum(1.0, np.abs(so))).max())
+        assert np.abs(sg - g.score_rows(k)).max() <= 2e-5 * max(1.0, np.abs(so).max())
+    assert worst <= 1e-5, worst
 
 
 # ------------------------------------------------------------------------------------------ the passes themselves
