@@ -15,6 +15,8 @@
 #include <cstring>
 
 #include "lb_accum.cuh"
+#include <cub/cub.cuh>
+
 #include "lb_internal.h"
 
 #define FULL 0xffffffffu
@@ -619,6 +621,7 @@ k_cat_sweep(SweepChain one, const SweepChain *many, int n_chains, int smem_per_c
 }
 
 #include "lb_sweep_spec.cuh"
+#include "lb_sweep_flat.cuh"
 
 static int lb_upload_desc(Engine *e, const void *host, size_t bytes, void **dev);
 
@@ -650,8 +653,10 @@ int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *
         const KindHost &k = e->kinds[kid];
         if ((int)k.fids.size() > SW_PF * 32 * SW_MAX_WARPS)
             return lb_fail("cat_sweep: kind %d has %zu features (limit %d)", kid, k.fids.size(), SW_PF * 32 * SW_MAX_WARPS);
-        if (k.Gcap > SW_MAX_G)
-            return lb_fail("cat_sweep: kind %d needs %d group slots (limit %d)", kid, k.Gcap, SW_MAX_G);
+        // featureless kinds go to the linear-prior kernel (K3f), whose only limit is its count table in shared memory
+        const int limit = k.fids.empty() && e->empty_group_count == 1 ? 25600 : SW_MAX_G;
+        if (k.Gcap > limit)
+            return lb_fail("cat_sweep: kind %d needs %d group slots (limit %d)", kid, k.Gcap, limit);
     }
     if ((int)kind_ids.size() > e->d_kind_ids_cap) {
         if (e->d_kind_ids) cudaFree(e->d_kind_ids);
@@ -683,36 +688,45 @@ int lb_sweep_chain(Engine *e, const std::vector<int> &kind_ids, const uint32_t *
 static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
                                 const std::vector<std::vector<int>> &kind_ids) {
     struct Cost { SweepPair p; size_t cost; };
-    std::vector<Cost> cls[3];                      // 0 narrow (1 warp), 1 wide (8 warps), 2 wider (16 warps)
-    size_t smem[3] = {0, 0, 0};
+    // 0 narrow (1 warp), 1 wide (8 warps), 2 wider (16 warps), 3 flat: featureless kinds on the linear-prior kernel (K3f)
+    std::vector<Cost> cls[4];
+    size_t smem[4] = {0, 0, 0, 0};
     bool catonly = true;                           // no GP / NICH column anywhere in the launch: the lean instantiation
     const int warps_of[3] = {1, 8, LB_SPEC_WIDER};
     const char *w16 = getenv("LB_SPEC_WIDE16");
     const bool use16 = !w16 || atoi(w16) != 0;
+    const char *fl = getenv("LB_SWEEP_FLAT");
+    const bool use_flat = !fl || atoi(fl) != 0;
     for (int c = 0; c < n; ++c)
         for (int kid : kind_ids[c]) {
             const KindHost &k = engines[c]->kinds[kid];
             const int nf = (int)k.fids.size();
+            if (nf == 0 && use_flat && engines[c]->empty_group_count == 1 && !chains[c].dbg_scores && 8 * (size_t)k.Gcap <= 200 * 1024) {
+                smem[3] = std::max(smem[3], 8 * (size_t)k.Gcap);
+                cls[3].push_back(Cost{SweepPair{c, kid}, (size_t)(k.G + 8)});
+                continue;
+            }
             for (int f : k.fids) {
                 const int t = engines[c]->specs[f].type;
                 catonly = catonly && (t == LB_BB || t == LB_DD || t == LB_DPD);
             }
             const int w = nf >= SP_WIDER_NF && use16 ? 2 : (nf >= SP_WIDE_NF ? 1 : 0);
             if (nf > SW_PF * 32 * warps_of[w]) return 1;
+            if (k.Gcap > SW_MAX_G) return 1;
             smem[w] = std::max(smem[w], (spec_smem_bytes(nf, k.Gcap, warps_of[w]) + 15) / 16 * 16);
             cls[w].push_back(Cost{SweepPair{c, kid}, (size_t)(nf + 1) * (size_t)(k.G + 8)});
         }
     if (smem[1] > 220 * 1024 || smem[2] > 220 * 1024 || smem[0] * SP_CPB > 220 * 1024) return 1;
     auto by_cost = [](const Cost &a, const Cost &b) { return a.cost > b.cost; };
     for (auto &v : cls) std::stable_sort(v.begin(), v.end(), by_cost);
-    // one upload: [chains][wider pairs][wide pairs][narrow pairs]
+    // one upload: [chains][wider pairs][wide pairs][narrow pairs][flat pairs]
     const size_t cb = (sizeof(SweepChain) * (size_t)n + 15) / 16 * 16;
-    const size_t n_pairs = cls[0].size() + cls[1].size() + cls[2].size();
+    const size_t n_pairs = cls[0].size() + cls[1].size() + cls[2].size() + cls[3].size();
     std::vector<unsigned char> host(cb + sizeof(SweepPair) * n_pairs + 16);
     memcpy(host.data(), chains, sizeof(SweepChain) * (size_t)n);
     SweepPair *hp = (SweepPair *)(host.data() + cb);
-    size_t at = 0, first[3];
-    for (int w = 2; w >= 0; --w) { first[w] = at; for (const Cost &c : cls[w]) hp[at++] = c.p; }
+    size_t at = 0, first[4];
+    for (int w : {2, 1, 0, 3}) { first[w] = at; for (const Cost &c : cls[w]) hp[at++] = c.p; }
     void *d = nullptr;
     LB_TRY(lb_upload_desc(leader, host.data(), host.size(), &d));
     const SweepChain *d_chains = (const SweepChain *)d;
@@ -720,9 +734,11 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
     if (!leader->stream2) {
         LB_CUDA(cudaStreamCreateWithFlags(&leader->stream2, cudaStreamNonBlocking));
         LB_CUDA(cudaStreamCreateWithFlags(&leader->stream3, cudaStreamNonBlocking));
+        LB_CUDA(cudaStreamCreateWithFlags(&leader->stream4, cudaStreamNonBlocking));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_fork, cudaEventDisableTiming));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join, cudaEventDisableTiming));
         LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join3, cudaEventDisableTiming));
+        LB_CUDA(cudaEventCreateWithFlags(&leader->ev_join4, cudaEventDisableTiming));
     }
     if (const char *v = getenv("LB_SPEC_CATONLY")) catonly = catonly && atoi(v) != 0;      // A/B switch
     auto kernel_of = [&](int w) {
@@ -734,22 +750,28 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
     for (int w = 0; w < 3; ++w)
         if (!cls[w].empty())
             LB_CUDA(cudaFuncSetAttribute(kernel_of(w), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(w ? smem[w] : smem[0] * SP_CPB)));
+    // flat class: as many one-warp pairs to a block as their count tables leave room for
+    const int flat_ppb = cls[3].empty() ? 1 : (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem[3], 1)));
+    if (!cls[3].empty())
+        LB_CUDA(cudaFuncSetAttribute(k_cat_sweep_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem[3] * flat_ppb)));
     LB_CUDA(cudaEventRecord(leader->kev0, leader->stream));
     LB_CUDA(cudaEventRecord(leader->ev_fork, leader->stream));
     // the longest-running class goes first on the leader's stream; the others fork off it and join back
-    const int lead_cls = !cls[2].empty() ? 2 : (!cls[1].empty() ? 1 : 0);
-    cudaStream_t side[2] = {leader->stream2, leader->stream3};
-    cudaEvent_t joined[2] = {leader->ev_join, leader->ev_join3};
+    const int lead_cls = !cls[2].empty() ? 2 : (!cls[1].empty() ? 1 : (!cls[0].empty() ? 0 : 3));
+    cudaStream_t side[3] = {leader->stream2, leader->stream3, leader->stream4};
+    cudaEvent_t joined[3] = {leader->ev_join, leader->ev_join3, leader->ev_join4};
     int n_side = 0;
-    for (int w = 2; w >= 0; --w) {
+    for (int w : {2, 1, 0, 3}) {
         if (cls[w].empty()) continue;
         cudaStream_t s = leader->stream;
         if (w != lead_cls) { s = side[n_side]; LB_CUDA(cudaStreamWaitEvent(s, leader->ev_fork, 0)); }
         const int np = (int)cls[w].size();
         if (w == 2) kernel_of(2)<<<(unsigned)np, 32 * LB_SPEC_WIDER, smem[2], s>>>(d_chains, d_pairs + first[2], np, (int)smem[2]);
         else if (w == 1) kernel_of(1)<<<(unsigned)np, 256, smem[1], s>>>(d_chains, d_pairs + first[1], np, (int)smem[1]);
-        else kernel_of(0)<<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
+        else if (w == 0) kernel_of(0)<<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
                  d_chains, d_pairs + first[0], np, (int)smem[0]);
+        else k_cat_sweep_flat<<<(unsigned)((np + flat_ppb - 1) / flat_ppb), 32 * flat_ppb, smem[3] * flat_ppb, s>>>(
+                 d_chains, d_pairs + first[3], np, (int)smem[3]);
         LB_CUDA(cudaGetLastError());
         if (w != lead_cls) { LB_CUDA(cudaEventRecord(joined[n_side], s)); ++n_side; }
         leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
@@ -772,19 +794,26 @@ static bool sweep_use_spec(const Engine *e, size_t n_ctas) {
 // One launch for `n` chains on the leader's stream: grid (max active kinds, chains).
 int lb_launch_sweep_chains(Engine *leader, const SweepChain *chains, int n, const std::vector<Engine *> &engines,
                            const std::vector<std::vector<int>> &kind_ids) {
-    size_t n_ctas = 0, smem = 0;
+    size_t n_ctas = 0, n_featured = 0, smem = 0;
     int max_nf = 0, max_ids = 0;
     for (int c = 0; c < n; ++c) {
         n_ctas += kind_ids[c].size();
         max_ids = std::max(max_ids, (int)kind_ids[c].size());
-        for (int kid : kind_ids[c]) max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
+        for (int kid : kind_ids[c]) {
+            max_nf = std::max(max_nf, (int)engines[c]->kinds[kid].fids.size());
+            n_featured += !engines[c]->kinds[kid].fids.empty();
+        }
     }
     if (!n_ctas) return 0;
-    if (sweep_use_spec(leader, n_ctas)) {
+    if (sweep_use_spec(leader, std::max<size_t>(n_featured, 1))) {   // featureless kinds are one cheap warp each (K3f)
         const int rc = lb_launch_sweep_spec(leader, chains, n, engines, kind_ids);
         if (rc <= 0) return rc;      // launched (0) or failed (< 0); 1 = does not fit, use the classic kernel
     }
     if (max_ids > 65535) return lb_fail("cat_sweep: %d kinds in one launch (limit 65535)", max_ids);
+    for (int c = 0; c < n; ++c)
+        for (int kid : kind_ids[c])
+            if (engines[c]->kinds[kid].Gcap > SW_MAX_G)
+                return lb_fail("cat_sweep: kind %d needs %d group slots (limit %d in the many-chain kernel)", kid, engines[c]->kinds[kid].Gcap, SW_MAX_G);
     int W = sweep_warps(leader, n_ctas, max_nf);
     for (;;) {
         smem = 0;
@@ -888,13 +917,14 @@ template <int NJ, bool LSE = false>
 __global__ void __launch_bounds__(SC_THREADS)
 k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *kind_feats,
              const int32_t *row_base, const float *tab, RowsDev rows, uint64_t b, uint64_t en,
-             int n_empty, int g_base, float *out, int lse_first = 0) {
+             int n_empty, int g_base, float *out, int lse_first = 0, const int32_t *flist = nullptr, int n_flist = 0) {
     __shared__ FeatDev s_feat[SC_FC];
     __shared__ int32_t s_fid[SC_FC];
     __shared__ uint32_t s_row[SC_FC][SC_TR];     // table row of the cell (0 = unobserved), or raw bits for NICH
     __shared__ uint32_t s_obs[SC_FC][SC_TR / 32];
+    __shared__ int32_t s_rb[SC_FC];
     const KindDev &kd = kinds[kid];
-    const int nf = kd.nf, st = kd.Gcap, G = kd.G;
+    const int nf = flist ? n_flist : kd.nf, st = kd.Gcap, G = kd.G;     // flist: the kind-local features to score (K1d: the untared ones)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *cache = kd.cache;
     const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
@@ -918,9 +948,11 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
             const int fc = min(SC_FC, nf - f0);
             __syncthreads();   // previous chunk fully consumed
             for (int j = tid; j < fc; j += SC_THREADS) {
-                const int fid = kind_feats[kd.feat_begin + f0 + j];
+                const int jl = flist ? flist[f0 + j] : f0 + j;           // kind-local index
+                const int fid = kind_feats[kd.feat_begin + jl];
                 s_feat[j] = feats[fid];
                 s_fid[j] = fid;
+                s_rb[j] = row_base[jl];
             }
             __syncthreads();
             for (int idx = tid; idx < fc * (SC_TR / 32); idx += SC_THREADS) {
@@ -952,7 +984,7 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
                 if (f.type != LB_NICH) {
                     if (!obs) v = 0u;
                     else if (f.type == LB_GP && raw >= (uint32_t)LB_GP_TAB) v = 0x80000000u | raw;  // direct evaluation
-                    else v = (uint32_t)row_base[f0 + j] + raw;
+                    else v = (uint32_t)s_rb[j] + raw;
                 }
                 s_row[j][rr] = v;
             }
@@ -1163,10 +1195,17 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
 // ===========================================================================
 __global__ void k_tare_scores(const KindDev *kinds, int kid, const int32_t *kind_feats, const int32_t *row_base,
                               const float *tab, const uint8_t *tare_obs, const uint32_t *tare_val, float *tare_scores,
-                              int32_t *frow) {
+                              int32_t *frow, int32_t *fn, const FeatDev *feats) {
     const KindDev &kd = kinds[kid];
     const int st = kd.Gcap;
-    for (int j = threadIdx.x; j < kd.nf; j += blockDim.x) frow[kind_feats[kd.feat_begin + j]] = row_base[j];   // feature -> first table row
+    // feature -> first table row, for the TARED features of this kind only (the rest stay -1: the dense pass scores them)
+    for (int j = threadIdx.x; j < kd.nf; j += blockDim.x) {
+        const int f = kind_feats[kd.feat_begin + j];
+        if (tare_obs[f]) {
+            frow[f] = row_base[j];
+            fn[f] = feats[f].type == LB_BB ? 2 : (feats[f].type == LB_GP ? LB_GP_TAB : feats[f].dim);    // tabulated values
+        }
+    }
     for (int g = threadIdx.x; g < st; g += blockDim.x) {
         float acc = 0.f;
         if (g < kd.G)
@@ -1178,77 +1217,161 @@ __global__ void k_tare_scores(const KindDev *kinds, int kid, const int32_t *kind
     }
 }
 
+// out[r][g] += (row references the tare ? tare_score[g] : 0) + sum over the row's pos cells in tared columns of this
+// kind - sum over its neg cells.  A warp takes a row: 32 diff entries are read at once (coalesced), each lane turns its
+// entry into a table-row offset (or nothing: another kind / an untared column), and the warp walks the hits.
 __global__ void __launch_bounds__(256)
-k_score_rows_diff(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *frow, const float *tab,
-                  const float *tare_scores, const uint8_t *row_has_tare, const uint32_t *tare_val, const uint64_t *pos_ptr,
+k_score_rows_diff(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t *frow, const int32_t *fn, const float *tab,
+                  const float *tare_scores,
+                  const uint8_t *row_has_tare, const uint32_t *tare_val, const uint64_t *pos_ptr,
                   const uint32_t *pos_feature, const uint32_t *pos_value, const uint64_t *neg_ptr, const uint32_t *neg_feature,
-                  uint64_t b, uint64_t en, int n_empty, float *out) {
+                  uint64_t b, uint64_t en, float *out) {
     const KindDev &kd = kinds[kid];
     const int G = kd.G, st = kd.Gcap;
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const float base = -logf((float)kd.sample_size + kd.alpha);
-    const float sh_empty = logf((kd.alpha + kd.d * (float)(G - n_empty)) / (float)n_empty);
     for (int g0 = 0; g0 < G; g0 += 128) {
-        float prior[4], tare[4];
+        float tare[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int g = g0 + lane + 32 * jj;
-            prior[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
-            tare[jj] = g < G ? tare_scores[g] : 0.f;
-        }
+        for (int jj = 0; jj < 4; ++jj) tare[jj] = g0 + lane + 32 * jj < G ? tare_scores[g0 + lane + 32 * jj] : 0.f;
         const float *tabg = tab + g0 + lane;
         for (uint64_t r = b + warp; r < en; r += n_warps) {
             float acc[4];
             const bool has = !row_has_tare || row_has_tare[r];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[jj] = prior[jj] + (has ? tare[jj] : 0.f);
-            for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1]; ++i) {
-                const int f = (int)pos_feature[i];
-                const int row0 = frow[f];
-                if (row0 < 0) continue;                                    // a cell of another kind
-                const FeatDev &fd = feats[f];
-                const uint32_t raw = pos_value[i];
-                if (fd.type == LB_NICH || (fd.type == LB_GP && raw >= (uint32_t)LB_GP_TAB)) {
-                    const float lf = fd.type == LB_GP ? lb_log_factorial(raw) : 0.f;
+            for (int jj = 0; jj < 4; ++jj) acc[jj] = has ? tare[jj] : 0.f;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int g = g0 + lane + 32 * jj;
-                        if (g < G) acc[jj] += lb_score_cell(fd, kd.ints + (size_t)fd.int_row * st + g, kd.cache + (size_t)fd.cache_row * st + g, st, raw, lf);
+            for (int pass = 0; pass < 2; ++pass) {           // 0: pos cells (+), 1: neg cells (-)
+                const uint64_t lo = pass ? neg_ptr[r] : pos_ptr[r], hi = pass ? neg_ptr[r + 1] : pos_ptr[r + 1];
+                for (uint64_t i0 = lo; i0 < hi; i0 += 32) {
+                    const uint64_t i = i0 + lane;
+                    int off = -1, f = -1;
+                    uint32_t raw = 0;
+                    if (i < hi) {
+                        f = (int)(pass ? neg_feature[i] : pos_feature[i]);
+                        const int row0 = frow[f];
+                        if (row0 >= 0) {
+                            raw = pass ? tare_val[f] : pos_value[i];
+                            off = raw < (uint32_t)fn[f] ? (row0 + (int)raw) * st : -2;      // -2: a count beyond the table (GP >= 16)
+                        }
                     }
-                } else {
-                    const float *t = tabg + (size_t)(row0 + (int)raw) * st;
+                    unsigned direct = __ballot_sync(FULL, off == -2);
+                    while (direct) {                              // rare: evaluate the predictive directly
+                        const int src = __ffs(direct) - 1;
+                        direct &= direct - 1;
+                        const FeatDev &fd = feats[__shfl_sync(FULL, f, src)];
+                        const uint32_t x = __shfl_sync(FULL, raw, src);
+                        const float lf = lb_log_factorial(x);
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) if (g0 + 32 * jj < st) acc[jj] += t[32 * jj];
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int g = g0 + lane + 32 * jj;
+                            if (g < G) {
+                                const float v = lb_score_cell(fd, kd.ints + (size_t)fd.int_row * st + g, kd.cache + (size_t)fd.cache_row * st + g, st, x, lf);
+                                acc[jj] += pass ? -v : v;
+                            }
+                        }
+                    }
+                    unsigned hits = __ballot_sync(FULL, off >= 0);
+                    while (hits) {
+                        const int src = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float *t = tabg + __shfl_sync(FULL, off, src);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (g0 + 32 * jj < st) acc[jj] += pass ? -t[32 * jj] : t[32 * jj];
+                    }
                 }
-            }
-            for (uint64_t i = neg_ptr[r]; i < neg_ptr[r + 1]; ++i) {
-                const int f = (int)neg_feature[i];
-                const int row0 = frow[f];
-                if (row0 < 0) continue;
-                const float *t = tabg + (size_t)(row0 + (int)tare_val[f]) * st;   // tare cells are tabulated (booleans, counts < 16)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) if (g0 + 32 * jj < st) acc[jj] -= t[32 * jj];
             }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int g = g0 + lane + 32 * jj;
-                if (g < G) out[(r - b) * (uint64_t)G + g] = acc[jj];
+                if (g < G) out[(r - b) * (uint64_t)G + g] += acc[jj];
             }
         }
     }
 }
 
+// the pos cells that sit in tared columns: count per row, scan, fill (once per loaded block)
+__global__ void k_tpos_count(uint64_t R, const uint64_t *pos_ptr, const uint32_t *pos_feature, const uint8_t *tare_obs, uint64_t *cnt) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t n = 0;
+        for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1]; ++i) n += tare_obs[pos_feature[i]];
+        cnt[r + 1] = n;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[0] = 0;
+}
+__global__ void k_tpos_fill(uint64_t R, const uint64_t *pos_ptr, const uint32_t *pos_feature, const uint32_t *pos_value,
+                            const uint8_t *tare_obs, const uint64_t *tptr, uint32_t *tfeat, uint32_t *tval) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t o = tptr[r];
+        for (uint64_t i = pos_ptr[r]; i < pos_ptr[r + 1]; ++i)
+            if (tare_obs[pos_feature[i]]) { tfeat[o] = pos_feature[i]; tval[o] = pos_value[i]; ++o; }
+    }
+}
+static int tared_pos_build(Engine *e) {
+    if (e->tpos_valid) return 0;
+    const uint64_t R = e->R;
+    const char *diff = (const char *)e->d_diff;
+    const uint8_t *tare_obs = (const uint8_t *)(diff + e->diff_off[0]);
+    const uint64_t *pos_ptr = (const uint64_t *)(diff + e->diff_off[3]);
+    const uint32_t *pos_feature = (const uint32_t *)(diff + e->diff_off[4]), *pos_value = (const uint32_t *)(diff + e->diff_off[5]);
+    if (R + 1 > e->tpos_cap_rows) {
+        if (e->d_tpos_ptr) cudaFree(e->d_tpos_ptr);
+        e->d_tpos_ptr = nullptr; e->tpos_cap_rows = 0;
+        LB_CUDA(cudaMalloc((void **)&e->d_tpos_ptr, 8 * (size_t)(R + 1)));
+        e->tpos_cap_rows = R + 1;
+    }
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((R + 255) / 256, (uint64_t)e->n_sm * 16));
+    k_tpos_count<<<grid, 256, 0, e->stream>>>(R, pos_ptr, pos_feature, tare_obs, e->d_tpos_ptr);
+    size_t scan_bytes = 0;
+    LB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, e->d_tpos_ptr + 1, e->d_tpos_ptr + 1, (int)std::max<uint64_t>(R, 1), e->stream));
+    void *d_scan = nullptr;
+    LB_CUDA(cudaMallocAsync(&d_scan, scan_bytes + 256, e->stream));
+    LB_CUDA(cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, e->d_tpos_ptr + 1, e->d_tpos_ptr + 1, (int)R, e->stream));
+    LB_CUDA(cudaFreeAsync(d_scan, e->stream));
+    unsigned long long total = 0;
+    LB_CUDA(cudaMemcpyAsync(&total, e->d_tpos_ptr + R, 8, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    if (total > e->tpos_cap || !e->d_tpos_feature) {
+        if (e->d_tpos_feature) cudaFree(e->d_tpos_feature);
+        if (e->d_tpos_value) cudaFree(e->d_tpos_value);
+        e->d_tpos_feature = e->d_tpos_value = nullptr; e->tpos_cap = 0;
+        LB_CUDA(cudaMalloc((void **)&e->d_tpos_feature, 4 * (size_t)std::max<unsigned long long>(total, 1)));
+        LB_CUDA(cudaMalloc((void **)&e->d_tpos_value, 4 * (size_t)std::max<unsigned long long>(total, 1)));
+        e->tpos_cap = (size_t)std::max<unsigned long long>(total, 1);
+    }
+    k_tpos_fill<<<grid, 256, 0, e->stream>>>(R, pos_ptr, pos_feature, pos_value, tare_obs, e->d_tpos_ptr, e->d_tpos_feature, e->d_tpos_value);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_MISC] += 2;
+    e->tpos_valid = true;
+    return 0;
+}
+
 int lb_launch_score_rows_diff(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out) {
+    LB_TRY(tared_pos_build(e));
     const KindHost &k = e->kinds[kid];
+    const int nf = (int)k.fids.size();
     std::vector<int32_t> row_base;
     int n_rows = 0;
     int32_t *d_row_base = nullptr;
     float *d_tab = nullptr;
     LB_TRY(score_table_build(e, kid, row_base, &n_rows, &d_row_base, &d_tab));
-    // per-call scratch: [tare_scores Gcap f32][feature -> table row, F i32]
+    // which columns the tare covers is host knowledge of the model file's tare row; mirror the device copy
+    std::vector<uint8_t> tare_obs(e->F);
+    const char *diff = (const char *)e->d_diff;
+    LB_CUDA(cudaMemcpyAsync(tare_obs.data(), diff + e->diff_off[0], (size_t)e->F, cudaMemcpyDeviceToHost, e->stream));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<int32_t> flist;                                  // kind-local features the dense pass scores
+    for (int j = 0; j < nf; ++j) {
+        const int f = k.fids[j];
+        if (!tare_obs[f]) flist.push_back(j);
+        else if (e->specs[f].type == LB_NICH) return lb_fail("score_rows_diff: feature %d is real-valued and tared (src/differ.cc:121 never tares reals)", f);
+    }
+    // per-call scratch: [tare_scores Gcap f32][feature -> table row, F i32][tabulated values, F i32][dense feature list nf i32]
     const size_t o_frow = (4 * (size_t)k.Gcap + 255) / 256 * 256;
-    const size_t need = o_frow + 4 * (size_t)e->F + 256;
+    const size_t o_fn = o_frow + (4 * (size_t)e->F + 255) / 256 * 256;
+    const size_t o_flist = o_fn + (4 * (size_t)e->F + 255) / 256 * 256;
+    const size_t need = o_flist + 4 * (size_t)std::max(nf, 1) + 256;
     if (need > e->tc_aux_bytes) {
         if (e->d_tc_aux) cudaFree(e->d_tc_aux);
         e->d_tc_aux = nullptr; e->tc_aux_bytes = 0;
@@ -1257,20 +1380,40 @@ int lb_launch_score_rows_diff(Engine *e, int kid, uint64_t b, uint64_t en, float
     }
     float *d_tare = (float *)e->d_tc_aux;
     int32_t *d_frow = (int32_t *)((char *)e->d_tc_aux + o_frow);
-    const char *diff = (const char *)e->d_diff;
-    const uint8_t *tare_obs = (const uint8_t *)(diff + e->diff_off[0]);
+    int32_t *d_fn = (int32_t *)((char *)e->d_tc_aux + o_fn);
+    int32_t *d_flist = (int32_t *)((char *)e->d_tc_aux + o_flist);
     const uint32_t *tare_val = (const uint32_t *)(diff + e->diff_off[1]);
-    for (int f : k.fids)
-        if (e->specs[f].type == LB_NICH) { /* reals are never tared (src/differ.cc:121,137-140); checked on the device copy below */ }
     LB_CUDA(cudaMemsetAsync(d_frow, 0xFF, 4 * (size_t)e->F, e->stream));
-    k_tare_scores<<<1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_kind_feats, d_row_base, d_tab, tare_obs, tare_val, d_tare, d_frow);
+    if (!flist.empty()) LB_CUDA(cudaMemcpyAsync(d_flist, flist.data(), 4 * flist.size(), cudaMemcpyHostToDevice, e->stream));
+    k_tare_scores<<<1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_kind_feats, d_row_base, d_tab, (const uint8_t *)(diff + e->diff_off[0]),
+                                            tare_val, d_tare, d_frow, d_fn, e->d_feats);
+    // dense pass: prior + the untared columns, the tile kernel of K1 over the sub-list (an empty list writes the prior)
+    {
+        const uint64_t n_tiles = (en - b + SC_TR - 1) / SC_TR;
+        const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)e->n_sm * 4));
+        RowsDev rows{e->R, e->W, e->d_cat8, e->d_wide, e->d_mask};
+        const int nl = (int)flist.size();
+        for (int g_base = 0; g_base < k.G; g_base += 128) {
+            const int left = k.G - g_base;
+            if (left <= 32)
+                k_score_rows<1><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_tab, rows, b, en,
+                                                                   e->empty_group_count, g_base, d_out, 0, d_flist, nl);
+            else if (left <= 64)
+                k_score_rows<2><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_tab, rows, b, en,
+                                                                   e->empty_group_count, g_base, d_out, 0, d_flist, nl);
+            else
+                k_score_rows<4><<<grid, SC_THREADS, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats, d_row_base, d_tab, rows, b, en,
+                                                                   e->empty_group_count, g_base, d_out, 0, d_flist, nl);
+            e->launches[LB_L_TOTAL]++; e->launches[LB_L_SCORE]++;
+        }
+    }
     const uint64_t n = en - b;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n * 32 + 255) / 256, (uint64_t)e->n_sm * 8));
     k_score_rows_diff<<<grid, 256, 0, e->stream>>>(
-        e->d_kinds, kid, e->d_feats, d_frow, d_tab, d_tare,
+        e->d_kinds, kid, e->d_feats, d_frow, d_fn, d_tab, d_tare,
         e->diff_has_row_flags ? (const uint8_t *)(diff + e->diff_off[2]) : nullptr, tare_val,
-        (const uint64_t *)(diff + e->diff_off[3]), (const uint32_t *)(diff + e->diff_off[4]), (const uint32_t *)(diff + e->diff_off[5]),
-        (const uint64_t *)(diff + e->diff_off[6]), (const uint32_t *)(diff + e->diff_off[7]), b, en, e->empty_group_count, d_out);
+        e->d_tpos_ptr, e->d_tpos_feature, e->d_tpos_value,
+        (const uint64_t *)(diff + e->diff_off[6]), (const uint32_t *)(diff + e->diff_off[7]), b, en, d_out);
     LB_CUDA(cudaGetLastError());
     e->launches[LB_L_TOTAL] += 2; e->launches[LB_L_SCORE] += 2;
     return 0;

@@ -290,8 +290,25 @@ extern "C" int lb_create(int device, lb_handle *out) {
 // forget a borrowed row block (never free it) so the engine can allocate its own
 static void drop_borrowed_rows(Engine *e) {
     if (!e->rows_borrowed) return;
+    if (e->rows_owner) {
+        auto &b = e->rows_owner->borrowers;
+        b.erase(std::remove(b.begin(), b.end(), e), b.end());
+    }
+    e->rows_owner = nullptr;
     e->d_cat8 = nullptr; e->d_wide = nullptr; e->d_mask = nullptr;
     e->rows_borrowed = false;
+}
+// The owner is about to free or replace its row block: the engines that borrow it are left without rows (their next
+// call that needs rows fails with a message) instead of reading freed memory.
+static void detach_borrowers(Engine *e) {
+    for (Engine *b : e->borrowers) {
+        cudaStreamSynchronize(b->stream);
+        b->rows_owner = nullptr;
+        b->d_cat8 = nullptr; b->d_wide = nullptr; b->d_mask = nullptr;
+        b->rows_borrowed = false;
+        b->R = 0; b->W = 0;
+    }
+    e->borrowers.clear();
 }
 
 static void clear_model(Engine *e) {
@@ -325,6 +342,7 @@ extern "C" void lb_destroy(lb_handle h) {
     }
     clear_model(e);
     drop_borrowed_rows(e);
+    detach_borrowers(e);
     dev_free(e->d_kinds); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
     if (e->pinned_kinds) cudaFreeHost(e->pinned_kinds);
     lb_release_proposer(e);
@@ -336,12 +354,15 @@ extern "C" void lb_destroy(lb_handle h) {
     if (e->d_score_aux) cudaFree(e->d_score_aux);
     if (e->d_tc_aux) cudaFree(e->d_tc_aux);
     if (e->d_diff) cudaFree(e->d_diff);
+    if (e->d_tpos_ptr) cudaFree(e->d_tpos_ptr);
+    if (e->d_tpos_feature) cudaFree(e->d_tpos_feature);
+    if (e->d_tpos_value) cudaFree(e->d_tpos_value);
     if (e->d_fid_list) cudaFree(e->d_fid_list);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
     cudaEventDestroy(e->kev0); cudaEventDestroy(e->kev1);
     if (e->stream2) {
-        cudaStreamDestroy(e->stream2); cudaStreamDestroy(e->stream3);
-        cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_join3);
+        cudaStreamDestroy(e->stream2); cudaStreamDestroy(e->stream3); cudaStreamDestroy(e->stream4);
+        cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaEventDestroy(e->ev_join3); cudaEventDestroy(e->ev_join4);
     }
     cudaStreamDestroy(e->stream);
     delete e;
@@ -404,13 +425,16 @@ extern "C" int lb_share_rows(lb_handle h, lb_handle owner_h) {
     for (int f = 0; f < e->F; ++f)
         if (e->specs[f].type != o->specs[f].type || e->specs[f].dim != o->specs[f].dim)
             return lb_fail("share_rows: feature %d differs between the two models", f);
-    if (!e->rows_borrowed) { dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask); }
+    if (!e->rows_borrowed) { detach_borrowers(e); dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask); }
+    else drop_borrowed_rows(e);
     e->diff_valid = false;
     if (o->R != e->R)
         for (auto &k : e->kinds) { dev_free(k.assign); k.assign_pooled = false; LB_TRY(dev_alloc(&k.assign, o->R)); }
     e->R = o->R; e->W = o->W;
     e->d_cat8 = o->d_cat8; e->d_wide = o->d_wide; e->d_mask = o->d_mask;
     e->rows_borrowed = true;
+    e->rows_owner = o;
+    o->borrowers.push_back(e);
     for (auto &k : e->kinds) LB_CUDA(cudaMemsetAsync(k.assign, 0xFF, 4 * (size_t)e->R, e->stream));
     LB_CUDA(cudaStreamSynchronize(o->stream));   // the owner's upload (validated by its set_rows) is complete
     return lb_sync_model(e);
@@ -425,6 +449,7 @@ extern "C" int lb_set_rows(lb_handle h, uint64_t R, const uint8_t *cat8, const u
     drop_borrowed_rows(e);
     e->diff_valid = false;
     if (R != e->R || !e->d_mask) {
+        detach_borrowers(e);
         dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
         e->R = R; e->W = (R + 31) / 32;
         LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
@@ -516,6 +541,7 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
     const int F = e->F;
     drop_borrowed_rows(e);
     if (R != e->R || !e->d_mask) {
+        detach_borrowers(e);
         dev_free(e->d_cat8); dev_free(e->d_wide); dev_free(e->d_mask);
         e->R = R; e->W = (R + 31) / 32;
         LB_TRY(dev_alloc(&e->d_cat8, (size_t)e->F8 * R));
@@ -534,6 +560,9 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
     // the compressed block stays on the device: the sparse scorer (lb_score_rows_diff) reads it
     if (off[8] + 256 > e->diff_bytes) {
         if (e->d_diff) cudaFree(e->d_diff);
+    if (e->d_tpos_ptr) cudaFree(e->d_tpos_ptr);
+    if (e->d_tpos_feature) cudaFree(e->d_tpos_feature);
+    if (e->d_tpos_value) cudaFree(e->d_tpos_value);
         e->d_diff = nullptr; e->diff_bytes = 0;
         LB_CUDA(cudaMalloc(&e->d_diff, off[8] + 256));
         e->diff_bytes = off[8] + 256;
@@ -564,6 +593,7 @@ extern "C" int lb_set_rows_diff(lb_handle h, uint64_t R, const uint8_t *tare_obs
     LB_TRY(lb_launch_validate_rows(e, &bad));
     if (bad) return lb_fail("set_rows_diff: an observed categorical value is out of range for its feature");
     e->diff_valid = true;
+    e->tpos_valid = false;
     return 0;
 }
 

@@ -60,8 +60,8 @@ struct PackSrc {               // out[r] = g2p[assign[r]] narrowed to `width` by
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr, stream3 = nullptr;   // K3s: the width classes of a sweep run side by side
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // K3s / K3f: the classes of a sweep run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sm = 148;
 
@@ -87,6 +87,8 @@ struct Engine {
     // rows
     uint64_t R = 0, W = 0;
     bool rows_borrowed = false;        // row block belongs to another engine (lb_share_rows)
+    Engine *rows_owner = nullptr;      // ... this one; it lists us in `borrowers` until we let go
+    std::vector<Engine *> borrowers;   // engines reading OUR row block: detached before the block is freed or replaced
     uint8_t *d_cat8 = nullptr;
     uint32_t *d_wide = nullptr, *d_mask = nullptr;
 
@@ -105,6 +107,11 @@ struct Engine {
     void *d_diff = nullptr;            // [tare_obs F][tare_val F][row_has_tare R?][pos_ptr R+1][pos_feature][pos_value][neg_ptr R+1][neg_feature]
     size_t diff_bytes = 0, diff_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool diff_valid = false, diff_has_row_flags = false;
+    // the pos cells of TARED columns only (the untared ones are scored densely): built on first use by K1d
+    uint64_t *d_tpos_ptr = nullptr;
+    uint32_t *d_tpos_feature = nullptr, *d_tpos_value = nullptr;
+    size_t tpos_cap_rows = 0, tpos_cap = 0;
+    bool tpos_valid = false;
     void *d_tc_aux = nullptr;          // K1t: producer records, chunk lists and the bf16 operand planes
     size_t tc_aux_bytes = 0;
     int d_kind_ids_cap = 0;

@@ -707,6 +707,12 @@ extern "C" int lb_set_hyper_prior(lb_handle h, const lb_hyper_prior *pr) {
     Engine *e = (Engine *)h;
     for (auto &v : e->hp) v.clear();
     if (!pr) return 0;
+    {   // the grid kernels hold one coordinate's scores in 256 slots (loom's default grids have at most 201 points)
+        const int32_t ns[] = {pr->n_bb_alpha, pr->n_bb_beta, pr->n_dd_alpha, pr->n_dpd_gamma, pr->n_dpd_alpha, pr->n_gp_alpha,
+                              pr->n_gp_inv_beta, pr->n_nich_mu, pr->n_nich_kappa, pr->n_nich_sigmasq, pr->n_nich_nu};
+        for (int32_t n : ns)
+            if (n > 256) return lb_fail("set_hyper_prior: a feature grid has %d points (limit 256)", (int)n);
+    }
     auto put = [&](int i, const float *p, int n, int mult) { if (n > 0) e->hp[i].assign(p, p + (size_t)n * mult); };
     put(0, pr->topology, pr->n_topology, 2); put(1, pr->clustering, pr->n_clustering, 2);
     put(2, pr->bb_alpha, pr->n_bb_alpha, 1); put(3, pr->bb_beta, pr->n_bb_beta, 1);

@@ -39,8 +39,9 @@ def test_make_tare_rules():
 def _equivalence(abi):
     model, rows, _ = synth.generate(600, [("bb", 6), ("dd4", 2), ("gp", 2), ("nich", 2)], density=0.8, seed=4)
     rows.cat8[:4] = (np.random.default_rng(0).random((4, 600)) < 0.05)   # sparse booleans: tare = 0
+    rows.wide[0, :] = 3; rows.wide[0, ::7] = 25; rows.wide[0, ::11] = 5   # a tared count column (mode 3) with counts beyond 16
     to, tv = tare.make_tare(model, rows)
-    assert to[:4].all()
+    assert to[:4].all() and to[model.n8()] == 1 and tv[model.n8()] == 3
     d = tare.sparsify(model, rows, to, tv)
     dense, diff = Engine(abi), Engine(abi)
     for e in (dense, diff):
