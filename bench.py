@@ -621,21 +621,25 @@ def main():
         peaks = json.load(open(ppath))
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    n_sweep = int(launches[1])
+    # one "launch" of the dominant kernel = one sweep call: the four class kernels (16-warp, 8-warp, one-warp, featureless)
+    # run side by side on four streams and the 16-warp class (k_cat_sweep_spec<16>) is the longest; sweep_ms is the device
+    # time from the first kernel's start to the last one's end, relaunch rounds after table growth included
+    n_sweep = args.steps
     sweep_ms = float(kms[1])
     bytes_per_action = algorithmic_bytes_per_action(model, rows, K_all)
-    alg_bytes_per_launch = bytes_per_action * len(pass_acts) * args.steps * S / max(n_sweep, 1)
+    alg_bytes_per_launch = bytes_per_action * len(pass_acts) * S
     avg_launch_ms = sweep_ms / max(n_sweep, 1)
     achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms else 0.0
     traffic = None
     tpath = os.path.join(REPO, "profiles", "r2_k_cat_sweep_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
-        if t.get("workload") == args.workload and t.get("chains") == S and not args.rows:
-            traffic = t.get("dram_bytes_per_launch")           # ncu dram__bytes_{read,write}.sum of one launch
+        if t.get("workload") == args.workload and t.get("chains") == S and t.get("rows") == R:
+            traffic = t.get("dram_bytes_per_launch")           # ncu dram__bytes_{read,write}.sum of one sweep at this size
     roofline = {"bound": "hbm", "kernel": "k_cat_sweep_spec", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": avg_launch_ms, "launches": n_sweep,
+                "avg_launch_ms": avg_launch_ms, "launches": n_sweep, "class_kernels_launched": int(launches[1]),
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "kernel_share_of_step": sweep_ms / (dev_ms or 1.0),
                 "chains_per_launch": S, "algorithmic_bytes_per_row_action": bytes_per_action,
                 "note": "exact sequential Gibbs: a dependent chain per (chain, kind) CTA, bound by the latency of one "

@@ -766,6 +766,12 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
         cudaStream_t s = leader->stream;
         if (w != lead_cls) { s = side[n_side]; LB_CUDA(cudaStreamWaitEvent(s, leader->ev_fork, 0)); }
         const int np = (int)cls[w].size();
+        const bool timing = getenv("LB_SWEEP_TIMING") != nullptr;
+        leader->cls_pairs[w] = timing ? np : 0;
+        if (timing) {
+            if (!leader->cls_ev[w][0]) { LB_CUDA(cudaEventCreate(&leader->cls_ev[w][0])); LB_CUDA(cudaEventCreate(&leader->cls_ev[w][1])); }
+            LB_CUDA(cudaEventRecord(leader->cls_ev[w][0], s));
+        }
         if (w == 2) kernel_of(2)<<<(unsigned)np, 32 * LB_SPEC_WIDER, smem[2], s>>>(d_chains, d_pairs + first[2], np, (int)smem[2]);
         else if (w == 1) kernel_of(1)<<<(unsigned)np, 256, smem[1], s>>>(d_chains, d_pairs + first[1], np, (int)smem[1]);
         else if (w == 0) kernel_of(0)<<<(unsigned)((np + SP_CPB - 1) / SP_CPB), 32 * SP_CPB, smem[0] * SP_CPB, s>>>(
@@ -773,9 +779,11 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
         else k_cat_sweep_flat<<<(unsigned)((np + flat_ppb - 1) / flat_ppb), 32 * flat_ppb, smem[3] * flat_ppb, s>>>(
                  d_chains, d_pairs + first[3], np, (int)smem[3]);
         LB_CUDA(cudaGetLastError());
+        if (timing) LB_CUDA(cudaEventRecord(leader->cls_ev[w][1], s));
         if (w != lead_cls) { LB_CUDA(cudaEventRecord(joined[n_side], s)); ++n_side; }
         leader->launches[LB_L_TOTAL]++; leader->launches[LB_L_SWEEP]++;
     }
+    for (int w : {0, 1, 2, 3}) if (cls[w].empty()) leader->cls_pairs[w] = 0;
     for (int q = 0; q < n_side; ++q) LB_CUDA(cudaStreamWaitEvent(leader->stream, joined[q], 0));
     LB_CUDA(cudaEventRecord(leader->kev1, leader->stream));
     leader->kev_pending = true;

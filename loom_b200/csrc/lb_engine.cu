@@ -745,6 +745,17 @@ static int sweep_chains(const lb_handle *handles, int32_t n_handles, const uint3
         if (chains.empty()) break;
         LB_TRY(lb_launch_sweep_chains(lead, chains.data(), (int)chains.size(), live, live_ids));
         LB_CUDA(cudaStreamSynchronize(lead->stream));
+        if (getenv("LB_SWEEP_TIMING")) {
+            const char *names[4] = {"narrow(1 warp)", "wide(8)", "wider(16)", "flat"};
+            fprintf(stderr, "[LB_SWEEP_TIMING] round %d, %zu chain(s):", round, chains.size());
+            for (int w = 0; w < 4; ++w)
+                if (lead->cls_pairs[w] && lead->cls_ev[w][0]) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, lead->cls_ev[w][0], lead->cls_ev[w][1]) == cudaSuccess)
+                        fprintf(stderr, " %s x%d %.1f ms;", names[w], lead->cls_pairs[w], ms);
+                }
+            fprintf(stderr, "\n");
+        }
         if (lead->kev_pending) {
             float ms = 0.f;
             LB_CUDA(cudaEventElapsedTime(&ms, lead->kev0, lead->kev1));
@@ -774,12 +785,27 @@ static int sweep_chains(const lb_handle *handles, int32_t n_handles, const uint3
             }
             for (int kid : again) {
                 KindHost &k = e->kinds[kid];
+                if (getenv("LB_SWEEP_TIMING"))
+                    fprintf(stderr, "[LB_SWEEP_TIMING]   chain %d kind %d (%zu features) stopped at action %llu of %llu: G %d / %d columns, next id %u / %u\n",
+                            c, kid, k.fids.size(), (unsigned long long)progress[c][kid], (unsigned long long)n, k.G, k.Gcap, k.next_global, k.g2p_cap);
                 if (k.G + 1 > k.Gcap) LB_TRY(lb_kind_grow(e, kid, 2 * k.Gcap));
                 if (k.next_global + 1 > k.g2p_cap) LB_TRY(lb_launch_renumber(e, kid));
             }
             if (!again.empty()) LB_TRY(lb_sync_model(e));
             active[c].swap(again);
         }
+    }
+    // A pair that runs out of columns mid-sweep stops, waits for the whole launch and then runs the rest of its actions
+    // alone (measured: +30 % on a pass when one of 90 pairs does).  Group counts drift by a few per pass, so kinds that
+    // END a sweep within a few columns of their capacity are re-strided now, between sweeps, where it costs microseconds.
+    for (int c = 0; c < n_handles; ++c) {
+        Engine *e = es[c];
+        bool grew = false;
+        for (int kid = 0; kid < (int)e->kinds.size(); ++kid) {
+            KindHost &k = e->kinds[kid];
+            if (k.G + std::max(8, k.G / 8) > k.Gcap) { LB_TRY(lb_kind_grow(e, kid, 2 * k.Gcap)); grew = true; }
+        }
+        if (grew) LB_TRY(lb_sync_model(e));
     }
     return 0;
 }

@@ -62,6 +62,8 @@ struct Engine {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // K3s / K3f: the classes of a sweep run side by side
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+    cudaEvent_t cls_ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // LB_SWEEP_TIMING=1: per-class kernel times
+    int cls_pairs[4] = {0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int n_sm = 148;
 

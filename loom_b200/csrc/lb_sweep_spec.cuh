@@ -48,7 +48,10 @@ constexpr int SP_MAXW = 16;
 #ifndef LB_CO_ADDGROUP
 #define LB_CO_ADDGROUP 1
 #endif
-constexpr int SP_UNROLL = 8;      // cells whose table rows a gathering warp requests before it uses the first
+#ifndef LB_SP_UNROLL
+#define LB_SP_UNROLL 9
+#endif
+constexpr int SP_UNROLL = LB_SP_UNROLL;      // cells whose table rows a gathering warp requests before it uses the first
 
 struct SweepPair { int32_t chain, kid; };
 
