@@ -782,7 +782,7 @@ def main():
         except Exception as exc:
             rates["single_chain_error"] = str(exc)
         if world == 1:
-            for n_ch, n_rows in ((100, 100000), (1008, 20000)):
+            for n_ch, n_rows in ((100, 100000), (1008, 20000), (30, 200000)):
                 r = measure_in_subprocess("sweep_bench.py", [args.workload, n_ch, n_rows, EPHEMERAL], timeout=150,
                                           env={"LB_BENCH_CLOCK_MS": "0"})
                 rates["chains_%d" % n_ch] = ({"cells_per_s": r.get("phases", {}).get("remove_add_pairs", {}).get("cells_per_s"),

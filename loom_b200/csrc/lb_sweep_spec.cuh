@@ -375,7 +375,7 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
         const uint32_t *rv = s_voff + slot * nf, *rs = s_soff + slot * nf, *rr = s_raw + slot * nf, *ro = s_obs + slot * nf;
         for (int g0 = 0; g0 < G; g0 += 32 * PER) {
             const int gl = g0 + PER * lane;
-            if (gl >= st) continue;                        // beyond the tables' columns (G > 128 only)
+            if (gl >= G) continue;                         // this lane's groups do not exist: no table traffic for padding columns
             float acc[PER];
 #pragma unroll
             for (int q = 0; q < PER; ++q) acc[q] = 0.f;

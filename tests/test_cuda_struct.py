@@ -147,3 +147,29 @@ def test_ephemeral_kinds_seated_ahead_of_time_equal_the_direct_draw(oracle_abi, 
         assert np.array_equal(a.get_assignments(k), b.get_assignments(k)), k
         assert np.array_equal(o.get_groups(k)[0], a.get_groups(k)[0])
     assert a.kind_info(o.n_kinds() - 1).sample_size == rows.n_rows
+
+
+def test_featureless_kinds_with_thousands_of_groups_replay(oracle_abi, cuda_abi):
+    """K3f (lb_sweep_flat.cuh): ephemeral kinds whose clustering draw gives thousands of groups (loom's grid reaches
+    alpha = 50, d = 0.36; here alpha = 300, d = 0.5 on 12 000 rows -> ~3 000 groups, 256 per lane block, so both levels
+    of the warp scan and the table growth path run).  Every pick replays on the oracle, final state bit-exact."""
+    model, rows, _ = synth.generate(12000, [("bb", 3)], density=0.8, seed=2, single_kind=True)
+    o, g = both(oracle_abi, cuda_abi, model, rows)
+    grids = {"clustering": [(300.0, 0.5)]}
+    for e in (o, g):
+        e.set_hyper_prior(grids)
+    lockstep_sweep(oracle_abi, o, g, sweep_actions(rows.n_rows), 3)
+    for e in (o, g):
+        e.init_featureless_kinds(2, seed=4)             # seated from PY(300, 0.5): thousands of groups each
+    n_groups = [g.kind_info(k).n_groups for k in range(g.n_kinds())]
+    assert max(n_groups[1:]) > 1500, n_groups
+    acts = sweep_actions(rows.n_rows, add=True, remove=True)
+    lockstep_sweep(oracle_abi, o, g, acts, 5)
+    for k in range(o.n_kinds()):
+        assert np.array_equal(o.get_assignments(k), g.get_assignments(k)), k
+        co, cg = o.get_groups(k)[0], g.get_groups(k)[0]
+        assert np.array_equal(co, cg), k
+    # and once more from the state the device left (counts / id maps written back by the flat kernel)
+    lockstep_sweep(oracle_abi, o, g, acts, 6)
+    for k in range(o.n_kinds()):
+        assert np.array_equal(o.get_assignments(k), g.get_assignments(k)), k
