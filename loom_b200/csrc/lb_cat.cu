@@ -697,6 +697,8 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
     const bool use16 = !w16 || atoi(w16) != 0;
     const char *fl = getenv("LB_SWEEP_FLAT");
     const bool use_flat = !fl || atoi(fl) != 0;
+    const char *wn = getenv("LB_SPEC_WIDE_NF");         // kinds with at least this many columns get an 8-warp CTA
+    const int wide_nf = wn ? std::max(1, atoi(wn)) : SP_WIDE_NF;
     for (int c = 0; c < n; ++c)
         for (int kid : kind_ids[c]) {
             const KindHost &k = engines[c]->kinds[kid];
@@ -710,7 +712,7 @@ static int lb_launch_sweep_spec(Engine *leader, const SweepChain *chains, int n,
                 const int t = engines[c]->specs[f].type;
                 catonly = catonly && (t == LB_BB || t == LB_DD || t == LB_DPD);
             }
-            const int w = nf >= SP_WIDER_NF && use16 ? 2 : (nf >= SP_WIDE_NF ? 1 : 0);
+            const int w = nf >= SP_WIDER_NF && use16 ? 2 : (nf >= wide_nf ? 1 : 0);
             if (nf > SW_PF * 32 * warps_of[w]) return 1;
             if (k.Gcap > SW_MAX_G) return 1;
             smem[w] = std::max(smem[w], (spec_smem_bytes(nf, k.Gcap, warps_of[w]) + 15) / 16 * 16);

@@ -48,6 +48,9 @@ constexpr int SP_MAXW = 16;
 #ifndef LB_CO_ADDGROUP
 #define LB_CO_ADDGROUP 1
 #endif
+#ifndef LB_SP_PREFETCH
+#define LB_SP_PREFETCH 2
+#endif
 #ifndef LB_SP_UNROLL
 #define LB_SP_UNROLL 9
 #endif
@@ -336,6 +339,23 @@ k_cat_sweep_spec(const SweepChain *chains, const SweepPair *pairs, int n_pairs, 
                 }
                 const int at = slot * nf + k;
                 s_voff[at] = vo; s_soff[at] = so; s_ioff[at] = io; s_raw[at] = raw; s_obs[at] = obs;
+#if LB_SP_PREFETCH
+                // the value row this cell will gather SP_AHEAD actions from now: ask the L2 for it today.  With many
+                // chains the tables (10 x 25 MB of value rows on C3) do not fit the L2 and a sweep's time follows its
+                // DRAM bytes (8.7 s at 399 GB, 6.6 s at 223 GB): the misses cost latency inside the gather, not bandwidth.
+                if (vo != zoff) {
+                    const float *row = cache + vo;
+                    const int Gn = ss->G;
+                    for (int g0 = 0; g0 < Gn; g0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + g0));
+#if LB_SP_PREFETCH >= 2
+                    // ... and the count row the update will bump (its column is not known yet: the whole row)
+                    if (so != zoff) {
+                        const uint32_t *crow = ints + io;
+                        for (int g0 = 0; g0 < Gn; g0 += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + g0));
+                    }
+#endif
+                }
+#endif
             }
         }
         if (tid == 0) pf_pg = (pf_is_remove && pf_assign != LB_UNASSIGNED) ? g2p[pf_assign] : LB_UNASSIGNED;
