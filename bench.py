@@ -194,7 +194,7 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
         out = [os.path.join(d, n) for n in ("out.model.pb.gz", "out.groups", "out.assign.pbs.gz")]
         cmd = [exe, os.path.join(d, "config.pb.gz"), os.path.join(d, "rows.pbs.gz"), "--none",
                os.path.join(d, "model.pb.gz"), "--none", "--none", "--none", out[0], out[1], out[2], "--none", "--none"]
-        env = dict(os.environ, LOOM_B200_DEVICE=str(device))
+        env = dict(os.environ, LOOM_B200_DEVICE=str(device), LOOM_B200_TIMING="1")
         t0 = time.perf_counter()
         proc = subprocess.run(cmd, capture_output=True, timeout=timeout, env=env)
         wall = time.perf_counter() - t0
@@ -202,7 +202,9 @@ def measure_loom_infer(model, rows, device=0, exe=None, extra_passes=1.0, timeou
             return {"error": proc.stderr.decode(errors="replace")[-300:]}
         n_assigned = len(pbio.assign_read(out[2])[0])
         cells = n_actions * rows.n_cells() / float(R)
+        phases = [l.strip() for l in proc.stderr.decode(errors="replace").splitlines() if "LOOM_B200_TIMING" in l]
         return {"wall_s": wall, "rows": R, "row_actions": n_actions, "batches": batches, "assigned_rows_out": n_assigned,
+                "phases": phases,
                 "cells_per_s": cells / wall, "extra_passes": extra_passes,
                 "note": "whole process: context + rows.pbs.gz decode + upload + %d batch sweeps (one chain, one CTA per "
                         "kind) + dump to model/groups/assign files" % batches}

@@ -1,8 +1,19 @@
 #!/bin/bash
-mkdir -p gpurun_out
-run() { LB_SWEEP_TIMING=1 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-aux > gpurun_out/z_b.json 2> gpurun_out/z_b.err
-  grep "round 0" gpurun_out/z_b.err | tail -1 | cut -c1-160
-  python -c "
-import json; d=json.load(open('gpurun_out/z_b.json')); print('$1', '%.4g'%d['value'], '%.0f'%d['ms_per_step'], d['roofline_aux']['phases_ms_per_step']['cat_kernel'])"; }
-run "prefetch value rows"
-LOOM_B200_LIB=$PWD/loom_b200/csrc/libloomb200_pf2.so run "prefetch value + count rows"
+python - <<'PY'
+import time, sys, os, ctypes
+t0=time.perf_counter()
+rt=ctypes.CDLL("libcudart.so.12")
+rt.cudaFree(0)
+t1=time.perf_counter(); print("cudaFree(0) = context creation: %.3f s"%(t1-t0))
+sys.path.insert(0,'.')
+from loom_b200 import _abi, Engine, synth
+cuda=_abi.load_cuda(); t2=time.perf_counter(); print("dlopen libloomb200: %.3f s"%(t2-t1))
+e=Engine(cuda); t3=time.perf_counter(); print("lb_create: %.3f s"%(t3-t2))
+m,r,_=synth.generate(2000,[("bb",5),("dd256",5),("gp",5),("nich",5)],seed=1); t4=time.perf_counter()
+e.set_model(m); t5=time.perf_counter(); print("lb_set_model: %.3f s"%(t5-t4))
+e.set_rows(r); t6=time.perf_counter(); print("lb_set_rows: %.3f s"%(t6-t5))
+from loom_b200 import sweep_actions
+e.cat_sweep(sweep_actions(2000),seed=1); t7=time.perf_counter(); print("first sweep (module load of the sweep kernels): %.3f s"%(t7-t6))
+e.cat_sweep(sweep_actions(2000,add=True,remove=True),seed=2); t8=time.perf_counter(); print("second sweep: %.3f s"%(t8-t7))
+PY
+nvidia-smi --query-gpu=persistence_mode --format=csv,noheader

@@ -63,6 +63,13 @@ int lb_comm_hyper_run(lb_handle h, uint64_t seed, double *allreduce_ms);
  * bytes_out / ms_out (optional): payload bytes and device time of the broadcast group. */
 int lb_comm_sync_kinds(lb_handle h, const int32_t *owner, double *bytes_out, double *ms_out);
 
+/* Row-sharded bulk accumulate (ProductMixture::add_value over every row with its given assignment,
+ * src/product_mixture.cc:165-184, as lb_accumulate_rows does on one device): every rank holds the same groups and the
+ * assignments of all rows, zeroes the statistics, adds its share of the rows; counts and integer statistics are summed as
+ * uint32, float statistics as float64 sums (moments are formed after the reduce); one NCCL group of all-reduces.  Every
+ * rank ends with the statistics of all rows. */
+int lb_comm_accumulate_rows(lb_handle h, double *allreduce_ms, double *allreduce_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,7 @@ COMM_SIGNATURES = {
     "comm_max_f64": (C.c_int, [_h, _f64p, C.c_int32]),
     "comm_kind_proposer_score": (C.c_int, [_h, _f32p, C.POINTER(CommRoundStats)]),
     "comm_hyper_run": (C.c_int, [_h, C.c_uint64, _f64p]),
+    "comm_accumulate_rows": (C.c_int, [_h, _f64p, _f64p]),
     "comm_sync_kinds": (C.c_int, [_h, C.POINTER(C.c_int32), _f64p, _f64p]),
 }
 

@@ -1599,7 +1599,7 @@ int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vecto
     return 0;
 }
 
-int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) {
+int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign, bool sums_only) {
     const KindHost &k = e->kinds[kid];
     const int nf = (int)k.fids.size();
     const int items = std::max(1, nf * k.G);
@@ -1619,9 +1619,22 @@ int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign) 
         LB_TRY(lb_launch_accum_features(e, e->d_feats, k.fids, {AccTarget{d_packed, k.ints, k.flts, k.Gcap, k.G, width}},
                                         b, en, sign, LB_L_ACCUM));
     }
+    if (sums_only) { LB_CUDA(cudaGetLastError()); e->launches[LB_L_TOTAL] += nf ? 1 : 0; e->launches[LB_L_ACCUM] += nf ? 1 : 0; return 0; }
     if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
     LB_CUDA(cudaGetLastError());
     e->launches[LB_L_TOTAL] += nf ? 2 : 0; e->launches[LB_L_ACCUM] += nf ? 2 : 0;
+    return lb_launch_refresh(e, kid);
+}
+
+// the second half of a row-sharded accumulate: the tables hold SUMS (sum x, sum x^2 for NICH; every other statistic
+// is a sum anyway) that have been added up over the ranks; back to moments, cached scorers rebuilt
+int lb_launch_sums_to_moments(Engine *e, int kid) {
+    const KindHost &k = e->kinds[kid];
+    const int nf = (int)k.fids.size();
+    const int g1 = std::min((std::max(1, nf * k.G) + 255) / 256, e->n_sm * 4);
+    if (nf) k_sums_to_moments<<<g1, 256, 0, e->stream>>>(e->d_kinds, kid, e->d_feats, e->d_kind_feats);
+    LB_CUDA(cudaGetLastError());
+    e->launches[LB_L_TOTAL] += nf ? 1 : 0; e->launches[LB_L_ACCUM] += nf ? 1 : 0;
     return lb_launch_refresh(e, kid);
 }
 

@@ -335,3 +335,66 @@ extern "C" int lb_comm_sync_kinds(lb_handle h, const int32_t *owner, double *byt
     if (ms_out) { float ms = 0; LB_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); *ms_out = ms; }
     return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-sharded bulk accumulate (K2; ProductMixture::add_value over all rows with given assignments,
+// src/product_mixture.cc:165-184).  Every rank holds the same groups and the assignments of ALL rows; it zeroes the
+// statistics, adds rows [R r / N, R (r + 1) / N), and the tables are summed over the ranks: clustering counts and the
+// integer statistics as uint32 (exact in any order), the float statistics as float64 SUMS (GP sum log x!, NICH sum x and
+// sum x^2 -- the moments are formed after the reduce, as in the proposer).  One NCCL group per kind.  Every rank ends
+// with the statistics a single-device lb_accumulate_rows over all rows leaves.
+extern "C" int lb_comm_accumulate_rows(lb_handle h, double *allreduce_ms, double *allreduce_bytes) {
+    Engine *e = (Engine *)h;
+    LB_CUDA(cudaSetDevice(e->device));
+    Comm *c = comm_of(e);
+    const int world = c ? c->world : 1, rank = c ? c->rank : 0;
+    if (allreduce_ms) *allreduce_ms = 0.0;
+    if (allreduce_bytes) *allreduce_bytes = 0.0;
+    LB_TRY(lb_sync_model(e));
+    LB_TRY(lb_pull_kinds(e));
+    const int K = (int)e->kinds.size();
+    const uint64_t lo = e->R * (uint64_t)rank / world, hi = e->R * (uint64_t)(rank + 1) / world;
+    for (int kid = 0; kid < K; ++kid) {
+        KindHost &k = e->kinds[kid];
+        const size_t cap = (size_t)k.Gcap;
+        LB_CUDA(cudaMemsetAsync(k.counts, 0, 4 * cap, e->stream));
+        if (k.n_int_rows) LB_CUDA(cudaMemsetAsync(k.ints, 0, 4 * (size_t)k.n_int_rows * cap, e->stream));
+        if (k.n_flt_rows) LB_CUDA(cudaMemsetAsync(k.flts, 0, 8 * (size_t)k.n_flt_rows * cap, e->stream));
+        k.sample_size = 0;
+    }
+    LB_TRY(lb_sync_model(e));
+    double bytes = 0.0;
+    for (int kid = 0; kid < K; ++kid) LB_TRY(lb_launch_accumulate(e, kid, lo, hi, +1, /*sums_only=*/true));
+    if (world > 1) {
+        LB_CUDA(cudaEventRecord(c->ev[0], e->stream));
+        LB_NCCL(ncclGroupStart());
+        for (int kid = 0; kid < K; ++kid) {
+            KindHost &k = e->kinds[kid];
+            const size_t cap = (size_t)k.Gcap;
+            LB_NCCL(ncclAllReduce(k.counts, k.counts, cap, ncclUint32, ncclSum, c->comm, e->stream));
+            bytes += 4.0 * cap;
+            if (k.n_int_rows) { LB_NCCL(ncclAllReduce(k.ints, k.ints, (size_t)k.n_int_rows * cap, ncclUint32, ncclSum, c->comm, e->stream)); bytes += 4.0 * k.n_int_rows * cap; }
+            if (k.n_flt_rows) { LB_NCCL(ncclAllReduce(k.flts, k.flts, (size_t)k.n_flt_rows * cap, ncclFloat64, ncclSum, c->comm, e->stream)); bytes += 8.0 * k.n_flt_rows * cap; }
+        }
+        LB_NCCL(ncclGroupEnd());
+        LB_CUDA(cudaEventRecord(c->ev[1], e->stream));
+    }
+    // sample sizes follow the summed counts
+    for (int kid = 0; kid < K; ++kid) {
+        KindHost &k = e->kinds[kid];
+        std::vector<uint32_t> counts((size_t)std::max(k.G, 1));
+        LB_CUDA(cudaMemcpyAsync(counts.data(), k.counts, 4 * (size_t)k.G, cudaMemcpyDeviceToHost, e->stream));
+        LB_CUDA(cudaStreamSynchronize(e->stream));
+        uint64_t n = 0;
+        for (int g = 0; g < k.G; ++g) n += counts[g];
+        k.sample_size = n;
+    }
+    LB_TRY(lb_sync_model(e));
+    for (int kid = 0; kid < K; ++kid) LB_TRY(lb_launch_sums_to_moments(e, kid));
+    LB_CUDA(cudaStreamSynchronize(e->stream));
+    lb_free_proposer(e);
+    if (world > 1 && allreduce_ms) { float ms = 0; LB_CUDA(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); *allreduce_ms = ms; }
+    if (allreduce_bytes) *allreduce_bytes = bytes;
+    return 0;
+}

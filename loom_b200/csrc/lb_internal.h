@@ -207,7 +207,8 @@ int lb_launch_score_rows(Engine *e, int kid, uint64_t b, uint64_t en, float *d_o
 int lb_launch_score_rows_tc(Engine *e, int kid, uint64_t b, uint64_t en, const float *d_tab, const int32_t *row_base,
                             int K_total, float *d_out, int planes, int *used);   // lb_score_tc.cu
 int lb_launch_score_rows_diff(Engine *e, int kid, uint64_t b, uint64_t en, float *d_out);
-int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign);
+int lb_launch_accumulate(Engine *e, int kid, uint64_t b, uint64_t en, int sign, bool sums_only = false);
+int lb_launch_sums_to_moments(Engine *e, int kid);
 int lb_launch_accum_features(Engine *e, const FeatDev *d_feats, const std::vector<int> &fids,
                              const std::vector<AccTarget> &targets, uint64_t b, uint64_t en, int sign,
                              int launch_family);

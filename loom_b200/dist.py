@@ -93,3 +93,10 @@ def sync_kinds(engine, owner):
     b, ms = C.c_double(), C.c_double()
     engine.abi.check(engine.abi.comm_sync_kinds(engine.h, owner.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(b), C.byref(ms)))
     return b.value, ms.value
+
+
+def sharded_accumulate_rows(engine):
+    """bulk accumulate with the rows dealt over the ranks and the tables all-reduced; returns (all-reduce ms, bytes)"""
+    ms, b = C.c_double(), C.c_double()
+    engine.abi.check(engine.abi.comm_accumulate_rows(engine.h, C.byref(ms), C.byref(b)))
+    return ms.value, b.value

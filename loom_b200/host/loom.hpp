@@ -161,7 +161,12 @@ public:
 
     // Loom::infer_multi_pass (src/loom.cc:167-215)
     void infer_multi_pass(const char *rows_in, const char *checkpoint_in = nullptr, const char *checkpoint_out = nullptr) {
+        const bool timing = std::getenv("LOOM_B200_TIMING") != nullptr;
+        const auto t_begin = std::chrono::steady_clock::now();
         rows_load(rows_in);
+        if (timing)
+            std::fprintf(stderr, "[LOOM_B200_TIMING]   rows decode + upload       %8.1f ms\n",
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         const uint64_t R = row_count();
         ScheduleConfig sc;
         sc.extra_passes = config_.extra_passes;

@@ -7,6 +7,7 @@
 //
 // `--none` = absent; names ending in .gz are gzip-compressed (src/args.hpp:56-64).
 // LOOM_B200_DEVICE selects the GPU (default 0).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,18 +57,32 @@ int main(int argc, char **argv) {
     const char *checkpoint_out = pop_optional_file();
     const char *log_out = pop_optional_file();
 
+    // LOOM_B200_TIMING=1: wall clock of the process's phases on stderr (where a run's seconds go: DESIGN.md 9)
+    const bool timing = std::getenv("LOOM_B200_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[LOOM_B200_TIMING] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     lbio_config config;
     LOOM_B200_IO(lbio_config_read(config_in, &config));
     const char *device_env = std::getenv("LOOM_B200_DEVICE");
     loom::b200::Loom engine(config, model_in, groups_in, assign_in, tares_in, device_env ? std::atoi(device_env) : 0);
     if (log_out) engine.log_to(log_out, checkpoint_in != nullptr);   // append when resuming (src/infer.cc:83-89)
+    lap("context + model + groups");
 
     if (config.extra_passes > 0) {
         engine.infer_multi_pass(rows_in, checkpoint_in, checkpoint_out);
+        lap("infer_multi_pass");
         engine.dump(model_out, groups_out, assign_out);
+        lap("dump");
     } else {
         engine.infer_single_pass(rows_in, assign_out);
+        lap("infer_single_pass");
         engine.dump(model_out, groups_out);
+        lap("dump");
     }
     return 0;
 }

@@ -235,6 +235,21 @@ more = sweep_actions(3000, add=True, remove=True)    # and the chain goes on fro
 one.cat_sweep(more, seed=22, action_offset=len(acts)); sh.cat_sweep(more, seed=22, action_offset=len(acts))
 for k in range(K):
     assert np.array_equal(one.get_assignments(k), sh.get_assignments(k)), k
+# --- row-sharded bulk accumulate (K2) == the single-device accumulate: integers bit-exact, float64 moments to 1e-9
+acc_ref, acc = engine(), engine(False)
+for k in range(K):
+    uniq, inv = np.unique(truth["assign"][k].astype(np.uint32), return_inverse=True)
+    acc.set_groups(k, len(uniq)); acc.set_assignments(k, inv.astype(np.uint32))
+dist.init(acc, rank, world, tag={tag!r} + "a")
+ar_ms, ar_bytes = dist.sharded_accumulate_rows(acc)
+assert ar_bytes > 0
+for k in range(K):
+    (c0, i0, f0), (c1, i1, f1) = acc_ref.get_groups(k), acc.get_groups(k)
+    assert np.array_equal(c0, c1) and np.array_equal(i0, i1), k
+    assert np.allclose(f0, f1, rtol=1e-9, atol=1e-9), k
+    assert acc_ref.kind_info(k).sample_size == acc.kind_info(k).sample_size
+    assert np.abs(acc_ref.score_rows(k, 0, 64) - acc.score_rows(k, 0, 64)).max() <= 1e-5
+assert abs(acc_ref.score_data() - acc.score_data()) <= 1e-9 * abs(acc_ref.score_data())
 dist.barrier(e)
 print("rank %d ok: proposer err %.2e allreduce %.0f B %.3f ms, allgather %.0f B, sync_kinds %.0f B %.3f ms" % (
     rank, err.max(), stats["allreduce_bytes"], stats["allreduce_ms"], stats["allgather_bytes"], nbytes, ms), flush=True)
