@@ -947,6 +947,9 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
         prior[jj] = g < G ? (kd.counts[g] ? kd.shifted[g] : sh_empty) + base : 0.f;
     }
     const float *tabg = tab + g_base + lane;
+    bool live[NJ];                      // this lane's groups that exist: padding columns are never loaded (the gather is
+#pragma unroll                          // L2-bandwidth-bound on DD-256 kinds: 68 groups in 128 columns was 47 % wasted sectors)
+    for (int jj = 0; jj < NJ; ++jj) live[jj] = g_base + lane + 32 * jj < G;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t r0 = b + tile * SC_TR;
         float acc[SC_RW][NJ];
@@ -1035,7 +1038,7 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
                             }
                         } else {
 #pragma unroll
-                            for (int jj = 0; jj < NJ; ++jj) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
+                            for (int jj = 0; jj < NJ; ++jj) if (live[jj]) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
                         }
                     }
                 } else {
@@ -1043,7 +1046,7 @@ k_score_rows(const KindDev *kinds, int kid, const FeatDev *feats, const int32_t 
                     for (int q = 0; q < SC_RW; ++q) {
                         const uint32_t row = s_row[j][warp * SC_RW + q];
 #pragma unroll
-                        for (int jj = 0; jj < NJ; ++jj) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
+                        for (int jj = 0; jj < NJ; ++jj) if (live[jj]) acc[q][jj] += tabg[(size_t)row * st + 32 * jj];
                     }
                 }
             }

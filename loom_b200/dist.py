@@ -23,7 +23,9 @@ ID_BYTES = 128
 
 def exchange_unique_id(abi, rank, world, tag=None, timeout=120.0):
     """rank 0 calls ncclGetUniqueId and publishes the bytes in a file; the other ranks wait for it."""
-    tag = tag or "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+    # all ranks of one launch are children of one launcher process (torchrun's agent, a test's Popen loop): its pid makes
+    # the file name unique to the launch, so a file a crashed earlier run left behind under the same port is never read
+    tag = "%s_%s_%d" % (tag or os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"), os.getppid())
     path = os.path.join(tempfile.gettempdir(), "loom_b200_nccl_id_%s" % tag)
     if rank == 0:
         buf = np.zeros(ID_BYTES, np.uint8)
