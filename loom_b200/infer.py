@@ -79,6 +79,8 @@ class AcceleratingSchedule:
             return self.base
         if row_count > self.big:
             return 0.0
+        if self.small == 0:           # the reference divides by log(big / 0) = inf: power 0, one pass (IEEE arithmetic in C++)
+            return 0.0
         power = math.log(self.big / row_count) / math.log(self.big / self.small)
         passes = (1.0 + self.base) ** power
         return passes - 1.0 if passes > 2.0 else 0.0

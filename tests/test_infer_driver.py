@@ -150,3 +150,38 @@ def test_default_config_and_grids_are_wired(oracle_abi):
 def test_infer_multi_pass_on_the_gpu(cuda_abi):
     _check(*_run(cuda_abi, 3, 0), kinds_may_move=False)
     _check(*_run(cuda_abi, 2, 4), kinds_may_move=True)
+
+
+def test_schedules_reproduce_the_reference_binary():
+    """The ONE piece of the path whose reference implementation runs in the build container: src/schedules.hpp, compiled
+    in place (oracle/Makefile `ref`) and driven through loom.cc's loop; its ADD / REMOVE decisions and batch boundaries
+    are the committed fixture (tests/golden/make_reference_schedules.py).  The product's schedule driver must make
+    exactly the same decisions: this pins WHEN every kernel fires against the reference itself."""
+    import json
+    import os
+    from loom_b200 import infer as driver
+    fixture = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_schedules.json")))
+    assert len(fixture["cases"]) >= 10
+    for case in fixture["cases"]:
+        R = case["rows"]
+        accelerating = driver.AcceleratingSchedule(case["extra_passes"], case["small"], case["big"])
+        annealing = driver.AnnealingSchedule(case["extra_passes"])
+        annealing.set_extra_passes(accelerating.extra_passes(0))
+        batching, window = driver.BatchingSchedule(0), driver.RowWindow(R)
+        limit = case["max_actions"] or float("inf")
+        assigned, text, n = 0, [], 0
+        while assigned != R and n < limit:
+            acts, assigned, boundary = driver.next_batch(R, assigned, annealing, batching, window)
+            text.append("".join("R" if a & 1 else "A" for a in acts))
+            n += len(acts)
+            if boundary:
+                text.append("|")
+                annealing.set_extra_passes(accelerating.extra_passes(assigned))
+        got = "".join(text)
+        want = case["decisions"]
+        if case["assigned"] != R:                    # the reference run was cut by max_actions: compare the common prefix
+            k = min(len(got), len(want))
+            assert k > 5000 and got[:k] == want[:k], (case["extra_passes"], case["small"], case["big"], R)
+        else:
+            assert got == want, (case["extra_passes"], case["small"], case["big"], R)
+            assert assigned == case["assigned"] == R
