@@ -1,0 +1,38 @@
+// TEST INFRASTRUCTURE.  Stand-in for <distributions/random.hpp> of forcedotcom/distributions 2.0.28 (un-vendored; see
+// DESIGN.md section 2) so that the reference's OWN src/kind_proposer.cc compiles here.  `rng_t` is a SCRIPTED source:
+// the uniforms come from a list the harness supplies, so that the reference's decisions can be compared draw for draw
+// with the oracle's (which consumes the same uniforms from its Philox stream).  sample_from_likelihoods restates the
+// library's published inverse-CDF walk (random.hpp: t = total * unif01; subtract until negative; last index otherwise).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+namespace distributions {
+typedef std::vector<float> VectorFloat;
+struct rng_t {
+    const std::vector<double> *script;
+    size_t pos;
+    rng_t() : script(nullptr), pos(0) {}
+    explicit rng_t(uint64_t) : script(nullptr), pos(0) {}          // the per-feature generators of infer_assignments: unused by the stubs
+    explicit rng_t(const std::vector<double> &s) : script(&s), pos(0) {}
+    uint64_t operator()() { return 0; }                            // `seed = rng()`: does not consume the script
+    double next() {
+        if (!script || pos >= script->size()) std::abort();        // a draw the harness did not foresee is an error
+        return (*script)[pos++];
+    }
+};
+inline std::vector<uint32_t> &pick_log() { static std::vector<uint32_t> log; return log; }   // every draw, in order
+inline std::vector<float> &total_log() { static std::vector<float> log; return log; }      // and the total it was drawn against
+inline float sample_unif01(rng_t &rng) { return (float)rng.next(); }
+inline size_t sample_from_likelihoods(rng_t &rng, const VectorFloat &likelihoods, float total_likelihood) {
+    const size_t size = likelihoods.size();
+    float t = total_likelihood * sample_unif01(rng);
+    for (size_t i = 0; i < size; ++i) {
+        t -= likelihoods[i];
+        if (t < 0) { pick_log().push_back((uint32_t)i); total_log().push_back(total_likelihood); return i; }
+    }
+    pick_log().push_back((uint32_t)(size - 1)); total_log().push_back(total_likelihood);
+    return size - 1;
+}
+}  // namespace distributions

@@ -185,3 +185,22 @@ def test_schedules_reproduce_the_reference_binary():
         else:
             assert got == want, (case["extra_passes"], case["small"], case["big"], R)
             assert assigned == case["assigned"] == R
+
+
+def test_cpp_host_schedules_reproduce_the_reference_binary(tmp_path):
+    """Same fixture, the C++ host: the schedule classes of loom_b200/host/loom_b200.hpp (what loom_infer runs), compiled
+    into tests/cpp/host_schedules_main.cc's loop, must print the reference's decision string."""
+    import json
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "host_schedules")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(here, "cpp", "host_schedules_main.cc")])
+    fixture = json.load(open(os.path.join(here, "golden", "reference_schedules.json")))
+    for case in fixture["cases"]:
+        args = [repr(case["extra_passes"]), repr(case["small"]), repr(case["big"]), str(case["rows"])]
+        if case["max_actions"]:
+            args.append(str(case["max_actions"]))
+        decisions, assigned = subprocess.check_output([exe] + args).decode().split()
+        assert decisions == case["decisions"], args
+        assert int(assigned) == case["assigned"]
