@@ -1,0 +1,151 @@
+// TEST INFRASTRUCTURE.  Stand-in for the protoc-generated <loom/schema.pb.h> (protoc is not in this image) covering the
+// messages the reference's value path touches -- ProductValue, ProductValue.Observed, ProductValue.Diff, Row
+// (src/schema.proto) -- as plain structs with the accessor names protoc generates, over a minimal RepeatedField.
+// ProductModel / HyperPrior exist only so that src/protobuf.hpp's Fields<> declarations parse.  Written from
+// schema.proto's field list and protobuf's public C++ API; nothing of the reference is copied.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <exception>
+#include <ostream>
+#include <string>
+#include <vector>
+namespace google { namespace protobuf {
+struct FatalException : std::exception {};          // what the reference's try blocks around protobuf calls catch
+template <class T> class RepeatedField {
+    std::vector<T> v_;
+
+public:
+    typedef typename std::vector<T>::iterator iterator;
+    typedef typename std::vector<T>::const_iterator const_iterator;
+    int size() const { return (int)v_.size(); }
+    const T &Get(int i) const { return v_[i]; }
+    void Set(int i, const T &x) { v_[i] = x; }
+    void Add(const T &x) { v_.push_back(x); }
+    void AddAlreadyReserved(const T &x) { v_.push_back(x); }
+    void Reserve(int n) { v_.reserve(n); }
+    void Clear() { v_.clear(); }
+    void CopyFrom(const RepeatedField &o) { v_ = o.v_; }
+    iterator begin() { return v_.begin(); }
+    iterator end() { return v_.end(); }
+    const_iterator begin() const { return v_.begin(); }
+    const_iterator end() const { return v_.end(); }
+    bool operator==(const RepeatedField &o) const { return v_ == o.v_; }
+};
+// std::vector<bool> has proxy iterators; the reference writes `*it = true` and reads `*it++` through protobuf's plain
+// bool arrays, so booleans are stored as bytes
+template <> class RepeatedField<bool> {
+    std::vector<unsigned char> v_;
+
+public:
+    typedef bool *iterator;
+    typedef const bool *const_iterator;
+    static_assert(sizeof(bool) == 1, "bool is one byte");
+    int size() const { return (int)v_.size(); }
+    bool Get(int i) const { return v_[i] != 0; }
+    void Set(int i, bool x) { v_[i] = x; }
+    void Add(bool x) { v_.push_back(x); }
+    void AddAlreadyReserved(bool x) { v_.push_back(x); }
+    void Reserve(int n) { v_.reserve(n); }
+    void Clear() { v_.clear(); }
+    iterator begin() { return reinterpret_cast<bool *>(v_.data()); }
+    iterator end() { return begin() + v_.size(); }
+    const_iterator begin() const { return reinterpret_cast<const bool *>(v_.data()); }
+    const_iterator end() const { return begin() + v_.size(); }
+    bool operator==(const RepeatedField &o) const { return v_ == o.v_; }
+};
+template <class T> inline std::ostream &operator<<(std::ostream &os, const RepeatedField<T> &f) {   // error messages only
+    os << "[";
+    for (int i = 0; i < f.size(); ++i) os << (i ? "," : "") << f.Get(i);
+    return os << "]";
+}
+}}  // namespace google::protobuf
+
+namespace protobuf { namespace loom {
+using google::protobuf::RepeatedField;
+
+struct ProductValue {
+    struct Observed {
+        enum Sparsity { NONE = 0, SPARSE = 1, DENSE = 2, ALL = 3 };          // src/schema.proto:76-81
+        static const char *Sparsity_Name(Sparsity s) {
+            static const char *names[] = {"NONE", "SPARSE", "DENSE", "ALL"};
+            return names[(int)s];
+        }
+        Sparsity sparsity_ = NONE;
+        RepeatedField<bool> dense_;
+        RepeatedField<uint32_t> sparse_;
+        Sparsity sparsity() const { return sparsity_; }
+        void set_sparsity(Sparsity s) { sparsity_ = s; }
+        const RepeatedField<bool> &dense() const { return dense_; }
+        RepeatedField<bool> *mutable_dense() { return &dense_; }
+        bool dense(int i) const { return dense_.Get(i); }
+        void add_dense(bool x) { dense_.Add(x); }
+        void set_dense(int i, bool x) { dense_.Set(i, x); }
+        int dense_size() const { return dense_.size(); }
+        bool has_dense() const { return dense_.size() != 0; }
+        void clear_dense() { dense_.Clear(); }
+        const RepeatedField<uint32_t> &sparse() const { return sparse_; }
+        RepeatedField<uint32_t> *mutable_sparse() { return &sparse_; }
+        uint32_t sparse(int i) const { return sparse_.Get(i); }
+        void add_sparse(uint32_t x) { sparse_.Add(x); }
+        int sparse_size() const { return sparse_.size(); }
+        void clear_sparse() { sparse_.Clear(); }
+        void Clear() { sparsity_ = NONE; dense_.Clear(); sparse_.Clear(); }
+    };
+    struct Diff;
+    Observed observed_;
+    RepeatedField<bool> booleans_;
+    RepeatedField<uint32_t> counts_;
+    RepeatedField<float> reals_;
+    const Observed &observed() const { return observed_; }
+    Observed *mutable_observed() { return &observed_; }
+#define LB_STUB_REPEATED(T, name)                                            \
+    const RepeatedField<T> &name() const { return name##_; }                 \
+    RepeatedField<T> *mutable_##name() { return &name##_; }                  \
+    T name(int i) const { return name##_.Get(i); }                           \
+    void add_##name(T x) { name##_.Add(x); }                                 \
+    void set_##name(int i, T x) { name##_.Set(i, x); }                       \
+    int name##_size() const { return name##_.size(); }                       \
+    void clear_##name() { name##_.Clear(); }
+    LB_STUB_REPEATED(bool, booleans)
+    LB_STUB_REPEATED(uint32_t, counts)
+    LB_STUB_REPEATED(float, reals)
+#undef LB_STUB_REPEATED
+    void Clear() { observed_.Clear(); booleans_.Clear(); counts_.Clear(); reals_.Clear(); }
+    std::string ShortDebugString() const { return "<ProductValue>"; }
+};
+struct ProductValue::Diff {
+    ProductValue pos_, neg_;
+    RepeatedField<uint32_t> tares_;
+    const ProductValue &pos() const { return pos_; }
+    ProductValue *mutable_pos() { return &pos_; }
+    const ProductValue &neg() const { return neg_; }
+    ProductValue *mutable_neg() { return &neg_; }
+    const RepeatedField<uint32_t> &tares() const { return tares_; }
+    RepeatedField<uint32_t> *mutable_tares() { return &tares_; }
+    uint32_t tares(int i) const { return tares_.Get(i); }
+    void add_tares(uint32_t x) { tares_.Add(x); }
+    int tares_size() const { return tares_.size(); }
+    void clear_tares() { tares_.Clear(); }
+    void Clear() { pos_.Clear(); neg_.Clear(); tares_.Clear(); }
+};
+struct Row {
+    uint64_t id_ = 0;
+    ProductValue::Diff diff_;
+    uint64_t id() const { return id_; }
+    void set_id(uint64_t x) { id_ = x; }
+    const ProductValue::Diff &diff() const { return diff_; }
+    ProductValue::Diff *mutable_diff() { return &diff_; }
+    void Clear() { id_ = 0; diff_.Clear(); }
+};
+// only so that the Fields<> specialisations of src/protobuf.hpp parse
+struct FieldListStub {
+    int bb() const { return 0; } int dd() const { return 0; } int dpd() const { return 0; }
+    int gp() const { return 0; } int nich() const { return 0; }
+    int *mutable_bb() { return nullptr; } int *mutable_dd() { return nullptr; } int *mutable_dpd() { return nullptr; }
+    int *mutable_gp() { return nullptr; } int *mutable_nich() { return nullptr; }
+};
+struct ProductModel { struct Shared : FieldListStub {}; struct Group : FieldListStub {}; };
+struct HyperPrior : FieldListStub {};
+inline std::ostream &operator<<(std::ostream &os, const ProductValue &v) { return os << v.ShortDebugString(); }
+}}  // namespace protobuf::loom

@@ -6,6 +6,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
@@ -76,3 +77,88 @@ def test_block_pitman_yor_totals_match_the_reference():
                 assign[f] = int(picks[it, f])
                 counts[assign[f]] += 1
     assert worst < 2e-6, worst
+
+
+# ------------------------------------------------------------------------------------------ loom::Differ (tare, sparsify)
+def _differ_cases():
+    return json.load(open(os.path.join(HERE, "golden", "reference_differ.json")))["cases"]
+
+
+def _model_of(types):
+    from loom_b200 import synth
+    from loom_b200.engine import Model
+    feats = synth.make_features([tuple(t) for t in types])
+    return Model(feats, np.zeros(len(feats), np.uint32), kind_py=[synth.CLUSTERING], topology=synth.CLUSTERING)
+
+
+def _cells(model, value):
+    """a fixture ProductValue -> (feature ids, raw uint32 cells in the engine's encoding: NICH as float bits)"""
+    feats = list(value["features"])
+    vals = list(value["booleans"]) + list(value["counts"]) + [int(np.float32(x).view(np.uint32)) for x in value["reals"]]
+    assert len(vals) == len(feats)
+    return feats, vals
+
+
+def differ_matches_the_reference(abi, tmp_path=None):
+    """Differ::add_rows -> get_tare and Differ::compress_rows of the reference (tests/golden/reference_differ.json, from
+    src/differ.cc compiled unmodified) against the engine's differ_* entry points on the same tables: the tare row,
+    and for every row the features and values of pos and the features of neg, bit for bit.  With tmp_path the rows are
+    also written through the product's codec and read back with google.protobuf: the representation of every
+    pos / neg (NONE / SPARSE / DENSE / ALL, ValueSchema::normalize_small), neg's values (the tare's) and the `tares`
+    field must be the reference's too."""
+    from loom_b200 import Engine
+    from loom_b200.engine import RowBlock
+    checked = 0
+    for case in _differ_cases():
+        model = _model_of(case["types"])
+        table = case["table"]
+        e = Engine(abi)
+        e.set_model(model)
+        e.set_rows(RowBlock.from_table(model, table))
+        obs, val = e.make_tare()
+        want_f, want_v = _cells(model, case["tare"])
+        assert np.flatnonzero(obs).tolist() == want_f, case["name"]
+        assert val[want_f].tolist() == want_v, case["name"]
+        d = e.sparsify(obs, val)
+        for r, row in enumerate(case["rows"]):
+            pf, pv = _cells(model, row["pos"])
+            nf, nv = _cells(model, row["neg"])
+            p0, p1 = int(d["pos_ptr"][r]), int(d["pos_ptr"][r + 1])
+            n0, n1 = int(d["neg_ptr"][r]), int(d["neg_ptr"][r + 1])
+            assert d["pos_feature"][p0:p1].tolist() == pf and d["pos_value"][p0:p1].tolist() == pv, (case["name"], r)
+            assert d["neg_feature"][n0:n1].tolist() == nf, (case["name"], r)
+            assert val[nf].tolist() == nv, (case["name"], r)        # neg carries the tare's values (differ.cc:277-286)
+            assert row["tares"] == (1 if want_f else 0)
+            checked += 1
+        if tmp_path is not None:
+            import pb_schema
+            from loom_b200 import pbio
+            mf = pbio.ModelFile.create(model, None, None)
+            tared = np.full(len(table), 1 if want_f else 0, np.uint8)
+            out = pbio.Rows(np.arange(len(table)), tared, d["pos_ptr"], d["pos_feature"], d["pos_value"], d["neg_ptr"], d["neg_feature"])
+            path = tmp_path / (case["name"] + ".pbs.gz")
+            pbio.rows_write(path, mf, out, tare_values=val)
+            msgs = pb_schema.load_stream(path, pb_schema.messages()["Row"])
+            names = {0: "NONE", 1: "SPARSE", 2: "DENSE", 3: "ALL"}
+            for r, (m, row) in enumerate(zip(msgs, case["rows"])):
+                assert m.id == row["id"]
+                for side, got in (("pos", m.diff.pos), ("neg", m.diff.neg)):
+                    want = row[side]
+                    assert names[got.observed.sparsity] == want["sparsity"], (case["name"], r, side)
+                    if want["sparsity"] == "SPARSE":
+                        assert list(got.observed.sparse) == want["features"]
+                    if want["sparsity"] == "DENSE":
+                        assert np.flatnonzero(list(got.observed.dense)).tolist() == want["features"]
+                    assert [int(b) for b in got.booleans] == want["booleans"] and list(got.counts) == want["counts"]
+                    assert np.array_equal(np.asarray(list(got.reals), np.float32), np.asarray(want["reals"], np.float32))
+                assert len(m.diff.tares) == row["tares"]
+    assert checked >= 470
+
+
+def test_oracle_differ_reproduces_the_reference(oracle_abi, tmp_path):
+    differ_matches_the_reference(oracle_abi, tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_differ_reproduces_the_reference(cuda_abi, tmp_path):
+    differ_matches_the_reference(cuda_abi, tmp_path)
