@@ -1,7 +1,9 @@
 /*
  * oracle_structure.c -- CPU restatement of loom's kind kernel and hyper kernel
  * (float64).  TEST INFRASTRUCTURE ONLY; PARITY UNPINNED vs the reference
- * binary (see loom_oracle.h).  Control flow follows:
+ * binary (see loom_oracle.h), except oracle_block_py, which reproduces the
+ * reference's own compiled kind_proposer.cc draw for draw
+ * (tests/test_reference_pins.py).  Control flow follows:
  *   src/kind_kernel.hpp:193-217       add_to_kind_proposer (bulk form)
  *   src/kind_proposer.cc:131-362      BlockPitmanYorSampler, infer_assignments
  *   src/kind_kernel.cc:83-255         move_features, init_featureless_kinds
