@@ -46,6 +46,12 @@ double lo_feature_score_data(const lb_feature_spec *spec, const float *aux,
                              const uint32_t *ints, const double *flts);
 double lo_py_score_counts(double alpha, double d, const uint32_t *counts, int n);
 
+/* Replace the score matrix L[f][k] ([F][K], row f = feature f) that kind_proposer_score computed, keeping the
+ * proposer's tables: lets tests/test_reference_pins.py drive kind_run + init_featureless_kinds with the score
+ * matrices the compiled reference KindKernel was driven with (oracle/ref_kind_kernel_main.cc).  Checker-only:
+ * the product library has no such entry point. */
+int lo_set_proposer_scores(lb_handle h, const float *scores);
+
 /* Number of OpenMP threads the kind-parallel sweep / feature-parallel scoring
  * may use (reference threading model: one thread per kind,
  * src/cat_pipeline.cc:103-125; OMP over features src/kind_proposer.cc:339). */

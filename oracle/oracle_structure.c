@@ -129,6 +129,13 @@ int lo_kind_proposer_score(lb_handle h, float *out) {
     return rc ? rc : lo_proposer_finish(h, out);
 }
 
+int lo_set_proposer_scores(lb_handle h, const float *scores) {
+    engine_t *e = h;
+    if (!e->prop_scores || e->prop_K != e->K) return lo_fail("set_proposer_scores: call kind_proposer_score first");
+    memcpy(e->prop_scores, scores, sizeof(float) * (size_t)e->F * e->K);
+    return 0;
+}
+
 /* ---- Block Pitman-Yor sampler (src/kind_proposer.cc:131-300) ------------ */
 static double likelihood_empty(double alpha, double d, int K, int n_empty) {
     return n_empty ? (alpha + d * (K - n_empty)) / n_empty : 0.0;

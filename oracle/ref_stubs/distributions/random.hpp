@@ -7,14 +7,25 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 namespace distributions {
 typedef std::vector<float> VectorFloat;
+struct rng_t;
+inline std::vector<std::pair<uint64_t, const std::vector<double> *>> &seeded_scripts() {    // scripts for generators built from a seed
+    static std::vector<std::pair<uint64_t, const std::vector<double> *>> scripts;
+    return scripts;
+}
 struct rng_t {
+    typedef uint64_t result_type;
     const std::vector<double> *script;
     size_t pos;
     rng_t() : script(nullptr), pos(0) {}
-    explicit rng_t(uint64_t) : script(nullptr), pos(0) {}          // the per-feature generators of infer_assignments: unused by the stubs
+    // generators the reference builds itself: KindKernel's `rng_(seed)` finds the script the harness registered for
+    // that seed; the per-feature `rng_t(seed + f)` of infer_assignments find none and never draw
+    explicit rng_t(uint64_t seed) : script(nullptr), pos(0) {
+        for (const auto &s : seeded_scripts()) if (s.first == seed) script = s.second;
+    }
     explicit rng_t(const std::vector<double> &s) : script(&s), pos(0) {}
     uint64_t operator()() { return 0; }                            // `seed = rng()`: does not consume the script
     double next() {
@@ -35,4 +46,7 @@ inline size_t sample_from_likelihoods(rng_t &rng, const VectorFloat &likelihoods
     pick_log().push_back((uint32_t)(size - 1)); total_log().push_back(total_likelihood);
     return size - 1;
 }
+// names src/infer_grid.hpp and src/kind_kernel.hpp use; never reached by the harnesses (grids of size 0, no rows scored)
+inline int sample_int(rng_t &rng, int low, int high) { return low + (int)(rng.next() * (high - low + 1)); }
+inline size_t sample_from_scores_overwrite(rng_t &, VectorFloat &) { std::abort(); }
 }  // namespace distributions

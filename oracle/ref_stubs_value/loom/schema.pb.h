@@ -138,6 +138,20 @@ struct Row {
     ProductValue::Diff *mutable_diff() { return &diff_; }
     void Clear() { id_ = 0; diff_.Clear(); }
 };
+struct Config {                                     // Config.Kernels as src/kind_kernel.cc:40-43 reads it
+    struct Kernels {
+        struct Cat { uint32_t empty_group_count_ = 1; uint32_t empty_group_count() const { return empty_group_count_; } } cat_;
+        struct Kind {
+            uint32_t empty_kind_count_ = 32, iterations_ = 32;
+            bool score_parallel_ = false;
+            uint32_t empty_kind_count() const { return empty_kind_count_; }
+            uint32_t iterations() const { return iterations_; }
+            bool score_parallel() const { return score_parallel_; }
+        } kind_;
+        const Cat &cat() const { return cat_; }
+        const Kind &kind() const { return kind_; }
+    };
+};
 // only so that the Fields<> specialisations of src/protobuf.hpp parse
 struct FieldListStub {
     int bb() const { return 0; } int dd() const { return 0; } int dpd() const { return 0; }

@@ -162,3 +162,31 @@ def test_oracle_differ_reproduces_the_reference(oracle_abi, tmp_path):
 @pytest.mark.gpu
 def test_cuda_differ_reproduces_the_reference(cuda_abi, tmp_path):
     differ_matches_the_reference(cuda_abi, tmp_path)
+
+
+# ------------------------------------------------------------------------------------------ KindKernel bookkeeping
+def test_kind_kernel_bookkeeping_reproduces_the_reference(oracle_abi):
+    """src/kind_kernel.cc + src/kind_proposer.cc compiled unmodified (a KindKernel constructed over a CrossCat, try_run()
+    on supplied score matrices, destroyed: tests/golden/reference_kind_kernel.json) against the oracle's
+    init_featureless_kinds / kind_run on the same scores and uniforms: after EVERY step the feature -> kind map and the
+    number of kinds must be the reference's -- which features moved, which kinds died, how swap-removal renumbered the
+    survivors (src/kind_kernel.cc:196-206), where the fresh ephemeral kinds went.  19 try_run calls over 5 cases with
+    births and deaths in most of them.  (The product's lb_kind_run / lb_init_featureless_kinds are tied to the oracle's
+    by the -m gpu kind tests.)"""
+    import kind_pin_util
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_kind_kernel.json")))
+    runs = births = deaths = 0
+    for case in fixture["cases"]:
+        states = kind_pin_util.life_cycle(oracle_abi, case, lambda r, n_kinds: case["scores"][r])
+        assert len(states) == len(case["steps"])
+        for (step, f2k, n_kinds), want in zip(states, case["steps"]):
+            assert step == want["step"]
+            assert n_kinds == want["n_kinds"], (case["seed"], step)
+            assert f2k == want["f2k"], (case["seed"], step)
+            # the reference's own view of the same state: every kind's feature count
+            assert np.bincount(f2k, minlength=n_kinds).tolist() == want["n_features"]
+            if step == "try_run":
+                runs += 1
+                births += want["birth_count"]
+                deaths += want["death_count"]
+    assert runs >= 19 and births >= 30 and deaths >= 30
