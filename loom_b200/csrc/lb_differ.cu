@@ -7,10 +7,13 @@
 //                 the interesting columns are exactly the ones where nearly every row holds the same value
 //   compress_rows _abs_to_rel (src/differ.cc:248-298): thread per row walks the columns (adjacent threads
 //                 read adjacent rows of a column: coalesced), counts its pos / neg entries, an exclusive
-//                 scan turns counts into CSR offsets, a second walk writes the entries
+//                 scan turns counts into CSR offsets, a second walk (a warp per 32 rows, cells transposed through
+//                 shared memory so that a row's entries are stored by consecutive lanes) writes the entries
 // Both are HBM streams over the block: 1 B (BB, DD) or 4 B (DPD, GP) per cell + 1 mask bit; reals are
 // only read by compress_rows.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
@@ -110,6 +113,84 @@ __global__ void k_differ_rows(const FeatDev *feats, int F, RowsDev rows, const u
             }
         }
         if (!FILL) { pos_ptr[r + 1] = np; neg_ptr[r + 1] = nn; }
+    }
+}
+
+// The second walk with coalesced stores.  k_differ_rows<true> keeps a thread per row, so the 32 rows of a warp write 32
+// different places of the CSR arrays 4 bytes at a time: sectors leave the L2 half-filled and come back to be completed
+// (ncu, 10^6 rows x 100 columns: 576 MB read and 770 MB written for 322 MB of output; profiles/r2_differ_dram.md).
+// Here a warp takes 32 consecutive rows and 32 columns at a time: the cells are loaded with lane = row (coalesced along
+// the feature-major block, as before), transposed through shared memory, and emitted row by row with lane = column -- a
+// ballot and a popcount place every entry, so a row's entries are stored by consecutive lanes at consecutive addresses.
+// Entry order inside a row is ascending column, as _abs_to_rel_type produces it (src/differ.cc:248-298).
+#define DF_WARPS 4
+__global__ void __launch_bounds__(32 * DF_WARPS)
+k_differ_fill(const FeatDev *feats, int F, RowsDev rows, const uint8_t *tare_obs, const uint32_t *tare_val,
+              const unsigned long long *pos_ptr, const unsigned long long *neg_ptr, uint32_t *pos_feature,
+              uint32_t *pos_value, uint32_t *neg_feature) {
+    __shared__ uint32_t s_val[DF_WARPS][32][33];    // [column of the chunk][row of the tile], padded: both walks conflict-free
+    __shared__ uint32_t s_obs[DF_WARPS][32];        // per column: bit i = row i of the tile observes it
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t n_tiles = (rows.R + 31) >> 5;
+    for (uint64_t tile = (uint64_t)blockIdx.x * DF_WARPS + warp; tile < n_tiles; tile += (uint64_t)gridDim.x * DF_WARPS) {
+        const uint64_t r0 = tile << 5, r = r0 + lane;
+        const int n_rows = (int)min((uint64_t)32, rows.R - r0);
+        const uint32_t live = n_rows == 32 ? FULL : ((1u << n_rows) - 1u);
+        unsigned long long np = lane < n_rows ? pos_ptr[r] : 0ull, nn = lane < n_rows ? neg_ptr[r] : 0ull;   // lane = row
+        for (int f0 = 0; f0 < F; f0 += 32) {
+            const int nf = min(32, F - f0);
+            for (int j0 = 0; j0 < nf; j0 += 8) {                             // lane = row; 8 columns' loads in flight at once
+                uint32_t word[8], v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)                                  // the tile's rows are one mask word per column
+                    word[u] = j0 + u < nf ? rows.mask[(uint64_t)(f0 + j0 + u) * rows.W + tile] & live : 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = 0u;
+                    if ((word[u] >> lane) & 1u) {
+                        const FeatDev &ft = feats[f0 + j0 + u];
+                        v[u] = ft.is_wide ? rows.wide[(uint64_t)ft.col * rows.R + r] : (uint32_t)rows.cat8[(uint64_t)ft.col * rows.R + r];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (j0 + u < nf) {
+                        s_val[warp][j0 + u][lane] = v[u];
+                        if (lane == 0) s_obs[warp][j0 + u] = word[u];
+                    }
+            }
+            __syncwarp();
+            const int f = f0 + lane;                                         // lane = column
+            const bool have = lane < nf;
+            const bool t_obs = have && tare_obs[f];
+            const uint32_t t_val = have ? tare_val[f] : 0u;
+            const uint32_t obs_word = have ? s_obs[warp][lane] : 0u;
+            const uint32_t below = (1u << lane) - 1u;
+            for (int i = 0; i < n_rows; ++i) {
+                const bool obs = (obs_word >> i) & 1u;
+                const uint32_t v = s_val[warp][lane][i];
+                bool to_pos, to_neg;
+                if (t_obs) {
+                    const bool differs = obs && v != t_val;
+                    to_pos = differs;
+                    to_neg = !obs || differs;
+                } else {
+                    to_pos = obs;                                            // obs is false for lanes past the last column
+                    to_neg = false;
+                }
+                const uint32_t mp = __ballot_sync(FULL, to_pos), mn = __ballot_sync(FULL, to_neg);
+                const unsigned long long bp = __shfl_sync(FULL, np, i), bn = __shfl_sync(FULL, nn, i);
+                if (to_pos) {
+                    const unsigned long long at = bp + (unsigned long long)__popc(mp & below);
+                    pos_feature[at] = (uint32_t)f;
+                    pos_value[at] = v;
+                }
+                if (to_neg) neg_feature[bn + (unsigned long long)__popc(mn & below)] = (uint32_t)f;
+                if (lane == i) { np += (unsigned long long)__popc(mp); nn += (unsigned long long)__popc(mn); }
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -271,8 +352,16 @@ extern "C" int lb_differ_compress_rows(lb_handle h, const uint8_t *tare_observed
         s->cap_neg = total[1];
     }
     if (R) {
-        k_differ_rows<true><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
-                                                        s->d_pos_feature, s->d_pos_value, s->d_neg_feature);
+        static const bool thread_per_row = getenv("LB_DIFFER_FILL") && !strcmp(getenv("LB_DIFFER_FILL"), "rows");   // A/B switch
+        if (thread_per_row) {
+            k_differ_rows<true><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
+                                                            s->d_pos_feature, s->d_pos_value, s->d_neg_feature);
+        } else {
+            const uint64_t tiles = (R + 31) / 32;
+            const int fill_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((tiles + DF_WARPS - 1) / DF_WARPS, (uint64_t)e->n_sm * 16));
+            k_differ_fill<<<fill_grid, 32 * DF_WARPS, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
+                                                                     s->d_pos_feature, s->d_pos_value, s->d_neg_feature);
+        }
         LB_CUDA(cudaGetLastError());
         e->launches[LB_L_TOTAL] += 4; e->launches[LB_L_MISC] += 4;
         LB_CUDA(cudaStreamSynchronize(e->stream));
