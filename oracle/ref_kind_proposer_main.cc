@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE.  Drives the REFERENCE'S OWN KindProposer::infer_assignments (src/kind_proposer.cc, compiled
-// unmodified from /root/reference by `make -C oracle ref`; oracle/ref_stubs/ stands in for its collaborators and for
-// the un-vendored distributions library) on a score matrix, a feature -> kind assignment and a list of uniforms read
+// unmodified from /root/reference by `make -C oracle ref`, with the reference's own kind_proposer.hpp; oracle/ref_stubs_kind/
+// stands in for CrossCat and the mixtures, oracle/ref_stubs_value/ and oracle/ref_stubs/ for protoc's classes and the
+// un-vendored distributions library) on a score matrix, a feature -> kind assignment and a list of uniforms read
 // from stdin, and prints every draw of the block Pitman-Yor sampler and the final assignment as one JSON line.
 // tests/golden/make_reference_kind_proposer.py turns that into the committed fixture the oracle's sampler
 // (oracle_structure.c: oracle_block_py) must reproduce draw for draw.
@@ -15,7 +16,8 @@ int main() {
     if (std::scanf("%lf %lf %d %d %d", &alpha, &d, &F, &K, &iterations) != 5) return 2;
     std::vector<uint32_t> assign(F);
     for (auto &a : assign) if (std::scanf("%u", &a) != 1) return 2;
-    std::vector<std::vector<float>> by_kind(K, std::vector<float>(F));
+    std::vector<std::vector<float>> &by_kind = loom::score_script().by_label;     // kind k's tables carry label k
+    by_kind.assign(K, std::vector<float>(F));
     for (int f = 0; f < F; ++f)
         for (int k = 0; k < K; ++k) if (std::scanf("%f", &by_kind[k][f]) != 1) return 2;
     if (std::scanf("%d", &n) != 1) return 2;
@@ -25,10 +27,10 @@ int main() {
     loom::CrossCat cross_cat;
     cross_cat.topology.alpha = (float)alpha;
     cross_cat.topology.d = (float)d;
-    cross_cat.kinds.resize(K);
+    for (int k = 0; k < K; ++k) cross_cat.kinds.packed_add();
     loom::KindProposer proposer;
     proposer.kinds.resize(K);
-    for (int k = 0; k < K; ++k) proposer.kinds[k].mixture.scores = &by_kind[k];
+    for (int k = 0; k < K; ++k) proposer.kinds[k].mixture.label = k;             // proposer kind k shadows kind k
     loom::rng_t rng(uniforms);
     proposer.infer_assignments(cross_cat, assign, (size_t)iterations, false, rng);
 

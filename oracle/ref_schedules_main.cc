@@ -1,5 +1,7 @@
 // TEST INFRASTRUCTURE.  Drives the REFERENCE'S OWN schedule classes (compiled from /root/reference/src/schedules.hpp
-// where it lies; oracle/ref_stubs/ stands in for the four headers it includes) through the loop of
+// where it lies, with the reference's own common.hpp / protobuf.hpp / timer.hpp / assignments.hpp behind it;
+// oracle/ref_stubs_value/ and oracle/ref_stubs/ stand in for protoc's generated classes, libprotobuf's streams and the
+// un-vendored distributions headers) through the loop of
 // Loom::infer_kind_structure_sequential (src/loom.cc:217-262) and prints, per configuration, every ADD / REMOVE decision
 // and every batch boundary.  tests/golden/make_reference_schedules.py turns the output into the committed fixture
 // tests/golden/reference_schedules.json that the schedule driver of the product (loom_b200/infer.py, loom.hpp) is

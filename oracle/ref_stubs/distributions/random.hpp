@@ -4,6 +4,7 @@
 // with the oracle's (which consumes the same uniforms from its Philox stream).  sample_from_likelihoods restates the
 // library's published inverse-CDF walk (random.hpp: t = total * unif01; subtract until negative; last index otherwise).
 #pragma once
+#include <cmath>      // the library's headers bring <cmath> in; src/schedules.hpp relies on it
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>

@@ -138,7 +138,16 @@ struct Row {
     ProductValue::Diff *mutable_diff() { return &diff_; }
     void Clear() { id_ = 0; diff_.Clear(); }
 };
-struct Config {                                     // Config.Kernels as src/kind_kernel.cc:40-43 reads it
+struct Config {                                     // Config.Schedule as src/schedules.hpp reads it, Config.Kernels as src/kind_kernel.cc:40-43 does
+    struct Schedule {
+        double extra_passes_ = 0, small_data_size_ = 0, big_data_size_ = 0, checkpoint_period_sec_ = 1e9;
+        uint32_t max_reject_iters_ = 0;
+        double extra_passes() const { return extra_passes_; }
+        double small_data_size() const { return small_data_size_; }
+        double big_data_size() const { return big_data_size_; }
+        uint32_t max_reject_iters() const { return max_reject_iters_; }
+        double checkpoint_period_sec() const { return checkpoint_period_sec_; }
+    };
     struct Kernels {
         struct Cat { uint32_t empty_group_count_ = 1; uint32_t empty_group_count() const { return empty_group_count_; } } cat_;
         struct Kind {
@@ -150,6 +159,19 @@ struct Config {                                     // Config.Kernels as src/kin
         } kind_;
         const Cat &cat() const { return cat_; }
         const Kind &kind() const { return kind_; }
+    };
+};
+struct Checkpoint {                                 // Checkpoint.Schedule: what the schedules load and dump
+    struct Schedule {
+        double annealing_state_ = 0;
+        uint64_t row_count_ = 0;
+        uint32_t reject_iters_ = 0;
+        double annealing_state() const { return annealing_state_; }
+        void set_annealing_state(double x) { annealing_state_ = x; }
+        uint64_t row_count() const { return row_count_; }
+        void set_row_count(uint64_t x) { row_count_ = x; }
+        uint32_t reject_iters() const { return reject_iters_; }
+        void set_reject_iters(uint32_t x) { reject_iters_ = x; }
     };
 };
 // only so that the Fields<> specialisations of src/protobuf.hpp parse
