@@ -5,7 +5,7 @@
 // Loom::infer_kind_structure_sequential (src/loom.cc:217-262) and prints, per configuration, every ADD / REMOVE decision
 // and every batch boundary.  tests/golden/make_reference_schedules.py turns the output into the committed fixture
 // tests/golden/reference_schedules.json that the schedule driver of the product (loom_b200/infer.py, loom.hpp) is
-// checked against -- the one piece of the path whose reference implementation can run in this container.
+// checked against.
 //   usage: ref_schedules EXTRA_PASSES SMALL BIG ROWS [MAX_ACTIONS]
 #include <cstdio>
 #include <cstdlib>

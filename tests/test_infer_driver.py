@@ -153,8 +153,7 @@ def test_infer_multi_pass_on_the_gpu(cuda_abi):
 
 
 def test_schedules_reproduce_the_reference_binary():
-    """The ONE piece of the path whose reference implementation runs in the build container: src/schedules.hpp, compiled
-    in place (oracle/Makefile `ref`) and driven through loom.cc's loop; its ADD / REMOVE decisions and batch boundaries
+    """src/schedules.hpp, compiled in place in the build container (oracle/Makefile `ref`) and driven through loom.cc's loop; its ADD / REMOVE decisions and batch boundaries
     are the committed fixture (tests/golden/make_reference_schedules.py).  The product's schedule driver must make
     exactly the same decisions: this pins WHEN every kernel fires against the reference itself."""
     import json
