@@ -116,6 +116,56 @@ __global__ void k_differ_rows(const FeatDev *feats, int F, RowsDev rows, const u
     }
 }
 
+// The first walk (counts only), eight columns at a time: the thread-per-row walk above issues one mask word and one
+// cell per column behind a branch, so a warp has one load in flight; here the eight mask words are requested together,
+// then the eight cells (predicated, no branch between them), then the entries are counted.  Same predicate as
+// k_differ_rows / k_differ_fill, so the offsets the scan makes of these counts are the ones the fill pass consumes.
+#define DC_U 8
+__global__ void __launch_bounds__(128)
+k_differ_count(const FeatDev *feats, int F, RowsDev rows, const uint8_t *tare_obs, const uint32_t *tare_val,
+               unsigned long long *pos_ptr, unsigned long long *neg_ptr) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows.R; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t np = 0, nn = 0;
+        const uint64_t word_at = r >> 5;
+        const uint32_t bit = (uint32_t)(r & 31);
+        for (int f0 = 0; f0 < F; f0 += DC_U) {
+            bool obs[DC_U];
+            uint32_t v[DC_U];
+#pragma unroll
+            for (int u = 0; u < DC_U; ++u)
+                obs[u] = f0 + u < F && ((rows.mask[(uint64_t)(f0 + u) * rows.W + word_at] >> bit) & 1u);
+            int col[DC_U];
+            bool is_wide[DC_U];
+#pragma unroll
+            for (int u = 0; u < DC_U; ++u) {                       // descriptors without a branch (cached, the same for every row)
+                const int f = min(f0 + u, F - 1);
+                col[u] = feats[f].col;
+                is_wide[u] = feats[f].is_wide != 0;
+            }
+#pragma unroll
+            for (int u = 0; u < DC_U; ++u) {                       // one predicated load each: all eight go out together
+                uint32_t w = 0u, b = 0u;
+                if (obs[u] && is_wide[u]) w = rows.wide[(uint64_t)col[u] * rows.R + r];
+                if (obs[u] && !is_wide[u]) b = rows.cat8[(uint64_t)col[u] * rows.R + r];
+                v[u] = w | b;
+            }
+#pragma unroll
+            for (int u = 0; u < DC_U; ++u) {
+                if (f0 + u >= F) break;
+                if (tare_obs[f0 + u]) {
+                    const bool differs = obs[u] && v[u] != tare_val[f0 + u];
+                    np += differs;
+                    nn += !obs[u] || differs;
+                } else {
+                    np += obs[u];
+                }
+            }
+        }
+        pos_ptr[r + 1] = np;
+        neg_ptr[r + 1] = nn;
+    }
+}
+
 // The second walk with coalesced stores.  k_differ_rows<true> keeps a thread per row, so the 32 rows of a warp write 32
 // different places of the CSR arrays 4 bytes at a time: sectors leave the L2 half-filled and come back to be completed
 // (ncu, 10^6 rows x 100 columns: 576 MB read and 770 MB written for 322 MB of output; profiles/r2_differ_dram.md).
@@ -146,12 +196,14 @@ k_differ_fill(const FeatDev *feats, int F, RowsDev rows, const uint8_t *tare_obs
                 for (int u = 0; u < 8; ++u)                                  // the tile's rows are one mask word per column
                     word[u] = j0 + u < nf ? rows.mask[(uint64_t)(f0 + j0 + u) * rows.W + tile] & live : 0u;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    v[u] = 0u;
-                    if ((word[u] >> lane) & 1u) {
-                        const FeatDev &ft = feats[f0 + j0 + u];
-                        v[u] = ft.is_wide ? rows.wide[(uint64_t)ft.col * rows.R + r] : (uint32_t)rows.cat8[(uint64_t)ft.col * rows.R + r];
-                    }
+                for (int u = 0; u < 8; ++u) {                                // descriptor without a branch, then one predicated load
+                    const int f = min(f0 + j0 + u, F - 1);
+                    const int col = feats[f].col;
+                    const bool is_wide = feats[f].is_wide != 0, on = (word[u] >> lane) & 1u;
+                    uint32_t w = 0u, b = 0u;
+                    if (on && is_wide) w = rows.wide[(uint64_t)col * rows.R + r];
+                    if (on && !is_wide) b = rows.cat8[(uint64_t)col * rows.R + r];
+                    v[u] = w | b;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -327,8 +379,12 @@ extern "C" int lb_differ_compress_rows(lb_handle h, const uint8_t *tare_observed
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((R + 127) / 128, (uint64_t)e->n_sm * 16));
     unsigned long long total[2] = {0, 0};
     if (R) {
-        k_differ_rows<false><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
-                                                         nullptr, nullptr, nullptr);
+        static const bool plain_count = getenv("LB_DIFFER_FILL") && !strcmp(getenv("LB_DIFFER_FILL"), "rows");   // A/B switch
+        if (plain_count)
+            k_differ_rows<false><<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr,
+                                                             nullptr, nullptr, nullptr);
+        else
+            k_differ_count<<<grid, 128, 0, e->stream>>>(e->d_feats, e->F, rows, d_obs, d_val, s->d_pos_ptr, s->d_neg_ptr);
         LB_CUDA(cudaGetLastError());
         LB_CUDA(cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, s->d_pos_ptr + 1, s->d_pos_ptr + 1, (int)R, e->stream));
         LB_CUDA(cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, s->d_neg_ptr + 1, s->d_neg_ptr + 1, (int)R, e->stream));
