@@ -8,10 +8,25 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
+#include <numeric>
 #include <utility>
 #include <vector>
 namespace distributions {
-typedef std::vector<float> VectorFloat;
+// distributions::Packed_ (vector.hpp of 2.0.28), restated from its published behaviour: a vector whose removal moves the
+// LAST element into the hole -- the renumbering KindKernel::remove_featureless_kind (src/kind_kernel.cc:196-206) and the
+// group bookkeeping of ProductMixture rely on.  VectorFloat is the library's Packed_<float> (aligned there).
+template <class Value> struct Packed_ : std::vector<Value> {
+    Packed_() {}
+    explicit Packed_(size_t size) : std::vector<Value>(size) {}
+    Packed_(size_t size, const Value &value) : std::vector<Value>(size, value) {}
+    Value &packed_add() { this->emplace_back(); return this->back(); }
+    Value &packed_add(const Value &value) { this->push_back(value); return this->back(); }
+    void packed_remove(size_t pos) {
+        if (pos + 1 != this->size()) (*this)[pos] = std::move(this->back());
+        this->pop_back();
+    }
+};
+typedef Packed_<float> VectorFloat;
 struct rng_t;
 inline std::vector<std::pair<uint64_t, const std::vector<double> *>> &seeded_scripts() {    // scripts for generators built from a seed
     static std::vector<std::pair<uint64_t, const std::vector<double> *>> scripts;

@@ -30,7 +30,8 @@ template <class count_t> struct Clustering {
     };
 };
 template <class Model, class count_t> struct MixtureDriver {};
-template <class Model> struct Protobuf { typedef int t; };
+struct ProtobufStub { struct Shared {}; struct Group {}; };
+template <class Model> struct Protobuf { typedef ProtobufStub t; };
 namespace protobuf { struct Clustering { struct PitmanYor {}; }; }
 }  // namespace distributions
 namespace protobuf { namespace distributions {} }

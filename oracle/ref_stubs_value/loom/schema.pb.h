@@ -174,14 +174,34 @@ struct Checkpoint {                                 // Checkpoint.Schedule: what
         void set_reject_iters(uint32_t x) { reject_iters_ = x; }
     };
 };
-// only so that the Fields<> specialisations of src/protobuf.hpp parse
-struct FieldListStub {
-    int bb() const { return 0; } int dd() const { return 0; } int dpd() const { return 0; }
-    int gp() const { return 0; } int nich() const { return 0; }
-    int *mutable_bb() { return nullptr; } int *mutable_dd() { return nullptr; } int *mutable_dpd() { return nullptr; }
-    int *mutable_gp() { return nullptr; } int *mutable_nich() { return nullptr; }
+// only so that the Fields<> specialisations of src/protobuf.hpp and the load / dump code of src/product_mixture.cc parse:
+// per-model-type lists of empty messages
+struct MessageStub {};
+struct MessageListStub {
+    int size() const { return 0; }
+    const MessageStub &Get(int) const { static MessageStub m; return m; }
+    MessageStub *Add() { static MessageStub m; return &m; }
 };
-struct ProductModel { struct Shared : FieldListStub {}; struct Group : FieldListStub {}; };
+struct FieldListStub {
+    MessageListStub list_;
+    const MessageListStub &bb() const { return list_; } const MessageListStub &dd() const { return list_; }
+    const MessageListStub &dpd() const { return list_; } const MessageListStub &gp() const { return list_; }
+    const MessageListStub &nich() const { return list_; }
+    MessageListStub *mutable_bb() { return &list_; } MessageListStub *mutable_dd() { return &list_; }
+    MessageListStub *mutable_dpd() { return &list_; } MessageListStub *mutable_gp() { return &list_; }
+    MessageListStub *mutable_nich() { return &list_; }
+};
+struct ProductModel {
+    struct Shared : FieldListStub {};
+    struct Group : FieldListStub {
+        uint64_t count_ = 0;
+        uint64_t count() const { return count_; }
+        void set_count(uint64_t x) { count_ = x; }
+        void Clear() { count_ = 0; }
+    };
+};
+typedef ProductModel::Shared ProductModel_Shared;      // protoc's flat names for the nested messages
+typedef ProductModel::Group ProductModel_Group;
 struct HyperPrior : FieldListStub {};
 inline std::ostream &operator<<(std::ostream &os, const ProductValue &v) { return os << v.ShortDebugString(); }
 }}  // namespace protobuf::loom
