@@ -9,8 +9,10 @@
  * exact libm.  It is pinned instead against scipy known-answer tests and loom's
  * own posterior-enumeration chi-square test (tests/test_oracle_*.py).
  * The pieces of the reference that DO compile here (Makefile target `ref`: the
- * schedules, kind_proposer.cc's block Pitman-Yor sampler, differ.cc +
- * product_value.cc) are pinned against the reference's own output:
+ * schedules, kind_proposer.cc's block Pitman-Yor sampler, kind_kernel.cc's
+ * bookkeeping, differ.cc + product_value.cc, and product_mixture.cc over
+ * stand-in mixtures whose arithmetic is this file's) are pinned against the
+ * reference's own output:
  * tests/golden/reference_*.json, tests/test_reference_pins.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /

@@ -190,3 +190,56 @@ def test_kind_kernel_bookkeeping_reproduces_the_reference(oracle_abi):
                 births += want["birth_count"]
                 deaths += want["death_count"]
     assert runs >= 19 and births >= 30 and deaths >= 30
+
+
+# ------------------------------------------------------------------------------------------ ProductMixture along a sweep
+def product_mixture_matches_the_reference(abi, tol=2e-5):
+    """src/product_mixture.cc compiled unmodified (tests/golden/reference_product_mixture.json: the score vector of
+    ProductMixture::score_value -- score_diff on rows the reference's own Differ compressed -- before every ADD of a
+    cat-kernel trajectory, then add_value / remove_value with the trajectory's packed groups) against the engine's own
+    sweep of the same table with the debug taps on.  The trajectory is the engine's (same seed => same picks as when the
+    fixture was made); what must agree at every one of the 830 ADDs is the reference's view of the state: how many
+    groups there are, which packed index each has after every birth and death, the clustering prior and the sum over
+    the observed features of every group.  Per-feature arithmetic on the reference side is the oracle's own (see
+    oracle/ref_stubs_mix), so the tolerance only covers the reference's float32 accumulation."""
+    import ctypes
+    import mixture_pin_util as U
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_product_mixture.json")))
+    lib = ctypes.CDLL(os.path.join(REPO, "oracle", "libloom_oracle.so"))
+    lib.lo_py_score_counts.restype = ctypes.c_double
+    lib.lo_py_score_counts.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int]
+    adds = 0
+    for case in fixture["cases"]:
+        model, table = U.build(case)
+        assert table == case["table"], case["name"]                     # the generator's table, rebuilt from the seed
+        for mine, theirs in zip(model.features, case["features"]):
+            assert mine == theirs, case["name"]
+        tare = None
+        if case["tare"]:
+            obs = np.array([v is not None for v in case["tare"]], np.uint8)
+            val = np.array([v or 0 for v in case["tare"]], np.uint32)
+            tare = (obs, val)
+        acts, picks, scores, score_data, counts = U.sweep(abi, case, model, table, tare)
+        assert picks.tolist() == case["picks"], case["name"]
+        assert len(scores) == len(case["adds"])
+        for i, (mine, ref) in enumerate(zip(scores, case["adds"])):
+            ref = np.asarray(ref, np.float64)
+            assert len(mine) == len(ref), (case["name"], i)              # the same number of groups, empties included
+            assert np.all(np.abs(mine - ref) <= tol * np.maximum(1.0, np.abs(ref))), (case["name"], i)
+            adds += 1
+        assert counts.tolist() == case["counts"], case["name"]           # packed order after the last action
+        # CrossCat::score_data = the topology's score of the feature counts + every kind's mixture.score_data
+        # (src/cross_cat.cc:238-250); the fixture holds the mixture's part
+        one_kind = np.array([model.n_features], np.uint32)
+        topology = lib.lo_py_score_counts(case["alpha"], case["d"], one_kind.ctypes.data, 1)
+        assert abs(score_data - (case["score_data"] + topology)) <= 2e-5 * abs(score_data), case["name"]
+    assert adds >= 800
+
+
+def test_oracle_sweep_agrees_with_the_reference_product_mixture(oracle_abi):
+    product_mixture_matches_the_reference(oracle_abi)
+
+
+@pytest.mark.gpu
+def test_cuda_sweep_agrees_with_the_reference_product_mixture(cuda_abi):
+    product_mixture_matches_the_reference(cuda_abi, tol=4e-5)      # float32 tables on the device (1e-5 against the oracle) + the reference's float32 sums
