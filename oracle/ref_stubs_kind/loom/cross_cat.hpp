@@ -81,11 +81,6 @@ template <bool cached> struct ProductMixture_ {
 typedef ProductMixture_<true> ProductMixture;
 typedef ProductMixture_<false> SmallProductMixture;
 
-struct HyperPriorStub {
-    struct Grid { size_t size() const { return 0; } int Get(size_t) const { return 0; } };
-    Grid clustering() const { return Grid(); }
-};
-
 struct CrossCat : noncopyable {
     struct Kind {
         ProductModel model;
@@ -100,7 +95,7 @@ struct CrossCat : noncopyable {
     struct SplitterStub {
         template <class D, class P> void split(const D &, P &) const {}
     } splitter;
-    HyperPriorStub hyper_prior;
+    protobuf::HyperPrior hyper_prior;                 // the stub's clustering grid is empty
     Clustering::Shared topology;
     distributions::Packed_<Kind> kinds;
     std::vector<uint32_t> featureid_to_kindid;

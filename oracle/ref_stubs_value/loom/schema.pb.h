@@ -176,23 +176,38 @@ struct Checkpoint {                                 // Checkpoint.Schedule: what
 };
 // only so that the Fields<> specialisations of src/protobuf.hpp and the load / dump code of src/product_mixture.cc parse:
 // per-model-type lists of empty messages
-struct MessageStub {};
+struct MessageListStub;
+struct MessageStub {
+    const MessageListStub &alphas() const;            // DirichletDiscrete.Shared.alphas: product_model.cc:60 reads its size
+};
 struct MessageListStub {
     int size() const { return 0; }
     const MessageStub &Get(int) const { static MessageStub m; return m; }
     MessageStub *Add() { static MessageStub m; return &m; }
+    const MessageStub *begin() const { return nullptr; }
+    const MessageStub *end() const { return nullptr; }
 };
+inline const MessageListStub &MessageStub::alphas() const { static MessageListStub l; return l; }
 struct FieldListStub {
     MessageListStub list_;
     const MessageListStub &bb() const { return list_; } const MessageListStub &dd() const { return list_; }
     const MessageListStub &dpd() const { return list_; } const MessageListStub &gp() const { return list_; }
     const MessageListStub &nich() const { return list_; }
+    const MessageStub &bb(int) const { return list_.Get(0); } const MessageStub &dd(int) const { return list_.Get(0); }
+    const MessageStub &dpd(int) const { return list_.Get(0); } const MessageStub &gp(int) const { return list_.Get(0); }
+    const MessageStub &nich(int) const { return list_.Get(0); }
+    int bb_size() const { return 0; } int dd_size() const { return 0; } int dpd_size() const { return 0; }
+    int gp_size() const { return 0; } int nich_size() const { return 0; }
     MessageListStub *mutable_bb() { return &list_; } MessageListStub *mutable_dd() { return &list_; }
     MessageListStub *mutable_dpd() { return &list_; } MessageListStub *mutable_gp() { return &list_; }
     MessageListStub *mutable_nich() { return &list_; }
 };
 struct ProductModel {
-    struct Shared : FieldListStub {};
+    struct Shared : FieldListStub {
+        MessageStub clustering_;
+        const MessageStub &clustering() const { return clustering_; }
+        MessageStub *mutable_clustering() { return &clustering_; }
+    };
     struct Group : FieldListStub {
         uint64_t count_ = 0;
         uint64_t count() const { return count_; }
@@ -202,6 +217,31 @@ struct ProductModel {
 };
 typedef ProductModel::Shared ProductModel_Shared;      // protoc's flat names for the nested messages
 typedef ProductModel::Group ProductModel_Group;
-struct HyperPrior : FieldListStub {};
+struct HyperPrior : FieldListStub {
+    MessageListStub clustering_;                       // an EMPTY clustering grid: new kinds copy kind 0's (kind_kernel.cc:167-171)
+    const MessageListStub &clustering() const { return clustering_; }
+    const MessageListStub &topology() const { return clustering_; }
+};
+struct CrossCat {                                      // what CrossCat::model_load / model_dump touch (never called by the harnesses)
+    struct Kind {
+        std::vector<uint32_t> featureids_;
+        ProductModel::Shared product_model_;
+        size_t featureids_size() const { return featureids_.size(); }
+        uint32_t featureids(int i) const { return featureids_[i]; }
+        void add_featureids(uint32_t f) { featureids_.push_back(f); }
+        const ProductModel::Shared &product_model() const { return product_model_; }
+        ProductModel::Shared *mutable_product_model() { return &product_model_; }
+    };
+    std::vector<Kind> kinds_;
+    MessageStub topology_;
+    HyperPrior hyper_prior_;
+    size_t kinds_size() const { return kinds_.size(); }
+    const Kind &kinds(int i) const { return kinds_[i]; }
+    Kind *add_kinds() { kinds_.emplace_back(); return &kinds_.back(); }
+    const MessageStub &topology() const { return topology_; }
+    MessageStub *mutable_topology() { return &topology_; }
+    const HyperPrior &hyper_prior() const { return hyper_prior_; }
+    HyperPrior *mutable_hyper_prior() { return &hyper_prior_; }
+};
 inline std::ostream &operator<<(std::ostream &os, const ProductValue &v) { return os << v.ShortDebugString(); }
 }}  // namespace protobuf::loom
