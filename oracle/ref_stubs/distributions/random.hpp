@@ -64,5 +64,30 @@ inline size_t sample_from_likelihoods(rng_t &rng, const VectorFloat &likelihoods
 }
 // names src/infer_grid.hpp and src/kind_kernel.hpp use; never reached by the harnesses (grids of size 0, no rows scored)
 inline int sample_int(rng_t &rng, int low, int high) { return low + (int)(rng.next() * (high - low + 1)); }
-inline size_t sample_from_scores_overwrite(rng_t &, VectorFloat &) { std::abort(); }
+// sample_from_scores_overwrite: the cat kernel's draw.  The harness SCRIPTS it -- the next entry of pick_script() is the
+// group to take (the oracle's own pick for that row and kind) -- and keeps the score vector it was called with
+inline std::vector<uint32_t> &pick_script() { static std::vector<uint32_t> s; return s; }
+inline size_t &pick_script_pos() { static size_t p = 0; return p; }
+inline std::vector<std::vector<float>> &scores_log() { static std::vector<std::vector<float>> l; return l; }
+inline size_t sample_from_scores_overwrite(rng_t &, VectorFloat &scores) {
+    if (pick_script_pos() >= pick_script().size()) std::abort();
+    scores_log().emplace_back(scores.begin(), scores.end());
+    const size_t pick = pick_script()[pick_script_pos()++];
+    if (pick >= scores.size()) std::abort();
+    return pick;
+}
+// PitmanYor::sample_assignments: the prior partition of a fresh ephemeral kind, scripted the same way (one vector per
+// kind, in creation order); without a script every row alternates between two groups
+inline std::vector<std::vector<int>> &seating_script() { static std::vector<std::vector<int>> s; return s; }
+inline size_t &seating_script_pos() { static size_t p = 0; return p; }
+inline std::vector<int> scripted_seating(size_t size) {
+    if (seating_script_pos() < seating_script().size()) {
+        std::vector<int> a = seating_script()[seating_script_pos()++];
+        if (a.size() != size) std::abort();
+        return a;
+    }
+    std::vector<int> a(size);
+    for (size_t i = 0; i < size; ++i) a[i] = (int)(i & 1);
+    return a;
+}
 }  // namespace distributions

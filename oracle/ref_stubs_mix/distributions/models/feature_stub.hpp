@@ -120,11 +120,7 @@ template <class count_t> struct Clustering {
             std::vector<uint32_t> c(counts.begin(), counts.end());
             return (float)lo_py_score_counts(alpha, d, c.data(), (int)c.size());
         }
-        std::vector<int> sample_assignments(size_t size, rng_t &) const {
-            std::vector<int> assignments(size);
-            for (size_t i = 0; i < size; ++i) assignments[i] = (int)(i & 1);
-            return assignments;
-        }
+        std::vector<int> sample_assignments(size_t size, rng_t &) const { return scripted_seating(size); }
         struct Mixture {
             std::vector<int> counts_;
             std::vector<int> &counts() { return counts_; }

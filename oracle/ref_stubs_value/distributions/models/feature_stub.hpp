@@ -22,11 +22,7 @@ template <class count_t> struct Clustering {
         float score_counts(const std::vector<int> &) const { return 0.f; }
         // the prior partition of an ephemeral kind: not what this program pins (the oracle seats with its own Philox
         // stream); two groups, so that the group bookkeeping around it has something to count
-        std::vector<int> sample_assignments(size_t size, rng_t &) const {
-            std::vector<int> assignments(size);
-            for (size_t i = 0; i < size; ++i) assignments[i] = (int)(i & 1);
-            return assignments;
-        }
+        std::vector<int> sample_assignments(size_t size, rng_t &) const { return scripted_seating(size); }
     };
 };
 template <class Model, class count_t> struct MixtureDriver {};

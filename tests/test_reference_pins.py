@@ -243,3 +243,26 @@ def test_oracle_sweep_agrees_with_the_reference_product_mixture(oracle_abi):
 @pytest.mark.gpu
 def test_cuda_sweep_agrees_with_the_reference_product_mixture(cuda_abi):
     product_mixture_matches_the_reference(cuda_abi, tol=4e-5)      # float32 tables on the device (1e-5 against the oracle) + the reference's float32 sums
+
+
+# ------------------------------------------------------------------------------------------ a whole kind-structure pass
+def test_oracle_kind_structure_pass_reproduces_the_reference(oracle_abi):
+    """The reference's own CrossCat + KindKernel + KindProposer + ProductModel + ProductMixture + ValueSplitter +
+    Assignments, compiled unmodified and run through a kind-structure pass (tests/golden/reference_kind_structure.json:
+    KindKernel::add_row / remove_row for every action, try_run() per round, the kernel destroyed at the end; random
+    decisions scripted from this oracle's run), against the oracle's init_featureless_kinds / cat_sweep /
+    kind_proposer_score / kind_run on the same tables.  Must agree: the score vector of every one of the 1 670 draws
+    over all kinds (ephemeral ones included), L[f][k] of every round -- the proposer's statistics are the FULL row added
+    to every kind's group (a9) and every (feature, kind) pair is scored from them (a10) --, the feature -> kind map the
+    block sampler and move_features leave (a11, a12), and at the end every surviving kind's counts and sufficient
+    statistics (integers bit for bit: moved features carry the proposer's statistics, src/product_mixture.cc:886-915)
+    and CrossCat::score_data (a14)."""
+    import structure_pin_util as U
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_kind_structure.json")))
+    vectors = rounds = 0
+    for case in fixture["cases"]:
+        model, table = U.build(case)
+        mine = U.run(oracle_abi, case, model, table)
+        vectors += U.compare(case, model, mine, case["reference"])
+        rounds += case["n_rounds"]
+    assert vectors >= 1600 and rounds >= 7
