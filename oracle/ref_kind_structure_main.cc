@@ -35,12 +35,10 @@ static bool read_row(const std::vector<int> &types, loom::ProductValue &value) {
 }
 
 template <class S> static void read_spec(S &shared, int type, int dim, const float *hp, int aux_n) {
-    shared.spec.type = type;
-    shared.spec.dim = dim;
-    std::memcpy(shared.spec.hp, hp, sizeof shared.spec.hp);
-    shared.spec.aux_off = 0;
-    shared.aux.resize(aux_n);
-    for (auto &a : shared.aux) if (std::scanf("%f", &a) != 1) std::abort();
+    (void)type;
+    std::vector<float> aux(aux_n);
+    for (auto &a : aux) if (std::scanf("%f", &a) != 1) std::abort();
+    shared.load(dim, hp, aux);
 }
 
 struct print_stats_fun {                      // every feature of a kind: its groups' statistics in packed order
@@ -103,8 +101,7 @@ int main() {
         loom::CrossCat::Kind &kind = cross_cat.kinds[kind_of[f]];
         const Spec &s = specs[f];
         kind.featureids.insert(f);
-#define LB_PUT(container) do { auto &shared = kind.model.features.container.insert(f); shared.spec.type = s.type; shared.spec.dim = s.dim; \
-                               std::memcpy(shared.spec.hp, s.hp, sizeof s.hp); shared.spec.aux_off = 0; shared.aux = s.aux; } while (0)
+#define LB_PUT(container) kind.model.features.container.insert(f).load(s.dim, s.hp, s.aux)
         switch (s.type) {
             case LB_BB: LB_PUT(bb); break;
             case LB_DD: if (s.dim <= 16) LB_PUT(dd16); else LB_PUT(dd256); break;

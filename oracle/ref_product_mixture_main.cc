@@ -33,12 +33,10 @@ static bool read_value_row(const std::vector<int> &types, loom::ProductValue &va
 }
 
 template <class S> static void read_spec(S &shared, int type, int dim, const float *hp, int aux_n) {
-    shared.spec.type = type;
-    shared.spec.dim = dim;
-    std::memcpy(shared.spec.hp, hp, sizeof shared.spec.hp);
-    shared.spec.aux_off = 0;
-    shared.aux.resize(aux_n);
-    for (auto &a : shared.aux) if (std::scanf("%f", &a) != 1) std::abort();
+    (void)type;
+    std::vector<float> aux(aux_n);
+    for (auto &a : aux) if (std::scanf("%f", &a) != 1) std::abort();
+    shared.load(dim, hp, aux);
 }
 
 int main() {

@@ -35,33 +35,82 @@ inline uint32_t raw_cell(bool v) { return v ? 1u : 0u; }
 inline uint32_t raw_cell(uint32_t v) { return v; }
 inline uint32_t raw_cell(float v) { uint32_t r; std::memcpy(&r, &v, 4); return r; }
 
-// Shared / Group / Mixture of one feature model; TYPE is the engine's LB_* code, V the library's Value type
-template <class V, int TYPE> struct FeatureStub {
+// The hyperparameters of one feature, with the member names the library's Shared structs have (src/hyper_prior.hpp
+// writes `shared.alpha = ...`), and their image as the oracle's lb_feature_spec + aux array
+struct SharedBase {
+    int dim = 0;
+    void add_value(...) {}                             // DPD dictionaries are complete at ingest
+    void remove_value(...) {}
+    void realize(rng_t &) {}
+    template <class M> void protobuf_load(const M &) {}
+    template <class M> void protobuf_dump(M &) const {}
+};
+struct BBShared : SharedBase {
+    float alpha = 1, beta = 1;
+    void load(int, const float *hp, const std::vector<float> &) { alpha = hp[0]; beta = hp[1]; }
+    lb_feature_spec spec() const { lb_feature_spec s = {LB_BB, 0, {alpha, beta, 0, 0}, 0}; return s; }
+    const float *aux() const { return nullptr; }
+    int int_rows() const { return 2; }
+    int flt_rows() const { return 0; }
+};
+struct DDShared : SharedBase {
+    std::vector<float> alphas;
+    void load(int d, const float *, const std::vector<float> &a) { dim = d; alphas = a; }
+    lb_feature_spec spec() const { lb_feature_spec s = {LB_DD, dim, {0, 0, 0, 0}, 0}; return s; }
+    const float *aux() const { return alphas.data(); }
+    int int_rows() const { return dim + 1; }
+    int flt_rows() const { return 0; }
+};
+struct DPDShared : SharedBase {
+    float gamma = 1, alpha = 1, beta0 = 1;
+    struct Betas {                                     // the library's sparse map value -> beta; dense here (value = index)
+        std::vector<float> v;
+        float &get(uint32_t value) { return v[value]; }
+        float get(uint32_t value) const { return v[value]; }
+        size_t size() const { return v.size(); }
+    } betas;
+    void load(int d, const float *hp, const std::vector<float> &a) { dim = d; gamma = hp[0]; alpha = hp[1]; beta0 = hp[2]; betas.v = a; }
+    lb_feature_spec spec() const { lb_feature_spec s = {LB_DPD, dim, {gamma, alpha, beta0, 0}, 0}; return s; }
+    const float *aux() const { return betas.v.data(); }
+    int int_rows() const { return dim + 1; }
+    int flt_rows() const { return 0; }
+};
+struct GPShared : SharedBase {
+    float alpha = 1, inv_beta = 1;
+    void load(int, const float *hp, const std::vector<float> &) { alpha = hp[0]; inv_beta = hp[1]; }
+    lb_feature_spec spec() const { lb_feature_spec s = {LB_GP, 0, {alpha, inv_beta, 0, 0}, 0}; return s; }
+    const float *aux() const { return nullptr; }
+    int int_rows() const { return 2; }
+    int flt_rows() const { return 1; }
+};
+struct NICHShared : SharedBase {
+    float mu = 0, kappa = 1, sigmasq = 1, nu = 1;
+    void load(int, const float *hp, const std::vector<float> &) { mu = hp[0]; kappa = hp[1]; sigmasq = hp[2]; nu = hp[3]; }
+    lb_feature_spec spec() const { lb_feature_spec s = {LB_NICH, 0, {mu, kappa, sigmasq, nu}, 0}; return s; }
+    const float *aux() const { return nullptr; }
+    int int_rows() const { return 1; }
+    int flt_rows() const { return 2; }
+};
+
+// Shared / Group / Mixture of one feature model; V is the library's Value type, S one of the structs above
+template <class V, class S> struct FeatureStub {
     typedef V Value;
-    struct Shared {
-        lb_feature_spec spec;
-        std::vector<float> aux;                       // DD alphas / DPD betas
-        Shared() { std::memset(&spec, 0, sizeof spec); spec.type = TYPE; }
-        int int_rows() const { return TYPE == LB_BB ? 2 : TYPE == LB_DD || TYPE == LB_DPD ? spec.dim + 1 : TYPE == LB_GP ? 2 : 1; }
-        int flt_rows() const { return TYPE == LB_GP ? 1 : TYPE == LB_NICH ? 2 : 0; }
-        void add_value(const Value &, rng_t &) {}      // DPD dictionaries are complete at ingest
-        void remove_value(const Value &, rng_t &) {}
-        void realize(rng_t &) {}
-        template <class M> void protobuf_load(const M &) {}
-        template <class M> void protobuf_dump(M &) const {}
-    };
+    typedef S Shared;
     struct Group {
         std::vector<uint32_t> ints;
         std::vector<double> flts;
+        std::unordered_map<uint32_t, uint32_t> counts;   // named by the DPD branch of src/hyper_kernel.cc (never run here)
         void init(const Shared &s, rng_t &) { ints.assign(s.int_rows(), 0u); flts.assign(s.flt_rows() + 1, 0.0); }
-        void add_value(const Shared &s, const Value &v, rng_t &) { om_add_value(&s.spec, ints.data(), flts.data(), 1, raw_cell(v), +1); }
+        void add_value(const Shared &s, const Value &v, rng_t &) { const lb_feature_spec sp = s.spec(); om_add_value(&sp, ints.data(), flts.data(), 1, raw_cell(v), +1); }
         void add_repeated_value(const Shared &s, const Value &v, int count, rng_t &rng) { for (int i = 0; i < count; ++i) add_value(s, v, rng); }
-        void remove_value(const Shared &s, const Value &v, rng_t &) { om_add_value(&s.spec, ints.data(), flts.data(), 1, raw_cell(v), -1); }
+        void remove_value(const Shared &s, const Value &v, rng_t &) { const lb_feature_spec sp = s.spec(); om_add_value(&sp, ints.data(), flts.data(), 1, raw_cell(v), -1); }
         float score_value(const Shared &s, const Value &v, rng_t &) const {
-            return (float)om_score_value(&s.spec, s.aux.data() - s.spec.aux_off, ints.data(), flts.data(), 1, raw_cell(v));
+            const lb_feature_spec sp = s.spec();
+            return (float)om_score_value(&sp, s.aux(), ints.data(), flts.data(), 1, raw_cell(v));
         }
         float score_data(const Shared &s, rng_t &) const {
-            return (float)om_score_data(&s.spec, s.aux.data() - s.spec.aux_off, ints.data(), flts.data(), 1);
+            const lb_feature_spec sp = s.spec();
+            return (float)om_score_data(&sp, s.aux(), ints.data(), flts.data(), 1);
         }
         Value sample_value(const Shared &, rng_t &) const { return Value(); }
         void validate(const Shared &) const {}
@@ -72,6 +121,7 @@ template <class V, int TYPE> struct FeatureStub {
     // distributions' Mixture: the groups of one feature, in PACKED order; removal moves the last group into the hole
     // (Packed_::packed_remove), the cached form only adds score tables that do not change the results
     struct Mixture {
+        typedef S Shared;
         std::vector<Group> groups_;
         std::vector<Group> &groups() { return groups_; }
         const std::vector<Group> &groups() const { return groups_; }
@@ -94,16 +144,23 @@ template <class V, int TYPE> struct FeatureStub {
             for (const auto &g : groups_) score += g.score_data(s, rng);
             return score;
         }
+        // the hyper kernel's grid step (src/infer_grid.hpp:83): the data score of all groups under every hypothesis
+        void score_data_grid(const std::vector<Shared> &shareds, VectorFloat &scores, rng_t &rng) const {
+            for (size_t i = 0; i < shareds.size(); ++i) scores[i] = score_data(shareds[i], rng);
+        }
         void validate(const Shared &) const {}
     };
     typedef Mixture FastMixture;
     typedef Mixture SmallMixture;
+    typedef FeatureStub Model;
+    static uint32_t OTHER() { return 0xFFFFFFFFu; }
+    static float MIN_BETA() { return 1e-6f; }
 };
-struct BetaBernoulli : FeatureStub<bool, LB_BB> {};
-template <int max_dim> struct DirichletDiscrete : FeatureStub<uint32_t, LB_DD> {};
-struct DirichletProcessDiscrete : FeatureStub<uint32_t, LB_DPD> {};
-struct GammaPoisson : FeatureStub<uint32_t, LB_GP> {};
-struct NormalInverseChiSq : FeatureStub<float, LB_NICH> {};
+struct BetaBernoulli : FeatureStub<bool, BBShared> {};
+template <int max_dim> struct DirichletDiscrete : FeatureStub<uint32_t, DDShared> {};
+struct DirichletProcessDiscrete : FeatureStub<uint32_t, DPDShared> {};
+struct GammaPoisson : FeatureStub<uint32_t, GPShared> {};
+struct NormalInverseChiSq : FeatureStub<float, NICHShared> {};
 
 // distributions::Clustering<int>::PitmanYor and its mixture, restated from the library's published behaviour
 // (clustering.hpp of 2.0.28; the formulas are SURVEY.md 8c's): counts in packed order with exactly the empty groups the
@@ -114,7 +171,9 @@ template <class count_t> struct Clustering {
     struct PitmanYor {
         float alpha, d;
         PitmanYor() : alpha(1.f), d(0.f) {}
-        template <class Message> void protobuf_load(const Message &) {}
+        template <class Message> void protobuf_load(const Message &m) { load_point(m, 0); }       // a hyper-prior grid point carries (alpha, d)
+        template <class Message> auto load_point(const Message &m, int) -> decltype(m.alpha(), void()) { alpha = m.alpha(); d = m.d(); }
+        template <class Message> void load_point(const Message &, long) {}
         template <class Message> void protobuf_dump(Message &) const {}
         float score_counts(const std::vector<int> &counts) const {
             std::vector<uint32_t> c(counts.begin(), counts.end());
@@ -197,6 +256,13 @@ struct MixtureIdTracker {
     uint32_t global_to_packed(size_t global) const { return global_to_packed_.at((uint32_t)global); }
 };
 
+// names the DPD branch of src/hyper_kernel.cc uses (Stirling row, safe Dirichlet draw, fast_log / fast_lgamma): the
+// harnesses hold no DPD column when they run the hyper kernel (the oracle's DPD sampler is a documented statistical
+// equivalent, not a restatement), so these only have to exist
+inline void get_log_stirling1_row(size_t, VectorFloat &) { std::abort(); }
+inline void sample_dirichlet_safe(rng_t &, size_t, const float *, float *, float) { std::abort(); }
+inline float fast_log(float x) { return std::log(x); }
+inline float fast_lgamma(float x) { return std::lgamma(x); }
 inline void vector_zero(size_t size, float *x) { for (size_t i = 0; i < size; ++i) x[i] = 0.f; }
 inline void vector_negate(size_t size, float *x) { for (size_t i = 0; i < size; ++i) x[i] = -x[i]; }
 inline void vector_add(size_t size, float *x, const float *y) { for (size_t i = 0; i < size; ++i) x[i] += y[i]; }
