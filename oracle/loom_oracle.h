@@ -10,8 +10,10 @@
  * own posterior-enumeration chi-square test (tests/test_oracle_*.py).
  * The pieces of the reference that DO compile here (Makefile target `ref`: the
  * schedules, kind_proposer.cc's block Pitman-Yor sampler, kind_kernel.cc's
- * bookkeeping, differ.cc + product_value.cc, and product_mixture.cc over
- * stand-in mixtures whose arithmetic is this file's) are pinned against the
+ * bookkeeping, differ.cc + product_value.cc, and -- over stand-in mixtures
+ * whose per-feature arithmetic is this library's -- product_mixture.cc, a whole
+ * kind-structure pass of cross_cat.cc + kind_kernel.cc, hyper_kernel.cc) are
+ * pinned against the
  * reference's own output:
  * tests/golden/reference_*.json, tests/test_reference_pins.py.
  *

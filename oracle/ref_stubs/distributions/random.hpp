@@ -69,9 +69,20 @@ inline int sample_int(rng_t &rng, int low, int high) { return low + (int)(rng.ne
 inline std::vector<uint32_t> &pick_script() { static std::vector<uint32_t> s; return s; }
 inline size_t &pick_script_pos() { static size_t p = 0; return p; }
 inline std::vector<std::vector<float>> &scores_log() { static std::vector<std::vector<float>> l; return l; }
-inline size_t sample_from_scores_overwrite(rng_t &, VectorFloat &scores) {
-    if (pick_script_pos() >= pick_script().size()) std::abort();
+inline bool &draw_from_uniforms() { static bool b = false; return b; }
+inline size_t sample_from_scores_overwrite(rng_t &rng, VectorFloat &scores) {
     scores_log().emplace_back(scores.begin(), scores.end());
+    if (draw_from_uniforms()) {
+        // the library's published algorithm (random.hpp / special.hpp of 2.0.28): subtract the maximum, exponentiate in
+        // place, walk the inverse CDF with one uniform -- here the generator's next scripted uniform
+        float max_score = scores[0], total = 0;
+        for (float s : scores) if (s > max_score) max_score = s;
+        for (float &s : scores) total += s = std::exp(s - max_score);
+        float t = total * (float)rng.next();
+        for (size_t i = 0; i < scores.size(); ++i) { t -= scores[i]; if (t < 0) return i; }
+        return scores.size() - 1;
+    }
+    if (pick_script_pos() >= pick_script().size()) std::abort();
     const size_t pick = pick_script()[pick_script_pos()++];
     if (pick >= scores.size()) std::abort();
     return pick;

@@ -15,7 +15,8 @@ struct Logger {
             void set_sample_time(uint64_t) {}
             void set_total_time(uint64_t) {}
         } kind_;
-        struct KernelStatus { Kind *kind; Kind *mutable_kind() { return kind; } } status_{&kind_};
+        struct Hyper { void set_total_time(uint64_t) {} } hyper_;
+        struct KernelStatus { Kind *kind; Hyper *hyper; Kind *mutable_kind() { return kind; } Hyper *mutable_hyper() { return hyper; } } status_{&kind_, &hyper_};
         KernelStatus *mutable_kernel_status() { return &status_; }
     };
 };

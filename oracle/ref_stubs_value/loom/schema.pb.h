@@ -149,6 +149,8 @@ struct Config {                                     // Config.Schedule as src/sc
         double checkpoint_period_sec() const { return checkpoint_period_sec_; }
     };
     struct Kernels {
+        struct Hyper { bool run_ = true, parallel_ = false; bool run() const { return run_; } bool parallel() const { return parallel_; } } hyper_;
+        const Hyper &hyper() const { return hyper_; }
         struct Cat { uint32_t empty_group_count_ = 1; uint32_t empty_group_count() const { return empty_group_count_; } } cat_;
         struct Kind {
             uint32_t empty_kind_count_ = 32, iterations_ = 32;
@@ -217,10 +219,31 @@ struct ProductModel {
 };
 typedef ProductModel::Shared ProductModel_Shared;      // protoc's flat names for the nested messages
 typedef ProductModel::Group ProductModel_Group;
-struct HyperPrior : FieldListStub {
-    MessageListStub clustering_;                       // an EMPTY clustering grid: new kinds copy kind 0's (kind_kernel.cc:167-171)
-    const MessageListStub &clustering() const { return clustering_; }
-    const MessageListStub &topology() const { return clustering_; }
+struct HyperPrior {                                   // src/schema.proto:34-71: one grid per hyperparameter
+    typedef google::protobuf::RepeatedField<float> Grid;
+    struct PitmanYorPoint { float alpha_ = 0, d_ = 0; float alpha() const { return alpha_; } float d() const { return d_; } };
+    struct PitmanYorGrid {
+        std::vector<PitmanYorPoint> points;
+        size_t size() const { return points.size(); }
+        const PitmanYorPoint &Get(int i) const { return points[i]; }
+    };
+#define LB_STUB_GRID(name) Grid name##_; const Grid &name() const { return name##_; } int name##_size() const { return name##_.size(); } float name(int i) const { return name##_.Get(i); }
+    struct BetaBernoulli { LB_STUB_GRID(alpha) LB_STUB_GRID(beta) };
+    struct DirichletDiscrete { LB_STUB_GRID(alpha) };
+    struct DirichletProcessDiscrete { LB_STUB_GRID(gamma) LB_STUB_GRID(alpha) };
+    struct GammaPoisson { LB_STUB_GRID(alpha) LB_STUB_GRID(inv_beta) };
+    struct BetaNegativeBinomial { LB_STUB_GRID(alpha) LB_STUB_GRID(beta) LB_STUB_GRID(r) };
+    struct NormalInverseChiSq { LB_STUB_GRID(mu) LB_STUB_GRID(kappa) LB_STUB_GRID(sigmasq) LB_STUB_GRID(nu) };
+#undef LB_STUB_GRID
+    PitmanYorGrid topology_, clustering_;             // EMPTY grids: the kernel keeps the hypers (new kinds copy kind 0's, kind_kernel.cc:167-171)
+    BetaBernoulli bb_; DirichletDiscrete dd_; DirichletProcessDiscrete dpd_; GammaPoisson gp_; NormalInverseChiSq nich_;
+    const PitmanYorGrid &topology() const { return topology_; }
+    const PitmanYorGrid &clustering() const { return clustering_; }
+    const BetaBernoulli &bb() const { return bb_; }
+    const DirichletDiscrete &dd() const { return dd_; }
+    const DirichletProcessDiscrete &dpd() const { return dpd_; }
+    const GammaPoisson &gp() const { return gp_; }
+    const NormalInverseChiSq &nich() const { return nich_; }
 };
 struct CrossCat {                                      // what CrossCat::model_load / model_dump touch (never called by the harnesses)
     struct Kind {

@@ -266,3 +266,25 @@ def test_oracle_kind_structure_pass_reproduces_the_reference(oracle_abi):
         vectors += U.compare(case, model, mine, case["reference"])
         rounds += case["n_rounds"]
     assert vectors >= 1600 and rounds >= 7
+
+
+# ------------------------------------------------------------------------------------------ HyperKernel::run
+def hyper_run_matches_the_reference(abi):
+    """src/hyper_kernel.cc compiled unmodified (HyperKernel::run over infer_grid.hpp / hyper_prior.hpp and the real
+    CrossCat: tests/golden/reference_hyper.json) against hyper_run on the same tables, groups, grids and uniforms: the
+    grid point chosen for the topology, for every kind's clustering and for every coordinate of every feature (88 draws
+    over 3 cases; single-point grids set without a draw) must be the reference's, which requires the same hypotheses
+    scored in the same order from the same statistics with the same task -> random stream numbering
+    (src/hyper_kernel.cc:195-235).  No DPD column."""
+    import hyper_pin_util as U
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_hyper.json")))
+    draws = 0
+    for case in fixture["cases"]:
+        model, table = U.build(case)
+        U.compare(case, U.run(abi, case, model, table), case["reference"])
+        draws += case["reference"]["draws"]
+    assert draws >= 80
+
+
+def test_oracle_hyper_run_reproduces_the_reference(oracle_abi):
+    hyper_run_matches_the_reference(oracle_abi)
