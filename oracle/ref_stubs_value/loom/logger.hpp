@@ -16,7 +16,12 @@ struct Logger {
             void set_total_time(uint64_t) {}
         } kind_;
         struct Hyper { void set_total_time(uint64_t) {} } hyper_;
-        struct KernelStatus { Kind *kind; Hyper *hyper; Kind *mutable_kind() { return kind; } Hyper *mutable_hyper() { return hyper; } } status_{&kind_, &hyper_};
+        struct KernelStatus {
+            Kind *kind; Hyper *hyper;
+            Kind *mutable_kind() { return kind; }
+            Hyper *mutable_hyper() { return hyper; }
+            Hyper *mutable_cat() { return hyper; }      // Cat status: total_time only, like Hyper
+        } status_{&kind_, &hyper_};
         KernelStatus *mutable_kernel_status() { return &status_; }
     };
 };

@@ -138,6 +138,16 @@ struct Row {
     ProductValue::Diff *mutable_diff() { return &diff_; }
     void Clear() { id_ = 0; diff_.Clear(); }
 };
+struct Assignment {                                   // src/schema.proto:160-163
+    uint64_t rowid_ = 0;
+    std::vector<uint32_t> groupids_;
+    uint64_t rowid() const { return rowid_; }
+    void set_rowid(uint64_t x) { rowid_ = x; }
+    int groupids_size() const { return (int)groupids_.size(); }
+    uint32_t groupids(int i) const { return groupids_[i]; }
+    void add_groupids(uint32_t g) { groupids_.push_back(g); }
+    void clear_groupids() { groupids_.clear(); }
+};
 struct Config {                                     // Config.Schedule as src/schedules.hpp reads it, Config.Kernels as src/kind_kernel.cc:40-43 does
     struct Schedule {
         double extra_passes_ = 0, small_data_size_ = 0, big_data_size_ = 0, checkpoint_period_sec_ = 1e9;

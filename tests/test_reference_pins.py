@@ -288,3 +288,24 @@ def hyper_run_matches_the_reference(abi):
 
 def test_oracle_hyper_run_reproduces_the_reference(oracle_abi):
     hyper_run_matches_the_reference(oracle_abi)
+
+
+# ------------------------------------------------------------------------------------------ CatKernel over several kinds
+def test_oracle_multi_kind_sweep_reproduces_the_reference_cat_kernel(oracle_abi):
+    """src/cat_kernel.hpp compiled unmodified over the reference's own CrossCat, ValueSplitter, Assignments, ProductModel
+    and ProductMixture -- and its own Differ and CrossCat::update_tares for the tared case
+    (tests/golden/reference_cat_kernel.json: every action through CatKernel::add_row / remove_row(rng, row,
+    assignments), draws scripted from this oracle's sweep) against the oracle's cat_sweep over the same multi-kind
+    tables: the score vector of each of the 1 300 (row, kind) draws (which cells of a row reach which kind: a7), the
+    final clustering counts of every kind, which rows are still assigned and the PACKED group of each -- the reference
+    keeps global ids in FIFO queues and maps them through the id tracker (a8) --, and CrossCat::score_data (a14)."""
+    import cat_pin_util as U
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_cat_kernel.json")))
+    vectors = 0
+    for case in fixture["cases"]:
+        model, table = U.build(case)
+        tare = None
+        if case["tare_row"]:
+            tare = (np.array([v is not None for v in case["tare_row"]], np.uint8), np.array([v or 0 for v in case["tare_row"]], np.uint32))
+        vectors += U.compare(case, U.run(oracle_abi, case, model, table, tare), case["reference"])
+    assert vectors >= 1300
