@@ -157,6 +157,13 @@ int lbio_rows_read_open(const char *path, lbio_model *m, uint64_t seed, int32_t 
 int lbio_model_adopt_dictionaries(lbio_model *dst, const lbio_model *src, uint64_t seed);
 /* InFile::stream_stats (src/protobuf_stream.hpp:156-184) */
 int lbio_stream_stats(const char *path, uint64_t *message_count, uint32_t *max_message_size);
+/* CrossCat::get_sorted_groupids for one kind (src/cross_cat.cc:212-236): the packed ids of the non-empty groups, largest
+ * first -- the order groups are dumped in (ProductMixture::dump) and assignments renumbered to (Assignments::dump).  The
+ * reference sorts with std::sort and a `counts[x] > counts[y]` comparator, which leaves the order of EQUAL counts to the
+ * library's introsort; this entry point runs the same call on the same initial sequence (ascending packed id), so a
+ * build against the same libstdc++ orders tied groups identically (pinned by tests/golden/reference_sorted_groupids.json).
+ * order_out has room for n_groups entries; *n_out = number of non-empty groups. */
+int lbio_sorted_groupids(const uint32_t *counts, int32_t n_groups, uint32_t *order_out, int32_t *n_out);
 /* shuffle_stream (src/shuffle.hpp:38-86): a seeded permutation of the messages of a stream file, produced in chunks
  * of at most target_mem_bytes (the result does not depend on the chunk size).  What `loom_shuffle` runs. */
 int lbio_shuffle_stream(const char *messages_in, const char *shuffled_out, uint64_t seed, double target_mem_bytes);

@@ -106,10 +106,10 @@ public:
                 std::vector<double> flts((size_t)std::max(info.n_flt_rows, 1) * G);
                 LOOM_B200_CHECK(LB_NAME(get_groups)(h(), k, counts.data(), ints.data(), flts.data()));
                 // CrossCat::get_sorted_groupids (src/cross_cat.cc:212-236): non-empty groups, largest first
-                std::vector<uint32_t> order;
-                for (uint32_t g = 0; g < G; ++g)
-                    if (counts[g]) order.push_back(g);
-                std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return counts[x] > counts[y]; });
+                std::vector<uint32_t> order(G);
+                int32_t n_live = 0;
+                LOOM_B200_IO(lbio_sorted_groupids(counts.data(), (int32_t)G, order.data(), &n_live));
+                order.resize((size_t)n_live);
                 packed_to_sorted[k].assign(G, LB_UNASSIGNED);
                 for (size_t s = 0; s < order.size(); ++s) packed_to_sorted[k][order[s]] = (uint32_t)s;
                 if (groups_out) {

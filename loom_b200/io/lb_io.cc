@@ -1073,6 +1073,17 @@ extern "C" int lbio_stream_stats(const char *path, uint64_t *message_count, uint
 // seeded permutation; the output is produced in chunks of at most target_mem_bytes, one pass over the input each,
 // so the result does not depend on the chunk size.  (The permutation comes from SplitMix64 + Fisher-Yates, not from
 // the reference's std::shuffle(rng_t): same law, different draws.)
+extern "C" int lbio_sorted_groupids(const uint32_t *counts, int32_t n_groups, uint32_t *order_out, int32_t *n_out) {
+    std::vector<uint32_t> order;
+    for (int32_t g = 0; g < n_groups; ++g)
+        if (counts[g]) order.push_back((uint32_t)g);
+    // std::sort, not stable_sort: the reference's own call (src/cross_cat.cc:228-231), so that tied groups land where its do
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return counts[x] > counts[y]; });
+    std::copy(order.begin(), order.end(), order_out);
+    *n_out = (int32_t)order.size();
+    return 0;
+}
+
 extern "C" int lbio_shuffle_stream(const char *messages_in, const char *shuffled_out, uint64_t seed, double target_mem_bytes) {
     if (std::string(messages_in) == std::string(shuffled_out)) return fail("cannot shuffle file in-place: %s", messages_in);
     if (std::string(messages_in) == "-" || std::string(messages_in) == "-.gz") return fail("shuffle input is not a file: %s", messages_in);

@@ -157,6 +157,7 @@ SIGNATURES = {   # must list every function of include/loom_b200_io.h
     "log_close": (None, [C.c_void_p]),
     "tares_read_open": (C.c_int, [_cs, _model, C.c_uint64, _u8p, _u32p, _i32p, _i32p]),
     "shuffle_stream": (C.c_int, [_cs, _cs, C.c_uint64, C.c_double]),
+    "sorted_groupids": (C.c_int, [_u32p, C.c_int32, _u32p, _i32p]),
     "rows_writer_open": (C.c_int, [_cs, _P(C.c_void_p)]),
     "rows_writer_write": (C.c_int, [C.c_void_p, _model, C.c_void_p, _u32p]),
     "rows_writer_close": (C.c_int, [C.c_void_p]),
@@ -534,6 +535,16 @@ def groups_write(path, model_file, featureids, counts, ints, flts, order=None):
 def mixture_path(groups_dir, kindid):
     """store::get_mixture_path (src/store.hpp:59-66)"""
     return os.path.join(groups_dir, "mixture.%d.pbs.gz" % kindid)
+
+
+def sorted_groupids(counts):
+    """CrossCat::get_sorted_groupids for one kind (src/cross_cat.cc:212-236): packed ids of the non-empty groups, largest
+    first, tied groups in the order the reference's own std::sort call leaves them"""
+    counts = np.ascontiguousarray(counts, np.uint32)
+    order = np.zeros(max(len(counts), 1), np.uint32)
+    n = C.c_int32()
+    _check(lib().lbio_sorted_groupids(_abi.ptr(counts, _u32p), len(counts), _abi.ptr(order, _u32p), C.byref(n)))
+    return order[:n.value].copy()
 
 
 def shuffle_stream(messages_in, shuffled_out, seed=0, target_mem_bytes=4e9):

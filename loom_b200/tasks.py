@@ -80,8 +80,7 @@ def _dump_sample(engine, model_file, rowids, window, out, hyper_prior, dpd_value
         os.makedirs(out["groups"], exist_ok=True)
     for k in range(n_kinds):
         counts, ints, flts = engine.get_groups(k)
-        live = np.flatnonzero(counts)
-        sorted_ids = live[np.argsort(-counts[live].astype(np.int64), kind="stable")]   # cross_cat.cc:212-236
+        sorted_ids = pbio.sorted_groupids(counts)                                      # cross_cat.cc:212-236
         if out.get("groups"):
             pbio.groups_write(pbio.mixture_path(out["groups"], k), out_file, model.kind_features(k), counts, ints,
                               flts, sorted_ids)

@@ -309,3 +309,19 @@ def test_oracle_multi_kind_sweep_reproduces_the_reference_cat_kernel(oracle_abi)
             tare = (np.array([v is not None for v in case["tare_row"]], np.uint8), np.array([v or 0 for v in case["tare_row"]], np.uint32))
         vectors += U.compare(case, U.run(oracle_abi, case, model, table, tare), case["reference"])
     assert vectors >= 1300
+
+
+# ------------------------------------------------------------------------------------------ the dump order of groups
+def test_dump_order_of_groups_is_the_reference_s():
+    """CrossCat::get_sorted_groupids compiled unmodified (tests/golden/reference_sorted_groupids.json) against
+    lbio_sorted_groupids, the one implementation both hosts dump with (loom.hpp, loom_b200/tasks.py): non-empty groups,
+    largest first, and groups of EQUAL count exactly where the reference's std::sort leaves them -- several of the
+    fixture's kinds differ from what a stable sort would give."""
+    from loom_b200 import pbio
+    fixture = json.load(open(os.path.join(HERE, "golden", "reference_sorted_groupids.json")))
+    unstable = 0
+    for kind in fixture["kinds"]:
+        counts = kind["counts"]
+        assert pbio.sorted_groupids(counts).tolist() == kind["order"], len(counts)
+        unstable += kind["order"] != sorted([g for g in range(len(counts)) if counts[g]], key=lambda g: -counts[g])
+    assert len(fixture["kinds"]) >= 20 and unstable >= 5
