@@ -1,0 +1,84 @@
+"""Fuzz the reference pins: random cases through the generators of tests/golden/make_reference_{cat_kernel,
+kind_structure,hyper,product_mixture}.py -- i.e. the REFERENCE'S OWN code compiled under oracle/_ref against the oracle on
+tables, kind structures, hypers and schedules nobody chose by hand -- without writing fixtures.  Runs only where
+/root/reference exists (the build container).  usage: fuzz_reference_pins.py N [first_seed]   -> one line per failure"""
+import importlib.util
+import os
+import sys
+import traceback
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+
+def load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REPO, "tests", "golden", "make_reference_%s.py" % name))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+gens = {n: load(n) for n in ("cat_kernel", "kind_structure", "hyper", "product_mixture")}
+TYPES = ["bb", "dd4", "dd16", "dd256", "dpd5", "gp", "nich"]
+
+
+def random_types(rng, allow_dpd=True, max_each=3):
+    names = [t for t in TYPES if allow_dpd or not t.startswith("dpd")]
+    picked = rng.choice(len(names), size=rng.randint(1, 5), replace=False)
+    return [(names[i], int(rng.randint(1, max_each + 1))) for i in sorted(picked)]
+
+
+def n_features(types):
+    return sum(n for _, n in types)
+
+
+def random_case(kind, seed):
+    rng = np.random.RandomState(seed)
+    types = random_types(rng, allow_dpd=kind != "hyper")
+    F = n_features(types)
+    K = int(rng.randint(1, min(F, 4) + 1))
+    f2k = rng.randint(0, K, F)
+    f2k[:K] = np.arange(K)                                  # every kind has a feature
+    rng.shuffle(f2k)
+    base = dict(name="%s_%d" % (kind, seed), types=types, n_rows=int(rng.randint(2, 45)), density=float(rng.choice([0.3, 0.7, 1.0])),
+                seed=int(seed), passes=int(rng.randint(0, 3)))
+    py = [float(np.float32(rng.choice([0.3, 1.0, 4.0]))), float(np.float32(rng.choice([0.0, 0.2, 0.6])))]
+    if kind == "product_mixture":
+        return dict(base, alpha=py[0], d=py[1], tare=bool(rng.randint(0, 2)) and any(t == "bb" for t, _ in types))
+    case = dict(base, f2k=f2k.tolist(), kind_py=py, topology=[float(np.float32(rng.choice([0.5, 2.0]))), float(np.float32(rng.choice([0.0, 0.3])))])
+    if kind == "cat_kernel":
+        return dict(case, tare=bool(rng.randint(0, 2)) and any(t == "bb" for t, _ in types))
+    if kind == "kind_structure":
+        return dict(case, E=int(rng.randint(1, 4)), iterations=int(rng.choice([1, 4, 16])), n_rounds=int(rng.randint(1, 4)))
+    return dict(case, grids=gens["hyper"].GRIDS if rng.randint(0, 3) else gens["hyper"].ONE)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    devnull = open(os.devnull, "w")
+    failures = 0
+    for kind, gen in gens.items():
+        ok = 0
+        for seed in range(first, first + n):
+            case = random_case(kind, seed)
+            stdout, sys.stdout = sys.stdout, devnull
+            try:
+                gen.run_case(case)
+                ok += 1
+            except Exception:                              # noqa: BLE001 -- report and go on: the point is to find them all
+                sys.stdout = stdout
+                failures += 1
+                print("FAIL", kind, seed, {k: v for k, v in case.items() if k != "grids"})
+                traceback.print_exc(limit=3)
+            finally:
+                sys.stdout = stdout
+        print(kind, "%d / %d cases agree" % (ok, n))
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()

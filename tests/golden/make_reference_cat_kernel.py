@@ -38,8 +38,7 @@ def token(v):
     return "-" if v is None else repr(v)
 
 
-out = []
-for case in cases:
+def run_case(case):
     model, table = U.build(case)
     tare = tare_row = None
     if case.get("tare"):
@@ -72,8 +71,12 @@ for case in cases:
     n = U.compare(case, mine, ref)
     print(case["name"], "score vectors", n, "rows left", len(ref["rowids"]), "counts", [k["counts"] for k in ref["kinds"]], "score_data",
           ref["score_data"])
-    out.append(dict(case, tare_row=tare_row, reference=ref))
-json.dump({"source": "/root/reference/src/cat_kernel.hpp over {cross_cat,product_model,product_mixture,product_value,differ}.cc compiled by "
-                     "oracle/Makefile `ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* "
-                     "per-feature functions, driven by oracle/ref_cat_kernel_main.cc", "cases": out},
-          open(os.path.join(REPO, "tests", "golden", "reference_cat_kernel.json"), "w"), separators=(",", ":"))
+    return dict(case, tare_row=tare_row, reference=ref)
+
+
+if __name__ == "__main__":
+    out = [run_case(case) for case in cases]
+    json.dump({"source": "/root/reference/src/cat_kernel.hpp over {cross_cat,product_model,product_mixture,product_value,differ}.cc compiled by "
+                         "oracle/Makefile `ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* "
+                         "per-feature functions, driven by oracle/ref_cat_kernel_main.cc", "cases": out},
+              open(os.path.join(REPO, "tests", "golden", "reference_cat_kernel.json"), "w"), separators=(",", ":"))

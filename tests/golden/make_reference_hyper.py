@@ -56,8 +56,7 @@ def grid_text(values):
     return "%d %s\n" % (len(values), " ".join("%.9g" % v for v in values))
 
 
-out = []
-for case in cases:
+def run_case(case):
     model, table = U.build(case)
     mine = U.run(abi, case, model, table)
     picks = mine[0]
@@ -80,14 +79,18 @@ for case in cases:
         for p in params:
             text += grid_text(g[t][p])
     for task in range(1 + K + F):
-        text += "40 " + " ".join("%.17g" % abi.lib.lo_uniform(case["seed"] + 7, 2, task, j) for j in range(40)) + "\n"
+        text += "300 " + " ".join("%.17g" % abi.lib.lo_uniform(case["seed"] + 7, 2, task, j) for j in range(300)) + "\n"
     proc = subprocess.run([exe], input=text.encode(), stdout=subprocess.PIPE)
     assert proc.returncode == 0, (case["name"], proc.returncode)
     ref = json.loads(proc.stdout)
     U.compare(case, mine, ref)
     print(case["name"], "draws", ref["draws"], "topology", ref["topology"], "kinds", ref["kinds"], "first features", ref["features"][:2])
-    out.append(dict(case, reference=ref))
-json.dump({"source": "/root/reference/src/{hyper_kernel,cross_cat,product_model,product_mixture,product_value}.cc compiled by oracle/Makefile "
-                     "`ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* per-feature "
-                     "functions, driven by oracle/ref_hyper_main.cc; uniforms of task t = lo_uniform(seed + 7, 2, t, draw)", "cases": out},
-          open(os.path.join(REPO, "tests", "golden", "reference_hyper.json"), "w"), separators=(",", ":"))
+    return dict(case, reference=ref)
+
+
+if __name__ == "__main__":
+    out = [run_case(case) for case in cases]
+    json.dump({"source": "/root/reference/src/{hyper_kernel,cross_cat,product_model,product_mixture,product_value}.cc compiled by oracle/Makefile "
+                         "`ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* per-feature "
+                         "functions, driven by oracle/ref_hyper_main.cc; uniforms of task t = lo_uniform(seed + 7, 2, t, draw)", "cases": out},
+              open(os.path.join(REPO, "tests", "golden", "reference_hyper.json"), "w"), separators=(",", ":"))

@@ -43,8 +43,7 @@ def token(v):
     return "-" if v is None else repr(v)
 
 
-out = []
-for case in cases:
+def run_case(case):
     model, table = U.build(case)
     mine = U.run(abi, case, model, table)
     F = model.n_features
@@ -73,8 +72,12 @@ for case in cases:
     n = U.compare(case, model, mine, ref)
     print(case["name"], "score vectors", n, "kinds per round", [rd["kinds_scored"] for rd in ref["rounds"]],
           "maps", [rd["f2k"] for rd in ref["rounds"]], "final kinds", ref["final"]["n_kinds"], "score_data", ref["final"]["score_data"])
-    out.append(dict(case, reference=ref))
-json.dump({"source": "/root/reference/src/{cross_cat,kind_kernel,kind_proposer,product_model,product_mixture,product_value}.cc compiled by "
-                     "oracle/Makefile `ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* "
-                     "per-feature functions, driven by oracle/ref_kind_structure_main.cc", "cases": out},
-          open(os.path.join(REPO, "tests", "golden", "reference_kind_structure.json"), "w"), separators=(",", ":"))
+    return dict(case, reference=ref)
+
+
+if __name__ == "__main__":
+    out = [run_case(case) for case in cases]
+    json.dump({"source": "/root/reference/src/{cross_cat,kind_kernel,kind_proposer,product_model,product_mixture,product_value}.cc compiled by "
+                         "oracle/Makefile `ref` (g++ -O2) against oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* "
+                         "per-feature functions, driven by oracle/ref_kind_structure_main.cc", "cases": out},
+              open(os.path.join(REPO, "tests", "golden", "reference_kind_structure.json"), "w"), separators=(",", ":"))

@@ -41,8 +41,7 @@ def token(v):
     return "-" if v is None else repr(v)
 
 
-out = []
-for case in cases:
+def run_case(case):
     model, table = U.build(case)
     tare = tare_row = None
     if case.get("tare"):
@@ -73,9 +72,13 @@ for case in cases:
         worst = max(worst, float(np.max(np.abs(mine - ref) / np.maximum(1.0, np.abs(ref)))))
     print(case["name"], "adds", len(scores), "max groups", max(len(s) for s in scores), "worst rel diff %.2e" % worst,
           "score_data", score_data, got["score_data"], "counts", list(counts), got["counts"])
-    out.append(dict(case, features=model.features, table=table, tare=tare_row, picks=[int(p) for p in picks],
-                    adds=got["adds"], score_data=got["score_data"], counts=got["counts"], packed_to_global=got["packed_to_global"]))
-json.dump({"source": "/root/reference/src/product_mixture.cc + product_value.cc + differ.cc compiled by oracle/Makefile `ref` (g++ -O2) against "
-                     "oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* per-feature functions, driven by "
-                     "oracle/ref_product_mixture_main.cc", "cases": out},
-          open(os.path.join(REPO, "tests", "golden", "reference_product_mixture.json"), "w"), separators=(",", ":"))
+    return dict(case, features=model.features, table=table, tare=tare_row, picks=[int(p) for p in picks],
+                    adds=got["adds"], score_data=got["score_data"], counts=got["counts"], packed_to_global=got["packed_to_global"])
+
+
+if __name__ == "__main__":
+    out = [run_case(case) for case in cases]
+    json.dump({"source": "/root/reference/src/product_mixture.cc + product_value.cc + differ.cc compiled by oracle/Makefile `ref` (g++ -O2) against "
+                         "oracle/ref_stubs_mix + ref_stubs_value + ref_stubs, linked to liboracle's om_* per-feature functions, driven by "
+                         "oracle/ref_product_mixture_main.cc", "cases": out},
+              open(os.path.join(REPO, "tests", "golden", "reference_product_mixture.json"), "w"), separators=(",", ":"))
