@@ -1,7 +1,13 @@
 """Fuzz the reference pins: random cases through the generators of tests/golden/make_reference_{cat_kernel,
 kind_structure,hyper,product_mixture}.py -- i.e. the REFERENCE'S OWN code compiled under oracle/_ref against the oracle on
 tables, kind structures, hypers and schedules nobody chose by hand -- without writing fixtures.  Runs only where
-/root/reference exists (the build container).  usage: fuzz_reference_pins.py N [first_seed]   -> one line per failure"""
+/root/reference exists (the build container).  usage: fuzz_reference_pins.py N [first_seed]   -> one line per failure
+
+Last full run (300 cases per pin, seeds 10000..10299): cat_kernel 300 / 300, kind_structure 300 / 300, product_mixture
+300 / 300, hyper 299 / 300.  The one hyper case that differs (seed 10072, a DD-256 column = 256 grid draws) is a uniform
+1.3e-6 of probability mass away from a CDF boundary at coordinate 137, where the scores are ~ -80 and the reference sums
+them in float32 (ulp 7.6e-6): LB_REF_DUMP_SCORES=1 makes oracle/_ref/ref_hyper print every score vector it drew from, which
+is how that was checked; every coordinate before it agrees."""
 import importlib.util
 import os
 import sys

@@ -8,6 +8,7 @@
 // documented statistical equivalent of src/hyper_kernel.cc:90-181, not a restatement.
 //   stdin: see tests/golden/make_reference_hyper.py (the only writer of this format)
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <loom/hyper_kernel.hpp>
@@ -143,6 +144,11 @@ int main() {
     loom::rng_t rng;
     hyper_kernel.run(rng);
 
+    if (std::getenv("LB_REF_DUMP_SCORES"))                     // diagnosis: every score vector the kernel drew from, in order
+        for (const auto &v : distributions::scores_log()) {
+            for (float x : v) std::fprintf(stderr, "%.9g ", x);
+            std::fprintf(stderr, "\n");
+        }
     std::printf("{\"topology\": [%.9g, %.9g], \"kinds\": [", cross_cat.topology.alpha, cross_cat.topology.d);
     for (int k = 0; k < K; ++k) std::printf("%s[%.9g, %.9g]", k ? ", " : "", cross_cat.kinds[k].model.clustering.alpha, cross_cat.kinds[k].model.clustering.d);
     std::printf("], \"features\": [");

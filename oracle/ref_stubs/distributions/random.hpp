@@ -75,11 +75,17 @@ inline size_t sample_from_scores_overwrite(rng_t &rng, VectorFloat &scores) {
     if (draw_from_uniforms()) {
         // the library's published algorithm (random.hpp / special.hpp of 2.0.28): subtract the maximum, exponentiate in
         // place, walk the inverse CDF with one uniform -- here the generator's next scripted uniform
-        float max_score = scores[0], total = 0;
+#ifdef LB_STUB_DOUBLE_SAMPLER                               // diagnosis only: is a disagreement float32 rounding at a CDF boundary?
+        typedef double real_t;
+#else
+        typedef float real_t;
+#endif
+        real_t max_score = scores[0], total = 0;
         for (float s : scores) if (s > max_score) max_score = s;
-        for (float &s : scores) total += s = std::exp(s - max_score);
-        float t = total * (float)rng.next();
-        for (size_t i = 0; i < scores.size(); ++i) { t -= scores[i]; if (t < 0) return i; }
+        std::vector<real_t> likelihoods(scores.size());
+        for (size_t i = 0; i < scores.size(); ++i) total += likelihoods[i] = std::exp((real_t)scores[i] - max_score);
+        real_t t = total * (real_t)rng.next();
+        for (size_t i = 0; i < scores.size(); ++i) { t -= likelihoods[i]; if (t < 0) return i; }
         return scores.size() - 1;
     }
     if (pick_script_pos() >= pick_script().size()) std::abort();

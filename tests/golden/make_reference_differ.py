@@ -72,11 +72,7 @@ def no_tare(rng, R):
     return [("bb", 1), ("gp", 1), ("nich", 1)], table
 
 
-rng = np.random.default_rng(20)
-cases = [("mixed", ) + mixed(rng, 400), ("wide_booleans", ) + wide_booleans(rng, 60, 120), ("edges", ) + edges(),
-         ("no_tare", ) + no_tare(rng, 12)]
-out = []
-for name, types, table in cases:
+def run_case(name, types, table, verbose=True):
     sizes = [0, 0, 0]
     for t, n in types:
         sizes[0 if t == "bb" else 2 if t == "nich" else 1] += n
@@ -84,9 +80,17 @@ for name, types, table in cases:
     text += "\n".join(" ".join("-" if v is None else repr(v) for v in row) for row in table) + "\n"
     got = json.loads(subprocess.run([exe], input=text.encode(), stdout=subprocess.PIPE, check=True).stdout)
     assert len(got["rows"]) == len(table)
-    out.append(dict(name=name, types=types, table=table, tare=got["tare"], rows=got["rows"]))
-    print(name, "tare over", len(got["tare"]["features"]), "of", sum(sizes), "columns;",
-          sorted(set(r["pos"]["sparsity"] for r in got["rows"])), sorted(set(r["neg"]["sparsity"] for r in got["rows"])))
-json.dump({"source": "/root/reference/src/differ.cc + src/product_value.cc compiled by oracle/Makefile `ref` (g++ -O2) against "
-                     "oracle/ref_stubs_value, driven by oracle/ref_differ_main.cc",
-           "cases": out}, open(os.path.join(REPO, "tests", "golden", "reference_differ.json"), "w"), separators=(",", ":"))
+    if verbose:
+        print(name, "tare over", len(got["tare"]["features"]), "of", sum(sizes), "columns;",
+              sorted(set(r["pos"]["sparsity"] for r in got["rows"])), sorted(set(r["neg"]["sparsity"] for r in got["rows"])))
+    return dict(name=name, types=types, table=table, tare=got["tare"], rows=got["rows"])
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(20)
+    cases = [("mixed", ) + mixed(rng, 400), ("wide_booleans", ) + wide_booleans(rng, 60, 120), ("edges", ) + edges(),
+             ("no_tare", ) + no_tare(rng, 12)]
+    out = [run_case(*case) for case in cases]
+    json.dump({"source": "/root/reference/src/differ.cc + src/product_value.cc compiled by oracle/Makefile `ref` (g++ -O2) against "
+                         "oracle/ref_stubs_value, driven by oracle/ref_differ_main.cc",
+               "cases": out}, open(os.path.join(REPO, "tests", "golden", "reference_differ.json"), "w"), separators=(",", ":"))

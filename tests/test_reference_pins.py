@@ -99,7 +99,7 @@ def _cells(model, value):
     return feats, vals
 
 
-def differ_matches_the_reference(abi, tmp_path=None):
+def differ_matches_the_reference(abi, tmp_path=None, cases=None, min_rows=470):
     """Differ::add_rows -> get_tare and Differ::compress_rows of the reference (tests/golden/reference_differ.json, from
     src/differ.cc compiled unmodified) against the engine's differ_* entry points on the same tables: the tare row,
     and for every row the features and values of pos and the features of neg, bit for bit.  With tmp_path the rows are
@@ -109,7 +109,7 @@ def differ_matches_the_reference(abi, tmp_path=None):
     from loom_b200 import Engine
     from loom_b200.engine import RowBlock
     checked = 0
-    for case in _differ_cases():
+    for case in (_differ_cases() if cases is None else cases):
         model = _model_of(case["types"])
         table = case["table"]
         e = Engine(abi)
@@ -152,7 +152,7 @@ def differ_matches_the_reference(abi, tmp_path=None):
                     assert [int(b) for b in got.booleans] == want["booleans"] and list(got.counts) == want["counts"]
                     assert np.array_equal(np.asarray(list(got.reals), np.float32), np.asarray(want["reals"], np.float32))
                 assert len(m.diff.tares) == row["tares"]
-    assert checked >= 470
+    assert checked >= min_rows
 
 
 def test_oracle_differ_reproduces_the_reference(oracle_abi, tmp_path):
