@@ -62,11 +62,56 @@ def random_case(kind, seed):
     return dict(case, grids=gens["hyper"].GRIDS if rng.randint(0, 3) else gens["hyper"].ONE)
 
 
+def random_table(rng, types, n_rows):
+    """cells with a dominant value per column (so that tare rows exist), some columns rarely observed, some always"""
+    cols = []
+    for t, n in types:
+        for _ in range(n):
+            observed = rng.choice([0.2, 0.8, 1.0])
+            dominant = rng.choice([0.0, 0.6, 0.95])
+            if t == "bb":
+                mode, draw = int(rng.randint(0, 2)), lambda: int(rng.randint(0, 2))
+            elif t == "nich":
+                mode, draw = 0.5, lambda: float("%.9g" % np.float32(rng.standard_normal()))
+            elif t == "gp":
+                mode, draw = int(rng.choice([0, 3, 15, 16, 40])), lambda: int(rng.poisson(4.0))
+            else:
+                dim = int(t[2:]) if t.startswith("dd") else int(t[3:])
+                mode, draw = int(rng.randint(0, dim)), lambda dim=dim: int(rng.randint(0, dim))
+            cols.append([None if rng.uniform() > observed else (mode if rng.uniform() < dominant else draw()) for _ in range(n_rows)])
+    return [[c[r] for c in cols] for r in range(n_rows)]
+
+
+def fuzz_differ(n, first):
+    import tempfile
+    import pathlib
+    import test_reference_pins as T
+    from loom_b200 import _abi
+    gen = load("differ")
+    abi = _abi.Abi(os.path.join(REPO, "oracle", "libloom_oracle.so"), "lo_")
+    ok = 0
+    for seed in range(first, first + n):
+        rng = np.random.RandomState(seed)
+        types = random_types(rng, max_each=int(rng.choice([3, 12])))
+        types.sort(key=lambda tn: ({"bb": 0, "dd": 1, "dp": 2, "gp": 3, "ni": 4}[tn[0][:2]], int(tn[0][2:]) if tn[0].startswith("dd") else 0))
+        table = random_table(rng, types, int(rng.randint(1, 60)))
+        try:
+            case = gen.run_case("differ_%d" % seed, types, table, verbose=False)
+            with tempfile.TemporaryDirectory() as tmp:
+                T.differ_matches_the_reference(abi, pathlib.Path(tmp), cases=[case], min_rows=0)
+            ok += 1
+        except Exception:                                  # noqa: BLE001
+            print("FAIL differ", seed, types)
+            traceback.print_exc(limit=3)
+    print("differ %d / %d cases agree" % (ok, n))
+    return n - ok
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     devnull = open(os.devnull, "w")
-    failures = 0
+    failures = fuzz_differ(n, first)
     for kind, gen in gens.items():
         ok = 0
         for seed in range(first, first + n):
