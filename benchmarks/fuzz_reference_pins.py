@@ -3,11 +3,11 @@ kind_structure,hyper,product_mixture}.py -- i.e. the REFERENCE'S OWN code compil
 tables, kind structures, hypers and schedules nobody chose by hand -- without writing fixtures.  Runs only where
 /root/reference exists (the build container).  usage: fuzz_reference_pins.py N [first_seed]   -> one line per failure
 
-Last full run (300 cases per pin, seeds 10000..10299): cat_kernel 300 / 300, kind_structure 300 / 300, product_mixture
-300 / 300, hyper 299 / 300.  The one hyper case that differs (seed 10072, a DD-256 column = 256 grid draws) is a uniform
-1.3e-6 of probability mass away from a CDF boundary at coordinate 137, where the scores are ~ -80 and the reference sums
-them in float32 (ulp 7.6e-6): LB_REF_DUMP_SCORES=1 makes oracle/_ref/ref_hyper print every score vector it drew from, which
-is how that was checked; every coordinate before it agrees."""
+Full runs so far (300 cases per pin each; seeds 10000.. and 20000..): differ 300 / 300, cat_kernel 600 / 600,
+kind_structure 600 / 600, product_mixture 600 / 600, hyper 599 / 600.  The one hyper case that differs (seed 10072, a DD-256
+column = 256 grid draws) is a uniform 1.3e-6 of probability mass away from a CDF boundary at coordinate 137, where the scores
+are ~ -80 and the reference sums them in float32 (ulp 7.6e-6): LB_REF_DUMP_SCORES=1 makes oracle/_ref/ref_hyper print every
+score vector it drew from, which is how that was checked; every coordinate before it agrees."""
 import importlib.util
 import os
 import sys
