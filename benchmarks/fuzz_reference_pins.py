@@ -16,6 +16,7 @@ import traceback
 import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("PIN_STRIDE", "256")                 # room for the score vectors of the longer random trajectories
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
@@ -49,8 +50,9 @@ def random_case(kind, seed):
     f2k = rng.randint(0, K, F)
     f2k[:K] = np.arange(K)                                  # every kind has a feature
     rng.shuffle(f2k)
-    base = dict(name="%s_%d" % (kind, seed), types=types, n_rows=int(rng.randint(2, 45)), density=float(rng.choice([0.3, 0.7, 1.0])),
-                seed=int(seed), passes=int(rng.randint(0, 3)))
+    big = bool(os.environ.get("FUZZ_BIG"))                  # longer trajectories: more births, deaths and renumbering per case
+    base = dict(name="%s_%d" % (kind, seed), types=types, n_rows=int(rng.randint(2, 160 if big else 45)),
+                density=float(rng.choice([0.3, 0.7, 1.0])), seed=int(seed), passes=int(rng.randint(0, 5 if big else 3)))
     py = [float(np.float32(rng.choice([0.3, 1.0, 4.0]))), float(np.float32(rng.choice([0.0, 0.2, 0.6])))]
     if kind == "product_mixture":
         return dict(base, alpha=py[0], d=py[1], tare=bool(rng.randint(0, 2)) and any(t == "bb" for t, _ in types))

@@ -2,12 +2,15 @@
 single-kind engine swept by the cat kernel with its debug taps on -- the trajectory (packed group of every ADD and
 REMOVE) and the score vector of every ADD that the compiled reference ProductMixture was driven with / must agree
 with (oracle/ref_product_mixture_main.cc).  Test infrastructure."""
+import os
+
 import numpy as np
 
 from loom_b200 import Engine, synth, sweep_actions
 from loom_b200.engine import Model, RowBlock
 
-STRIDE = 64          # score slots per ADD in the debug buffer; the cases stay below it
+STRIDE = int(os.environ.get("PIN_STRIDE", 64))     # score slots per ADD in the debug buffer; the committed cases stay below 64,
+                                                  # the fuzzer's longer trajectories ask for more
 
 
 def build(case):
