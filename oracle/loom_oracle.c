@@ -116,7 +116,10 @@ static void feature_refresh(engine_t *e, kind_t *k, int j, int g, int64_t raw) {
         break;
     }
     case LB_GP: {
-        double a = s->hp[0] + in[st], b = s->hp[1] + in[0];
+        /* (double) first: float + uint32 is a FLOAT sum in C, and an a rounded to float32 here against the exact a of the
+         * scoring loop's lgamma(a + x) left an error of psi(a) * ulp(a) / 2 in every score of a large group whenever alpha
+         * is not an integer (found by benchmarks/fuzz_reference_pins.py against the compiled reference) */
+        double a = (double)s->hp[0] + in[st], b = (double)s->hp[1] + in[0];
         c[0] = -lgamma(a) + a * log(b / (b + 1.0));
         c[st] = -log(1.0 + b);
         break;
