@@ -7,7 +7,10 @@ Full runs so far (300 cases per pin each; seeds 10000.. and 20000..): differ 300
 kind_structure 600 / 600, product_mixture 600 / 600, hyper 599 / 600.  The one hyper case that differs (seed 10072, a DD-256
 column = 256 grid draws) is a uniform 1.3e-6 of probability mass away from a CDF boundary at coordinate 137, where the scores
 are ~ -80 and the reference sums them in float32 (ulp 7.6e-6): LB_REF_DUMP_SCORES=1 makes oracle/_ref/ref_hyper print every
-score vector it drew from, which is how that was checked; every coordinate before it agrees."""
+score vector it drew from, which is how that was checked; every coordinate before it agrees.
+FUZZ_BIG=1 (120 cases per pin, seeds 30000..): 14 cat_kernel / kind_structure cases disagreed at 2e-5 -- all with a
+Gamma-Poisson column in a large group -- which was a float32 promotion bug in the ORACLE's score cache (loom_oracle.c,
+feature_refresh); with it fixed all 600 agree."""
 import importlib.util
 import os
 import sys
