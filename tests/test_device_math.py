@@ -1,0 +1,113 @@
+"""The device's score arithmetic on the CPU suite: loom_b200/csrc/lb_common.cuh (lb_refresh_row + lb_score_cell, the
+float32 formulas k_cat_sweep* and k_score_rows run) compiled for the host (tests/cpp/device_math_host.cc through
+tests/cpp/cuda_shim/) against the float64 oracle's per-feature closed forms, for RANDOM hyperparameters and group sizes
+from empty to 10^6 rows.  The GPU parity tests visit the default hypers (alpha = 2, 0.5, ...) almost exclusively; after
+hyper inference the hypers are arbitrary grid values, which is where a float32 formula loses digits first (the oracle's
+own Gamma-Poisson cache had such a loss: see DESIGN.md section 2).  Host libm is not CUDA's, so this is an accuracy
+bound on the formulas, not a bit-level check."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from loom_b200.engine import FeatureSpec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+TOL = 1e-5                      # the score tolerance of the GPU parity tests (tests/test_cuda_cat.py SCORE_TOL)
+
+
+@pytest.fixture(scope="module")
+def device_math(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("device_math") / "device_math_host")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-I", os.path.join(HERE, "cpp", "cuda_shim"), "-o", exe,
+                           os.path.join(HERE, "cpp", "device_math_host.cc")])
+    return exe
+
+
+def _cases(rng, n):
+    """(type, dim, hp[4], aux, ints, flts, raw): sufficient statistics of ONE group of `size` rows"""
+    out = []
+    for _ in range(n):
+        t = int(rng.integers(0, 5))
+        size = int(rng.choice([0, 1, 3, 40, 1000, 30000, 10 ** 6]))
+        hp, aux, ints, flts, dim = [0.0] * 4, [], [], [], 0
+        if t == 0:
+            hp[:2] = 10 ** rng.uniform(-1, 1, 2)
+            heads = int(rng.binomial(size, rng.uniform(0.01, 0.99))) if size else 0
+            ints, raw = [heads, size - heads], int(rng.integers(0, 2))
+        elif t in (1, 2):
+            dim = int(rng.choice([2, 5, 16, 256]))
+            if t == 1:
+                aux = (10 ** rng.uniform(-1, 1, dim)).tolist()
+            else:
+                hp[:3] = [10 ** rng.uniform(-1, 2), 10 ** rng.uniform(-1, 1), 0.05]
+                b = rng.dirichlet(np.ones(dim)) * 0.95
+                aux = np.maximum(b, 1e-4).tolist()
+            counts = rng.multinomial(size, rng.dirichlet(np.ones(dim) * 0.3)) if size else np.zeros(dim, int)
+            ints, raw = counts.tolist() + [size], int(rng.integers(0, dim))
+        elif t == 3:
+            hp[:2] = [10 ** rng.uniform(-1, 2), 10 ** rng.uniform(-2, 1)]
+            lam = 10 ** rng.uniform(-1, 2)
+            ints = [size, int(rng.poisson(lam * size)) if size else 0]
+            flts, raw = [0.0], int(rng.poisson(lam) if rng.uniform() < 0.8 else rng.poisson(5 * lam + 3))
+        else:
+            hp[:4] = [rng.uniform(-3, 3), 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(-1, 1), 10 ** rng.uniform(0, 1.5)]
+            mean, sd = rng.uniform(-50, 50), 10 ** rng.uniform(-1, 1.5)
+            ints, flts = [size], ([mean, sd * sd * size] if size else [0.0, 0.0])
+            raw = int(np.float32(mean + sd * rng.standard_normal() * rng.choice([1, 4])).view(np.uint32))
+        hp = [float(np.float32(h)) for h in hp]
+        aux = [float(np.float32(a)) for a in aux]
+        out.append((t, dim, hp, aux, ints, flts, raw))
+    return out
+
+
+def test_device_score_formulas_against_the_float64_oracle(device_math):
+    lib = C.CDLL(os.path.join(REPO, "oracle", "libloom_oracle.so"))
+    lib.lo_feature_score_value.restype = C.c_double
+    rng = np.random.default_rng(7)
+    cases = _cases(rng, 4000)
+    text = ""
+    for t, dim, hp, aux, ints, flts, raw in cases:
+        text += "%d %d %s %d %s %d %s %d %s %d\n" % (t, dim, " ".join("%.9g" % h for h in hp), len(aux), " ".join("%.9g" % a for a in aux),
+                                                  len(ints), " ".join(str(i) for i in ints), len(flts), " ".join("%.17g" % x for x in flts), raw)
+    got = np.array(subprocess.run([device_math], input=text.encode(), stdout=subprocess.PIPE, check=True).stdout.split(), np.float64)
+    assert len(got) == len(cases)
+    # err = |device - oracle| / max(1, |oracle|), the metric of the GPU parity tests, per regime
+    envelope = {}
+    for (t, dim, hp, aux, ints, flts, raw), mine in zip(cases, got):
+        spec = FeatureSpec()
+        spec.type, spec.dim, spec.aux_off = t, dim, 0
+        for j in range(4):
+            spec.hp[j] = hp[j]
+        a = (C.c_float * max(len(aux), 1))(*aux)
+        i = (C.c_uint32 * max(len(ints), 1))(*ints)
+        f = (C.c_double * max(len(flts), 2))(*flts)
+        want = lib.lo_feature_score_value(C.byref(spec), a, i, f, C.c_uint32(raw))
+        err = abs(mine - want) / max(1.0, abs(want))
+        size = ints[0] + ints[1] if t == 0 else ints[-1] if t in (1, 2) else ints[0]
+        if t == 3:
+            regime = "gp, value <= 20" if raw <= 20 and ints[1] < 2 ** 24 else "gp, value > 20"
+        elif t == 4:
+            regime = "nich, group <= 1000 rows" if size <= 1000 else "nich, group > 1000 rows"
+        else:
+            regime = ["bb", "dd", "dpd"][t]
+        if err > envelope.get(regime, 0.0) and os.environ.get("LB_DEVICE_MATH_VERBOSE"):
+            print(regime, "%.2e" % err, mine, want, hp[:2], ints, raw)
+        envelope[regime] = max(envelope.get(regime, 0.0), err)
+    print({k: "%.1e" % v for k, v in sorted(envelope.items())})
+    # Bernoulli / categorical tables: one log per entry, nothing cancels
+    for regime in ("bb", "dd", "dpd"):
+        assert envelope[regime] <= 2e-6, (regime, envelope[regime])
+    # the regimes the parity tests live in hold the 1e-5 of the north star ...
+    assert envelope["gp, value <= 20"] <= TOL, envelope
+    assert envelope["nich, group <= 1000 rows"] <= TOL, envelope
+    # ... and the two known envelopes beyond it: a Gamma-Poisson score is a sum of float32 terms of
+    # size x ln(a + x) (hundreds for counts in the hundreds) that cancel to O(1), and a group whose values sum past 2^24
+    # no longer has an exact float32 shape ("value > 20" below also holds those); a Student-t score of a 10^6-row group
+    # multiplies (nu' + 1) / 2 ~ 5e5 into a float32 log1p; both stay an order of magnitude inside the reference's own
+    # float32 tolerance (LOOM_ASSERT_CLOSE 1e-4, src/kind_proposer.cc:34-35)
+    assert envelope["gp, value > 20"] <= 1e-4, envelope
+    assert envelope["nich, group > 1000 rows"] <= 4e-5, envelope
