@@ -101,13 +101,14 @@ def test_device_score_formulas_against_the_float64_oracle(device_math):
     # Bernoulli / categorical tables: one log per entry, nothing cancels
     for regime in ("bb", "dd", "dpd"):
         assert envelope[regime] <= 2e-6, (regime, envelope[regime])
-    # the regimes the parity tests live in hold the 1e-5 of the north star ...
+    # the Student-t predictive holds 1e-5 everywhere since the posterior mean is formed with a float64 division (a float32
+    # reciprocal there cost 1.7e-5 at 10^6-row groups whose |mean| is hundreds of sigmas: found with this test)
+    assert envelope["nich, group <= 1000 rows"] <= 3e-6, envelope
+    assert envelope["nich, group > 1000 rows"] <= 3e-6, envelope
+    # Gamma-Poisson: the regime the parity tests live in holds the 1e-5 of the north star ...
     assert envelope["gp, value <= 20"] <= TOL, envelope
-    assert envelope["nich, group <= 1000 rows"] <= TOL, envelope
-    # ... and the two known envelopes beyond it: a Gamma-Poisson score is a sum of float32 terms of
-    # size x ln(a + x) (hundreds for counts in the hundreds) that cancel to O(1), and a group whose values sum past 2^24
-    # no longer has an exact float32 shape ("value > 20" below also holds those); a Student-t score of a 10^6-row group
-    # multiplies (nu' + 1) / 2 ~ 5e5 into a float32 log1p; both stay an order of magnitude inside the reference's own
-    # float32 tolerance (LOOM_ASSERT_CLOSE 1e-4, src/kind_proposer.cc:34-35)
+    # ... and the known envelope beyond it: the score is a sum of float32 terms of size x ln(a + x)
+    # (hundreds for counts in the hundreds) that cancel to O(1), and a group whose values sum past 2^24 no longer has an
+    # exact float32 shape ("value > 20" also holds those); it stays inside the reference's own float32 tolerance
+    # (LOOM_ASSERT_CLOSE 1e-4, src/kind_proposer.cc:34-35)
     assert envelope["gp, value > 20"] <= 1e-4, envelope
-    assert envelope["nich, group > 1000 rows"] <= 4e-5, envelope
