@@ -365,6 +365,21 @@ __device__ __forceinline__ void lb_update_cell_x(const FeatDev &f, const float *
     }
 }
 
+// Gamma-Poisson predictive of a count x > 8 in a group with a = alpha + sum >= 8, b1 = inv_beta + count + 1, float32.
+// The textbook sum lgamma(a + x) - lgamma(a) - lgamma(x + 1) + a log(b/(b+1)) - x log(1+b) is four terms of size
+// x ln(a + x) -- thousands for counts in the hundreds -- that cancel to O(1): 5e-5 of error in float32.  With Stirling's
+// series for all three lgammas the large parts combine before they are evaluated (Loader's saddle-point idea):
+//   (a - 1/2) log1p(x/a) + a log1p(-1/b1)  =  a log1p(x/a - (1 + x/a)/b1) - log1p(x/a)/2      ~ (x - mean) + ...
+//   x log(a + x) - x log x - x log b1       =  x log1p((a + x - b1 x) / (b1 x))                ~ (mean - x) + ...
+// and what is left is - log(2 pi x)/2 and the three 1/(12 z) tails.  Every term is O(|x - mean|) or smaller.
+__device__ __forceinline__ float lb_gp_score_stirling(float a, float b1, float x) {
+    const float xa = x / a;
+    const float t1 = a * log1pf(xa - (1.f + xa) / b1) - 0.5f * log1pf(xa);
+    const float bx = b1 * x, r = (a + x) / bx;           // r ~ mean / x
+    const float t2 = x * (fabsf(r - 1.f) < 0.5f ? log1pf(((a - bx) + x) / bx) : logf(r));   // near the mean: the difference first
+    return t1 + t2 - 0.5f * logf(6.28318531f * x) + (lb_stirling_corr(a + x) - lb_stirling_corr(a)) - lb_stirling_corr(x);
+}
+
 // log posterior-predictive of one cell for one group from the cached scorer.
 __device__ __forceinline__ float lb_score_cell(const FeatDev &f, const uint32_t *in, const float *c,
                                                int st, uint32_t raw, float cell_const) {
@@ -376,6 +391,7 @@ __device__ __forceinline__ float lb_score_cell(const FeatDev &f, const uint32_t 
         return c[(size_t)raw * st] - c[(size_t)f.dim * st];
     case LB_GP: {
         const float a = f.hp[0] + (float)in[st];
+        if (raw > 8u && a >= 8.f) return lb_gp_score_stirling(a, f.hp[1] + (float)in[0] + 1.f, (float)raw);
         return lb_lgamma_diff_int(a, raw) - cell_const + c[0] + (float)raw * c[st];
     }
     case LB_NICH: {
