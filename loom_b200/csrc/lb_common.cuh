@@ -372,6 +372,8 @@ __device__ __forceinline__ void lb_update_cell_x(const FeatDev &f, const float *
 //   (a - 1/2) log1p(x/a) + a log1p(-1/b1)  =  a log1p(x/a - (1 + x/a)/b1) - log1p(x/a)/2      ~ (x - mean) + ...
 //   x log(a + x) - x log x - x log b1       =  x log1p((a + x - b1 x) / (b1 x))                ~ (mean - x) + ...
 // and what is left is - log(2 pi x)/2 and the three 1/(12 z) tails.  Every term is O(|x - mean|) or smaller.
+// (Used by lb_score_cell: K1, K1d and the sweep's one-column patch.  The sweeps' gather loops still inline the textbook
+// sum: this form reads the group's count as well as its sum, one more load per cell there -- DESIGN.md section 5.)
 __device__ __forceinline__ float lb_gp_score_stirling(float a, float b1, float x) {
     const float xa = x / a;
     const float t1 = a * log1pf(xa - (1.f + xa) / b1) - 0.5f * log1pf(xa);
