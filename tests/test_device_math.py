@@ -139,3 +139,58 @@ def test_gamma_poisson_score_over_extreme_regimes(device_math):
         want = lib.lo_feature_score_value(C.byref(spec), (C.c_float * 1)(0), (C.c_uint32 * 2)(size, total), (C.c_double * 2)(0, 0), C.c_uint32(x))
         errs[j] = abs(mine - want) / max(1.0, abs(want))
     assert np.quantile(errs, 0.99) <= 1e-5 and errs.max() <= 6e-5, (np.quantile(errs, [0.5, 0.99, 0.999]), errs.max())
+
+
+@pytest.fixture(scope="module")
+def device_marginal(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("device_marginal") / "device_marginal_host")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-I", os.path.join(HERE, "cpp", "cuda_shim"), "-o", exe,
+                           os.path.join(HERE, "cpp", "device_marginal_host.cc")])
+    return exe
+
+
+def test_device_marginal_formulas_against_the_float64_oracle(device_marginal):
+    """lb_marginal.cuh (lb_marginal_group: K5's scalar path and K7; lb_lgamma_rise: K5's Dirichlet table walk) against
+    the oracle's om_score_data over the same random (hypers, group) pairs as the score test, per group.  What matters
+    downstream is DIFFERENCES of sums of these over the groups of a kind (a feature's score under one kind against
+    another, one grid point against the next), so the bound is relative to the marginal itself, as in the GPU tests."""
+    lib = C.CDLL(os.path.join(REPO, "oracle", "libloom_oracle.so"))
+    lib.lo_feature_score_data.restype = C.c_double
+    rng = np.random.default_rng(11)
+    cases = [c for c in _cases(rng, 4000)]
+    text = ""
+    for t, dim, hp, aux, ints, flts, raw in cases:
+        if t == 3:                                          # log_prod consistent with (count, sum): count cells of the mean value
+            flts = [float(ints[0]) * float(np.log(np.arange(1, max(ints[1] // max(ints[0], 1), 1) + 1)).sum())]
+        text += "%d %d %s %d %s %d %s %d %s\n" % (t, dim, " ".join("%.9g" % h for h in hp), len(aux), " ".join("%.9g" % a for a in aux),
+                                               len(ints), " ".join(str(i) for i in ints), len(flts), " ".join("%.17g" % x for x in flts))
+    got = np.array(subprocess.run([device_marginal], input=text.encode(), stdout=subprocess.PIPE, check=True).stdout.split(),
+                   np.float64).reshape(-1, 2)
+    assert len(got) == len(cases) and np.isfinite(got).all()
+    # A log marginal of an n-row group is a few lgamma differences of size n ln n that largely cancel; the device takes each
+    # difference in float32 (lb_lgamma_diff) and combines them in float64, so its ABSOLUTE error is a float32 ulp of n ln n
+    # -- 0.8 nat at 10^6 rows, the same as the reference's own float32 arithmetic -- however small the marginal itself is.
+    # Bound: 1e-5 of the marginal plus 2e-7 n ln(n + 3) (n = rows, or the sum of the values for Gamma-Poisson).
+    envelope, slack = {}, {}
+    for (t, dim, hp, aux, ints, flts, raw), (group, table) in zip(cases, got):
+        if t == 3:
+            flts = [float(ints[0]) * float(np.log(np.arange(1, max(ints[1] // max(ints[0], 1), 1) + 1)).sum())]
+        spec = FeatureSpec()
+        spec.type, spec.dim, spec.aux_off = t, dim, 0
+        for j in range(4):
+            spec.hp[j] = hp[j]
+        a = (C.c_float * max(len(aux), 1))(*aux)
+        i = (C.c_uint32 * max(len(ints), 1))(*ints)
+        f = (C.c_double * max(len(flts), 2))(*flts)
+        want = lib.lo_feature_score_data(C.byref(spec), a, i, f)
+        n = ints[0] + ints[1] if t == 0 else ints[-1] if t in (1, 2) else ints[0]
+        big = max(n, ints[1]) if t == 3 else n                  # Gamma-Poisson: the lgamma difference runs over the SUM of the values
+        allowed = TOL * max(1.0, abs(want)) + 2e-7 * big * np.log(big + 3.0)
+        name = ["bb", "dd", "dpd", "gp", "nich"][t]
+        for label, mine in ((name, group),) + (((name + " (table walk)", table),) if t in (1, 2) else ()):
+            envelope[label] = max(envelope.get(label, 0.0), abs(mine - want))
+            slack[label] = max(slack.get(label, 0.0), abs(mine - want) / allowed)
+    print("largest absolute error (nats):", {k: "%.2g" % v for k, v in sorted(envelope.items())})
+    print("largest error / allowed:", {k: "%.2f" % v for k, v in sorted(slack.items())})
+    for label, ratio in slack.items():
+        assert ratio <= 1.0, (label, slack, envelope)
